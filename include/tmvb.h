@@ -1,0 +1,116 @@
+/*
+ * tmvb.h -- C ABI of libtmvb.so, the sm_100a CAVI engine that stands in for the OpenCL layer of
+ * ericproffitt/TopicModelsVB.jl (src/gpuLDA.jl, src/gpuCTM.jl, src/gpuCTPF.jl and the device
+ * plumbing update_buffer!/update_host!/@buffer/@host in src/modelutils.jl:369-570, src/macros.jl:60-104).
+ *
+ * The reference has no FFI: its seam is the set of Julia methods that touch `cl.*`.  Every entry
+ * point below names the reference call site(s) it replaces (file:line under the reference root).
+ * INTEGRATION.md shows the Julia `ccall` binding; topicmodelsvb.jl_b200/_lib.py is the ctypes one.
+ *
+ * Conventions
+ *  - plain pointers and sizes only; the caller owns every host array for the duration of the call.
+ *  - dense host matrices are Julia column-major Float32: beta[K*j + i] = topic i of term j (K x V),
+ *    Elogtheta[K*d + i] (K x M), ... exactly what update_buffer! uploads (modelutils.jl:390-392).
+ *  - corpus indices are Int64, 0-based, flattened (modelutils.jl:371-380).
+ *  - every function returns 0 on success, <0 for an invalid argument, >0 for a CUDA error code;
+ *    tmvb_last_error() returns a thread-local message.  No exception crosses the ABI.
+ *  - calls on one handle must be serialised by the caller.  Work is enqueued on the handle's
+ *    stream; functions that return host data synchronise that stream first.
+ *  - one handle owns one shard of documents on one device.  Multi-GPU runs use one handle per
+ *    GPU and sum the buffers exposed by tmvb_*_reduce_buffers() between estep and mstep.
+ *  - there is NO CPU fallback: without a CUDA device every create() fails.
+ */
+#ifndef TMVB_H
+#define TMVB_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TMVB_VERSION 100
+
+typedef struct tmvb_lda_s *tmvb_lda_t;
+
+/* Timings (ms, CUDA events on the handle's stream) and counters of the most recent calls. */
+typedef struct tmvb_stats {
+    double estep_ms;        /* last tmvb_*_estep                                          */
+    double mstep_ms;        /* last tmvb_*_mstep                                          */
+    int64_t sweeps;         /* total inner sweeps of the last estep (sum over documents)  */
+    int64_t kernel_launches;/* kernels launched by this handle since creation             */
+    int64_t h2d_bytes;      /* host->device bytes copied by this handle since creation    */
+    int64_t d2h_bytes;      /* device->host bytes copied by this handle since creation    */
+} tmvb_stats;
+
+int tmvb_version(void);
+const char *tmvb_last_error(void);
+/* number of visible CUDA devices (0 and an error code when there is none) */
+int tmvb_device_count(int *count);
+
+/* ------------------------------------------------------------------ LDA ------------------ */
+
+/* gpuLDA(corp, K) device side (gpuLDA.jl:64-80: cl.create_compute_context + 7 cl.Program builds).
+ * M, V may be 0 (the `gpuLDA(Corpus(), 1)` construction of macros.jl:114).  `device` < 0 picks the
+ * current device; `stream` may be NULL (a private stream is created) or a caller-owned cudaStream_t. */
+int tmvb_lda_create(tmvb_lda_t *h, int64_t K, int64_t M, int64_t V, int device, void *stream);
+int tmvb_lda_destroy(tmvb_lda_t h); /* idempotent on NULL */
+
+/* update_buffer!(model::gpuLDA), corpus half (modelutils.jl:371-388).  N_cumsum[M+1], terms[sumN]
+ * (0-based), counts[sumN].  The inverted index (J_cumsum / terms_sortperm) is not needed.
+ * Pointers may be pinned or pageable host memory. */
+int tmvb_lda_set_corpus(tmvb_lda_t h, const int64_t *N_cumsum, const int64_t *terms, const int64_t *counts);
+
+/* update_buffer!(model::gpuLDA), parameter half (modelutils.jl:390-392) and `@buffer model.alpha`
+ * (macros.jl:64).  Any pointer may be NULL (left unchanged).  gamma is optional (the reference
+ * allocates it uninitialised, modelutils.jl:395).  Also resets beta_old/Elogtheta_old := beta/Elogtheta
+ * as the constructors do (LDA.jl:36,39). */
+int tmvb_lda_upload(tmvb_lda_t h, const float *alpha, const float *beta, const float *Elogtheta, const float *gamma);
+int tmvb_lda_set_alpha(tmvb_lda_t h, const float *alpha);
+
+/* The whole inner loop `for v in 1:viter` (gpuLDA.jl:356-364: update_phi!/update_gamma!/
+ * update_Elogtheta!) with the CPU model's per-document stopping rule (LDA.jl:170-178), followed by
+ * the scatter half of update_beta! (gpuLDA.jl:156-177 / LDA.jl:129-132) into the K x V statistics.
+ * want_elbo != 0 also accumulates the per-document ELBO terms.  Asynchronous. */
+int tmvb_lda_estep(tmvb_lda_t h, int viter, float vtol, int want_elbo);
+
+/* Device buffers that a multi-GPU driver must sum over ranks between estep and mstep:
+ * stats = float[n_stats] (K_ld x V padded statistics), small = double[n_small]
+ * (sum_d Elogtheta_d, ELBO partials, sweep counter). */
+int tmvb_lda_reduce_buffers(tmvb_lda_t h, void **stats, int64_t *n_stats, void **small, int64_t *n_small);
+
+/* normalize_beta (gpuLDA.jl:179-204 / LDA.jl:121-125): beta_old <- beta; beta = stats ./ rowsum;
+ * stats <- 0.  M_total is the corpus-wide document count (== M unless sharded).  Asynchronous. */
+int tmvb_lda_mstep(tmvb_lda_t h);
+
+/* `@host model.Elogtheta_sum_buffer` (macros.jl:79, gpuLDA.jl:133); fp64. */
+int tmvb_lda_get_elogtheta_sum(tmvb_lda_t h, double *out);
+
+/* update_alpha! (LDA.jl:97-118 / gpuLDA.jl:132-154) done inside the library in fp64 on the host
+ * from the reduced Elogtheta_sum, then written to the device.  M_total as above.  alpha_out[K] may be NULL. */
+int tmvb_lda_update_alpha(tmvb_lda_t h, int64_t M_total, int niter, double ntol, float *alpha_out);
+
+/* update_elbo! (gpuLDA.jl:121-128 via check_elbo!, modelutils.jl:574-585) without the K x sumN phi
+ * transfer.  mode 0: assemble from the partials accumulated by the last estep(want_elbo=1)+mstep
+ * (needs the current alpha; M_total as above).  mode 1: full recomputation from device state with
+ * the CPU model's lagged-phi semantics (LDA.jl:83-93); used for the initial ELBO.  For sharded runs
+ * mode 1 returns this shard's document terms plus the global terms on every rank, so the caller
+ * sums `*elbo_docs` over ranks and adds `*elbo_global` once. */
+int tmvb_lda_elbo(tmvb_lda_t h, int mode, int64_t M_total, double *elbo_docs, double *elbo_global);
+
+/* update_host!(model::gpuLDA) (modelutils.jl:501-514): any pointer may be NULL. */
+int tmvb_lda_download(tmvb_lda_t h, float *alpha, float *beta, float *Elogtheta, float *gamma);
+/* the lagged copies the CPU struct keeps (LDA.jl:17,20): beta_old, Elogtheta_old */
+int tmvb_lda_download_old(tmvb_lda_t h, float *beta_old, float *Elogtheta_old);
+/* phi of every document, K x sumN column-major, original token order (modelutils.jl:515-516) */
+int tmvb_lda_materialize_phi(tmvb_lda_t h, float *phi);
+
+int tmvb_lda_sync(tmvb_lda_t h);
+int tmvb_lda_get_stats(tmvb_lda_t h, tmvb_stats *out);
+/* padded leading dimension of the device K-vectors (rows of beta/stats are K_ld floats) */
+int tmvb_lda_kld(tmvb_lda_t h, int64_t *K_ld);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TMVB_H */

@@ -1,0 +1,138 @@
+"""Independent NumPy/SciPy restatement of the reference's CPU models -- TEST INFRASTRUCTURE ONLY.
+
+Second opinion for the C oracle (``*_oracle.c``): written straight from the Julia source with
+scipy.special for psi / psi' / ln Gamma, per-document Python loops (small cases only).
+The two restatements must agree to <= 1e-12 relative (tests/test_oracle_*.py).
+
+Arrays are (V, K) / (M, K) C-order views of the reference's column-major K x V / K x M.
+"""
+from __future__ import annotations
+
+import numpy as np
+from scipy.special import digamma, gammaln, polygamma
+
+EPSILON = 2.0 ** -99  # utils.jl:3  eps(1e-14)
+
+
+def _finite(x):  # utils.jl:107
+    return np.sign(x) * np.minimum(np.abs(x), np.finfo(np.float64).max)
+
+
+class LDATwin:
+    """src/LDA.jl, line for line."""
+
+    def __init__(self, N_cumsum, terms, counts, K, V, beta, alpha=None):
+        self.K, self.V = K, V
+        self.M = len(N_cumsum) - 1
+        self.off = np.asarray(N_cumsum, dtype=np.int64)
+        self.terms = np.asarray(terms, dtype=np.int64)
+        self.counts = np.asarray(counts, dtype=np.float64)
+        self.alpha = np.ones(K) if alpha is None else np.array(alpha, dtype=np.float64)
+        self.beta = np.array(beta, dtype=np.float64).reshape(V, K)
+        self.beta_old = self.beta.copy()
+        self.beta_temp = np.zeros((V, K))
+        self.Elogtheta = np.full((self.M, K), -np.euler_gamma - digamma(K))  # LDA.jl:38
+        self.Elogtheta_old = self.Elogtheta.copy()
+        self.gamma = np.ones((self.M, K))
+        self.phi = None
+        self.elbo = 0.0
+
+    def _doc(self, d):
+        s = slice(self.off[d], self.off[d + 1])
+        return self.terms[s], self.counts[s]
+
+    # LDA.jl:150-154
+    def update_phi(self, d):
+        terms, _ = self._doc(d)
+        phi = EPSILON + self.beta[terms] * np.exp(self.Elogtheta[d])[None, :]
+        self.phi = phi / phi.sum(axis=1, keepdims=True)
+
+    # LDA.jl:143-146
+    def update_gamma(self, d):
+        _, counts = self._doc(d)
+        self.gamma[d] = EPSILON + (self.alpha + counts @ self.phi)
+
+    # LDA.jl:136-139
+    def update_Elogtheta(self, d):
+        self.Elogtheta_old[d] = self.Elogtheta[d]
+        self.Elogtheta[d] = digamma(self.gamma[d]) - digamma(self.gamma[d].sum())
+
+    # LDA.jl:129-132
+    def update_beta_doc(self, d):
+        terms, counts = self._doc(d)
+        self.beta_temp[terms] += self.phi * counts[:, None]
+
+    # LDA.jl:121-125
+    def update_beta(self):
+        self.beta_old = self.beta
+        self.beta = self.beta_temp / self.beta_temp.sum(axis=0, keepdims=True)
+        self.beta_temp = np.zeros((self.V, self.K))
+
+    # LDA.jl:97-118
+    def update_alpha(self, niter, ntol):
+        Elogtheta_sum = self.Elogtheta.sum(axis=0)
+        K, M = self.K, self.M
+        nu = float(K)
+        for _ in range(niter):
+            rho = 1.0
+            a = self.alpha
+            grad = nu / a + M * (digamma(a.sum()) - digamma(a)) + Elogtheta_sum
+            h_inv = -1.0 / (M * polygamma(1, a) + nu / a**2)
+            p = (grad - np.dot(grad, h_inv) / (1.0 / (M * polygamma(1, a.sum())) + h_inv.sum())) * h_inv
+            while np.min(a - rho * p) < 0:
+                rho *= 0.5
+            self.alpha = np.sign(a) * np.minimum(np.abs(a - rho * p), np.finfo(np.float64).max)
+            if (rho * np.linalg.norm(grad) < ntol) and (nu / K < ntol):
+                break
+            nu *= 0.5
+        self.alpha = self.alpha + EPSILON
+
+    # LDA.jl:50-93
+    def update_elbo(self):
+        elbo = 0.0
+        a = self.alpha
+        for d in range(self.M):
+            terms, counts = self._doc(d)
+            phi = EPSILON + self.beta_old[terms] * np.exp(self.Elogtheta_old[d])[None, :]
+            phi = phi / phi.sum(axis=1, keepdims=True)
+            Et, g = self.Elogtheta[d], self.gamma[d]
+            Elogptheta = _finite(gammaln(a.sum())) - _finite(gammaln(a).sum()) + np.dot(a - 1, Et)
+            Elogpz = np.dot(counts @ phi, Et)
+            Elogpw = np.sum((phi * np.log(self.beta[terms] + EPSILON)) * counts[:, None])
+            if self.K == 1:
+                ent_dir = 0.0
+            else:  # utils.jl:163-180
+                ent_dir = (gammaln(g).sum() - gammaln(g.sum()) + (g.sum() - self.K) * digamma(g.sum())
+                           - np.dot(g - 1.0, digamma(g)))
+            with np.errstate(divide="ignore", invalid="ignore"):
+                plogp = np.where(phi > 0, phi * np.log(phi), 0.0)
+            ent_z = -(plogp.sum(axis=1) * counts).sum()
+            elbo += Elogptheta + Elogpz + Elogpw + ent_dir + ent_z
+        self.elbo = elbo
+        return elbo
+
+    # LDA.jl:161-191 (+ check_elbo!, modelutils.jl:574-585)
+    def train(self, iter=150, tol=1.0, niter=1000, ntol=None, viter=10, vtol=None, checkelbo=1):
+        ntol = 1.0 / self.K**2 if ntol is None else ntol
+        vtol = 1.0 / self.K**2 if vtol is None else vtol
+        trace = [np.nan] * (iter + 1)
+        if checkelbo <= iter:
+            trace[0] = self.update_elbo()
+        for k in range(1, iter + 1):
+            for d in range(self.M):
+                for _ in range(viter):
+                    self.update_phi(d)
+                    self.update_gamma(d)
+                    self.update_Elogtheta(d)
+                    if np.linalg.norm(self.Elogtheta[d] - self.Elogtheta_old[d]) < vtol:
+                        break
+                self.update_beta_doc(d)
+            self.update_beta()
+            self.update_alpha(niter, ntol)
+            if k % checkelbo == 0:
+                old = self.elbo
+                delta = self.update_elbo() - old
+                trace[k] = self.elbo
+                if delta < tol:
+                    break
+        return np.array(trace)

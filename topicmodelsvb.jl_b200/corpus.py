@@ -1,0 +1,128 @@
+"""Minimal host-side data model: the output contract of the reference's Corpus.jl that the device
+path consumes (Document.terms/counts/readers/ratings, 1-based keys; Corpus.jl:14-26,62-78).
+
+Only what ``update_buffer!`` (modelutils.jl:370-494) reads is mirrored here; corpus cleaning,
+vocab handling and text I/O stay with the reference package.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import List, Optional, Sequence
+
+import numpy as np
+
+from .synth import CSR
+
+
+class DocumentError(ValueError):
+    """Corpus.jl:30-34"""
+
+
+class CorpusError(ValueError):
+    """Corpus.jl:85-89"""
+
+
+def _ivec(x) -> np.ndarray:
+    return np.ascontiguousarray(np.asarray(x, dtype=np.int64).reshape(-1))
+
+
+@dataclass
+class Document:
+    """Document(;terms, counts, readers, ratings, title) -- keys are 1-based as in the reference."""
+
+    terms: np.ndarray
+    counts: Optional[np.ndarray] = None
+    readers: np.ndarray = field(default_factory=lambda: np.zeros(0, np.int64))
+    ratings: Optional[np.ndarray] = None
+    title: str = ""
+
+    def __post_init__(self):
+        self.terms = _ivec(self.terms)
+        self.counts = np.ones_like(self.terms) if self.counts is None else _ivec(self.counts)
+        self.readers = _ivec(self.readers)
+        self.ratings = np.ones_like(self.readers) if self.ratings is None else _ivec(self.ratings)
+        check_doc(self)
+
+    def __len__(self):
+        return len(self.terms)
+
+
+def check_doc(doc: Document) -> None:
+    """Corpus.jl:41-49"""
+    if not np.all(doc.terms > 0):
+        raise DocumentError("all terms must be positive integers.")
+    if not np.all(doc.counts > 0):
+        raise DocumentError("all counts must be positive integers.")
+    if len(doc.terms) != len(doc.counts):
+        raise DocumentError("terms and counts vectors must have the same length.")
+    if not np.all(doc.readers > 0):
+        raise DocumentError("all readers must be positive integers.")
+    if not np.all(doc.ratings > 0):
+        raise DocumentError("all ratings must be positive integers.")
+    if len(doc.readers) != len(doc.ratings):
+        raise DocumentError("readers and ratings vectors must have the same length.")
+
+
+class Corpus:
+    """Corpus(;docs, vocab, users).  ``vocab``/``users`` may be sequences of names or plain sizes."""
+
+    def __init__(self, docs: Sequence[Document] = (), vocab=None, users=None):
+        self.docs: List[Document] = list(docs)
+        self._flat: Optional[CSR] = None
+        if isinstance(vocab, (int, np.integer)):
+            self.V = int(vocab)
+        elif vocab is not None:
+            self.V = len(vocab)
+        else:
+            self.V = int(max([d.terms.max() for d in self.docs if len(d.terms)], default=0))
+        if isinstance(users, (int, np.integer)):
+            self.U = int(users)
+        elif users is not None:
+            self.U = len(users)
+        else:
+            self.U = int(max([d.readers.max() for d in self.docs if len(d.readers)], default=0))
+        check_corp(self)
+
+    @classmethod
+    def from_csr(cls, c: CSR) -> "Corpus":
+        """Wrap a flattened corpus without building per-document objects (large corpora)."""
+        self = cls.__new__(cls)
+        self.docs = None
+        self._flat = c
+        self.V, self.U = c.V, c.U
+        return self
+
+    def __len__(self):
+        return self._flat.M if self.docs is None else len(self.docs)
+
+    def size(self):
+        return len(self), self.V, self.U
+
+    def flat(self) -> CSR:
+        """The flattening of update_buffer! (modelutils.jl:371-380): 0-based Int64 CSR."""
+        if self._flat is not None:
+            return self._flat
+        M = len(self.docs)
+        N = np.array([len(d.terms) for d in self.docs], dtype=np.int64)
+        R = np.array([len(d.readers) for d in self.docs], dtype=np.int64)
+        cat = lambda xs: (np.concatenate(xs) if len(xs) else np.zeros(0, np.int64)).astype(np.int64)
+        self._flat = CSR(M, self.V, np.concatenate([[0], np.cumsum(N)]).astype(np.int64),
+                         cat([d.terms for d in self.docs]) - 1, cat([d.counts for d in self.docs]),
+                         self.U, np.concatenate([[0], np.cumsum(R)]).astype(np.int64),
+                         cat([d.readers for d in self.docs]) - 1, cat([d.ratings for d in self.docs]))
+        return self._flat
+
+
+def check_corp(corp: Corpus) -> None:
+    """Corpus.jl:111-122 (the parts that concern the flattened arrays)."""
+    if corp.docs is None:
+        return
+    for d, doc in enumerate(corp.docs):
+        try:
+            check_doc(doc)
+        except DocumentError:
+            raise CorpusError("document %d failed check." % (d + 1))
+        if len(doc.terms) and doc.terms.max() > corp.V:
+            raise CorpusError("documents contain term keys not found in corpus vocabulary (see fixcorp! function).")
+        if len(doc.readers) and doc.readers.max() > corp.U:
+            raise CorpusError("documents contain user keys not found in corpus users (see fixcorp! function).")

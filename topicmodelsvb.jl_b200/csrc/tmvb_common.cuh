@@ -1,0 +1,136 @@
+// tmvb_common.cuh -- shared host/device helpers for libtmvb (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+#include <vector>
+
+#include "../../include/tmvb.h"
+
+namespace tmvb {
+
+// ---------------------------------------------------------------- errors ------------------
+std::string &last_error();
+int fail(int code, const char *fmt, ...);
+
+#define TMVB_CUDA(expr)                                                                        \
+    do {                                                                                       \
+        cudaError_t _e = (expr);                                                               \
+        if (_e != cudaSuccess)                                                                 \
+            return ::tmvb::fail((int)_e, "%s failed at %s:%d: %s", #expr, __FILE__, __LINE__,  \
+                                cudaGetErrorString(_e));                                       \
+    } while (0)
+
+#define TMVB_CHECK_ARG(cond, msg)                                                              \
+    do {                                                                                       \
+        if (!(cond)) return ::tmvb::fail(-1, "invalid argument: %s (%s)", msg, #cond);         \
+    } while (0)
+
+#define TMVB_TRY(expr)                                                                         \
+    do {                                                                                       \
+        int _r = (expr);                                                                       \
+        if (_r != 0) return _r;                                                                \
+    } while (0)
+
+// ---------------------------------------------------------------- constants ---------------
+// EPSILON = eps(1e-14) = 2^-99 (utils.jl:3); representable in fp32 (min normal 2^-126).
+#define TMVB_EPS 1.5777218104420236e-30f
+#define TMVB_EPS_D 1.5777218104420236e-30
+
+constexpr int kWarp = 32;
+constexpr int kLanesPerToken = 8;  // lanes that share one token's K-vector
+
+// ---------------------------------------------------------------- device math -------------
+#ifdef __CUDACC__
+
+__device__ __forceinline__ float warp_xor_add(float v, int m) { return v + __shfl_xor_sync(0xffffffffu, v, m); }
+
+// sum over the 8 lanes that share a token (lane bits 0..2)
+__device__ __forceinline__ float group8_sum(float v)
+{
+    v = warp_xor_add(v, 1);
+    v = warp_xor_add(v, 2);
+    v = warp_xor_add(v, 4);
+    return v;
+}
+// sum over the 4 token streams of a warp (lane bits 3..4)
+__device__ __forceinline__ float streams_sum(float v)
+{
+    v = warp_xor_add(v, 8);
+    v = warp_xor_add(v, 16);
+    return v;
+}
+__device__ __forceinline__ float warp_sum(float v) { return streams_sum(group8_sum(v)); }
+__device__ __forceinline__ double warp_sum_d(double v)
+{
+#pragma unroll
+    for (int m = 16; m > 0; m >>= 1) v += __shfl_xor_sync(0xffffffffu, v, m);
+    return v;
+}
+
+// psi(x) and ln Gamma(x) for x > 0 in fp32, evaluated in-register.
+//
+// For x < 6 the argument is shifted by 6 with the recurrence folded into one rational term:
+//   P(x) = x(x+1)...(x+5),  psi(x) = psi(x+6) - P'(x)/P(x),  lnG(x) = lnG(x+6) - ln P(x)
+// (one division instead of the reference's six, utils.jl:27-36), then the asymptotic series
+//   psi(y) ~ ln y - 1/(2y) - 1/(12y^2) + 1/(120y^4) - 1/(252y^6)          (|err| < 3e-9, y >= 6)
+//   lnG(y) ~ (y-.5) ln y - y + .5 ln(2pi) + 1/(12y) - 1/(360y^3) + 1/(1260y^5)
+// replace the reference's 8-term fp32 series (utils.jl:39-50; Koelbig 1972).
+struct PsiLg {
+    float psi, lg;
+};
+
+template <bool WANT_LG>
+__device__ __forceinline__ PsiLg psi_lgamma(float x)
+{
+    float P = 1.0f, D = 0.0f, y = x;
+    if (x < 6.0f) {
+        // P = prod (x+k), D = dP/dx via the product rule, k = 0..5
+        P = x;
+        D = 1.0f;
+#pragma unroll
+        for (int k = 1; k < 6; k++) {
+            float f = x + (float)k;
+            D = fmaf(D, f, P);
+            P *= f;
+        }
+        y = x + 6.0f;
+    }
+    float ly = logf(y);
+    float t = __frcp_rn(y), t2 = t * t;
+    PsiLg r;
+    float ser = t2 * (8.3333333333e-2f - t2 * (8.3333333333e-3f - t2 * 3.9682539683e-3f));
+    r.psi = ly - 0.5f * t - ser;
+    if (x < 6.0f) r.psi -= D / P;
+    r.lg = 0.0f;
+    if (WANT_LG) {
+        float sl = t * (8.3333333333e-2f - t2 * (2.7777777778e-3f - t2 * 7.9365079365e-4f));
+        r.lg = fmaf(y - 0.5f, ly, -y) + 0.91893853320467f + sl;
+        if (x < 6.0f) r.lg -= logf(P);
+    }
+    return r;
+}
+
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src)
+{
+    unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
+
+// fire-and-forget fp32 add into global memory (RED.E.ADD.F32)
+__device__ __forceinline__ void red_add(float *addr, float v)
+{
+    asm volatile("red.global.add.f32 [%0], %1;\n" ::"l"(addr), "f"(v) : "memory");
+}
+
+#endif  // __CUDACC__
+
+// ---------------------------------------------------------------- host fp64 special functions
+double h_digamma(double x);
+double h_trigamma(double x);
+
+}  // namespace tmvb

@@ -1,0 +1,63 @@
+"""Multi-GPU plumbing: one process per GPU, documents sharded d -> d % world, one all-reduce of the
+sufficient statistics per outer iteration.  The collective itself is
+torch.distributed (NCCL over NVLink on GPUs, gloo in the CPU tests); this module only wraps the
+library's device buffers as tensors so they can be reduced in place on the handle's stream.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+
+class _DevBuf:
+    """A raw device pointer exposed through __cuda_array_interface__ (zero-copy torch view)."""
+
+    def __init__(self, ptr: int, n: int, typestr: str):
+        self.__cuda_array_interface__ = {"shape": (int(n),), "typestr": typestr, "data": (int(ptr), False),
+                                         "version": 2, "strides": None}
+
+
+class Reducer:
+    """Sum-reduces (stats fp32, small fp64) device buffers across the ranks of a torch process group."""
+
+    def __init__(self, group=None):
+        import torch
+        import torch.distributed as dist
+
+        assert dist.is_initialized(), "torch.distributed must be initialised (torchrun)"
+        self.torch, self.dist, self.group = torch, dist, group
+        self.rank = dist.get_rank(group)
+        self.world = dist.get_world_size(group)
+        self._views = {}
+
+    def stream_ptr(self) -> int:
+        return int(self.torch.cuda.current_stream().cuda_stream)
+
+    def view(self, ptr: int, n: int, typestr: str, device: int):
+        key = (ptr, n, typestr)
+        if key not in self._views:
+            self._views[key] = self.torch.as_tensor(_DevBuf(ptr, n, typestr), device="cuda:%d" % device)
+        return self._views[key]
+
+    def allreduce_device(self, bufs, device: int) -> None:
+        """bufs: [(ptr, n, typestr)] -- in-place sum over ranks, enqueued on torch's current stream."""
+        for ptr, n, typestr in bufs:
+            if n:
+                self.dist.all_reduce(self.view(ptr, n, typestr, device), op=self.dist.ReduceOp.SUM, group=self.group)
+
+    def allreduce_host(self, x: float) -> float:
+        t = self.torch.tensor([x], dtype=self.torch.float64)
+        if self.dist.get_backend(self.group) == "nccl":
+            t = t.cuda()
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM, group=self.group)
+        return float(t.item())
+
+
+def default_reducer() -> Optional[Reducer]:
+    """A Reducer when running under torchrun with world_size > 1, else None."""
+    try:
+        import torch.distributed as dist
+    except Exception:  # pragma: no cover
+        return None
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        return Reducer()
+    return None

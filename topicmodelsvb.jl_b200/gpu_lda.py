@@ -1,0 +1,263 @@
+"""gpuLDA -- host mirror of the reference's ``gpuLDA`` model and its ``train!`` (src/gpuLDA.jl),
+driving libtmvb.so through the C ABI (include/tmvb.h).  Julia is not installed in this image, so this
+Python layer stands where the Julia shim of INTEGRATION.md would: same struct fields, same keyword
+arguments, same argument checks and error kinds, same order of operations.
+
+Semantics follow the CPU model (src/LDA.jl) where the two reference implementations differ
+(per-document stopping rule, lagged-phi ELBO) -- BASELINE.json pins parity to the CPU LDA.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from typing import Optional
+
+import numpy as np
+from scipy.special import digamma
+
+from . import _lib
+from .corpus import Corpus, check_corp
+from .dist import Reducer
+
+
+def _fmat(x, K, n, name):
+    a = np.asarray(x, dtype=np.float32)
+    if a.shape != (K, n):
+        raise _lib.TopicModelError("%s must be of size (%d, %d)." % (name, K, n))
+    return np.asfortranarray(a)
+
+
+class gpuLDA:
+    """GPU accelerated latent Dirichlet allocation model (gpuLDA.jl:6-85).
+
+    Dense matrices are (K, V) / (K, M) Fortran-ordered float32 arrays -- byte-identical to the
+    reference's column-major Float32 matrices, so ``beta[i, j]`` and ``Elogtheta[:, d]`` read as in Julia.
+    ``phi`` is materialised lazily (``model.phi``) instead of living in HBM: the fused E-step never
+    writes it.
+
+    ``reducer``: a ``dist.Reducer`` when this model holds one shard (documents d % world == rank) of
+    a corpus trained on several GPUs; ``M_total`` is then the corpus-wide document count.
+    """
+
+    def __init__(self, corp: Corpus, K: int, seed: Optional[int] = None, device: int = -1,
+                 reducer: Optional[Reducer] = None, M_total: Optional[int] = None):
+        check_corp(corp)
+        if not (isinstance(K, (int, np.integer)) and K > 0):
+            raise ValueError("number of topics must be a positive integer.")  # gpuLDA.jl:47
+        M, V, _ = corp.size()
+        flat = corp.flat()
+        self.K, self.M, self.V = int(K), int(M), int(V)
+        self.N = np.diff(flat.N_cumsum).astype(np.int64)
+        cs = np.concatenate([[0], np.cumsum(flat.counts)]).astype(np.int64)
+        self.C = cs[flat.N_cumsum[1:]] - cs[flat.N_cumsum[:-1]]
+        self.corp = corp
+        self.topics = [np.arange(1, V + 1) for _ in range(K)]
+        rng = np.random.default_rng(seed)
+        self.alpha = np.ones(K, dtype=np.float32)                                        # gpuLDA.jl:55
+        g = rng.standard_exponential(size=(K, V)) if V else np.zeros((K, 0))
+        self.beta = np.asfortranarray((g / g.sum(axis=1, keepdims=True)).astype(np.float32)) if V else np.zeros((K, 0), np.float32, order="F")
+        e0 = np.float32(-(np.euler_gamma + digamma(K)))                                  # gpuLDA.jl:57
+        self.Elogtheta = np.full((K, M), e0, dtype=np.float32, order="F")
+        self.Elogtheta_sum = self.Elogtheta.sum(axis=1, dtype=np.float64)
+        self.gamma = np.ones((K, M), dtype=np.float32, order="F")                        # gpuLDA.jl:60
+        self.beta_old = self.beta.copy(order="F")
+        self.Elogtheta_old = self.Elogtheta.copy(order="F")
+        self.elbo = 0.0
+        self.sweeps = 0
+        self.reducer = reducer
+        self.M_total = int(M_total) if M_total is not None else self.M
+        self._device = device
+        self._h = None
+        self._resident = False
+
+    # ------------------------------------------------------------------ device plumbing ------
+    def _handle(self):
+        if self._h is None:
+            lib = _lib.load()
+            h = C.c_void_p()
+            stream = self.reducer.stream_ptr() if self.reducer is not None else None
+            _lib.check(lib.tmvb_lda_create(C.byref(h), self.K, self.M, self.V, self._device, stream))
+            self._h = h
+        return self._h
+
+    def close(self):
+        if self._h is not None:
+            _lib.load().tmvb_lda_destroy(self._h)
+            self._h = None
+            self._resident = False
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def update_buffer(self):
+        """update_buffer!(model::gpuLDA) (modelutils.jl:370-397): flatten, upload corpus and parameters."""
+        lib, h = _lib.load(), self._handle()
+        f = self.corp.flat()
+        _lib.check(lib.tmvb_lda_set_corpus(h, _lib.ptr(f.N_cumsum), _lib.ptr(f.terms), _lib.ptr(f.counts)))
+        self.alpha = np.ascontiguousarray(self.alpha, dtype=np.float32)
+        self.beta = _fmat(self.beta, self.K, self.V, "beta")
+        self.Elogtheta = _fmat(self.Elogtheta, self.K, self.M, "Elogtheta")
+        self.gamma = _fmat(self.gamma, self.K, self.M, "gamma")
+        _lib.check(lib.tmvb_lda_upload(h, _lib.ptr(self.alpha), self.beta.ctypes.data, self.Elogtheta.ctypes.data,
+                                       self.gamma.ctypes.data))
+        self._resident = True
+
+    def update_host(self):
+        """update_host!(model::gpuLDA) (modelutils.jl:501-516) minus phi (see ``phi``)."""
+        if not self._resident:
+            return
+        lib, h = _lib.load(), self._handle()
+        _lib.check(lib.tmvb_lda_download(h, _lib.ptr(self.alpha), self.beta.ctypes.data, self.Elogtheta.ctypes.data,
+                                         self.gamma.ctypes.data))
+        _lib.check(lib.tmvb_lda_download_old(h, self.beta_old.ctypes.data, self.Elogtheta_old.ctypes.data))
+        es = np.zeros(self.K)
+        _lib.check(lib.tmvb_lda_get_elogtheta_sum(h, _lib.ptr(es)))
+        self.Elogtheta_sum = es
+
+    @property
+    def phi(self):
+        """phi[d] (K x N_d) for every document: the last phi of the E-step (LDA.jl:87-88).  K*sum(N) floats."""
+        f = self.corp.flat()
+        if not self._resident:
+            self.update_buffer()
+        out = np.zeros((f.nnz, self.K), dtype=np.float32)
+        _lib.check(_lib.load().tmvb_lda_materialize_phi(self._handle(), _lib.ptr(out)))
+        return [out[f.N_cumsum[d]:f.N_cumsum[d + 1]].T for d in range(self.M)]
+
+    def stats(self) -> _lib.TmvbStats:
+        st = _lib.TmvbStats()
+        _lib.check(_lib.load().tmvb_lda_get_stats(self._handle(), C.byref(st)))
+        return st
+
+    # ------------------------------------------------------------------ the train! steps -----
+    def estep(self, viter: int, vtol: float, want_elbo: bool = True):
+        """The folded inner loop: update_phi!/update_gamma!/update_Elogtheta! (gpuLDA.jl:356-364) + scatter."""
+        _lib.check(_lib.load().tmvb_lda_estep(self._handle(), int(viter), float(vtol), int(bool(want_elbo))))
+
+    def _reduce(self):
+        if self.reducer is None:
+            return
+        lib, h = _lib.load(), self._handle()
+        sp, sn, mp, mn = C.c_void_p(), C.c_int64(), C.c_void_p(), C.c_int64()
+        _lib.check(lib.tmvb_lda_reduce_buffers(h, C.byref(sp), C.byref(sn), C.byref(mp), C.byref(mn)))
+        dev = self.reducer.torch.cuda.current_device()
+        self.reducer.allreduce_device([(sp.value, sn.value, "<f4"), (mp.value, mn.value, "<f8")], dev)
+
+    def update_beta(self):
+        """update_beta!(model::gpuLDA) (gpuLDA.jl:201-204): [all-reduce the statistics,] normalise."""
+        self._reduce()
+        _lib.check(_lib.load().tmvb_lda_mstep(self._handle()))
+
+    def update_alpha(self, niter: int, ntol: float):
+        """update_alpha!(model::gpuLDA, niter, ntol) (gpuLDA.jl:132-154), fp64 on the host inside the library."""
+        _lib.check(_lib.load().tmvb_lda_update_alpha(self._handle(), self.M_total, int(niter), float(ntol), _lib.ptr(self.alpha)))
+
+    def update_elbo(self, mode: int = 0) -> float:
+        """update_elbo!(model) (gpuLDA.jl:121-128) from device-side partials; no phi transfer."""
+        docs, glob = C.c_double(), C.c_double()
+        _lib.check(_lib.load().tmvb_lda_elbo(self._handle(), mode, self.M_total, C.byref(docs), C.byref(glob)))
+        d = docs.value
+        if mode == 1 and self.reducer is not None:
+            d = self.reducer.allreduce_host(d)
+        self.elbo = d + glob.value
+        return self.elbo
+
+
+def check_model(model: gpuLDA) -> None:
+    """check_model(model::gpuLDA) (modelutils.jl:255-279) -- the invariants that do not need phi."""
+    E = _lib.TopicModelError
+    K, M, V = model.K, model.M, model.V
+    f = model.corp.flat()
+    if M != len(model.corp):
+        raise E("M must equal the number of documents in the corpus.")
+    if not np.array_equal(model.N, np.diff(f.N_cumsum)):
+        raise E("N must contain document lengths.")
+    a = np.asarray(model.alpha)
+    if a.shape != (K,):
+        raise E("alpha must be of length K.")
+    if not np.all(np.isfinite(a)):
+        raise E("alpha must be finite.")
+    if not np.all(a > 0):
+        raise E("alpha must be positive.")
+    b = np.asarray(model.beta)
+    if b.shape != (K, V):
+        raise E("beta must be of size (K, V).")
+    if V and not (np.all(b >= 0) and np.allclose(b.sum(axis=1, dtype=np.float64), 1.0, rtol=math.sqrt(np.finfo(np.float32).eps))):
+        raise E("beta must be a right stochastic matrix.")
+    Et = np.asarray(model.Elogtheta)
+    if Et.shape != (K, M):
+        raise E("Elogtheta must contain M vectors of length K.")
+    if not np.all(np.isfinite(Et)):
+        raise E("Elogtheta must be finite.")
+    if not np.all(Et <= 0):
+        raise E("Elogtheta must be nonpositive.")
+    g = np.asarray(model.gamma)
+    if g.shape != (K, M):
+        raise E("gamma must contain M vectors of length K.")
+    if not np.all(np.isfinite(g)):
+        raise E("gamma must be finite.")
+    if not np.all(g > 0):
+        raise E("gamma must be positive.")
+    if not math.isfinite(model.elbo):
+        raise E("elbo must be finite.")
+
+
+def check_elbo(model, checkelbo, printelbo: bool, k: int, tol: float) -> bool:
+    """check_elbo!(model, checkelbo, printelbo, k, tol) (modelutils.jl:574-585).  The reference first
+    copies the whole model (incl. K x sumN phi) to the host; here the ELBO is assembled from
+    device-side partials, so nothing but O(K) doubles crosses the bus."""
+    if checkelbo != math.inf and k % checkelbo == 0:
+        old = model.elbo
+        delta = model.update_elbo(0) - old
+        if printelbo:
+            print("%d ∆elbo: %.3f" % (k, delta))
+        if delta < tol:
+            return True
+    return False
+
+
+def train(model: gpuLDA, iter: int = 150, tol: float = 1.0, niter: int = 1000, ntol: Optional[float] = None,
+          viter: int = 10, vtol: Optional[float] = None, checkelbo=1, printelbo: bool = True, trace: Optional[list] = None):
+    """train!(model::gpuLDA; iter, tol, niter, ntol, viter, vtol, checkelbo, printelbo) (gpuLDA.jl:347-376).
+
+    ``trace`` (optional list) receives the ELBO after every checked iteration (slot 0 = initial).
+    """
+    K = model.K
+    ntol = 1.0 / K**2 if ntol is None else ntol
+    vtol = 1.0 / K**2 if vtol is None else vtol
+    check_model(model)
+    if not all(t >= 0 for t in (tol, ntol, vtol)):
+        raise ValueError("tolerance parameters must be nonnegative.")
+    if not all(t >= 0 for t in (iter, niter, viter)):
+        raise ValueError("iteration parameters must be nonnegative.")
+    if not ((isinstance(checkelbo, (int, np.integer)) and checkelbo > 0) or checkelbo == math.inf):
+        raise ValueError("checkelbo parameter must be a positive integer or Inf.")
+    if model.corp.flat().nnz == 0 and (model.reducer is None):
+        iter = 0                                               # gpuLDA.jl:352
+    else:
+        model.update_buffer()
+    check = checkelbo != math.inf
+    if check and checkelbo <= iter:
+        model.update_elbo(1)                                   # gpuLDA.jl:353
+        if trace is not None:
+            trace.append(model.elbo)
+
+    for k in range(1, iter + 1):
+        want = check and (k % checkelbo == 0)
+        model.estep(viter, vtol, want_elbo=want)               # gpuLDA.jl:356-364, per-document stopping (LDA.jl:171-178)
+        model.update_beta()                                    # gpuLDA.jl:365
+        model.update_alpha(niter, ntol)                        # gpuLDA.jl:366
+        stop = check_elbo(model, checkelbo, printelbo, k, tol)  # gpuLDA.jl:368
+        if want and trace is not None:
+            trace.append(model.elbo)
+        if stop:
+            break
+
+    if iter > 0:
+        model.update_host()                                    # gpuLDA.jl:373
+    if model.V:
+        model.topics = [np.argsort(-model.beta[i, :], kind="stable") + 1 for i in range(K)]  # gpuLDA.jl:374
+    return None
