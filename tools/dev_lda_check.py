@@ -10,7 +10,7 @@ c = tm.synth.load_packed("nsf") or tm.synth.nsf_shaped()
 print("corpus", c.M, c.V, c.nnz, flush=True)
 model = tm.gpuLDA(tm.Corpus.from_csr(c), K, seed=7)
 t = time.time(); model.update_buffer(); print("update_buffer s", time.time() - t, flush=True)
-for it in range(6):
+for it in range(int(os.environ.get("ITERS", 6))):
     for want in (False, True):
         if want and it % 2: continue
         model.estep(10, 1.0 / K**2, want_elbo=want)

@@ -127,6 +127,12 @@ __device__ __forceinline__ void red_add(float *addr, float v)
     asm volatile("red.global.add.f32 [%0], %1;\n" ::"l"(addr), "f"(v) : "memory");
 }
 
+// 16-byte vector form (REDG.E.ADD.F32x4): addr must be 16-byte aligned
+__device__ __forceinline__ void red_add_v4(float *addr, float a, float b, float c, float d)
+{
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};\n" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
 #endif  // __CUDACC__
 
 // ---------------------------------------------------------------- host fp64 special functions

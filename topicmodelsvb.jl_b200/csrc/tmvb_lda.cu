@@ -6,7 +6,7 @@
 //
 // Device data layout (all owned by the handle):
 //   beta[2]      float [V][K_ld]   term-major rows ("term rows", == Julia's column-major K x V with
-//                                  the leading dimension padded to K_ld = 8*KPL, pad = 0); double
+//                                  the leading dimension padded to K_ld = 8*ceil(K/8), pad = 0); double
 //                                  buffered so beta_old (LDA.jl:122) costs nothing
 //   stats        float [V][K_ld]   sufficient statistics beta_temp (LDA.jl:131), RED.ADD target
 //   Elogtheta, Elogtheta_old, gamma  float [M][K_ld]   per-document K-vectors, internal doc order
@@ -38,84 +38,96 @@ struct LdaDev {
     float vtol;
 };
 
-template <int KPL>
-struct Geo {
-    static constexpr int K_ld = 8 * KPL;
-    // row stride of the shared-memory tile: (RS/8) must be odd so that the four token streams of
-    // a warp (rows n, n+1, n+2, n+3) hit disjoint banks when each reads 8 consecutive floats
-    static constexpr int RS = K_ld + ((KPL % 2 == 0) ? 8 : 0);
-    static constexpr int CH = 2 * KPL;  // 16-byte chunks per term row
-    static constexpr int RW = K_ld + 8; // cross-warp reduction row: K_ld partials + tsum
-    static constexpr int NM = (KPL + 3) / 4;
-};
-
-__host__ __device__ inline size_t lda_smem_bytes(int kpl, int cap, int warps)
+// Thread mapping of the E-step CTA (W warps, one document at a time):
+//   token phase  -- lane (ts = lane>>3, kl = lane&7) of warp w owns token stream 4w+ts and the
+//                   16-byte chunks q = kl + 8m (m < NQ) of every term row it visits, i.e. topics
+//                   4q..4q+3: a quarter-warp reads one 128-byte line of the tile per LDS.128.
+//   K phase      -- warp 0 only; lane l owns topics i = l + 32r (r < NQ): the K-vector algebra
+//                   (gamma, digamma, exp, convergence test) is done once per sweep, not per warp.
+__host__ __device__ inline size_t lda_smem_bytes(int K_ld, int cap, int warps)
 {
-    int K_ld = 8 * kpl, RS = K_ld + ((kpl % 2 == 0) ? 8 : 0), RW = K_ld + 8;
-    size_t b = (size_t)cap * RS * 4 + (size_t)cap * 8;    // tile + counts + terms
-    b += (size_t)2 * warps * RW * 4;                      // double-buffered cross-warp partials
-    b = (b + 7) & ~(size_t)7;
-    b += (size_t)K_ld * 8;                                // per-CTA sum of Elogtheta (fp64)
-    b += 16;                                              // next-document slot
+    size_t b = (size_t)cap * K_ld * 4 + (size_t)cap * 8;  // tile + counts + terms
+    b += (size_t)warps * K_ld * 4;                        // per-warp partial K-vectors
+    b += (size_t)K_ld * 4;                                // exp(Elogtheta) broadcast
+    b += 64;                                              // per-warp sum_n t_n (<= 8), flags
     return b;
 }
 
-// One pass over the document's tokens.  Lane (ts, kl) of warp w owns token stream 4w+ts and
-// topics i = kl + 8j.  Pass 1 (per token n):  s_n = K*eps + sum_i beta[i,w_n] e_i ;  t_n = c_n / s_n
-// Pass 2:  g_i += beta[i,w_n] t_n   so that   (phi * counts)_i = e_i g_i + eps sum_n t_n
+// One pass over the document's tokens.
+// Pass 1 (per token n):  s_n = K*eps + sum_i beta[i,w_n] e_i ;  t_n = c_n / s_n
+// Pass 2:                g_i += beta[i,w_n] t_n   so that   (phi * counts)_i = e_i g_i + eps sum_n t_n
 // which is update_phi! + update_gamma! (LDA.jl:143-154) without ever forming phi.
-// FINAL additionally scatters c_n phi_ni = t_n (eps + beta e_i) into stats (LDA.jl:129-132) and
-// accumulates sum_n c_n H(phi_n) (LDA.jl:76-80).
-template <int KPL, bool OVF, bool FINAL, bool ELBO>
+// FINAL instead scatters c_n phi_ni = t_n (eps + beta e_i) into stats (LDA.jl:129-132) with
+// 16-byte vector reductions and accumulates sum_n c_n H(phi_n) (LDA.jl:76-80).
+template <int NQ, bool OVF, bool FINAL, bool ELBO>
 __device__ __forceinline__ void lda_token_pass(const LdaDev &p, const float *tile, const float *cnt_s,
                                                const int *term_s, long long o, int Nd, int cap, int S,
-                                               int stream, int kl, const float (&e)[KPL], float (&g)[KPL],
+                                               int stream, int kl, const float4 (&e)[NQ], float4 (&g)[NQ],
                                                float &tsum, float &ent)
 {
-    using G = Geo<KPL>;
+    const int K_ld = p.K_ld, CH = K_ld >> 2;
     const float Keps = (float)p.K * TMVB_EPS;
     const int rounds = (Nd + S - 1) / S;
 #pragma unroll 2
     for (int r = 0; r < rounds; r++) {
         const int n = r * S + stream;
         const bool ok = n < Nd;
-        float b[KPL];
+        float4 b[NQ];
         float c = 0.0f;
         int term = 0;
         if (!OVF || n < cap) {
             const int nn = ok ? n : 0;
-            const float *row = tile + nn * G::RS + kl;
+            const float4 *row = reinterpret_cast<const float4 *>(tile + nn * K_ld) + kl;
 #pragma unroll
-            for (int j = 0; j < KPL; j++) b[j] = row[8 * j];
+            for (int m = 0; m < NQ; m++)
+                b[m] = (m < NQ - 1 || kl + 8 * m < CH) ? row[8 * m] : make_float4(0.f, 0.f, 0.f, 0.f);
             if (ok) c = cnt_s[nn];
             if (FINAL) term = term_s[nn];
         } else {
             const long long q = o + (ok ? n : 0);
             term = p.terms[q];
-            const float *row = p.beta + (size_t)term * G::K_ld + kl;
+            const float4 *row = reinterpret_cast<const float4 *>(p.beta + (size_t)term * K_ld) + kl;
 #pragma unroll
-            for (int j = 0; j < KPL; j++) b[j] = __ldg(row + 8 * j);
+            for (int m = 0; m < NQ; m++)
+                b[m] = (m < NQ - 1 || kl + 8 * m < CH) ? __ldg(row + 8 * m) : make_float4(0.f, 0.f, 0.f, 0.f);
             if (ok) c = p.counts[q];
         }
         float s = 0.0f;
 #pragma unroll
-        for (int j = 0; j < KPL; j++) s = fmaf(b[j], e[j], s);
+        for (int m = 0; m < NQ; m++) {
+            s = fmaf(b[m].x, e[m].x, s);
+            s = fmaf(b[m].y, e[m].y, s);
+            s = fmaf(b[m].z, e[m].z, s);
+            s = fmaf(b[m].w, e[m].w, s);
+        }
         s = group8_sum(s) + Keps;
         const float t = __fdividef(c, s);
         if (!FINAL) {
 #pragma unroll
-            for (int j = 0; j < KPL; j++) g[j] = fmaf(b[j], t, g[j]);
+            for (int m = 0; m < NQ; m++) {
+                g[m].x = fmaf(b[m].x, t, g[m].x);
+                g[m].y = fmaf(b[m].y, t, g[m].y);
+                g[m].z = fmaf(b[m].z, t, g[m].z);
+                g[m].w = fmaf(b[m].w, t, g[m].w);
+            }
             tsum += t;
         } else if (ok) {
-            float *srow = p.stats + (size_t)term * G::K_ld + kl;
+            float *srow = p.stats + (size_t)term * K_ld + 4 * kl;
             float a = 0.0f;
 #pragma unroll
-            for (int j = 0; j < KPL; j++) {
-                if (kl + 8 * j < p.K) {
-                    const float u = fmaf(b[j], e[j], TMVB_EPS);
-                    const float pcn = t * u;
-                    red_add(srow + 8 * j, pcn);
-                    if (ELBO) a = fmaf(pcn, __logf(u), a);
+            for (int m = 0; m < NQ; m++) {
+                const int i0 = 4 * (kl + 8 * m);
+                if (i0 < p.K) {
+                    // pad topics (i >= K) carry beta = e = 0: they get t*eps, which the M-step ignores
+                    const float ux = fmaf(b[m].x, e[m].x, TMVB_EPS), uy = fmaf(b[m].y, e[m].y, TMVB_EPS);
+                    const float uz = fmaf(b[m].z, e[m].z, TMVB_EPS), uw = fmaf(b[m].w, e[m].w, TMVB_EPS);
+                    red_add_v4(srow + 32 * m, t * ux, t * uy, t * uz, t * uw);
+                    if (ELBO) {
+                        a = fmaf(t * ux, __logf(ux), a);
+                        if (i0 + 1 < p.K) a = fmaf(t * uy, __logf(uy), a);
+                        if (i0 + 2 < p.K) a = fmaf(t * uz, __logf(uz), a);
+                        if (i0 + 3 < p.K) a = fmaf(t * uw, __logf(uw), a);
+                    }
                 }
             }
             if (ELBO) ent += ((kl == 0) ? c * __logf(s) : 0.0f) - a;
@@ -123,179 +135,189 @@ __device__ __forceinline__ void lda_token_pass(const LdaDev &p, const float *til
     }
 }
 
-template <int KPL, bool ELBO>
+template <int NQ, bool ELBO>
 __global__ void __launch_bounds__(256) lda_estep_kernel(const LdaDev p, int doc_begin, int doc_end, int cap, int *counter)
 {
-    using G = Geo<KPL>;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int T = blockDim.x, tid = threadIdx.x, W = T >> 5, warp = tid >> 5, lane = tid & 31;
     const int kl = lane & 7, ts = lane >> 3, S = 4 * W, stream = 4 * warp + ts;
+    const int K = p.K, K_ld = p.K_ld, CH = K_ld >> 2;
 
     float *tile = reinterpret_cast<float *>(smem_raw);
-    float *cnt_s = tile + (size_t)cap * G::RS;
+    float *cnt_s = tile + (size_t)cap * K_ld;
     int *term_s = reinterpret_cast<int *>(cnt_s + cap);
-    float *red = reinterpret_cast<float *>(term_s + cap);
-    size_t off = ((size_t)cap * G::RS * 4 + (size_t)cap * 8 + (size_t)2 * W * G::RW * 4 + 7) & ~(size_t)7;
-    double *esum_s = reinterpret_cast<double *>(smem_raw + off);
-    int *next_s = reinterpret_cast<int *>(esum_s + G::K_ld);
+    float *red = reinterpret_cast<float *>(term_s + cap);      // [W][K_ld]
+    float *e_s = red + (size_t)W * K_ld;                       // [K_ld]
+    float *redt = e_s + K_ld;                                  // [8]
+    int *flag_s = reinterpret_cast<int *>(redt + 8);           // [0] next document, [1] done
 
-    float alpha_r[KPL];
+    // K-phase state (meaningful in warp 0): topics i = lane + 32 r
+    float alpha_k[NQ], Eold_k[NQ], Enew_k[NQ], e_k[NQ], gam_k[NQ];
+    double esum_k[NQ];
 #pragma unroll
-    for (int j = 0; j < KPL; j++) alpha_r[j] = p.alpha[kl + 8 * j];
-    for (int i = tid; i < G::K_ld; i += T) esum_s[i] = 0.0;
+    for (int r = 0; r < NQ; r++) {
+        const int i = lane + 32 * r;
+        alpha_k[r] = (i < K) ? p.alpha[i] : 0.0f;
+        esum_k[r] = 0.0;
+        Enew_k[r] = gam_k[r] = 0.0f;
+    }
+    // a free K-phase slot (lane 31 of the last r) evaluates digamma(sum gamma) alongside the others
+    const bool spare = (32 * NQ - 1 >= K);
     double elbo_thr = 0.0;
     unsigned long long sweeps_thr = 0;
 
     for (;;) {
         __syncthreads();
-        if (tid == 0) *next_s = doc_begin + atomicAdd(counter, 1);
+        if (tid == 0) flag_s[0] = doc_begin + atomicAdd(counter, 1);
         __syncthreads();
-        const int d = *next_s;
+        const int d = flag_s[0];
         if (d >= doc_end) break;
         const long long o = p.doc_off[d];
         const int Nd = (int)(p.doc_off[d + 1] - o);
         const int ns = min(Nd, cap);
         const bool ovf = Nd > cap;
 
-        // stage the document: term ids + counts, then its K x N_d slab of beta (one 16-byte
-        // cp.async per lane, term rows are K_ld*4 contiguous bytes in HBM/L2)
+        // stage the document: term ids + counts, then its K x N_d slab of beta (16-byte cp.async
+        // per lane; a term row is K_ld*4 contiguous bytes in HBM/L2)
         for (int n = tid; n < ns; n += T) {
             term_s[n] = p.terms[o + n];
             cnt_s[n] = p.counts[o + n];
         }
         __syncthreads();
-        for (int c = tid; c < ns * G::CH; c += T) {
-            const int n = c / G::CH, q = c - n * G::CH;
-            cp_async16(tile + n * G::RS + 4 * q, p.beta + (size_t)term_s[n] * G::K_ld + 4 * q);
+        for (int c = tid; c < ns * CH; c += T) {
+            const int n = c / CH, q = c - n * CH;
+            cp_async16(tile + n * K_ld + 4 * q, p.beta + (size_t)term_s[n] * K_ld + 4 * q);
         }
         cp_async_commit();
-
-        float Eold[KPL], e[KPL], Enew[KPL], pc[KPL], gam[KPL], x[G::NM];
-        const float *Ed = p.Elogtheta + (size_t)d * G::K_ld + kl;
+        if (warp == 0) {
 #pragma unroll
-        for (int j = 0; j < KPL; j++) {
-            Eold[j] = Ed[8 * j];
-            e[j] = (kl + 8 * j < p.K) ? expf(Eold[j]) : 0.0f;
+            for (int r = 0; r < NQ; r++) {
+                const int i = lane + 32 * r;
+                Eold_k[r] = (i < K) ? p.Elogtheta[(size_t)d * K_ld + i] : 0.0f;
+                e_k[r] = (i < K) ? expf(Eold_k[r]) : 0.0f;
+                if (i < K_ld) e_s[i] = e_k[r];
+            }
         }
         cp_async_wait_all();
         __syncthreads();
 
+        float4 e[NQ];
         float gsum = 0.0f;
         int v = 0;
         for (;;) {
-            float g[KPL], tsum = 0.0f, dummy = 0.0f;
+            // ---- token phase: every warp sweeps its share of the tokens
 #pragma unroll
-            for (int j = 0; j < KPL; j++) g[j] = 0.0f;
+            for (int m = 0; m < NQ; m++)
+                e[m] = (m < NQ - 1 || kl + 8 * m < CH) ? reinterpret_cast<const float4 *>(e_s)[kl + 8 * m] : make_float4(0.f, 0.f, 0.f, 0.f);
+            float4 g[NQ];
+            float tsum = 0.0f, dummy = 0.0f;
+#pragma unroll
+            for (int m = 0; m < NQ; m++) g[m] = make_float4(0.f, 0.f, 0.f, 0.f);
             if (!ovf)
-                lda_token_pass<KPL, false, false, false>(p, tile, cnt_s, term_s, o, Nd, cap, S, stream, kl, e, g, tsum, dummy);
+                lda_token_pass<NQ, false, false, false>(p, tile, cnt_s, term_s, o, Nd, cap, S, stream, kl, e, g, tsum, dummy);
             else
-                lda_token_pass<KPL, true, false, false>(p, tile, cnt_s, term_s, o, Nd, cap, S, stream, kl, e, g, tsum, dummy);
-
-            // sum the partial K-vectors over the warp's 4 streams, then over the CTA's warps
+                lda_token_pass<NQ, true, false, false>(p, tile, cnt_s, term_s, o, Nd, cap, S, stream, kl, e, g, tsum, dummy);
 #pragma unroll
-            for (int j = 0; j < KPL; j++) g[j] = streams_sum(g[j]);
+            for (int m = 0; m < NQ; m++) {
+                g[m].x = streams_sum(g[m].x);
+                g[m].y = streams_sum(g[m].y);
+                g[m].z = streams_sum(g[m].z);
+                g[m].w = streams_sum(g[m].w);
+            }
             tsum = streams_sum(tsum);
-            if (W > 1) {
-                float *rb = red + (v & 1) * W * G::RW;
-                if (ts == 0) {
+            if (ts == 0) {
 #pragma unroll
-                    for (int j = 0; j < KPL; j++) rb[warp * G::RW + kl + 8 * j] = g[j];
-                    if (kl == 0) rb[warp * G::RW + G::K_ld] = tsum;
-                }
-                __syncthreads();
-#pragma unroll
-                for (int j = 0; j < KPL; j++) g[j] = 0.0f;
-                tsum = 0.0f;
-                for (int w = 0; w < W; w++) {
-#pragma unroll
-                    for (int j = 0; j < KPL; j++) g[j] += rb[w * G::RW + kl + 8 * j];
-                    tsum += rb[w * G::RW + G::K_ld];
-                }
+                for (int m = 0; m < NQ; m++)
+                    if (m < NQ - 1 || kl + 8 * m < CH) reinterpret_cast<float4 *>(red + warp * K_ld)[kl + 8 * m] = g[m];
+                if (kl == 0) redt[warp] = tsum;
             }
+            __syncthreads();
 
-            // update_gamma! (LDA.jl:143-146): gamma = EPS + (alpha + phi*counts)
-            float part = 0.0f;
+            // ---- K phase (warp 0): update_gamma! (LDA.jl:143-146), update_Elogtheta! (LDA.jl:136-139)
+            if (warp == 0) {
+                float tt = 0.0f;
+                for (int w = 0; w < W; w++) tt += redt[w];
+                float part = 0.0f;
 #pragma unroll
-            for (int j = 0; j < KPL; j++) {
-                const bool ok = kl + 8 * j < p.K;
-                pc[j] = fmaf(e[j], g[j], TMVB_EPS * tsum);
-                gam[j] = ok ? (alpha_r[j] + pc[j]) + TMVB_EPS : 1.0f;
-                part += ok ? gam[j] : 0.0f;
-            }
-            gsum = group8_sum(part);
-
-            // update_Elogtheta! (LDA.jl:136-139).  The K digammas are spread over the warp: lane
-            // (ts, kl) evaluates topics j = ts, ts+4, ... of column kl and the results are
-            // shuffled back, so a warp issues ceil(KPL/4)+1 digamma sequences instead of KPL+1.
+                for (int r = 0; r < NQ; r++) {
+                    const int i = lane + 32 * r;
+                    float gi = 0.0f;
+                    if (i < K)
+                        for (int w = 0; w < W; w++) gi += red[w * K_ld + i];
+                    // gamma = EPS + (alpha + phi*counts),   phi*counts = e .* g + eps * sum_n t_n
+                    gam_k[r] = (i < K) ? (alpha_k[r] + fmaf(e_k[r], gi, TMVB_EPS * tt)) + TMVB_EPS : 1.0f;
+                    part += (i < K) ? gam_k[r] : 0.0f;
+                }
+                gsum = warp_sum(part);
+                float x[NQ], ps[NQ];
 #pragma unroll
-            for (int m = 0; m < G::NM; m++) {
-                float xv = 1.0f;
+                for (int r = 0; r < NQ; r++) x[r] = gam_k[r];
+                if (spare && lane == 31) x[NQ - 1] = gsum;
 #pragma unroll
-                for (int q = 0; q < 4; q++)
-                    if (4 * m + q < KPL && ts == q) xv = gam[4 * m + q];
-                x[m] = xv;
-            }
-            float ps[G::NM];
+                for (int r = 0; r < NQ; r++) ps[r] = psi_lgamma<false>(x[r]).psi;
+                const float psi_sum = spare ? __shfl_sync(0xffffffffu, ps[NQ - 1], 31) : psi_lgamma<false>(gsum).psi;
+                float dpart = 0.0f;
 #pragma unroll
-            for (int m = 0; m < G::NM; m++) ps[m] = psi_lgamma<false>(x[m]).psi;
-            const float psi_sum = psi_lgamma<false>(gsum).psi;
-            float dpart = 0.0f;
+                for (int r = 0; r < NQ; r++) {
+                    const int i = lane + 32 * r;
+                    Enew_k[r] = ps[r] - psi_sum;
+                    if (i < K) {
+                        const float df = Enew_k[r] - Eold_k[r];
+                        dpart = fmaf(df, df, dpart);
+                    }
+                }
+                const float dist2 = warp_sum(dpart);
+                // LDA.jl:175: stop when ||Elogtheta - Elogtheta_old||_2 < vtol (or after viter sweeps)
+                const bool done = (sqrtf(dist2) < p.vtol) || (v + 1 >= p.viter);
+                if (lane == 0) flag_s[1] = done ? 1 : 0;
+                if (!done) {
 #pragma unroll
-            for (int j = 0; j < KPL; j++) {
-                const float pj = __shfl_sync(0xffffffffu, ps[j >> 2], ((j & 3) << 3) | kl);
-                Enew[j] = pj - psi_sum;
-                if (kl + 8 * j < p.K) {
-                    const float df = Enew[j] - Eold[j];
-                    dpart = fmaf(df, df, dpart);
+                    for (int r = 0; r < NQ; r++) {
+                        const int i = lane + 32 * r;
+                        Eold_k[r] = Enew_k[r];
+                        e_k[r] = (i < K) ? expf(Enew_k[r]) : 0.0f;
+                        if (i < K_ld) e_s[i] = e_k[r];
+                    }
                 }
             }
-            const float dist2 = group8_sum(dpart);
+            __syncthreads();
             v++;
-            // LDA.jl:175: stop when ||Elogtheta - Elogtheta_old||_2 < vtol (or after viter sweeps)
-            if (sqrtf(dist2) < p.vtol || v >= p.viter) break;
-#pragma unroll
-            for (int j = 0; j < KPL; j++) {
-                Eold[j] = Enew[j];
-                e[j] = (kl + 8 * j < p.K) ? expf(Enew[j]) : 0.0f;
-            }
+            if (flag_s[1]) break;
         }
 
         // update_beta!(model, d) (LDA.jl:129-132): scatter the last phi, weighted by counts
         {
-            float g[KPL], tsum = 0.0f, ent = 0.0f;
+            float4 g[NQ];
+            float tsum = 0.0f, ent = 0.0f;
             if (!ovf)
-                lda_token_pass<KPL, false, true, ELBO>(p, tile, cnt_s, term_s, o, Nd, cap, S, stream, kl, e, g, tsum, ent);
+                lda_token_pass<NQ, false, true, ELBO>(p, tile, cnt_s, term_s, o, Nd, cap, S, stream, kl, e, g, tsum, ent);
             else
-                lda_token_pass<KPL, true, true, ELBO>(p, tile, cnt_s, term_s, o, Nd, cap, S, stream, kl, e, g, tsum, ent);
+                lda_token_pass<NQ, true, true, ELBO>(p, tile, cnt_s, term_s, o, Nd, cap, S, stream, kl, e, g, tsum, ent);
             if (ELBO) elbo_thr += (double)ent;
         }
 
         if (warp == 0) {
-            if (ts == 0) {
-                float *gd = p.gamma + (size_t)d * G::K_ld + kl;
-                float *En = p.Elogtheta + (size_t)d * G::K_ld + kl;
-                float *Eo = p.Elogtheta_old + (size_t)d * G::K_ld + kl;
+            float a = 0.0f;
 #pragma unroll
-                for (int j = 0; j < KPL; j++) {
-                    const bool ok = kl + 8 * j < p.K;
-                    gd[8 * j] = ok ? gam[j] : 0.0f;
-                    En[8 * j] = ok ? Enew[j] : 0.0f;
-                    Eo[8 * j] = ok ? Eold[j] : 0.0f;
-                    if (ok) esum_s[kl + 8 * j] += (double)Enew[j];
+            for (int r = 0; r < NQ; r++) {
+                const int i = lane + 32 * r;
+                if (i < K_ld) {
+                    const bool ok = i < K;
+                    p.gamma[(size_t)d * K_ld + i] = ok ? gam_k[r] : 0.0f;
+                    p.Elogtheta[(size_t)d * K_ld + i] = ok ? Enew_k[r] : 0.0f;
+                    p.Elogtheta_old[(size_t)d * K_ld + i] = ok ? Eold_k[r] : 0.0f;
+                    if (ok) {
+                        esum_k[r] += (double)Enew_k[r];
+                        if (ELBO) a += psi_lgamma<true>(gam_k[r]).lg;
+                    }
                 }
-                // Dirichlet entropy (utils.jl:163-180) + Elogpz (LDA.jl:57-60): with gamma = alpha + phi*c
-                // and psi(gamma_i) = Elogtheta_i + psi(sum gamma) they collapse to
-                //   sum_i lnG(gamma_i) - lnG(sum gamma) + sum_i (1 - alpha_i) Elogtheta_i ;
-                // the last sum is linear in sum_d Elogtheta_d and is added on the host in fp64.
-                if (ELBO && kl == 0) elbo_thr -= (double)psi_lgamma<true>(gsum).lg;
             }
+            // Dirichlet entropy (utils.jl:163-180) + Elogpz (LDA.jl:57-60): with gamma = alpha + phi*c
+            // and psi(gamma_i) = Elogtheta_i + psi(sum gamma) they collapse to
+            //   sum_i lnG(gamma_i) - lnG(sum gamma) + sum_i (1 - alpha_i) Elogtheta_i ;
+            // the last sum is linear in sum_d Elogtheta_d and is added on the host in fp64.
             if (ELBO) {
-                float a = 0.0f;
-#pragma unroll
-                for (int m = 0; m < G::NM; m++) {
-                    const int j = 4 * m + ts;
-                    if (j < KPL && kl + 8 * j < p.K) a += psi_lgamma<true>(x[m]).lg;
-                }
+                if (lane == 0) a -= psi_lgamma<true>(gsum).lg;
                 elbo_thr += (double)a;
             }
             if (lane == 0) sweeps_thr += (unsigned long long)v;
@@ -305,11 +327,16 @@ __global__ void __launch_bounds__(256) lda_estep_kernel(const LdaDev p, int doc_
     // flush the CTA's accumulators
     if (ELBO) {
         const double tot = warp_sum_d(elbo_thr);
-        if (lane == 0 && tot != 0.0) atomicAdd(p.small + G::K_ld, tot);
+        if (lane == 0 && tot != 0.0) atomicAdd(p.small + K_ld, tot);
     }
-    for (int i = tid; i < p.K; i += T)
-        if (esum_s[i] != 0.0) atomicAdd(p.small + i, esum_s[i]);
-    if (tid == 0 && sweeps_thr) atomicAdd(p.small + G::K_ld + 1, (double)sweeps_thr);
+    if (warp == 0) {
+#pragma unroll
+        for (int r = 0; r < NQ; r++) {
+            const int i = lane + 32 * r;
+            if (i < K && esum_k[r] != 0.0) atomicAdd(p.small + i, esum_k[r]);
+        }
+        if (lane == 0 && sweeps_thr) atomicAdd(p.small + K_ld + 1, (double)sweeps_thr);
+    }
 }
 
 // ------------------------------------------------------------------ M-step ------------------
@@ -479,19 +506,18 @@ struct Bucket {
     size_t smem;
 };
 
-static const int kKplTable[] = {1, 2, 3, 4, 5, 6, 7, 8, 10, 13, 16, 20, 25, 32};
-
 typedef void (*EstepFn)(const LdaDev, int, int, int, int *);
 
-template <int KPL>
+template <int NQ>
 static EstepFn estep_fn(bool elbo)
 {
-    return elbo ? (EstepFn)lda_estep_kernel<KPL, true> : (EstepFn)lda_estep_kernel<KPL, false>;
+    return elbo ? (EstepFn)lda_estep_kernel<NQ, true> : (EstepFn)lda_estep_kernel<NQ, false>;
 }
 
-static EstepFn estep_dispatch(int kpl, bool elbo)
+// NQ = ceil(K_ld / 32): 16-byte chunks per lane in the token phase == topics per lane in the K phase
+static EstepFn estep_dispatch(int nq, bool elbo)
 {
-    switch (kpl) {
+    switch (nq) {
     case 1: return estep_fn<1>(elbo);
     case 2: return estep_fn<2>(elbo);
     case 3: return estep_fn<3>(elbo);
@@ -500,12 +526,6 @@ static EstepFn estep_dispatch(int kpl, bool elbo)
     case 6: return estep_fn<6>(elbo);
     case 7: return estep_fn<7>(elbo);
     case 8: return estep_fn<8>(elbo);
-    case 10: return estep_fn<10>(elbo);
-    case 13: return estep_fn<13>(elbo);
-    case 16: return estep_fn<16>(elbo);
-    case 20: return estep_fn<20>(elbo);
-    case 25: return estep_fn<25>(elbo);
-    case 32: return estep_fn<32>(elbo);
     }
     return nullptr;
 }
@@ -520,7 +540,7 @@ struct tmvb_lda_s {
     cudaStream_t stream = nullptr;
     bool own_stream = false;
     int64_t K = 0, M = 0, V = 0, nnz = 0;
-    int kpl = 0, K_ld = 0;
+    int nq = 0, K_ld = 0;
     bool corpus_set = false, params_set = false;
     // corpus
     long long *d_doc_off = nullptr, *d_src_off = nullptr;
@@ -609,7 +629,7 @@ int plan_buckets(tmvb_lda_t h, const std::vector<int> &len_sorted)
     const int force_w = env_int("TMVB_LDA_WARPS", 0);
     size_t budget = h->smem_optin;
     int cap_max = 16;
-    while (lda_smem_bytes(h->kpl, cap_max + 16, 8) <= budget) cap_max += 16;
+    while (lda_smem_bytes(h->K_ld, cap_max + 16, 8) <= budget) cap_max += 16;
     std::vector<int> caps;
     for (int c = 16; c < cap_max; c = (c < 128) ? c + 16 : (c < 256 ? c + 32 : c + c / 4 / 16 * 16)) caps.push_back(c);
     caps.push_back(cap_max);
@@ -625,7 +645,7 @@ int plan_buckets(tmvb_lda_t h, const std::vector<int> &len_sorted)
         b.cap = std::min(caps[ci], std::max(16, (len_sorted[begin] + 15) / 16 * 16));
         if (b.cap > cap_max) b.cap = cap_max;
         b.warps = force_w > 0 ? force_w : (b.cap <= 32 ? 1 : (b.cap <= 64 ? 2 : (b.cap <= 256 ? 4 : 8)));
-        b.smem = lda_smem_bytes(h->kpl, b.cap, b.warps);
+        b.smem = lda_smem_bytes(h->K_ld, b.cap, b.warps);
         b.grid = 0;
         h->buckets.push_back(b);
         begin = end;
@@ -680,13 +700,9 @@ int tmvb_lda_create(tmvb_lda_t *out, int64_t K, int64_t M, int64_t V, int device
     TMVB_CHECK_ARG(K > 0, "number of topics must be a positive integer");  // gpuLDA.jl:47
     TMVB_CHECK_ARG(M >= 0 && V >= 0, "M and V must be nonnegative");
     TMVB_CHECK_ARG(M < (1ll << 31) && V < (1ll << 31), "M and V must fit in int32");
-    int kpl = 0;
-    for (int c : kKplTable)
-        if (8 * c >= K) {
-            kpl = c;
-            break;
-        }
-    if (!kpl) return fail(-2, "K=%lld is not supported (K <= 256)", (long long)K);
+    if (K > 256) return fail(-2, "K=%lld is not supported (K <= 256)", (long long)K);
+    const int K_ld = (int)((K + 7) / 8 * 8);
+    const int nq = (K_ld + 31) / 32;
     int ndev = 0;
     TMVB_TRY(tmvb_device_count(&ndev));
     if (ndev == 0) return fail(-3, "no CUDA device: libtmvb has no CPU fallback");
@@ -704,8 +720,8 @@ int tmvb_lda_create(tmvb_lda_t *out, int64_t K, int64_t M, int64_t V, int device
     h->K = K;
     h->M = M;
     h->V = V;
-    h->kpl = kpl;
-    h->K_ld = 8 * kpl;
+    h->nq = nq;
+    h->K_ld = K_ld;
     if (stream) {
         h->stream = (cudaStream_t)stream;
     } else {
@@ -743,7 +759,7 @@ int tmvb_lda_create(tmvb_lda_t *out, int64_t K, int64_t M, int64_t V, int device
     h->h_alpha.assign(K, 1.0);
     // opt in to the large dynamic shared memory for both instantiations of this K
     for (int eb = 0; eb < 2; eb++) {
-        EstepFn fn = estep_dispatch(kpl, eb != 0);
+        EstepFn fn = estep_dispatch(nq, eb != 0);
         e = cudaFuncSetAttribute((const void *)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_optin);
         if (e != cudaSuccess) {
             free_all(h);
@@ -925,7 +941,7 @@ int tmvb_lda_estep(tmvb_lda_t h, int viter, float vtol, int want_elbo)
     TMVB_CUDA(cudaMemsetAsync(h->d_small, 0, (h->K_ld + 2) * 8, h->stream));
     TMVB_CUDA(cudaMemsetAsync(h->d_counters, 0, 64 * 4, h->stream));
     h->h_alpha_estep = h->h_alpha;
-    EstepFn fn = estep_dispatch(h->kpl, want_elbo != 0);
+    EstepFn fn = estep_dispatch(h->nq, want_elbo != 0);
     for (size_t bi = 0; bi < h->buckets.size(); bi++) {
         Bucket &b = h->buckets[bi];
         const int threads = 32 * b.warps;

@@ -110,6 +110,10 @@ class gpuLDA:
         if not self._resident:
             return
         lib, h = _lib.load(), self._handle()
+        # fresh arrays, as the reference's update_host! rebinds the fields (never write through to caller arrays)
+        self.alpha = np.empty(self.K, np.float32)
+        self.beta, self.beta_old = (np.empty((self.K, self.V), np.float32, order="F") for _ in range(2))
+        self.Elogtheta, self.Elogtheta_old, self.gamma = (np.empty((self.K, self.M), np.float32, order="F") for _ in range(3))
         _lib.check(lib.tmvb_lda_download(h, _lib.ptr(self.alpha), self.beta.ctypes.data, self.Elogtheta.ctypes.data,
                                          self.gamma.ctypes.data))
         _lib.check(lib.tmvb_lda_download_old(h, self.beta_old.ctypes.data, self.Elogtheta_old.ctypes.data))
