@@ -24,7 +24,7 @@
 namespace tmvb {
 
 struct LdaDev {
-    int K, K_ld, V;
+    int K, K_ld, V, RS;
     long long M;
     const float *beta;
     const float *alpha;
@@ -38,19 +38,38 @@ struct LdaDev {
     float vtol;
 };
 
-// Thread mapping of the E-step CTA (W warps, one document at a time):
-//   token phase  -- lane (ts = lane>>3, kl = lane&7) of warp w owns token stream 4w+ts and the
-//                   16-byte chunks q = kl + 8m (m < NQ) of every term row it visits, i.e. topics
-//                   4q..4q+3: a quarter-warp reads one 128-byte line of the tile per LDS.128.
-//   K phase      -- warp 0 only; lane l owns topics i = l + 32r (r < NQ): the K-vector algebra
-//                   (gamma, digamma, exp, convergence test) is done once per sweep, not per warp.
-__host__ __device__ inline size_t lda_smem_bytes(int K_ld, int cap, int warps)
+// Thread mapping of the E-step: ONE WARP PER DOCUMENT (a CTA is a single warp; the grid is
+// persistent and warps pull documents, longest first, from an atomic counter).
+//   token phase  -- lane (ts = lane / LPT, kl = lane % LPT) owns token stream ts (S = 32/LPT streams)
+//                   and the 16-byte chunks q = kl + LPT*m (m < CPL) of every term row it visits,
+//                   i.e. topics 4q..4q+3, read from the shared-memory tile with LDS.128.
+//   K phase      -- lane l owns topics i = l + 32r (r < R): gamma, digamma, exp and the
+//                   convergence test are evaluated once per sweep with 1-2 topics per lane.
+// The two layouts meet in shared memory: per-stream partial K-vectors are written as float4
+// chunks (gs), summed by the owner lanes, and exp(Elogtheta) travels back through e_s.
+// (LPT, CPL) is chosen per K on the host (lda_pick_layout); the row stride RS of tile/gs is padded
+// so that RS/4 = LPT (mod 2 LPT) for LPT < 8, which makes every LDS.128/STS.128 phase conflict-free.
+__host__ __device__ inline size_t lda_smem_bytes(int RS, int LPT, int cap)
 {
-    size_t b = (size_t)cap * K_ld * 4 + (size_t)cap * 8;  // tile + counts + terms
-    b += (size_t)warps * K_ld * 4;                        // per-warp partial K-vectors
-    b += (size_t)K_ld * 4;                                // exp(Elogtheta) broadcast
-    b += 64;                                              // per-warp sum_n t_n (<= 8), flags
+    size_t b = (size_t)cap * RS * 4 + (size_t)cap * 8;  // tile + counts + terms
+    b += (size_t)(32 / LPT) * RS * 4;                   // gs: per-stream partial K-vectors
+    b += (size_t)RS * 4;                                // e_s: exp(Elogtheta)
     return b;
+}
+
+template <int LPT>
+__device__ __forceinline__ float group_sum(float v)
+{
+#pragma unroll
+    for (int m = 1; m < LPT; m <<= 1) v += __shfl_xor_sync(0xffffffffu, v, m);
+    return v;
+}
+template <int LPT>
+__device__ __forceinline__ float across_streams_sum(float v)
+{
+#pragma unroll
+    for (int m = LPT; m < 32; m <<= 1) v += __shfl_xor_sync(0xffffffffu, v, m);
+    return v;
 }
 
 // One pass over the document's tokens.
@@ -59,28 +78,28 @@ __host__ __device__ inline size_t lda_smem_bytes(int K_ld, int cap, int warps)
 // which is update_phi! + update_gamma! (LDA.jl:143-154) without ever forming phi.
 // FINAL instead scatters c_n phi_ni = t_n (eps + beta e_i) into stats (LDA.jl:129-132) with
 // 16-byte vector reductions and accumulates sum_n c_n H(phi_n) (LDA.jl:76-80).
-template <int NQ, bool OVF, bool FINAL, bool ELBO>
+template <int LPT, int CPL, bool OVF, bool FINAL, bool ELBO>
 __device__ __forceinline__ void lda_token_pass(const LdaDev &p, const float *tile, const float *cnt_s,
-                                               const int *term_s, long long o, int Nd, int cap, int S,
-                                               int stream, int kl, const float4 (&e)[NQ], float4 (&g)[NQ],
+                                               const int *term_s, long long o, int Nd, int cap, int rounds,
+                                               int ts, int kl, const float4 (&e)[CPL], float4 (&g)[CPL],
                                                float &tsum, float &ent)
 {
-    const int K_ld = p.K_ld, CH = K_ld >> 2;
+    constexpr int S = 32 / LPT;
+    const int K_ld = p.K_ld, CH = K_ld >> 2, RS = p.RS;
     const float Keps = (float)p.K * TMVB_EPS;
-    const int rounds = (Nd + S - 1) / S;
+    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll 2
     for (int r = 0; r < rounds; r++) {
-        const int n = r * S + stream;
+        const int n = r * S + ts;
         const bool ok = n < Nd;
-        float4 b[NQ];
+        float4 b[CPL];
         float c = 0.0f;
         int term = 0;
         if (!OVF || n < cap) {
             const int nn = ok ? n : 0;
-            const float4 *row = reinterpret_cast<const float4 *>(tile + nn * K_ld) + kl;
+            const float4 *row = reinterpret_cast<const float4 *>(tile + nn * RS) + kl;
 #pragma unroll
-            for (int m = 0; m < NQ; m++)
-                b[m] = (m < NQ - 1 || kl + 8 * m < CH) ? row[8 * m] : make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int m = 0; m < CPL; m++) b[m] = (m < CPL - 1 || kl + LPT * m < CH) ? row[LPT * m] : zero4;
             if (ok) c = cnt_s[nn];
             if (FINAL) term = term_s[nn];
         } else {
@@ -88,23 +107,22 @@ __device__ __forceinline__ void lda_token_pass(const LdaDev &p, const float *til
             term = p.terms[q];
             const float4 *row = reinterpret_cast<const float4 *>(p.beta + (size_t)term * K_ld) + kl;
 #pragma unroll
-            for (int m = 0; m < NQ; m++)
-                b[m] = (m < NQ - 1 || kl + 8 * m < CH) ? __ldg(row + 8 * m) : make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int m = 0; m < CPL; m++) b[m] = (m < CPL - 1 || kl + LPT * m < CH) ? __ldg(row + LPT * m) : zero4;
             if (ok) c = p.counts[q];
         }
-        float s = 0.0f;
+        float s0 = 0.0f, s1 = 0.0f, s2 = 0.0f, s3 = 0.0f;
 #pragma unroll
-        for (int m = 0; m < NQ; m++) {
-            s = fmaf(b[m].x, e[m].x, s);
-            s = fmaf(b[m].y, e[m].y, s);
-            s = fmaf(b[m].z, e[m].z, s);
-            s = fmaf(b[m].w, e[m].w, s);
+        for (int m = 0; m < CPL; m++) {
+            s0 = fmaf(b[m].x, e[m].x, s0);
+            s1 = fmaf(b[m].y, e[m].y, s1);
+            s2 = fmaf(b[m].z, e[m].z, s2);
+            s3 = fmaf(b[m].w, e[m].w, s3);
         }
-        s = group8_sum(s) + Keps;
+        const float s = group_sum<LPT>((s0 + s1) + (s2 + s3)) + Keps;
         const float t = __fdividef(c, s);
         if (!FINAL) {
 #pragma unroll
-            for (int m = 0; m < NQ; m++) {
+            for (int m = 0; m < CPL; m++) {
                 g[m].x = fmaf(b[m].x, t, g[m].x);
                 g[m].y = fmaf(b[m].y, t, g[m].y);
                 g[m].z = fmaf(b[m].z, t, g[m].z);
@@ -115,13 +133,13 @@ __device__ __forceinline__ void lda_token_pass(const LdaDev &p, const float *til
             float *srow = p.stats + (size_t)term * K_ld + 4 * kl;
             float a = 0.0f;
 #pragma unroll
-            for (int m = 0; m < NQ; m++) {
-                const int i0 = 4 * (kl + 8 * m);
+            for (int m = 0; m < CPL; m++) {
+                const int i0 = 4 * (kl + LPT * m);
                 if (i0 < p.K) {
                     // pad topics (i >= K) carry beta = e = 0: they get t*eps, which the M-step ignores
                     const float ux = fmaf(b[m].x, e[m].x, TMVB_EPS), uy = fmaf(b[m].y, e[m].y, TMVB_EPS);
                     const float uz = fmaf(b[m].z, e[m].z, TMVB_EPS), uw = fmaf(b[m].w, e[m].w, TMVB_EPS);
-                    red_add_v4(srow + 32 * m, t * ux, t * uy, t * uz, t * uw);
+                    red_add_v4(srow + 4 * LPT * m, t * ux, t * uy, t * uz, t * uw);
                     if (ELBO) {
                         a = fmaf(t * ux, __logf(ux), a);
                         if (i0 + 1 < p.K) a = fmaf(t * uy, __logf(uy), a);
@@ -135,208 +153,188 @@ __device__ __forceinline__ void lda_token_pass(const LdaDev &p, const float *til
     }
 }
 
-template <int NQ, bool ELBO>
-__global__ void __launch_bounds__(256) lda_estep_kernel(const LdaDev p, int doc_begin, int doc_end, int cap, int *counter)
+template <int LPT, int CPL, bool ELBO>
+__global__ void __launch_bounds__(32) lda_estep_kernel(const LdaDev p, int doc_begin, int doc_end, int cap, int *counter)
 {
+    constexpr int S = 32 / LPT;                   // token streams per warp
+    constexpr int R = (LPT * CPL + 7) / 8;        // K-phase topics per lane (>= ceil(K_ld / 32))
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int T = blockDim.x, tid = threadIdx.x, W = T >> 5, warp = tid >> 5, lane = tid & 31;
-    const int kl = lane & 7, ts = lane >> 3, S = 4 * W, stream = 4 * warp + ts;
-    const int K = p.K, K_ld = p.K_ld, CH = K_ld >> 2;
+    const int lane = threadIdx.x;
+    const int kl = lane % LPT, ts = lane / LPT;
+    const int K = p.K, K_ld = p.K_ld, CH = K_ld >> 2, RS = p.RS;
+    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
 
     float *tile = reinterpret_cast<float *>(smem_raw);
-    float *cnt_s = tile + (size_t)cap * K_ld;
-    int *term_s = reinterpret_cast<int *>(cnt_s + cap);
-    float *red = reinterpret_cast<float *>(term_s + cap);      // [W][K_ld]
-    float *e_s = red + (size_t)W * K_ld;                       // [K_ld]
-    float *redt = e_s + K_ld;                                  // [8]
-    int *flag_s = reinterpret_cast<int *>(redt + 8);           // [0] next document, [1] done
+    float *gs = tile + (size_t)cap * RS;                       // [S][RS]
+    float *e_s = gs + (size_t)S * RS;                          // [RS]
+    float *cnt_s = e_s + RS;                                   // [cap]
+    int *term_s = reinterpret_cast<int *>(cnt_s + cap);        // [cap]
 
-    // K-phase state (meaningful in warp 0): topics i = lane + 32 r
-    float alpha_k[NQ], Eold_k[NQ], Enew_k[NQ], e_k[NQ], gam_k[NQ];
-    double esum_k[NQ];
+    // K-phase state: topics i = lane + 32 r
+    float alpha_k[R], Eold_k[R], Enew_k[R], e_k[R], gam_k[R];
+    double esum_k[R];
 #pragma unroll
-    for (int r = 0; r < NQ; r++) {
+    for (int r = 0; r < R; r++) {
         const int i = lane + 32 * r;
         alpha_k[r] = (i < K) ? p.alpha[i] : 0.0f;
         esum_k[r] = 0.0;
-        Enew_k[r] = gam_k[r] = 0.0f;
+        Enew_k[r] = gam_k[r] = Eold_k[r] = e_k[r] = 0.0f;
     }
     // a free K-phase slot (lane 31 of the last r) evaluates digamma(sum gamma) alongside the others
-    const bool spare = (32 * NQ - 1 >= K);
+    const bool spare = (32 * R - 1 >= K);
     double elbo_thr = 0.0;
     unsigned long long sweeps_thr = 0;
 
     for (;;) {
-        __syncthreads();
-        if (tid == 0) flag_s[0] = doc_begin + atomicAdd(counter, 1);
-        __syncthreads();
-        const int d = flag_s[0];
+        int d = 0;
+        if (lane == 0) d = doc_begin + atomicAdd(counter, 1);
+        d = __shfl_sync(0xffffffffu, d, 0);
         if (d >= doc_end) break;
         const long long o = p.doc_off[d];
         const int Nd = (int)(p.doc_off[d + 1] - o);
         const int ns = min(Nd, cap);
         const bool ovf = Nd > cap;
+        const int rounds = (Nd + S - 1) / S;
 
         // stage the document: term ids + counts, then its K x N_d slab of beta (16-byte cp.async
         // per lane; a term row is K_ld*4 contiguous bytes in HBM/L2)
-        for (int n = tid; n < ns; n += T) {
+        __syncwarp();
+        for (int n = lane; n < ns; n += 32) {
             term_s[n] = p.terms[o + n];
             cnt_s[n] = p.counts[o + n];
         }
-        __syncthreads();
-        for (int c = tid; c < ns * CH; c += T) {
+        __syncwarp();
+        for (int c = lane; c < ns * CH; c += 32) {
             const int n = c / CH, q = c - n * CH;
-            cp_async16(tile + n * K_ld + 4 * q, p.beta + (size_t)term_s[n] * K_ld + 4 * q);
+            cp_async16(tile + n * RS + 4 * q, p.beta + (size_t)term_s[n] * K_ld + 4 * q);
         }
         cp_async_commit();
-        if (warp == 0) {
 #pragma unroll
-            for (int r = 0; r < NQ; r++) {
-                const int i = lane + 32 * r;
-                Eold_k[r] = (i < K) ? p.Elogtheta[(size_t)d * K_ld + i] : 0.0f;
-                e_k[r] = (i < K) ? expf(Eold_k[r]) : 0.0f;
-                if (i < K_ld) e_s[i] = e_k[r];
-            }
+        for (int r = 0; r < R; r++) {
+            const int i = lane + 32 * r;
+            Eold_k[r] = (i < K) ? p.Elogtheta[(size_t)d * K_ld + i] : 0.0f;
+            e_k[r] = (i < K) ? expf(Eold_k[r]) : 0.0f;
+            if (i < K_ld) e_s[i] = e_k[r];
         }
         cp_async_wait_all();
-        __syncthreads();
+        __syncwarp();
 
-        float4 e[NQ];
+        float4 e[CPL];
         float gsum = 0.0f;
         int v = 0;
         for (;;) {
-            // ---- token phase: every warp sweeps its share of the tokens
+            // ---- token phase
 #pragma unroll
-            for (int m = 0; m < NQ; m++)
-                e[m] = (m < NQ - 1 || kl + 8 * m < CH) ? reinterpret_cast<const float4 *>(e_s)[kl + 8 * m] : make_float4(0.f, 0.f, 0.f, 0.f);
-            float4 g[NQ];
+            for (int m = 0; m < CPL; m++)
+                e[m] = (m < CPL - 1 || kl + LPT * m < CH) ? reinterpret_cast<const float4 *>(e_s)[kl + LPT * m] : zero4;
+            float4 g[CPL];
             float tsum = 0.0f, dummy = 0.0f;
 #pragma unroll
-            for (int m = 0; m < NQ; m++) g[m] = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int m = 0; m < CPL; m++) g[m] = zero4;
             if (!ovf)
-                lda_token_pass<NQ, false, false, false>(p, tile, cnt_s, term_s, o, Nd, cap, S, stream, kl, e, g, tsum, dummy);
+                lda_token_pass<LPT, CPL, false, false, false>(p, tile, cnt_s, term_s, o, Nd, cap, rounds, ts, kl, e, g, tsum, dummy);
             else
-                lda_token_pass<NQ, true, false, false>(p, tile, cnt_s, term_s, o, Nd, cap, S, stream, kl, e, g, tsum, dummy);
+                lda_token_pass<LPT, CPL, true, false, false>(p, tile, cnt_s, term_s, o, Nd, cap, rounds, ts, kl, e, g, tsum, dummy);
 #pragma unroll
-            for (int m = 0; m < NQ; m++) {
-                g[m].x = streams_sum(g[m].x);
-                g[m].y = streams_sum(g[m].y);
-                g[m].z = streams_sum(g[m].z);
-                g[m].w = streams_sum(g[m].w);
-            }
-            tsum = streams_sum(tsum);
-            if (ts == 0) {
-#pragma unroll
-                for (int m = 0; m < NQ; m++)
-                    if (m < NQ - 1 || kl + 8 * m < CH) reinterpret_cast<float4 *>(red + warp * K_ld)[kl + 8 * m] = g[m];
-                if (kl == 0) redt[warp] = tsum;
-            }
-            __syncthreads();
+            for (int m = 0; m < CPL; m++)
+                if (m < CPL - 1 || kl + LPT * m < CH) reinterpret_cast<float4 *>(gs + ts * RS)[kl + LPT * m] = g[m];
+            const float tt = across_streams_sum<LPT>(tsum);
+            __syncwarp();
 
-            // ---- K phase (warp 0): update_gamma! (LDA.jl:143-146), update_Elogtheta! (LDA.jl:136-139)
-            if (warp == 0) {
-                float tt = 0.0f;
-                for (int w = 0; w < W; w++) tt += redt[w];
-                float part = 0.0f;
+            // ---- K phase: update_gamma! (LDA.jl:143-146), update_Elogtheta! (LDA.jl:136-139)
+            float part = 0.0f;
 #pragma unroll
-                for (int r = 0; r < NQ; r++) {
-                    const int i = lane + 32 * r;
-                    float gi = 0.0f;
-                    if (i < K)
-                        for (int w = 0; w < W; w++) gi += red[w * K_ld + i];
-                    // gamma = EPS + (alpha + phi*counts),   phi*counts = e .* g + eps * sum_n t_n
-                    gam_k[r] = (i < K) ? (alpha_k[r] + fmaf(e_k[r], gi, TMVB_EPS * tt)) + TMVB_EPS : 1.0f;
-                    part += (i < K) ? gam_k[r] : 0.0f;
+            for (int r = 0; r < R; r++) {
+                const int i = lane + 32 * r;
+                float gi = 0.0f;
+                if (i < K) {
+#pragma unroll
+                    for (int w = 0; w < S; w++) gi += gs[w * RS + i];
                 }
-                gsum = warp_sum(part);
-                float x[NQ], ps[NQ];
+                // gamma = EPS + (alpha + phi*counts),   phi*counts = e .* g + eps * sum_n t_n
+                gam_k[r] = (i < K) ? (alpha_k[r] + fmaf(e_k[r], gi, TMVB_EPS * tt)) + TMVB_EPS : 1.0f;
+                part += (i < K) ? gam_k[r] : 0.0f;
+            }
+            gsum = warp_sum(part);
+            float x[R], ps[R];
 #pragma unroll
-                for (int r = 0; r < NQ; r++) x[r] = gam_k[r];
-                if (spare && lane == 31) x[NQ - 1] = gsum;
+            for (int r = 0; r < R; r++) x[r] = gam_k[r];
+            if (spare && lane == 31) x[R - 1] = gsum;
 #pragma unroll
-                for (int r = 0; r < NQ; r++) ps[r] = psi_lgamma<false>(x[r]).psi;
-                const float psi_sum = spare ? __shfl_sync(0xffffffffu, ps[NQ - 1], 31) : psi_lgamma<false>(gsum).psi;
-                float dpart = 0.0f;
+            for (int r = 0; r < R; r++) ps[r] = psi_lgamma<false>(x[r]).psi;
+            const float psi_sum = spare ? __shfl_sync(0xffffffffu, ps[R - 1], 31) : psi_lgamma<false>(gsum).psi;
+            float dpart = 0.0f;
 #pragma unroll
-                for (int r = 0; r < NQ; r++) {
-                    const int i = lane + 32 * r;
-                    Enew_k[r] = ps[r] - psi_sum;
-                    if (i < K) {
-                        const float df = Enew_k[r] - Eold_k[r];
-                        dpart = fmaf(df, df, dpart);
-                    }
-                }
-                const float dist2 = warp_sum(dpart);
-                // LDA.jl:175: stop when ||Elogtheta - Elogtheta_old||_2 < vtol (or after viter sweeps)
-                const bool done = (sqrtf(dist2) < p.vtol) || (v + 1 >= p.viter);
-                if (lane == 0) flag_s[1] = done ? 1 : 0;
-                if (!done) {
-#pragma unroll
-                    for (int r = 0; r < NQ; r++) {
-                        const int i = lane + 32 * r;
-                        Eold_k[r] = Enew_k[r];
-                        e_k[r] = (i < K) ? expf(Enew_k[r]) : 0.0f;
-                        if (i < K_ld) e_s[i] = e_k[r];
-                    }
+            for (int r = 0; r < R; r++) {
+                const int i = lane + 32 * r;
+                Enew_k[r] = ps[r] - psi_sum;
+                if (i < K) {
+                    const float df = Enew_k[r] - Eold_k[r];
+                    dpart = fmaf(df, df, dpart);
                 }
             }
-            __syncthreads();
+            const float dist2 = warp_sum(dpart);
             v++;
-            if (flag_s[1]) break;
+            // LDA.jl:175: stop when ||Elogtheta - Elogtheta_old||_2 < vtol (or after viter sweeps)
+            if ((sqrtf(dist2) < p.vtol) || (v >= p.viter)) break;
+#pragma unroll
+            for (int r = 0; r < R; r++) {
+                const int i = lane + 32 * r;
+                Eold_k[r] = Enew_k[r];
+                e_k[r] = (i < K) ? expf(Enew_k[r]) : 0.0f;
+                if (i < K_ld) e_s[i] = e_k[r];
+            }
+            __syncwarp();
         }
 
         // update_beta!(model, d) (LDA.jl:129-132): scatter the last phi, weighted by counts
         {
-            float4 g[NQ];
+            float4 g[CPL];
             float tsum = 0.0f, ent = 0.0f;
             if (!ovf)
-                lda_token_pass<NQ, false, true, ELBO>(p, tile, cnt_s, term_s, o, Nd, cap, S, stream, kl, e, g, tsum, ent);
+                lda_token_pass<LPT, CPL, false, true, ELBO>(p, tile, cnt_s, term_s, o, Nd, cap, rounds, ts, kl, e, g, tsum, ent);
             else
-                lda_token_pass<NQ, true, true, ELBO>(p, tile, cnt_s, term_s, o, Nd, cap, S, stream, kl, e, g, tsum, ent);
+                lda_token_pass<LPT, CPL, true, true, ELBO>(p, tile, cnt_s, term_s, o, Nd, cap, rounds, ts, kl, e, g, tsum, ent);
             if (ELBO) elbo_thr += (double)ent;
         }
 
-        if (warp == 0) {
-            float a = 0.0f;
+        float a = 0.0f;
 #pragma unroll
-            for (int r = 0; r < NQ; r++) {
-                const int i = lane + 32 * r;
-                if (i < K_ld) {
-                    const bool ok = i < K;
-                    p.gamma[(size_t)d * K_ld + i] = ok ? gam_k[r] : 0.0f;
-                    p.Elogtheta[(size_t)d * K_ld + i] = ok ? Enew_k[r] : 0.0f;
-                    p.Elogtheta_old[(size_t)d * K_ld + i] = ok ? Eold_k[r] : 0.0f;
-                    if (ok) {
-                        esum_k[r] += (double)Enew_k[r];
-                        if (ELBO) a += psi_lgamma<true>(gam_k[r]).lg;
-                    }
+        for (int r = 0; r < R; r++) {
+            const int i = lane + 32 * r;
+            if (i < K_ld) {
+                const bool ok = i < K;
+                p.gamma[(size_t)d * K_ld + i] = ok ? gam_k[r] : 0.0f;
+                p.Elogtheta[(size_t)d * K_ld + i] = ok ? Enew_k[r] : 0.0f;
+                p.Elogtheta_old[(size_t)d * K_ld + i] = ok ? Eold_k[r] : 0.0f;
+                if (ok) {
+                    esum_k[r] += (double)Enew_k[r];
+                    if (ELBO) a += psi_lgamma<true>(gam_k[r]).lg;
                 }
             }
-            // Dirichlet entropy (utils.jl:163-180) + Elogpz (LDA.jl:57-60): with gamma = alpha + phi*c
-            // and psi(gamma_i) = Elogtheta_i + psi(sum gamma) they collapse to
-            //   sum_i lnG(gamma_i) - lnG(sum gamma) + sum_i (1 - alpha_i) Elogtheta_i ;
-            // the last sum is linear in sum_d Elogtheta_d and is added on the host in fp64.
-            if (ELBO) {
-                if (lane == 0) a -= psi_lgamma<true>(gsum).lg;
-                elbo_thr += (double)a;
-            }
-            if (lane == 0) sweeps_thr += (unsigned long long)v;
         }
+        // Dirichlet entropy (utils.jl:163-180) + Elogpz (LDA.jl:57-60): with gamma = alpha + phi*c
+        // and psi(gamma_i) = Elogtheta_i + psi(sum gamma) they collapse to
+        //   sum_i lnG(gamma_i) - lnG(sum gamma) + sum_i (1 - alpha_i) Elogtheta_i ;
+        // the last sum is linear in sum_d Elogtheta_d and is added on the host in fp64.
+        if (ELBO) {
+            if (lane == 0) a -= psi_lgamma<true>(gsum).lg;
+            elbo_thr += (double)a;
+        }
+        if (lane == 0) sweeps_thr += (unsigned long long)v;
     }
 
-    // flush the CTA's accumulators
+    // flush the warp's accumulators
     if (ELBO) {
         const double tot = warp_sum_d(elbo_thr);
         if (lane == 0 && tot != 0.0) atomicAdd(p.small + K_ld, tot);
     }
-    if (warp == 0) {
 #pragma unroll
-        for (int r = 0; r < NQ; r++) {
-            const int i = lane + 32 * r;
-            if (i < K && esum_k[r] != 0.0) atomicAdd(p.small + i, esum_k[r]);
-        }
-        if (lane == 0 && sweeps_thr) atomicAdd(p.small + K_ld + 1, (double)sweeps_thr);
+    for (int r = 0; r < R; r++) {
+        const int i = lane + 32 * r;
+        if (i < K && esum_k[r] != 0.0) atomicAdd(p.small + i, esum_k[r]);
     }
+    if (lane == 0 && sweeps_thr) atomicAdd(p.small + K_ld + 1, (double)sweeps_thr);
 }
 
 // ------------------------------------------------------------------ M-step ------------------
@@ -508,26 +506,48 @@ struct Bucket {
 
 typedef void (*EstepFn)(const LdaDev, int, int, int, int *);
 
-template <int NQ>
-static EstepFn estep_fn(bool elbo)
+struct Layout {
+    int lpt, cpl;
+    EstepFn fn[2];  // [want_elbo]
+};
+#define TMVB_LAYOUT(L, C) {L, C, {(EstepFn)lda_estep_kernel<L, C, false>, (EstepFn)lda_estep_kernel<L, C, true>}}
+// the (LPT, CPL) pairs lda_pick_layout can select for K <= 256
+static const Layout kLayouts[] = {
+    TMVB_LAYOUT(1, 4), TMVB_LAYOUT(1, 8), TMVB_LAYOUT(2, 1), TMVB_LAYOUT(2, 3), TMVB_LAYOUT(2, 5), TMVB_LAYOUT(2, 6),
+    TMVB_LAYOUT(2, 7), TMVB_LAYOUT(2, 8), TMVB_LAYOUT(4, 5), TMVB_LAYOUT(4, 6), TMVB_LAYOUT(4, 7), TMVB_LAYOUT(4, 8),
+    TMVB_LAYOUT(8, 5), TMVB_LAYOUT(8, 6), TMVB_LAYOUT(8, 7), TMVB_LAYOUT(8, 8),
+};
+
+// row stride (in floats) of the shared-memory tile for CH 16-byte chunks per row
+static int lda_row_stride(int CH, int lpt)
 {
-    return elbo ? (EstepFn)lda_estep_kernel<NQ, true> : (EstepFn)lda_estep_kernel<NQ, false>;
+    int r = CH;
+    if (lpt < 8)
+        while (r % (2 * lpt) != lpt) r++;
+    return 4 * r;
 }
 
-// NQ = ceil(K_ld / 32): 16-byte chunks per lane in the token phase == topics per lane in the K phase
-static EstepFn estep_dispatch(int nq, bool elbo)
+// Pick the lane layout for K: minimise (estimated warp-instructions per token) x sqrt(shared-memory inflation)
+static const Layout *lda_pick_layout(int K_ld, int *RS_out)
 {
-    switch (nq) {
-    case 1: return estep_fn<1>(elbo);
-    case 2: return estep_fn<2>(elbo);
-    case 3: return estep_fn<3>(elbo);
-    case 4: return estep_fn<4>(elbo);
-    case 5: return estep_fn<5>(elbo);
-    case 6: return estep_fn<6>(elbo);
-    case 7: return estep_fn<7>(elbo);
-    case 8: return estep_fn<8>(elbo);
+    const int CH = K_ld / 4;
+    const Layout *best = nullptr;
+    double best_cost = 0.0;
+    const int force_lpt = getenv("TMVB_LDA_LPT") ? atoi(getenv("TMVB_LDA_LPT")) : 0;
+    for (const Layout &l : kLayouts) {
+        if (l.lpt * l.cpl < CH) continue;
+        if (force_lpt && l.lpt != force_lpt) continue;
+        const int S = 32 / l.lpt, RS = lda_row_stride(CH, l.lpt);
+        const double instr_tok = (l.cpl * 9.0 + 2.0 * log2((double)l.lpt) + 12.0) / S;
+        const double fixed = (l.cpl + ((K_ld + 31) / 32) * 2.0 * S) / 80.0;
+        const double cost = (instr_tok + fixed) * sqrt((double)RS / K_ld);
+        if (!best || cost < best_cost - 1e-9) {
+            best = &l;
+            best_cost = cost;
+            *RS_out = RS;
+        }
     }
-    return nullptr;
+    return best;
 }
 
 }  // namespace tmvb
@@ -540,7 +560,8 @@ struct tmvb_lda_s {
     cudaStream_t stream = nullptr;
     bool own_stream = false;
     int64_t K = 0, M = 0, V = 0, nnz = 0;
-    int nq = 0, K_ld = 0;
+    int K_ld = 0, RS = 0;
+    const tmvb::Layout *layout = nullptr;
     bool corpus_set = false, params_set = false;
     // corpus
     long long *d_doc_off = nullptr, *d_src_off = nullptr;
@@ -587,6 +608,7 @@ LdaDev dev_view(tmvb_lda_t h)
     LdaDev p;
     p.K = (int)h->K;
     p.K_ld = h->K_ld;
+    p.RS = h->RS;
     p.V = (int)h->V;
     p.M = h->M;
     p.beta = h->d_beta[h->cur];
@@ -626,10 +648,9 @@ int plan_buckets(tmvb_lda_t h, const std::vector<int> &len_sorted)
     h->buckets.clear();
     const int M = (int)len_sorted.size();
     if (M == 0) return 0;
-    const int force_w = env_int("TMVB_LDA_WARPS", 0);
     size_t budget = h->smem_optin;
     int cap_max = 16;
-    while (lda_smem_bytes(h->K_ld, cap_max + 16, 8) <= budget) cap_max += 16;
+    while (lda_smem_bytes(h->RS, h->layout->lpt, cap_max + 16) <= budget) cap_max += 16;
     std::vector<int> caps;
     for (int c = 16; c < cap_max; c = (c < 128) ? c + 16 : (c < 256 ? c + 32 : c + c / 4 / 16 * 16)) caps.push_back(c);
     caps.push_back(cap_max);
@@ -644,8 +665,8 @@ int plan_buckets(tmvb_lda_t h, const std::vector<int> &len_sorted)
         b.doc_end = end;
         b.cap = std::min(caps[ci], std::max(16, (len_sorted[begin] + 15) / 16 * 16));
         if (b.cap > cap_max) b.cap = cap_max;
-        b.warps = force_w > 0 ? force_w : (b.cap <= 32 ? 1 : (b.cap <= 64 ? 2 : (b.cap <= 256 ? 4 : 8)));
-        b.smem = lda_smem_bytes(h->K_ld, b.cap, b.warps);
+        b.warps = 1;
+        b.smem = lda_smem_bytes(h->RS, h->layout->lpt, b.cap);
         b.grid = 0;
         h->buckets.push_back(b);
         begin = end;
@@ -702,7 +723,9 @@ int tmvb_lda_create(tmvb_lda_t *out, int64_t K, int64_t M, int64_t V, int device
     TMVB_CHECK_ARG(M < (1ll << 31) && V < (1ll << 31), "M and V must fit in int32");
     if (K > 256) return fail(-2, "K=%lld is not supported (K <= 256)", (long long)K);
     const int K_ld = (int)((K + 7) / 8 * 8);
-    const int nq = (K_ld + 31) / 32;
+    int RS = 0;
+    const Layout *layout = lda_pick_layout(K_ld, &RS);
+    if (!layout) return fail(-2, "internal: no lane layout for K=%lld", (long long)K);
     int ndev = 0;
     TMVB_TRY(tmvb_device_count(&ndev));
     if (ndev == 0) return fail(-3, "no CUDA device: libtmvb has no CPU fallback");
@@ -720,7 +743,8 @@ int tmvb_lda_create(tmvb_lda_t *out, int64_t K, int64_t M, int64_t V, int device
     h->K = K;
     h->M = M;
     h->V = V;
-    h->nq = nq;
+    h->layout = layout;
+    h->RS = RS;
     h->K_ld = K_ld;
     if (stream) {
         h->stream = (cudaStream_t)stream;
@@ -759,7 +783,7 @@ int tmvb_lda_create(tmvb_lda_t *out, int64_t K, int64_t M, int64_t V, int device
     h->h_alpha.assign(K, 1.0);
     // opt in to the large dynamic shared memory for both instantiations of this K
     for (int eb = 0; eb < 2; eb++) {
-        EstepFn fn = estep_dispatch(nq, eb != 0);
+        EstepFn fn = layout->fn[eb];
         e = cudaFuncSetAttribute((const void *)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_optin);
         if (e != cudaSuccess) {
             free_all(h);
@@ -941,7 +965,7 @@ int tmvb_lda_estep(tmvb_lda_t h, int viter, float vtol, int want_elbo)
     TMVB_CUDA(cudaMemsetAsync(h->d_small, 0, (h->K_ld + 2) * 8, h->stream));
     TMVB_CUDA(cudaMemsetAsync(h->d_counters, 0, 64 * 4, h->stream));
     h->h_alpha_estep = h->h_alpha;
-    EstepFn fn = estep_dispatch(h->nq, want_elbo != 0);
+    EstepFn fn = h->layout->fn[want_elbo != 0];
     for (size_t bi = 0; bi < h->buckets.size(); bi++) {
         Bucket &b = h->buckets[bi];
         const int threads = 32 * b.warps;
