@@ -82,7 +82,7 @@ struct PsiLg {
     float psi, lg;
 };
 
-template <bool WANT_LG>
+template <bool WANT_LG, bool FAST = false>
 __device__ __forceinline__ PsiLg psi_lgamma(float x)
 {
     float P = 1.0f, D = 0.0f, y = x;
@@ -98,12 +98,12 @@ __device__ __forceinline__ PsiLg psi_lgamma(float x)
         }
         y = x + 6.0f;
     }
-    float ly = logf(y);
+    float ly = FAST ? __logf(y) : logf(y);
     float t = __frcp_rn(y), t2 = t * t;
     PsiLg r;
     float ser = t2 * (8.3333333333e-2f - t2 * (8.3333333333e-3f - t2 * 3.9682539683e-3f));
     r.psi = ly - 0.5f * t - ser;
-    if (x < 6.0f) r.psi -= D / P;
+    if (x < 6.0f) r.psi -= FAST ? __fdividef(D, P) : D / P;
     r.lg = 0.0f;
     if (WANT_LG) {
         float sl = t * (8.3333333333e-2f - t2 * (2.7777777778e-3f - t2 * 7.9365079365e-4f));
@@ -120,6 +120,47 @@ __device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src)
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
+
+// ---- TMA bulk copy (cp.async.bulk, SASS UBLKCP) + mbarrier transaction tracking ------------
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count)
+{
+    unsigned s = (unsigned)__cvta_generic_to_shared(bar);
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(s), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(unsigned long long *bar, unsigned bytes)
+{
+    unsigned s = (unsigned)__cvta_generic_to_shared(bar);
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(s), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity)
+{
+    unsigned s = (unsigned)__cvta_generic_to_shared(bar);
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra.uni WAIT_DONE;\n"
+        "bra.uni WAIT_LOOP;\n"
+        "WAIT_DONE:\n"
+        "}\n" ::"r"(s), "r"(parity)
+        : "memory");
+}
+// order earlier generic-proxy accesses to shared memory before later async-proxy (TMA) writes
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
+// one contiguous global -> shared copy of `bytes` (multiple of 16; both addresses 16-byte aligned)
+__device__ __forceinline__ void bulk_g2s(void *smem_dst, const void *gmem_src, unsigned bytes, unsigned long long *bar)
+{
+    unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst), b = (unsigned)__cvta_generic_to_shared(bar);
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(d), "l"(gmem_src),
+                 "r"(bytes), "r"(b)
+                 : "memory");
+}
+
+// fast fp32 transcendental forms used inside the per-sweep K phase
+__device__ __forceinline__ float fast_log(float x) { return __logf(x); }   // MUFU.LG2 * ln2
+__device__ __forceinline__ float fast_exp(float x) { return __expf(x); }   // MUFU.EX2(x * log2e)
 
 // fire-and-forget fp32 add into global memory (RED.E.ADD.F32)
 __device__ __forceinline__ void red_add(float *addr, float v)

@@ -36,6 +36,7 @@ struct LdaDev {
     double *small;
     int viter;
     float vtol;
+    int stage_bulk;  // 1: TMA bulk row copies (UBLKCP), 0: 16-byte cp.async (LDGSTS)
 };
 
 // Thread mapping of the E-step: ONE WARP PER DOCUMENT (a CTA is a single warp; the grid is
@@ -54,6 +55,7 @@ __host__ __device__ inline size_t lda_smem_bytes(int RS, int LPT, int cap)
     size_t b = (size_t)cap * RS * 4 + (size_t)cap * 8;  // tile + counts + terms
     b += (size_t)(32 / LPT) * RS * 4;                   // gs: per-stream partial K-vectors
     b += (size_t)RS * 4;                                // e_s: exp(Elogtheta)
+    b += 16;                                            // mbarrier of the TMA staging
     return b;
 }
 
@@ -164,7 +166,8 @@ __global__ void __launch_bounds__(32) lda_estep_kernel(const LdaDev p, int doc_b
     const int K = p.K, K_ld = p.K_ld, CH = K_ld >> 2, RS = p.RS;
     const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
 
-    float *tile = reinterpret_cast<float *>(smem_raw);
+    unsigned long long *mbar = reinterpret_cast<unsigned long long *>(smem_raw);
+    float *tile = reinterpret_cast<float *>(smem_raw + 16);
     float *gs = tile + (size_t)cap * RS;                       // [S][RS]
     float *e_s = gs + (size_t)S * RS;                          // [RS]
     float *cnt_s = e_s + RS;                                   // [cap]
@@ -173,17 +176,25 @@ __global__ void __launch_bounds__(32) lda_estep_kernel(const LdaDev p, int doc_b
     // K-phase state: topics i = lane + 32 r
     float alpha_k[R], Eold_k[R], Enew_k[R], e_k[R], gam_k[R];
     double esum_k[R];
+    float asum = 0.0f;
 #pragma unroll
     for (int r = 0; r < R; r++) {
         const int i = lane + 32 * r;
         alpha_k[r] = (i < K) ? p.alpha[i] : 0.0f;
+        asum += alpha_k[r];
         esum_k[r] = 0.0;
         Enew_k[r] = gam_k[r] = Eold_k[r] = e_k[r] = 0.0f;
     }
-    // a free K-phase slot (lane 31 of the last r) evaluates digamma(sum gamma) alongside the others
-    const bool spare = (32 * R - 1 >= K);
+    asum = warp_sum(asum);
+    // convergence test in fixed point: sum_i (dE_i)^2 * (2^20 / vtol^2) < 2^20, summed with one REDUX
+    const float dscale = (p.vtol > 0.0f) ? 1048576.0f / (p.vtol * p.vtol) : 0.0f;
     double elbo_thr = 0.0;
     unsigned long long sweeps_thr = 0;
+    unsigned phase = 0;
+    if (p.stage_bulk) {
+        if (lane == 0) mbar_init(mbar, 1);
+        __syncwarp();
+    }
 
     for (;;) {
         int d = 0;
@@ -196,19 +207,33 @@ __global__ void __launch_bounds__(32) lda_estep_kernel(const LdaDev p, int doc_b
         const bool ovf = Nd > cap;
         const int rounds = (Nd + S - 1) / S;
 
-        // stage the document: term ids + counts, then its K x N_d slab of beta (16-byte cp.async
-        // per lane; a term row is K_ld*4 contiguous bytes in HBM/L2)
+        // stage the document: term ids + counts, then its K x N_d slab of beta -- one TMA bulk copy
+        // per term row (a row is K_ld*4 contiguous bytes in HBM/L2), completion tracked by an mbarrier
         __syncwarp();
-        for (int n = lane; n < ns; n += 32) {
-            term_s[n] = p.terms[o + n];
-            cnt_s[n] = p.counts[o + n];
+        float csum = 0.0f;
+        for (int n = lane; n < Nd; n += 32) {
+            const float c = p.counts[o + n];
+            csum += c;
+            if (n < ns) {
+                term_s[n] = p.terms[o + n];
+                cnt_s[n] = c;
+            }
         }
-        __syncwarp();
-        for (int c = lane; c < ns * CH; c += 32) {
-            const int n = c / CH, q = c - n * CH;
-            cp_async16(tile + n * RS + 4 * q, p.beta + (size_t)term_s[n] * K_ld + 4 * q);
+        if (p.stage_bulk) {
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_expect_tx(mbar, (unsigned)(ns * K_ld * 4));
+            __syncwarp();
+            for (int n = lane; n < ns; n += 32)
+                bulk_g2s(tile + n * RS, p.beta + (size_t)term_s[n] * K_ld, (unsigned)(K_ld * 4), mbar);
+        } else {
+            __syncwarp();
+            for (int c = lane; c < ns * CH; c += 32) {
+                const int n = c / CH, q = c - n * CH;
+                cp_async16(tile + n * RS + 4 * q, p.beta + (size_t)term_s[n] * K_ld + 4 * q);
+            }
+            cp_async_commit();
         }
-        cp_async_commit();
 #pragma unroll
         for (int r = 0; r < R; r++) {
             const int i = lane + 32 * r;
@@ -216,11 +241,19 @@ __global__ void __launch_bounds__(32) lda_estep_kernel(const LdaDev p, int doc_b
             e_k[r] = (i < K) ? expf(Eold_k[r]) : 0.0f;
             if (i < K_ld) e_s[i] = e_k[r];
         }
-        cp_async_wait_all();
+        // sum(gamma_d) = sum(alpha) + sum_n c_n + K*EPS whatever phi is (each phi column sums to one),
+        // so digamma(sum gamma) (LDA.jl:138) is a per-document constant
+        const float gsum = (asum + warp_sum(csum)) + (float)K * TMVB_EPS;
+        const float psi_sum = psi_lgamma<false>(gsum).psi;
+        if (p.stage_bulk) {
+            mbar_wait(mbar, phase);
+            phase ^= 1u;
+        } else {
+            cp_async_wait_all();
+        }
         __syncwarp();
 
         float4 e[CPL];
-        float gsum = 0.0f;
         int v = 0;
         for (;;) {
             // ---- token phase
@@ -242,46 +275,44 @@ __global__ void __launch_bounds__(32) lda_estep_kernel(const LdaDev p, int doc_b
             __syncwarp();
 
             // ---- K phase: update_gamma! (LDA.jl:143-146), update_Elogtheta! (LDA.jl:136-139)
-            float part = 0.0f;
-#pragma unroll
-            for (int r = 0; r < R; r++) {
-                const int i = lane + 32 * r;
-                float gi = 0.0f;
-                if (i < K) {
-#pragma unroll
-                    for (int w = 0; w < S; w++) gi += gs[w * RS + i];
-                }
-                // gamma = EPS + (alpha + phi*counts),   phi*counts = e .* g + eps * sum_n t_n
-                gam_k[r] = (i < K) ? (alpha_k[r] + fmaf(e_k[r], gi, TMVB_EPS * tt)) + TMVB_EPS : 1.0f;
-                part += (i < K) ? gam_k[r] : 0.0f;
-            }
-            gsum = warp_sum(part);
-            float x[R], ps[R];
-#pragma unroll
-            for (int r = 0; r < R; r++) x[r] = gam_k[r];
-            if (spare && lane == 31) x[R - 1] = gsum;
-#pragma unroll
-            for (int r = 0; r < R; r++) ps[r] = psi_lgamma<false>(x[r]).psi;
-            const float psi_sum = spare ? __shfl_sync(0xffffffffu, ps[R - 1], 31) : psi_lgamma<false>(gsum).psi;
             float dpart = 0.0f;
 #pragma unroll
             for (int r = 0; r < R; r++) {
                 const int i = lane + 32 * r;
-                Enew_k[r] = ps[r] - psi_sum;
+                float g0 = 0.0f, g1 = 0.0f, g2 = 0.0f, g3 = 0.0f;
+                if (i < K) {
+                    if (S >= 4) {
+#pragma unroll
+                        for (int w = 0; w < S; w += 4) {
+                            g0 += gs[w * RS + i];
+                            g1 += gs[(w + 1) * RS + i];
+                            g2 += gs[(w + 2) * RS + i];
+                            g3 += gs[(w + 3) * RS + i];
+                        }
+                    } else {
+#pragma unroll
+                        for (int w = 0; w < S; w++) g0 += gs[w * RS + i];
+                    }
+                }
+                const float gi = (g0 + g1) + (g2 + g3);
+                // gamma = EPS + (alpha + phi*counts),   phi*counts = e .* g + eps * sum_n t_n
+                gam_k[r] = (i < K) ? (alpha_k[r] + fmaf(e_k[r], gi, TMVB_EPS * tt)) + TMVB_EPS : 1.0f;
+                Enew_k[r] = psi_lgamma<false, true>(gam_k[r]).psi - psi_sum;
                 if (i < K) {
                     const float df = Enew_k[r] - Eold_k[r];
                     dpart = fmaf(df, df, dpart);
                 }
             }
-            const float dist2 = warp_sum(dpart);
             v++;
             // LDA.jl:175: stop when ||Elogtheta - Elogtheta_old||_2 < vtol (or after viter sweeps)
-            if ((sqrtf(dist2) < p.vtol) || (v >= p.viter)) break;
+            if (v >= p.viter) break;
+            // per-lane clamp 2^26 keeps the 32-lane integer sum below 2^31
+            if (dscale > 0.0f && __reduce_add_sync(0xffffffffu, (unsigned)fminf(dpart * dscale, 67108864.0f)) < 1048576u) break;
 #pragma unroll
             for (int r = 0; r < R; r++) {
                 const int i = lane + 32 * r;
                 Eold_k[r] = Enew_k[r];
-                e_k[r] = (i < K) ? expf(Enew_k[r]) : 0.0f;
+                e_k[r] = (i < K) ? fast_exp(Enew_k[r]) : 0.0f;
                 if (i < K_ld) e_s[i] = e_k[r];
             }
             __syncwarp();
@@ -584,6 +615,11 @@ struct tmvb_lda_s {
     size_t scratch_bytes = 0;
     double *h_pinned = nullptr;   // small pinned read-back buffer
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    // bucket launches are spread over the main stream + aux streams so that their tails overlap
+    static constexpr int kAux = 3;
+    cudaStream_t aux[kAux] = {nullptr, nullptr, nullptr};
+    cudaEvent_t ev_fork = nullptr, ev_join[kAux] = {nullptr, nullptr, nullptr};
+    int n_streams = 1;
     bool estep_timed = false, mstep_timed = false, elbo_valid = false;
     tmvb_stats st{};
 };
@@ -601,6 +637,12 @@ int ensure_scratch(tmvb_lda_t h, size_t bytes)
     TMVB_CUDA(cudaMalloc(&h->d_scratch, bytes));
     h->scratch_bytes = bytes;
     return 0;
+}
+
+int env_int(const char *name, int dflt)
+{
+    const char *s = getenv(name);
+    return (s && *s) ? atoi(s) : dflt;
 }
 
 LdaDev dev_view(tmvb_lda_t h)
@@ -623,6 +665,7 @@ LdaDev dev_view(tmvb_lda_t h)
     p.small = h->d_small;
     p.viter = 0;
     p.vtol = 0.f;
+    p.stage_bulk = env_int("TMVB_LDA_STAGE_BULK", 1);
     return p;
 }
 
@@ -633,12 +676,6 @@ int grid_for(long long work, int block, int n_sm)
     if (g > cap) g = cap;
     if (g < 1) g = 1;
     return (int)g;
-}
-
-int env_int(const char *name, int dflt)
-{
-    const char *s = getenv(name);
-    return (s && *s) ? atoi(s) : dflt;
 }
 
 // Split the length-sorted documents into launches whose shared-memory tile capacity ("cap", in
@@ -696,6 +733,11 @@ int free_all(tmvb_lda_t h)
     if (h->h_pinned) cudaFreeHost(h->h_pinned);
     for (auto &e : h->ev)
         if (e) cudaEventDestroy(e);
+    for (auto &a : h->aux)
+        if (a) cudaStreamDestroy(a);
+    for (auto &e : h->ev_join)
+        if (e) cudaEventDestroy(e);
+    if (h->ev_fork) cudaEventDestroy(h->ev_fork);
     if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
     return 0;
 }
@@ -775,6 +817,12 @@ int tmvb_lda_create(tmvb_lda_t *out, int64_t K, int64_t M, int64_t V, int device
     if (e == cudaSuccess) e = cudaMallocHost((void **)&h->h_pinned, (3 * h->K_ld + 8) * 8);
     for (auto &evx : h->ev)
         if (e == cudaSuccess) e = cudaEventCreate(&evx);
+    h->n_streams = std::min(1 + tmvb_lda_s::kAux, std::max(1, env_int("TMVB_LDA_STREAMS", 4)));
+    for (int a = 0; a + 1 < h->n_streams; a++) {
+        if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->aux[a], cudaStreamNonBlocking);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_join[a], cudaEventDisableTiming);
+    }
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming);
     if (e != cudaSuccess) {
         free_all(h);
         delete h;
@@ -966,6 +1014,11 @@ int tmvb_lda_estep(tmvb_lda_t h, int viter, float vtol, int want_elbo)
     TMVB_CUDA(cudaMemsetAsync(h->d_counters, 0, 64 * 4, h->stream));
     h->h_alpha_estep = h->h_alpha;
     EstepFn fn = h->layout->fn[want_elbo != 0];
+    const int ns = (h->buckets.size() > 1) ? h->n_streams : 1;
+    if (ns > 1) {
+        TMVB_CUDA(cudaEventRecord(h->ev_fork, h->stream));
+        for (int a = 0; a + 1 < ns; a++) TMVB_CUDA(cudaStreamWaitEvent(h->aux[a], h->ev_fork, 0));
+    }
     for (size_t bi = 0; bi < h->buckets.size(); bi++) {
         Bucket &b = h->buckets[bi];
         const int threads = 32 * b.warps;
@@ -978,8 +1031,13 @@ int tmvb_lda_estep(tmvb_lda_t h, int viter, float vtol, int want_elbo)
         void *args[] = {(void *)&p, (void *)&b.doc_begin, (void *)&b.doc_end, (void *)&b.cap, (void *)nullptr};
         int *counter = h->d_counters + bi;
         args[4] = (void *)&counter;
-        TMVB_CUDA(cudaLaunchKernel((const void *)fn, dim3(b.grid), dim3(threads), args, b.smem, h->stream));
+        cudaStream_t st = (bi % ns == 0) ? h->stream : h->aux[bi % ns - 1];
+        TMVB_CUDA(cudaLaunchKernel((const void *)fn, dim3(b.grid), dim3(threads), args, b.smem, st));
         h->st.kernel_launches++;
+    }
+    for (int a = 0; a + 1 < ns; a++) {
+        TMVB_CUDA(cudaEventRecord(h->ev_join[a], h->aux[a]));
+        TMVB_CUDA(cudaStreamWaitEvent(h->stream, h->ev_join[a], 0));
     }
     TMVB_CUDA(cudaEventRecord(h->ev[1], h->stream));
     h->estep_timed = true;
