@@ -47,6 +47,9 @@ int tmvb_version(void);
 const char *tmvb_last_error(void);
 /* number of visible CUDA devices (0 and an error code when there is none) */
 int tmvb_device_count(int *count);
+/* page-locked host memory for the caller's arrays (update_buffer!/update_host! then run at PCIe speed) */
+int tmvb_alloc_pinned(void **ptr, int64_t bytes);
+int tmvb_free_pinned(void *ptr);
 
 /* ------------------------------------------------------------------ LDA ------------------ */
 
@@ -104,6 +107,10 @@ int tmvb_lda_download(tmvb_lda_t h, float *alpha, float *beta, float *Elogtheta,
 int tmvb_lda_download_old(tmvb_lda_t h, float *beta_old, float *Elogtheta_old);
 /* phi of every document, K x sumN column-major, original token order (modelutils.jl:515-516) */
 int tmvb_lda_materialize_phi(tmvb_lda_t h, float *phi);
+
+/* model.topics = [reverse(sortperm(vec(beta[i,:]))) for i in 1:K] (gpuLDA.jl:374), ranked on the device.
+ * topics[i*V + r] = 1-based term id of rank r in topic i (int32, K*V). */
+int tmvb_lda_topics(tmvb_lda_t h, int32_t *topics);
 
 int tmvb_lda_sync(tmvb_lda_t h);
 int tmvb_lda_get_stats(tmvb_lda_t h, tmvb_stats *out);

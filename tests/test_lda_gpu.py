@@ -138,6 +138,15 @@ def test_argument_errors(tm):
     m.alpha = np.array([1.0, -1.0, 1.0], dtype=np.float32)
     with pytest.raises(tm.TopicModelError):
         tm.train(m, iter=1)
+    # element-wise invariants are checked on the device copy (modelutils.jl:264-273)
+    m3 = tm.gpuLDA(tm.Corpus.from_csr(c), 3, seed=0)
+    m3.gamma[1, 2] = 0.0
+    with pytest.raises(tm.TopicModelError, match="gamma must be positive"):
+        tm.train(m3, iter=1, printelbo=False)
+    m3 = tm.gpuLDA(tm.Corpus.from_csr(c), 3, seed=0)
+    m3.Elogtheta[0, 0] = np.nan
+    with pytest.raises(tm.TopicModelError, match="Elogtheta must be finite"):
+        tm.train(m3, iter=1, printelbo=False)
     # out-of-range term id is rejected by the library
     bad = tm.synth.CSR(1, 5, np.array([0, 2], np.int64), np.array([1, 7], np.int64), np.array([1, 1], np.int64))
     m2 = tm.gpuLDA(tm.Corpus.from_csr(bad), 2)
@@ -159,3 +168,15 @@ def test_nsf_shaped_full_size_parity(tm, orc):
     assert np.all(rel < ELBO_RTOL)
     assert np.all(np.diff(trace[1:]) > 0)          # CAVI ascent after the first iteration
     tm.check_model(model)
+
+
+def test_topics_ranked_on_device(tm):
+    """model.topics == [reverse(sortperm(beta[i,:]))] (gpuLDA.jl:374), 1-based, ties resolved like Julia's stable sort."""
+    c = tm.synth.gencorp_lda(M=80, V=400, K=4, seed=9)
+    K = 6
+    model = tm.gpuLDA(tm.Corpus.from_csr(c), K, seed=3)
+    tm.train(model, iter=3, tol=0.0, printelbo=False)
+    assert len(model.topics) == K
+    for i in range(K):
+        want = np.argsort(model.beta[i, :], kind="stable")[::-1] + 1
+        np.testing.assert_array_equal(np.asarray(model.topics[i]), want)

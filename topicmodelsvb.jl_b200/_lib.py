@@ -70,6 +70,8 @@ SIGNATURES = {
     "tmvb_version": (C.c_int, []),
     "tmvb_last_error": (C.c_char_p, []),
     "tmvb_device_count": (C.c_int, [C.POINTER(C.c_int)]),
+    "tmvb_alloc_pinned": (C.c_int, [C.POINTER(_vp), C.c_int64]),
+    "tmvb_free_pinned": (C.c_int, [_vp]),
     "tmvb_lda_create": (C.c_int, [C.POINTER(_vp), C.c_int64, C.c_int64, C.c_int64, C.c_int, _vp]),
     "tmvb_lda_destroy": (C.c_int, [_vp]),
     "tmvb_lda_set_corpus": (C.c_int, [_vp, _vp, _vp, _vp]),
@@ -84,6 +86,7 @@ SIGNATURES = {
     "tmvb_lda_download": (C.c_int, [_vp, _vp, _vp, _vp, _vp]),
     "tmvb_lda_download_old": (C.c_int, [_vp, _vp, _vp]),
     "tmvb_lda_materialize_phi": (C.c_int, [_vp, _vp]),
+    "tmvb_lda_topics": (C.c_int, [_vp, _vp]),
     "tmvb_lda_sync": (C.c_int, [_vp]),
     "tmvb_lda_get_stats": (C.c_int, [_vp, C.POINTER(TmvbStats)]),
     "tmvb_lda_kld": (C.c_int, [_vp, C.POINTER(C.c_int64)]),
@@ -112,6 +115,8 @@ def check(rc: int):
     if rc == 0:
         return
     msg = load().tmvb_last_error().decode()
+    if rc == -5:   # a check_model invariant evaluated on the device
+        raise TopicModelError(msg)
     if rc < 0:
         raise ValueError(msg)
     raise TopicModelError("CUDA error %d: %s" % (rc, msg))
@@ -123,3 +128,27 @@ def ptr(a):
         return None
     assert a.flags["C_CONTIGUOUS"]
     return a.ctypes.data
+
+
+def pinned_empty(shape, dtype, order="C"):
+    """numpy array over page-locked host memory (tmvb_alloc_pinned); freed when the array is collected."""
+    import weakref
+
+    lib = load()
+    dtype = np.dtype(dtype)
+    shape = (shape,) if isinstance(shape, (int, np.integer)) else tuple(int(x) for x in shape)
+    nbytes = int(np.prod(shape, dtype=np.int64)) * dtype.itemsize
+    p = C.c_void_p()
+    check(lib.tmvb_alloc_pinned(C.byref(p), nbytes))
+    buf = (C.c_char * max(nbytes, 1)).from_address(p.value)
+    weakref.finalize(buf, lib.tmvb_free_pinned, p.value)
+    return np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape, dtype=np.int64))).reshape(shape, order=order)
+
+
+def pinned_copy(a, order=None):
+    a = np.asarray(a)
+    if order is None:
+        order = "F" if (a.ndim > 1 and a.flags["F_CONTIGUOUS"] and not a.flags["C_CONTIGUOUS"]) else "C"
+    out = pinned_empty(a.shape, a.dtype, order=order)
+    out[...] = a
+    return out

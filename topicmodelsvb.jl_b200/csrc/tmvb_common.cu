@@ -68,4 +68,18 @@ int tmvb_device_count(int *count)
     return 0;
 }
 
+int tmvb_alloc_pinned(void **ptr, int64_t bytes)
+{
+    TMVB_CHECK_ARG(ptr != nullptr && bytes >= 0, "bad pinned allocation request");
+    *ptr = nullptr;
+    TMVB_CUDA(cudaHostAlloc(ptr, (size_t)(bytes > 0 ? bytes : 1), cudaHostAllocDefault));
+    return 0;
+}
+
+int tmvb_free_pinned(void *ptr)
+{
+    if (ptr) TMVB_CUDA(cudaFreeHost(ptr));
+    return 0;
+}
+
 }  // extern "C"

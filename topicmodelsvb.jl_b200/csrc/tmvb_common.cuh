@@ -177,6 +177,10 @@ __device__ __forceinline__ void red_add_v4(float *addr, float a, float b, float 
 #endif  // __CUDACC__
 
 // ---------------------------------------------------------------- host fp64 special functions
+// rank the vocabulary per topic on the device (tmvb_sort.cu); out[i*V + r] = 1-based term id of rank r
+int topics_argsort(const float *d_mat, const float *d_scale, int K, int ld, int V, int *d_out, void **ws, size_t *ws_bytes,
+                   cudaStream_t stream, int n_sm);
+
 double h_digamma(double x);
 double h_trigamma(double x);
 

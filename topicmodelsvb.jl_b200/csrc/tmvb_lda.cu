@@ -37,6 +37,7 @@ struct LdaDev {
     int viter;
     float vtol;
     int stage_bulk;  // 1: TMA bulk row copies (UBLKCP), 0: 16-byte cp.async (LDGSTS)
+    int dbg;         // developer probes: bit0 skip the scatter, bit1 skip the final pass
 };
 
 // Thread mapping of the E-step: ONE WARP PER DOCUMENT (a CTA is a single warp; the grid is
@@ -141,7 +142,7 @@ __device__ __forceinline__ void lda_token_pass(const LdaDev &p, const float *til
                     // pad topics (i >= K) carry beta = e = 0: they get t*eps, which the M-step ignores
                     const float ux = fmaf(b[m].x, e[m].x, TMVB_EPS), uy = fmaf(b[m].y, e[m].y, TMVB_EPS);
                     const float uz = fmaf(b[m].z, e[m].z, TMVB_EPS), uw = fmaf(b[m].w, e[m].w, TMVB_EPS);
-                    red_add_v4(srow + 4 * LPT * m, t * ux, t * uy, t * uz, t * uw);
+                    if (!(p.dbg & 1)) red_add_v4(srow + 4 * LPT * m, t * ux, t * uy, t * uz, t * uw);
                     if (ELBO) {
                         a = fmaf(t * ux, __logf(ux), a);
                         if (i0 + 1 < p.K) a = fmaf(t * uy, __logf(uy), a);
@@ -319,7 +320,7 @@ __global__ void __launch_bounds__(32) lda_estep_kernel(const LdaDev p, int doc_b
         }
 
         // update_beta!(model, d) (LDA.jl:129-132): scatter the last phi, weighted by counts
-        {
+        if (!(p.dbg & 2)) {
             float4 g[CPL];
             float tsum = 0.0f, ent = 0.0f;
             if (!ovf)
@@ -427,10 +428,13 @@ __device__ inline double d_digamma(double x)
 // update_elbo! exactly as the CPU model states it (LDA.jl:50-93): phi rebuilt from beta_old and
 // Elogtheta_old, the five expectations evaluated with alpha, beta, gamma, Elogtheta.  fp64
 // arithmetic on the fp32 device state; one warp per document, lanes over topics.
+template <typename real>
 __global__ void lda_elbo_kernel(const LdaDev p, const float *__restrict__ beta_old, double lg_alpha_term, double *out)
 {
+    constexpr bool F64 = sizeof(real) == 8;
     const int lane = threadIdx.x & 31;
     const int wpb = blockDim.x >> 5;
+    const real eps = (real)TMVB_EPS_D;
     double acc = 0.0;
     for (long long d = (long long)blockIdx.x * wpb + (threadIdx.x >> 5); d < p.M; d += (long long)gridDim.x * wpb) {
         const long long o = p.doc_off[d];
@@ -440,23 +444,33 @@ __global__ void lda_elbo_kernel(const LdaDev p, const float *__restrict__ beta_o
         for (int i = lane; i < p.K; i += 32) {
             const double g = gm[i], E = En[i];
             g0 += g;
-            dacc += ((double)p.alpha[i] - 1.0) * E + lgamma(g) - (g - 1.0) * d_digamma(g);
+            if (F64) {
+                dacc += ((double)p.alpha[i] - 1.0) * E + lgamma(g) - (g - 1.0) * d_digamma(g);
+            } else {
+                const PsiLg pl = psi_lgamma<true>((float)g);
+                dacc += ((double)p.alpha[i] - 1.0) * E + (double)pl.lg - (g - 1.0) * (double)pl.psi;
+            }
         }
         g0 = warp_sum_d(g0);
+        real tacc = 0;
         for (int n = 0; n < Nd; n++) {
             const int term = p.terms[o + n];
-            const double c = p.counts[o + n];
+            const real c = p.counts[o + n];
             const float *bo = beta_old + (size_t)term * p.K_ld, *bn = p.beta + (size_t)term * p.K_ld;
-            double s = 0.0;
-            for (int i = lane; i < p.K; i += 32) s += TMVB_EPS_D + (double)bo[i] * exp((double)Eo[i]);
-            s = warp_sum_d(s);
-            double a = 0.0;
+            real s = 0;
+            for (int i = lane; i < p.K; i += 32) s += eps + (real)bo[i] * (F64 ? (real)exp((double)Eo[i]) : (real)expf(Eo[i]));
+            s = F64 ? (real)warp_sum_d((double)s) : (real)warp_sum((float)s);
+            real a = 0;
             for (int i = lane; i < p.K; i += 32) {
-                const double ph = (TMVB_EPS_D + (double)bo[i] * exp((double)Eo[i])) / s;
-                a += ph * ((double)En[i] + log((double)bn[i] + TMVB_EPS_D) - (ph > 0.0 ? log(ph) : 0.0));
+                const real u = eps + (real)bo[i] * (F64 ? (real)exp((double)Eo[i]) : (real)expf(Eo[i]));
+                const real ph = u / s;
+                const real lb = F64 ? (real)log((double)bn[i] + TMVB_EPS_D) : (real)logf(bn[i] + TMVB_EPS);
+                const real lp = F64 ? (real)(ph > 0 ? log((double)ph) : 0.0) : (real)(ph > 0 ? logf((float)ph) : 0.f);
+                a += ph * ((real)En[i] + lb - lp);
             }
-            dacc += c * a;
+            if (F64) dacc += (double)(c * a); else tacc += c * a;
         }
+        dacc += (double)tacc;
         dacc = warp_sum_d(dacc);
         if (lane == 0) {
             double ent = 0.0;
@@ -509,6 +523,19 @@ __global__ void unpad_rows_kernel(const float *__restrict__ src, float *__restri
         dst[dr * K + i] = src[r * K_ld + i];
     }
 }
+// check_model(::gpuLDA) invariants that need a pass over the data (modelutils.jl:264-273), evaluated on
+// the device copy: bit0 non-finite, bit1 sign violation (what=0: beta >= 0; 1: Elogtheta <= 0; 2: gamma > 0)
+__global__ void validate_kernel(const float *__restrict__ x, long long n, int what, int *__restrict__ err)
+{
+    int e = 0;
+    for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < n; q += (long long)gridDim.x * blockDim.x) {
+        const float v = x[q];
+        if (!isfinite(v)) e |= 1;
+        if ((what == 0 && v < 0.f) || (what == 1 && v > 0.f) || (what == 2 && !(v > 0.f))) e |= 2;
+    }
+    if (e) atomicOr(err, e << (2 * what));
+}
+
 // CSR re-layout: internal document p takes the tokens of caller document perm[p]; Int64 -> int32 / float
 __global__ void pack_corpus_kernel(const long long *__restrict__ terms64, const long long *__restrict__ counts64,
                                    const long long *__restrict__ src_off, const long long *__restrict__ dst_off, long long M,
@@ -591,6 +618,7 @@ struct tmvb_lda_s {
     cudaStream_t stream = nullptr;
     bool own_stream = false;
     int64_t K = 0, M = 0, V = 0, nnz = 0;
+    size_t nnz_cap = 0;
     int K_ld = 0, RS = 0;
     const tmvb::Layout *layout = nullptr;
     bool corpus_set = false, params_set = false;
@@ -613,6 +641,8 @@ struct tmvb_lda_s {
     // scratch
     void *d_scratch = nullptr;
     size_t scratch_bytes = 0;
+    void *d_sort_ws = nullptr;
+    size_t sort_ws_bytes = 0;
     double *h_pinned = nullptr;   // small pinned read-back buffer
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     // bucket launches are spread over the main stream + aux streams so that their tails overlap
@@ -666,6 +696,7 @@ LdaDev dev_view(tmvb_lda_t h)
     p.viter = 0;
     p.vtol = 0.f;
     p.stage_bulk = env_int("TMVB_LDA_STAGE_BULK", 1);
+    p.dbg = env_int("TMVB_LDA_DBG", 0);
     return p;
 }
 
@@ -730,6 +761,7 @@ int free_all(tmvb_lda_t h)
     cudaFree(h->d_local);
     cudaFree(h->d_counters);
     cudaFree(h->d_scratch);
+    cudaFree(h->d_sort_ws);
     if (h->h_pinned) cudaFreeHost(h->h_pinned);
     for (auto &e : h->ev)
         if (e) cudaEventDestroy(e);
@@ -896,20 +928,22 @@ int tmvb_lda_set_corpus(tmvb_lda_t h, const int64_t *N_cumsum, const int64_t *te
     }
     TMVB_TRY(plan_buckets(h, len_sorted));
 
-    cudaFree(h->d_doc_off);
-    cudaFree(h->d_src_off);
-    cudaFree(h->d_terms);
-    cudaFree(h->d_counts);
-    cudaFree(h->d_perm);
-    h->d_doc_off = h->d_src_off = nullptr;
-    h->d_terms = h->d_perm = nullptr;
-    h->d_counts = nullptr;
     const size_t nz = (size_t)std::max<int64_t>(nnz, 1);
-    TMVB_CUDA(cudaMalloc((void **)&h->d_doc_off, (M + 1) * 8));
-    TMVB_CUDA(cudaMalloc((void **)&h->d_src_off, std::max<int64_t>(M, 1) * 8));
-    TMVB_CUDA(cudaMalloc((void **)&h->d_perm, std::max<int64_t>(M, 1) * 4));
-    TMVB_CUDA(cudaMalloc((void **)&h->d_terms, nz * 4));
-    TMVB_CUDA(cudaMalloc((void **)&h->d_counts, nz * 4));
+    if (!h->d_doc_off) {
+        TMVB_CUDA(cudaMalloc((void **)&h->d_doc_off, (M + 1) * 8));
+        TMVB_CUDA(cudaMalloc((void **)&h->d_src_off, std::max<int64_t>(M, 1) * 8));
+        TMVB_CUDA(cudaMalloc((void **)&h->d_perm, std::max<int64_t>(M, 1) * 4));
+    }
+    if (nz > h->nnz_cap) {  // token arrays are reused across calls while they fit
+        cudaFree(h->d_terms);
+        cudaFree(h->d_counts);
+        h->d_terms = nullptr;
+        h->d_counts = nullptr;
+        h->nnz_cap = 0;
+        TMVB_CUDA(cudaMalloc((void **)&h->d_terms, nz * 4));
+        TMVB_CUDA(cudaMalloc((void **)&h->d_counts, nz * 4));
+        h->nnz_cap = nz;
+    }
     TMVB_CUDA(cudaMemcpyAsync(h->d_doc_off, dst_off.data(), (M + 1) * 8, cudaMemcpyHostToDevice, h->stream));
     if (M > 0) {
         TMVB_CUDA(cudaMemcpyAsync(h->d_src_off, src_off.data(), M * 8, cudaMemcpyHostToDevice, h->stream));
@@ -965,6 +999,7 @@ int tmvb_lda_upload(tmvb_lda_t h, const float *alpha, const float *beta, const f
     if (beta && V > 0) {
         TMVB_TRY(ensure_scratch(h, (size_t)K * V * 4));
         TMVB_CUDA(cudaMemcpyAsync(h->d_scratch, beta, (size_t)K * V * 4, cudaMemcpyHostToDevice, h->stream));
+        validate_kernel<<<grid_for(K * V, 256, h->n_sm), 256, 0, h->stream>>>((const float *)h->d_scratch, K * V, 0, h->d_counters + 62);
         pad_rows_kernel<<<grid_for(V * h->K_ld, 256, h->n_sm), 256, 0, h->stream>>>((const float *)h->d_scratch, h->d_beta[h->cur], nullptr, V, (int)K, h->K_ld);
         TMVB_CUDA(cudaGetLastError());
         // beta_old = copy(beta)  (LDA.jl:36)
@@ -978,6 +1013,7 @@ int tmvb_lda_upload(tmvb_lda_t h, const float *alpha, const float *beta, const f
         TMVB_TRY(ensure_scratch(h, (size_t)K * M * 4));
         if (Elogtheta) {
             TMVB_CUDA(cudaMemcpyAsync(h->d_scratch, Elogtheta, (size_t)K * M * 4, cudaMemcpyHostToDevice, h->stream));
+            validate_kernel<<<grid_for(K * M, 256, h->n_sm), 256, 0, h->stream>>>((const float *)h->d_scratch, K * M, 1, h->d_counters + 62);
             pad_rows_kernel<<<grid_for(M * h->K_ld, 256, h->n_sm), 256, 0, h->stream>>>((const float *)h->d_scratch, h->d_Elogtheta, h->d_perm, M, (int)K, h->K_ld);
             TMVB_CUDA(cudaGetLastError());
             // Elogtheta_old = deepcopy(Elogtheta)  (LDA.jl:39)
@@ -987,13 +1023,23 @@ int tmvb_lda_upload(tmvb_lda_t h, const float *alpha, const float *beta, const f
         }
         if (gamma) {
             TMVB_CUDA(cudaMemcpyAsync(h->d_scratch, gamma, (size_t)K * M * 4, cudaMemcpyHostToDevice, h->stream));
+            validate_kernel<<<grid_for(K * M, 256, h->n_sm), 256, 0, h->stream>>>((const float *)h->d_scratch, K * M, 2, h->d_counters + 62);
             pad_rows_kernel<<<grid_for(M * h->K_ld, 256, h->n_sm), 256, 0, h->stream>>>((const float *)h->d_scratch, h->d_gamma, h->d_perm, M, (int)K, h->K_ld);
             TMVB_CUDA(cudaGetLastError());
             h->st.kernel_launches++;
             h->st.h2d_bytes += K * M * 4;
         }
     }
+    int verr = 0;
+    TMVB_CUDA(cudaMemcpyAsync(&verr, h->d_counters + 62, 4, cudaMemcpyDeviceToHost, h->stream));
     TMVB_CUDA(cudaStreamSynchronize(h->stream));
+    TMVB_CUDA(cudaMemsetAsync(h->d_counters + 62, 0, 4, h->stream));
+    // the messages of check_model(::gpuLDA), modelutils.jl:264-273
+    if (verr & 0x3) return fail(-5, "beta must be a right stochastic matrix.");
+    if (verr & 0x4) return fail(-5, "Elogtheta must be finite.");
+    if (verr & 0x8) return fail(-5, "Elogtheta must be nonpositive.");
+    if (verr & 0x10) return fail(-5, "gamma must be finite.");
+    if (verr & 0x20) return fail(-5, "gamma must be positive.");
     h->params_set = true;
     h->elbo_valid = false;
     return 0;
@@ -1141,7 +1187,7 @@ int tmvb_lda_update_alpha(tmvb_lda_t h, int64_t M_total, int niter, double ntol,
 int tmvb_lda_elbo(tmvb_lda_t h, int mode, int64_t M_total, double *elbo_docs, double *elbo_global)
 {
     TMVB_CHECK_ARG(h && elbo_docs && elbo_global, "NULL argument");
-    TMVB_CHECK_ARG(mode == 0 || mode == 1, "mode must be 0 or 1");
+    TMVB_CHECK_ARG(mode >= 0 && mode <= 2, "mode must be 0, 1 or 2");
     TMVB_CUDA(cudaSetDevice(h->device));
     const int K = (int)h->K, K_ld = h->K_ld;
     if (mode == 0) {
@@ -1165,7 +1211,10 @@ int tmvb_lda_elbo(tmvb_lda_t h, int mode, int64_t M_total, double *elbo_docs, do
     double *out = h->d_local + 2 * K_ld;
     TMVB_CUDA(cudaMemsetAsync(out, 0, 8, h->stream));
     if (h->M > 0) {
-        lda_elbo_kernel<<<grid_for(h->M * 32, 128, h->n_sm), 128, 0, h->stream>>>(p, h->d_beta[h->cur ^ 1], lg_alpha_term(h->h_alpha), out);
+        if (mode == 2)
+            lda_elbo_kernel<double><<<grid_for(h->M * 32, 128, h->n_sm), 128, 0, h->stream>>>(p, h->d_beta[h->cur ^ 1], lg_alpha_term(h->h_alpha), out);
+        else
+            lda_elbo_kernel<float><<<grid_for(h->M * 32, 128, h->n_sm), 128, 0, h->stream>>>(p, h->d_beta[h->cur ^ 1], lg_alpha_term(h->h_alpha), out);
         TMVB_CUDA(cudaGetLastError());
         h->st.kernel_launches++;
     }
@@ -1227,6 +1276,22 @@ int tmvb_lda_materialize_phi(tmvb_lda_t h, float *phi)
     TMVB_CUDA(cudaGetLastError());
     h->st.kernel_launches++;
     TMVB_CUDA(cudaMemcpyAsync(phi, h->d_scratch, bytes, cudaMemcpyDeviceToHost, h->stream));
+    TMVB_CUDA(cudaStreamSynchronize(h->stream));
+    h->st.d2h_bytes += bytes;
+    return 0;
+}
+
+int tmvb_lda_topics(tmvb_lda_t h, int32_t *topics)
+{
+    TMVB_CHECK_ARG(h && topics, "NULL argument");
+    TMVB_CUDA(cudaSetDevice(h->device));
+    if (h->V == 0) return 0;
+    const size_t bytes = (size_t)h->K * h->V * 4;
+    TMVB_TRY(ensure_scratch(h, bytes));
+    TMVB_TRY(topics_argsort(h->d_beta[h->cur], nullptr, (int)h->K, h->K_ld, (int)h->V, (int *)h->d_scratch, &h->d_sort_ws, &h->sort_ws_bytes,
+                            h->stream, h->n_sm));
+    h->st.kernel_launches += 3;
+    TMVB_CUDA(cudaMemcpyAsync(topics, h->d_scratch, bytes, cudaMemcpyDeviceToHost, h->stream));
     TMVB_CUDA(cudaStreamSynchronize(h->stream));
     h->st.d2h_bytes += bytes;
     return 0;

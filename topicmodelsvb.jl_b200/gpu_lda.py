@@ -40,7 +40,7 @@ class gpuLDA:
     """
 
     def __init__(self, corp: Corpus, K: int, seed: Optional[int] = None, device: int = -1,
-                 reducer: Optional[Reducer] = None, M_total: Optional[int] = None):
+                 reducer: Optional[Reducer] = None, M_total: Optional[int] = None, stream: Optional[int] = None):
         check_corp(corp)
         if not (isinstance(K, (int, np.integer)) and K > 0):
             raise ValueError("number of topics must be a positive integer.")  # gpuLDA.jl:47
@@ -67,15 +67,17 @@ class gpuLDA:
         self.reducer = reducer
         self.M_total = int(M_total) if M_total is not None else self.M
         self._device = device
+        self._stream = stream  # caller-owned cudaStream_t (int) or None
         self._h = None
         self._resident = False
+        self._pinned = None
 
     # ------------------------------------------------------------------ device plumbing ------
     def _handle(self):
         if self._h is None:
             lib = _lib.load()
             h = C.c_void_p()
-            stream = self.reducer.stream_ptr() if self.reducer is not None else None
+            stream = self._stream if self._stream is not None else (self.reducer.stream_ptr() if self.reducer is not None else None)
             _lib.check(lib.tmvb_lda_create(C.byref(h), self.K, self.M, self.V, self._device, stream))
             self._h = h
         return self._h
@@ -111,15 +113,37 @@ class gpuLDA:
             return
         lib, h = _lib.load(), self._handle()
         # fresh arrays, as the reference's update_host! rebinds the fields (never write through to caller arrays)
+        # page-locked staging arrays (D2H at PCIe speed), allocated once per model: the fields are live
+        # views of these buffers and are overwritten by the next update_host! -- copy to keep a snapshot
+        if self._pinned is None:
+            pe = _lib.pinned_empty
+            self._pinned = dict(beta=pe((self.K, self.V), np.float32, order="F"), beta_old=pe((self.K, self.V), np.float32, order="F"),
+                                Elogtheta=pe((self.K, self.M), np.float32, order="F"),
+                                Elogtheta_old=pe((self.K, self.M), np.float32, order="F"),
+                                gamma=pe((self.K, self.M), np.float32, order="F"), topics=pe((self.K, self.V), np.int32))
+        pb = self._pinned
         self.alpha = np.empty(self.K, np.float32)
-        self.beta, self.beta_old = (np.empty((self.K, self.V), np.float32, order="F") for _ in range(2))
-        self.Elogtheta, self.Elogtheta_old, self.gamma = (np.empty((self.K, self.M), np.float32, order="F") for _ in range(3))
+        self.beta, self.beta_old, self.Elogtheta, self.Elogtheta_old, self.gamma = (
+            pb["beta"], pb["beta_old"], pb["Elogtheta"], pb["Elogtheta_old"], pb["gamma"])
         _lib.check(lib.tmvb_lda_download(h, _lib.ptr(self.alpha), self.beta.ctypes.data, self.Elogtheta.ctypes.data,
                                          self.gamma.ctypes.data))
         _lib.check(lib.tmvb_lda_download_old(h, self.beta_old.ctypes.data, self.Elogtheta_old.ctypes.data))
         es = np.zeros(self.K)
         _lib.check(lib.tmvb_lda_get_elogtheta_sum(h, _lib.ptr(es)))
         self.Elogtheta_sum = es
+
+    def update_topics(self):
+        """model.topics = [reverse(sortperm(vec(beta[i,:]))) for i in 1:K] (gpuLDA.jl:374), ranked on the device."""
+        if not self.V:
+            return
+        if not self._resident:
+            self.topics = [np.argsort(self.beta[i, :], kind="stable")[::-1] + 1 for i in range(self.K)]
+            return
+        if self._pinned is None:
+            self.update_host()
+        t = self._pinned["topics"]
+        _lib.check(_lib.load().tmvb_lda_topics(self._handle(), t.ctypes.data))
+        self.topics = list(t)
 
     @property
     def phi(self):
@@ -186,25 +210,18 @@ def check_model(model: gpuLDA) -> None:
         raise E("alpha must be finite.")
     if not np.all(a > 0):
         raise E("alpha must be positive.")
-    b = np.asarray(model.beta)
-    if b.shape != (K, V):
+    # the element-wise invariants (beta right-stochastic/non-negative, Elogtheta finite and <= 0, gamma
+    # finite and > 0; modelutils.jl:264-273) are evaluated on the device copy during update_buffer!
+    if np.shape(model.beta) != (K, V):
         raise E("beta must be of size (K, V).")
-    if V and not (np.all(b >= 0) and np.allclose(b.sum(axis=1, dtype=np.float64), 1.0, rtol=math.sqrt(np.finfo(np.float32).eps))):
-        raise E("beta must be a right stochastic matrix.")
-    Et = np.asarray(model.Elogtheta)
-    if Et.shape != (K, M):
+    if V:
+        rs = np.asarray(model.beta).sum(axis=1, dtype=np.float64)
+        if not np.allclose(rs, 1.0, rtol=math.sqrt(np.finfo(np.float32).eps)):
+            raise E("beta must be a right stochastic matrix.")
+    if np.shape(model.Elogtheta) != (K, M):
         raise E("Elogtheta must contain M vectors of length K.")
-    if not np.all(np.isfinite(Et)):
-        raise E("Elogtheta must be finite.")
-    if not np.all(Et <= 0):
-        raise E("Elogtheta must be nonpositive.")
-    g = np.asarray(model.gamma)
-    if g.shape != (K, M):
+    if np.shape(model.gamma) != (K, M):
         raise E("gamma must contain M vectors of length K.")
-    if not np.all(np.isfinite(g)):
-        raise E("gamma must be finite.")
-    if not np.all(g > 0):
-        raise E("gamma must be positive.")
     if not math.isfinite(model.elbo):
         raise E("elbo must be finite.")
 
@@ -262,6 +279,5 @@ def train(model: gpuLDA, iter: int = 150, tol: float = 1.0, niter: int = 1000, n
 
     if iter > 0:
         model.update_host()                                    # gpuLDA.jl:373
-    if model.V:
-        model.topics = [np.argsort(-model.beta[i, :], kind="stable") + 1 for i in range(K)]  # gpuLDA.jl:374
+    model.update_topics()                                      # gpuLDA.jl:374
     return None
