@@ -1,0 +1,110 @@
+"""CPU tests of the oracle (test infrastructure): special functions vs SciPy, the C restatement vs the
+independent NumPy twin, the committed golden vectors, invariants of check_model (modelutils.jl:39-67)."""
+import os
+
+import numpy as np
+import pytest
+from scipy.special import digamma, gammaln, polygamma
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def test_special_functions_match_scipy(orc):
+    lib = orc.load()
+    xs = np.concatenate([np.geomspace(1e-3, 1e4, 400), np.linspace(0.5, 12, 47), [1.0, 2.0, 6.0, 10.0]])
+    d = np.array([lib.orc_digamma_export(float(x)) for x in xs])
+    t = np.array([lib.orc_trigamma_export(float(x)) for x in xs])
+    g = np.array([lib.orc_lgamma_export(float(x)) for x in xs])
+    np.testing.assert_allclose(d, digamma(xs), rtol=4e-15, atol=4e-15)
+    np.testing.assert_allclose(t, polygamma(1, xs), rtol=4e-15)
+    np.testing.assert_allclose(g, gammaln(xs), rtol=1e-14, atol=1e-14)
+    assert abs(lib.orc_digamma_export(1.0) + np.euler_gamma) < 1e-15          # psi(1) = -gamma (LDA.jl:38)
+
+
+def test_epsilon_is_eps_of_1e_minus_14():
+    from oracle.numpy_twin import EPSILON
+    assert EPSILON == np.spacing(1e-14) == 2.0 ** -99                           # utils.jl:3
+
+
+@pytest.mark.parametrize("K,M,V,seed", [(5, 100, 500, 0), (3, 40, 120, 4), (1, 20, 60, 5), (12, 30, 200, 6)])
+def test_c_oracle_matches_numpy_twin(orc, K, M, V, seed):
+    import topicmodelsvb_b200.synth as synth
+    from oracle.numpy_twin import LDATwin
+
+    c = synth.gencorp_lda(M=M, V=V, K=max(K, 2), seed=seed)
+    beta0 = synth.init_beta(K, c.V, seed=7)
+    st = orc.LDAState(K, c.M, c.V, beta=beta0)
+    tr, sw, done = orc.lda_train(st, c.N_cumsum, c.terms, c.counts, iter=6, tol=-np.inf)
+    tw = LDATwin(c.N_cumsum, c.terms, c.counts, K, c.V, beta0)
+    t2 = tw.train(iter=6, tol=-np.inf)
+    np.testing.assert_allclose(tr, t2, rtol=1e-12)
+    np.testing.assert_allclose(st.alpha, tw.alpha, rtol=1e-10)
+    np.testing.assert_allclose(st.beta, tw.beta, rtol=1e-10, atol=1e-300)
+    np.testing.assert_allclose(st.gamma, tw.gamma, rtol=1e-10)
+    np.testing.assert_allclose(st.Elogtheta, tw.Elogtheta, rtol=1e-10, atol=1e-12)
+
+
+def test_golden_lda_cfg0(orc):
+    g = np.load(os.path.join(GOLD, "lda_cfg0.npz"))
+    K, V = int(g["K"]), int(g["V"])
+    M = len(g["N_cumsum"]) - 1
+    st = orc.LDAState(K, M, V, beta=g["beta0"])
+    tr, sw, done = orc.lda_train(st, g["N_cumsum"], g["terms"].astype(np.int64), g["counts"].astype(np.int64), iter=20, tol=0.0)
+    np.testing.assert_allclose(tr, g["elbo"], rtol=1e-12)
+    np.testing.assert_array_equal(sw, g["sweeps"])
+    np.testing.assert_allclose(st.alpha, g["alpha"], rtol=1e-10)
+    np.testing.assert_allclose(st.beta, g["beta"], rtol=1e-10, atol=1e-300)
+    np.testing.assert_allclose(st.gamma, g["gamma"], rtol=1e-10)
+    # ELBO never decreases on this configuration (CAVI ascent; the alpha barrier step is benign here)
+    assert np.all(np.diff(tr) > 0)
+    # invariants of check_model(::LDA) (modelutils.jl:39-67)
+    np.testing.assert_allclose(st.beta.sum(axis=0), 1.0, rtol=1e-12)
+    assert np.all(st.alpha > 0) and np.all(st.gamma > 0) and np.all(st.Elogtheta <= 0)
+
+
+def test_threaded_oracle_only_reassociates(orc):
+    import topicmodelsvb_b200.synth as synth
+
+    c = synth.gencorp_lda(M=150, V=300, K=4, seed=8)
+    beta0 = synth.init_beta(6, c.V, seed=7)
+    a = orc.LDAState(6, c.M, c.V, beta=beta0)
+    b = orc.LDAState(6, c.M, c.V, beta=beta0)
+    ta, _, _ = orc.lda_train(a, c.N_cumsum, c.terms, c.counts, iter=5, tol=0.0, nthreads=1)
+    tb, _, _ = orc.lda_train(b, c.N_cumsum, c.terms, c.counts, iter=5, tol=0.0, nthreads=4)
+    np.testing.assert_allclose(ta, tb, rtol=1e-12)
+    np.testing.assert_allclose(a.beta, b.beta, rtol=1e-9, atol=1e-300)
+
+
+def test_checkelbo_and_tol_semantics(orc):
+    """check_elbo! (modelutils.jl:574-585): evaluated when k % checkelbo == 0; delta < tol stops."""
+    import topicmodelsvb_b200.synth as synth
+
+    c = synth.gencorp_lda(M=60, V=200, K=3, seed=1)
+    beta0 = synth.init_beta(4, c.V, seed=7)
+    st = orc.LDAState(4, c.M, c.V, beta=beta0)
+    tr, _, done = orc.lda_train(st, c.N_cumsum, c.terms, c.counts, iter=6, tol=0.0, checkelbo=2)
+    assert done == 6 and np.isfinite(tr[[0, 2, 4, 6]]).all() and np.isnan(tr[[1, 3, 5]]).all()
+    st = orc.LDAState(4, c.M, c.V, beta=beta0)
+    tr, _, done = orc.lda_train(st, c.N_cumsum, c.terms, c.counts, iter=50, tol=1e12)
+    assert done == 1
+    st = orc.LDAState(4, c.M, c.V, beta=beta0)
+    tr, _, done = orc.lda_train(st, c.N_cumsum, c.terms, c.counts, iter=3, tol=0.0, checkelbo=float("inf"))
+    assert done == 3 and np.isnan(tr).all()
+
+
+def test_estep_scatter_equals_train_statistics(orc):
+    """orc.lda_estep (what bench.py's cpu_baseline times) == the E-step inside train!."""
+    import topicmodelsvb_b200.synth as synth
+
+    c = synth.gencorp_lda(M=50, V=150, K=3, seed=2)
+    K = 5
+    beta0 = synth.init_beta(K, c.V, seed=7)
+    a = orc.LDAState(K, c.M, c.V, beta=beta0)
+    stats, sweeps = orc.lda_estep(a, c.N_cumsum, c.terms, c.counts)
+    b = orc.LDAState(K, c.M, c.V, beta=beta0)
+    _, sw, _ = orc.lda_train(b, c.N_cumsum, c.terms, c.counts, iter=1, tol=0.0, checkelbo=float("inf"))
+    assert sweeps == int(sw[0])
+    np.testing.assert_allclose(stats / stats.sum(axis=0, keepdims=True), b.beta, rtol=1e-12)
+    np.testing.assert_allclose(stats.sum(), c.counts.sum(), rtol=1e-12)       # every token's phi sums to one
+    phi = orc.lda_phi(K, c.M, c.N_cumsum, c.terms, b.beta_old, b.Elogtheta_old)
+    np.testing.assert_allclose(phi.sum(axis=1), 1.0, rtol=1e-12)
