@@ -138,7 +138,10 @@ def run_ours(args):
     shard = shard._replace(N_cumsum=pin(shard.N_cumsum), terms=pin(shard.terms), counts=pin(shard.counts))
     beta0 = np.asfortranarray(tm.synth.init_beta(K, full.V, seed=7).T.astype(np.float32))   # (K, V)
 
-    stream = torch.cuda.current_stream().cuda_stream
+    # one explicit stream for everything: the library's kernels, torch's L2 flush and timing events, NCCL
+    work_stream = torch.cuda.Stream()
+    torch.cuda.set_stream(work_stream)
+    stream = work_stream.cuda_stream
     model = tm.gpuLDA(tm.Corpus.from_csr(shard), K, reducer=reducer, M_total=M_total, stream=stream)
     model.beta = pin(beta0)
     model.Elogtheta = pin(model.Elogtheta)

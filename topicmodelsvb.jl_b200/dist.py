@@ -30,7 +30,10 @@ class Reducer:
         self._views = {}
 
     def stream_ptr(self) -> int:
-        return int(self.torch.cuda.current_stream().cuda_stream)
+        """cudaStream_t of torch's current stream; the legacy default stream (0) is passed as cudaStreamLegacy (0x1)
+        because a NULL stream asks the library for a private one."""
+        p = int(self.torch.cuda.current_stream().cuda_stream)
+        return p if p != 0 else 1
 
     def view(self, ptr: int, n: int, typestr: str, device: int):
         key = (ptr, n, typestr)
