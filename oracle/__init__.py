@@ -68,6 +68,18 @@ def load():
     ]
     lib.orc_lda_phi.restype = None
     lib.orc_lda_phi.argtypes = [_c.c_int64, _c.c_int64, _i64p, _i64p, _f64p, _f64p, _f64p]
+    lib.orc_ctm_train.restype = _c.c_int
+    lib.orc_ctm_train.argtypes = [
+        _c.c_int64, _c.c_int64, _c.c_int64, _i64p, _i64p, _i64p,
+        _f64p, _f64p, _f64p, _f64p, _f64p, _f64p, _f64p, _f64p, _f64p,
+        _c.c_int, _c.c_double, _c.c_int, _c.c_double, _c.c_int, _c.c_double, _c.c_int,
+        _f64p, _i64p, _c.POINTER(_c.c_int), _c.c_int,
+    ]
+    lib.orc_ctm_elbo.restype = _c.c_double
+    lib.orc_ctm_elbo.argtypes = [
+        _c.c_int64, _c.c_int64, _c.c_int64, _i64p, _i64p, _i64p,
+        _f64p, _f64p, _f64p, _f64p, _f64p, _f64p, _f64p, _f64p, _c.c_int,
+    ]
     _lib = lib
     return lib
 
@@ -165,3 +177,41 @@ def lda_phi(K, M, N_cumsum, terms, beta_old, Elogtheta_old):
                     np.ascontiguousarray(beta_old, dtype=np.float64),
                     np.ascontiguousarray(Elogtheta_old, dtype=np.float64), phi)
     return phi
+
+
+class CTMState:
+    """The mutable fields of the reference's ``CTM`` struct (CTM.jl:6-25, init :38-49) as fp64 arrays."""
+
+    def __init__(self, K, M, V, beta):
+        self.K, self.M, self.V = int(K), int(M), int(V)
+        self.mu = np.zeros(K)
+        self.sigma = np.eye(K)
+        self.invsigma = np.eye(K)
+        self.beta = np.ascontiguousarray(beta, dtype=np.float64).reshape(V, K).copy()
+        self.beta_old = self.beta.copy()
+        self.lam = np.zeros((M, K))
+        self.lam_old = np.zeros((M, K))
+        self.vsq = np.ones((M, K))
+        self.logzeta = np.full(M, 0.5)
+        self.elbo = 0.0
+
+
+def ctm_train(st: CTMState, N_cumsum, terms, counts, iter=150, tol=1.0, niter=1000, ntol=None, viter=10, vtol=None,
+              checkelbo=1, nthreads=1):
+    """train!(model::CTM; ...) (CTM.jl:185-217) on the C oracle.  Returns (elbo_trace, sweeps, iters_done)."""
+    lib = load()
+    K = st.K
+    ntol = 1.0 / K**2 if ntol is None else ntol
+    vtol = 1.0 / K**2 if vtol is None else vtol
+    trace = np.full(iter + 1, np.nan)
+    sweeps = np.zeros(max(iter, 1), dtype=np.int64)
+    done = _c.c_int(0)
+    ce = 0 if (checkelbo is None or checkelbo == float("inf")) else int(checkelbo)
+    lib.orc_ctm_train(K, st.M, st.V, np.ascontiguousarray(N_cumsum, dtype=np.int64), np.ascontiguousarray(terms, dtype=np.int64),
+                      np.ascontiguousarray(counts, dtype=np.int64), st.mu, st.sigma, st.invsigma, st.beta, st.beta_old,
+                      st.lam, st.lam_old, st.vsq, st.logzeta, int(iter), float(tol), int(niter), float(ntol), int(viter),
+                      float(vtol), ce, trace, sweeps, _c.byref(done), int(nthreads))
+    fin = trace[np.isfinite(trace)]
+    if fin.size:
+        st.elbo = float(fin[-1])
+    return trace, sweeps[:iter], done.value

@@ -136,3 +136,126 @@ class LDATwin:
                 if delta < tol:
                     break
         return np.array(trace)
+
+
+class CTMTwin:
+    """src/CTM.jl, line for line (numpy.linalg for `\\`, inv, logdet)."""
+
+    def __init__(self, N_cumsum, terms, counts, K, V, beta):
+        self.K, self.V = K, V
+        self.M = len(N_cumsum) - 1
+        self.off = np.asarray(N_cumsum, dtype=np.int64)
+        self.terms = np.asarray(terms, dtype=np.int64)
+        self.counts = np.asarray(counts, dtype=np.float64)
+        self.C = np.array([self.counts[self.off[d]:self.off[d + 1]].sum() for d in range(self.M)])
+        self.mu = np.zeros(K)                                   # CTM.jl:38-49
+        self.sigma = np.eye(K)
+        self.invsigma = np.eye(K)
+        self.beta = np.array(beta, dtype=np.float64).reshape(V, K)
+        self.beta_old = self.beta.copy()
+        self.beta_temp = np.zeros((V, K))
+        self.lam = np.zeros((self.M, K))
+        self.lam_old = np.zeros((self.M, K))
+        self.vsq = np.ones((self.M, K))
+        self.logzeta = np.full(self.M, 0.5)
+        self.phi = None
+        self.elbo = 0.0
+
+    def _doc(self, d):
+        s = slice(self.off[d], self.off[d + 1])
+        return self.terms[s], self.counts[s]
+
+    @staticmethod
+    def _softmax_rows(x):
+        x = np.exp(x - x.max(axis=1, keepdims=True))
+        return x / x.sum(axis=1, keepdims=True)
+
+    def update_phi(self, d):  # CTM.jl:175-178
+        terms, _ = self._doc(d)
+        with np.errstate(divide="ignore"):
+            self.phi = self._softmax_rows(np.log(self.beta[terms]) + self.lam[d][None, :])
+
+    def update_logzeta(self, d):  # CTM.jl:169-171
+        x = self.lam[d] + 0.5 * self.vsq[d]
+        self.logzeta[d] = x.max() + np.log(np.exp(x - x.max()).sum())
+
+    def update_vsq(self, d, niter, ntol):  # CTM.jl:146-165
+        for i in range(self.K):
+            for _ in range(niter):
+                rho = 1.0
+                ex = self.C[d] * np.exp(self.lam[d, i] + 0.5 * self.vsq[d, i] - self.logzeta[d])
+                grad = -0.5 * (self.invsigma[i, i] + ex - 1.0 / self.vsq[d, i])
+                invhess = -1.0 / (0.25 * ex + 0.5 / self.vsq[d, i] ** 2)
+                p = invhess * grad
+                while self.vsq[d, i] - rho * p <= 0:
+                    rho *= 0.5
+                self.vsq[d, i] -= rho * p
+                if rho * abs(grad) < ntol:
+                    break
+        self.vsq[d] += EPSILON
+
+    def update_lambda(self, d, niter, ntol):  # CTM.jl:129-142
+        self.lam_old[d] = self.lam[d]
+        _, counts = self._doc(d)
+        phic = counts @ self.phi
+        for _ in range(niter):
+            w = self.C[d] * np.exp(self.lam[d] + 0.5 * self.vsq[d] - self.logzeta[d])
+            grad = self.invsigma @ (self.mu - self.lam[d]) + phic - w
+            H = self.invsigma + np.diag(w)
+            self.lam[d] = self.lam[d] + np.linalg.solve(H, grad)
+            if np.linalg.norm(grad) < ntol:
+                break
+
+    def update_elbo(self):  # CTM.jl:56-98
+        elbo = 0.0
+        K = self.K
+        _, logdet = np.linalg.slogdet(self.invsigma)
+        for d in range(self.M):
+            terms, counts = self._doc(d)
+            with np.errstate(divide="ignore"):
+                phi = self._softmax_rows(np.log(self.beta_old[terms]) + self.lam_old[d][None, :])
+            lam, v = self.lam[d], self.vsq[d]
+            df = lam - self.mu
+            Elogpeta = 0.5 * (logdet - K * np.log(2 * np.pi) - np.dot(np.diag(self.invsigma), v) - df @ self.invsigma @ df)
+            Elogpz = np.dot(phi @ lam, counts) - self.C[d] * (np.exp(lam + 0.5 * v - self.logzeta[d]).sum() + self.logzeta[d] - 1)
+            Elogpw = np.sum((phi * np.log(self.beta[terms] + EPSILON)) * counts[:, None])
+            ent_eta = 0.5 * (K * (np.log(2 * np.pi) + 1) + np.log(v).sum())
+            with np.errstate(divide="ignore", invalid="ignore"):
+                plogp = np.where(phi > 0, phi * np.log(phi), 0.0)
+            ent_z = -(plogp.sum(axis=1) * counts).sum()
+            elbo += Elogpeta + Elogpz + Elogpw + ent_eta + ent_z
+        self.elbo = elbo
+        return elbo
+
+    def train(self, iter=150, tol=1.0, niter=1000, ntol=None, viter=10, vtol=None, checkelbo=1):  # CTM.jl:185-217
+        K = self.K
+        ntol = 1.0 / K**2 if ntol is None else ntol
+        vtol = 1.0 / K**2 if vtol is None else vtol
+        trace = [np.nan] * (iter + 1)
+        if checkelbo <= iter:
+            trace[0] = self.update_elbo()
+        for k in range(1, iter + 1):
+            for d in range(self.M):
+                terms, counts = self._doc(d)
+                for _ in range(viter):
+                    self.update_phi(d)
+                    self.update_logzeta(d)
+                    self.update_vsq(d, niter, ntol)
+                    self.update_lambda(d, niter, ntol)
+                    if np.linalg.norm(self.lam[d] - self.lam_old[d]) < vtol:
+                        break
+                self.beta_temp[terms] += self.phi * counts[:, None]      # CTM.jl:122-125
+            self.beta_old = self.beta                                    # CTM.jl:114-118
+            self.beta = self.beta_temp / self.beta_temp.sum(axis=0, keepdims=True)
+            self.beta_temp = np.zeros((self.V, K))
+            dl = self.lam - self.mu[None, :]                             # CTM.jl:108-111 (old mu)
+            self.sigma = (np.diag(self.vsq.sum(axis=0)) + dl.T @ dl) / self.M
+            self.invsigma = np.linalg.inv(self.sigma)
+            self.mu = self.lam.sum(axis=0) / self.M                      # CTM.jl:102-104
+            if k % checkelbo == 0:
+                old = self.elbo
+                delta = self.update_elbo() - old
+                trace[k] = self.elbo
+                if delta < tol:
+                    break
+        return np.array(trace)

@@ -1,0 +1,491 @@
+// tmvb_shard.cu -- implementation of the shard plumbing shared by the LDA / CTM / CTPF handles.
+#include <algorithm>
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "tmvb_shard.cuh"
+
+namespace tmvb {
+
+// ------------------------------------------------------------------ lane layouts ------------
+int row_stride(int CH, int lpt)
+{
+    int r = CH;
+    if (lpt < 8)
+        while (r % (2 * lpt) != lpt) r++;
+    return 4 * r;
+}
+
+int pick_layout(int K_ld, int *RS_out)
+{
+    const int CH = K_ld / 4;
+    int best = -1;
+    double best_cost = 0.0;
+    const int force_lpt = env_int("TMVB_LPT", 0);
+    for (int k = 0; k < kNumLaneLayouts; k++) {
+        const LaneLayout &l = kLaneLayouts[k];
+        if (l.lpt * l.cpl < CH) continue;
+        if (force_lpt && l.lpt != force_lpt) continue;
+        const int S = 32 / l.lpt, RS = row_stride(CH, l.lpt);
+        const double instr_tok = (l.cpl * 9.0 + 2.0 * log2((double)l.lpt) + 12.0) / S;
+        const double fixed = (l.cpl + ((K_ld + 31) / 32) * 2.0 * S) / 80.0;
+        const double cost = (instr_tok + fixed) * sqrt((double)RS / K_ld);
+        if (best < 0 || cost < best_cost - 1e-9) {
+            best = k;
+            best_cost = cost;
+            *RS_out = RS;
+        }
+    }
+    return best;
+}
+
+int env_int(const char *name, int dflt)
+{
+    const char *s = getenv(name);
+    return (s && *s) ? atoi(s) : dflt;
+}
+
+int grid_for(long long work, int block, int n_sm)
+{
+    long long g = (work + block - 1) / block;
+    long long cap = (long long)n_sm * 16;
+    if (g > cap) g = cap;
+    if (g < 1) g = 1;
+    return (int)g;
+}
+
+// ------------------------------------------------------------------ layout kernels ----------
+// dst[p][0..K_ld) = src[perm ? perm[p] : p][0..K) , zero padded
+__global__ void pad_rows_kernel(const float *__restrict__ src, float *__restrict__ dst, const int *__restrict__ perm,
+                                long long rows, int K, int K_ld)
+{
+    for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < rows * K_ld; q += (long long)gridDim.x * blockDim.x) {
+        const long long r = q / K_ld;
+        const int i = (int)(q - r * K_ld);
+        const long long sr = perm ? perm[r] : r;
+        dst[q] = (i < K) ? src[sr * K + i] : 0.0f;
+    }
+}
+// dst[perm ? perm[p] : p][0..K) = src[p][0..K)
+__global__ void unpad_rows_kernel(const float *__restrict__ src, float *__restrict__ dst, const int *__restrict__ perm,
+                                  long long rows, int K, int K_ld)
+{
+    for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < rows * K; q += (long long)gridDim.x * blockDim.x) {
+        const long long r = q / K;
+        const int i = (int)(q - r * K);
+        const long long dr = perm ? perm[r] : r;
+        dst[dr * K + i] = src[r * K_ld + i];
+    }
+}
+// check_model invariants that need a pass over the data (modelutils.jl:264-273 and the gpuCTM/gpuCTPF
+// counterparts), evaluated on the device copy: bit0 non-finite, bit1 sign violation
+// (what = 0: x >= 0; 1: x <= 0; 2: x > 0; 3: finite only)
+__global__ void validate_kernel(const float *__restrict__ x, long long n, int what, int *__restrict__ err)
+{
+    int e = 0;
+    for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < n; q += (long long)gridDim.x * blockDim.x) {
+        const float v = x[q];
+        if (!isfinite(v)) e |= 1;
+        if ((what == 0 && v < 0.f) || (what == 1 && v > 0.f) || (what == 2 && !(v > 0.f))) e |= 2;
+    }
+    if (e) atomicOr(err, e << (2 * what));
+}
+// CSR re-layout: internal document p takes the tokens of caller document perm[p]; Int64 -> int32 / float
+__global__ void pack_corpus_kernel(const long long *__restrict__ terms64, const long long *__restrict__ counts64,
+                                   const long long *__restrict__ src_off, const long long *__restrict__ dst_off, long long M,
+                                   int V, int *__restrict__ terms, float *__restrict__ counts, int *__restrict__ err)
+{
+    const int lane = threadIdx.x & 31;
+    const int wpb = blockDim.x >> 5;
+    for (long long d = (long long)blockIdx.x * wpb + (threadIdx.x >> 5); d < M; d += (long long)gridDim.x * wpb) {
+        const long long so = src_off[d], o = dst_off[d];
+        const int Nd = (int)(dst_off[d + 1] - o);
+        for (int n = lane; n < Nd; n += 32) {
+            const long long t = terms64[so + n], c = counts64[so + n];
+            if (t < 0 || t >= V) atomicOr(err, 1);
+            if (c <= 0) atomicOr(err, 2);
+            terms[o + n] = (int)t;
+            counts[o + n] = (float)c;
+        }
+    }
+}
+// rowsum_i = sum_j stats[j][i]   (the `sum(beta_temp, dims=2)` of LDA.jl:123)
+__global__ void colsum_kernel(const float *__restrict__ stats, int V, int K_ld, double *__restrict__ rowsum)
+{
+    extern __shared__ double sh[];
+    const int R = blockDim.x / K_ld;
+    const int r = threadIdx.x / K_ld, i = threadIdx.x - r * K_ld;
+    double acc = 0.0;
+    if (r < R)
+        for (int j = blockIdx.x * R + r; j < V; j += gridDim.x * R) acc += (double)stats[(size_t)j * K_ld + i];
+    sh[threadIdx.x] = (r < R) ? acc : 0.0;
+    __syncthreads();
+    if (threadIdx.x < K_ld) {
+        double a = 0.0;
+        for (int q = 0; q < R; q++) a += sh[q * K_ld + threadIdx.x];
+        if (a != 0.0) atomicAdd(rowsum + threadIdx.x, a);
+    }
+}
+// beta_new = stats ./ rowsum ; stats <- 0 ; elbo_w += sum stats * ln(beta_new + eps)
+// (LDA.jl:121-125 / CTM.jl:114-118 and the Elogpw term LDA.jl:64-67 / CTM.jl:69-73 rewritten over the statistics)
+__global__ void normalize_kernel(float *__restrict__ stats, float *__restrict__ beta_new, const double *__restrict__ rowsum,
+                                 long long n, int K, int K_ld, double *__restrict__ elbo_w, int want_elbo)
+{
+    double acc = 0.0;
+    for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < n; q += (long long)gridDim.x * blockDim.x) {
+        const int i = (int)(q % K_ld);
+        float s = stats[q];
+        float b = 0.0f;
+        if (i < K) {
+            const double rs = rowsum[i];
+            b = rs > 0.0 ? (float)((double)s / rs) : 0.0f;
+            if (want_elbo) acc += (double)(s * logf(b + TMVB_EPS));
+        }
+        beta_new[q] = b;
+        stats[q] = 0.0f;
+    }
+    if (want_elbo) {
+        acc = warp_sum_d(acc);
+        if ((threadIdx.x & 31) == 0 && acc != 0.0) atomicAdd(elbo_w, acc);
+    }
+}
+
+// ------------------------------------------------------------------ shard ------------------
+int shard_create(Shard *s, int64_t K, int64_t M, int64_t V, int device, void *stream, size_t pinned_doubles)
+{
+    TMVB_CHECK_ARG(K > 0, "number of topics must be a positive integer");  // gpuLDA.jl:47
+    TMVB_CHECK_ARG(M >= 0 && V >= 0, "M and V must be nonnegative");
+    TMVB_CHECK_ARG(M < (1ll << 31) && V < (1ll << 31), "M and V must fit in int32");
+    if (K > 256) return fail(-2, "K=%lld is not supported (K <= 256)", (long long)K);
+    const int K_ld = (int)((K + 7) / 8 * 8);
+    int RS = 0;
+    const int li = pick_layout(K_ld, &RS);
+    if (li < 0) return fail(-2, "internal: no lane layout for K=%lld", (long long)K);
+    int ndev = 0;
+    TMVB_TRY(tmvb_device_count(&ndev));
+    if (ndev == 0) return fail(-3, "no CUDA device: libtmvb has no CPU fallback");
+    if (device < 0) TMVB_CUDA(cudaGetDevice(&device));
+    TMVB_CHECK_ARG(device < ndev, "device index out of range");
+    TMVB_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    TMVB_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10) return fail(-3, "device %d is sm_%d%d; libtmvb is built for sm_100a only", device, prop.major, prop.minor);
+
+    s->device = device;
+    s->n_sm = prop.multiProcessorCount;
+    s->smem_optin = prop.sharedMemPerBlockOptin;
+    s->K = K;
+    s->M = M;
+    s->V = V;
+    s->K_ld = K_ld;
+    s->RS = RS;
+    s->layout = li;
+    s->lpt = kLaneLayouts[li].lpt;
+    s->cpl = kLaneLayouts[li].cpl;
+    if (stream) {
+        s->stream = (cudaStream_t)stream;
+    } else {
+        TMVB_CUDA(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
+        s->own_stream = true;
+    }
+    const size_t kv = (size_t)std::max<int64_t>(V, 1) * K_ld;
+    for (int b = 0; b < 2; b++) {
+        TMVB_CUDA(cudaMalloc((void **)&s->d_beta[b], kv * 4));
+        TMVB_CUDA(cudaMemsetAsync(s->d_beta[b], 0, kv * 4, s->stream));
+    }
+    TMVB_CUDA(cudaMalloc((void **)&s->d_stats, kv * 4));
+    TMVB_CUDA(cudaMemsetAsync(s->d_stats, 0, kv * 4, s->stream));
+    TMVB_CUDA(cudaMalloc((void **)&s->d_counters, 64 * 4));
+    TMVB_CUDA(cudaMemsetAsync(s->d_counters, 0, 64 * 4, s->stream));
+    s->pinned_doubles = pinned_doubles;
+    TMVB_CUDA(cudaMallocHost((void **)&s->h_pinned, pinned_doubles * 8));
+    for (auto &e : s->ev) TMVB_CUDA(cudaEventCreate(&e));
+    s->n_streams = std::min(1 + Shard::kAux, std::max(1, env_int("TMVB_STREAMS", 4)));
+    for (int a = 0; a + 1 < s->n_streams; a++) {
+        TMVB_CUDA(cudaStreamCreateWithFlags(&s->aux[a], cudaStreamNonBlocking));
+        TMVB_CUDA(cudaEventCreateWithFlags(&s->ev_join[a], cudaEventDisableTiming));
+    }
+    TMVB_CUDA(cudaEventCreateWithFlags(&s->ev_fork, cudaEventDisableTiming));
+    return 0;
+}
+
+void shard_free(Shard *s)
+{
+    cudaSetDevice(s->device);
+    if (s->stream) cudaStreamSynchronize(s->stream);
+    cudaFree(s->d_doc_off);
+    cudaFree(s->d_src_off);
+    cudaFree(s->d_terms);
+    cudaFree(s->d_perm);
+    cudaFree(s->d_counts);
+    cudaFree(s->d_beta[0]);
+    cudaFree(s->d_beta[1]);
+    cudaFree(s->d_stats);
+    cudaFree(s->d_counters);
+    cudaFree(s->d_scratch);
+    cudaFree(s->d_sort_ws);
+    if (s->h_pinned) cudaFreeHost(s->h_pinned);
+    for (auto &e : s->ev)
+        if (e) cudaEventDestroy(e);
+    for (auto &a : s->aux)
+        if (a) cudaStreamDestroy(a);
+    for (auto &e : s->ev_join)
+        if (e) cudaEventDestroy(e);
+    if (s->ev_fork) cudaEventDestroy(s->ev_fork);
+    if (s->own_stream && s->stream) cudaStreamDestroy(s->stream);
+    *s = Shard();
+}
+
+int shard_scratch(Shard *s, size_t bytes)
+{
+    if (bytes <= s->scratch_bytes) return 0;
+    if (s->d_scratch) TMVB_CUDA(cudaFree(s->d_scratch));
+    s->d_scratch = nullptr;
+    s->scratch_bytes = 0;
+    TMVB_CUDA(cudaMalloc(&s->d_scratch, bytes));
+    s->scratch_bytes = bytes;
+    return 0;
+}
+
+// Split the length-sorted documents into launches whose shared-memory tile capacity ("cap", in tokens) fits the
+// longest document of the launch.
+static int plan_buckets(Shard *s, size_t fixed_bytes)
+{
+    s->buckets.clear();
+    const std::vector<int> &len_sorted = s->len_sorted;
+    const int M = (int)len_sorted.size();
+    if (M == 0) return 0;
+    const size_t per_tok = (size_t)s->RS * 4 + 8;
+    if (fixed_bytes + 16 * per_tok > s->smem_optin) return fail(-4, "internal: E-step working set does not fit in shared memory");
+    int cap_max = 16;
+    while (fixed_bytes + (size_t)(cap_max + 16) * per_tok <= s->smem_optin) cap_max += 16;
+    std::vector<int> caps;
+    for (int c = 16; c < cap_max; c = (c < 128) ? c + 16 : (c < 256 ? c + 32 : c + c / 4 / 16 * 16)) caps.push_back(c);
+    caps.push_back(cap_max);
+    int begin = 0;  // documents are sorted by length, longest first
+    for (int ci = (int)caps.size() - 1; ci >= 0 && begin < M; ci--) {
+        const int lo = (ci == 0) ? -1 : caps[ci - 1];  // this launch takes lengths in (lo, caps[ci]] (+ overflow for the largest)
+        int end = begin;
+        while (end < M && len_sorted[end] > lo) end++;
+        if (end == begin) continue;
+        Bucket b;
+        b.doc_begin = begin;
+        b.doc_end = end;
+        b.cap = std::min(caps[ci], std::max(16, (len_sorted[begin] + 15) / 16 * 16));
+        if (b.cap > cap_max) b.cap = cap_max;
+        b.cap2 = 0;
+        b.smem = fixed_bytes + (size_t)b.cap * per_tok;
+        b.grid = 0;
+        s->buckets.push_back(b);
+        begin = end;
+    }
+    if ((int)s->buckets.size() > kMaxBuckets) return fail(-1, "internal: too many launch buckets");
+    return 0;
+}
+
+int shard_set_corpus(Shard *s, const int64_t *N_cumsum, const int64_t *terms, const int64_t *counts, size_t fixed_bytes)
+{
+    TMVB_CHECK_ARG(N_cumsum != nullptr, "N_cumsum is NULL");
+    TMVB_CUDA(cudaSetDevice(s->device));
+    const int64_t M = s->M;
+    TMVB_CHECK_ARG(N_cumsum[0] == 0, "N_cumsum[0] must be 0");
+    const int64_t nnz = N_cumsum[M];
+    TMVB_CHECK_ARG(nnz >= 0, "N_cumsum must be nondecreasing");
+    TMVB_CHECK_ARG(nnz == 0 || (terms != nullptr && counts != nullptr), "terms/counts are NULL");
+
+    // host: O(M) counting sort of the documents by length (descending, stable)
+    std::vector<int> len(M);
+    int maxlen = 0;
+    for (int64_t d = 0; d < M; d++) {
+        const int64_t l = N_cumsum[d + 1] - N_cumsum[d];
+        if (l < 0 || l > (1 << 30)) return fail(-1, "invalid argument: N_cumsum must be nondecreasing (document %lld)", (long long)d);
+        len[d] = (int)l;
+        maxlen = std::max(maxlen, (int)l);
+    }
+    std::vector<int64_t> start((size_t)maxlen + 2, 0);
+    for (int64_t d = 0; d < M; d++) start[maxlen - len[d] + 1]++;
+    for (int l = 0; l <= maxlen; l++) start[l + 1] += start[l];
+    s->h_perm.assign(M, 0);
+    for (int64_t d = 0; d < M; d++) s->h_perm[start[maxlen - len[d]]++] = (int)d;
+    std::vector<long long> src_off(std::max<int64_t>(M, 1)), dst_off(M + 1);
+    s->len_sorted.assign(M, 0);
+    dst_off[0] = 0;
+    for (int64_t p = 0; p < M; p++) {
+        const int d = s->h_perm[p];
+        src_off[p] = N_cumsum[d];
+        s->len_sorted[p] = len[d];
+        dst_off[p + 1] = dst_off[p] + len[d];
+    }
+    TMVB_TRY(plan_buckets(s, fixed_bytes));
+
+    const size_t nz = (size_t)std::max<int64_t>(nnz, 1);
+    if (!s->d_doc_off) {
+        TMVB_CUDA(cudaMalloc((void **)&s->d_doc_off, (M + 1) * 8));
+        TMVB_CUDA(cudaMalloc((void **)&s->d_src_off, std::max<int64_t>(M, 1) * 8));
+        TMVB_CUDA(cudaMalloc((void **)&s->d_perm, std::max<int64_t>(M, 1) * 4));
+    }
+    if (nz > s->nnz_cap) {  // token arrays are reused across calls while they fit
+        cudaFree(s->d_terms);
+        cudaFree(s->d_counts);
+        s->d_terms = nullptr;
+        s->d_counts = nullptr;
+        s->nnz_cap = 0;
+        TMVB_CUDA(cudaMalloc((void **)&s->d_terms, nz * 4));
+        TMVB_CUDA(cudaMalloc((void **)&s->d_counts, nz * 4));
+        s->nnz_cap = nz;
+    }
+    TMVB_CUDA(cudaMemcpyAsync(s->d_doc_off, dst_off.data(), (M + 1) * 8, cudaMemcpyHostToDevice, s->stream));
+    if (M > 0) {
+        TMVB_CUDA(cudaMemcpyAsync(s->d_src_off, src_off.data(), M * 8, cudaMemcpyHostToDevice, s->stream));
+        TMVB_CUDA(cudaMemcpyAsync(s->d_perm, s->h_perm.data(), M * 4, cudaMemcpyHostToDevice, s->stream));
+    }
+    s->st.h2d_bytes += (M + 1) * 8 + M * 12;
+    if (nnz > 0) {
+        TMVB_TRY(shard_scratch(s, (size_t)nnz * 16));
+        long long *t64 = (long long *)s->d_scratch, *c64 = t64 + nnz;
+        TMVB_CUDA(cudaMemcpyAsync(t64, terms, nnz * 8, cudaMemcpyHostToDevice, s->stream));
+        TMVB_CUDA(cudaMemcpyAsync(c64, counts, nnz * 8, cudaMemcpyHostToDevice, s->stream));
+        s->st.h2d_bytes += nnz * 16;
+        TMVB_CUDA(cudaMemsetAsync(s->d_counters + 63, 0, 4, s->stream));
+        pack_corpus_kernel<<<grid_for(M * 32, 256, s->n_sm), 256, 0, s->stream>>>(t64, c64, s->d_src_off, s->d_doc_off, M, (int)s->V,
+                                                                                 s->d_terms, s->d_counts, s->d_counters + 63);
+        s->st.kernel_launches++;
+        TMVB_CUDA(cudaGetLastError());
+        int err = 0;
+        TMVB_CUDA(cudaMemcpyAsync(&err, s->d_counters + 63, 4, cudaMemcpyDeviceToHost, s->stream));
+        TMVB_CUDA(cudaStreamSynchronize(s->stream));  // also keeps the host vectors alive long enough
+        if (err & 1) return fail(-1, "invalid argument: terms must lie in [0, V)");
+        if (err & 2) return fail(-1, "invalid argument: all counts must be positive integers");  // Corpus.jl:43
+    } else {
+        TMVB_CUDA(cudaStreamSynchronize(s->stream));
+    }
+    s->nnz = nnz;
+    s->corpus_set = true;
+    return 0;
+}
+
+int shard_upload_rows(Shard *s, const float *host, float *d_dst, int64_t rows, const int *d_perm, int validate)
+{
+    if (!host || rows == 0) return 0;
+    const size_t n = (size_t)rows * s->K;
+    TMVB_TRY(shard_scratch(s, n * 4));
+    TMVB_CUDA(cudaMemcpyAsync(s->d_scratch, host, n * 4, cudaMemcpyHostToDevice, s->stream));
+    if (validate >= 0) {
+        validate_kernel<<<grid_for(n, 256, s->n_sm), 256, 0, s->stream>>>((const float *)s->d_scratch, n, validate, s->d_counters + 62);
+        s->st.kernel_launches++;
+    }
+    pad_rows_kernel<<<grid_for(rows * s->K_ld, 256, s->n_sm), 256, 0, s->stream>>>((const float *)s->d_scratch, d_dst, d_perm, rows, (int)s->K, s->K_ld);
+    TMVB_CUDA(cudaGetLastError());
+    s->st.kernel_launches++;
+    s->st.h2d_bytes += n * 4;
+    return 0;
+}
+
+int shard_validation(Shard *s, int *mask)
+{
+    *mask = 0;
+    TMVB_CUDA(cudaMemcpyAsync(mask, s->d_counters + 62, 4, cudaMemcpyDeviceToHost, s->stream));
+    TMVB_CUDA(cudaStreamSynchronize(s->stream));
+    TMVB_CUDA(cudaMemsetAsync(s->d_counters + 62, 0, 4, s->stream));
+    return 0;
+}
+
+int shard_download_rows(Shard *s, const float *d_src, float *host, int64_t rows, const int *d_perm)
+{
+    if (!host || rows == 0) return 0;
+    const size_t n = (size_t)rows * s->K;
+    TMVB_TRY(shard_scratch(s, n * 4));
+    unpad_rows_kernel<<<grid_for(n, 256, s->n_sm), 256, 0, s->stream>>>(d_src, (float *)s->d_scratch, d_perm, rows, (int)s->K, s->K_ld);
+    TMVB_CUDA(cudaGetLastError());
+    s->st.kernel_launches++;
+    TMVB_CUDA(cudaMemcpyAsync(host, s->d_scratch, n * 4, cudaMemcpyDeviceToHost, s->stream));
+    TMVB_CUDA(cudaStreamSynchronize(s->stream));
+    s->st.d2h_bytes += n * 4;
+    return 0;
+}
+
+int shard_launch(Shard *s, const void *fn, void *dev_struct)
+{
+    TMVB_CUDA(cudaMemsetAsync(s->d_counters, 0, kMaxBuckets * 4, s->stream));
+    const int ns = (s->buckets.size() > 1) ? s->n_streams : 1;
+    if (ns > 1) {
+        TMVB_CUDA(cudaEventRecord(s->ev_fork, s->stream));
+        for (int a = 0; a + 1 < ns; a++) TMVB_CUDA(cudaStreamWaitEvent(s->aux[a], s->ev_fork, 0));
+    }
+    for (size_t bi = 0; bi < s->buckets.size(); bi++) {
+        Bucket &b = s->buckets[bi];
+        if (b.grid == 0) {
+            int occ = 0;
+            TMVB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, 32, b.smem));
+            if (occ < 1) return fail(-4, "internal: E-step kernel does not fit (cap=%d smem=%zu)", b.cap, b.smem);
+            b.grid = std::min(b.doc_end - b.doc_begin, occ * s->n_sm);
+        }
+        int *counter = s->d_counters + bi;
+        void *args[] = {dev_struct, (void *)&b.doc_begin, (void *)&b.doc_end, (void *)&b.cap, (void *)&b.cap2, (void *)&counter};
+        cudaStream_t st = (bi % ns == 0) ? s->stream : s->aux[bi % ns - 1];
+        TMVB_CUDA(cudaLaunchKernel(fn, dim3(b.grid), dim3(32), args, b.smem, st));
+        s->st.kernel_launches++;
+    }
+    for (int a = 0; a + 1 < ns; a++) {
+        TMVB_CUDA(cudaEventRecord(s->ev_join[a], s->aux[a]));
+        TMVB_CUDA(cudaStreamWaitEvent(s->stream, s->ev_join[a], 0));
+    }
+    return 0;
+}
+
+int shard_normalize(Shard *s, double *d_acc, bool want_elbo, float prior)
+{
+    (void)prior;
+    if (s->V == 0) return 0;
+    TMVB_CUDA(cudaMemsetAsync(d_acc, 0, (2 * s->K_ld) * 8, s->stream));
+    const int R = std::max(1, 256 / s->K_ld);
+    const int threads = std::max(R * s->K_ld, s->K_ld);
+    const int grid = (int)std::min<int64_t>((s->V + R - 1) / R, (int64_t)s->n_sm * 8);
+    colsum_kernel<<<grid, threads, threads * 8, s->stream>>>(s->d_stats, (int)s->V, s->K_ld, d_acc);
+    TMVB_CUDA(cudaGetLastError());
+    const long long n = (long long)s->V * s->K_ld;
+    normalize_kernel<<<grid_for(n, 256, s->n_sm), 256, 0, s->stream>>>(s->d_stats, s->d_beta[s->cur ^ 1], d_acc, n, (int)s->K, s->K_ld,
+                                                                      d_acc + s->K_ld, want_elbo ? 1 : 0);
+    TMVB_CUDA(cudaGetLastError());
+    s->st.kernel_launches += 2;
+    s->cur ^= 1;  // beta_old <- beta ; beta <- new  (LDA.jl:122-123)
+    return 0;
+}
+
+int shard_topics(Shard *s, const float *d_mat, const float *d_scale, int32_t *out)
+{
+    if (s->V == 0) return 0;
+    const size_t bytes = (size_t)s->K * s->V * 4;
+    TMVB_TRY(shard_scratch(s, bytes));
+    TMVB_TRY(topics_argsort(d_mat, d_scale, (int)s->K, s->K_ld, (int)s->V, (int *)s->d_scratch, &s->d_sort_ws, &s->sort_ws_bytes, s->stream,
+                            s->n_sm));
+    s->st.kernel_launches += 3;
+    TMVB_CUDA(cudaMemcpyAsync(out, s->d_scratch, bytes, cudaMemcpyDeviceToHost, s->stream));
+    TMVB_CUDA(cudaStreamSynchronize(s->stream));
+    s->st.d2h_bytes += bytes;
+    return 0;
+}
+
+int shard_get_stats(Shard *s, const double *d_sweeps, tmvb_stats *out)
+{
+    TMVB_CUDA(cudaSetDevice(s->device));
+    TMVB_CUDA(cudaStreamSynchronize(s->stream));
+    float ms = 0.f;
+    if (s->estep_timed) {
+        TMVB_CUDA(cudaEventElapsedTime(&ms, s->ev[0], s->ev[1]));
+        s->st.estep_ms = ms;
+        if (d_sweeps) {
+            TMVB_CUDA(cudaMemcpy(s->h_pinned, d_sweeps, 8, cudaMemcpyDeviceToHost));
+            s->st.sweeps = (int64_t)s->h_pinned[0];
+        }
+    }
+    if (s->mstep_timed) {
+        TMVB_CUDA(cudaEventElapsedTime(&ms, s->ev[2], s->ev[3]));
+        s->st.mstep_ms = ms;
+    }
+    *out = s->st;
+    return 0;
+}
+
+}  // namespace tmvb

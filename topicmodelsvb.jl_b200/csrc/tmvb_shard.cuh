@@ -1,0 +1,77 @@
+// tmvb_shard.cuh -- host-side state and plumbing common to the three model handles: one shard of documents
+// on one device (CSR re-layout, length buckets, topic-word table + statistics, staging, streams, counters).
+#pragma once
+
+#include <vector>
+
+#include "tmvb_estep.cuh"
+
+namespace tmvb {
+
+struct Bucket {
+    int doc_begin, doc_end, cap, grid;
+    int cap2;  // second tile capacity (CTPF reader lists); 0 otherwise
+    size_t smem;
+};
+
+struct Shard {
+    int device = 0, n_sm = 0;
+    size_t smem_optin = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    static constexpr int kAux = 3;  // bucket launches are spread over stream + aux streams so their tails overlap
+    cudaStream_t aux[kAux] = {nullptr, nullptr, nullptr};
+    cudaEvent_t ev_fork = nullptr, ev_join[kAux] = {nullptr, nullptr, nullptr};
+    int n_streams = 1;
+
+    int64_t K = 0, M = 0, V = 0, nnz = 0;
+    size_t nnz_cap = 0;
+    int K_ld = 0, RS = 0, lpt = 0, cpl = 0, layout = -1;
+    bool corpus_set = false;
+
+    // corpus, internal order = documents sorted by length (descending)
+    long long *d_doc_off = nullptr, *d_src_off = nullptr;
+    int *d_terms = nullptr, *d_perm = nullptr;
+    float *d_counts = nullptr;
+    std::vector<int> h_perm, len_sorted;
+    std::vector<Bucket> buckets;
+
+    // topic-word table (double buffered: [cur] current, [cur^1] previous) and its sufficient statistics
+    float *d_beta[2] = {nullptr, nullptr}, *d_stats = nullptr;
+    int cur = 0;
+
+    int *d_counters = nullptr;  // [0..47] bucket work counters, [62] validation flags, [63] corpus error flags
+    void *d_scratch = nullptr;
+    size_t scratch_bytes = 0;
+    void *d_sort_ws = nullptr;
+    size_t sort_ws_bytes = 0;
+    double *h_pinned = nullptr;  // small pinned read-back buffer
+    size_t pinned_doubles = 0;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    bool estep_timed = false, mstep_timed = false;
+    tmvb_stats st{};
+};
+
+constexpr int kMaxBuckets = 48;
+
+int env_int(const char *name, int dflt);
+int grid_for(long long work, int block, int n_sm);
+
+int shard_create(Shard *s, int64_t K, int64_t M, int64_t V, int device, void *stream, size_t pinned_doubles);
+void shard_free(Shard *s);
+int shard_scratch(Shard *s, size_t bytes);
+// CSR upload + device re-layout (modelutils.jl:371-388); buckets are planned with smem(cap) = cap*(RS*4+8) + fixed_bytes
+int shard_set_corpus(Shard *s, const int64_t *N_cumsum, const int64_t *terms, const int64_t *counts, size_t fixed_bytes);
+// host [rows][K] (caller order) -> device [rows][K_ld] (internal order when perm); validate: -1 none, 0 x>=0, 1 x<=0, 2 x>0
+int shard_upload_rows(Shard *s, const float *host, float *d_dst, int64_t rows, const int *d_perm, int validate);
+int shard_download_rows(Shard *s, const float *d_src, float *host, int64_t rows, const int *d_perm);
+// returns and clears the validation bit mask accumulated by shard_upload_rows (2 bits per `validate` code)
+int shard_validation(Shard *s, int *mask);
+// launch an E-step kernel `fn(Dev, doc_begin, doc_end, cap, cap2, counter)` over every bucket
+int shard_launch(Shard *s, const void *fn, void *dev_struct);
+// beta_new = stats ./ rowsum ; stats <- 0 ; [elbo_w = sum stats ln(beta_new + eps)].  d_acc: double[2*K_ld] (rowsum | elbo_w)
+int shard_normalize(Shard *s, double *d_acc, bool want_elbo, float prior);
+int shard_topics(Shard *s, const float *d_mat, const float *d_scale, int32_t *out);
+int shard_get_stats(Shard *s, const double *d_sweeps, tmvb_stats *out);
+
+}  // namespace tmvb
