@@ -32,6 +32,7 @@ extern "C" {
 #define TMVB_VERSION 100
 
 typedef struct tmvb_lda_s *tmvb_lda_t;
+typedef struct tmvb_ctm_s *tmvb_ctm_t;
 
 /* Timings (ms, CUDA events on the handle's stream) and counters of the most recent calls. */
 typedef struct tmvb_stats {
@@ -116,6 +117,46 @@ int tmvb_lda_sync(tmvb_lda_t h);
 int tmvb_lda_get_stats(tmvb_lda_t h, tmvb_stats *out);
 /* padded leading dimension of the device K-vectors (rows of beta/stats are K_ld floats) */
 int tmvb_lda_kld(tmvb_lda_t h, int64_t *K_ld);
+
+
+/* ------------------------------------------------------------------ CTM ------------------ */
+
+/* gpuCTM(corp, K) device side (gpuCTM.jl:74-92: context + 9 cl.Program builds).  K <= 64 in this build.
+ * Starts from mu = 0, sigma = invsigma = I (gpuCTM.jl:63-65). */
+int tmvb_ctm_create(tmvb_ctm_t *h, int64_t K, int64_t M, int64_t V, int device, void *stream);
+int tmvb_ctm_destroy(tmvb_ctm_t h);
+
+/* update_buffer!(model::gpuCTM), corpus half (modelutils.jl:401-417). */
+int tmvb_ctm_set_corpus(tmvb_ctm_t h, const int64_t *N_cumsum, const int64_t *terms, const int64_t *counts);
+
+/* update_buffer!(model::gpuCTM), parameter half (modelutils.jl:419-428) and `@buffer model.invsigma` (macros.jl:67):
+ * mu[K], sigma[K*K] (invsigma is recomputed in fp64, as gpuCTM.jl:203-205 does on the host), beta[K*V],
+ * lambda[K*M], vsq[K*M], logzeta[M].  Any pointer may be NULL. */
+int tmvb_ctm_upload(tmvb_ctm_t h, const float *mu, const float *sigma, const float *beta, const float *lambda, const float *vsq,
+                    const float *logzeta);
+
+/* The inner loop `for v in 1:viter` (gpuCTM.jl:497-507: update_phi!/update_logzeta!/update_vsq!/update_lambda!) with the
+ * CPU model's order and per-document stopping rule (CTM.jl:194-203), the scatter half of update_beta! (gpuCTM.jl:208-229)
+ * and the second moments update_sigma!/update_mu! need (gpuCTM.jl:144-196).  Asynchronous. */
+int tmvb_ctm_estep(tmvb_ctm_t h, int niter, float ntol, int viter, float vtol, int want_elbo);
+
+/* buffers a multi-GPU driver sums over ranks between estep and mstep (stats float, small double) */
+int tmvb_ctm_reduce_buffers(tmvb_ctm_t h, void **stats, int64_t *n_stats, void **small, int64_t *n_small);
+
+/* update_beta!() + update_sigma!() + update_mu!() (CTM.jl:102-118,207-208 / gpuCTM.jl:166-256): beta normalised on the
+ * device; sigma, invsigma = inv(sigma), mu in fp64 on the host from the reduced moments, then pushed to the device. */
+int tmvb_ctm_mstep(tmvb_ctm_t h, int64_t M_total);
+
+/* update_elbo! (gpuCTM.jl:135-142 via check_elbo!).  mode 0: from the partials of the last estep(want_elbo=1)+mstep;
+ * mode 1: full recomputation with the CPU model's lagged-phi semantics (CTM.jl:89-98). */
+int tmvb_ctm_elbo(tmvb_ctm_t h, int mode, int64_t M_total, double *elbo_docs, double *elbo_global);
+
+/* update_host!(model::gpuCTM) (modelutils.jl:518-537); any pointer may be NULL. */
+int tmvb_ctm_download(tmvb_ctm_t h, float *mu, float *sigma, float *invsigma, float *beta, float *lambda, float *vsq, float *logzeta);
+int tmvb_ctm_download_old(tmvb_ctm_t h, float *beta_old, float *lambda_old);
+int tmvb_ctm_materialize_phi(tmvb_ctm_t h, float *phi);
+int tmvb_ctm_topics(tmvb_ctm_t h, int32_t *topics); /* gpuCTM.jl:517 */
+int tmvb_ctm_get_stats(tmvb_ctm_t h, tmvb_stats *out);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,103 @@
+"""GPU parity tests for the CTM path (CUDA through the C ABI vs the fp64 CPU oracle, same seeded inputs).
+The inner Newton solvers run in fp32 against the oracle's fp64, so the per-iteration ELBO agrees to ~1e-6
+rather than LDA's 1e-7; asserted at 2e-5 (north star: 1e-4)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+ELBO_RTOL = 2e-5
+
+
+def _run_pair(tm, orc, c, K, iters, seed=7, nthreads=1):
+    beta0 = tm.synth.init_beta(K, c.V, seed=seed).astype(np.float32)
+    model = tm.gpuCTM(tm.Corpus.from_csr(c), K)
+    model.beta = np.array(beta0.T, order="F", copy=True)
+    trace = []
+    tm.train(model, iter=iters, tol=0.0, checkelbo=1, printelbo=False, trace=trace)
+    st = orc.CTMState(K, c.M, c.V, beta0)
+    ref, sweeps, done = orc.ctm_train(st, c.N_cumsum, c.terms, c.counts, iter=iters, tol=0.0, nthreads=nthreads)
+    ref = ref[np.isfinite(ref)]
+    return model, np.array(trace), st, ref, sweeps
+
+
+@pytest.mark.parametrize("K", [6, 1, 3, 8, 17, 30, 33, 64])
+def test_ctm_elbo_trajectory_small(tm, orc, K):
+    c = tm.synth.gencorp_lda(M=80, V=400, K=5, seed=1)
+    model, trace, st, ref, _ = _run_pair(tm, orc, c, K, iters=5)
+    assert len(trace) == len(ref) >= 2
+    np.testing.assert_allclose(trace, ref, rtol=ELBO_RTOL)
+    np.testing.assert_allclose(model.mu, st.mu, rtol=2e-3, atol=2e-4)
+    np.testing.assert_allclose(model.sigma, st.sigma, rtol=5e-3, atol=5e-4)
+    np.testing.assert_allclose(model.beta.T, st.beta, rtol=1e-2, atol=1e-8)
+    np.testing.assert_allclose(model.lam.T, st.lam, rtol=5e-3, atol=2e-3)
+    np.testing.assert_allclose(model.vsq.T, st.vsq, rtol=5e-3, atol=1e-5)
+    np.testing.assert_allclose(model.logzeta, st.logzeta, rtol=1e-3, atol=1e-3)
+    np.testing.assert_allclose(model.lam_old.T, st.lam_old, rtol=5e-3, atol=2e-3)
+    tm.check_model(model)
+    assert np.all(model.vsq > 0)
+    # invsigma really is the inverse of sigma (gpuCTM.jl:203-205)
+    np.testing.assert_allclose(model.invsigma.astype(np.float64) @ model.sigma.astype(np.float64), np.eye(K), atol=5e-3)
+
+
+def test_ctm_fused_elbo_equals_standalone(tm):
+    c = tm.synth.gencorp_lda(M=120, V=300, K=4, seed=2)
+    K = 9
+    model = tm.gpuCTM(tm.Corpus.from_csr(c), K, seed=5)
+    model.update_buffer()
+    for it in range(3):
+        model.estep(1000, 1.0 / K**2, 10, 1.0 / K**2, want_elbo=True)
+        model.mstep()
+        e0, e1 = model.update_elbo(0), model.update_elbo(1)
+        assert abs(e0 - e1) <= 2e-6 * abs(e1), (it, e0, e1)
+
+
+def test_ctm_ragged_documents_and_phi(tm, orc):
+    rng = np.random.default_rng(0)
+    V, K = 900, 12
+    lens = [0, 1, 2, 40, 700, 0, 33, 64, 65]
+    terms, counts, off = [], [], [0]
+    for L in lens:
+        terms.append(rng.choice(V, size=L, replace=False))
+        counts.append(rng.integers(1, 9, size=L))
+        off.append(off[-1] + L)
+    c = tm.synth.CSR(len(lens), V, np.array(off, np.int64), np.concatenate(terms).astype(np.int64), np.concatenate(counts).astype(np.int64))
+    model, trace, st, ref, _ = _run_pair(tm, orc, c, K, iters=3)
+    np.testing.assert_allclose(trace, ref, rtol=ELBO_RTOL)
+    phi = model.phi
+    got = np.concatenate([p.T for p in phi if p.size], axis=0)
+    np.testing.assert_allclose(got.sum(axis=1), 1.0, rtol=1e-5)      # left-stochastic (modelutils.jl:303-305)
+    for i in range(K):
+        want = np.argsort(model.beta[i, :], kind="stable")[::-1] + 1
+        np.testing.assert_array_equal(np.asarray(model.topics[i]), want)
+
+
+def test_ctm_argument_errors(tm):
+    c = tm.synth.gencorp_lda(M=10, V=50, K=3, seed=0)
+    with pytest.raises(ValueError):
+        tm.gpuCTM(tm.Corpus.from_csr(c), 0)
+    m = tm.gpuCTM(tm.Corpus.from_csr(c), 3)
+    with pytest.raises(ValueError):
+        tm.train(m, ntol=-1.0)
+    m.sigma = -np.eye(3, dtype=np.float32)
+    with pytest.raises(tm.TopicModelError, match="positive-definite"):
+        tm.train(m, iter=1, printelbo=False)
+    m = tm.gpuCTM(tm.Corpus.from_csr(c), 3)
+    m.vsq[0, 0] = -1.0
+    with pytest.raises(tm.TopicModelError, match="vsq must be positive"):
+        tm.train(m, iter=1, printelbo=False)
+    with pytest.raises(ValueError):
+        tm.train(tm.gpuCTM(tm.Corpus.from_csr(c), 65), iter=1, printelbo=False)   # K <= 64 in this build
+
+
+def test_ctm_citeulike_size_parity(tm, orc):
+    """BASELINE config 2: gpuCTM K=30 on CiteULike (16 980 docs x 8 000 vocab; packed real corpus when it travelled
+    with the snapshot, else CiteULike-shaped synthetic).  ELBO within 1e-4 relative of the CPU oracle (asserted 2e-5)."""
+    c = tm.synth.load_packed("citeu") or tm.synth.citeu_shaped()
+    c = tm.synth.CSR(c.M, c.V, c.N_cumsum, c.terms, c.counts)
+    model, trace, st, ref, sweeps = _run_pair(tm, orc, c, 30, iters=3, nthreads=orc.host_threads())
+    rel = np.abs(trace - ref) / np.abs(ref)
+    print("CiteULike-size CTM ELBO gpu   ", trace.tolist())
+    print("CiteULike-size CTM ELBO oracle", ref.tolist())
+    print("rel diff", rel.tolist(), "estep_ms", model.stats().estep_ms)
+    assert np.all(rel < ELBO_RTOL)
+    tm.check_model(model)

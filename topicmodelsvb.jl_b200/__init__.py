@@ -5,4 +5,25 @@ include/tmvb.h); this package is the host-side mirror of the reference's Julia A
 from . import _lib, synth  # noqa: F401
 from ._lib import TopicModelError, build  # noqa: F401
 from .corpus import Corpus, CorpusError, Document, DocumentError  # noqa: F401
-from .gpu_lda import check_elbo, check_model, gpuLDA, train  # noqa: F401
+from .gpu_ctm import check_model_ctm, gpuCTM, train_ctm  # noqa: F401
+from .gpu_lda import check_elbo, gpuLDA  # noqa: F401
+from .gpu_lda import check_model as check_model_lda  # noqa: F401
+from .gpu_lda import train as train_lda  # noqa: F401
+
+
+def train(model, **kwargs):
+    """train!(model; kwargs...) -- dispatches on the model type like the reference's methods."""
+    if isinstance(model, gpuLDA):
+        return train_lda(model, **kwargs)
+    if isinstance(model, gpuCTM):
+        return train_ctm(model, **kwargs)
+    raise TypeError("train!: unsupported model type %r" % type(model).__name__)
+
+
+def check_model(model):
+    """check_model(model) (modelutils.jl:255-360), dispatched on the model type."""
+    if isinstance(model, gpuLDA):
+        return check_model_lda(model)
+    if isinstance(model, gpuCTM):
+        return check_model_ctm(model)
+    raise TypeError("check_model: unsupported model type %r" % type(model).__name__)

@@ -90,6 +90,19 @@ SIGNATURES = {
     "tmvb_lda_sync": (C.c_int, [_vp]),
     "tmvb_lda_get_stats": (C.c_int, [_vp, C.POINTER(TmvbStats)]),
     "tmvb_lda_kld": (C.c_int, [_vp, C.POINTER(C.c_int64)]),
+    "tmvb_ctm_create": (C.c_int, [C.POINTER(_vp), C.c_int64, C.c_int64, C.c_int64, C.c_int, _vp]),
+    "tmvb_ctm_destroy": (C.c_int, [_vp]),
+    "tmvb_ctm_set_corpus": (C.c_int, [_vp, _vp, _vp, _vp]),
+    "tmvb_ctm_upload": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "tmvb_ctm_estep": (C.c_int, [_vp, C.c_int, C.c_float, C.c_int, C.c_float, C.c_int]),
+    "tmvb_ctm_reduce_buffers": (C.c_int, [_vp, C.POINTER(_vp), C.POINTER(C.c_int64), C.POINTER(_vp), C.POINTER(C.c_int64)]),
+    "tmvb_ctm_mstep": (C.c_int, [_vp, C.c_int64]),
+    "tmvb_ctm_elbo": (C.c_int, [_vp, C.c_int, C.c_int64, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
+    "tmvb_ctm_download": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "tmvb_ctm_download_old": (C.c_int, [_vp, _vp, _vp]),
+    "tmvb_ctm_materialize_phi": (C.c_int, [_vp, _vp]),
+    "tmvb_ctm_topics": (C.c_int, [_vp, _vp]),
+    "tmvb_ctm_get_stats": (C.c_int, [_vp, C.POINTER(TmvbStats)]),
 }
 
 

@@ -383,16 +383,16 @@ __global__ void ctm_moments_kernel(const float *__restrict__ lambda, const float
     extern __shared__ float lam_s[];  // [chunk][K_ld]
     const int CHUNK = 32;
     const int npairs = K * K;
-    double acc[8];
+    double acc[16];  // K*K <= 4096 pairs over 256 threads
 #pragma unroll
-    for (int q = 0; q < 8; q++) acc[q] = 0.0;
+    for (int q = 0; q < 16; q++) acc[q] = 0.0;
     double sl = 0.0, sv = 0.0;
     for (long long d0 = (long long)blockIdx.x * CHUNK; d0 < M; d0 += (long long)gridDim.x * CHUNK) {
         const int nd = (int)min((long long)CHUNK, M - d0);
         __syncthreads();
         for (int q = threadIdx.x; q < nd * K_ld; q += blockDim.x) lam_s[q] = lambda[d0 * K_ld + q];
         __syncthreads();
-        for (int q = 0, pr = threadIdx.x; q < 8 && pr < npairs; q++, pr += blockDim.x) {
+        for (int q = 0, pr = threadIdx.x; q < 16 && pr < npairs; q++, pr += blockDim.x) {
             const int i = pr / K, j = pr - i * K;
             double a = 0.0;
             for (int dd = 0; dd < nd; dd++) a += (double)(lam_s[dd * K_ld + i] * lam_s[dd * K_ld + j]);
@@ -404,7 +404,7 @@ __global__ void ctm_moments_kernel(const float *__restrict__ lambda, const float
                 sv += (double)vsq[(d0 + dd) * K_ld + threadIdx.x];
             }
     }
-    for (int q = 0, pr = threadIdx.x; q < 8 && pr < npairs; q++, pr += blockDim.x)
+    for (int q = 0, pr = threadIdx.x; q < 16 && pr < npairs; q++, pr += blockDim.x)
         if (acc[q] != 0.0) atomicAdd(mom + 2 * K_ld + pr, acc[q]);
     if (threadIdx.x < K) {
         atomicAdd(mom + threadIdx.x, sl);

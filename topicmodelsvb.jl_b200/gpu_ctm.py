@@ -1,0 +1,238 @@
+"""gpuCTM -- host mirror of the reference's ``gpuCTM`` model and its ``train!`` (src/gpuCTM.jl) over the C ABI.
+
+Semantics follow the CPU model (src/CTM.jl): update order phi -> logzeta -> vsq -> lambda inside a sweep,
+per-document stopping rule, true log-sum-exp (the OpenCL kernels start their running maximum at 0,
+gpuCTM.jl:404,456), lagged-phi ELBO.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from typing import Optional
+
+import numpy as np
+
+from . import _lib
+from .corpus import Corpus, check_corp
+from .dist import Reducer
+from .gpu_lda import _fmat
+
+
+class gpuCTM:
+    """GPU accelerated correlated topic model (gpuCTM.jl:6-99).  Matrices are Fortran-ordered float32 (K, V) / (K, M)."""
+
+    def __init__(self, corp: Corpus, K: int, seed: Optional[int] = None, device: int = -1,
+                 reducer: Optional[Reducer] = None, M_total: Optional[int] = None, stream: Optional[int] = None):
+        check_corp(corp)
+        if not (isinstance(K, (int, np.integer)) and K > 0):
+            raise ValueError("number of topics must be a positive integer.")  # gpuCTM.jl:55
+        M, V, _ = corp.size()
+        flat = corp.flat()
+        self.K, self.M, self.V = int(K), int(M), int(V)
+        self.N = np.diff(flat.N_cumsum).astype(np.int64)
+        cs = np.concatenate([[0], np.cumsum(flat.counts)]).astype(np.int64)
+        self.C = cs[flat.N_cumsum[1:]] - cs[flat.N_cumsum[:-1]]
+        self.corp = corp
+        self.topics = [np.arange(1, V + 1) for _ in range(K)]
+        rng = np.random.default_rng(seed)
+        self.mu = np.zeros(K, dtype=np.float32)                                   # gpuCTM.jl:63
+        self.sigma = np.eye(K, dtype=np.float32)                                  # gpuCTM.jl:64
+        self.invsigma = np.eye(K, dtype=np.float32)
+        g = rng.standard_exponential(size=(K, V)) if V else np.zeros((K, 0))
+        self.beta = np.asfortranarray((g / g.sum(axis=1, keepdims=True)).astype(np.float32)) if V else np.zeros((K, 0), np.float32, order="F")
+        self.lam = np.zeros((K, M), dtype=np.float32, order="F")                  # `lambda`, gpuCTM.jl:67
+        self.vsq = np.ones((K, M), dtype=np.float32, order="F")                   # gpuCTM.jl:69
+        self.logzeta = np.full(M, 0.5, dtype=np.float32)                          # gpuCTM.jl:70
+        self.beta_old = self.beta.copy(order="F")
+        self.lam_old = self.lam.copy(order="F")
+        self.elbo = 0.0
+        self.reducer = reducer
+        self.M_total = int(M_total) if M_total is not None else self.M
+        self._device, self._stream = device, stream
+        self._h = None
+        self._resident = False
+        self._pinned = None
+
+    # the reference's field is called `lambda`
+    def __getattr__(self, name):
+        if name == "lambda_":
+            return self.lam
+        raise AttributeError(name)
+
+    def _handle(self):
+        if self._h is None:
+            lib = _lib.load()
+            h = C.c_void_p()
+            stream = self._stream if self._stream is not None else (self.reducer.stream_ptr() if self.reducer is not None else None)
+            _lib.check(lib.tmvb_ctm_create(C.byref(h), self.K, self.M, self.V, self._device, stream))
+            self._h = h
+        return self._h
+
+    def close(self):
+        if self._h is not None:
+            _lib.load().tmvb_ctm_destroy(self._h)
+            self._h = None
+            self._resident = False
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def update_buffer(self):
+        """update_buffer!(model::gpuCTM) (modelutils.jl:400-435)."""
+        lib, h = _lib.load(), self._handle()
+        f = self.corp.flat()
+        _lib.check(lib.tmvb_ctm_set_corpus(h, _lib.ptr(f.N_cumsum), _lib.ptr(f.terms), _lib.ptr(f.counts)))
+        self.mu = np.ascontiguousarray(self.mu, dtype=np.float32)
+        self.sigma = np.ascontiguousarray(self.sigma, dtype=np.float32)
+        if self.sigma.shape != (self.K, self.K):
+            raise _lib.TopicModelError("sigma must be of size (K, K).")
+        self.beta = _fmat(self.beta, self.K, self.V, "beta")
+        self.lam = _fmat(self.lam, self.K, self.M, "lambda")
+        self.vsq = _fmat(self.vsq, self.K, self.M, "vsq")
+        self.logzeta = np.ascontiguousarray(self.logzeta, dtype=np.float32)
+        _lib.check(lib.tmvb_ctm_upload(h, _lib.ptr(self.mu), _lib.ptr(self.sigma), self.beta.ctypes.data, self.lam.ctypes.data,
+                                       self.vsq.ctypes.data, _lib.ptr(self.logzeta)))
+        self._resident = True
+
+    def update_host(self):
+        """update_host!(model::gpuCTM) (modelutils.jl:518-537) minus phi."""
+        if not self._resident:
+            return
+        lib, h = _lib.load(), self._handle()
+        if self._pinned is None:
+            pe = _lib.pinned_empty
+            K, M, V = self.K, self.M, self.V
+            self._pinned = dict(beta=pe((K, V), np.float32, order="F"), beta_old=pe((K, V), np.float32, order="F"),
+                                lam=pe((K, M), np.float32, order="F"), lam_old=pe((K, M), np.float32, order="F"),
+                                vsq=pe((K, M), np.float32, order="F"), topics=pe((K, V), np.int32))
+        pb = self._pinned
+        self.mu = np.empty(self.K, np.float32)
+        self.sigma = np.empty((self.K, self.K), np.float32)
+        self.invsigma = np.empty((self.K, self.K), np.float32)
+        self.logzeta = np.empty(self.M, np.float32)
+        self.beta, self.beta_old, self.lam, self.lam_old, self.vsq = pb["beta"], pb["beta_old"], pb["lam"], pb["lam_old"], pb["vsq"]
+        _lib.check(lib.tmvb_ctm_download(h, _lib.ptr(self.mu), _lib.ptr(self.sigma), _lib.ptr(self.invsigma), self.beta.ctypes.data,
+                                         self.lam.ctypes.data, self.vsq.ctypes.data, _lib.ptr(self.logzeta)))
+        _lib.check(lib.tmvb_ctm_download_old(h, self.beta_old.ctypes.data, self.lam_old.ctypes.data))
+
+    def update_topics(self):
+        if not self.V:
+            return
+        if not self._resident:
+            self.topics = [np.argsort(self.beta[i, :], kind="stable")[::-1] + 1 for i in range(self.K)]
+            return
+        if self._pinned is None:
+            self.update_host()
+        t = self._pinned["topics"]
+        _lib.check(_lib.load().tmvb_ctm_topics(self._handle(), t.ctypes.data))
+        self.topics = list(t)
+
+    @property
+    def phi(self):
+        f = self.corp.flat()
+        if not self._resident:
+            self.update_buffer()
+        out = np.zeros((f.nnz, self.K), dtype=np.float32)
+        _lib.check(_lib.load().tmvb_ctm_materialize_phi(self._handle(), _lib.ptr(out)))
+        return [out[f.N_cumsum[d]:f.N_cumsum[d + 1]].T for d in range(self.M)]
+
+    def stats(self) -> _lib.TmvbStats:
+        st = _lib.TmvbStats()
+        _lib.check(_lib.load().tmvb_ctm_get_stats(self._handle(), C.byref(st)))
+        return st
+
+    def estep(self, niter, ntol, viter, vtol, want_elbo=True):
+        """update_phi!/update_logzeta!/update_vsq!/update_lambda! for v in 1:viter (gpuCTM.jl:497-507) + scatter + moments."""
+        _lib.check(_lib.load().tmvb_ctm_estep(self._handle(), int(niter), float(ntol), int(viter), float(vtol), int(bool(want_elbo))))
+
+    def mstep(self):
+        """update_beta!(), update_sigma!(), update_mu!() (gpuCTM.jl:509-511)."""
+        if self.reducer is not None:
+            lib, h = _lib.load(), self._handle()
+            sp, sn, mp, mn = C.c_void_p(), C.c_int64(), C.c_void_p(), C.c_int64()
+            _lib.check(lib.tmvb_ctm_reduce_buffers(h, C.byref(sp), C.byref(sn), C.byref(mp), C.byref(mn)))
+            dev = self.reducer.torch.cuda.current_device()
+            self.reducer.allreduce_device([(sp.value, sn.value, "<f4"), (mp.value, mn.value, "<f8")], dev)
+        _lib.check(_lib.load().tmvb_ctm_mstep(self._handle(), self.M_total))
+
+    def update_elbo(self, mode: int = 0) -> float:
+        docs, glob = C.c_double(), C.c_double()
+        _lib.check(_lib.load().tmvb_ctm_elbo(self._handle(), mode, self.M_total, C.byref(docs), C.byref(glob)))
+        d = docs.value
+        if mode == 1 and self.reducer is not None:
+            d = self.reducer.allreduce_host(d)
+        self.elbo = d + glob.value
+        return self.elbo
+
+
+def check_model_ctm(model: gpuCTM) -> None:
+    """check_model(model::gpuCTM) (modelutils.jl:281-309): shapes and the global parameters on the host; the
+    element-wise invariants of beta / lambda / vsq / logzeta run on the device copy during update_buffer!."""
+    E = _lib.TopicModelError
+    K, M, V = model.K, model.M, model.V
+    if M != len(model.corp):
+        raise E("M must equal the number of documents in the corpus.")
+    if not np.all(np.isfinite(model.mu)):
+        raise E("mu must be finite.")
+    if np.shape(model.sigma) != (K, K):
+        raise E("sigma must be of size (K, K).")
+    try:
+        np.linalg.cholesky(np.asarray(model.sigma, dtype=np.float64))
+    except np.linalg.LinAlgError:
+        raise E("sigma must be positive-definite.")
+    if np.shape(model.beta) != (K, V):
+        raise E("beta must be of size (K, V).")
+    if V:
+        rs = np.asarray(model.beta).sum(axis=1, dtype=np.float64)
+        if not np.allclose(rs, 1.0, rtol=math.sqrt(np.finfo(np.float32).eps)):
+            raise E("beta must be a right stochastic matrix.")
+    if np.shape(model.lam) != (K, M):
+        raise E("lambda must contain M vectors of length K.")
+    if np.shape(model.vsq) != (K, M):
+        raise E("vsq must contain M vectors of length K.")
+    if np.shape(model.logzeta) != (M,):
+        raise E("logzeta must be of length M.")
+    if not math.isfinite(model.elbo):
+        raise E("elbo must be finite.")
+
+
+def train_ctm(model: gpuCTM, iter: int = 150, tol: float = 1.0, niter: int = 1000, ntol: Optional[float] = None,
+              viter: int = 10, vtol: Optional[float] = None, checkelbo=1, printelbo: bool = True, trace: Optional[list] = None):
+    """train!(model::gpuCTM; iter, tol, niter, ntol, viter, vtol, checkelbo, printelbo) (gpuCTM.jl:487-519)."""
+    from .gpu_lda import check_elbo
+
+    K = model.K
+    ntol = 1.0 / K**2 if ntol is None else ntol
+    vtol = 1.0 / K**2 if vtol is None else vtol
+    check_model_ctm(model)
+    if not all(t >= 0 for t in (tol, ntol, vtol)):
+        raise ValueError("tolerance parameters must be nonnegative.")
+    if not all(t >= 0 for t in (iter, niter, viter)):
+        raise ValueError("iteration parameters must be nonnegative.")
+    if not ((isinstance(checkelbo, (int, np.integer)) and checkelbo > 0) or checkelbo == math.inf):
+        raise ValueError("checkelbo parameter must be a positive integer or Inf.")
+    if model.corp.flat().nnz == 0 and model.reducer is None:
+        iter = 0
+    else:
+        model.update_buffer()
+    check = checkelbo != math.inf
+    if check and checkelbo <= iter:
+        model.update_elbo(1)
+        if trace is not None:
+            trace.append(model.elbo)
+    for k in range(1, iter + 1):
+        want = check and (k % checkelbo == 0)
+        model.estep(niter, ntol, viter, vtol, want_elbo=want)       # gpuCTM.jl:497-507
+        model.mstep()                                               # gpuCTM.jl:509-511
+        stop = check_elbo(model, checkelbo, printelbo, k, tol)      # gpuCTM.jl:513
+        if want and trace is not None:
+            trace.append(model.elbo)
+        if stop:
+            break
+    if iter > 0:
+        model.update_host()
+    model.update_topics()                                           # gpuCTM.jl:517
+    return None
