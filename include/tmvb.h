@@ -33,6 +33,7 @@ extern "C" {
 
 typedef struct tmvb_lda_s *tmvb_lda_t;
 typedef struct tmvb_ctm_s *tmvb_ctm_t;
+typedef struct tmvb_ctpf_s *tmvb_ctpf_t;
 
 /* Timings (ms, CUDA events on the handle's stream) and counters of the most recent calls. */
 typedef struct tmvb_stats {
@@ -157,6 +158,45 @@ int tmvb_ctm_download_old(tmvb_ctm_t h, float *beta_old, float *lambda_old);
 int tmvb_ctm_materialize_phi(tmvb_ctm_t h, float *phi);
 int tmvb_ctm_topics(tmvb_ctm_t h, int32_t *topics); /* gpuCTM.jl:517 */
 int tmvb_ctm_get_stats(tmvb_ctm_t h, tmvb_stats *out);
+
+
+/* ------------------------------------------------------------------ CTPF ----------------- */
+
+/* gpuCTPF(corp, K) device side (gpuCTPF.jl:121-147: context + 12 cl.Program builds).  Starts from a..h = 0.1 and all
+ * rates = 1 (gpuCTPF.jl:107-119). */
+int tmvb_ctpf_create(tmvb_ctpf_t *h, int64_t K, int64_t M, int64_t V, int64_t U, int device, void *stream);
+int tmvb_ctpf_destroy(tmvb_ctpf_t h);
+
+/* update_buffer!(model::gpuCTPF), corpus half (modelutils.jl:439-472): terms/counts and readers/ratings CSR (0-based Int64).
+ * The inverted indices (J_cumsum, Y_cumsum, *_sortperm) are not needed. */
+int tmvb_ctpf_set_corpus(tmvb_ctpf_t h, const int64_t *N_cumsum, const int64_t *terms, const int64_t *counts, const int64_t *R_cumsum,
+                         const int64_t *readers, const int64_t *ratings);
+
+/* update_buffer!(model::gpuCTPF), parameter half (modelutils.jl:474-493): hyp[8] = {a,b,c,d,e,f,g,h} (the struct fields
+ * gpuCTPF.jl:26-33), alef[K*V], he[K*U], bet[K], vav[K], gimel[K*M], zayin[K*M], dalet[K], het[K].  Any pointer may be NULL. */
+int tmvb_ctpf_upload(tmvb_ctpf_t h, const double *hyp, const float *alef, const float *he, const float *bet, const float *vav,
+                     const float *gimel, const float *zayin, const float *dalet, const float *het);
+
+/* The inner loop (gpuCTPF.jl:687-697: update_xi!/update_phi!/update_zayin!/update_gimel!) with the CPU model's formulas and
+ * per-document stopping rule (CTPF.jl:353-362), then the scatter halves of update_he!/update_alef! (CTPF.jl:259-277). */
+int tmvb_ctpf_estep(tmvb_ctpf_t h, int viter, float vtol, int want_elbo);
+
+int tmvb_ctpf_reduce_buffers(tmvb_ctpf_t h, void **stats_alef, int64_t *n_alef, void **stats_he, int64_t *n_he, void **small, int64_t *n_small);
+
+/* update_he!(), update_alef!(), update_dalet!(), update_het!(), update_bet!(), update_vav!() in the reference's order
+ * (CTPF.jl:366-371 / gpuCTPF.jl:699-704): shapes on the device, the four rate vectors in fp64 on the host. */
+int tmvb_ctpf_mstep(tmvb_ctpf_t h, int64_t M_total);
+
+/* update_elbo! (gpuCTPF.jl:280-286).  mode 0: from the partials of the last estep(want_elbo=1)+mstep; mode 1: recomputed
+ * per document with the CPU model's lagged phi / xi (CTPF.jl:232-247). */
+int tmvb_ctpf_elbo(tmvb_ctpf_t h, int mode, int64_t M_total, double *elbo_docs, double *elbo_global);
+
+/* update_host!(model::gpuCTPF) (modelutils.jl:540-570) and the *_old copies of the CPU struct (CTPF.jl:27-45) */
+int tmvb_ctpf_download(tmvb_ctpf_t h, float *alef, float *he, float *bet, float *vav, float *gimel, float *zayin, float *dalet, float *het);
+int tmvb_ctpf_download_old(tmvb_ctpf_t h, float *alef_old, float *he_old, float *bet_old, float *vav_old, float *gimel_old, float *zayin_old,
+                           float *dalet_old, float *het_old);
+int tmvb_ctpf_topics(tmvb_ctpf_t h, int32_t *topics); /* gpuCTPF.jl:706-707 */
+int tmvb_ctpf_get_stats(tmvb_ctpf_t h, tmvb_stats *out);
 
 #ifdef __cplusplus
 }

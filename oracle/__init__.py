@@ -80,6 +80,9 @@ def load():
         _c.c_int64, _c.c_int64, _c.c_int64, _i64p, _i64p, _i64p,
         _f64p, _f64p, _f64p, _f64p, _f64p, _f64p, _f64p, _f64p, _c.c_int,
     ]
+    lib.orc_ctpf_train.restype = _c.c_int
+    lib.orc_ctpf_train.argtypes = ([_c.c_int64] * 4 + [_i64p] * 6 + [_f64p] * 17
+                                   + [_c.c_int, _c.c_double, _c.c_int, _c.c_double, _c.c_int, _f64p, _i64p, _c.POINTER(_c.c_int), _c.c_int])
     _lib = lib
     return lib
 
@@ -211,6 +214,44 @@ def ctm_train(st: CTMState, N_cumsum, terms, counts, iter=150, tol=1.0, niter=10
                       np.ascontiguousarray(counts, dtype=np.int64), st.mu, st.sigma, st.invsigma, st.beta, st.beta_old,
                       st.lam, st.lam_old, st.vsq, st.logzeta, int(iter), float(tol), int(niter), float(ntol), int(viter),
                       float(vtol), ce, trace, sweeps, _c.byref(done), int(nthreads))
+    fin = trace[np.isfinite(trace)]
+    if fin.size:
+        st.elbo = float(fin[-1])
+    return trace, sweeps[:iter], done.value
+
+
+class CTPFState:
+    """The mutable fields of the reference's ``CTPF`` struct (CTPF.jl:6-47, init :81-103) as fp64 arrays."""
+
+    def __init__(self, K, M, V, U, alef, hyp=None):
+        self.K, self.M, self.V, self.U = int(K), int(M), int(V), int(U)
+        self.hyp = np.full(8, 0.1) if hyp is None else np.array(hyp, dtype=np.float64)
+        self.alef = np.ascontiguousarray(alef, dtype=np.float64).reshape(V, K).copy()
+        self.he = np.ones((max(U, 1), K))[:U] if U else np.ones((0, K))
+        self.bet, self.vav, self.dalet, self.het = np.ones(K), np.ones(K), np.ones(K), np.ones(K)
+        self.gimel, self.zayin = np.ones((M, K)), np.ones((M, K))
+        for n in ("alef", "he", "bet", "vav", "dalet", "het", "gimel", "zayin"):
+            setattr(self, n + "_old", getattr(self, n).copy())
+        self.elbo = 0.0
+
+
+def ctpf_train(st: CTPFState, c, iter=150, tol=1.0, viter=10, vtol=None, checkelbo=1, nthreads=1):
+    """train!(model::CTPF; ...) (CTPF.jl:344-371) on the C oracle; ``c`` is a synth.CSR with reader lists."""
+    lib = load()
+    K = st.K
+    vtol = 1.0 / K**2 if vtol is None else vtol
+    trace = np.full(iter + 1, np.nan)
+    sweeps = np.zeros(max(iter, 1), dtype=np.int64)
+    done = _c.c_int(0)
+    ce = 0 if (checkelbo is None or checkelbo == float("inf")) else int(checkelbo)
+    i64 = lambda a: np.ascontiguousarray(a, dtype=np.int64)
+    he = np.ascontiguousarray(st.he)
+    he_old = np.ascontiguousarray(st.he_old)
+    lib.orc_ctpf_train(K, st.M, st.V, st.U, i64(c.N_cumsum), i64(c.terms), i64(c.counts), i64(c.R_cumsum), i64(c.readers),
+                       i64(c.ratings), st.hyp, st.alef, st.alef_old, he, he_old, st.bet, st.bet_old, st.vav, st.vav_old,
+                       st.gimel, st.gimel_old, st.zayin, st.zayin_old, st.dalet, st.dalet_old, st.het, st.het_old,
+                       int(iter), float(tol), int(viter), float(vtol), ce, trace, sweeps, _c.byref(done), int(nthreads))
+    st.he, st.he_old = he, he_old
     fin = trace[np.isfinite(trace)]
     if fin.size:
         st.elbo = float(fin[-1])

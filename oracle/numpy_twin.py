@@ -259,3 +259,110 @@ class CTMTwin:
                 if delta < tol:
                     break
         return np.array(trace)
+
+
+class CTPFTwin:
+    """src/CTPF.jl restated with NumPy.  The ELBO uses the closed form the Binomial * lnGamma sums of
+    Elogpya/Elogpyb/Elogpz (CTPF.jl:111-141) and of Distributions' entropy(Multinomial) (CTPF.jl:179-194) collapse
+    to -- per token -lnG(c+1) + c H(phi_n), per reader -lnG(r+1) + r H(xi_r) -- so agreement with the C oracle
+    (which evaluates the long form) also checks that identity."""
+
+    def __init__(self, N_cumsum, terms, counts, R_cumsum, readers, ratings, K, V, U, alef, hyp=None):
+        self.K, self.V, self.U = K, V, U
+        self.M = len(N_cumsum) - 1
+        self.off, self.roff = np.asarray(N_cumsum, np.int64), np.asarray(R_cumsum, np.int64)
+        self.terms, self.counts = np.asarray(terms, np.int64), np.asarray(counts, np.float64)
+        self.readers, self.ratings = np.asarray(readers, np.int64), np.asarray(ratings, np.float64)
+        self.a, self.b, self.c, self.d, self.e, self.f, self.g, self.h = (0.1,) * 8 if hyp is None else hyp
+        self.alef = np.array(alef, dtype=np.float64).reshape(V, K)          # CTPF.jl:83-100
+        self.he = np.ones((U, K))
+        self.bet, self.vav, self.dalet, self.het = np.ones(K), np.ones(K), np.ones(K), np.ones(K)
+        self.gimel, self.zayin = np.ones((self.M, K)), np.ones((self.M, K))
+        for n in ("alef", "he", "bet", "vav", "dalet", "het", "gimel", "zayin"):
+            setattr(self, n + "_old", getattr(self, n).copy())
+        self.alef_temp, self.he_temp = np.full((V, K), self.a), np.full((U, K), self.e)
+        self.elbo = 0.0
+
+    @staticmethod
+    def _softmax_rows(x):
+        x = np.exp(x - x.max(axis=1, keepdims=True))
+        return x / x.sum(axis=1, keepdims=True)
+
+    def _phi(self, d, alef, gimel, dalet, bet):  # CTPF.jl:327-330
+        t = self.terms[self.off[d]:self.off[d + 1]]
+        return self._softmax_rows((digamma(gimel[d]) - np.log(dalet) - np.log(bet))[None, :] + digamma(alef[t]))
+
+    def _xi(self, d, he, gimel, zayin, dalet, het, vav):  # CTPF.jl:334-337
+        r = self.readers[self.roff[d]:self.roff[d + 1]]
+        ph = digamma(he[r])
+        xa = (digamma(gimel[d]) - np.log(dalet) - np.log(vav))[None, :] + ph
+        xb = (digamma(zayin[d]) - np.log(het) - np.log(vav))[None, :] + ph
+        return self._softmax_rows(np.concatenate([xa, xb], axis=1)) if len(r) else np.zeros((0, 2 * self.K))
+
+    @staticmethod
+    def _ent_gamma(alpha, theta):
+        return alpha + np.log(theta) + gammaln(alpha) + (1 - alpha) * digamma(alpha)
+
+    def update_elbo(self):  # CTPF.jl:111-247
+        K = self.K
+        a, b, c, dd, e, f, g, h = self.a, self.b, self.c, self.d, self.e, self.f, self.g, self.h
+        x = self.V * K * (a * np.log(b) - gammaln(a)) + np.sum((a - 1) * (digamma(self.alef) - np.log(self.bet)[None, :]) - b * self.alef / self.bet[None, :])
+        x += np.sum(self._ent_gamma(self.alef, 1.0 / self.bet[None, :]))
+        x += self.U * K * (e * np.log(f) - gammaln(e)) + np.sum((e - 1) * (digamma(self.he) - np.log(self.vav)[None, :]) - f * self.he / self.vav[None, :])
+        x += np.sum(self._ent_gamma(self.he, 1.0 / self.vav[None, :]))
+        alsum, hesum = self.alef.sum(axis=0), self.he.sum(axis=0)
+        for d in range(self.M):
+            t, cn = self.terms[self.off[d]:self.off[d + 1]], self.counts[self.off[d]:self.off[d + 1]]
+            r, ra = self.readers[self.roff[d]:self.roff[d + 1]], self.ratings[self.roff[d]:self.roff[d + 1]]
+            phi = self._phi(d, self.alef_old, self.gimel_old, self.dalet_old, self.bet_old)
+            xi = self._xi(d, self.he_old, self.gimel_old, self.zayin_old, self.dalet_old, self.het_old, self.vav_old)
+            gm, zy = self.gimel[d], self.zayin[d]
+            x -= np.dot(gm / (self.dalet * self.vav), hesum) + np.dot(zy / (self.het * self.vav), hesum) + np.dot(gm / (self.dalet * self.bet), alsum)
+            ph = digamma(self.he[r])
+            x += np.sum(ra[:, None] * xi[:, :K] * ((digamma(gm) - np.log(self.dalet) - np.log(self.vav))[None, :] + ph))
+            x += np.sum(ra[:, None] * xi[:, K:] * ((digamma(zy) - np.log(self.het) - np.log(self.vav))[None, :] + ph))
+            x += np.sum(cn[:, None] * phi * ((digamma(gm) - np.log(self.dalet) - np.log(self.bet))[None, :] + digamma(self.alef[t])))
+            with np.errstate(divide="ignore", invalid="ignore"):
+                hx = -np.where(xi > 0, xi * np.log(xi), 0.0).sum(axis=1)
+                hp = -np.where(phi > 0, phi * np.log(phi), 0.0).sum(axis=1)
+            x += np.sum(ra * hx - gammaln(ra + 1)) + np.sum(cn * hp - gammaln(cn + 1))
+            x += K * (c * np.log(dd) - gammaln(c)) + np.sum((c - 1) * (digamma(gm) - np.log(self.dalet)) - dd * gm / self.dalet)
+            x += K * (g * np.log(h) - gammaln(g)) + np.sum((g - 1) * (digamma(zy) - np.log(self.het)) - h * zy / self.het)
+            x += np.sum(self._ent_gamma(gm, 1.0 / self.dalet)) + np.sum(self._ent_gamma(zy, 1.0 / self.het))
+        self.elbo = x
+        return x
+
+    def train(self, iter=150, tol=1.0, viter=10, vtol=None, checkelbo=1):  # CTPF.jl:344-371
+        K = self.K
+        vtol = 1.0 / K**2 if vtol is None else vtol
+        trace = [np.nan] * (iter + 1)
+        if checkelbo <= iter:
+            trace[0] = self.update_elbo()
+        for k in range(1, iter + 1):
+            for d in range(self.M):
+                t, cn = self.terms[self.off[d]:self.off[d + 1]], self.counts[self.off[d]:self.off[d + 1]]
+                r, ra = self.readers[self.roff[d]:self.roff[d + 1]], self.ratings[self.roff[d]:self.roff[d + 1]]
+                for _ in range(viter):
+                    xi = self._xi(d, self.he, self.gimel, self.zayin, self.dalet, self.het, self.vav)
+                    phi = self._phi(d, self.alef, self.gimel, self.dalet, self.bet)
+                    self.zayin_old[d] = self.zayin[d]
+                    self.zayin[d] = self.g + ra @ xi[:, K:]
+                    self.gimel_old[d] = self.gimel[d]
+                    self.gimel[d] = self.c + cn @ phi + ra @ xi[:, :K]
+                    if np.linalg.norm(self.gimel[d] - self.gimel_old[d]) < vtol:
+                        break
+                np.add.at(self.he_temp, r, (xi[:, :K] + xi[:, K:]) * ra[:, None])
+                self.alef_temp[t] += phi * cn[:, None]
+            self.he_old, self.he, self.he_temp = self.he, self.he_temp, np.full((self.U, K), self.e)
+            self.alef_old, self.alef, self.alef_temp = self.alef, self.alef_temp, np.full((self.V, K), self.a)
+            self.dalet_old, self.dalet = self.dalet, self.d + self.alef.sum(axis=0) / self.bet + self.he.sum(axis=0) / self.vav
+            self.het_old, self.het = self.het, self.h + self.he.sum(axis=0) / self.vav
+            self.bet_old, self.bet = self.bet, self.b + self.gimel.sum(axis=0) / self.dalet
+            self.vav_old, self.vav = self.vav, self.f + self.gimel.sum(axis=0) / self.dalet + self.zayin.sum(axis=0) / self.het
+            if k % checkelbo == 0:
+                old = self.elbo
+                delta = self.update_elbo() - old
+                trace[k] = self.elbo
+                if delta < tol:
+                    break
+        return np.array(trace)

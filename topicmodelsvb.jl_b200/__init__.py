@@ -6,6 +6,7 @@ from . import _lib, synth  # noqa: F401
 from ._lib import TopicModelError, build  # noqa: F401
 from .corpus import Corpus, CorpusError, Document, DocumentError  # noqa: F401
 from .gpu_ctm import check_model_ctm, gpuCTM, train_ctm  # noqa: F401
+from .gpu_ctpf import check_model_ctpf, gpuCTPF, train_ctpf  # noqa: F401
 from .gpu_lda import check_elbo, gpuLDA  # noqa: F401
 from .gpu_lda import check_model as check_model_lda  # noqa: F401
 from .gpu_lda import train as train_lda  # noqa: F401
@@ -17,6 +18,8 @@ def train(model, **kwargs):
         return train_lda(model, **kwargs)
     if isinstance(model, gpuCTM):
         return train_ctm(model, **kwargs)
+    if isinstance(model, gpuCTPF):
+        return train_ctpf(model, **kwargs)
     raise TypeError("train!: unsupported model type %r" % type(model).__name__)
 
 
@@ -26,4 +29,6 @@ def check_model(model):
         return check_model_lda(model)
     if isinstance(model, gpuCTM):
         return check_model_ctm(model)
+    if isinstance(model, gpuCTPF):
+        return check_model_ctpf(model)
     raise TypeError("check_model: unsupported model type %r" % type(model).__name__)

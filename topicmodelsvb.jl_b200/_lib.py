@@ -103,6 +103,18 @@ SIGNATURES = {
     "tmvb_ctm_materialize_phi": (C.c_int, [_vp, _vp]),
     "tmvb_ctm_topics": (C.c_int, [_vp, _vp]),
     "tmvb_ctm_get_stats": (C.c_int, [_vp, C.POINTER(TmvbStats)]),
+    "tmvb_ctpf_create": (C.c_int, [C.POINTER(_vp), C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int, _vp]),
+    "tmvb_ctpf_destroy": (C.c_int, [_vp]),
+    "tmvb_ctpf_set_corpus": (C.c_int, [_vp] * 7),
+    "tmvb_ctpf_upload": (C.c_int, [_vp] * 10),
+    "tmvb_ctpf_estep": (C.c_int, [_vp, C.c_int, C.c_float, C.c_int]),
+    "tmvb_ctpf_reduce_buffers": (C.c_int, [_vp, C.POINTER(_vp), C.POINTER(C.c_int64), C.POINTER(_vp), C.POINTER(C.c_int64), C.POINTER(_vp), C.POINTER(C.c_int64)]),
+    "tmvb_ctpf_mstep": (C.c_int, [_vp, C.c_int64]),
+    "tmvb_ctpf_elbo": (C.c_int, [_vp, C.c_int, C.c_int64, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
+    "tmvb_ctpf_download": (C.c_int, [_vp] * 9),
+    "tmvb_ctpf_download_old": (C.c_int, [_vp] * 9),
+    "tmvb_ctpf_topics": (C.c_int, [_vp, _vp]),
+    "tmvb_ctpf_get_stats": (C.c_int, [_vp, C.POINTER(TmvbStats)]),
 }
 
 

@@ -1,0 +1,942 @@
+// tmvb_ctpf.cu -- collaborative topic Poisson factorization coordinate-ascent VB on sm_100a and the tmvb_ctpf_* C ABI.
+//
+// Reference semantics: the CPU model src/CTPF.jl (per-document stopping rule ||gimel - gimel_old|| < vtol, `vav` in
+// update_xi where the OpenCL kernel has `bet` (gpuCTPF.jl:624 vs CTPF.jl:336), lagged phi/xi ELBO).  Replaced:
+// src/gpuCTPF.jl's 12 OpenCL kernels + modelutils.jl:438-494,540-570.
+//
+// The two softmaxes of a sweep share the structure of tmvb_estep.cuh:
+//   phi_n  = softmax_i(psi(gimel_i) - ln dalet_i - ln bet_i + psi(alef[i,w_n]))            (CTPF.jl:327-330)
+//          = A[i,w_n] ephi_i / s_n,   A = exp(psi(alef) - rowmax)  (a K x V table rebuilt once per outer iteration
+//            instead of one digamma per (topic, token, sweep), gpuCTPF.jl:560),  ephi = exp(psi(gimel) - ln dalet - ln bet - max)
+//   xi_r   = softmax over 2K of [psi(gimel) - ln dalet - ln vav + psi(he[:,r]) ; psi(zayin) - ln het - ln vav + psi(he[:,r])]
+//          = [H[:,r] ea ; H[:,r] eb] / s_r,   H = exp(psi(he) - rowmax) (K x U table)              (CTPF.jl:334-337)
+// so gimel = c + ephi .* gphi + ea .* gx and zayin = g + eb .* gx with gphi = sum_n A[:,w_n] c_n/s_n, gx = sum_r H[:,r] rating_r/s_r
+// (CTPF.jl:309-323): two token passes per sweep over two shared-memory tiles (term rows of A, reader rows of H).
+// Scatters (CTPF.jl:259-262,274-277) and rate updates (CTPF.jl:281-305) follow; the global Gamma-rate algebra runs in fp64
+// on the host from K-vectors.
+#include <algorithm>
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "tmvb_shard.cuh"
+
+namespace tmvb {
+
+enum { KV_LNDB = 0, KV_LNDV, KV_LNHV, KV_LN_DALET, KV_LN_BET, KV_LN_VAV, KV_LN_HET, KV_AL_DB, KV_HE_DV, KV_HE_HV, KV_INV_DALET, KV_INV_HET,
+       KV_LNDB_OLD, KV_LNDV_OLD, KV_LNHV_OLD, KV_COUNT };
+
+struct CtpfDev {
+    int K, K_ld, V, U, RS;
+    long long M;
+    const float *A;       // [V][K_ld] exp(psi(alef) - rowmax)
+    const float *H;       // [U][K_ld] exp(psi(he) - rowmax)
+    float *stats_a;       // [V][K_ld]
+    float *stats_h;       // [U][K_ld]
+    const long long *doc_off, *r_off;
+    const int *terms, *readers;
+    const float *counts, *ratings;
+    float *gimel, *gimel_old, *zayin, *zayin_old;  // [M][K_ld]
+    const float *kv;      // [KV_COUNT][K_ld]
+    double *small;        // [K_ld] sum gimel | [K_ld] sum zayin | [1] per-document ELBO terms | [1] sweeps
+    float hc, hg;         // hyper-parameters c and g (shape priors of theta and epsilon)
+    int viter;
+    float vtol;
+    int stage_bulk, dbg;
+};
+
+static size_t ctpf_fixed_smem(int RS, int lpt) { return 16 + (size_t)(32 / lpt) * RS * 4 + (size_t)RS * 4; }
+
+__device__ __forceinline__ float warp_max_f(float v)
+{
+#pragma unroll
+    for (int m = 16; m > 0; m >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, m));
+    return v;
+}
+
+template <int LPT, int CPL, bool ELBO>
+__global__ void __launch_bounds__(32) ctpf_estep_kernel(const CtpfDev p, int doc_begin, int doc_end, int cap, int cap2, int *counter)
+{
+    constexpr int S = 32 / LPT;
+    constexpr int R = (LPT * CPL + 7) / 8;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x;
+    const int kl = lane % LPT, ts = lane / LPT;
+    const int K = p.K, K_ld = p.K_ld, CH = K_ld >> 2, RS = p.RS;
+    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+
+    unsigned long long *mbar = reinterpret_cast<unsigned long long *>(smem_raw);
+    float *gs = reinterpret_cast<float *>(smem_raw + 16);  // [S][RS]
+    float *e_s = gs + (size_t)S * RS;                      // [RS]
+    float *tile = e_s + RS;                                // [cap][RS]   term rows of A
+    float *tile2 = tile + (size_t)cap * RS;                // [cap2][RS]  reader rows of H
+    float *cnt_s = tile2 + (size_t)cap2 * RS;              // [cap]
+    float *cnt2_s = cnt_s + cap;                           // [cap2]
+    int *term_s = reinterpret_cast<int *>(cnt2_s + cap2);  // [cap]
+    int *term2_s = term_s + cap;                           // [cap2]
+
+    float lndb_k[R], lndv_k[R], lnhv_k[R];
+    double gs_k[R], zs_k[R];
+#pragma unroll
+    for (int r = 0; r < R; r++) {
+        const int i = lane + 32 * r;
+        lndb_k[r] = (i < K) ? p.kv[KV_LNDB * K_ld + i] : 0.0f;
+        lndv_k[r] = (i < K) ? p.kv[KV_LNDV * K_ld + i] : 0.0f;
+        lnhv_k[r] = (i < K) ? p.kv[KV_LNHV * K_ld + i] : 0.0f;
+        gs_k[r] = zs_k[r] = 0.0;
+    }
+    const float dscale = (p.vtol > 0.0f) ? 1048576.0f / (p.vtol * p.vtol) : 0.0f;
+    double elbo_thr = 0.0;
+    unsigned long long sweeps_thr = 0;
+    unsigned phase = 0;
+    if (p.stage_bulk) {
+        if (lane == 0) mbar_init(mbar, 1);
+    }
+    __syncwarp();
+
+    for (;;) {
+        int d = 0;
+        if (lane == 0) d = doc_begin + atomicAdd(counter, 1);
+        d = __shfl_sync(0xffffffffu, d, 0);
+        if (d >= doc_end) break;
+        const long long o = p.doc_off[d], ro = p.r_off[d];
+        const int Nd = (int)(p.doc_off[d + 1] - o), Rd = (int)(p.r_off[d + 1] - ro);
+        const int ns = min(Nd, cap), nr = min(Rd, cap2);
+        const bool ovf = Nd > cap, ovf2 = Rd > cap2;
+
+        // stage both tiles under one mbarrier transaction
+        __syncwarp();
+        float lg_c = 0.0f;  // sum_n lnG(c_n + 1) + sum_r lnG(rating_r + 1)
+        for (int n = lane; n < Nd; n += 32) {
+            const float c = p.counts[o + n];
+            if (ELBO && c > 1.5f) lg_c += lgammaf(c + 1.0f);
+            if (n < ns) {
+                term_s[n] = p.terms[o + n];
+                cnt_s[n] = c;
+            }
+        }
+        for (int n = lane; n < Rd; n += 32) {
+            const float c = p.ratings[ro + n];
+            if (ELBO && c > 1.5f) lg_c += lgammaf(c + 1.0f);
+            if (n < nr) {
+                term2_s[n] = p.readers[ro + n];
+                cnt2_s[n] = c;
+            }
+        }
+        if (p.stage_bulk) {
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_expect_tx(mbar, (unsigned)((ns + nr) * K_ld * 4));
+            __syncwarp();
+            for (int n = lane; n < ns; n += 32) bulk_g2s(tile + n * RS, p.A + (size_t)term_s[n] * K_ld, (unsigned)(K_ld * 4), mbar);
+            for (int n = lane; n < nr; n += 32) bulk_g2s(tile2 + n * RS, p.H + (size_t)term2_s[n] * K_ld, (unsigned)(K_ld * 4), mbar);
+        } else {
+            __syncwarp();
+            for (int c = lane; c < ns * CH; c += 32) {
+                const int n = c / CH, q = c - n * CH;
+                cp_async16(tile + n * RS + 4 * q, p.A + (size_t)term_s[n] * K_ld + 4 * q);
+            }
+            for (int c = lane; c < nr * CH; c += 32) {
+                const int n = c / CH, q = c - n * CH;
+                cp_async16(tile2 + n * RS + 4 * q, p.H + (size_t)term2_s[n] * K_ld + 4 * q);
+            }
+            cp_async_commit();
+        }
+        float gim_k[R], gimo_k[R], zay_k[R], zayo_k[R];
+#pragma unroll
+        for (int r = 0; r < R; r++) {
+            const int i = lane + 32 * r;
+            gim_k[r] = (i < K) ? p.gimel[(size_t)d * K_ld + i] : 1.0f;
+            zay_k[r] = (i < K) ? p.zayin[(size_t)d * K_ld + i] : 1.0f;
+            gimo_k[r] = gim_k[r];
+            zayo_k[r] = zay_k[r];
+        }
+        stage_wait(mbar, phase, p.stage_bulk);
+
+        TokArgs ta, tb;
+        ta.tile = tile;
+        ta.cnt_s = cnt_s;
+        ta.term_s = term_s;
+        ta.gtable = p.A;
+        ta.gterms = p.terms + o;
+        ta.gcounts = p.counts + o;
+        ta.stats = p.stats_a;
+        ta.Nd = Nd;
+        ta.cap = cap;
+        ta.rounds = (Nd + S - 1) / S;
+        ta.K = K;
+        ta.K_ld = K_ld;
+        ta.RS = RS;
+        ta.dbg = p.dbg;
+        tb = ta;
+        tb.tile = tile2;
+        tb.cnt_s = cnt2_s;
+        tb.term_s = term2_s;
+        tb.gtable = p.H;
+        tb.gterms = p.readers + ro;
+        tb.gcounts = p.ratings + ro;
+        tb.stats = p.stats_h;
+        tb.Nd = Rd;
+        tb.cap = cap2;
+        tb.rounds = (Rd + S - 1) / S;
+
+        float ephi_k[R], ea_k[R], eb_k[R];
+        int v = 0;
+        for (;;) {
+            // ---- the per-document halves of update_xi! / update_phi! (CTPF.jl:327-337)
+            float mphi = -INFINITY, mx = -INFINITY;
+            float aphi[R], aa[R], ab[R];
+#pragma unroll
+            for (int r = 0; r < R; r++) {
+                const float pg = psi_lgamma<false, true>(gim_k[r]).psi, pz = psi_lgamma<false, true>(zay_k[r]).psi;
+                aphi[r] = pg + lndb_k[r];
+                aa[r] = pg + lndv_k[r];
+                ab[r] = pz + lnhv_k[r];
+                if (lane + 32 * r < K) {
+                    mphi = fmaxf(mphi, aphi[r]);
+                    mx = fmaxf(mx, fmaxf(aa[r], ab[r]));
+                }
+            }
+            mphi = warp_max_f(mphi);
+            mx = warp_max_f(mx);
+#pragma unroll
+            for (int r = 0; r < R; r++) {
+                const int i = lane + 32 * r;
+                ephi_k[r] = (i < K) ? __expf(aphi[r] - mphi) : 0.0f;
+                ea_k[r] = (i < K) ? __expf(aa[r] - mx) : 0.0f;
+                eb_k[r] = (i < K) ? __expf(ab[r] - mx) : 0.0f;
+                if (i < K_ld) e_s[i] = ephi_k[r];
+            }
+            __syncwarp();
+            float4 e[CPL], g[CPL];
+            float tsum = 0.0f;
+            // ---- phi pass over the term tile
+#pragma unroll
+            for (int m = 0; m < CPL; m++) {
+                e[m] = (m < CPL - 1 || kl + LPT * m < CH) ? reinterpret_cast<const float4 *>(e_s)[kl + LPT * m] : zero4;
+                g[m] = zero4;
+            }
+            if (!ovf)
+                tok_sweep<LPT, CPL, false, false>(ta, ts, kl, e, g, tsum);
+            else
+                tok_sweep<LPT, CPL, true, false>(ta, ts, kl, e, g, tsum);
+#pragma unroll
+            for (int m = 0; m < CPL; m++)
+                if (m < CPL - 1 || kl + LPT * m < CH) reinterpret_cast<float4 *>(gs + ts * RS)[kl + LPT * m] = g[m];
+            __syncwarp();
+            float gphi[R];
+#pragma unroll
+            for (int r = 0; r < R; r++) {
+                const int i = lane + 32 * r;
+                gphi[r] = (i < K) ? owner_sum<S>(gs, RS, i) : 0.0f;
+                if (i < K_ld) e_s[i] = ea_k[r] + eb_k[r];
+            }
+            __syncwarp();
+            // ---- xi pass over the reader tile
+#pragma unroll
+            for (int m = 0; m < CPL; m++) {
+                e[m] = (m < CPL - 1 || kl + LPT * m < CH) ? reinterpret_cast<const float4 *>(e_s)[kl + LPT * m] : zero4;
+                g[m] = zero4;
+            }
+            if (!ovf2)
+                tok_sweep<LPT, CPL, false, false>(tb, ts, kl, e, g, tsum);
+            else
+                tok_sweep<LPT, CPL, true, false>(tb, ts, kl, e, g, tsum);
+#pragma unroll
+            for (int m = 0; m < CPL; m++)
+                if (m < CPL - 1 || kl + LPT * m < CH) reinterpret_cast<float4 *>(gs + ts * RS)[kl + LPT * m] = g[m];
+            __syncwarp();
+            // ---- update_zayin!, update_gimel! (CTPF.jl:309-323)
+            float dpart = 0.0f;
+#pragma unroll
+            for (int r = 0; r < R; r++) {
+                const int i = lane + 32 * r;
+                const float gx = (i < K) ? owner_sum<S>(gs, RS, i) : 0.0f;
+                zayo_k[r] = zay_k[r];
+                gimo_k[r] = gim_k[r];
+                if (i < K) {
+                    zay_k[r] = p.hg + eb_k[r] * gx;
+                    gim_k[r] = p.hc + fmaf(ephi_k[r], gphi[r], ea_k[r] * gx);
+                    const float df = gim_k[r] - gimo_k[r];
+                    dpart = fmaf(df, df, dpart);
+                }
+            }
+            __syncwarp();
+            v++;
+            if (v >= p.viter) break;  // CTPF.jl:359
+            if (dscale > 0.0f && __reduce_add_sync(0xffffffffu, (unsigned)fminf(dpart * dscale, 67108864.0f)) < 1048576u) break;
+        }
+
+        // ---- update_alef!(d) and update_he!(d) (CTPF.jl:259-262,274-277): scatter the last phi / xi
+        float ent = 0.0f;
+        {
+            float4 e[CPL], e2[CPL];
+#pragma unroll
+            for (int r = 0; r < R; r++)
+                if (lane + 32 * r < K_ld) e_s[lane + 32 * r] = ephi_k[r];
+            __syncwarp();
+#pragma unroll
+            for (int m = 0; m < CPL; m++)
+                e[m] = (m < CPL - 1 || kl + LPT * m < CH) ? reinterpret_cast<const float4 *>(e_s)[kl + LPT * m] : zero4;
+            if (!ovf)
+                tok_final<LPT, CPL, false, false, ELBO>(ta, ts, kl, e, ent);
+            else
+                tok_final<LPT, CPL, true, false, ELBO>(ta, ts, kl, e, ent);
+            if (Rd > 0) {
+                __syncwarp();
+#pragma unroll
+                for (int r = 0; r < R; r++)
+                    if (lane + 32 * r < K_ld) e_s[lane + 32 * r] = ea_k[r];
+                __syncwarp();
+#pragma unroll
+                for (int m = 0; m < CPL; m++)
+                    e[m] = (m < CPL - 1 || kl + LPT * m < CH) ? reinterpret_cast<const float4 *>(e_s)[kl + LPT * m] : zero4;
+                __syncwarp();
+#pragma unroll
+                for (int r = 0; r < R; r++)
+                    if (lane + 32 * r < K_ld) e_s[lane + 32 * r] = eb_k[r];
+                __syncwarp();
+#pragma unroll
+                for (int m = 0; m < CPL; m++)
+                    e2[m] = (m < CPL - 1 || kl + LPT * m < CH) ? reinterpret_cast<const float4 *>(e_s)[kl + LPT * m] : zero4;
+                if (!ovf2)
+                    tok_final2<LPT, CPL, false, ELBO>(tb, ts, kl, e, e2, ent);
+                else
+                    tok_final2<LPT, CPL, true, ELBO>(tb, ts, kl, e, e2, ent);
+            }
+        }
+
+        float a = 0.0f;
+#pragma unroll
+        for (int r = 0; r < R; r++) {
+            const int i = lane + 32 * r;
+            if (i < K_ld) {
+                const bool ok = i < K;
+                p.gimel[(size_t)d * K_ld + i] = ok ? gim_k[r] : 0.0f;
+                p.gimel_old[(size_t)d * K_ld + i] = ok ? gimo_k[r] : 0.0f;
+                p.zayin[(size_t)d * K_ld + i] = ok ? zay_k[r] : 0.0f;
+                p.zayin_old[(size_t)d * K_ld + i] = ok ? zayo_k[r] : 0.0f;
+                if (ok) {
+                    gs_k[r] += (double)gim_k[r];
+                    zs_k[r] += (double)zay_k[r];
+                    // every psi(gimel), psi(zayin) term of the ELBO cancels (see tmvb_ctpf_elbo); what is left per
+                    // document is sum_i lnG(gimel_i) + lnG(zayin_i) and the z / y entropies
+                    if (ELBO) a += psi_lgamma<true>(gim_k[r]).lg + psi_lgamma<true>(zay_k[r]).lg;
+                }
+            }
+        }
+        if (ELBO) elbo_thr += (double)a + (double)ent - (double)lg_c;
+        if (lane == 0) sweeps_thr += (unsigned long long)v;
+    }
+
+    if (ELBO) {
+        const double tot = warp_sum_d(elbo_thr);
+        if (lane == 0 && tot != 0.0) atomicAdd(p.small + 2 * K_ld, tot);
+    }
+#pragma unroll
+    for (int r = 0; r < R; r++) {
+        const int i = lane + 32 * r;
+        if (i < K) {
+            if (gs_k[r] != 0.0) atomicAdd(p.small + i, gs_k[r]);
+            if (zs_k[r] != 0.0) atomicAdd(p.small + K_ld + i, zs_k[r]);
+        }
+    }
+    if (lane == 0 && sweeps_thr) atomicAdd(p.small + 2 * K_ld + 1, (double)sweeps_thr);
+}
+
+// x = prior + stats (one warp per table row): raw <- x, table <- exp(psi(x) - rowmax), stats <- 0, and per-topic sums
+// acc = [sum psi(x) (K_ld) | sum x (K_ld) | sum lnG(x) + (1-x) psi(x) (K_ld) | sum stats psi(x) (1)]
+// (update_alef!/update_he! CTPF.jl:251-270 + the table of exp(psi) the sweeps read + the global ELBO sums CTPF.jl:143-168,197-221)
+__global__ void ctpf_table_kernel(float *__restrict__ stats, float prior, float *__restrict__ raw, float *__restrict__ table, int rows,
+                                  int K, int K_ld, double *__restrict__ acc, int zero_stats)
+{
+    const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+    constexpr int RMAX = 8;
+    double t1[RMAX], t2[RMAX], t3[RMAX], t4 = 0.0;
+#pragma unroll
+    for (int r = 0; r < RMAX; r++) t1[r] = t2[r] = t3[r] = 0.0;
+    for (int j = blockIdx.x * wpb + (threadIdx.x >> 5); j < rows; j += gridDim.x * wpb) {
+        float ps[RMAX], x[RMAX];
+        float mx = -INFINITY;
+#pragma unroll
+        for (int r = 0; r < RMAX; r++) {
+            const int i = lane + 32 * r;
+            ps[r] = 0.0f;
+            x[r] = 0.0f;
+            if (i < K) {
+                const float sv = stats[(size_t)j * K_ld + i];
+                x[r] = prior + sv;
+                const PsiLg pl = psi_lgamma<true>(x[r]);
+                ps[r] = pl.psi;
+                mx = fmaxf(mx, ps[r]);
+                t1[r] += (double)ps[r];
+                t2[r] += (double)x[r];
+                t3[r] += (double)(pl.lg + (1.0f - x[r]) * ps[r]);
+                t4 += (double)(sv * ps[r]);
+            }
+        }
+        mx = warp_max_f(mx);
+#pragma unroll
+        for (int r = 0; r < RMAX; r++) {
+            const int i = lane + 32 * r;
+            if (i < K_ld) {
+                raw[(size_t)j * K_ld + i] = (i < K) ? x[r] : 0.0f;
+                table[(size_t)j * K_ld + i] = (i < K) ? expf(ps[r] - mx) : 0.0f;
+                if (zero_stats) stats[(size_t)j * K_ld + i] = 0.0f;
+            }
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < RMAX; r++) {
+        const int i = lane + 32 * r;
+        if (i < K) {
+            atomicAdd(acc + i, t1[r]);
+            atomicAdd(acc + K_ld + i, t2[r]);
+            atomicAdd(acc + 2 * K_ld + i, t3[r]);
+        }
+    }
+    t4 = warp_sum_d(t4);
+    if (lane == 0 && t4 != 0.0) atomicAdd(acc + 3 * K_ld, t4);
+}
+
+// update_elbo! restated (CTPF.jl:232-247) per document: phi / xi from the *_old state (A_old, H_old, gimel_old, zayin_old,
+// old rates), every expectation with the current alef / he / rates / gimel / zayin.  One warp per document, lanes over
+// topics; fp32 per element, fp64 accumulation.  The corpus-level Gamma terms of alef / he are added on the host.
+__global__ void ctpf_elbo_kernel(const CtpfDev p, const float *__restrict__ A_old, const float *__restrict__ H_old,
+                                 const float *__restrict__ alef, const float *__restrict__ he, float hd, float hh, double *out)
+{
+    const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+    const int K = p.K, K_ld = p.K_ld;
+    const float *kv = p.kv;
+    double acc = 0.0;
+    for (long long d = (long long)blockIdx.x * wpb + (threadIdx.x >> 5); d < p.M; d += (long long)gridDim.x * wpb) {
+        const long long o = p.doc_off[d], ro = p.r_off[d];
+        const int Nd = (int)(p.doc_off[d + 1] - o), Rd = (int)(p.r_off[d + 1] - ro);
+        const float *gm = p.gimel + d * K_ld, *zy = p.zayin + d * K_ld, *go = p.gimel_old + d * K_ld, *zo = p.zayin_old + d * K_ld;
+        float mphi = -INFINITY, mx = -INFINITY;
+        for (int i = lane; i < K; i += 32) {
+            const float pg = psi_lgamma<false>(go[i]).psi, pz = psi_lgamma<false>(zo[i]).psi;
+            mphi = fmaxf(mphi, pg + kv[KV_LNDB_OLD * K_ld + i]);
+            mx = fmaxf(mx, fmaxf(pg + kv[KV_LNDV_OLD * K_ld + i], pz + kv[KV_LNHV_OLD * K_ld + i]));
+        }
+        mphi = warp_max_f(mphi);
+        mx = warp_max_f(mx);
+        double dacc = 0.0;
+        for (int n = 0; n < Nd; n++) {
+            const int term = p.terms[o + n];
+            const float c = p.counts[o + n];
+            float s = 0.0f;
+            for (int i = lane; i < K; i += 32) s += A_old[(size_t)term * K_ld + i] * expf(psi_lgamma<false>(go[i]).psi + kv[KV_LNDB_OLD * K_ld + i] - mphi);
+            s = warp_sum(s);
+            float a = 0.0f;
+            for (int i = lane; i < K; i += 32) {
+                const float ph = A_old[(size_t)term * K_ld + i] * expf(psi_lgamma<false>(go[i]).psi + kv[KV_LNDB_OLD * K_ld + i] - mphi) / s;
+                if (ph > 0.0f)
+                    a += ph * (psi_lgamma<false>(gm[i]).psi - kv[KV_LN_DALET * K_ld + i] - kv[KV_LN_BET * K_ld + i] +
+                               psi_lgamma<false>(alef[(size_t)term * K_ld + i]).psi - logf(ph));
+            }
+            dacc += (double)(c * a);
+            if (lane == 0) dacc -= (double)lgammaf(c + 1.0f);
+        }
+        for (int n = 0; n < Rd; n++) {
+            const int u = p.readers[ro + n];
+            const float c = p.ratings[ro + n];
+            float s = 0.0f;
+            for (int i = lane; i < K; i += 32) {
+                const float hv = H_old[(size_t)u * K_ld + i];
+                s += hv * (expf(psi_lgamma<false>(go[i]).psi + kv[KV_LNDV_OLD * K_ld + i] - mx) + expf(psi_lgamma<false>(zo[i]).psi + kv[KV_LNHV_OLD * K_ld + i] - mx));
+            }
+            s = warp_sum(s);
+            float a = 0.0f;
+            for (int i = lane; i < K; i += 32) {
+                const float hv = H_old[(size_t)u * K_ld + i], phe = psi_lgamma<false>(he[(size_t)u * K_ld + i]).psi;
+                const float xa = hv * expf(psi_lgamma<false>(go[i]).psi + kv[KV_LNDV_OLD * K_ld + i] - mx) / s;
+                const float xb = hv * expf(psi_lgamma<false>(zo[i]).psi + kv[KV_LNHV_OLD * K_ld + i] - mx) / s;
+                if (xa > 0.0f) a += xa * (psi_lgamma<false>(gm[i]).psi - kv[KV_LN_DALET * K_ld + i] - kv[KV_LN_VAV * K_ld + i] + phe - logf(xa));
+                if (xb > 0.0f) a += xb * (psi_lgamma<false>(zy[i]).psi - kv[KV_LN_HET * K_ld + i] - kv[KV_LN_VAV * K_ld + i] + phe - logf(xb));
+            }
+            dacc += (double)(c * a);
+            if (lane == 0) dacc -= (double)lgammaf(c + 1.0f);
+        }
+        float b = 0.0f;
+        for (int i = lane; i < K; i += 32) {
+            const PsiLg pg = psi_lgamma<true>(gm[i]), pz = psi_lgamma<true>(zy[i]);
+            b -= gm[i] * (kv[KV_HE_DV * K_ld + i] + kv[KV_AL_DB * K_ld + i]) + zy[i] * kv[KV_HE_HV * K_ld + i];   // CTPF.jl:112,123,134
+            b += (p.hc - 1.0f) * (pg.psi - kv[KV_LN_DALET * K_ld + i]) - hd * gm[i] * kv[KV_INV_DALET * K_ld + i];  // Elogptheta
+            b += (p.hg - 1.0f) * (pz.psi - kv[KV_LN_HET * K_ld + i]) - hh * zy[i] * kv[KV_INV_HET * K_ld + i];      // Elogpepsilon
+            b += gm[i] - kv[KV_LN_DALET * K_ld + i] + pg.lg + (1.0f - gm[i]) * pg.psi;                              // entropy(Gamma)
+            b += zy[i] - kv[KV_LN_HET * K_ld + i] + pz.lg + (1.0f - zy[i]) * pz.psi;
+        }
+        dacc += (double)b;
+        dacc = warp_sum_d(dacc);
+        if (lane == 0) acc += dacc;
+    }
+    if (lane == 0 && acc != 0.0) atomicAdd(out, acc);
+}
+
+typedef void (*CtpfEstepFn)(const CtpfDev, int, int, int, int, int *);
+#define TMVB_CTPF_FN(L, C) {(CtpfEstepFn)ctpf_estep_kernel<L, C, false>, (CtpfEstepFn)ctpf_estep_kernel<L, C, true>},
+static const CtpfEstepFn kCtpfEstep[kNumLaneLayouts][2] = {TMVB_FOR_EACH_LAYOUT(TMVB_CTPF_FN)};
+
+}  // namespace tmvb
+
+using namespace tmvb;
+
+struct tmvb_ctpf_s {
+    Shard s;  // d_beta[2] = A tables (current / previous), d_stats = alef statistics
+    int64_t U = 0, nnz_r = 0;
+    bool elbo_valid = false, readers_set = false;
+    double hyp[8] = {0.1, 0.1, 0.1, 0.1, 0.1, 0.1, 0.1, 0.1};  // a b c d e f g h (gpuCTPF.jl:107)
+    float *d_alef = nullptr, *d_alef_old = nullptr;            // raw [V][K_ld]
+    float *d_he = nullptr, *d_he_old = nullptr;                // raw [U][K_ld]
+    float *d_H[2] = {nullptr, nullptr}, *d_hstats = nullptr;   // [U][K_ld]
+    int hcur = 0;
+    long long *d_r_off = nullptr;
+    int *d_readers = nullptr;
+    float *d_ratings = nullptr;
+    float *d_gimel = nullptr, *d_gimel_old = nullptr, *d_zayin = nullptr, *d_zayin_old = nullptr;
+    float *d_kv = nullptr;
+    std::vector<double> bet, vav, dalet, het, bet_old, vav_old, dalet_old, het_old;  // fp64 masters
+    double *d_small = nullptr;  // [2 K_ld + 2]
+    double *d_tsum = nullptr;   // [2][3 K_ld + 1] table sums (alef | he) + [1] standalone ELBO
+    std::vector<double> h_small, h_tsum;
+    std::vector<int> r_len;
+};
+
+namespace {
+
+CtpfDev ctpf_view(tmvb_ctpf_t h)
+{
+    Shard &s = h->s;
+    CtpfDev p;
+    p.K = (int)s.K;
+    p.K_ld = s.K_ld;
+    p.V = (int)s.V;
+    p.U = (int)h->U;
+    p.RS = s.RS;
+    p.M = s.M;
+    p.A = s.d_beta[s.cur];
+    p.H = h->d_H[h->hcur];
+    p.stats_a = s.d_stats;
+    p.stats_h = h->d_hstats;
+    p.doc_off = s.d_doc_off;
+    p.r_off = h->d_r_off;
+    p.terms = s.d_terms;
+    p.readers = h->d_readers;
+    p.counts = s.d_counts;
+    p.ratings = h->d_ratings;
+    p.gimel = h->d_gimel;
+    p.gimel_old = h->d_gimel_old;
+    p.zayin = h->d_zayin;
+    p.zayin_old = h->d_zayin_old;
+    p.kv = h->d_kv;
+    p.small = h->d_small;
+    p.hc = (float)h->hyp[2];
+    p.hg = (float)h->hyp[6];
+    p.viter = 0;
+    p.vtol = 0.f;
+    p.stage_bulk = env_int("TMVB_STAGE_BULK", 1);
+    p.dbg = env_int("TMVB_DBG", 0);
+    return p;
+}
+
+void ctpf_free(tmvb_ctpf_t h)
+{
+    cudaSetDevice(h->s.device);
+    if (h->s.stream) cudaStreamSynchronize(h->s.stream);
+    cudaFree(h->d_alef);
+    cudaFree(h->d_alef_old);
+    cudaFree(h->d_he);
+    cudaFree(h->d_he_old);
+    cudaFree(h->d_H[0]);
+    cudaFree(h->d_H[1]);
+    cudaFree(h->d_hstats);
+    cudaFree(h->d_r_off);
+    cudaFree(h->d_readers);
+    cudaFree(h->d_ratings);
+    cudaFree(h->d_gimel);
+    cudaFree(h->d_gimel_old);
+    cudaFree(h->d_zayin);
+    cudaFree(h->d_zayin_old);
+    cudaFree(h->d_kv);
+    cudaFree(h->d_small);
+    cudaFree(h->d_tsum);
+    shard_free(&h->s);
+}
+
+// K-vectors the kernels read, from the fp64 masters; AL / HE are the row sums of the current alef / he
+int ctpf_push_kv(tmvb_ctpf_t h)
+{
+    Shard &s = h->s;
+    const int K = (int)s.K, K_ld = s.K_ld;
+    std::vector<float> kv((size_t)KV_COUNT * K_ld, 0.f);
+    const double *AL = h->h_tsum.data() + K_ld, *HE = h->h_tsum.data() + (3 * K_ld + 1) + K_ld;
+    for (int i = 0; i < K; i++) {
+        kv[KV_LNDB * K_ld + i] = (float)(-log(h->dalet[i]) - log(h->bet[i]));
+        kv[KV_LNDV * K_ld + i] = (float)(-log(h->dalet[i]) - log(h->vav[i]));
+        kv[KV_LNHV * K_ld + i] = (float)(-log(h->het[i]) - log(h->vav[i]));
+        kv[KV_LN_DALET * K_ld + i] = (float)log(h->dalet[i]);
+        kv[KV_LN_BET * K_ld + i] = (float)log(h->bet[i]);
+        kv[KV_LN_VAV * K_ld + i] = (float)log(h->vav[i]);
+        kv[KV_LN_HET * K_ld + i] = (float)log(h->het[i]);
+        kv[KV_AL_DB * K_ld + i] = (float)(AL[i] / (h->dalet[i] * h->bet[i]));
+        kv[KV_HE_DV * K_ld + i] = (float)(HE[i] / (h->dalet[i] * h->vav[i]));
+        kv[KV_HE_HV * K_ld + i] = (float)(HE[i] / (h->het[i] * h->vav[i]));
+        kv[KV_INV_DALET * K_ld + i] = (float)(1.0 / h->dalet[i]);
+        kv[KV_INV_HET * K_ld + i] = (float)(1.0 / h->het[i]);
+        kv[KV_LNDB_OLD * K_ld + i] = (float)(-log(h->dalet_old[i]) - log(h->bet_old[i]));
+        kv[KV_LNDV_OLD * K_ld + i] = (float)(-log(h->dalet_old[i]) - log(h->vav_old[i]));
+        kv[KV_LNHV_OLD * K_ld + i] = (float)(-log(h->het_old[i]) - log(h->vav_old[i]));
+    }
+    TMVB_CUDA(cudaMemcpyAsync(h->d_kv, kv.data(), kv.size() * 4, cudaMemcpyHostToDevice, s.stream));
+    TMVB_CUDA(cudaStreamSynchronize(s.stream));
+    s.st.h2d_bytes += (int64_t)kv.size() * 4;
+    return 0;
+}
+
+// run the table kernel for alef (which = 0) or he (which = 1); results land in h_tsum after the caller's D2H
+int ctpf_build_table(tmvb_ctpf_t h, int which, float prior, int zero_stats)
+{
+    Shard &s = h->s;
+    const int rows = which == 0 ? (int)s.V : (int)h->U;
+    double *acc = h->d_tsum + (size_t)which * (3 * s.K_ld + 1);
+    TMVB_CUDA(cudaMemsetAsync(acc, 0, (3 * s.K_ld + 1) * 8, s.stream));
+    if (rows == 0) return 0;
+    float *stats = which == 0 ? s.d_stats : h->d_hstats;
+    float *raw = which == 0 ? h->d_alef : h->d_he;
+    float *table = which == 0 ? s.d_beta[s.cur] : h->d_H[h->hcur];
+    ctpf_table_kernel<<<std::min((rows + 7) / 8, s.n_sm * 8), 256, 0, s.stream>>>(stats, prior, raw, table, rows, (int)s.K, s.K_ld, acc, zero_stats);
+    TMVB_CUDA(cudaGetLastError());
+    s.st.kernel_launches++;
+    return 0;
+}
+
+int ctpf_fetch_tsum(tmvb_ctpf_t h)
+{
+    Shard &s = h->s;
+    const size_t n = 2 * (3 * s.K_ld + 1);
+    TMVB_CUDA(cudaMemcpyAsync(s.h_pinned, h->d_tsum, n * 8, cudaMemcpyDeviceToHost, s.stream));
+    TMVB_CUDA(cudaStreamSynchronize(s.stream));
+    memcpy(h->h_tsum.data(), s.h_pinned, n * 8);
+    s.st.d2h_bytes += n * 8;
+    return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int tmvb_ctpf_create(tmvb_ctpf_t *out, int64_t K, int64_t M, int64_t V, int64_t U, int device, void *stream)
+{
+    TMVB_CHECK_ARG(out != nullptr, "handle pointer is NULL");
+    *out = nullptr;
+    TMVB_CHECK_ARG(U >= 0 && U < (1ll << 31), "U must be nonnegative and fit in int32");
+    tmvb_ctpf_t h = new tmvb_ctpf_s();
+    const int64_t K_ld = (K + 7) / 8 * 8;
+    int rc = shard_create(&h->s, K, M, V, device, stream, (size_t)(8 * K_ld + 16));
+    if (rc == 0) {
+        Shard &s = h->s;
+        h->U = U;
+        const size_t kv = (size_t)std::max<int64_t>(V, 1) * s.K_ld, ku = (size_t)std::max<int64_t>(U, 1) * s.K_ld,
+                     km = (size_t)std::max<int64_t>(M, 1) * s.K_ld;
+        cudaError_t e = cudaSuccess;
+        auto A = [&](void **p, size_t bytes) {
+            if (e == cudaSuccess) e = cudaMalloc(p, bytes);
+            if (e == cudaSuccess) e = cudaMemsetAsync(*p, 0, bytes, s.stream);
+        };
+        A((void **)&h->d_alef, kv * 4);
+        A((void **)&h->d_alef_old, kv * 4);
+        A((void **)&h->d_he, ku * 4);
+        A((void **)&h->d_he_old, ku * 4);
+        A((void **)&h->d_H[0], ku * 4);
+        A((void **)&h->d_H[1], ku * 4);
+        A((void **)&h->d_hstats, ku * 4);
+        A((void **)&h->d_gimel, km * 4);
+        A((void **)&h->d_gimel_old, km * 4);
+        A((void **)&h->d_zayin, km * 4);
+        A((void **)&h->d_zayin_old, km * 4);
+        A((void **)&h->d_kv, (size_t)KV_COUNT * s.K_ld * 4);
+        A((void **)&h->d_small, (2 * s.K_ld + 2) * 8);
+        A((void **)&h->d_tsum, (2 * (3 * s.K_ld + 1) + 1) * 8);
+        for (int eb = 0; eb < 2 && e == cudaSuccess; eb++)
+            e = cudaFuncSetAttribute((const void *)kCtpfEstep[s.layout][eb], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s.smem_optin);
+        if (e != cudaSuccess) rc = fail((int)e, "device allocation failed: %s", cudaGetErrorString(e));
+    }
+    if (rc != 0) {
+        ctpf_free(h);
+        delete h;
+        return rc;
+    }
+    for (auto *v : {&h->bet, &h->vav, &h->dalet, &h->het, &h->bet_old, &h->vav_old, &h->dalet_old, &h->het_old}) v->assign(K, 1.0);  // gpuCTPF.jl:110-119
+    h->h_small.assign(2 * K_ld + 2, 0.0);
+    h->h_tsum.assign(2 * (3 * K_ld + 1), 0.0);
+    *out = h;
+    return 0;
+}
+
+int tmvb_ctpf_destroy(tmvb_ctpf_t h)
+{
+    if (!h) return 0;
+    ctpf_free(h);
+    delete h;
+    return 0;
+}
+
+int tmvb_ctpf_set_corpus(tmvb_ctpf_t h, const int64_t *N_cumsum, const int64_t *terms, const int64_t *counts, const int64_t *R_cumsum,
+                         const int64_t *readers, const int64_t *ratings)
+{
+    TMVB_CHECK_ARG(h != nullptr, "handle is NULL");
+    Shard &s = h->s;
+    const size_t per_tok = (size_t)s.RS * 4 + 8;
+    const int cap2_max = 64;
+    TMVB_TRY(shard_set_corpus(&s, N_cumsum, terms, counts, ctpf_fixed_smem(s.RS, s.lpt) + cap2_max * per_tok));
+    TMVB_TRY(shard_pack_aux(&s, R_cumsum, readers, ratings, h->U, &h->d_r_off, &h->d_readers, &h->d_ratings, &h->nnz_r, &h->r_len));
+    // size the reader tile of each launch for (about) the 90th percentile of its documents' reader counts;
+    // longer reader lists read their overflow rows from L2
+    for (Bucket &b : s.buckets) {
+        std::vector<int> rl(h->r_len.begin() + b.doc_begin, h->r_len.begin() + b.doc_end);
+        std::sort(rl.begin(), rl.end());
+        const int p90 = rl.empty() ? 0 : rl[(rl.size() - 1) * 9 / 10];
+        b.cap2 = std::min(cap2_max, std::max(16, (p90 + 15) / 16 * 16));
+        b.smem = ctpf_fixed_smem(s.RS, s.lpt) + (size_t)(b.cap + b.cap2) * per_tok;
+        b.grid = 0;
+    }
+    h->readers_set = true;
+    return 0;
+}
+
+int tmvb_ctpf_upload(tmvb_ctpf_t h, const double *hyp, const float *alef, const float *he, const float *bet, const float *vav,
+                     const float *gimel, const float *zayin, const float *dalet, const float *het)
+{
+    TMVB_CHECK_ARG(h != nullptr, "handle is NULL");
+    Shard &s = h->s;
+    TMVB_CUDA(cudaSetDevice(s.device));
+    const int K = (int)s.K;
+    static const char *hn = "abcdefgh";
+    if (hyp)
+        for (int q = 0; q < 8; q++) {
+            if (!(hyp[q] > 0.0)) return fail(-5, "%c must be positive.", hn[q]);  // modelutils.jl:319-326
+            h->hyp[q] = hyp[q];
+        }
+    auto setk = [&](const float *src, std::vector<double> &dst, std::vector<double> &old, const char *name) -> int {
+        if (!src) return 0;
+        for (int i = 0; i < K; i++) {
+            if (!isfinite(src[i])) return fail(-5, "%s must be finite.", name);
+            if (!(src[i] > 0.f)) return fail(-5, "%s must be positive.", name);
+            dst[i] = old[i] = (double)src[i];  // the *_old copies start equal (CTPF.jl:89-99)
+        }
+        return 0;
+    };
+    TMVB_TRY(setk(bet, h->bet, h->bet_old, "bet"));
+    TMVB_TRY(setk(vav, h->vav, h->vav_old, "vav"));
+    TMVB_TRY(setk(dalet, h->dalet, h->dalet_old, "dalet"));
+    TMVB_TRY(setk(het, h->het, h->het_old, "het"));
+    if (alef && s.V > 0) {
+        TMVB_TRY(shard_upload_rows(&s, alef, s.d_stats, s.V, nullptr, 2));
+        TMVB_TRY(ctpf_build_table(h, 0, 0.0f, 1));
+        TMVB_CUDA(cudaMemcpyAsync(s.d_beta[s.cur ^ 1], s.d_beta[s.cur], (size_t)s.V * s.K_ld * 4, cudaMemcpyDeviceToDevice, s.stream));
+        TMVB_CUDA(cudaMemcpyAsync(h->d_alef_old, h->d_alef, (size_t)s.V * s.K_ld * 4, cudaMemcpyDeviceToDevice, s.stream));
+    }
+    if (he && h->U > 0) {
+        const int64_t Ksave = s.K;
+        (void)Ksave;
+        // shard_upload_rows is row-count agnostic: U rows of K floats
+        TMVB_TRY(shard_upload_rows(&s, he, h->d_hstats, h->U, nullptr, 2));
+        TMVB_TRY(ctpf_build_table(h, 1, 0.0f, 1));
+        TMVB_CUDA(cudaMemcpyAsync(h->d_H[h->hcur ^ 1], h->d_H[h->hcur], (size_t)h->U * s.K_ld * 4, cudaMemcpyDeviceToDevice, s.stream));
+        TMVB_CUDA(cudaMemcpyAsync(h->d_he_old, h->d_he, (size_t)h->U * s.K_ld * 4, cudaMemcpyDeviceToDevice, s.stream));
+    }
+    if ((gimel || zayin) && s.M > 0) {
+        TMVB_CHECK_ARG(s.corpus_set, "set_corpus must precede the upload of per-document parameters");
+        TMVB_TRY(shard_upload_rows(&s, gimel, h->d_gimel, s.M, s.d_perm, 2));
+        if (gimel) TMVB_CUDA(cudaMemcpyAsync(h->d_gimel_old, h->d_gimel, (size_t)s.M * s.K_ld * 4, cudaMemcpyDeviceToDevice, s.stream));
+        TMVB_TRY(shard_upload_rows(&s, zayin, h->d_zayin, s.M, s.d_perm, 2));
+        if (zayin) TMVB_CUDA(cudaMemcpyAsync(h->d_zayin_old, h->d_zayin, (size_t)s.M * s.K_ld * 4, cudaMemcpyDeviceToDevice, s.stream));
+    }
+    int verr = 0;
+    TMVB_TRY(shard_validation(&s, &verr));
+    if (verr & 0x10) return fail(-5, "alef, he, gimel and zayin must be finite.");   // modelutils.jl:328-349
+    if (verr & 0x20) return fail(-5, "alef, he, gimel and zayin must be positive.");
+    TMVB_TRY(ctpf_fetch_tsum(h));
+    TMVB_TRY(ctpf_push_kv(h));
+    h->elbo_valid = false;
+    return 0;
+}
+
+int tmvb_ctpf_estep(tmvb_ctpf_t h, int viter, float vtol, int want_elbo)
+{
+    TMVB_CHECK_ARG(h != nullptr, "handle is NULL");
+    TMVB_CHECK_ARG(viter >= 1, "viter must be at least 1");
+    TMVB_CHECK_ARG(vtol >= 0.f, "tolerance parameters must be nonnegative");  // gpuCTPF.jl:679
+    Shard &s = h->s;
+    TMVB_CHECK_ARG(s.corpus_set && h->readers_set, "set_corpus has not been called");
+    TMVB_CUDA(cudaSetDevice(s.device));
+    CtpfDev p = ctpf_view(h);
+    p.viter = viter;
+    p.vtol = vtol;
+    TMVB_CUDA(cudaEventRecord(s.ev[0], s.stream));
+    TMVB_CUDA(cudaMemsetAsync(h->d_small, 0, (2 * s.K_ld + 2) * 8, s.stream));
+    TMVB_TRY(shard_launch(&s, (const void *)kCtpfEstep[s.layout][want_elbo != 0], &p));
+    TMVB_CUDA(cudaEventRecord(s.ev[1], s.stream));
+    s.estep_timed = true;
+    h->elbo_valid = (want_elbo != 0);
+    return 0;
+}
+
+int tmvb_ctpf_reduce_buffers(tmvb_ctpf_t h, void **stats_alef, int64_t *n_alef, void **stats_he, int64_t *n_he, void **small, int64_t *n_small)
+{
+    TMVB_CHECK_ARG(h != nullptr, "handle is NULL");
+    if (stats_alef) *stats_alef = h->s.d_stats;
+    if (n_alef) *n_alef = (int64_t)h->s.V * h->s.K_ld;
+    if (stats_he) *stats_he = h->d_hstats;
+    if (n_he) *n_he = h->U * h->s.K_ld;
+    if (small) *small = h->d_small;
+    if (n_small) *n_small = 2 * h->s.K_ld + 2;
+    return 0;
+}
+
+int tmvb_ctpf_mstep(tmvb_ctpf_t h, int64_t M_total)
+{
+    TMVB_CHECK_ARG(h != nullptr && M_total > 0, "bad arguments");
+    Shard &s = h->s;
+    TMVB_CUDA(cudaSetDevice(s.device));
+    TMVB_CUDA(cudaEventRecord(s.ev[2], s.stream));
+    const int K = (int)s.K, K_ld = s.K_ld;
+    const double b = h->hyp[1], dd = h->hyp[3], f = h->hyp[5], hh = h->hyp[7];
+    // update_he!() / update_alef!() (CTPF.jl:251-270): he_old <- he ; he <- e + statistics  (likewise alef)
+    std::swap(h->d_alef, h->d_alef_old);
+    std::swap(h->d_he, h->d_he_old);
+    s.cur ^= 1;
+    h->hcur ^= 1;
+    TMVB_TRY(ctpf_build_table(h, 0, (float)h->hyp[0], 1));
+    TMVB_TRY(ctpf_build_table(h, 1, (float)h->hyp[4], 1));
+    TMVB_CUDA(cudaMemcpyAsync(s.h_pinned + 2 * (3 * K_ld + 1), h->d_small, (2 * K_ld + 2) * 8, cudaMemcpyDeviceToHost, s.stream));
+    TMVB_TRY(ctpf_fetch_tsum(h));
+    memcpy(h->h_small.data(), s.h_pinned + 2 * (3 * K_ld + 1), (2 * K_ld + 2) * 8);
+    s.st.d2h_bytes += (2 * K_ld + 2) * 8;
+    const double *AL = h->h_tsum.data() + K_ld, *HE = h->h_tsum.data() + (3 * K_ld + 1) + K_ld;
+    const double *Gs = h->h_small.data(), *Zs = Gs + K_ld;
+    h->dalet_old = h->dalet;
+    h->het_old = h->het;
+    h->bet_old = h->bet;
+    h->vav_old = h->vav;
+    for (int i = 0; i < K; i++) {
+        h->dalet[i] = dd + AL[i] / h->bet_old[i] + HE[i] / h->vav_old[i];  // update_dalet! CTPF.jl:295-298
+        h->het[i] = hh + HE[i] / h->vav_old[i];                            // update_het!   CTPF.jl:302-305
+        h->bet[i] = b + Gs[i] / h->dalet[i];                               // update_bet!   CTPF.jl:281-284
+        h->vav[i] = f + Gs[i] / h->dalet[i] + Zs[i] / h->het[i];           // update_vav!   CTPF.jl:288-291
+    }
+    TMVB_TRY(ctpf_push_kv(h));
+    TMVB_CUDA(cudaEventRecord(s.ev[3], s.stream));
+    s.mstep_timed = true;
+    return 0;
+}
+
+int tmvb_ctpf_elbo(tmvb_ctpf_t h, int mode, int64_t M_total, double *elbo_docs, double *elbo_global)
+{
+    TMVB_CHECK_ARG(h && elbo_docs && elbo_global, "NULL argument");
+    TMVB_CHECK_ARG(mode == 0 || mode == 1, "mode must be 0 or 1");
+    Shard &s = h->s;
+    TMVB_CUDA(cudaSetDevice(s.device));
+    const int K = (int)s.K, K_ld = s.K_ld;
+    const double a = h->hyp[0], b = h->hyp[1], c = h->hyp[2], dd = h->hyp[3], e = h->hyp[4], f = h->hyp[5], g = h->hyp[6], hh = h->hyp[7];
+    const double Md = (double)M_total, Vd = (double)s.V, Ud = (double)h->U;
+    const double *T1a = h->h_tsum.data(), *AL = T1a + K_ld, *T3a = AL + K_ld, T4a = h->h_tsum[3 * K_ld];
+    const double *T1h = h->h_tsum.data() + (3 * K_ld + 1), *HE = T1h + K_ld, *T3h = HE + K_ld, T4h = h->h_tsum[(3 * K_ld + 1) + 3 * K_ld];
+    // Elogpbeta - Elogqbeta + Elogpeta - Elogqeta (CTPF.jl:143-168,197-221) from the table sums
+    double glob = Vd * K * (a * log(b) - lgamma(a)) + Ud * K * (e * log(f) - lgamma(e));
+    for (int i = 0; i < K; i++) {
+        glob += (a - 1.0) * (T1a[i] - Vd * log(h->bet[i])) - b * AL[i] / h->bet[i] + AL[i] - Vd * log(h->bet[i]) + T3a[i];
+        glob += (e - 1.0) * (T1h[i] - Ud * log(h->vav[i])) - f * HE[i] / h->vav[i] + HE[i] - Ud * log(h->vav[i]) + T3h[i];
+    }
+    if (mode == 0) {
+        TMVB_CHECK_ARG(h->elbo_valid, "mode 0 needs estep(want_elbo=1) followed by mstep");
+        const double *Gs = h->h_small.data(), *Zs = Gs + K_ld;
+        double x = T4a + T4h;  // sum S psi(alef), sum S psi(he): the table halves of Elogpz / Elogpya / Elogpyb
+        for (int i = 0; i < K; i++) {
+            const double lnd = log(h->dalet[i]), lnb = log(h->bet[i]), lnv = log(h->vav[i]), lnh = log(h->het[i]);
+            const double Sphi = AL[i] - Vd * a, Sxa = Gs[i] - Md * c - Sphi, Sxb = Zs[i] - Md * g;
+            x -= Gs[i] * HE[i] / (h->dalet[i] * h->vav[i]) + Zs[i] * HE[i] / (h->het[i] * h->vav[i]) + Gs[i] * AL[i] / (h->dalet[i] * h->bet[i]);
+            x += Sxa * (-lnd - lnv) + Sxb * (-lnh - lnv) + Sphi * (-lnd - lnb);
+            x += -(c - 1.0) * Md * lnd - dd * Gs[i] / h->dalet[i] - (g - 1.0) * Md * lnh - hh * Zs[i] / h->het[i];
+            x += Gs[i] - Md * lnd + Zs[i] - Md * lnh;
+        }
+        x += Md * K * (c * log(dd) - lgamma(c)) + Md * K * (g * log(hh) - lgamma(g));
+        *elbo_docs = h->h_small[2 * K_ld];
+        *elbo_global = glob + x;
+        return 0;
+    }
+    TMVB_CHECK_ARG(s.corpus_set && h->readers_set, "set_corpus has not been called");
+    CtpfDev p = ctpf_view(h);
+    double *out = h->d_tsum + 2 * (3 * K_ld + 1);
+    TMVB_CUDA(cudaMemsetAsync(out, 0, 8, s.stream));
+    if (s.M > 0) {
+        ctpf_elbo_kernel<<<grid_for(s.M * 32, 128, s.n_sm), 128, 0, s.stream>>>(p, s.d_beta[s.cur ^ 1], h->d_H[h->hcur ^ 1], h->d_alef, h->d_he,
+                                                                               (float)dd, (float)hh, out);
+        TMVB_CUDA(cudaGetLastError());
+        s.st.kernel_launches++;
+    }
+    TMVB_CUDA(cudaMemcpyAsync(s.h_pinned, out, 8, cudaMemcpyDeviceToHost, s.stream));
+    TMVB_CUDA(cudaStreamSynchronize(s.stream));
+    s.st.d2h_bytes += 8;
+    *elbo_docs = s.h_pinned[0] + (double)s.M * K * (c * log(dd) - lgamma(c) + g * log(hh) - lgamma(g));
+    *elbo_global = glob;
+    return 0;
+}
+
+int tmvb_ctpf_download(tmvb_ctpf_t h, float *alef, float *he, float *bet, float *vav, float *gimel, float *zayin, float *dalet, float *het)
+{
+    TMVB_CHECK_ARG(h != nullptr, "handle is NULL");
+    Shard &s = h->s;
+    TMVB_CUDA(cudaSetDevice(s.device));
+    TMVB_CUDA(cudaStreamSynchronize(s.stream));
+    const int K = (int)s.K;
+    for (int i = 0; i < K; i++) {
+        if (bet) bet[i] = (float)h->bet[i];
+        if (vav) vav[i] = (float)h->vav[i];
+        if (dalet) dalet[i] = (float)h->dalet[i];
+        if (het) het[i] = (float)h->het[i];
+    }
+    TMVB_TRY(shard_download_rows(&s, h->d_alef, alef, s.V, nullptr));
+    TMVB_TRY(shard_download_rows(&s, h->d_he, he, h->U, nullptr));
+    TMVB_TRY(shard_download_rows(&s, h->d_gimel, gimel, s.M, s.d_perm));
+    TMVB_TRY(shard_download_rows(&s, h->d_zayin, zayin, s.M, s.d_perm));
+    return 0;
+}
+
+int tmvb_ctpf_download_old(tmvb_ctpf_t h, float *alef_old, float *he_old, float *bet_old, float *vav_old, float *gimel_old, float *zayin_old,
+                           float *dalet_old, float *het_old)
+{
+    TMVB_CHECK_ARG(h != nullptr, "handle is NULL");
+    Shard &s = h->s;
+    TMVB_CUDA(cudaSetDevice(s.device));
+    TMVB_CUDA(cudaStreamSynchronize(s.stream));
+    const int K = (int)s.K;
+    for (int i = 0; i < K; i++) {
+        if (bet_old) bet_old[i] = (float)h->bet_old[i];
+        if (vav_old) vav_old[i] = (float)h->vav_old[i];
+        if (dalet_old) dalet_old[i] = (float)h->dalet_old[i];
+        if (het_old) het_old[i] = (float)h->het_old[i];
+    }
+    TMVB_TRY(shard_download_rows(&s, h->d_alef_old, alef_old, s.V, nullptr));
+    TMVB_TRY(shard_download_rows(&s, h->d_he_old, he_old, h->U, nullptr));
+    TMVB_TRY(shard_download_rows(&s, h->d_gimel_old, gimel_old, s.M, s.d_perm));
+    TMVB_TRY(shard_download_rows(&s, h->d_zayin_old, zayin_old, s.M, s.d_perm));
+    return 0;
+}
+
+/* topics = per-topic ranking of Ebeta = alef ./ bet (gpuCTPF.jl:706-707): scaling a row by 1/bet_i does not change its order */
+int tmvb_ctpf_topics(tmvb_ctpf_t h, int32_t *topics)
+{
+    TMVB_CHECK_ARG(h && topics, "NULL argument");
+    TMVB_CUDA(cudaSetDevice(h->s.device));
+    return shard_topics(&h->s, h->d_alef, nullptr, topics);
+}
+
+int tmvb_ctpf_get_stats(tmvb_ctpf_t h, tmvb_stats *out)
+{
+    TMVB_CHECK_ARG(h && out, "NULL argument");
+    return shard_get_stats(&h->s, h->d_small + 2 * h->s.K_ld + 1, out);
+}
+
+}  // extern "C"

@@ -164,6 +164,71 @@ __device__ __forceinline__ void tok_final(const TokArgs &a, int ts, int kl, cons
     }
 }
 
+// Final pass for a 2K-way softmax that shares one table row: xi_r = [T ea ; T eb] / s_r, s_r = sum_i T_i (ea_i + eb_i)
+// (CTPF.jl:334-337).  Scatters rating_r (xi_a + xi_b) (CTPF.jl:274-277) and accumulates rating_r H(xi_r).
+template <int LPT, int CPL, bool OVF, bool ELBO>
+__device__ __forceinline__ void tok_final2(const TokArgs &a, int ts, int kl, const float4 (&ea)[CPL], const float4 (&eb)[CPL], float &ent)
+{
+    constexpr int S = 32 / LPT;
+    const int CH = a.K_ld >> 2;
+    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int r = 0; r < a.rounds; r++) {
+        const int n = r * S + ts;
+        const bool ok = n < a.Nd;
+        float4 b[CPL];
+        float c = 0.0f;
+        int term = 0;
+        const int nn = ok ? n : 0;
+        if (!OVF || n < a.cap) {
+            const float4 *row = reinterpret_cast<const float4 *>(a.tile + nn * a.RS) + kl;
+#pragma unroll
+            for (int m = 0; m < CPL; m++) b[m] = (m < CPL - 1 || kl + LPT * m < CH) ? row[LPT * m] : zero4;
+            if (ok) c = a.cnt_s[nn];
+            term = a.term_s[nn];
+        } else {
+            term = a.gterms[nn];
+            const float4 *row = reinterpret_cast<const float4 *>(a.gtable + (size_t)term * a.K_ld) + kl;
+#pragma unroll
+            for (int m = 0; m < CPL; m++) b[m] = (m < CPL - 1 || kl + LPT * m < CH) ? __ldg(row + LPT * m) : zero4;
+            if (ok) c = a.gcounts[nn];
+        }
+        float s0 = 0.0f, s1 = 0.0f;
+#pragma unroll
+        for (int m = 0; m < CPL; m++) {
+            s0 = fmaf(b[m].x, ea[m].x + eb[m].x, s0);
+            s1 = fmaf(b[m].y, ea[m].y + eb[m].y, s1);
+            s0 = fmaf(b[m].z, ea[m].z + eb[m].z, s0);
+            s1 = fmaf(b[m].w, ea[m].w + eb[m].w, s1);
+        }
+        const float s = group_sum<LPT>(s0 + s1);
+        if (ok) {
+            const float t = __fdividef(c, s);
+            float *srow = a.stats + (size_t)term * a.K_ld + 4 * kl;
+            float acc = 0.0f;
+#pragma unroll
+            for (int m = 0; m < CPL; m++) {
+                const int i0 = 4 * (kl + LPT * m);
+                if (i0 < a.K) {
+                    const float ax = b[m].x * ea[m].x, ay = b[m].y * ea[m].y, az = b[m].z * ea[m].z, aw = b[m].w * ea[m].w;
+                    const float bx = b[m].x * eb[m].x, by = b[m].y * eb[m].y, bz = b[m].z * eb[m].z, bw = b[m].w * eb[m].w;
+                    if (!(a.dbg & 1)) red_add_v4(srow + 4 * LPT * m, t * (ax + bx), t * (ay + by), t * (az + bz), t * (aw + bw));
+                    if (ELBO) {
+                        if (ax > 0.f) acc = fmaf(t * ax, __logf(ax), acc);
+                        if (bx > 0.f) acc = fmaf(t * bx, __logf(bx), acc);
+                        if (i0 + 1 < a.K && ay > 0.f) acc = fmaf(t * ay, __logf(ay), acc);
+                        if (i0 + 1 < a.K && by > 0.f) acc = fmaf(t * by, __logf(by), acc);
+                        if (i0 + 2 < a.K && az > 0.f) acc = fmaf(t * az, __logf(az), acc);
+                        if (i0 + 2 < a.K && bz > 0.f) acc = fmaf(t * bz, __logf(bz), acc);
+                        if (i0 + 3 < a.K && aw > 0.f) acc = fmaf(t * aw, __logf(aw), acc);
+                        if (i0 + 3 < a.K && bw > 0.f) acc = fmaf(t * bw, __logf(bw), acc);
+                    }
+                }
+            }
+            if (ELBO) ent += ((kl == 0) ? c * __logf(s) : 0.0f) - acc;
+        }
+    }
+}
+
 // owner-lane sum of the S per-stream partials of topic i (4 independent chains)
 template <int S>
 __device__ __forceinline__ float owner_sum(const float *gs, int RS, int i)

@@ -467,6 +467,61 @@ int shard_topics(Shard *s, const float *d_mat, const float *d_scale, int32_t *ou
     return 0;
 }
 
+int shard_pack_aux(Shard *s, const int64_t *cumsum, const int64_t *ids, const int64_t *vals, int64_t id_limit, long long **d_off, int **d_ids,
+                   float **d_vals, int64_t *nnz_out, std::vector<int> *len_internal)
+{
+    TMVB_CHECK_ARG(s->corpus_set, "set_corpus must precede the reader lists");
+    TMVB_CHECK_ARG(cumsum != nullptr && cumsum[0] == 0, "R_cumsum[0] must be 0");
+    const int64_t M = s->M, nnz = cumsum[M];
+    TMVB_CHECK_ARG(nnz >= 0 && (nnz == 0 || (ids && vals)), "reader arrays are NULL");
+    std::vector<long long> src_off(std::max<int64_t>(M, 1)), dst_off(M + 1);
+    len_internal->assign(M, 0);
+    dst_off[0] = 0;
+    for (int64_t p = 0; p < M; p++) {
+        const int d = s->h_perm[p];
+        const int64_t l = cumsum[d + 1] - cumsum[d];
+        if (l < 0 || l > (1 << 30)) return fail(-1, "invalid argument: R_cumsum must be nondecreasing (document %lld)", (long long)d);
+        src_off[p] = cumsum[d];
+        (*len_internal)[p] = (int)l;
+        dst_off[p + 1] = dst_off[p] + l;
+    }
+    cudaFree(*d_off);
+    cudaFree(*d_ids);
+    cudaFree(*d_vals);
+    *d_off = nullptr;
+    *d_ids = nullptr;
+    *d_vals = nullptr;
+    const size_t nz = (size_t)std::max<int64_t>(nnz, 1);
+    long long *d_src = nullptr;
+    TMVB_CUDA(cudaMalloc((void **)d_off, (M + 1) * 8));
+    TMVB_CUDA(cudaMalloc((void **)d_ids, nz * 4));
+    TMVB_CUDA(cudaMalloc((void **)d_vals, nz * 4));
+    TMVB_CUDA(cudaMalloc((void **)&d_src, std::max<int64_t>(M, 1) * 8));
+    TMVB_CUDA(cudaMemcpyAsync(*d_off, dst_off.data(), (M + 1) * 8, cudaMemcpyHostToDevice, s->stream));
+    if (M > 0) TMVB_CUDA(cudaMemcpyAsync(d_src, src_off.data(), M * 8, cudaMemcpyHostToDevice, s->stream));
+    s->st.h2d_bytes += (2 * M + 1) * 8;
+    int err = 0;
+    if (nnz > 0) {
+        TMVB_TRY(shard_scratch(s, (size_t)nnz * 16));
+        long long *t64 = (long long *)s->d_scratch, *c64 = t64 + nnz;
+        TMVB_CUDA(cudaMemcpyAsync(t64, ids, nnz * 8, cudaMemcpyHostToDevice, s->stream));
+        TMVB_CUDA(cudaMemcpyAsync(c64, vals, nnz * 8, cudaMemcpyHostToDevice, s->stream));
+        s->st.h2d_bytes += nnz * 16;
+        TMVB_CUDA(cudaMemsetAsync(s->d_counters + 63, 0, 4, s->stream));
+        pack_corpus_kernel<<<grid_for(M * 32, 256, s->n_sm), 256, 0, s->stream>>>(t64, c64, d_src, *d_off, M, (int)id_limit, *d_ids, *d_vals,
+                                                                                 s->d_counters + 63);
+        s->st.kernel_launches++;
+        TMVB_CUDA(cudaGetLastError());
+        TMVB_CUDA(cudaMemcpyAsync(&err, s->d_counters + 63, 4, cudaMemcpyDeviceToHost, s->stream));
+    }
+    TMVB_CUDA(cudaStreamSynchronize(s->stream));
+    cudaFree(d_src);
+    if (err & 1) return fail(-1, "invalid argument: readers must lie in [0, U)");
+    if (err & 2) return fail(-1, "invalid argument: all ratings must be positive integers");  // Corpus.jl:46
+    *nnz_out = nnz;
+    return 0;
+}
+
 int shard_get_stats(Shard *s, const double *d_sweeps, tmvb_stats *out)
 {
     TMVB_CUDA(cudaSetDevice(s->device));

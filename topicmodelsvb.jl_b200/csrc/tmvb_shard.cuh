@@ -73,5 +73,8 @@ int shard_launch(Shard *s, const void *fn, void *dev_struct);
 int shard_normalize(Shard *s, double *d_acc, bool want_elbo, float prior);
 int shard_topics(Shard *s, const float *d_mat, const float *d_scale, int32_t *out);
 int shard_get_stats(Shard *s, const double *d_sweeps, tmvb_stats *out);
+// a second per-document list (CTPF reader lists, modelutils.jl:443-472) re-laid-out in the shard's internal document order
+int shard_pack_aux(Shard *s, const int64_t *cumsum, const int64_t *ids, const int64_t *vals, int64_t id_limit, long long **d_off, int **d_ids,
+                   float **d_vals, int64_t *nnz_out, std::vector<int> *len_internal);
 
 }  // namespace tmvb

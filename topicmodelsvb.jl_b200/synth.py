@@ -146,3 +146,20 @@ def init_beta(K: int, V: int, seed: int = 7) -> np.ndarray:
     g = rng.standard_exponential(size=(K, V))
     g /= g.sum(axis=1, keepdims=True)
     return np.ascontiguousarray(g.T)
+
+
+def init_alef(K: int, V: int, seed: int = 7) -> np.ndarray:
+    """alef = exp.(rand(Dirichlet(V, 1.0), K)' .- 0.5) (CTPF.jl:83), returned (V, K) C-order."""
+    return np.exp(init_beta(K, V, seed) - 0.5)
+
+
+def gencorp_ctpf(M=60, V=300, U=40, K=4, seed=0, mean_len=40.0, mean_readers=4.0) -> CSR:
+    """LDA-generated documents plus random reader lists (ratings all 1, as readcorp(:citeu) yields, Corpus.jl:21,351)."""
+    c = gencorp_lda(M=M, V=V, K=K, seed=seed, mean_len=mean_len)
+    rng = np.random.default_rng(seed + 1000)
+    R = rng.poisson(mean_readers, size=M)
+    R[0] = 0                                     # a document nobody has in their library
+    d = np.repeat(np.arange(M), R)
+    u = rng.integers(0, U, size=d.size)
+    roff, rd, _ = _condense(d, u, M, U)
+    return CSR(M, V, c.N_cumsum, c.terms, c.counts, U, roff, rd, np.ones_like(rd))
