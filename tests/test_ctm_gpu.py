@@ -101,3 +101,16 @@ def test_ctm_citeulike_size_parity(tm, orc):
     print("rel diff", rel.tolist(), "estep_ms", model.stats().estep_ms)
     assert np.all(rel < ELBO_RTOL)
     tm.check_model(model)
+
+
+def test_ctm_against_committed_golden(tm):
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ctm_cfg.npz"))
+    K, V = int(g["K"]), int(g["V"])
+    c = tm.synth.CSR(len(g["N_cumsum"]) - 1, V, g["N_cumsum"], g["terms"].astype(np.int64), g["counts"].astype(np.int64))
+    model = tm.gpuCTM(tm.Corpus.from_csr(c), K)
+    model.beta = np.array(g["beta0"].T, dtype=np.float32, order="F")
+    tr = []
+    tm.train(model, iter=len(g["elbo"]) - 1, tol=0.0, printelbo=False, trace=tr)
+    np.testing.assert_allclose(tr, g["elbo"][: len(tr)], rtol=ELBO_RTOL)
+    np.testing.assert_allclose(model.sigma, g["sigma"], rtol=1e-2, atol=1e-3)

@@ -108,3 +108,17 @@ def test_ctpf_citeulike_size_parity(tm, orc):
     print("rel diff", rel.tolist(), "estep_ms", model.stats().estep_ms)
     assert np.all(rel < ELBO_RTOL)
     tm.check_model(model)
+
+
+def test_ctpf_against_committed_golden(tm):
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ctpf_cfg.npz"))
+    K, V, U = int(g["K"]), int(g["V"]), int(g["U"])
+    c = tm.synth.CSR(len(g["N_cumsum"]) - 1, V, g["N_cumsum"], g["terms"].astype(np.int64), g["counts"].astype(np.int64), U,
+                     g["R_cumsum"], g["readers"].astype(np.int64), g["ratings"].astype(np.int64))
+    model = tm.gpuCTPF(tm.Corpus.from_csr(c), K)
+    model.alef = np.array(g["alef0"].T, dtype=np.float32, order="F")
+    tr = []
+    tm.train(model, iter=len(g["elbo"]) - 1, tol=0.0, printelbo=False, trace=tr)
+    np.testing.assert_allclose(tr, g["elbo"][: len(tr)], rtol=ELBO_RTOL)
+    np.testing.assert_allclose(model.vav, g["vav"], rtol=2e-3)

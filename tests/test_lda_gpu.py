@@ -180,3 +180,26 @@ def test_topics_ranked_on_device(tm):
     for i in range(K):
         want = np.argsort(model.beta[i, :], kind="stable")[::-1] + 1
         np.testing.assert_array_equal(np.asarray(model.topics[i]), want)
+
+
+def test_lda_against_committed_golden(tm):
+    """tests/golden/lda_cfg0.npz (generated by tools/make_golden.py from both oracle restatements)."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "lda_cfg0.npz"))
+    K, V = int(g["K"]), int(g["V"])
+    c = tm.synth.CSR(len(g["N_cumsum"]) - 1, V, g["N_cumsum"], g["terms"].astype(np.int64), g["counts"].astype(np.int64))
+    model = tm.gpuLDA(tm.Corpus.from_csr(c), K)
+    model.beta = np.array(g["beta0"].T, dtype=np.float32, order="F")
+    tr = []
+    tm.train(model, iter=20, tol=0.0, printelbo=False, trace=tr)
+    np.testing.assert_allclose(tr, g["elbo"], rtol=ELBO_RTOL)
+    np.testing.assert_allclose(model.alpha, g["alpha"], rtol=5e-4)
+    np.testing.assert_allclose(model.beta.T, g["beta"], rtol=1e-2, atol=1e-8)
+
+
+def test_lda_k200_layout(tm, orc):
+    """K=200 (BASELINE config 5's topic count): the LPT=8 x CPL=7 lane layout and 7 topics per lane in the K phase."""
+    c = tm.synth.gencorp_lda(M=120, V=900, K=12, seed=4, mean_len=80)
+    model, trace, st, ref, _ = _run_pair(tm, orc, c, 200, iters=3)
+    np.testing.assert_allclose(trace, ref, rtol=ELBO_RTOL)
+    np.testing.assert_allclose(model.gamma.T, st.gamma, rtol=2e-3, atol=1e-6)

@@ -108,3 +108,67 @@ def test_estep_scatter_equals_train_statistics(orc):
     np.testing.assert_allclose(stats.sum(), c.counts.sum(), rtol=1e-12)       # every token's phi sums to one
     phi = orc.lda_phi(K, c.M, c.N_cumsum, c.terms, b.beta_old, b.Elogtheta_old)
     np.testing.assert_allclose(phi.sum(axis=1), 1.0, rtol=1e-12)
+
+
+@pytest.mark.parametrize("K,seed", [(6, 1), (1, 2), (11, 3)])
+def test_ctm_c_oracle_matches_numpy_twin(orc, K, seed):
+    import topicmodelsvb_b200.synth as synth
+    from oracle.numpy_twin import CTMTwin
+
+    c = synth.gencorp_lda(M=40, V=150, K=4, seed=seed)
+    beta0 = synth.init_beta(K, c.V, seed=7)
+    st = orc.CTMState(K, c.M, c.V, beta0)
+    tr, sw, done = orc.ctm_train(st, c.N_cumsum, c.terms, c.counts, iter=4, tol=0.0)
+    tw = CTMTwin(c.N_cumsum, c.terms, c.counts, K, c.V, beta0)
+    t2 = tw.train(iter=4, tol=0.0)
+    np.testing.assert_allclose(tr, t2, rtol=1e-10)
+    np.testing.assert_allclose(st.lam, tw.lam, rtol=1e-8, atol=1e-10)
+    np.testing.assert_allclose(st.vsq, tw.vsq, rtol=1e-8)
+    np.testing.assert_allclose(st.sigma, tw.sigma, rtol=1e-8, atol=1e-12)
+    np.testing.assert_allclose(st.mu, tw.mu, rtol=1e-8, atol=1e-12)
+    np.testing.assert_allclose(st.invsigma @ st.sigma, np.eye(K), atol=1e-9)          # CTM.jl:110
+    assert np.all(st.vsq > 0) and np.all(np.linalg.eigvalsh(st.sigma) > 0)             # check_model, modelutils.jl:113-119
+
+
+@pytest.mark.parametrize("K,ratings_max", [(5, 1), (3, 4), (1, 2)])
+def test_ctpf_c_oracle_long_form_matches_closed_form_twin(orc, K, ratings_max):
+    """The C oracle evaluates the reference's Binomial x lnGamma sums and Distributions' entropy(Multinomial) literally
+    (CTPF.jl:111-141,179-194); the NumPy twin uses the closed form they collapse to.  Agreement pins that identity."""
+    import topicmodelsvb_b200.synth as synth
+    from oracle.numpy_twin import CTPFTwin
+
+    c = synth.gencorp_ctpf(M=30, V=120, U=25, K=3, seed=4)
+    if ratings_max > 1:
+        c = c._replace(ratings=np.random.default_rng(5).integers(1, ratings_max + 1, size=len(c.readers)))
+    alef0 = synth.init_alef(K, c.V, seed=7)
+    st = orc.CTPFState(K, c.M, c.V, c.U, alef0)
+    tr, sw, done = orc.ctpf_train(st, c, iter=4, tol=0.0)
+    tw = CTPFTwin(c.N_cumsum, c.terms, c.counts, c.R_cumsum, c.readers, c.ratings, K, c.V, c.U, alef0)
+    t2 = tw.train(iter=4, tol=0.0)
+    n = min(int(np.isfinite(tr).sum()), int(np.isfinite(t2).sum()))
+    np.testing.assert_allclose(tr[:n], t2[:n], rtol=1e-11)
+    np.testing.assert_allclose(st.gimel, tw.gimel, rtol=1e-9)
+    np.testing.assert_allclose(st.zayin, tw.zayin, rtol=1e-9)
+    np.testing.assert_allclose(st.alef, tw.alef, rtol=1e-9)
+    np.testing.assert_allclose(st.he, tw.he, rtol=1e-9)
+    for nme in ("bet", "vav", "dalet", "het"):
+        np.testing.assert_allclose(getattr(st, nme), getattr(tw, nme), rtol=1e-10)
+
+
+def test_golden_ctm_and_ctpf(orc):
+    g = np.load(os.path.join(GOLD, "ctm_cfg.npz"))
+    K, V = int(g["K"]), int(g["V"])
+    M = len(g["N_cumsum"]) - 1
+    st = orc.CTMState(K, M, V, g["beta0"])
+    tr, _, _ = orc.ctm_train(st, g["N_cumsum"], g["terms"].astype(np.int64), g["counts"].astype(np.int64), iter=len(g["elbo"]) - 1, tol=0.0)
+    np.testing.assert_allclose(tr, g["elbo"], rtol=1e-10)
+    np.testing.assert_allclose(st.sigma, g["sigma"], rtol=1e-8, atol=1e-12)
+    import topicmodelsvb_b200.synth as synth
+    g = np.load(os.path.join(GOLD, "ctpf_cfg.npz"))
+    K, V, U = int(g["K"]), int(g["V"]), int(g["U"])
+    c = synth.CSR(len(g["N_cumsum"]) - 1, V, g["N_cumsum"], g["terms"].astype(np.int64), g["counts"].astype(np.int64), U,
+                  g["R_cumsum"], g["readers"].astype(np.int64), g["ratings"].astype(np.int64))
+    st = orc.CTPFState(K, c.M, V, U, g["alef0"])
+    tr, _, _ = orc.ctpf_train(st, c, iter=len(g["elbo"]) - 1, tol=0.0)
+    np.testing.assert_allclose(tr, g["elbo"], rtol=1e-10)
+    np.testing.assert_allclose(st.vav, g["vav"], rtol=1e-10)

@@ -14,7 +14,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import oracle  # noqa: E402
-from oracle.numpy_twin import LDATwin  # noqa: E402
+from oracle.numpy_twin import CTMTwin, CTPFTwin, LDATwin  # noqa: E402
 import topicmodelsvb_b200.synth as synth  # noqa: E402
 
 
@@ -34,9 +34,37 @@ def lda_cfg0():
                 Elogtheta=st.Elogtheta, beta_old=st.beta_old, Elogtheta_old=st.Elogtheta_old)
 
 
+def ctm_cfg():
+    K = 6
+    c = synth.gencorp_lda(M=60, V=300, K=4, seed=1)
+    beta0 = synth.init_beta(K, c.V, seed=7)
+    st = oracle.CTMState(K, c.M, c.V, beta0)
+    trace, sweeps, _ = oracle.ctm_train(st, c.N_cumsum, c.terms, c.counts, iter=8, tol=0.0)
+    tw = CTMTwin(c.N_cumsum, c.terms, c.counts, K, c.V, beta0)
+    assert np.max(np.abs(trace - tw.train(iter=8, tol=0.0)) / np.abs(trace)) < 1e-10
+    return dict(K=K, V=c.V, N_cumsum=c.N_cumsum, terms=c.terms.astype(np.int32), counts=c.counts.astype(np.int32), beta0=beta0,
+                elbo=trace, sweeps=sweeps, mu=st.mu, sigma=st.sigma, beta=st.beta, lam=st.lam, vsq=st.vsq, logzeta=st.logzeta)
+
+
+def ctpf_cfg():
+    K = 5
+    c = synth.gencorp_ctpf(M=60, V=300, U=40, K=4, seed=0)
+    alef0 = synth.init_alef(K, c.V, seed=7)
+    st = oracle.CTPFState(K, c.M, c.V, c.U, alef0)
+    trace, sweeps, _ = oracle.ctpf_train(st, c, iter=8, tol=0.0)
+    tw = CTPFTwin(c.N_cumsum, c.terms, c.counts, c.R_cumsum, c.readers, c.ratings, K, c.V, c.U, alef0)
+    assert np.nanmax(np.abs(trace - tw.train(iter=8, tol=0.0)) / np.abs(trace)) < 1e-10
+    return dict(K=K, V=c.V, U=c.U, N_cumsum=c.N_cumsum, terms=c.terms.astype(np.int32), counts=c.counts.astype(np.int32),
+                R_cumsum=c.R_cumsum, readers=c.readers.astype(np.int32), ratings=c.ratings.astype(np.int32), alef0=alef0,
+                elbo=trace, sweeps=sweeps, alef=st.alef, he=st.he, bet=st.bet, vav=st.vav, dalet=st.dalet, het=st.het,
+                gimel=st.gimel, zayin=st.zayin)
+
+
 if __name__ == "__main__":
     out = os.path.join(ROOT, "tests", "golden")
     os.makedirs(out, exist_ok=True)
     np.savez_compressed(os.path.join(out, "lda_cfg0.npz"), **lda_cfg0())
+    np.savez_compressed(os.path.join(out, "ctm_cfg.npz"), **ctm_cfg())
+    np.savez_compressed(os.path.join(out, "ctpf_cfg.npz"), **ctpf_cfg())
     for f in sorted(os.listdir(out)):
         print(f, os.path.getsize(os.path.join(out, f)), "bytes")
