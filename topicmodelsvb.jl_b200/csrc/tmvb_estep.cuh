@@ -22,6 +22,9 @@
 
 namespace tmvb {
 
+// rounds of the sweep pass kept in flight per warp (independent LDS.128 -> FFMA -> shuffle chains)
+constexpr int kSweepUnroll = 2;
+
 #ifdef __CUDACC__
 
 template <int LPT>
@@ -59,7 +62,7 @@ __device__ __forceinline__ void tok_sweep(const TokArgs &a, int ts, int kl, cons
     const int CH = a.K_ld >> 2;
     const float Keps = EPS ? (float)a.K * TMVB_EPS : 0.0f;
     const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll 2
+#pragma unroll kSweepUnroll
     for (int r = 0; r < a.rounds; r++) {
         const int n = r * S + ts;
         const bool ok = n < a.Nd;
