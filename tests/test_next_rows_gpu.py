@@ -1,0 +1,87 @@
+"""GPU tests of the 'next' rows of SURVEY 8(f): predict (E-step-only inference) and the 2-GPU NCCL exchange."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_predict_lda_matches_oracle_estep(tm, orc):
+    """predict(corp, train_model) (modelutils.jl:831-855): frozen alpha/beta, per-document sweeps on unseen documents."""
+    train = tm.synth.gencorp_lda(M=150, V=400, K=5, seed=1)
+    new = tm.synth.gencorp_lda(M=40, V=400, K=5, seed=2)
+    K = 6
+    m = tm.gpuLDA(tm.Corpus.from_csr(train), K, seed=3)
+    tm.train(m, iter=5, tol=0.0, printelbo=False)
+    p = tm.predict(tm.Corpus.from_csr(new), m)
+    st = orc.LDAState(K, new.M, new.V, alpha=m.alpha, beta=np.ascontiguousarray(m.beta.T))
+    orc.lda_estep(st, new.N_cumsum, new.terms, new.counts, viter=10, want_stats=False)
+    np.testing.assert_allclose(p.gamma.T, st.gamma, rtol=2e-3, atol=1e-5)
+    np.testing.assert_allclose(p.Elogtheta.T, st.Elogtheta, rtol=2e-3, atol=5e-4)
+    td = tm.topicdist(p, 0)
+    np.testing.assert_allclose(td, st.gamma[0] / st.gamma[0].sum(), rtol=2e-3, atol=1e-6)
+    with pytest.raises(tm.CorpusError):
+        tm.predict(tm.Corpus.from_csr(tm.synth.gencorp_lda(M=5, V=77, K=3, seed=0)), m)
+
+
+def test_predict_ctm_runs_and_is_finite(tm):
+    train = tm.synth.gencorp_lda(M=100, V=300, K=4, seed=1)
+    new = tm.synth.gencorp_lda(M=30, V=300, K=4, seed=5)
+    m = tm.gpuCTM(tm.Corpus.from_csr(train), 5, seed=3)
+    tm.train(m, iter=3, tol=0.0, printelbo=False)
+    p = tm.predict(tm.Corpus.from_csr(new), m)
+    assert p.lam.shape == (5, new.M) and np.all(np.isfinite(p.lam)) and np.all(p.vsq > 0)
+    td = tm.topicdist(p, 3)
+    assert abs(td.sum() - 1) < 1e-6
+
+
+_WORKER = r'''
+import os, sys, json
+import numpy as np
+sys.path.insert(0, %r)
+import torch, torch.distributed as dist
+import topicmodelsvb_b200 as tm
+rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+torch.cuda.set_device(int(os.environ["LOCAL_RANK"]))
+dist.init_process_group("nccl", device_id=torch.device("cuda", int(os.environ["LOCAL_RANK"])))
+work = torch.cuda.Stream(); torch.cuda.set_stream(work)
+red = tm.dist.Reducer()
+c = tm.synth.gencorp_lda(M=400, V=600, K=6, seed=11)
+K = 8
+beta0 = tm.synth.init_beta(K, c.V, seed=7).astype(np.float32)
+sh = c.shard(rank, world)
+m = tm.gpuLDA(tm.Corpus.from_csr(sh), K, reducer=red, M_total=c.M, stream=work.cuda_stream)
+m.beta = np.array(beta0.T, order="F", copy=True)
+tr = []
+tm.train(m, iter=4, tol=0.0, printelbo=False, trace=tr)
+if rank == 0:
+    print("RESULT " + json.dumps({"elbo": tr, "alpha": m.alpha.tolist()}))
+dist.destroy_process_group()
+'''
+
+
+def test_two_gpu_nccl_matches_single_gpu(tm, orc, tmp_path):
+    """Doc-sharded d %% 2 over two GPUs with an NCCL all-reduce of the statistics == the single-process trajectory."""
+    import torch
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (run with gpurun --gpus 2)")
+    script = tmp_path / "worker.py"
+    script.write_text(_WORKER % ROOT)
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                        "--master-port", "29533", str(script)], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    import json
+    line = [l for l in r.stdout.splitlines() if l.startswith("RESULT ")][-1]
+    got = json.loads(line[7:])
+    c = tm.synth.gencorp_lda(M=400, V=600, K=6, seed=11)
+    K = 8
+    beta0 = tm.synth.init_beta(K, c.V, seed=7).astype(np.float32)
+    st = orc.LDAState(K, c.M, c.V, beta=beta0)
+    ref, _, _ = orc.lda_train(st, c.N_cumsum, c.terms, c.counts, iter=4, tol=0.0)
+    np.testing.assert_allclose(got["elbo"], ref, rtol=2e-6)
+    np.testing.assert_allclose(got["alpha"], st.alpha, rtol=5e-4)

@@ -11,6 +11,8 @@ from .gpu_lda import check_elbo, gpuLDA  # noqa: F401
 from .gpu_lda import check_model as check_model_lda  # noqa: F401
 from .gpu_lda import train as train_lda  # noqa: F401
 
+from .predict import predict, topicdist  # noqa: F401,E402
+
 
 def train(model, **kwargs):
     """train!(model; kwargs...) -- dispatches on the model type like the reference's methods."""
