@@ -31,6 +31,14 @@ def test_predict_lda_matches_oracle_estep(tm, orc):
 def test_predict_ctm_runs_and_is_finite(tm):
     train = tm.synth.gencorp_lda(M=100, V=300, K=4, seed=1)
     new = tm.synth.gencorp_lda(M=30, V=300, K=4, seed=5)
+    # CTM has no epsilon in phi (CTM.jl:177): a term unseen in training has beta = 0 for every topic and yields NaN in the
+    # reference as well, so keep only terms the training corpus contains
+    seen = np.zeros(300, bool)
+    seen[train.terms] = True
+    keep = seen[new.terms]
+    doc = np.repeat(np.arange(new.M), np.diff(new.N_cumsum))[keep]
+    off = np.concatenate([[0], np.cumsum(np.bincount(doc, minlength=new.M))]).astype(np.int64)
+    new = tm.synth.CSR(new.M, new.V, off, new.terms[keep], new.counts[keep])
     m = tm.gpuCTM(tm.Corpus.from_csr(train), 5, seed=3)
     tm.train(m, iter=3, tol=0.0, printelbo=False)
     p = tm.predict(tm.Corpus.from_csr(new), m)
