@@ -257,6 +257,7 @@ template <typename real>
 __global__ void lda_elbo_kernel(const LdaDev p, const float *__restrict__ beta_old, double lg_alpha_term, double *out)
 {
     constexpr bool F64 = sizeof(real) == 8;
+    constexpr int RM = 8;  // K <= 256: topics i = lane + 32 r held in registers
     const int lane = threadIdx.x & 31;
     const int wpb = blockDim.x >> 5;
     const real eps = (real)TMVB_EPS_D;
@@ -266,14 +267,23 @@ __global__ void lda_elbo_kernel(const LdaDev p, const float *__restrict__ beta_o
         const int Nd = (int)(p.doc_off[d + 1] - o);
         const float *En = p.Elogtheta + d * p.K_ld, *Eo = p.Elogtheta_old + d * p.K_ld, *gm = p.gamma + d * p.K_ld;
         double dacc = 0.0, g0 = 0.0;
-        for (int i = lane; i < p.K; i += 32) {
-            const double g = gm[i], E = En[i];
-            g0 += g;
-            if (F64) {
-                dacc += ((double)p.alpha[i] - 1.0) * E + lgamma(g) - (g - 1.0) * d_digamma(g);
-            } else {
-                const PsiLg pl = psi_lgamma<true>((float)g);
-                dacc += ((double)p.alpha[i] - 1.0) * E + (double)pl.lg - (g - 1.0) * (double)pl.psi;
+        real e_r[RM], En_r[RM];
+#pragma unroll
+        for (int r = 0; r < RM; r++) {
+            const int i = lane + 32 * r;
+            e_r[r] = 0;
+            En_r[r] = 0;
+            if (i < p.K) {
+                const double g = gm[i], E = En[i];
+                g0 += g;
+                e_r[r] = F64 ? (real)exp((double)Eo[i]) : (real)expf(Eo[i]);
+                En_r[r] = (real)E;
+                if (F64) {
+                    dacc += ((double)p.alpha[i] - 1.0) * E + lgamma(g) - (g - 1.0) * d_digamma(g);
+                } else {
+                    const PsiLg pl = psi_lgamma<true>((float)g);
+                    dacc += ((double)p.alpha[i] - 1.0) * E + (double)pl.lg - (g - 1.0) * (double)pl.psi;
+                }
             }
         }
         g0 = warp_sum_d(g0);
@@ -282,18 +292,27 @@ __global__ void lda_elbo_kernel(const LdaDev p, const float *__restrict__ beta_o
             const int term = p.terms[o + n];
             const real c = p.counts[o + n];
             const float *bo = beta_old + (size_t)term * p.K_ld, *bn = p.beta + (size_t)term * p.K_ld;
-            real s = 0;
-            for (int i = lane; i < p.K; i += 32) s += eps + (real)bo[i] * (F64 ? (real)exp((double)Eo[i]) : (real)expf(Eo[i]));
-            s = F64 ? (real)warp_sum_d((double)s) : (real)warp_sum((float)s);
-            real a = 0;
-            for (int i = lane; i < p.K; i += 32) {
-                const real u = eps + (real)bo[i] * (F64 ? (real)exp((double)Eo[i]) : (real)expf(Eo[i]));
-                const real ph = u / s;
-                const real lb = F64 ? (real)log((double)bn[i] + TMVB_EPS_D) : (real)logf(bn[i] + TMVB_EPS);
-                const real lp = F64 ? (real)(ph > 0 ? log((double)ph) : 0.0) : (real)(ph > 0 ? logf((float)ph) : 0.f);
-                a += ph * ((real)En[i] + lb - lp);
+            real u_r[RM], s = 0;
+#pragma unroll
+            for (int r = 0; r < RM; r++) {
+                const int i = lane + 32 * r;
+                u_r[r] = (i < p.K) ? eps + (real)bo[i] * e_r[r] : (real)0;
+                s += u_r[r];
             }
-            if (F64) dacc += (double)(c * a); else tacc += c * a;
+            s = F64 ? (real)warp_sum_d((double)s) : (real)warp_sum((float)s);
+            // sum_i phi_i (E_i + ln(beta_i + eps) - ln phi_i),  phi = u / s,  ln phi = ln u - ln s
+            const real ls = F64 ? (real)log((double)s) : (real)__logf((float)s);
+            real a = 0;
+#pragma unroll
+            for (int r = 0; r < RM; r++) {
+                const int i = lane + 32 * r;
+                if (i < p.K) {
+                    const real lb = F64 ? (real)log((double)bn[i] + TMVB_EPS_D) : (real)__logf(bn[i] + TMVB_EPS);
+                    const real lu = F64 ? (real)log((double)u_r[r]) : (real)__logf((float)u_r[r]);
+                    a += u_r[r] * (En_r[r] + lb - lu + ls);
+                }
+            }
+            if (F64) dacc += (double)(c * a / s); else tacc += c * a / s;
         }
         dacc += (double)tacc;
         dacc = warp_sum_d(dacc);
