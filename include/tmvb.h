@@ -91,13 +91,14 @@ int tmvb_lda_mstep(tmvb_lda_t h);
 /* `@host model.Elogtheta_sum_buffer` (macros.jl:79, gpuLDA.jl:133); fp64. */
 int tmvb_lda_get_elogtheta_sum(tmvb_lda_t h, double *out);
 
-/* update_alpha! (LDA.jl:97-118 / gpuLDA.jl:132-154) done inside the library in fp64 on the host
- * from the reduced Elogtheta_sum, then written to the device.  M_total as above.  alpha_out[K] may be NULL. */
+/* update_alpha! (LDA.jl:97-118 / gpuLDA.jl:132-154): the interior-point Newton iteration in fp64 in a one-warp device kernel
+ * on the reduced Elogtheta_sum, fused with the assembly of the ELBO from the partials of the last estep/mstep.  M_total as
+ * above.  Asynchronous when alpha_out is NULL; otherwise alpha_out[K] receives the new alpha (synchronises). */
 int tmvb_lda_update_alpha(tmvb_lda_t h, int64_t M_total, int niter, double ntol, float *alpha_out);
 
 /* update_elbo! (gpuLDA.jl:121-128 via check_elbo!, modelutils.jl:574-585) without the K x sumN phi
- * transfer.  mode 0: assemble from the partials accumulated by the last estep(want_elbo=1)+mstep
- * (needs the current alpha; M_total as above).  mode 1: full recomputation from device state with
+ * transfer.  mode 0: the value assembled on the device by estep(want_elbo=1) -> mstep -> update_alpha (one 8-byte
+ * read-back).  mode 1 (fp32 elements) / mode 2 (fp64): full recomputation from device state with
  * the CPU model's lagged-phi semantics (LDA.jl:83-93); used for the initial ELBO.  For sharded runs
  * mode 1 returns this shard's document terms plus the global terms on every rank, so the caller
  * sums `*elbo_docs` over ranks and adds `*elbo_global` once. */

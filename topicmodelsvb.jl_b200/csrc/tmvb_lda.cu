@@ -325,6 +325,116 @@ __global__ void lda_elbo_kernel(const LdaDev p, const float *__restrict__ beta_o
     if (lane == 0 && acc != 0.0) atomicAdd(out, acc);
 }
 
+// psi(x) and psi'(x) together in fp64 without a division per recurrence step: with P(x) = x (x+1) ... (x+9),
+//   psi(x) = psi(x+10) - P'/P ,   psi'(x) = psi'(x+10) + (P'^2 - P P'') / P^2 ,
+// P, P', P'' by the product rule (fixed 10 steps, branch-free), then the Bernoulli series at y = x + 10 >= 10.
+__device__ __forceinline__ void d_psi_tri(double x, double &psi, double &tri)
+{
+    double P = x, D1 = 1.0, D2 = 0.0;
+#pragma unroll
+    for (int k = 1; k < 10; k++) {
+        const double f = x + (double)k;
+        D2 = fma(D2, f, 2.0 * D1);
+        D1 = fma(D1, f, P);
+        P *= f;
+    }
+    const double y = x + 10.0, t = 1.0 / y, t2 = t * t, iP = 1.0 / P, q = D1 * iP;
+    const double sp = t2 * (1.0 / 12 - t2 * (1.0 / 120 - t2 * (1.0 / 252 - t2 * (1.0 / 240 - t2 * (1.0 / 132 - t2 * (691.0 / 32760 - t2 * (1.0 / 12)))))));
+    psi = log(y) - 0.5 * t - sp - q;
+    const double st = t * (1.0 + 0.5 * t + t2 * (1.0 / 6 - t2 * (1.0 / 30 - t2 * (1.0 / 42 - t2 * (1.0 / 30 - t2 * (5.0 / 66 - t2 * (691.0 / 2730 - t2 * (7.0 / 6))))))));
+    tri = st + (q * q - D2 * iP);
+}
+__device__ __forceinline__ double warp_min_d(double v)
+{
+#pragma unroll
+    for (int m = 16; m > 0; m >>= 1) v = fmin(v, __shfl_xor_sync(0xffffffffu, v, m));
+    return v;
+}
+
+// update_alpha! (LDA.jl:97-118): interior-point Newton with log barrier, fp64, one warp (lane l owns alpha_{l+32r});
+// then, when the last E-step accumulated ELBO partials, the whole ELBO is assembled here (see tmvb_lda_elbo) so that
+// an outer iteration needs a single 8-byte read-back instead of three host round trips.
+//   small = [sum_d Elogtheta_d (K_ld) | per-document ELBO terms | sweeps], local = [rowsum (K_ld) | elbo_w]
+__global__ void lda_alpha_kernel(double *__restrict__ alpha64, float *__restrict__ alpha32, const double *__restrict__ small,
+                                 const double *__restrict__ local, int K, int K_ld, double Md, int niter, double ntol, int want_elbo,
+                                 double *__restrict__ result)
+{
+    constexpr int RM = 8;
+    const int lane = threadIdx.x;
+    double a[RM], a_estep[RM], Es[RM], grad[RM], hinv[RM], pd[RM];
+#pragma unroll
+    for (int r = 0; r < RM; r++) {
+        const int i = lane + 32 * r;
+        a[r] = (i < K) ? alpha64[i] : 1.0;
+        a_estep[r] = a[r];
+        Es[r] = (i < K) ? small[i] : 0.0;
+    }
+    double nu = (double)K;
+    for (int it = 0; it < niter; it++) {
+        double a0 = 0.0;
+#pragma unroll
+        for (int r = 0; r < RM; r++)
+            if (lane + 32 * r < K) a0 += a[r];
+        a0 = warp_sum_d(a0);
+        double dg0, tg0;
+        d_psi_tri(a0, dg0, tg0);
+        double gh = 0.0, hs = 0.0, gn = 0.0;
+#pragma unroll
+        for (int r = 0; r < RM; r++) {
+            grad[r] = hinv[r] = 0.0;
+            if (lane + 32 * r < K) {
+                double dg, tg;
+                d_psi_tri(a[r], dg, tg);
+                grad[r] = nu / a[r] + Md * (dg0 - dg) + Es[r];
+                hinv[r] = -1.0 / (Md * tg + nu / (a[r] * a[r]));
+                gh += grad[r] * hinv[r];
+                hs += hinv[r];
+                gn += grad[r] * grad[r];
+            }
+        }
+        gh = warp_sum_d(gh);
+        hs = warp_sum_d(hs);
+        gn = warp_sum_d(gn);
+        const double z = gh / (1.0 / (Md * tg0) + hs);
+        double rho = 1.0;
+#pragma unroll
+        for (int r = 0; r < RM; r++) pd[r] = (grad[r] - z) * hinv[r];
+        for (;;) {
+            double mn = 1e300;
+#pragma unroll
+            for (int r = 0; r < RM; r++)
+                if (lane + 32 * r < K) mn = fmin(mn, a[r] - rho * pd[r]);
+            mn = warp_min_d(mn);
+            if (!(mn < 0.0)) break;
+            rho *= 0.5;
+        }
+#pragma unroll
+        for (int r = 0; r < RM; r++)  // @finite alpha -= rho * p  (macros.jl:52-54)
+            if (lane + 32 * r < K) a[r] = copysign(fmin(fabs(a[r] - rho * pd[r]), 1.7976931348623157e308), a[r]);
+        if ((rho * sqrt(gn) < ntol) && (nu / (double)K < ntol)) break;
+        nu *= 0.5;
+    }
+    double a0 = 0.0, sl = 0.0, lin = 0.0;
+#pragma unroll
+    for (int r = 0; r < RM; r++) {
+        const int i = lane + 32 * r;
+        if (i < K) {
+            a[r] += TMVB_EPS_D;  // @positive model.alpha
+            alpha64[i] = a[r];
+            alpha32[i] = fmaxf((float)a[r], 1.1754944e-38f);
+            a0 += a[r];
+            sl += lgamma(a[r]);
+            lin += (a[r] - a_estep[r] - TMVB_EPS_D) * Es[r];
+        }
+    }
+    if (want_elbo) {
+        a0 = warp_sum_d(a0);
+        sl = warp_sum_d(sl);
+        lin = warp_sum_d(lin);
+        if (lane == 0) result[0] = small[K_ld] + Md * (lgamma(a0) - sl) + lin + local[K_ld];
+    }
+}
+
 // phi[K x sumN] in the caller's token order, rebuilt from beta_old / Elogtheta_old (LDA.jl:87-88)
 __global__ void lda_phi_kernel(const LdaDev p, const float *__restrict__ beta_old, const long long *__restrict__ src_off, float *__restrict__ phi)
 {
@@ -358,7 +468,8 @@ struct tmvb_lda_s {
     float *d_alpha = nullptr;
     float *d_Elogtheta = nullptr, *d_Elogtheta_old = nullptr, *d_gamma = nullptr;
     std::vector<double> h_alpha;        // fp64 master copy of alpha (update_alpha! runs in fp64 on the host)
-    std::vector<double> h_alpha_estep;  // alpha the last E-step ran with
+    double *d_alpha64 = nullptr;        // [K_ld] fp64 alpha on the device (master while alpha_on_device)
+    bool alpha_on_device = false, elbo_dev_valid = false;
     double *d_small = nullptr;          // [K_ld+2], summed over ranks
     double *d_local = nullptr;          // [K_ld] rowsum | [K_ld] elbo_w | [K_ld+1] scratch for the standalone ELBO
 };
@@ -396,12 +507,26 @@ void lda_free(tmvb_lda_t h)
     cudaSetDevice(h->s.device);
     if (h->s.stream) cudaStreamSynchronize(h->s.stream);
     cudaFree(h->d_alpha);
+    cudaFree(h->d_alpha64);
     cudaFree(h->d_Elogtheta);
     cudaFree(h->d_Elogtheta_old);
     cudaFree(h->d_gamma);
     cudaFree(h->d_small);
     cudaFree(h->d_local);
     shard_free(&h->s);
+}
+
+// bring the fp64 host copy of alpha up to date after a device-side update_alpha!
+int sync_alpha(tmvb_lda_t h)
+{
+    if (!h->alpha_on_device) return 0;
+    Shard &s = h->s;
+    TMVB_CUDA(cudaMemcpyAsync(s.h_pinned, h->d_alpha64, s.K * 8, cudaMemcpyDeviceToHost, s.stream));
+    TMVB_CUDA(cudaStreamSynchronize(s.stream));
+    memcpy(h->h_alpha.data(), s.h_pinned, s.K * 8);
+    s.st.d2h_bytes += s.K * 8;
+    h->alpha_on_device = false;
+    return 0;
 }
 
 double lg_alpha_term(const std::vector<double> &a)
@@ -433,6 +558,7 @@ int tmvb_lda_create(tmvb_lda_t *out, int64_t K, int64_t M, int64_t V, int device
             if (e == cudaSuccess) e = cudaMemsetAsync(*p, 0, bytes, s.stream);
         };
         A((void **)&h->d_alpha, s.K_ld * 4);
+        A((void **)&h->d_alpha64, s.K_ld * 8);
         A((void **)&h->d_Elogtheta, km * 4);
         A((void **)&h->d_Elogtheta_old, km * 4);
         A((void **)&h->d_gamma, km * 4);
@@ -449,6 +575,15 @@ int tmvb_lda_create(tmvb_lda_t *out, int64_t K, int64_t M, int64_t V, int device
         return rc;
     }
     h->h_alpha.assign(K, 1.0);
+    {  // alpha = ones(K) (gpuLDA.jl:55) on the device as well
+        std::vector<float> ones(K, 1.0f);
+        rc = tmvb_lda_set_alpha(h, ones.data());
+        if (rc != 0) {
+            lda_free(h);
+            delete h;
+            return rc;
+        }
+    }
     *out = h;
     return 0;
 }
@@ -486,8 +621,11 @@ int tmvb_lda_set_alpha(tmvb_lda_t h, const float *alpha)
     std::vector<float> pad(s.K_ld, 0.f);
     memcpy(pad.data(), alpha, s.K * 4);
     TMVB_CUDA(cudaMemcpyAsync(h->d_alpha, pad.data(), s.K_ld * 4, cudaMemcpyHostToDevice, s.stream));
+    TMVB_CUDA(cudaMemcpyAsync(h->d_alpha64, h->h_alpha.data(), s.K * 8, cudaMemcpyHostToDevice, s.stream));
     TMVB_CUDA(cudaStreamSynchronize(s.stream));
-    s.st.h2d_bytes += s.K * 4;
+    s.st.h2d_bytes += s.K * 12;
+    h->alpha_on_device = false;
+    h->elbo_dev_valid = false;
     return 0;
 }
 
@@ -536,7 +674,7 @@ int tmvb_lda_estep(tmvb_lda_t h, int viter, float vtol, int want_elbo)
     p.vtol = vtol;
     TMVB_CUDA(cudaEventRecord(s.ev[0], s.stream));
     TMVB_CUDA(cudaMemsetAsync(h->d_small, 0, (s.K_ld + 2) * 8, s.stream));
-    h->h_alpha_estep = h->h_alpha;
+    h->elbo_dev_valid = false;
     TMVB_TRY(shard_launch(&s, (const void *)kLdaEstep[s.layout][want_elbo != 0], &p));
     TMVB_CUDA(cudaEventRecord(s.ev[1], s.stream));
     s.estep_timed = true;
@@ -583,47 +721,19 @@ int tmvb_lda_update_alpha(tmvb_lda_t h, int64_t M_total, int niter, double ntol,
     TMVB_CHECK_ARG(h != nullptr, "handle is NULL");
     TMVB_CHECK_ARG(niter >= 0 && ntol >= 0.0, "iteration/tolerance parameters must be nonnegative");
     Shard &s = h->s;
-    const int K = (int)s.K;
-    std::vector<double> Esum(K), grad(K), hinv(K), pdir(K);
-    TMVB_TRY(tmvb_lda_get_elogtheta_sum(h, Esum.data()));
-    std::vector<double> &a = h->h_alpha;
-    // LDA.jl:97-118: interior-point Newton, log barrier nu halved every step
-    double nu = (double)K;
-    const double Md = (double)M_total;
-    for (int it = 0; it < niter; it++) {
-        double rho = 1.0, a0 = 0.0;
-        for (int i = 0; i < K; i++) a0 += a[i];
-        const double dg0 = h_digamma(a0);
-        double gh = 0.0, hs = 0.0, gn = 0.0;
-        for (int i = 0; i < K; i++) {
-            grad[i] = nu / a[i] + Md * (dg0 - h_digamma(a[i])) + Esum[i];
-            hinv[i] = -1.0 / (Md * h_trigamma(a[i]) + nu / (a[i] * a[i]));
-            gh += grad[i] * hinv[i];
-            hs += hinv[i];
-            gn += grad[i] * grad[i];
-        }
-        const double z = gh / (1.0 / (Md * h_trigamma(a0)) + hs);
-        for (int i = 0; i < K; i++) pdir[i] = (grad[i] - z) * hinv[i];
-        for (;;) {
-            double mn = INFINITY;
-            for (int i = 0; i < K; i++) mn = std::min(mn, a[i] - rho * pdir[i]);
-            if (!(mn < 0.0)) break;
-            rho *= 0.5;
-        }
-        for (int i = 0; i < K; i++) a[i] = copysign(std::min(fabs(a[i] - rho * pdir[i]), 1.7976931348623157e308), a[i]);
-        if ((rho * sqrt(gn) < ntol) && (nu / (double)K < ntol)) break;
-        nu *= 0.5;
+    TMVB_CUDA(cudaSetDevice(s.device));
+    // LDA.jl:97-118 on the device in fp64 (one warp), fused with the ELBO assembly; asynchronous unless alpha_out is given
+    double *result = h->d_local + 2 * s.K_ld + 1;
+    lda_alpha_kernel<<<1, 32, 0, s.stream>>>(h->d_alpha64, h->d_alpha, h->d_small, h->d_local, (int)s.K, s.K_ld, (double)M_total, niter, ntol,
+                                            h->elbo_valid ? 1 : 0, result);
+    TMVB_CUDA(cudaGetLastError());
+    s.st.kernel_launches++;
+    h->alpha_on_device = true;
+    h->elbo_dev_valid = h->elbo_valid;
+    if (alpha_out) {
+        TMVB_TRY(sync_alpha(h));
+        for (int64_t i = 0; i < s.K; i++) alpha_out[i] = std::max((float)h->h_alpha[i], 1.1754944e-38f);
     }
-    for (int i = 0; i < K; i++) a[i] += TMVB_EPS_D;
-    std::vector<float> pad(s.K_ld, 0.f);
-    for (int i = 0; i < K; i++) {
-        // keep the fp32 device copy strictly positive (the fp64 iterate can sit below FLT_MIN)
-        pad[i] = std::max((float)a[i], 1.1754944e-38f);
-        if (alpha_out) alpha_out[i] = pad[i];
-    }
-    TMVB_CUDA(cudaMemcpyAsync(h->d_alpha, pad.data(), s.K_ld * 4, cudaMemcpyHostToDevice, s.stream));
-    TMVB_CUDA(cudaStreamSynchronize(s.stream));
-    s.st.h2d_bytes += s.K * 4;
     return 0;
 }
 
@@ -635,21 +745,20 @@ int tmvb_lda_elbo(tmvb_lda_t h, int mode, int64_t M_total, double *elbo_docs, do
     TMVB_CUDA(cudaSetDevice(s.device));
     const int K = (int)s.K, K_ld = s.K_ld;
     if (mode == 0) {
-        TMVB_CHECK_ARG(h->elbo_valid, "mode 0 needs estep(want_elbo=1) followed by mstep");
-        TMVB_CUDA(cudaMemcpyAsync(s.h_pinned, h->d_small, (K_ld + 2) * 8, cudaMemcpyDeviceToHost, s.stream));
-        TMVB_CUDA(cudaMemcpyAsync(s.h_pinned + K_ld + 2, h->d_local + K_ld, 8, cudaMemcpyDeviceToHost, s.stream));
+        TMVB_CHECK_ARG(h->elbo_valid && h->elbo_dev_valid, "mode 0 needs estep(want_elbo=1), mstep, update_alpha in this order");
+        // assembled by lda_alpha_kernel:  docs + M (lnG(sum alpha) - sum lnG(alpha))                      [Elogptheta, LDA.jl:51]
+        //   + sum_i (alpha_i - alpha_estep_i - eps) Esum_i   [dot(alpha .- 1, Elogtheta) plus the (1 - alpha_estep) . Esum left over
+        //                                                     from the per-document entropy/Elogpz terms, see lda_estep_kernel]
+        //   + sum_ij S_ij ln(beta_ij + eps)                                                              [Elogpw over the statistics]
+        TMVB_CUDA(cudaMemcpyAsync(s.h_pinned, h->d_local + 2 * K_ld + 1, 8, cudaMemcpyDeviceToHost, s.stream));
         TMVB_CUDA(cudaStreamSynchronize(s.stream));
-        s.st.d2h_bytes += (K_ld + 3) * 8;
-        const double *Esum = s.h_pinned;
-        double g = (double)M_total * lg_alpha_term(h->h_alpha);  // Elogptheta, LDA.jl:51
-        // dot(alpha .- 1, Elogtheta[d]) summed over d, plus the (1 - alpha_estep) . Elogtheta_sum left
-        // over from the per-document entropy/Elogpz terms (see lda_estep_kernel)
-        for (int i = 0; i < K; i++) g += (h->h_alpha[i] - h->h_alpha_estep[i] - TMVB_EPS_D) * Esum[i];
-        g += s.h_pinned[K_ld + 2];  // Elogpw over the statistics
-        *elbo_docs = s.h_pinned[K_ld];
-        *elbo_global = g;
+        s.st.d2h_bytes += 8;
+        *elbo_docs = s.h_pinned[0];
+        *elbo_global = 0.0;
+        (void)K;
         return 0;
     }
+    TMVB_TRY(sync_alpha(h));
     TMVB_CHECK_ARG(s.corpus_set, "set_corpus has not been called");
     LdaDev p = dev_view(h);
     double *out = h->d_local + 2 * K_ld;
@@ -676,7 +785,7 @@ int tmvb_lda_download(tmvb_lda_t h, float *alpha, float *beta, float *Elogtheta,
     Shard &s = h->s;
     TMVB_CUDA(cudaSetDevice(s.device));
     if (alpha) {
-        TMVB_CUDA(cudaStreamSynchronize(s.stream));
+        TMVB_TRY(sync_alpha(h));
         for (int64_t i = 0; i < s.K; i++) alpha[i] = std::max((float)h->h_alpha[i], 1.1754944e-38f);
     }
     TMVB_TRY(shard_download_rows(&s, s.d_beta[s.cur], beta, s.V, nullptr));

@@ -180,8 +180,9 @@ class gpuLDA:
         _lib.check(_lib.load().tmvb_lda_mstep(self._handle()))
 
     def update_alpha(self, niter: int, ntol: float):
-        """update_alpha!(model::gpuLDA, niter, ntol) (gpuLDA.jl:132-154), fp64 on the host inside the library."""
-        _lib.check(_lib.load().tmvb_lda_update_alpha(self._handle(), self.M_total, int(niter), float(ntol), _lib.ptr(self.alpha)))
+        """update_alpha!(model::gpuLDA, niter, ntol) (gpuLDA.jl:132-154), fp64 as in LDA.jl:97-118."""
+        # asynchronous: the Newton iteration runs in an fp64 device kernel; model.alpha is refreshed by update_host!
+        _lib.check(_lib.load().tmvb_lda_update_alpha(self._handle(), self.M_total, int(niter), float(ntol), None))
 
     def update_elbo(self, mode: int = 0) -> float:
         """update_elbo!(model) (gpuLDA.jl:121-128) from device-side partials; no phi transfer."""
