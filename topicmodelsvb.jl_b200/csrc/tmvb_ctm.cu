@@ -217,6 +217,8 @@ __global__ void __launch_bounds__(32) ctm_estep_kernel(const CtmDev p, int doc_b
         ta.K_ld = K_ld;
         ta.RS = RS;
         ta.dbg = p.dbg;
+        ta.r0 = 0;
+        ta.rstep = 1;
 
         float4 e[CPL];
         float logzeta = 0.0f;
@@ -756,7 +758,8 @@ int tmvb_ctm_estep(tmvb_ctm_t h, int niter, float ntol, int viter, float vtol, i
     p.vtol = vtol;
     TMVB_CUDA(cudaEventRecord(s.ev[0], s.stream));
     TMVB_CUDA(cudaMemsetAsync(h->d_small, 0, h->n_small * 8, s.stream));
-    TMVB_TRY(shard_launch(&s, (const void *)ctm_fn(s.layout, want_elbo != 0), &p));
+    const void *fns[2] = {(const void *)ctm_fn(s.layout, want_elbo != 0), (const void *)ctm_fn(s.layout, want_elbo != 0)};
+    TMVB_TRY(shard_launch(&s, fns, &p));
     if (s.M > 0) {
         const int grid = (int)std::min<int64_t>((s.M + 31) / 32, (int64_t)s.n_sm * 4);
         ctm_moments_kernel<<<grid, 256, 32 * s.K_ld * 4, s.stream>>>(h->d_lambda, h->d_vsq, s.M, (int)s.K, s.K_ld, h->d_small + 2);

@@ -168,6 +168,8 @@ __global__ void __launch_bounds__(32) ctpf_estep_kernel(const CtpfDev p, int doc
         ta.K_ld = K_ld;
         ta.RS = RS;
         ta.dbg = p.dbg;
+        ta.r0 = 0;
+        ta.rstep = 1;
         tb = ta;
         tb.tile = tile2;
         tb.cnt_s = cnt2_s;
@@ -776,7 +778,8 @@ int tmvb_ctpf_estep(tmvb_ctpf_t h, int viter, float vtol, int want_elbo)
     p.vtol = vtol;
     TMVB_CUDA(cudaEventRecord(s.ev[0], s.stream));
     TMVB_CUDA(cudaMemsetAsync(h->d_small, 0, (2 * s.K_ld + 2) * 8, s.stream));
-    TMVB_TRY(shard_launch(&s, (const void *)kCtpfEstep[s.layout][want_elbo != 0], &p));
+    const void *fns[2] = {(const void *)kCtpfEstep[s.layout][want_elbo != 0], (const void *)kCtpfEstep[s.layout][want_elbo != 0]};
+    TMVB_TRY(shard_launch(&s, fns, &p));
     TMVB_CUDA(cudaEventRecord(s.ev[1], s.stream));
     s.estep_timed = true;
     h->elbo_valid = (want_elbo != 0);

@@ -52,18 +52,19 @@ struct TokArgs {
     const float *gcounts;  // global: this document's counts
     float *stats;          // global: [rows][K_ld] scatter target (final pass)
     int Nd, cap, rounds, K, K_ld, RS, dbg;
+    int r0, rstep;         // this warp takes rounds r0, r0 + rstep, ... (rstep = warps cooperating on the document)
 };
 
 // Sweep pass: s_n, t_n = c_n / s_n, g += T t.  EPS selects the reference's "@positive" epsilon (LDA) or none.
-template <int LPT, int CPL, bool OVF, bool EPS>
+template <int LPT, int CPL, bool OVF, bool EPS, int UNR = kSweepUnroll>
 __device__ __forceinline__ void tok_sweep(const TokArgs &a, int ts, int kl, const float4 (&e)[CPL], float4 (&g)[CPL], float &tsum)
 {
     constexpr int S = 32 / LPT;
     const int CH = a.K_ld >> 2;
     const float Keps = EPS ? (float)a.K * TMVB_EPS : 0.0f;
     const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll kSweepUnroll
-    for (int r = 0; r < a.rounds; r++) {
+#pragma unroll UNR
+    for (int r = a.r0; r < a.rounds; r += a.rstep) {
         const int n = r * S + ts;
         const bool ok = n < a.Nd;
         float4 b[CPL];
@@ -112,7 +113,7 @@ __device__ __forceinline__ void tok_final(const TokArgs &a, int ts, int kl, cons
     const float Keps = EPS ? (float)a.K * TMVB_EPS : 0.0f;
     const float eps = EPS ? TMVB_EPS : 0.0f;
     const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int r = 0; r < a.rounds; r++) {
+    for (int r = a.r0; r < a.rounds; r += a.rstep) {
         const int n = r * S + ts;
         const bool ok = n < a.Nd;
         float4 b[CPL];
@@ -175,7 +176,7 @@ __device__ __forceinline__ void tok_final2(const TokArgs &a, int ts, int kl, con
     constexpr int S = 32 / LPT;
     const int CH = a.K_ld >> 2;
     const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int r = 0; r < a.rounds; r++) {
+    for (int r = a.r0; r < a.rounds; r += a.rstep) {
         const int n = r * S + ts;
         const bool ok = n < a.Nd;
         float4 b[CPL];

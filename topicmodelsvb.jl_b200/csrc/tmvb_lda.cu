@@ -40,55 +40,78 @@ struct LdaDev {
     int dbg;         // developer probes: bit0 skip the scatter, bit1 skip the final pass
 };
 
-// shared memory of one E-step CTA (= one warp) beyond the tile: mbarrier | gs [S][RS] | e_s [RS]
-static size_t lda_fixed_smem(int RS, int lpt) { return 16 + (size_t)(32 / lpt) * RS * 4 + (size_t)RS * 4; }
+// shared memory of one E-step CTA beyond the tile: header (mbarrier, next-document slot, per-warp partial sums) |
+// gs [W][S][RS] | e_s [RS]
+static size_t lda_fixed_smem(int RS, int lpt, int W) { return 128 + (size_t)W * (32 / lpt) * RS * 4 + (size_t)RS * 4; }
 
-template <int LPT, int CPL, bool ELBO>
-__global__ void __launch_bounds__(32) lda_estep_kernel(const LdaDev p, int doc_begin, int doc_end, int cap, int cap2, int *counter)
+template <int W>
+__device__ __forceinline__ void cta_sync()
 {
-    constexpr int S = 32 / LPT;                   // token streams per warp
-    constexpr int R = (LPT * CPL + 7) / 8;        // K-phase topics per lane (>= ceil(K_ld / 32))
+    if (W == 1)
+        __syncwarp();
+    else
+        __syncthreads();
+}
+
+// W warps cooperate on one document (W = 1 for short documents, 2 for the rest): they share the staged tile, split the
+// token rounds (warp w takes rounds w, w+W, ...) and split the topics of the K phase (thread t owns topics t + 32W r).
+// Two CTA barriers per sweep: after the per-stream partial K-vectors are in shared memory, and after exp(Elogtheta) and
+// the partial convergence sums are.
+template <int LPT, int CPL, int W, bool ELBO>
+__global__ void __launch_bounds__(32 * W, W == 2 ? 8 : 1) lda_estep_kernel(const LdaDev p, int doc_begin, int doc_end, int cap, int cap2, int *counter)
+{
+    constexpr int S = 32 / LPT;                             // token streams per warp
+    constexpr int T = 32 * W;                               // threads per document
+    constexpr int R = (4 * LPT * CPL + T - 1) / T;          // K-phase topics per thread
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int lane = threadIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int kl = lane % LPT, ts = lane / LPT;
     const int K = p.K, K_ld = p.K_ld, CH = K_ld >> 2, RS = p.RS;
     const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
     (void)cap2;
 
     unsigned long long *mbar = reinterpret_cast<unsigned long long *>(smem_raw);
-    float *gs = reinterpret_cast<float *>(smem_raw + 16);      // [S][RS]
-    float *e_s = gs + (size_t)S * RS;                          // [RS]
-    float *tile = e_s + RS;                                    // [cap][RS]
-    float *cnt_s = tile + (size_t)cap * RS;                    // [cap]
-    int *term_s = reinterpret_cast<int *>(cnt_s + cap);        // [cap]
+    int *next_s = reinterpret_cast<int *>(smem_raw + 16);
+    float *csum_s = reinterpret_cast<float *>(smem_raw + 32);        // [W]
+    float *tsum_s = reinterpret_cast<float *>(smem_raw + 48);        // [W]
+    unsigned *dsum_s = reinterpret_cast<unsigned *>(smem_raw + 64);  // [2][W]
+    float *gs = reinterpret_cast<float *>(smem_raw + 128);           // [W][S][RS]
+    float *e_s = gs + (size_t)W * S * RS;                            // [RS]
+    float *tile = e_s + RS;                                          // [cap][RS]
+    float *cnt_s = tile + (size_t)cap * RS;                          // [cap]
+    int *term_s = reinterpret_cast<int *>(cnt_s + cap);              // [cap]
 
-    // K-phase state: topics i = lane + 32 r
+    // K-phase state: topics i = tid + T r
     float alpha_k[R], Eold_k[R], Enew_k[R], e_k[R], gam_k[R];
     double esum_k[R];
     float asum = 0.0f;
+    for (int i = lane; i < K; i += 32) asum += p.alpha[i];
+    asum = warp_sum(asum);
 #pragma unroll
     for (int r = 0; r < R; r++) {
-        const int i = lane + 32 * r;
+        const int i = tid + T * r;
         alpha_k[r] = (i < K) ? p.alpha[i] : 0.0f;
-        asum += alpha_k[r];
         esum_k[r] = 0.0;
         Enew_k[r] = gam_k[r] = Eold_k[r] = e_k[r] = 0.0f;
     }
-    asum = warp_sum(asum);
-    // convergence test in fixed point: sum_i (dE_i)^2 * (2^20 / vtol^2) < 2^20, summed with one REDUX
+    // convergence test in fixed point: sum_i (dE_i)^2 * (2^20 / vtol^2) < 2^20, summed with one REDUX per warp
     const float dscale = (p.vtol > 0.0f) ? 1048576.0f / (p.vtol * p.vtol) : 0.0f;
     double elbo_thr = 0.0;
     unsigned long long sweeps_thr = 0;
     unsigned phase = 0;
-    if (p.stage_bulk) {
-        if (lane == 0) mbar_init(mbar, 1);
-        __syncwarp();
-    }
+    if (p.stage_bulk && tid == 0) mbar_init(mbar, 1);
+    cta_sync<W>();
 
     for (;;) {
         int d = 0;
-        if (lane == 0) d = doc_begin + atomicAdd(counter, 1);
-        d = __shfl_sync(0xffffffffu, d, 0);
+        if (W == 1) {
+            if (lane == 0) d = doc_begin + atomicAdd(counter, 1);
+            d = __shfl_sync(0xffffffffu, d, 0);
+        } else {
+            if (tid == 0) *next_s = doc_begin + atomicAdd(counter, 1);
+            __syncthreads();
+            d = *next_s;
+        }
         if (d >= doc_end) break;
         const long long o = p.doc_off[d];
         const int Nd = (int)(p.doc_off[d + 1] - o);
@@ -97,9 +120,8 @@ __global__ void __launch_bounds__(32) lda_estep_kernel(const LdaDev p, int doc_b
 
         // stage the document: term ids + counts, then its K x N_d slab of beta -- one TMA bulk copy per term row
         // (a row is K_ld*4 contiguous bytes in HBM/L2), completion tracked by an mbarrier
-        __syncwarp();
         float csum = 0.0f;
-        for (int n = lane; n < Nd; n += 32) {
+        for (int n = tid; n < Nd; n += T) {
             const float c = p.counts[o + n];
             csum += c;
             if (n < ns) {
@@ -107,19 +129,45 @@ __global__ void __launch_bounds__(32) lda_estep_kernel(const LdaDev p, int doc_b
                 cnt_s[n] = c;
             }
         }
-        stage_rows(tile, term_s, p.beta, ns, K_ld, RS, lane, mbar, p.stage_bulk);
+        csum = warp_sum(csum);
+        if (W > 1 && lane == 0) csum_s[warp] = csum;
+        if (p.stage_bulk) {
+            fence_proxy_async_smem();
+            cta_sync<W>();
+            if (tid == 0) mbar_arrive_expect_tx(mbar, (unsigned)(ns * K_ld * 4));
+            cta_sync<W>();
+            for (int n = tid; n < ns; n += T) bulk_g2s(tile + n * RS, p.beta + (size_t)term_s[n] * K_ld, (unsigned)(K_ld * 4), mbar);
+        } else {
+            cta_sync<W>();
+            for (int c = tid; c < ns * CH; c += T) {
+                const int n = c / CH, q = c - n * CH;
+                cp_async16(tile + n * RS + 4 * q, p.beta + (size_t)term_s[n] * K_ld + 4 * q);
+            }
+            cp_async_commit();
+        }
 #pragma unroll
         for (int r = 0; r < R; r++) {
-            const int i = lane + 32 * r;
+            const int i = tid + T * r;
             Eold_k[r] = (i < K) ? p.Elogtheta[(size_t)d * K_ld + i] : 0.0f;
             e_k[r] = (i < K) ? expf(Eold_k[r]) : 0.0f;
             if (i < K_ld) e_s[i] = e_k[r];
         }
+        if (W > 1) {
+            csum = 0.0f;
+#pragma unroll
+            for (int w = 0; w < W; w++) csum += csum_s[w];
+        }
         // sum(gamma_d) = sum(alpha) + sum_n c_n + K*EPS whatever phi is (each phi column sums to one), so
         // digamma(sum gamma) (LDA.jl:138) is a per-document constant
-        const float gsum = (asum + warp_sum(csum)) + (float)K * TMVB_EPS;
+        const float gsum = (asum + csum) + (float)K * TMVB_EPS;
         const float psi_sum = psi_lgamma<false>(gsum).psi;
-        stage_wait(mbar, phase, p.stage_bulk);
+        if (p.stage_bulk) {
+            mbar_wait(mbar, phase);
+            phase ^= 1u;
+        } else {
+            cp_async_wait_all();
+        }
+        cta_sync<W>();
 
         TokArgs ta;
         ta.tile = tile;
@@ -136,6 +184,8 @@ __global__ void __launch_bounds__(32) lda_estep_kernel(const LdaDev p, int doc_b
         ta.K_ld = K_ld;
         ta.RS = RS;
         ta.dbg = p.dbg;
+        ta.r0 = warp;
+        ta.rstep = W;
 
         float4 e[CPL];
         int v = 0;
@@ -149,42 +199,73 @@ __global__ void __launch_bounds__(32) lda_estep_kernel(const LdaDev p, int doc_b
 #pragma unroll
             for (int m = 0; m < CPL; m++) g[m] = zero4;
             if (!ovf)
-                tok_sweep<LPT, CPL, false, true>(ta, ts, kl, e, g, tsum);
+                tok_sweep<LPT, CPL, false, true, (W == 2 ? 1 : kSweepUnroll)>(ta, ts, kl, e, g, tsum);
             else
-                tok_sweep<LPT, CPL, true, true>(ta, ts, kl, e, g, tsum);
+                tok_sweep<LPT, CPL, true, true, (W == 2 ? 1 : kSweepUnroll)>(ta, ts, kl, e, g, tsum);
 #pragma unroll
             for (int m = 0; m < CPL; m++)
-                if (m < CPL - 1 || kl + LPT * m < CH) reinterpret_cast<float4 *>(gs + ts * RS)[kl + LPT * m] = g[m];
-            const float tt = across_streams_sum<LPT>(tsum);
-            __syncwarp();
+                if (m < CPL - 1 || kl + LPT * m < CH) reinterpret_cast<float4 *>(gs + (warp * S + ts) * RS)[kl + LPT * m] = g[m];
+            float tt = across_streams_sum<LPT>(tsum);
+            if (W > 1 && lane == 0) tsum_s[warp] = tt;
+            cta_sync<W>();  // also orders this sweep's reads of e_s before the K phase overwrites it
+            if (W > 1) {
+                tt = 0.0f;
+#pragma unroll
+                for (int w = 0; w < W; w++) tt += tsum_s[w];
+            }
 
             // ---- K phase: update_gamma! (LDA.jl:143-146), update_Elogtheta! (LDA.jl:136-139)
             float dpart = 0.0f;
+            float e_new[R];
 #pragma unroll
             for (int r = 0; r < R; r++) {
-                const int i = lane + 32 * r;
-                const float gi = (i < K) ? owner_sum<S>(gs, RS, i) : 0.0f;
+                const int i = tid + T * r;
+                const float gi = (i < K) ? owner_sum<W * S>(gs, RS, i) : 0.0f;
                 // gamma = EPS + (alpha + phi*counts),   phi*counts = e .* g + eps * sum_n t_n
                 gam_k[r] = (i < K) ? (alpha_k[r] + fmaf(e_k[r], gi, TMVB_EPS * tt)) + TMVB_EPS : 1.0f;
                 Enew_k[r] = psi_lgamma<false, true>(gam_k[r]).psi - psi_sum;
+                e_new[r] = 0.0f;
                 if (i < K) {
                     const float df = Enew_k[r] - Eold_k[r];
                     dpart = fmaf(df, df, dpart);
+                    e_new[r] = fast_exp(Enew_k[r]);
                 }
             }
             v++;
             // LDA.jl:175: stop when ||Elogtheta - Elogtheta_old||_2 < vtol (or after viter sweeps)
             if (v >= p.viter) break;
-            // per-lane clamp 2^26 keeps the 32-lane integer sum below 2^31
-            if (dscale > 0.0f && __reduce_add_sync(0xffffffffu, (unsigned)fminf(dpart * dscale, 67108864.0f)) < 1048576u) break;
+            // per-lane clamp 2^25 keeps the integer sum over up to 64 threads below 2^31
+            unsigned dtot = (dscale > 0.0f) ? __reduce_add_sync(0xffffffffu, (unsigned)fminf(dpart * dscale, 33554432.0f)) : 0xffffffffu;
+            if (W > 1) {
+                // tentatively publish exp(Elogtheta_new): the token phase keeps e in registers, so overwriting e_s is
+                // harmless even if the document turns out to have converged
 #pragma unroll
-            for (int r = 0; r < R; r++) {
-                const int i = lane + 32 * r;
-                Eold_k[r] = Enew_k[r];
-                e_k[r] = (i < K) ? fast_exp(Enew_k[r]) : 0.0f;
-                if (i < K_ld) e_s[i] = e_k[r];
+                for (int r = 0; r < R; r++)
+                    if (tid + T * r < K_ld) e_s[tid + T * r] = e_new[r];
+                if (lane == 0) dsum_s[(v & 1) * W + warp] = dtot;
+                __syncthreads();
+                dtot = 0;
+#pragma unroll
+                for (int w = 0; w < W; w++) {
+                    const unsigned x = dsum_s[(v & 1) * W + w];
+                    dtot = (x > 0x7fffffffu - dtot) ? 0x7fffffffu : dtot + x;
+                }
+                if (dscale > 0.0f && dtot < 1048576u) break;
+#pragma unroll
+                for (int r = 0; r < R; r++) {
+                    Eold_k[r] = Enew_k[r];
+                    e_k[r] = e_new[r];
+                }
+            } else {
+                if (dscale > 0.0f && dtot < 1048576u) break;
+#pragma unroll
+                for (int r = 0; r < R; r++) {
+                    Eold_k[r] = Enew_k[r];
+                    e_k[r] = e_new[r];
+                    if (tid + T * r < K_ld) e_s[tid + T * r] = e_new[r];
+                }
+                __syncwarp();
             }
-            __syncwarp();
         }
 
         // update_beta!(model, d) (LDA.jl:129-132): scatter the last phi, weighted by counts
@@ -200,7 +281,7 @@ __global__ void __launch_bounds__(32) lda_estep_kernel(const LdaDev p, int doc_b
         float a = 0.0f;
 #pragma unroll
         for (int r = 0; r < R; r++) {
-            const int i = lane + 32 * r;
+            const int i = tid + T * r;
             if (i < K_ld) {
                 const bool ok = i < K;
                 p.gamma[(size_t)d * K_ld + i] = ok ? gam_k[r] : 0.0f;
@@ -215,25 +296,26 @@ __global__ void __launch_bounds__(32) lda_estep_kernel(const LdaDev p, int doc_b
         // Dirichlet entropy (utils.jl:163-180) + Elogpz (LDA.jl:57-60): with gamma = alpha + phi*c and
         // psi(gamma_i) = Elogtheta_i + psi(sum gamma) they collapse to
         //   sum_i lnG(gamma_i) - lnG(sum gamma) + sum_i (1 - alpha_i) Elogtheta_i ;
-        // the last sum is linear in sum_d Elogtheta_d and is added on the host in fp64.
+        // the last sum is linear in sum_d Elogtheta_d and is added by lda_alpha_kernel in fp64.
         if (ELBO) {
-            if (lane == 0) a -= psi_lgamma<true>(gsum).lg;
+            if (tid == 0) a -= psi_lgamma<true>(gsum).lg;
             elbo_thr += (double)a;
         }
-        if (lane == 0) sweeps_thr += (unsigned long long)v;
+        if (tid == 0) sweeps_thr += (unsigned long long)v;
+        cta_sync<W>();  // the tile, e_s and gs are free for the next document
     }
 
-    // flush the warp's accumulators
+    // flush the accumulators
     if (ELBO) {
         const double tot = warp_sum_d(elbo_thr);
         if (lane == 0 && tot != 0.0) atomicAdd(p.small + K_ld, tot);
     }
 #pragma unroll
     for (int r = 0; r < R; r++) {
-        const int i = lane + 32 * r;
+        const int i = tid + T * r;
         if (i < K && esum_k[r] != 0.0) atomicAdd(p.small + i, esum_k[r]);
     }
-    if (lane == 0 && sweeps_thr) atomicAdd(p.small + K_ld + 1, (double)sweeps_thr);
+    if (tid == 0 && sweeps_thr) atomicAdd(p.small + K_ld + 1, (double)sweeps_thr);
 }
 
 // ------------------------------------------------------------------ standalone ELBO ---------
@@ -455,8 +537,10 @@ __global__ void lda_phi_kernel(const LdaDev p, const float *__restrict__ beta_ol
 }
 
 typedef void (*LdaEstepFn)(const LdaDev, int, int, int, int, int *);
-#define TMVB_LDA_FN(L, C) {(LdaEstepFn)lda_estep_kernel<L, C, false>, (LdaEstepFn)lda_estep_kernel<L, C, true>},
-static const LdaEstepFn kLdaEstep[kNumLaneLayouts][2] = {TMVB_FOR_EACH_LAYOUT(TMVB_LDA_FN)};
+#define TMVB_LDA_FN1(L, C) {(LdaEstepFn)lda_estep_kernel<L, C, 1, false>, (LdaEstepFn)lda_estep_kernel<L, C, 1, true>},
+#define TMVB_LDA_FN2(L, C) {(LdaEstepFn)lda_estep_kernel<L, C, 2, false>, (LdaEstepFn)lda_estep_kernel<L, C, 2, true>},
+// [warps per document - 1][lane layout][want_elbo]
+static const LdaEstepFn kLdaEstep[2][kNumLaneLayouts][2] = {{TMVB_FOR_EACH_LAYOUT(TMVB_LDA_FN1)}, {TMVB_FOR_EACH_LAYOUT(TMVB_LDA_FN2)}};
 
 }  // namespace tmvb
 
@@ -565,8 +649,9 @@ int tmvb_lda_create(tmvb_lda_t *out, int64_t K, int64_t M, int64_t V, int device
         A((void **)&h->d_small, (s.K_ld + 2) * 8);
         A((void **)&h->d_local, (3 * s.K_ld + 2) * 8);
         // opt in to the large dynamic shared memory for both instantiations of this K
-        for (int eb = 0; eb < 2 && e == cudaSuccess; eb++)
-            e = cudaFuncSetAttribute((const void *)kLdaEstep[s.layout][eb], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s.smem_optin);
+        for (int w = 0; w < 2; w++)
+            for (int eb = 0; eb < 2 && e == cudaSuccess; eb++)
+                e = cudaFuncSetAttribute((const void *)kLdaEstep[w][s.layout][eb], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s.smem_optin);
         if (e != cudaSuccess) rc = fail((int)e, "device allocation failed: %s", cudaGetErrorString(e));
     }
     if (rc != 0) {
@@ -606,7 +691,17 @@ int tmvb_lda_kld(tmvb_lda_t h, int64_t *K_ld)
 int tmvb_lda_set_corpus(tmvb_lda_t h, const int64_t *N_cumsum, const int64_t *terms, const int64_t *counts)
 {
     TMVB_CHECK_ARG(h != nullptr, "handle is NULL");
-    return shard_set_corpus(&h->s, N_cumsum, terms, counts, lda_fixed_smem(h->s.RS, h->s.lpt));
+    Shard &s = h->s;
+    // buckets are planned with the two-warp working set; launches for short documents use one warp per document
+    TMVB_TRY(shard_set_corpus(&s, N_cumsum, terms, counts, lda_fixed_smem(s.RS, s.lpt, 2)));
+    const int force_w = env_int("TMVB_LDA_WARPS", 0);
+    const size_t per_tok = (size_t)s.RS * 4 + 8;
+    for (Bucket &b : s.buckets) {
+        b.warps = force_w ? std::min(2, std::max(1, force_w)) : (b.cap >= 48 ? 2 : 1);
+        b.smem = lda_fixed_smem(s.RS, s.lpt, b.warps) + (size_t)b.cap * per_tok;
+        b.grid = 0;
+    }
+    return 0;
 }
 
 int tmvb_lda_set_alpha(tmvb_lda_t h, const float *alpha)
@@ -675,7 +770,8 @@ int tmvb_lda_estep(tmvb_lda_t h, int viter, float vtol, int want_elbo)
     TMVB_CUDA(cudaEventRecord(s.ev[0], s.stream));
     TMVB_CUDA(cudaMemsetAsync(h->d_small, 0, (s.K_ld + 2) * 8, s.stream));
     h->elbo_dev_valid = false;
-    TMVB_TRY(shard_launch(&s, (const void *)kLdaEstep[s.layout][want_elbo != 0], &p));
+    const void *fns[2] = {(const void *)kLdaEstep[0][s.layout][want_elbo != 0], (const void *)kLdaEstep[1][s.layout][want_elbo != 0]};
+    TMVB_TRY(shard_launch(&s, fns, &p));
     TMVB_CUDA(cudaEventRecord(s.ev[1], s.stream));
     s.estep_timed = true;
     h->elbo_valid = (want_elbo != 0);

@@ -275,6 +275,7 @@ static int plan_buckets(Shard *s, size_t fixed_bytes)
         b.cap = std::min(caps[ci], std::max(16, (len_sorted[begin] + 15) / 16 * 16));
         if (b.cap > cap_max) b.cap = cap_max;
         b.cap2 = 0;
+        b.warps = 1;
         b.smem = fixed_bytes + (size_t)b.cap * per_tok;
         b.grid = 0;
         s->buckets.push_back(b);
@@ -405,7 +406,7 @@ int shard_download_rows(Shard *s, const float *d_src, float *host, int64_t rows,
     return 0;
 }
 
-int shard_launch(Shard *s, const void *fn, void *dev_struct)
+int shard_launch(Shard *s, const void *const *fn_by_warps, void *dev_struct)
 {
     TMVB_CUDA(cudaMemsetAsync(s->d_counters, 0, kMaxBuckets * 4, s->stream));
     const int ns = (s->buckets.size() > 1) ? s->n_streams : 1;
@@ -415,16 +416,18 @@ int shard_launch(Shard *s, const void *fn, void *dev_struct)
     }
     for (size_t bi = 0; bi < s->buckets.size(); bi++) {
         Bucket &b = s->buckets[bi];
+        const void *fn = fn_by_warps[b.warps - 1];
+        const int threads = 32 * b.warps;
         if (b.grid == 0) {
             int occ = 0;
-            TMVB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, 32, b.smem));
-            if (occ < 1) return fail(-4, "internal: E-step kernel does not fit (cap=%d smem=%zu)", b.cap, b.smem);
+            TMVB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, threads, b.smem));
+            if (occ < 1) return fail(-4, "internal: E-step kernel does not fit (cap=%d warps=%d smem=%zu)", b.cap, b.warps, b.smem);
             b.grid = std::min(b.doc_end - b.doc_begin, occ * s->n_sm);
         }
         int *counter = s->d_counters + bi;
         void *args[] = {dev_struct, (void *)&b.doc_begin, (void *)&b.doc_end, (void *)&b.cap, (void *)&b.cap2, (void *)&counter};
         cudaStream_t st = (bi % ns == 0) ? s->stream : s->aux[bi % ns - 1];
-        TMVB_CUDA(cudaLaunchKernel(fn, dim3(b.grid), dim3(32), args, b.smem, st));
+        TMVB_CUDA(cudaLaunchKernel(fn, dim3(b.grid), dim3(threads), args, b.smem, st));
         s->st.kernel_launches++;
     }
     for (int a = 0; a + 1 < ns; a++) {

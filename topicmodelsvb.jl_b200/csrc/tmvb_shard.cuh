@@ -11,6 +11,7 @@ namespace tmvb {
 struct Bucket {
     int doc_begin, doc_end, cap, grid;
     int cap2;  // second tile capacity (CTPF reader lists); 0 otherwise
+    int warps; // warps cooperating on one document in this launch (CTA = 32 * warps threads)
     size_t smem;
 };
 
@@ -67,8 +68,9 @@ int shard_upload_rows(Shard *s, const float *host, float *d_dst, int64_t rows, c
 int shard_download_rows(Shard *s, const float *d_src, float *host, int64_t rows, const int *d_perm);
 // returns and clears the validation bit mask accumulated by shard_upload_rows (2 bits per `validate` code)
 int shard_validation(Shard *s, int *mask);
-// launch an E-step kernel `fn(Dev, doc_begin, doc_end, cap, cap2, counter)` over every bucket
-int shard_launch(Shard *s, const void *fn, void *dev_struct);
+// launch an E-step kernel `fn(Dev, doc_begin, doc_end, cap, cap2, counter)` over every bucket; fn_by_warps[w-1] is the
+// instantiation for w warps per document (Bucket::warps)
+int shard_launch(Shard *s, const void *const *fn_by_warps, void *dev_struct);
 // beta_new = stats ./ rowsum ; stats <- 0 ; [elbo_w = sum stats ln(beta_new + eps)].  d_acc: double[2*K_ld] (rowsum | elbo_w)
 int shard_normalize(Shard *s, double *d_acc, bool want_elbo, float prior);
 int shard_topics(Shard *s, const float *d_mat, const float *d_scale, int32_t *out);
