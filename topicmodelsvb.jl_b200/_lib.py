@@ -123,10 +123,11 @@ def load():
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(SO_PATH):
+    so = os.environ.get("TMVB_SO") or SO_PATH   # TMVB_SO: developer A/B runs against another build of the same ABI
+    if not os.path.exists(so):
         raise TopicModelError("libtmvb.so is not built (run `python -c 'import __graft_entry__ as g; g.build()'`); "
                               "there is no CPU fallback")
-    lib = C.CDLL(SO_PATH)
+    lib = C.CDLL(so)
     for name, (res, args) in SIGNATURES.items():
         fn = getattr(lib, name)
         fn.restype = res

@@ -99,7 +99,7 @@ __device__ __forceinline__ PsiLg psi_lgamma(float x)
         y = x + 6.0f;
     }
     float ly = FAST ? __logf(y) : logf(y);
-    float t = __frcp_rn(y), t2 = t * t;
+    float t = FAST ? __fdividef(1.0f, y) : __frcp_rn(y), t2 = t * t;  // FAST: MUFU.RCP (1 ulp) instead of the IEEE sequence
     PsiLg r;
     float ser = t2 * (8.3333333333e-2f - t2 * (8.3333333333e-3f - t2 * 3.9682539683e-3f));
     r.psi = ly - 0.5f * t - ser;
@@ -111,6 +111,40 @@ __device__ __forceinline__ PsiLg psi_lgamma(float x)
         if (x < 6.0f) r.lg -= logf(P);
     }
     return r;
+}
+
+// ---- packed fp32 pairs (sm_100 FFMA2 / FADD2 / FMUL2: two lanes of fp32 per 64-bit register pair) ----
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pk2(float lo, float hi)
+{
+    f32x2 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void unpk2(f32x2 v, float &lo, float &hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c)
+{
+    f32x2 d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b)
+{
+    f32x2 d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b)
+{
+    f32x2 d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ float hsum2(f32x2 v)
+{
+    float lo, hi;
+    unpk2(v, lo, hi);
+    return lo + hi;
 }
 
 __device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src)

@@ -759,7 +759,7 @@ int tmvb_ctm_estep(tmvb_ctm_t h, int niter, float ntol, int viter, float vtol, i
     TMVB_CUDA(cudaEventRecord(s.ev[0], s.stream));
     TMVB_CUDA(cudaMemsetAsync(h->d_small, 0, h->n_small * 8, s.stream));
     const void *fns[2] = {(const void *)ctm_fn(s.layout, want_elbo != 0), (const void *)ctm_fn(s.layout, want_elbo != 0)};
-    TMVB_TRY(shard_launch(&s, fns, &p));
+    TMVB_TRY(shard_launch(&s, pick_by_warps, fns, &p));
     if (s.M > 0) {
         const int grid = (int)std::min<int64_t>((s.M + 31) / 32, (int64_t)s.n_sm * 4);
         ctm_moments_kernel<<<grid, 256, 32 * s.K_ld * 4, s.stream>>>(h->d_lambda, h->d_vsq, s.M, (int)s.K, s.K_ld, h->d_small + 2);
@@ -788,7 +788,7 @@ int tmvb_ctm_mstep(tmvb_ctm_t h, int64_t M_total)
     Shard &s = h->s;
     TMVB_CUDA(cudaSetDevice(s.device));
     TMVB_CUDA(cudaEventRecord(s.ev[2], s.stream));
-    TMVB_TRY(shard_normalize(&s, h->d_local, h->elbo_valid, 0.f));  // update_beta! CTM.jl:114-118
+    TMVB_TRY(shard_normalize(&s, h->d_local, h->elbo_valid, false));  // update_beta! CTM.jl:114-118
     TMVB_CUDA(cudaMemcpyAsync(s.h_pinned, h->d_small, h->n_small * 8, cudaMemcpyDeviceToHost, s.stream));
     TMVB_CUDA(cudaStreamSynchronize(s.stream));
     s.st.d2h_bytes += h->n_small * 8;

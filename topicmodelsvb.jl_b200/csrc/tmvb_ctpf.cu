@@ -779,7 +779,7 @@ int tmvb_ctpf_estep(tmvb_ctpf_t h, int viter, float vtol, int want_elbo)
     TMVB_CUDA(cudaEventRecord(s.ev[0], s.stream));
     TMVB_CUDA(cudaMemsetAsync(h->d_small, 0, (2 * s.K_ld + 2) * 8, s.stream));
     const void *fns[2] = {(const void *)kCtpfEstep[s.layout][want_elbo != 0], (const void *)kCtpfEstep[s.layout][want_elbo != 0]};
-    TMVB_TRY(shard_launch(&s, fns, &p));
+    TMVB_TRY(shard_launch(&s, pick_by_warps, fns, &p));
     TMVB_CUDA(cudaEventRecord(s.ev[1], s.stream));
     s.estep_timed = true;
     h->elbo_valid = (want_elbo != 0);

@@ -55,6 +55,52 @@ struct TokArgs {
     int r0, rstep;         // this warp takes rounds r0, r0 + rstep, ... (rstep = warps cooperating on the document)
 };
 
+// A staged table row as this lane sees it: CPL 16-byte chunks, each two packed fp32 pairs (.x = topics 4q, 4q+1; .y = 4q+2, 4q+3)
+// so that the FMA passes issue as FFMA2 (fma.rn.f32x2): half the floating-point issue slots of scalar FFMA.
+template <int LPT, int CPL, bool OVF>
+__device__ __forceinline__ void tok_load(const TokArgs &a, int n, bool ok, int kl, int CH, ulonglong2 (&b)[CPL], float &c, int &term, bool want_term)
+{
+    const ulonglong2 zero = make_ulonglong2(0ull, 0ull);
+    const int nn = ok ? n : 0;
+    c = 0.0f;
+    term = 0;
+    if (!OVF || n < a.cap) {
+        const ulonglong2 *row = reinterpret_cast<const ulonglong2 *>(a.tile + nn * a.RS) + kl;
+#pragma unroll
+        for (int m = 0; m < CPL; m++) b[m] = (m < CPL - 1 || kl + LPT * m < CH) ? row[LPT * m] : zero;
+        if (ok) c = a.cnt_s[nn];
+        if (want_term) term = a.term_s[nn];
+    } else {
+        term = a.gterms[nn];
+        const ulonglong2 *row = reinterpret_cast<const ulonglong2 *>(a.gtable + (size_t)term * a.K_ld) + kl;
+#pragma unroll
+        for (int m = 0; m < CPL; m++) b[m] = (m < CPL - 1 || kl + LPT * m < CH) ? __ldg(row + LPT * m) : zero;
+        if (ok) c = a.gcounts[nn];
+    }
+}
+
+// s = sum_i T_i e_i over this lane's chunks (two or four independent FFMA2 chains), then across the LPT lanes of the token
+template <int LPT, int CPL>
+__device__ __forceinline__ float tok_dot(const ulonglong2 (&b)[CPL], const f32x2 (&e01)[CPL], const f32x2 (&e23)[CPL])
+{
+    f32x2 sa = 0ull, sb = 0ull, sc = 0ull, sd = 0ull;
+#pragma unroll
+    for (int m = 0; m < CPL; m++) {
+        if (CPL >= 4 && (m & 1)) {
+            sc = fma2(b[m].x, e01[m], sc);
+            sd = fma2(b[m].y, e23[m], sd);
+        } else {
+            sa = fma2(b[m].x, e01[m], sa);
+            sb = fma2(b[m].y, e23[m], sb);
+        }
+    }
+    if (CPL >= 4) {
+        sa = add2(sa, sc);
+        sb = add2(sb, sd);
+    }
+    return group_sum<LPT>(hsum2(add2(sa, sb)));
+}
+
 // Sweep pass: s_n, t_n = c_n / s_n, g += T t.  EPS selects the reference's "@positive" epsilon (LDA) or none.
 template <int LPT, int CPL, bool OVF, bool EPS, int UNR = kSweepUnroll>
 __device__ __forceinline__ void tok_sweep(const TokArgs &a, int ts, int kl, const float4 (&e)[CPL], float4 (&g)[CPL], float &tsum)
@@ -62,89 +108,68 @@ __device__ __forceinline__ void tok_sweep(const TokArgs &a, int ts, int kl, cons
     constexpr int S = 32 / LPT;
     const int CH = a.K_ld >> 2;
     const float Keps = EPS ? (float)a.K * TMVB_EPS : 0.0f;
-    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    f32x2 e01[CPL], e23[CPL], g01[CPL], g23[CPL];
+#pragma unroll
+    for (int m = 0; m < CPL; m++) {
+        e01[m] = pk2(e[m].x, e[m].y);
+        e23[m] = pk2(e[m].z, e[m].w);
+        g01[m] = pk2(g[m].x, g[m].y);
+        g23[m] = pk2(g[m].z, g[m].w);
+    }
 #pragma unroll UNR
     for (int r = a.r0; r < a.rounds; r += a.rstep) {
         const int n = r * S + ts;
         const bool ok = n < a.Nd;
-        float4 b[CPL];
-        float c = 0.0f;
-        if (!OVF || n < a.cap) {
-            const int nn = ok ? n : 0;
-            const float4 *row = reinterpret_cast<const float4 *>(a.tile + nn * a.RS) + kl;
-#pragma unroll
-            for (int m = 0; m < CPL; m++) b[m] = (m < CPL - 1 || kl + LPT * m < CH) ? row[LPT * m] : zero4;
-            if (ok) c = a.cnt_s[nn];
-        } else {
-            const int nn = ok ? n : 0;
-            const float4 *row = reinterpret_cast<const float4 *>(a.gtable + (size_t)a.gterms[nn] * a.K_ld) + kl;
-#pragma unroll
-            for (int m = 0; m < CPL; m++) b[m] = (m < CPL - 1 || kl + LPT * m < CH) ? __ldg(row + LPT * m) : zero4;
-            if (ok) c = a.gcounts[nn];
-        }
-        float s0 = 0.0f, s1 = 0.0f, s2 = 0.0f, s3 = 0.0f;
-#pragma unroll
-        for (int m = 0; m < CPL; m++) {
-            s0 = fmaf(b[m].x, e[m].x, s0);
-            s1 = fmaf(b[m].y, e[m].y, s1);
-            s2 = fmaf(b[m].z, e[m].z, s2);
-            s3 = fmaf(b[m].w, e[m].w, s3);
-        }
-        const float s = group_sum<LPT>((s0 + s1) + (s2 + s3)) + Keps;
+        ulonglong2 b[CPL];
+        float c;
+        int term;
+        tok_load<LPT, CPL, OVF>(a, n, ok, kl, CH, b, c, term, false);
+        const float s = tok_dot<LPT, CPL>(b, e01, e23) + Keps;
         const float t = ok ? __fdividef(c, s) : 0.0f;
+        const f32x2 t2 = pk2(t, t);
 #pragma unroll
         for (int m = 0; m < CPL; m++) {
-            g[m].x = fmaf(b[m].x, t, g[m].x);
-            g[m].y = fmaf(b[m].y, t, g[m].y);
-            g[m].z = fmaf(b[m].z, t, g[m].z);
-            g[m].w = fmaf(b[m].w, t, g[m].w);
+            g01[m] = fma2(b[m].x, t2, g01[m]);
+            g23[m] = fma2(b[m].y, t2, g23[m]);
         }
         tsum += t;
+    }
+#pragma unroll
+    for (int m = 0; m < CPL; m++) {
+        unpk2(g01[m], g[m].x, g[m].y);
+        unpk2(g23[m], g[m].z, g[m].w);
     }
 }
 
 // Final pass: scatter c_n phi_ni = t_n (eps + T e_i) into stats with 16-byte vector reductions
-// (REDG.E.ADD.F32x4) and, when ELBO, accumulate sum_n c_n H(phi_n) = sum_n [c_n ln s_n - sum_i c_n phi_ni ln u_ni].
-template <int LPT, int CPL, bool OVF, bool EPS, bool ELBO>
+// (REDG.E.ADD.F32x4).  ELBO = 1: also accumulate sum_n c_n H(phi_n) = sum_n [c_n ln s_n - sum_i c_n phi_ni ln u_ni];
+// ELBO = 2: only sum_n c_n ln s_n -- the caller supplies sum_{n,i} c_n phi_ni ln u_ni in closed form from K- and
+// K x V-sized quantities (ln u_ni = ln T_i,w + ln e_i), so no per-(token, topic) logarithm is evaluated.
+template <int LPT, int CPL, bool OVF, bool EPS, int ELBO>
 __device__ __forceinline__ void tok_final(const TokArgs &a, int ts, int kl, const float4 (&e)[CPL], float &ent)
 {
     constexpr int S = 32 / LPT;
     const int CH = a.K_ld >> 2;
     const float Keps = EPS ? (float)a.K * TMVB_EPS : 0.0f;
     const float eps = EPS ? TMVB_EPS : 0.0f;
-    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    const f32x2 eps2 = pk2(eps, eps);
+    f32x2 e01[CPL], e23[CPL];
+#pragma unroll
+    for (int m = 0; m < CPL; m++) {
+        e01[m] = pk2(e[m].x, e[m].y);
+        e23[m] = pk2(e[m].z, e[m].w);
+    }
     for (int r = a.r0; r < a.rounds; r += a.rstep) {
         const int n = r * S + ts;
         const bool ok = n < a.Nd;
-        float4 b[CPL];
-        float c = 0.0f;
-        int term = 0;
-        if (!OVF || n < a.cap) {
-            const int nn = ok ? n : 0;
-            const float4 *row = reinterpret_cast<const float4 *>(a.tile + nn * a.RS) + kl;
-#pragma unroll
-            for (int m = 0; m < CPL; m++) b[m] = (m < CPL - 1 || kl + LPT * m < CH) ? row[LPT * m] : zero4;
-            if (ok) c = a.cnt_s[nn];
-            term = a.term_s[nn];
-        } else {
-            const int nn = ok ? n : 0;
-            term = a.gterms[nn];
-            const float4 *row = reinterpret_cast<const float4 *>(a.gtable + (size_t)term * a.K_ld) + kl;
-#pragma unroll
-            for (int m = 0; m < CPL; m++) b[m] = (m < CPL - 1 || kl + LPT * m < CH) ? __ldg(row + LPT * m) : zero4;
-            if (ok) c = a.gcounts[nn];
-        }
-        float s0 = 0.0f, s1 = 0.0f, s2 = 0.0f, s3 = 0.0f;
-#pragma unroll
-        for (int m = 0; m < CPL; m++) {
-            s0 = fmaf(b[m].x, e[m].x, s0);
-            s1 = fmaf(b[m].y, e[m].y, s1);
-            s2 = fmaf(b[m].z, e[m].z, s2);
-            s3 = fmaf(b[m].w, e[m].w, s3);
-        }
-        const float s = group_sum<LPT>((s0 + s1) + (s2 + s3)) + Keps;
+        ulonglong2 b[CPL];
+        float c;
+        int term;
+        tok_load<LPT, CPL, OVF>(a, n, ok, kl, CH, b, c, term, true);
+        const float s = tok_dot<LPT, CPL>(b, e01, e23) + Keps;
         if (ok) {
             const float t = __fdividef(c, s);
+            const f32x2 t2 = pk2(t, t);
             float *srow = a.stats + (size_t)term * a.K_ld + 4 * kl;
             float acc = 0.0f;
 #pragma unroll
@@ -152,14 +177,19 @@ __device__ __forceinline__ void tok_final(const TokArgs &a, int ts, int kl, cons
                 const int i0 = 4 * (kl + LPT * m);
                 if (i0 < a.K) {
                     // pad topics (i >= K) carry T = e = 0: they receive t*eps, which the M-step ignores
-                    const float ux = fmaf(b[m].x, e[m].x, eps), uy = fmaf(b[m].y, e[m].y, eps);
-                    const float uz = fmaf(b[m].z, e[m].z, eps), uw = fmaf(b[m].w, e[m].w, eps);
-                    if (!(a.dbg & 1)) red_add_v4(srow + 4 * LPT * m, t * ux, t * uy, t * uz, t * uw);
-                    if (ELBO) {
-                        if (EPS || ux > 0.f) acc = fmaf(t * ux, __logf(ux), acc);
-                        if (i0 + 1 < a.K && (EPS || uy > 0.f)) acc = fmaf(t * uy, __logf(uy), acc);
-                        if (i0 + 2 < a.K && (EPS || uz > 0.f)) acc = fmaf(t * uz, __logf(uz), acc);
-                        if (i0 + 3 < a.K && (EPS || uw > 0.f)) acc = fmaf(t * uw, __logf(uw), acc);
+                    const f32x2 u01 = fma2(b[m].x, e01[m], eps2), u23 = fma2(b[m].y, e23[m], eps2);
+                    float px, py, pz, pw;
+                    unpk2(mul2(t2, u01), px, py);
+                    unpk2(mul2(t2, u23), pz, pw);
+                    if (!(a.dbg & 1)) red_add_v4(srow + 4 * LPT * m, px, py, pz, pw);
+                    if (ELBO == 1) {
+                        float ux, uy, uz, uw;
+                        unpk2(u01, ux, uy);
+                        unpk2(u23, uz, uw);
+                        if (EPS || ux > 0.f) acc = fmaf(px, __logf(ux), acc);
+                        if (i0 + 1 < a.K && (EPS || uy > 0.f)) acc = fmaf(py, __logf(uy), acc);
+                        if (i0 + 2 < a.K && (EPS || uz > 0.f)) acc = fmaf(pz, __logf(uz), acc);
+                        if (i0 + 3 < a.K && (EPS || uw > 0.f)) acc = fmaf(pw, __logf(uw), acc);
                     }
                 }
             }
@@ -175,48 +205,43 @@ __device__ __forceinline__ void tok_final2(const TokArgs &a, int ts, int kl, con
 {
     constexpr int S = 32 / LPT;
     const int CH = a.K_ld >> 2;
-    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    f32x2 ea01[CPL], ea23[CPL], eb01[CPL], eb23[CPL], es01[CPL], es23[CPL];
+#pragma unroll
+    for (int m = 0; m < CPL; m++) {
+        ea01[m] = pk2(ea[m].x, ea[m].y);
+        ea23[m] = pk2(ea[m].z, ea[m].w);
+        eb01[m] = pk2(eb[m].x, eb[m].y);
+        eb23[m] = pk2(eb[m].z, eb[m].w);
+        es01[m] = add2(ea01[m], eb01[m]);
+        es23[m] = add2(ea23[m], eb23[m]);
+    }
     for (int r = a.r0; r < a.rounds; r += a.rstep) {
         const int n = r * S + ts;
         const bool ok = n < a.Nd;
-        float4 b[CPL];
-        float c = 0.0f;
-        int term = 0;
-        const int nn = ok ? n : 0;
-        if (!OVF || n < a.cap) {
-            const float4 *row = reinterpret_cast<const float4 *>(a.tile + nn * a.RS) + kl;
-#pragma unroll
-            for (int m = 0; m < CPL; m++) b[m] = (m < CPL - 1 || kl + LPT * m < CH) ? row[LPT * m] : zero4;
-            if (ok) c = a.cnt_s[nn];
-            term = a.term_s[nn];
-        } else {
-            term = a.gterms[nn];
-            const float4 *row = reinterpret_cast<const float4 *>(a.gtable + (size_t)term * a.K_ld) + kl;
-#pragma unroll
-            for (int m = 0; m < CPL; m++) b[m] = (m < CPL - 1 || kl + LPT * m < CH) ? __ldg(row + LPT * m) : zero4;
-            if (ok) c = a.gcounts[nn];
-        }
-        float s0 = 0.0f, s1 = 0.0f;
-#pragma unroll
-        for (int m = 0; m < CPL; m++) {
-            s0 = fmaf(b[m].x, ea[m].x + eb[m].x, s0);
-            s1 = fmaf(b[m].y, ea[m].y + eb[m].y, s1);
-            s0 = fmaf(b[m].z, ea[m].z + eb[m].z, s0);
-            s1 = fmaf(b[m].w, ea[m].w + eb[m].w, s1);
-        }
-        const float s = group_sum<LPT>(s0 + s1);
+        ulonglong2 b[CPL];
+        float c;
+        int term;
+        tok_load<LPT, CPL, OVF>(a, n, ok, kl, CH, b, c, term, true);
+        const float s = tok_dot<LPT, CPL>(b, es01, es23);
         if (ok) {
             const float t = __fdividef(c, s);
+            const f32x2 t2 = pk2(t, t);
             float *srow = a.stats + (size_t)term * a.K_ld + 4 * kl;
             float acc = 0.0f;
 #pragma unroll
             for (int m = 0; m < CPL; m++) {
                 const int i0 = 4 * (kl + LPT * m);
                 if (i0 < a.K) {
-                    const float ax = b[m].x * ea[m].x, ay = b[m].y * ea[m].y, az = b[m].z * ea[m].z, aw = b[m].w * ea[m].w;
-                    const float bx = b[m].x * eb[m].x, by = b[m].y * eb[m].y, bz = b[m].z * eb[m].z, bw = b[m].w * eb[m].w;
-                    if (!(a.dbg & 1)) red_add_v4(srow + 4 * LPT * m, t * (ax + bx), t * (ay + by), t * (az + bz), t * (aw + bw));
+                    float px, py, pz, pw;
+                    unpk2(mul2(t2, mul2(b[m].x, es01[m])), px, py);
+                    unpk2(mul2(t2, mul2(b[m].y, es23[m])), pz, pw);
+                    if (!(a.dbg & 1)) red_add_v4(srow + 4 * LPT * m, px, py, pz, pw);
                     if (ELBO) {
+                        float ax, ay, az, aw, bx, by, bz, bw;
+                        unpk2(mul2(b[m].x, ea01[m]), ax, ay);
+                        unpk2(mul2(b[m].y, ea23[m]), az, aw);
+                        unpk2(mul2(b[m].x, eb01[m]), bx, by);
+                        unpk2(mul2(b[m].y, eb23[m]), bz, bw);
                         if (ax > 0.f) acc = fmaf(t * ax, __logf(ax), acc);
                         if (bx > 0.f) acc = fmaf(t * bx, __logf(bx), acc);
                         if (i0 + 1 < a.K && ay > 0.f) acc = fmaf(t * ay, __logf(ay), acc);
@@ -231,6 +256,122 @@ __device__ __forceinline__ void tok_final2(const TokArgs &a, int ts, int kl, con
             if (ELBO) ent += ((kl == 0) ? c * __logf(s) : 0.0f) - acc;
         }
     }
+}
+
+// ---------------------------------------------------------------- register-resident documents ----------
+// For documents of at most W * NR * S tokens the K x N_d slab of the table never touches shared memory: warp w of the
+// W warps that share a document keeps rounds j = 0..NR-1 (token n = ((j W + w) S + ts)) in registers for all sweeps
+// (NR * CPL 16-byte chunks per lane), loaded once with LDG.128 straight from L2.  The loops over j are fully unrolled,
+// so the NR rounds of a sweep are independent instruction streams the scheduler can interleave.
+template <int LPT, int CPL, int NR>
+struct RegDoc {
+    ulonglong2 b[NR][CPL];
+    float c[NR];
+    int term[NR];
+};
+
+template <int LPT, int CPL, int W, int NR>
+__device__ __forceinline__ void reg_load(RegDoc<LPT, CPL, NR> &rd, const float *__restrict__ gtable, const int *__restrict__ gterms,
+                                         const float *__restrict__ gcounts, int Nd, int K_ld, int warp, int ts, int kl)
+{
+    constexpr int S = 32 / LPT;
+    const int CH = K_ld >> 2;
+    const ulonglong2 zero = make_ulonglong2(0ull, 0ull);
+#pragma unroll
+    for (int j = 0; j < NR; j++) {
+        const int n = (j * W + warp) * S + ts;
+        const bool ok = n < Nd;
+        rd.term[j] = ok ? __ldg(gterms + n) : 0;
+        rd.c[j] = ok ? __ldg(gcounts + n) : 0.0f;
+    }
+#pragma unroll
+    for (int j = 0; j < NR; j++) {
+        const int n = (j * W + warp) * S + ts;
+        const ulonglong2 *row = reinterpret_cast<const ulonglong2 *>(gtable + (size_t)rd.term[j] * K_ld) + kl;
+#pragma unroll
+        for (int m = 0; m < CPL; m++) rd.b[j][m] = (n < Nd && (m < CPL - 1 || kl + LPT * m < CH)) ? __ldg(row + LPT * m) : zero;
+    }
+}
+
+// one sweep over the register-resident rounds: s_n, t_n = c_n / s_n, g += T t (cf. tok_sweep)
+template <int LPT, int CPL, int NR, bool EPS>
+__device__ __forceinline__ void reg_sweep(const RegDoc<LPT, CPL, NR> &rd, int K, const f32x2 (&e01)[CPL], const f32x2 (&e23)[CPL],
+                                          f32x2 (&g01)[CPL], f32x2 (&g23)[CPL], float &tsum)
+{
+    const float Keps = EPS ? (float)K * TMVB_EPS : 0.0f;
+    float t[NR];
+#pragma unroll
+    for (int j = 0; j < NR; j++) {
+        const float s = tok_dot<LPT, CPL>(rd.b[j], e01, e23) + Keps;
+        t[j] = (rd.c[j] > 0.0f) ? __fdividef(rd.c[j], s) : 0.0f;
+    }
+#pragma unroll
+    for (int j = 0; j < NR; j++) {
+        const f32x2 t2 = pk2(t[j], t[j]);
+#pragma unroll
+        for (int m = 0; m < CPL; m++) {
+            g01[m] = fma2(rd.b[j][m].x, t2, g01[m]);
+            g23[m] = fma2(rd.b[j][m].y, t2, g23[m]);
+        }
+        tsum += t[j];
+    }
+}
+
+// final pass over the register-resident rounds: scatter t_n (eps + T e) into stats (REDG.E.ADD.F32x4) and, when ELBO,
+// accumulate sum_n c_n ln s_n (the "ELBO = 2" form of tok_final)
+template <int LPT, int CPL, int NR, bool EPS, bool ELBO>
+__device__ __forceinline__ void reg_final(const RegDoc<LPT, CPL, NR> &rd, float *__restrict__ stats, int K, int K_ld, int kl,
+                                          const f32x2 (&e01)[CPL], const f32x2 (&e23)[CPL], float &ent, int dbg)
+{
+    const float Keps = EPS ? (float)K * TMVB_EPS : 0.0f;
+    const float eps = EPS ? TMVB_EPS : 0.0f;
+    const f32x2 eps2 = pk2(eps, eps);
+#pragma unroll
+    for (int j = 0; j < NR; j++) {
+        const float s = tok_dot<LPT, CPL>(rd.b[j], e01, e23) + Keps;
+        if (rd.c[j] > 0.0f) {
+            const float t = __fdividef(rd.c[j], s);
+            const f32x2 t2 = pk2(t, t);
+            float *srow = stats + (size_t)rd.term[j] * K_ld + 4 * kl;
+#pragma unroll
+            for (int m = 0; m < CPL; m++) {
+                if (4 * (kl + LPT * m) < K) {
+                    float px, py, pz, pw;
+                    unpk2(mul2(t2, fma2(rd.b[j][m].x, e01[m], eps2)), px, py);
+                    unpk2(mul2(t2, fma2(rd.b[j][m].y, e23[m], eps2)), pz, pw);
+                    if (!(dbg & 1)) red_add_v4(srow + 4 * LPT * m, px, py, pz, pw);
+                }
+            }
+            if (ELBO && kl == 0) ent += rd.c[j] * __logf(s);
+        }
+    }
+}
+
+// psi(x) for two arguments at once in packed fp32 (FFMA2 / FMUL2 / FADD2; the MUFU ops stay scalar): the same
+// shift-by-6 rational recurrence and 3-term asymptotic series as psi_lgamma<false, true>.
+__device__ __forceinline__ void psi_pair(float x0, float x1, float &p0, float &p1)
+{
+    const f32x2 x = pk2(x0, x1);
+    f32x2 P = x, D = pk2(1.0f, 1.0f);
+#pragma unroll
+    for (int k = 1; k < 6; k++) {
+        const f32x2 f = add2(x, pk2((float)k, (float)k));
+        D = fma2(D, f, P);
+        P = mul2(P, f);
+    }
+    float P0, P1, D0, D1;
+    unpk2(P, P0, P1);
+    unpk2(D, D0, D1);
+    const bool lo0 = x0 < 6.0f, lo1 = x1 < 6.0f;
+    const float y0 = lo0 ? x0 + 6.0f : x0, y1 = lo1 ? x1 + 6.0f : x1;
+    const float c0 = lo0 ? __fdividef(D0, P0) : 0.0f, c1 = lo1 ? __fdividef(D1, P1) : 0.0f;
+    const f32x2 t = pk2(__fdividef(1.0f, y0), __fdividef(1.0f, y1)), nt2 = mul2(mul2(t, t), pk2(-1.0f, -1.0f));
+    // psi = ln y - t/2 - t2 (1/12 - t2 (1/120 - t2/252)) - corr
+    const f32x2 in1 = fma2(nt2, pk2(3.9682539683e-3f, 3.9682539683e-3f), pk2(8.3333333333e-3f, 8.3333333333e-3f));
+    const f32x2 in2 = fma2(nt2, in1, pk2(8.3333333333e-2f, 8.3333333333e-2f));
+    f32x2 r = fma2(t, pk2(-0.5f, -0.5f), pk2(__logf(y0) - c0, __logf(y1) - c1));
+    r = fma2(nt2, in2, r);
+    unpk2(r, p0, p1);
 }
 
 // owner-lane sum of the S per-stream partials of topic i (4 independent chains)
@@ -251,6 +392,28 @@ __device__ __forceinline__ float owner_sum(const float *gs, int RS, int i)
         for (int w = 0; w < S; w++) g0 += gs[w * RS + i];
     }
     return (g0 + g1) + (g2 + g3);
+}
+
+// owner-lane sums of two consecutive topics i, i+1 (i even): LDS.64 + FADD2, four independent chains
+template <int S>
+__device__ __forceinline__ float2 owner_sum2(const float *gs, int RS, int i)
+{
+    f32x2 g0 = 0ull, g1 = 0ull, g2 = 0ull, g3 = 0ull;
+    if (S >= 4) {
+#pragma unroll
+        for (int w = 0; w < S; w += 4) {
+            g0 = add2(g0, *reinterpret_cast<const f32x2 *>(gs + w * RS + i));
+            g1 = add2(g1, *reinterpret_cast<const f32x2 *>(gs + (w + 1) * RS + i));
+            g2 = add2(g2, *reinterpret_cast<const f32x2 *>(gs + (w + 2) * RS + i));
+            g3 = add2(g3, *reinterpret_cast<const f32x2 *>(gs + (w + 3) * RS + i));
+        }
+    } else {
+#pragma unroll
+        for (int w = 0; w < S; w++) g0 = add2(g0, *reinterpret_cast<const f32x2 *>(gs + w * RS + i));
+    }
+    float2 r;
+    unpk2(add2(add2(g0, g1), add2(g2, g3)), r.x, r.y);
+    return r;
 }
 
 // Stage `ns` table rows (ids in term_s) into the tile: one TMA bulk copy per row, completion on `mbar`

@@ -128,9 +128,12 @@ __global__ void colsum_kernel(const float *__restrict__ stats, int V, int K_ld, 
     }
 }
 // beta_new = stats ./ rowsum ; stats <- 0 ; elbo_w += sum stats * ln(beta_new + eps)
-// (LDA.jl:121-125 / CTM.jl:114-118 and the Elogpw term LDA.jl:64-67 / CTM.jl:69-73 rewritten over the statistics)
-__global__ void normalize_kernel(float *__restrict__ stats, float *__restrict__ beta_new, const double *__restrict__ rowsum,
-                                 long long n, int K, int K_ld, double *__restrict__ elbo_w, int want_elbo)
+// (LDA.jl:121-125 / CTM.jl:114-118 and the Elogpw term LDA.jl:64-67 / CTM.jl:69-73 rewritten over the statistics).
+// beta_old != NULL: elbo_w += sum stats * [ln(beta_new + eps) - ln(beta_old + eps)] -- the second term is the part of
+// sum_d sum_n c_n H(phi_n) (LDA.jl:76-79) that is linear in the statistics (ln u_ni = ln beta_old_i,w + Elogtheta_old_i),
+// which spares the E-step kernel one logarithm per (token, topic).
+__global__ void normalize_kernel(float *__restrict__ stats, float *__restrict__ beta_new, const float *__restrict__ beta_old,
+                                 const double *__restrict__ rowsum, long long n, int K, int K_ld, double *__restrict__ elbo_w, int want_elbo)
 {
     double acc = 0.0;
     for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < n; q += (long long)gridDim.x * blockDim.x) {
@@ -140,7 +143,11 @@ __global__ void normalize_kernel(float *__restrict__ stats, float *__restrict__ 
         if (i < K) {
             const double rs = rowsum[i];
             b = rs > 0.0 ? (float)((double)s / rs) : 0.0f;
-            if (want_elbo) acc += (double)(s * logf(b + TMVB_EPS));
+            if (want_elbo) {
+                float l = logf(b + TMVB_EPS);
+                if (beta_old) l -= logf(beta_old[q] + TMVB_EPS);
+                acc += (double)(s * l);
+            }
         }
         beta_new[q] = b;
         stats[q] = 0.0f;
@@ -276,6 +283,7 @@ static int plan_buckets(Shard *s, size_t fixed_bytes)
         if (b.cap > cap_max) b.cap = cap_max;
         b.cap2 = 0;
         b.warps = 1;
+        b.nr = 0;
         b.smem = fixed_bytes + (size_t)b.cap * per_tok;
         b.grid = 0;
         s->buckets.push_back(b);
@@ -406,7 +414,9 @@ int shard_download_rows(Shard *s, const float *d_src, float *host, int64_t rows,
     return 0;
 }
 
-int shard_launch(Shard *s, const void *const *fn_by_warps, void *dev_struct)
+const void *pick_by_warps(const Bucket &b, const void *ctx) { return static_cast<const void *const *>(ctx)[b.warps - 1]; }
+
+int shard_launch(Shard *s, BucketKernelFn pick, const void *ctx, void *dev_struct)
 {
     TMVB_CUDA(cudaMemsetAsync(s->d_counters, 0, kMaxBuckets * 4, s->stream));
     const int ns = (s->buckets.size() > 1) ? s->n_streams : 1;
@@ -416,7 +426,7 @@ int shard_launch(Shard *s, const void *const *fn_by_warps, void *dev_struct)
     }
     for (size_t bi = 0; bi < s->buckets.size(); bi++) {
         Bucket &b = s->buckets[bi];
-        const void *fn = fn_by_warps[b.warps - 1];
+        const void *fn = pick(b, ctx);
         const int threads = 32 * b.warps;
         if (b.grid == 0) {
             int occ = 0;
@@ -437,9 +447,8 @@ int shard_launch(Shard *s, const void *const *fn_by_warps, void *dev_struct)
     return 0;
 }
 
-int shard_normalize(Shard *s, double *d_acc, bool want_elbo, float prior)
+int shard_normalize(Shard *s, double *d_acc, bool want_elbo, bool entropy_term)
 {
-    (void)prior;
     if (s->V == 0) return 0;
     TMVB_CUDA(cudaMemsetAsync(d_acc, 0, (2 * s->K_ld) * 8, s->stream));
     const int R = std::max(1, 256 / s->K_ld);
@@ -448,8 +457,9 @@ int shard_normalize(Shard *s, double *d_acc, bool want_elbo, float prior)
     colsum_kernel<<<grid, threads, threads * 8, s->stream>>>(s->d_stats, (int)s->V, s->K_ld, d_acc);
     TMVB_CUDA(cudaGetLastError());
     const long long n = (long long)s->V * s->K_ld;
-    normalize_kernel<<<grid_for(n, 256, s->n_sm), 256, 0, s->stream>>>(s->d_stats, s->d_beta[s->cur ^ 1], d_acc, n, (int)s->K, s->K_ld,
-                                                                      d_acc + s->K_ld, want_elbo ? 1 : 0);
+    normalize_kernel<<<grid_for(n, 256, s->n_sm), 256, 0, s->stream>>>(s->d_stats, s->d_beta[s->cur ^ 1],
+                                                                      (want_elbo && entropy_term) ? s->d_beta[s->cur] : nullptr, d_acc, n, (int)s->K,
+                                                                      s->K_ld, d_acc + s->K_ld, want_elbo ? 1 : 0);
     TMVB_CUDA(cudaGetLastError());
     s->st.kernel_launches += 2;
     s->cur ^= 1;  // beta_old <- beta ; beta <- new  (LDA.jl:122-123)

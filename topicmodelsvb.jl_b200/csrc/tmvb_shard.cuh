@@ -12,6 +12,7 @@ struct Bucket {
     int doc_begin, doc_end, cap, grid;
     int cap2;  // second tile capacity (CTPF reader lists); 0 otherwise
     int warps; // warps cooperating on one document in this launch (CTA = 32 * warps threads)
+    int nr;    // > 0: register-resident kernel, rounds per warp (capacity warps * nr * S tokens); 0: shared-memory tile kernel
     size_t smem;
 };
 
@@ -68,11 +69,15 @@ int shard_upload_rows(Shard *s, const float *host, float *d_dst, int64_t rows, c
 int shard_download_rows(Shard *s, const float *d_src, float *host, int64_t rows, const int *d_perm);
 // returns and clears the validation bit mask accumulated by shard_upload_rows (2 bits per `validate` code)
 int shard_validation(Shard *s, int *mask);
-// launch an E-step kernel `fn(Dev, doc_begin, doc_end, cap, cap2, counter)` over every bucket; fn_by_warps[w-1] is the
-// instantiation for w warps per document (Bucket::warps)
-int shard_launch(Shard *s, const void *const *fn_by_warps, void *dev_struct);
+// launch an E-step kernel `fn(Dev, doc_begin, doc_end, cap, cap2, counter)` over every bucket; pick(bucket, ctx) returns the
+// instantiation for the bucket's (warps, nr)
+typedef const void *(*BucketKernelFn)(const Bucket &b, const void *ctx);
+int shard_launch(Shard *s, BucketKernelFn pick, const void *ctx, void *dev_struct);
+// pick for kernels that only come in "warps per document" flavours: ctx = const void *const fn_by_warps[]
+const void *pick_by_warps(const Bucket &b, const void *ctx);
 // beta_new = stats ./ rowsum ; stats <- 0 ; [elbo_w = sum stats ln(beta_new + eps)].  d_acc: double[2*K_ld] (rowsum | elbo_w)
-int shard_normalize(Shard *s, double *d_acc, bool want_elbo, float prior);
+// entropy_term: elbo_w additionally receives - sum stats ln(beta_old + eps) (see normalize_kernel)
+int shard_normalize(Shard *s, double *d_acc, bool want_elbo, bool entropy_term);
 int shard_topics(Shard *s, const float *d_mat, const float *d_scale, int32_t *out);
 int shard_get_stats(Shard *s, const double *d_sweeps, tmvb_stats *out);
 // a second per-document list (CTPF reader lists, modelutils.jl:443-472) re-laid-out in the shard's internal document order
