@@ -272,7 +272,7 @@ struct RegDoc {
 
 template <int LPT, int CPL, int W, int NR>
 __device__ __forceinline__ void reg_load(RegDoc<LPT, CPL, NR> &rd, const float *__restrict__ gtable, const int *__restrict__ gterms,
-                                         const float *__restrict__ gcounts, int Nd, int K_ld, int warp, int ts, int kl)
+                                         const float *__restrict__ gcounts, int Nd, int K_ld, int warp, int ts, int kl, int dbg)
 {
     constexpr int S = 32 / LPT;
     const int CH = K_ld >> 2;
@@ -287,7 +287,8 @@ __device__ __forceinline__ void reg_load(RegDoc<LPT, CPL, NR> &rd, const float *
 #pragma unroll
     for (int j = 0; j < NR; j++) {
         const int n = (j * W + warp) * S + ts;
-        const ulonglong2 *row = reinterpret_cast<const ulonglong2 *>(gtable + (size_t)rd.term[j] * K_ld) + kl;
+        // dbg bit 2 (developer probe): every token reads row 0 -- isolates the cost of the random row gather
+        const ulonglong2 *row = reinterpret_cast<const ulonglong2 *>(gtable + ((dbg & 4) ? (size_t)0 : (size_t)rd.term[j] * K_ld)) + kl;
 #pragma unroll
         for (int m = 0; m < CPL; m++) rd.b[j][m] = (n < Nd && (m < CPL - 1 || kl + LPT * m < CH)) ? __ldg(row + LPT * m) : zero;
     }
