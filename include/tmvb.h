@@ -88,6 +88,20 @@ int tmvb_lda_reduce_buffers(tmvb_lda_t h, void **stats, int64_t *n_stats, void *
  * stats <- 0.  M_total is the corpus-wide document count (== M unless sharded).  Asynchronous. */
 int tmvb_lda_mstep(tmvb_lda_t h);
 
+/* Multi-GPU exchange over peer memory (no reference counterpart: the reference is single-device).
+ * One process per GPU of one NVSwitch box.  Each rank exports CUDA IPC handles of its statistics / table / small buffers
+ * (comm_export -> blob), the host driver all-gathers the blobs (any transport), every rank maps its peers (comm_connect), and
+ * from then on tmvb_lda_exchange_mstep() replaces { sum reduce_buffers over ranks; tmvb_lda_mstep }: ONE kernel that
+ * reduce-scatters the statistics with loads from the peers' memory, normalises its slice of beta and all-gathers it with
+ * stores into the peers' memory (gpuLDA.jl:179-204 semantics on the summed statistics).  Every rank must call it once per
+ * outer iteration; a rank that does not arrive within 4 s makes the others give up (tmvb_lda_comm_status != 0) instead
+ * of hanging.  world <= 8. */
+#define TMVB_COMM_BLOB_BYTES 512
+int tmvb_lda_comm_export(tmvb_lda_t h, void *blob, int64_t blob_bytes);
+int tmvb_lda_comm_connect(tmvb_lda_t h, int rank, int world, const void *blobs /* [world][blob_bytes] */, int64_t blob_bytes);
+int tmvb_lda_exchange_mstep(tmvb_lda_t h);
+int tmvb_lda_comm_status(tmvb_lda_t h, int *status);
+
 /* `@host model.Elogtheta_sum_buffer` (macros.jl:79, gpuLDA.jl:133); fp64. */
 int tmvb_lda_get_elogtheta_sum(tmvb_lda_t h, double *out);
 

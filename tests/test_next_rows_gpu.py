@@ -66,26 +66,39 @@ m = tm.gpuLDA(tm.Corpus.from_csr(sh), K, reducer=red, M_total=c.M, stream=work.c
 m.beta = np.array(beta0.T, order="F", copy=True)
 tr = []
 tm.train(m, iter=4, tol=0.0, printelbo=False, trace=tr)
+import ctypes
+st = ctypes.c_int(0)
+tm._lib.check(tm._lib.load().tmvb_lda_comm_status(m._handle(), ctypes.byref(st)))
+bsum = torch.tensor([float(np.abs(m.beta).sum()), float(m.beta[1, 5])], dtype=torch.float64, device="cuda")
+both = [torch.empty_like(bsum) for _ in range(world)]
+dist.all_gather(both, bsum)
 if rank == 0:
-    print("RESULT " + json.dumps({"elbo": tr, "alpha": m.alpha.tolist()}))
+    print("RESULT " + json.dumps({"elbo": tr, "alpha": m.alpha.tolist(), "p2p": bool(m._p2p), "status": st.value,
+                                  "beta_probe": [b.tolist() for b in both]}))
 dist.destroy_process_group()
 '''
 
 
-def test_two_gpu_nccl_matches_single_gpu(tm, orc, tmp_path):
-    """Doc-sharded d %% 2 over two GPUs with an NCCL all-reduce of the statistics == the single-process trajectory."""
+@pytest.mark.parametrize("p2p", ["1", "0"])
+def test_two_gpu_exchange_matches_single_gpu(tm, orc, tmp_path, p2p):
+    """Doc-sharded d %% 2 over two GPUs == the single-process trajectory, with the statistics exchanged by the fused
+    peer-memory kernel (tmvb_lda_exchange_mstep, TMVB_P2P=1) and by NCCL all-reduce + tmvb_lda_mstep (TMVB_P2P=0)."""
     import torch
 
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs (run with gpurun --gpus 2)")
     script = tmp_path / "worker.py"
     script.write_text(_WORKER % ROOT)
+    env = dict(os.environ, TMVB_P2P=p2p)
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
-                        "--master-port", "29533", str(script)], capture_output=True, text=True, timeout=600)
+                        "--master-port", "29533" if p2p == "1" else "29534", str(script)], capture_output=True, text=True, timeout=600, env=env)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     import json
     line = [l for l in r.stdout.splitlines() if l.startswith("RESULT ")][-1]
     got = json.loads(line[7:])
+    assert got["status"] == 0
+    assert got["p2p"] == (p2p == "1"), "the peer-memory exchange was not used"
+    assert got["beta_probe"][0] == got["beta_probe"][1], "ranks disagree on beta"
     c = tm.synth.gencorp_lda(M=400, V=600, K=6, seed=11)
     K = 8
     beta0 = tm.synth.init_beta(K, c.V, seed=7).astype(np.float32)

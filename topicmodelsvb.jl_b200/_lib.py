@@ -15,6 +15,7 @@ import numpy as np
 _PKG = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_PKG)
 SO_PATH = os.path.join(_PKG, "libtmvb.so")
+COMM_BLOB_BYTES = 512   # TMVB_COMM_BLOB_BYTES
 _lib = None
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
@@ -80,6 +81,10 @@ SIGNATURES = {
     "tmvb_lda_estep": (C.c_int, [_vp, C.c_int, C.c_float, C.c_int]),
     "tmvb_lda_reduce_buffers": (C.c_int, [_vp, C.POINTER(_vp), C.POINTER(C.c_int64), C.POINTER(_vp), C.POINTER(C.c_int64)]),
     "tmvb_lda_mstep": (C.c_int, [_vp]),
+    "tmvb_lda_comm_export": (C.c_int, [_vp, _vp, C.c_int64]),
+    "tmvb_lda_comm_connect": (C.c_int, [_vp, C.c_int, C.c_int, _vp, C.c_int64]),
+    "tmvb_lda_exchange_mstep": (C.c_int, [_vp]),
+    "tmvb_lda_comm_status": (C.c_int, [_vp, C.POINTER(C.c_int)]),
     "tmvb_lda_get_elogtheta_sum": (C.c_int, [_vp, _vp]),
     "tmvb_lda_update_alpha": (C.c_int, [_vp, C.c_int64, C.c_int, C.c_double, _vp]),
     "tmvb_lda_elbo": (C.c_int, [_vp, C.c_int, C.c_int64, C.POINTER(C.c_double), C.POINTER(C.c_double)]),

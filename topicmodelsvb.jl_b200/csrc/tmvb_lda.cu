@@ -19,6 +19,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include "tmvb_comm.cuh"
 #include "tmvb_shard.cuh"
 
 namespace tmvb {
@@ -578,11 +579,10 @@ __device__ inline double d_digamma(double x)
 // update_elbo! exactly as the CPU model states it (LDA.jl:50-93): phi rebuilt from beta_old and
 // Elogtheta_old, the five expectations evaluated with alpha, beta, gamma, Elogtheta.  fp64
 // arithmetic on the fp32 device state; one warp per document, lanes over topics.
-template <typename real>
+template <typename real, int RM>
 __global__ void lda_elbo_kernel(const LdaDev p, const float *__restrict__ beta_old, double lg_alpha_term, double *out)
 {
-    constexpr bool F64 = sizeof(real) == 8;
-    constexpr int RM = 8;  // K <= 256: topics i = lane + 32 r held in registers
+    constexpr bool F64 = sizeof(real) == 8;  // RM = ceil(K / 32) rounded up to {1, 2, 4, 8}: topics i = lane + 32 r held in registers
     const int lane = threadIdx.x & 31;
     const int wpb = blockDim.x >> 5;
     const real eps = (real)TMVB_EPS_D;
@@ -613,31 +613,45 @@ __global__ void lda_elbo_kernel(const LdaDev p, const float *__restrict__ beta_o
         }
         g0 = warp_sum_d(g0);
         real tacc = 0;
-        for (int n = 0; n < Nd; n++) {
-            const int term = p.terms[o + n];
-            const real c = p.counts[o + n];
-            const float *bo = beta_old + (size_t)term * p.K_ld, *bn = p.beta + (size_t)term * p.K_ld;
-            real u_r[RM], s = 0;
+        // UN tokens per iteration: their row loads and warp reductions are independent, which hides the
+        // load -> reduce -> log latency chain that made this pass slower than a whole E-step
+        constexpr int UN = F64 ? 1 : 4;
+        for (int n0 = 0; n0 < Nd; n0 += UN) {
+            real u_r[UN][RM], s[UN], c[UN];
+            const float *bn[UN];
 #pragma unroll
-            for (int r = 0; r < RM; r++) {
-                const int i = lane + 32 * r;
-                u_r[r] = (i < p.K) ? eps + (real)bo[i] * e_r[r] : (real)0;
-                s += u_r[r];
-            }
-            s = F64 ? (real)warp_sum_d((double)s) : (real)warp_sum((float)s);
-            // sum_i phi_i (E_i + ln(beta_i + eps) - ln phi_i),  phi = u / s,  ln phi = ln u - ln s
-            const real ls = F64 ? (real)log((double)s) : (real)__logf((float)s);
-            real a = 0;
+            for (int q = 0; q < UN; q++) {
+                const int n = min(n0 + q, Nd - 1);
+                const int term = p.terms[o + n];
+                c[q] = (n0 + q < Nd) ? (real)p.counts[o + n] : (real)0;
+                const float *bo = beta_old + (size_t)term * p.K_ld;
+                bn[q] = p.beta + (size_t)term * p.K_ld;
+                s[q] = 0;
 #pragma unroll
-            for (int r = 0; r < RM; r++) {
-                const int i = lane + 32 * r;
-                if (i < p.K) {
-                    const real lb = F64 ? (real)log((double)bn[i] + TMVB_EPS_D) : (real)__logf(bn[i] + TMVB_EPS);
-                    const real lu = F64 ? (real)log((double)u_r[r]) : (real)__logf((float)u_r[r]);
-                    a += u_r[r] * (En_r[r] + lb - lu + ls);
+                for (int r = 0; r < RM; r++) {
+                    const int i = lane + 32 * r;
+                    u_r[q][r] = (i < p.K) ? eps + (real)bo[i] * e_r[r] : (real)0;
+                    s[q] += u_r[q][r];
                 }
             }
-            if (F64) dacc += (double)(c * a / s); else tacc += c * a / s;
+#pragma unroll
+            for (int q = 0; q < UN; q++) s[q] = F64 ? (real)warp_sum_d((double)s[q]) : (real)warp_sum((float)s[q]);
+#pragma unroll
+            for (int q = 0; q < UN; q++) {
+                // sum_i phi_i (E_i + ln(beta_i + eps) - ln phi_i),  phi = u / s,  ln phi = ln u - ln s
+                const real ls = F64 ? (real)log((double)s[q]) : (real)__logf((float)s[q]);
+                real a = 0;
+#pragma unroll
+                for (int r = 0; r < RM; r++) {
+                    const int i = lane + 32 * r;
+                    if (i < p.K) {
+                        const real lb = F64 ? (real)log((double)bn[q][i] + TMVB_EPS_D) : (real)__logf(bn[q][i] + TMVB_EPS);
+                        const real lu = F64 ? (real)log((double)u_r[q][r]) : (real)__logf((float)u_r[q][r]);
+                        a += u_r[q][r] * (En_r[r] + lb - lu + ls);
+                    }
+                }
+                if (F64) dacc += (double)(c[q] * a / s[q]); else tacc += c[q] * a / s[q];
+            }
         }
         dacc += (double)tacc;
         dacc = warp_sum_d(dacc);
@@ -779,6 +793,144 @@ __global__ void lda_phi_kernel(const LdaDev p, const float *__restrict__ beta_ol
     }
 }
 
+// ------------------------------------------------------------------ fused exchange + M-step ----------
+// One kernel per outer iteration replaces { all-reduce(stats), all-reduce(small), colsum, normalise } when the ranks of a
+// box have mapped each other's buffers (tmvb_comm.cuh).  V is cut into `world` row slices; rank r
+//   1. waits until every rank's E-step has finished                                              [peer barrier 1]
+//   2. reduce-scatter: sums its slice of the K x V statistics over all ranks with loads from the mapped peer buffers
+//      (fixed rank order: every rank would compute bit-identical sums), accumulates the slice's column sums in fp64,
+//      and sums the small fp64 vector (sum_d Elogtheta_d, ELBO partials, sweeps) of all ranks
+//   3. publishes its column-sum partials                                                          [peer barrier 2]
+//   4. normalises its slice (LDA.jl:121-125), all-gathers it by storing into EVERY rank's next beta buffer, accumulates
+//      sum S (ln beta_new - ln beta_old) (Elogpw + the linear part of -Elogqz), and zeroes its local statistics
+//   5. [peer barrier 3], then sums the ELBO partials of all ranks.
+// Traffic per rank: (world-1)/world of the table in, the same out, over NVLink; no NCCL call, no host round trip.
+struct LdaXchg {
+    int V, K, K_ld, rank, world, want_elbo, n_small, parity;
+    unsigned long long epoch;
+    const float *stats[kMaxPeers];
+    float *beta_new[kMaxPeers];
+    const double *small[kMaxPeers];
+    void *ctl[kMaxPeers];
+    float *my_stats;
+    const float *beta_old;
+    double *small_red, *local;
+};
+
+__global__ void __launch_bounds__(256) lda_exchange_mstep_kernel(const LdaXchg x)
+{
+    extern __shared__ double sh[];  // [RPP][K_ld] column-sum staging | rs[K_ld]
+    const int tid = threadIdx.x, G = gridDim.x;
+    const int K_ld = x.K_ld, CH = K_ld >> 2, RPP = blockDim.x / CH;
+    const int rl = tid / CH, c = tid - rl * CH;
+    const bool active = rl < RPP;
+    double *rs = sh + (size_t)RPP * K_ld;
+    void *my_ctl = x.ctl[x.rank];
+    const CtlView me = ctl_view(my_ctl);
+    double *my_part = me.part + x.parity * kCtlPartLen;
+    const int r0 = (int)((long long)x.V * x.rank / x.world), r1 = (int)((long long)x.V * (x.rank + 1) / x.world);
+
+    if (blockIdx.x == 0 && x.world > 1) peer_barrier(x.ctl, my_ctl, x.rank, x.world, x.epoch + 1);
+    grid_barrier(me.grid_count, 1u * G, me.status);
+
+    // ---- reduce-scatter + column sums of the slice
+    double cs0 = 0.0, cs1 = 0.0, cs2 = 0.0, cs3 = 0.0;
+    if (active) {
+        for (int r = r0 + blockIdx.x * RPP + rl; r < r1; r += G * RPP) {
+            const size_t q = (size_t)r * K_ld + 4 * c;
+            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int pr = 0; pr < x.world; pr++) {
+                const float4 v = __ldcg(reinterpret_cast<const float4 *>(x.stats[pr] + q));
+                acc.x += v.x;
+                acc.y += v.y;
+                acc.z += v.z;
+                acc.w += v.w;
+            }
+            *reinterpret_cast<float4 *>(x.my_stats + q) = acc;
+            cs0 += (double)acc.x;
+            cs1 += (double)acc.y;
+            cs2 += (double)acc.z;
+            cs3 += (double)acc.w;
+        }
+        double *row = sh + (size_t)rl * K_ld + 4 * c;
+        row[0] = cs0;
+        row[1] = cs1;
+        row[2] = cs2;
+        row[3] = cs3;
+    }
+    __syncthreads();
+    if (tid < K_ld) {
+        double a = 0.0;
+        for (int q = 0; q < RPP; q++) a += sh[(size_t)q * K_ld + tid];
+        if (a != 0.0) atomicAdd(my_part + tid, a);
+    }
+    if (blockIdx.x == 0)
+        for (int i = tid; i < x.n_small; i += blockDim.x) {
+            double a = 0.0;
+            for (int pr = 0; pr < x.world; pr++) a += __ldcg(x.small[pr] + i);
+            x.small_red[i] = a;
+        }
+    grid_barrier(me.grid_count, 2u * G, me.status);
+    if (blockIdx.x == 0 && x.world > 1) peer_barrier(x.ctl, my_ctl, x.rank, x.world, x.epoch + 2);
+    grid_barrier(me.grid_count, 3u * G, me.status);
+
+    // ---- total column sums (every CTA, fixed rank order), normalise + all-gather the slice, zero the local statistics
+    if (tid < K_ld) {
+        double a = 0.0;
+        for (int pr = 0; pr < x.world; pr++) a += __ldcg(ctl_view(x.ctl[pr]).part + x.parity * kCtlPartLen + tid);
+        rs[tid] = a;
+    }
+    __syncthreads();
+    double eacc = 0.0;
+    if (active) {
+        double inv[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) inv[j] = (4 * c + j < x.K && rs[4 * c + j] > 0.0) ? 1.0 / rs[4 * c + j] : 0.0;
+        for (int r = r0 + blockIdx.x * RPP + rl; r < r1; r += G * RPP) {
+            const size_t q = (size_t)r * K_ld + 4 * c;
+            const float4 S = *reinterpret_cast<const float4 *>(x.my_stats + q);
+            float4 b;
+            b.x = (float)((double)S.x * inv[0]);
+            b.y = (float)((double)S.y * inv[1]);
+            b.z = (float)((double)S.z * inv[2]);
+            b.w = (float)((double)S.w * inv[3]);
+            if (x.want_elbo) {
+                const float4 bo = *reinterpret_cast<const float4 *>(x.beta_old + q);
+                if (4 * c + 0 < x.K) eacc += (double)(S.x * (logf(b.x + TMVB_EPS) - logf(bo.x + TMVB_EPS)));
+                if (4 * c + 1 < x.K) eacc += (double)(S.y * (logf(b.y + TMVB_EPS) - logf(bo.y + TMVB_EPS)));
+                if (4 * c + 2 < x.K) eacc += (double)(S.z * (logf(b.z + TMVB_EPS) - logf(bo.z + TMVB_EPS)));
+                if (4 * c + 3 < x.K) eacc += (double)(S.w * (logf(b.w + TMVB_EPS) - logf(bo.w + TMVB_EPS)));
+            }
+            for (int pr = 0; pr < x.world; pr++) *reinterpret_cast<float4 *>(x.beta_new[pr] + q) = b;
+            *reinterpret_cast<float4 *>(x.my_stats + q) = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    }
+    {   // the rows outside the slice (the peers have finished reading them: peer barrier 2)
+        const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        float4 *st4 = reinterpret_cast<float4 *>(x.my_stats);
+        const size_t n4 = (size_t)x.V * CH, s0 = (size_t)r0 * CH, s1 = (size_t)r1 * CH;
+        for (size_t q = (size_t)blockIdx.x * blockDim.x + tid; q < n4; q += (size_t)G * blockDim.x)
+            if (q < s0 || q >= s1) st4[q] = z4;
+    }
+    if (x.want_elbo) {
+        eacc = warp_sum_d(eacc);
+        if ((tid & 31) == 0 && eacc != 0.0) atomicAdd(my_part + K_ld, eacc);
+    }
+    grid_barrier(me.grid_count, 4u * G, me.status);
+    if (blockIdx.x != 0) return;
+    if (x.world > 1) peer_barrier(x.ctl, my_ctl, x.rank, x.world, x.epoch + 3);
+
+    // ---- the reduced ELBO term; rowsum for inspection; recycle the other parity of the partial sums
+    if (tid < K_ld) x.local[tid] = rs[tid];
+    if (tid == 0) {
+        double a = 0.0;
+        for (int pr = 0; pr < x.world; pr++) a += __ldcg(ctl_view(x.ctl[pr]).part + x.parity * kCtlPartLen + K_ld);
+        x.local[K_ld] = a;
+    }
+    double *other = me.part + (x.parity ^ 1) * kCtlPartLen;
+    for (int i = tid; i < kCtlPartLen; i += blockDim.x) other[i] = 0.0;
+}
+
 typedef void (*LdaEstepFn)(const LdaDev, int, int, int, int, int *);
 // register-resident variants: (warps per document, rounds per warp), by descending capacity W * NR * S tokens
 constexpr int kNumRegVariants = 6;
@@ -834,6 +986,7 @@ struct tmvb_lda_s {
     bool alpha_on_device = false, elbo_dev_valid = false;
     double *d_small = nullptr;          // [K_ld+2], summed over ranks
     double *d_local = nullptr;          // [K_ld] rowsum | [K_ld] elbo_w | [K_ld+1] scratch for the standalone ELBO
+    Comm comm;                          // peer-memory exchange (multi-GPU), see tmvb_comm.cuh
 };
 
 namespace {
@@ -875,6 +1028,7 @@ void lda_free(tmvb_lda_t h)
     cudaFree(h->d_gamma);
     cudaFree(h->d_small);
     cudaFree(h->d_local);
+    comm_free(&h->comm);
     shard_free(&h->s);
 }
 
@@ -1118,6 +1272,89 @@ int tmvb_lda_mstep(tmvb_lda_t h)
     return 0;
 }
 
+int tmvb_lda_comm_export(tmvb_lda_t h, void *blob, int64_t blob_bytes)
+{
+    TMVB_CHECK_ARG(h != nullptr, "handle is NULL");
+    TMVB_CHECK_ARG(blob_bytes >= TMVB_COMM_BLOB_BYTES, "blob must hold TMVB_COMM_BLOB_BYTES");
+    Shard &s = h->s;
+    TMVB_CUDA(cudaSetDevice(s.device));
+    void *bufs[kCommBufs] = {s.d_stats, s.d_beta[0], s.d_beta[1], h->d_small, nullptr};
+    return comm_export(&h->comm, bufs, blob, (size_t)blob_bytes);
+}
+
+int tmvb_lda_comm_connect(tmvb_lda_t h, int rank, int world, const void *blobs, int64_t blob_bytes)
+{
+    TMVB_CHECK_ARG(h != nullptr, "handle is NULL");
+    TMVB_CUDA(cudaSetDevice(h->s.device));
+    return comm_connect(&h->comm, rank, world, blobs, (size_t)blob_bytes);
+}
+
+int tmvb_lda_exchange_mstep(tmvb_lda_t h)
+{
+    TMVB_CHECK_ARG(h != nullptr, "handle is NULL");
+    Shard &s = h->s;
+    Comm &c = h->comm;
+    TMVB_CHECK_ARG(c.connected, "tmvb_lda_comm_connect has not been called");
+    TMVB_CHECK_ARG(s.K_ld + 1 <= kCtlPartLen, "K too large for the exchange control block");
+    TMVB_CUDA(cudaSetDevice(s.device));
+    TMVB_CUDA(cudaEventRecord(s.ev[2], s.stream));
+    if (s.V > 0) {
+        LdaXchg x;
+        x.V = (int)s.V;
+        x.K = (int)s.K;
+        x.K_ld = s.K_ld;
+        x.rank = c.rank;
+        x.world = c.world;
+        x.want_elbo = h->elbo_valid ? 1 : 0;
+        x.n_small = s.K_ld + 2;
+        x.parity = (int)(c.calls & 1);
+        x.epoch = c.epoch;
+        const int nb = s.cur ^ 1;  // the buffer that becomes `beta`
+        for (int r = 0; r < kMaxPeers; r++) {
+            const bool ok = r < c.world;
+            x.stats[r] = ok ? (const float *)c.peer[0][r] : nullptr;
+            x.beta_new[r] = ok ? (float *)c.peer[1 + nb][r] : nullptr;
+            x.small[r] = ok ? (const double *)c.peer[3][r] : nullptr;
+            x.ctl[r] = ok ? c.peer[4][r] : nullptr;
+        }
+        x.my_stats = s.d_stats;
+        x.beta_old = s.d_beta[s.cur];
+        x.small_red = c.d_small_red;
+        x.local = h->d_local;
+        TMVB_CUDA(cudaMemsetAsync(c.d_ctl + 128, 0, 4, s.stream));  // grid barrier arrival counter
+        const int CH = s.K_ld / 4, RPP = 256 / CH;
+        const size_t smem = ((size_t)RPP * s.K_ld + s.K_ld) * 8;
+        const int rows = (int)((s.V + c.world - 1) / c.world);
+        int grid = std::min(s.n_sm, std::max(1, (rows + RPP - 1) / RPP));
+        void *args[] = {&x};
+        TMVB_CUDA(cudaLaunchCooperativeKernel((const void *)lda_exchange_mstep_kernel, dim3(grid), dim3(256), args, smem, s.stream));
+        s.st.kernel_launches++;
+        // the reduced small vector replaces the local one (peers read the local one only before their second barrier)
+        TMVB_CUDA(cudaMemcpyAsync(h->d_small, c.d_small_red, (s.K_ld + 2) * 8, cudaMemcpyDeviceToDevice, s.stream));
+        c.epoch += 3;
+        c.calls++;
+        s.cur ^= 1;  // beta_old <- beta ; beta <- new  (LDA.jl:122-123)
+    }
+    TMVB_CUDA(cudaEventRecord(s.ev[3], s.stream));
+    s.mstep_timed = true;
+    return 0;
+}
+
+int tmvb_lda_comm_status(tmvb_lda_t h, int *status)
+{
+    TMVB_CHECK_ARG(h && status, "NULL argument");
+    *status = 0;
+    if (!h->comm.d_ctl) return 0;
+    Shard &s = h->s;
+    TMVB_CUDA(cudaSetDevice(s.device));
+    unsigned st = 0;
+    TMVB_CUDA(cudaMemcpyAsync(&st, h->comm.d_ctl + 132, 4, cudaMemcpyDeviceToHost, s.stream));
+    TMVB_CUDA(cudaStreamSynchronize(s.stream));
+    *status = (int)st;
+    if (st) return fail(900 + (int)st, "peer exchange timed out (%s): a rank did not reach tmvb_lda_exchange_mstep", st == 1 ? "peer barrier" : "grid barrier");
+    return 0;
+}
+
 int tmvb_lda_get_elogtheta_sum(tmvb_lda_t h, double *out)
 {
     TMVB_CHECK_ARG(h && out, "NULL argument");
@@ -1178,10 +1415,18 @@ int tmvb_lda_elbo(tmvb_lda_t h, int mode, int64_t M_total, double *elbo_docs, do
     double *out = h->d_local + 2 * K_ld;
     TMVB_CUDA(cudaMemsetAsync(out, 0, 8, s.stream));
     if (s.M > 0) {
-        if (mode == 2)
-            lda_elbo_kernel<double><<<grid_for(s.M * 32, 128, s.n_sm), 128, 0, s.stream>>>(p, s.d_beta[s.cur ^ 1], lg_alpha_term(h->h_alpha), out);
-        else
-            lda_elbo_kernel<float><<<grid_for(s.M * 32, 128, s.n_sm), 128, 0, s.stream>>>(p, s.d_beta[s.cur ^ 1], lg_alpha_term(h->h_alpha), out);
+        const int grid = grid_for(s.M * 32, 128, s.n_sm);
+        const double lga = lg_alpha_term(h->h_alpha);
+        const float *bo = s.d_beta[s.cur ^ 1];
+#define TMVB_ELBO_LAUNCH(T, R) lda_elbo_kernel<T, R><<<grid, 128, 0, s.stream>>>(p, bo, lga, out)
+        if (mode == 2) {
+            if (K <= 32) TMVB_ELBO_LAUNCH(double, 1); else if (K <= 64) TMVB_ELBO_LAUNCH(double, 2);
+            else if (K <= 128) TMVB_ELBO_LAUNCH(double, 4); else TMVB_ELBO_LAUNCH(double, 8);
+        } else {
+            if (K <= 32) TMVB_ELBO_LAUNCH(float, 1); else if (K <= 64) TMVB_ELBO_LAUNCH(float, 2);
+            else if (K <= 128) TMVB_ELBO_LAUNCH(float, 4); else TMVB_ELBO_LAUNCH(float, 8);
+        }
+#undef TMVB_ELBO_LAUNCH
         TMVB_CUDA(cudaGetLastError());
         s.st.kernel_launches++;
     }

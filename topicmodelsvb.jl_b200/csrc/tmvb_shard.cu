@@ -303,12 +303,25 @@ int shard_set_corpus(Shard *s, const int64_t *N_cumsum, const int64_t *terms, co
     TMVB_CHECK_ARG(nnz >= 0, "N_cumsum must be nondecreasing");
     TMVB_CHECK_ARG(nnz == 0 || (terms != nullptr && counts != nullptr), "terms/counts are NULL");
 
+    // the token arrays do not depend on the document order: start their host -> device copies first so that they
+    // overlap the host-side sort below (the caller's arrays stay alive until the synchronize at the end of this call)
+    if (nnz > 0) {
+        TMVB_TRY(shard_scratch(s, (size_t)nnz * 16));
+        long long *t64 = (long long *)s->d_scratch, *c64 = t64 + nnz;
+        TMVB_CUDA(cudaMemcpyAsync(t64, terms, nnz * 8, cudaMemcpyHostToDevice, s->stream));
+        TMVB_CUDA(cudaMemcpyAsync(c64, counts, nnz * 8, cudaMemcpyHostToDevice, s->stream));
+        s->st.h2d_bytes += nnz * 16;
+    }
+
     // host: O(M) counting sort of the documents by length (descending, stable)
     std::vector<int> len(M);
     int maxlen = 0;
     for (int64_t d = 0; d < M; d++) {
         const int64_t l = N_cumsum[d + 1] - N_cumsum[d];
-        if (l < 0 || l > (1 << 30)) return fail(-1, "invalid argument: N_cumsum must be nondecreasing (document %lld)", (long long)d);
+        if (l < 0 || l > (1 << 30)) {
+            cudaStreamSynchronize(s->stream);  // the copies above still read the caller's arrays
+            return fail(-1, "invalid argument: N_cumsum must be nondecreasing (document %lld)", (long long)d);
+        }
         len[d] = (int)l;
         maxlen = std::max(maxlen, (int)l);
     }
@@ -326,7 +339,10 @@ int shard_set_corpus(Shard *s, const int64_t *N_cumsum, const int64_t *terms, co
         s->len_sorted[p] = len[d];
         dst_off[p + 1] = dst_off[p] + len[d];
     }
-    TMVB_TRY(plan_buckets(s, fixed_bytes));
+    if (int rc = plan_buckets(s, fixed_bytes)) {
+        cudaStreamSynchronize(s->stream);
+        return rc;
+    }
 
     const size_t nz = (size_t)std::max<int64_t>(nnz, 1);
     if (!s->d_doc_off) {
@@ -351,11 +367,7 @@ int shard_set_corpus(Shard *s, const int64_t *N_cumsum, const int64_t *terms, co
     }
     s->st.h2d_bytes += (M + 1) * 8 + M * 12;
     if (nnz > 0) {
-        TMVB_TRY(shard_scratch(s, (size_t)nnz * 16));
         long long *t64 = (long long *)s->d_scratch, *c64 = t64 + nnz;
-        TMVB_CUDA(cudaMemcpyAsync(t64, terms, nnz * 8, cudaMemcpyHostToDevice, s->stream));
-        TMVB_CUDA(cudaMemcpyAsync(c64, counts, nnz * 8, cudaMemcpyHostToDevice, s->stream));
-        s->st.h2d_bytes += nnz * 16;
         TMVB_CUDA(cudaMemsetAsync(s->d_counters + 63, 0, 4, s->stream));
         pack_corpus_kernel<<<grid_for(M * 32, 256, s->n_sm), 256, 0, s->stream>>>(t64, c64, s->d_src_off, s->d_doc_off, M, (int)s->V,
                                                                                  s->d_terms, s->d_counts, s->d_counters + 63);

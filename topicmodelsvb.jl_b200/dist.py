@@ -47,6 +47,45 @@ class Reducer:
             if n:
                 self.dist.all_reduce(self.view(ptr, n, typestr, device), op=self.dist.ReduceOp.SUM, group=self.group)
 
+    def all_gather_bytes(self, blob: bytes) -> list:
+        """Every rank's `blob` (same length on all ranks), in rank order."""
+        t = self.torch.frombuffer(bytearray(blob), dtype=self.torch.uint8)
+        nccl = self.dist.get_backend(self.group) == "nccl"
+        if nccl:
+            t = t.cuda()
+        out = [self.torch.empty_like(t) for _ in range(self.world)]
+        self.dist.all_gather(out, t, group=self.group)
+        return [bytes(o.cpu().numpy().tobytes()) for o in out]
+
+    def all_agree(self, ok: bool) -> bool:
+        """True iff `ok` on every rank."""
+        t = self.torch.tensor([1 if ok else 0], dtype=self.torch.int32)
+        if self.dist.get_backend(self.group) == "nccl":
+            t = t.cuda()
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MIN, group=self.group)
+        return bool(int(t.item()))
+
+    def connect_peers(self, export_fn, connect_fn, blob_bytes: int) -> bool:
+        """The handshake of the peer-memory exchange (tmvb_*_comm_export / _comm_connect): all-gather the IPC handle
+        blobs, map the peers.  Returns False (on every rank) when any rank cannot map its peers -- the caller then
+        keeps the NCCL all-reduce path."""
+        import ctypes as C
+
+        ok, blobs = True, None
+        try:
+            buf = C.create_string_buffer(blob_bytes)
+            export_fn(buf, blob_bytes)
+            blobs = self.all_gather_bytes(buf.raw)
+        except Exception:
+            ok = False
+            blobs = self.all_gather_bytes(bytes(blob_bytes)) if blobs is None else blobs
+        if ok:
+            try:
+                connect_fn(self.rank, self.world, b"".join(blobs), blob_bytes)
+            except Exception:
+                ok = False
+        return self.all_agree(ok)
+
     def allreduce_host(self, x: float) -> float:
         t = self.torch.tensor([x], dtype=self.torch.float64)
         if self.dist.get_backend(self.group) == "nccl":
