@@ -690,87 +690,100 @@ __device__ __forceinline__ double warp_min_d(double v)
     return v;
 }
 
-// update_alpha! (LDA.jl:97-118): interior-point Newton with log barrier, fp64, one warp (lane l owns alpha_{l+32r});
-// then, when the last E-step accumulated ELBO partials, the whole ELBO is assembled here (see tmvb_lda_elbo) so that
-// an outer iteration needs a single 8-byte read-back instead of three host round trips.
+// Block-wide fp64 reductions for lda_alpha_kernel (blockDim.x = 32 * nw, nw <= 9): warp shuffles, then one shared-memory
+// round; every thread receives the result.  `red` is double[3][16], two barriers per call.
+__device__ __forceinline__ void block_sum3(double &a, double &b, double &c, double (*red)[16])
+{
+    a = warp_sum_d(a);
+    b = warp_sum_d(b);
+    c = warp_sum_d(c);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    if (nw == 1) return;
+    __syncthreads();
+    if (lane == 0) {
+        red[0][warp] = a;
+        red[1][warp] = b;
+        red[2][warp] = c;
+    }
+    __syncthreads();
+    a = b = c = 0.0;
+    for (int w = 0; w < nw; w++) {
+        a += red[0][w];
+        b += red[1][w];
+        c += red[2][w];
+    }
+}
+__device__ __forceinline__ double block_min(double v, double (*red)[16])
+{
+    v = warp_min_d(v);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    if (nw == 1) return v;
+    __syncthreads();
+    if (lane == 0) red[0][warp] = v;
+    __syncthreads();
+    v = red[0][0];
+    for (int w = 1; w < nw; w++) v = fmin(v, red[0][w]);
+    return v;
+}
+
+// update_alpha! (LDA.jl:97-118): interior-point Newton with log barrier in fp64.  One CTA: thread i < K owns alpha_i, thread K
+// owns sum(alpha), so that every Newton step costs ONE digamma/trigamma evaluation per thread (the one-warp version
+// spent 57 us per outer iteration on three serial evaluations per lane).  Then, when the last E-step accumulated ELBO
+// partials, the whole ELBO is assembled here (see tmvb_lda_elbo) so that an outer iteration needs a single 8-byte
+// read-back instead of three host round trips.
 //   small = [sum_d Elogtheta_d (K_ld) | per-document ELBO terms | sweeps], local = [rowsum (K_ld) | elbo_w]
 __global__ void lda_alpha_kernel(double *__restrict__ alpha64, float *__restrict__ alpha32, const double *__restrict__ small,
                                  const double *__restrict__ local, int K, int K_ld, double Md, int niter, double ntol, int want_elbo,
                                  double *__restrict__ result)
 {
-    constexpr int RM = 8;
-    const int lane = threadIdx.x;
-    double a[RM], a_estep[RM], Es[RM], grad[RM], hinv[RM], pd[RM];
-#pragma unroll
-    for (int r = 0; r < RM; r++) {
-        const int i = lane + 32 * r;
-        a[r] = (i < K) ? alpha64[i] : 1.0;
-        a_estep[r] = a[r];
-        Es[r] = (i < K) ? small[i] : 0.0;
-    }
+    __shared__ double red[3][16];
+    __shared__ double bc[2];
+    const int tid = threadIdx.x;
+    const bool is_topic = tid < K, is_sum = tid == K;
+    double a = is_topic ? alpha64[tid] : 1.0;
+    const double a_estep = a, Es = is_topic ? small[tid] : 0.0;
     double nu = (double)K;
     for (int it = 0; it < niter; it++) {
-        double a0 = 0.0;
-#pragma unroll
-        for (int r = 0; r < RM; r++)
-            if (lane + 32 * r < K) a0 += a[r];
-        a0 = warp_sum_d(a0);
-        double dg0, tg0;
-        d_psi_tri(a0, dg0, tg0);
-        double gh = 0.0, hs = 0.0, gn = 0.0;
-#pragma unroll
-        for (int r = 0; r < RM; r++) {
-            grad[r] = hinv[r] = 0.0;
-            if (lane + 32 * r < K) {
-                double dg, tg;
-                d_psi_tri(a[r], dg, tg);
-                grad[r] = nu / a[r] + Md * (dg0 - dg) + Es[r];
-                hinv[r] = -1.0 / (Md * tg + nu / (a[r] * a[r]));
-                gh += grad[r] * hinv[r];
-                hs += hinv[r];
-                gn += grad[r] * grad[r];
-            }
+        double a0 = is_topic ? a : 0.0, u1 = 0.0, u2 = 0.0;
+        block_sum3(a0, u1, u2, red);
+        double dg = 0.0, tg = 1.0;
+        if (is_topic || is_sum) d_psi_tri(is_topic ? a : a0, dg, tg);
+        __syncthreads();
+        if (is_sum) {
+            bc[0] = dg;
+            bc[1] = tg;
         }
-        gh = warp_sum_d(gh);
-        hs = warp_sum_d(hs);
-        gn = warp_sum_d(gn);
+        __syncthreads();
+        const double dg0 = bc[0], tg0 = bc[1];
+        const double grad = is_topic ? nu / a + Md * (dg0 - dg) + Es : 0.0;
+        const double hinv = is_topic ? -1.0 / (Md * tg + nu / (a * a)) : 0.0;
+        double gh = grad * hinv, hs = hinv, gn = grad * grad;
+        block_sum3(gh, hs, gn, red);
         const double z = gh / (1.0 / (Md * tg0) + hs);
+        const double pd = (grad - z) * hinv;
         double rho = 1.0;
-#pragma unroll
-        for (int r = 0; r < RM; r++) pd[r] = (grad[r] - z) * hinv[r];
         for (;;) {
-            double mn = 1e300;
-#pragma unroll
-            for (int r = 0; r < RM; r++)
-                if (lane + 32 * r < K) mn = fmin(mn, a[r] - rho * pd[r]);
-            mn = warp_min_d(mn);
+            const double mn = block_min(is_topic ? a - rho * pd : 1e300, red);
             if (!(mn < 0.0)) break;
             rho *= 0.5;
         }
-#pragma unroll
-        for (int r = 0; r < RM; r++)  // @finite alpha -= rho * p  (macros.jl:52-54)
-            if (lane + 32 * r < K) a[r] = copysign(fmin(fabs(a[r] - rho * pd[r]), 1.7976931348623157e308), a[r]);
+        // @finite alpha -= rho * p  (macros.jl:52-54)
+        if (is_topic) a = copysign(fmin(fabs(a - rho * pd), 1.7976931348623157e308), a);
         if ((rho * sqrt(gn) < ntol) && (nu / (double)K < ntol)) break;
         nu *= 0.5;
     }
     double a0 = 0.0, sl = 0.0, lin = 0.0;
-#pragma unroll
-    for (int r = 0; r < RM; r++) {
-        const int i = lane + 32 * r;
-        if (i < K) {
-            a[r] += TMVB_EPS_D;  // @positive model.alpha
-            alpha64[i] = a[r];
-            alpha32[i] = fmaxf((float)a[r], 1.1754944e-38f);
-            a0 += a[r];
-            sl += lgamma(a[r]);
-            lin += (a[r] - a_estep[r] - TMVB_EPS_D) * Es[r];
-        }
+    if (is_topic) {
+        a += TMVB_EPS_D;  // @positive model.alpha
+        alpha64[tid] = a;
+        alpha32[tid] = fmaxf((float)a, 1.1754944e-38f);
+        a0 = a;
+        sl = lgamma(a);
+        lin = (a - a_estep - TMVB_EPS_D) * Es;
     }
     if (want_elbo) {
-        a0 = warp_sum_d(a0);
-        sl = warp_sum_d(sl);
-        lin = warp_sum_d(lin);
-        if (lane == 0) result[0] = small[K_ld] + Md * (lgamma(a0) - sl) + lin + local[K_ld];
+        block_sum3(a0, sl, lin, red);
+        if (tid == 0) result[0] = small[K_ld] + Md * (lgamma(a0) - sl) + lin + local[K_ld];
     }
 }
 
@@ -1375,7 +1388,7 @@ int tmvb_lda_update_alpha(tmvb_lda_t h, int64_t M_total, int niter, double ntol,
     TMVB_CUDA(cudaSetDevice(s.device));
     // LDA.jl:97-118 on the device in fp64 (one warp), fused with the ELBO assembly; asynchronous unless alpha_out is given
     double *result = h->d_local + 2 * s.K_ld + 1;
-    lda_alpha_kernel<<<1, 32, 0, s.stream>>>(h->d_alpha64, h->d_alpha, h->d_small, h->d_local, (int)s.K, s.K_ld, (double)M_total, niter, ntol,
+    lda_alpha_kernel<<<1, 32 * (((int)s.K + 1 + 31) / 32), 0, s.stream>>>(h->d_alpha64, h->d_alpha, h->d_small, h->d_local, (int)s.K, s.K_ld, (double)M_total, niter, ntol,
                                             h->elbo_valid ? 1 : 0, result);
     TMVB_CUDA(cudaGetLastError());
     s.st.kernel_launches++;
