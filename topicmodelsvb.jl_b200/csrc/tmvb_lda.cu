@@ -108,20 +108,22 @@ __global__ void __launch_bounds__(32 * W, W == 2 ? 8 : 1) lda_estep_kernel(const
     if (p.stage_bulk && tid == 0) mbar_init(mbar, 1);
     cta_sync<W>();
 
+    // documents per draw: kDocChunk, fewer when the launch has less than ~4 draws per CTA (multi-GPU shards: balance over atomics)
+    const int chunk = max(1, min(kDocChunk, (doc_end - doc_begin) / (4 * (int)gridDim.x)));
     int d_next = 0, d_lim = 0;
     for (;;) {
         // documents are drawn from the bucket's work counter kDocChunk at a time: one same-address atomic per document
         // serialises in L2 (128 804 of them cost ~0.4 ms of a 2.4 ms E-step)
         if (d_next >= d_lim) {
             if (W == 1) {
-                if (lane == 0) d_next = doc_begin + atomicAdd(counter, kDocChunk);
+                if (lane == 0) d_next = doc_begin + atomicAdd(counter, chunk);
                 d_next = __shfl_sync(0xffffffffu, d_next, 0);
             } else {
-                if (tid == 0) *next_s = doc_begin + atomicAdd(counter, kDocChunk);
+                if (tid == 0) *next_s = doc_begin + atomicAdd(counter, chunk);
                 __syncthreads();
                 d_next = *next_s;
             }
-            d_lim = min(d_next + kDocChunk, doc_end);
+            d_lim = min(d_next + chunk, doc_end);
         }
         if (d_next >= doc_end) break;
         const int d = d_next++;
@@ -360,7 +362,7 @@ __global__ void __launch_bounds__(32 * W, W == 2 ? 8 : 1) lda_estep_kernel(const
 static size_t lda_reg_smem(int RS, int lpt, int W) { return 128 + (size_t)W * (32 / lpt) * RS * 4 + (size_t)W * RS * 4 + (size_t)RS * 4; }
 
 // resident CTAs per SM the register allocation is held to (the tile alone is 4 CPL NR registers per thread)
-constexpr int lda_reg_min_ctas(int W, int NR) { return W == 1 ? (NR <= 2 ? 12 : 10) : W == 2 ? (NR <= 3 ? 6 : 5) : (NR <= 3 ? 3 : 2); }
+constexpr int lda_reg_min_ctas(int W, int NR) { return W == 1 ? (NR <= 2 ? 12 : 10) : W == 2 ? (NR <= 3 ? 6 : 5) : W == 4 ? (NR <= 3 ? 3 : 2) : 1; }
 
 template <int LPT, int CPL, int W, int NR, bool ELBO>
 __global__ void __launch_bounds__(32 * W, lda_reg_min_ctas(W, NR)) lda_estep_reg_kernel(const LdaDev p, int doc_begin, int doc_end, int cap, int cap2, int *counter)
@@ -375,8 +377,8 @@ __global__ void __launch_bounds__(32 * W, lda_reg_min_ctas(W, NR)) lda_estep_reg
     (void)cap2;
     int *next_s = reinterpret_cast<int *>(smem_raw + 16);
     int *flag_s = reinterpret_cast<int *>(smem_raw + 20);
-    float *csum_s = reinterpret_cast<float *>(smem_raw + 32);  // [W]
-    float *tsum_s = reinterpret_cast<float *>(smem_raw + 48);  // [W]
+    float *csum_s = reinterpret_cast<float *>(smem_raw + 32);  // [W <= 8]
+    float *tsum_s = reinterpret_cast<float *>(smem_raw + 64);  // [W <= 8]
     float *gs = reinterpret_cast<float *>(smem_raw + 128);     // [W][S][RS]
     float *xs = gs + (size_t)W * S * RS;                       // [W][RS]
     float *e_s = xs + (size_t)W * RS;                          // [RS]
@@ -392,19 +394,21 @@ __global__ void __launch_bounds__(32 * W, lda_reg_min_ctas(W, NR)) lda_estep_reg
     double esum0 = 0.0, esum1 = 0.0, elbo_thr = 0.0;
     unsigned long long sweeps_thr = 0;
 
+    // documents per draw: kDocChunk, fewer when the launch has less than ~4 draws per CTA (multi-GPU shards: balance over atomics)
+    const int chunk = max(1, min(kDocChunk, (doc_end - doc_begin) / (4 * (int)gridDim.x)));
     int d_next = 0, d_lim = 0;
     long long o_cur = 0, o_end = 0;
     for (;;) {
         if (d_next >= d_lim) {  // kDocChunk documents per draw from the work counter (see lda_estep_kernel)
             if (W == 1) {
-                if (lane == 0) d_next = doc_begin + atomicAdd(counter, kDocChunk);
+                if (lane == 0) d_next = doc_begin + atomicAdd(counter, chunk);
                 d_next = __shfl_sync(0xffffffffu, d_next, 0);
             } else {
-                if (tid == 0) *next_s = doc_begin + atomicAdd(counter, kDocChunk);
+                if (tid == 0) *next_s = doc_begin + atomicAdd(counter, chunk);
                 __syncthreads();
                 d_next = *next_s;
             }
-            d_lim = min(d_next + kDocChunk, doc_end);
+            d_lim = min(d_next + chunk, doc_end);
             if (d_next < doc_end) {
                 o_cur = p.doc_off[d_next];
                 o_end = p.doc_off[d_next + 1];
@@ -946,10 +950,13 @@ __global__ void __launch_bounds__(256) lda_exchange_mstep_kernel(const LdaXchg x
 
 typedef void (*LdaEstepFn)(const LdaDev, int, int, int, int, int *);
 // register-resident variants: (warps per document, rounds per warp), by descending capacity W * NR * S tokens
-constexpr int kNumRegVariants = 6;
-static const int kRegVariant[kNumRegVariants][2] = {{4, 4}, {4, 3}, {2, 4}, {2, 3}, {1, 4}, {1, 2}};
+// (the 8-warp variant exists for latency, not throughput: one warp would spend ~0.4 ms on a 400-token document, which
+// is the whole E-step of an 8-GPU run)
+constexpr int kNumRegVariants = 7;
+static const int kRegVariant[kNumRegVariants][2] = {{8, 4}, {4, 4}, {4, 3}, {2, 4}, {2, 3}, {1, 4}, {1, 2}};
 #define TMVB_LDA_REG_ROW(L, C, E)                                                                                              \
-    {(LdaEstepFn)lda_estep_reg_kernel<L, C, 4, 4, E>, (LdaEstepFn)lda_estep_reg_kernel<L, C, 4, 3, E>,                         \
+    {(LdaEstepFn)lda_estep_reg_kernel<L, C, 8, 4, E>,                                                                          \
+     (LdaEstepFn)lda_estep_reg_kernel<L, C, 4, 4, E>, (LdaEstepFn)lda_estep_reg_kernel<L, C, 4, 3, E>,                         \
      (LdaEstepFn)lda_estep_reg_kernel<L, C, 2, 4, E>, (LdaEstepFn)lda_estep_reg_kernel<L, C, 2, 3, E>,                         \
      (LdaEstepFn)lda_estep_reg_kernel<L, C, 1, 4, E>, (LdaEstepFn)lda_estep_reg_kernel<L, C, 1, 2, E>}
 // lane layouts with a register-resident instantiation: K_ld = 56 (K = 49..56, e.g. the K = 50 NSF configuration) and K_ld = 32
