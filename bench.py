@@ -2,7 +2,8 @@
 """bench.py -- LDA K=50 on NSF (BASELINE.json configs[1]): full VI iterations on 1..N B200s.
 
 A "step" is ONE outer VI iteration over the whole corpus: fused E-step (all inner sweeps of every
-document + scatter of the K x V statistics) -> [NCCL all-reduce when N > 1] -> M-step normalise ->
+document + scatter of the K x V statistics) -> M-step normalise (N > 1: one fused peer-memory kernel that
+reduce-scatters the statistics over NVLink, normalises and all-gathers; NCCL all-reduce as fallback) ->
 alpha Newton update -> ELBO.  Steps cycle through iterations 1..10 of a training run started from
 the initial state (the protocol of the reference's published "10 iterations" chart, plots.R:4);
 the re-initialisation every 10 steps is outside the timed region.
@@ -239,7 +240,7 @@ def run_ours(args):
     tpath = os.path.join(ROOT, "profiles", "r1_lda_estep_traffic.json")
     if os.path.exists(tpath):
         traffic = json.load(open(tpath)).get("dram_bytes_per_estep")
-    roofline = {"bound": "hbm", "kernel": "lda_estep_kernel (all length buckets of one E-step)", "achieved": achieved,
+    roofline = {"bound": "hbm", "kernel": "lda_estep_reg_kernel / lda_estep_kernel (all length-bucket launches of one E-step)", "achieved": achieved,
                 "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": est_bytes_total // world, "kernel_ms": est_ms,
                 "share_of_step": est_ms / ms_per_step}
@@ -252,7 +253,10 @@ def run_ours(args):
         "config": {"workload": "gpuLDA K=50 on NSF (128804 docs x 25319 vocab), doc-sharded d % N",
                    "M": int(M_total), "V": int(full.V), "K": K, "nnz": int(nnz_total), "viter": VITER, "vtol": vtol,
                    "step": "one outer VI iteration; steps cycle through iterations 1..%d from the initial state" % CYCLE,
-                   "l2": "256 MiB buffer written between timed steps (L2 flushed)", "parallelism": "dp%d" % world},
+                   "l2": "256 MiB buffer written between timed steps (L2 flushed)", "parallelism": "dp%d" % world,
+                   "exchange": ("none (one GPU)" if world == 1 else
+                                "fused peer-memory kernel (tmvb_lda_exchange_mstep: reduce-scatter + normalise + all-gather over NVLink)"
+                                if getattr(model, "_p2p", False) else "NCCL all-reduce + normalisation kernels")},
         "vi_iterations_per_sec": 1e3 / ms_per_step,
         "estep_docs_per_sec": M_total / (est_ms * 1e-3),
         "sweeps_per_doc": float(np.mean(sweeps)) / (M_total if world > 1 else shard.M),

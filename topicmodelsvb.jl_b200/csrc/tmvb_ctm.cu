@@ -562,6 +562,7 @@ CtmDev ctm_view(tmvb_ctm_t h)
 {
     Shard &s = h->s;
     CtmDev p;
+    memset(&p, 0, sizeof(p));  // the struct is also the key of the captured launch graph: no indeterminate padding
     p.K = (int)s.K;
     p.K_ld = s.K_ld;
     p.V = (int)s.V;
@@ -759,7 +760,7 @@ int tmvb_ctm_estep(tmvb_ctm_t h, int niter, float ntol, int viter, float vtol, i
     TMVB_CUDA(cudaEventRecord(s.ev[0], s.stream));
     TMVB_CUDA(cudaMemsetAsync(h->d_small, 0, h->n_small * 8, s.stream));
     const void *fns[2] = {(const void *)ctm_fn(s.layout, want_elbo != 0), (const void *)ctm_fn(s.layout, want_elbo != 0)};
-    TMVB_TRY(shard_launch(&s, pick_by_warps, fns, &p));
+    TMVB_TRY(shard_launch(&s, pick_by_warps, fns, &p, sizeof(p)));
     if (s.M > 0) {
         const int grid = (int)std::min<int64_t>((s.M + 31) / 32, (int64_t)s.n_sm * 4);
         ctm_moments_kernel<<<grid, 256, 32 * s.K_ld * 4, s.stream>>>(h->d_lambda, h->d_vsq, s.M, (int)s.K, s.K_ld, h->d_small + 2);

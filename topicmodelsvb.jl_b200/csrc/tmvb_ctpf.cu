@@ -511,6 +511,7 @@ CtpfDev ctpf_view(tmvb_ctpf_t h)
 {
     Shard &s = h->s;
     CtpfDev p;
+    memset(&p, 0, sizeof(p));  // the struct is also the key of the captured launch graph: no indeterminate padding
     p.K = (int)s.K;
     p.K_ld = s.K_ld;
     p.V = (int)s.V;
@@ -779,7 +780,7 @@ int tmvb_ctpf_estep(tmvb_ctpf_t h, int viter, float vtol, int want_elbo)
     TMVB_CUDA(cudaEventRecord(s.ev[0], s.stream));
     TMVB_CUDA(cudaMemsetAsync(h->d_small, 0, (2 * s.K_ld + 2) * 8, s.stream));
     const void *fns[2] = {(const void *)kCtpfEstep[s.layout][want_elbo != 0], (const void *)kCtpfEstep[s.layout][want_elbo != 0]};
-    TMVB_TRY(shard_launch(&s, pick_by_warps, fns, &p));
+    TMVB_TRY(shard_launch(&s, pick_by_warps, fns, &p, sizeof(p)));
     TMVB_CUDA(cudaEventRecord(s.ev[1], s.stream));
     s.estep_timed = true;
     h->elbo_valid = (want_elbo != 0);

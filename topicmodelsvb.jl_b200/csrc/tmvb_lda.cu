@@ -1015,6 +1015,7 @@ LdaDev dev_view(tmvb_lda_t h)
 {
     Shard &s = h->s;
     LdaDev p;
+    memset(&p, 0, sizeof(p));  // the struct is also the key of the captured launch graph: no indeterminate padding
     p.K = (int)s.K;
     p.K_ld = s.K_ld;
     p.V = (int)s.V;
@@ -1263,7 +1264,7 @@ int tmvb_lda_estep(tmvb_lda_t h, int viter, float vtol, int want_elbo)
     pk.tile[1] = (const void *)kLdaEstep[1][s.layout][want_elbo != 0];
     pk.reg = lda_reg_layout(s.lpt, s.cpl);
     pk.elbo = want_elbo != 0;
-    TMVB_TRY(shard_launch(&s, lda_pick, &pk, &p));
+    TMVB_TRY(shard_launch(&s, lda_pick, &pk, &p, sizeof(p)));
     TMVB_CUDA(cudaEventRecord(s.ev[1], s.stream));
     s.estep_timed = true;
     h->elbo_valid = (want_elbo != 0);

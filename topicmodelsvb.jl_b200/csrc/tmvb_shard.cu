@@ -3,6 +3,7 @@
 #include <math.h>
 #include <stdlib.h>
 #include <string.h>
+#include <string>
 
 #include "tmvb_shard.cuh"
 
@@ -209,6 +210,7 @@ int shard_create(Shard *s, int64_t K, int64_t M, int64_t V, int device, void *st
     TMVB_CUDA(cudaMallocHost((void **)&s->h_pinned, pinned_doubles * 8));
     for (auto &e : s->ev) TMVB_CUDA(cudaEventCreate(&e));
     s->n_streams = std::min(1 + Shard::kAux, std::max(1, env_int("TMVB_STREAMS", 4)));
+    s->use_graphs = env_int("TMVB_GRAPH", 1) != 0;
     for (int a = 0; a + 1 < s->n_streams; a++) {
         TMVB_CUDA(cudaStreamCreateWithFlags(&s->aux[a], cudaStreamNonBlocking));
         TMVB_CUDA(cudaEventCreateWithFlags(&s->ev_join[a], cudaEventDisableTiming));
@@ -221,6 +223,7 @@ void shard_free(Shard *s)
 {
     cudaSetDevice(s->device);
     if (s->stream) cudaStreamSynchronize(s->stream);
+    shard_drop_graphs(s);
     cudaFree(s->d_doc_off);
     cudaFree(s->d_src_off);
     cudaFree(s->d_terms);
@@ -428,7 +431,8 @@ int shard_download_rows(Shard *s, const float *d_src, float *host, int64_t rows,
 
 const void *pick_by_warps(const Bucket &b, const void *ctx) { return static_cast<const void *const *>(ctx)[b.warps - 1]; }
 
-int shard_launch(Shard *s, BucketKernelFn pick, const void *ctx, void *dev_struct)
+// the launches of one E-step, enqueued on s->stream and its auxiliary streams (fork / join through events)
+static int launch_buckets(Shard *s, BucketKernelFn pick, const void *ctx, void *dev_struct)
 {
     TMVB_CUDA(cudaMemsetAsync(s->d_counters, 0, kMaxBuckets * 4, s->stream));
     const int ns = (s->buckets.size() > 1) ? s->n_streams : 1;
@@ -439,23 +443,77 @@ int shard_launch(Shard *s, BucketKernelFn pick, const void *ctx, void *dev_struc
     for (size_t bi = 0; bi < s->buckets.size(); bi++) {
         Bucket &b = s->buckets[bi];
         const void *fn = pick(b, ctx);
-        const int threads = 32 * b.warps;
-        if (b.grid == 0) {
-            int occ = 0;
-            TMVB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, threads, b.smem));
-            if (occ < 1) return fail(-4, "internal: E-step kernel does not fit (cap=%d warps=%d smem=%zu)", b.cap, b.warps, b.smem);
-            b.grid = std::min(b.doc_end - b.doc_begin, occ * s->n_sm);
-        }
         int *counter = s->d_counters + bi;
         void *args[] = {dev_struct, (void *)&b.doc_begin, (void *)&b.doc_end, (void *)&b.cap, (void *)&b.cap2, (void *)&counter};
         cudaStream_t st = (bi % ns == 0) ? s->stream : s->aux[bi % ns - 1];
-        TMVB_CUDA(cudaLaunchKernel(fn, dim3(b.grid), dim3(threads), args, b.smem, st));
-        s->st.kernel_launches++;
+        TMVB_CUDA(cudaLaunchKernel(fn, dim3(b.grid), dim3(32 * b.warps), args, b.smem, st));
     }
     for (int a = 0; a + 1 < ns; a++) {
         TMVB_CUDA(cudaEventRecord(s->ev_join[a], s->aux[a]));
         TMVB_CUDA(cudaStreamWaitEvent(s->stream, s->ev_join[a], 0));
     }
+    return 0;
+}
+
+void shard_drop_graphs(Shard *s)
+{
+    for (auto &g : s->graphs)
+        if (g.exec) cudaGraphExecDestroy(g.exec);
+    s->graphs.clear();
+}
+
+// One E-step is up to ~10 short launches on 4 streams; on a multi-GPU shard each lasts 20-130 us, so the ~100 us the
+// host needs to issue them (8 processes competing for the host cores) would bound the E-step.  The launch sequence is
+// therefore captured once per distinct (kernel set, by-value parameter block) into a CUDA graph and replayed with a
+// single cudaGraphLaunch; the by-value struct changes only with beta's double-buffer parity, want_elbo and the
+// train! keywords, so a handful of graphs serves a whole training run.  TMVB_GRAPH=0 disables the capture.
+int shard_launch(Shard *s, BucketKernelFn pick, const void *ctx, void *dev_struct, size_t dev_struct_bytes)
+{
+    if (s->buckets.empty()) return 0;
+    std::string key((const char *)dev_struct, dev_struct_bytes);
+    for (Bucket &b : s->buckets) {
+        const void *fn = pick(b, ctx);
+        if (!fn) return fail(-4, "internal: no E-step kernel for a launch bucket (warps=%d nr=%d)", b.warps, b.nr);
+        if (b.grid == 0) {
+            int occ = 0;
+            TMVB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, 32 * b.warps, b.smem));
+            if (occ < 1) return fail(-4, "internal: E-step kernel does not fit (cap=%d warps=%d smem=%zu)", b.cap, b.warps, b.smem);
+            b.grid = std::min(b.doc_end - b.doc_begin, occ * s->n_sm);
+        }
+        // the launch geometry is part of the key, so a re-planned corpus never replays a stale graph
+        const long long geo[8] = {(long long)(size_t)fn, b.doc_begin, b.doc_end, b.cap, b.cap2, b.grid, (long long)b.smem, b.warps};
+        key.append((const char *)geo, sizeof(geo));
+    }
+    s->st.kernel_launches += (int64_t)s->buckets.size();
+    if (!s->use_graphs) return launch_buckets(s, pick, ctx, dev_struct);
+
+    for (auto &g : s->graphs)
+        if (g.key == key) {
+            TMVB_CUDA(cudaGraphLaunch(g.exec, s->stream));
+            return 0;
+        }
+    if (s->graphs.size() >= 16) shard_drop_graphs(s);
+    cudaGraph_t graph = nullptr;
+    TMVB_CUDA(cudaStreamBeginCapture(s->stream, cudaStreamCaptureModeThreadLocal));
+    const int rc = launch_buckets(s, pick, ctx, dev_struct);
+    const cudaError_t e = cudaStreamEndCapture(s->stream, &graph);
+    if (rc != 0 || e != cudaSuccess || !graph) {
+        if (graph) cudaGraphDestroy(graph);
+        cudaGetLastError();
+        s->use_graphs = false;  // capture is not possible here (e.g. the caller's stream is already capturing): launch directly
+        return launch_buckets(s, pick, ctx, dev_struct);
+    }
+    Shard::LaunchGraph lg;
+    lg.key = key;
+    const cudaError_t ei = cudaGraphInstantiate(&lg.exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (ei != cudaSuccess) {
+        cudaGetLastError();
+        s->use_graphs = false;
+        return launch_buckets(s, pick, ctx, dev_struct);
+    }
+    s->graphs.push_back(lg);
+    TMVB_CUDA(cudaGraphLaunch(lg.exec, s->stream));
     return 0;
 }
 

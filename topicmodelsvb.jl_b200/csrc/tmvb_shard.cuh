@@ -2,6 +2,7 @@
 // on one device (CSR re-layout, length buckets, topic-word table + statistics, staging, streams, counters).
 #pragma once
 
+#include <string>
 #include <vector>
 
 #include "tmvb_estep.cuh"
@@ -37,6 +38,13 @@ struct Shard {
     float *d_counts = nullptr;
     std::vector<int> h_perm, len_sorted;
     std::vector<Bucket> buckets;
+    // captured launch sequences of one E-step (see shard_launch), keyed by kernel set + by-value parameter block
+    struct LaunchGraph {
+        std::string key;
+        cudaGraphExec_t exec = nullptr;
+    };
+    std::vector<LaunchGraph> graphs;
+    bool use_graphs = true;
 
     // topic-word table (double buffered: [cur] current, [cur^1] previous) and its sufficient statistics
     float *d_beta[2] = {nullptr, nullptr}, *d_stats = nullptr;
@@ -72,7 +80,8 @@ int shard_validation(Shard *s, int *mask);
 // launch an E-step kernel `fn(Dev, doc_begin, doc_end, cap, cap2, counter)` over every bucket; pick(bucket, ctx) returns the
 // instantiation for the bucket's (warps, nr)
 typedef const void *(*BucketKernelFn)(const Bucket &b, const void *ctx);
-int shard_launch(Shard *s, BucketKernelFn pick, const void *ctx, void *dev_struct);
+int shard_launch(Shard *s, BucketKernelFn pick, const void *ctx, void *dev_struct, size_t dev_struct_bytes);
+void shard_drop_graphs(Shard *s);
 // pick for kernels that only come in "warps per document" flavours: ctx = const void *const fn_by_warps[]
 const void *pick_by_warps(const Bucket &b, const void *ctx);
 // beta_new = stats ./ rowsum ; stats <- 0 ; [elbo_w = sum stats ln(beta_new + eps)].  d_acc: double[2*K_ld] (rowsum | elbo_w)
