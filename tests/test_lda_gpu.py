@@ -64,7 +64,8 @@ def test_sweep_counts_match(tm, orc):
 
 
 def test_fused_elbo_equals_standalone(tm, orc):
-    """mode 0 (partials fused into the E-step/M-step) == mode 1 (update_elbo! restated, fp64 on device)."""
+    """mode 0 (partials fused into the E-step/M-step) == mode 1 (one table-assisted pass over the device state)
+    == mode 2 (update_elbo!, LDA.jl:50-93, restated literally in fp64 on the device)."""
     c = tm.synth.gencorp_lda(M=200, V=600, K=6, seed=5)
     K = 10
     model = tm.gpuLDA(tm.Corpus.from_csr(c), K, seed=11)
@@ -75,7 +76,9 @@ def test_fused_elbo_equals_standalone(tm, orc):
         model.update_alpha(1000, 1.0 / K**2)
         e0 = model.update_elbo(0)
         e1 = model.update_elbo(1)
-        assert abs(e0 - e1) <= 1e-6 * abs(e1), (it, e0, e1)
+        e2 = model.update_elbo(2)
+        assert abs(e0 - e2) <= 1e-6 * abs(e2), (it, e0, e2)
+        assert abs(e1 - e2) <= 1e-6 * abs(e2), (it, e1, e2)
 
 
 def test_ragged_and_edge_documents(tm, orc):

@@ -694,6 +694,87 @@ __device__ __forceinline__ double warp_min_d(double v)
     return v;
 }
 
+// update_elbo! for an arbitrary device state in one cheap pass (tmvb_lda_elbo mode 1, the `update_elbo!` at the top of
+// train!, gpuLDA.jl:353).  Same expectations as lda_elbo_kernel, with the two logarithms per (token, topic) moved into a
+// K x V table:  ln(beta_i,w + eps) - ln u_ni = D[w][i] - Elogtheta_old_i,  D = ln(beta + eps) - ln(beta_old + eps),
+// exact up to terms weighted by phi_ni ~ eps / s_n (u_ni = eps + beta_old_i,w e_i).  Per token: two FMA passes over the
+// row and one logarithm.  lda_elbo_kernel<double> (mode 2) stays the literal restatement the tests compare against.
+__global__ void lda_logratio_kernel(const float *__restrict__ beta, const float *__restrict__ beta_old, float *__restrict__ D, long long n,
+                                    int K, int K_ld)
+{
+    for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < n; q += (long long)gridDim.x * blockDim.x) {
+        const int i = (int)(q % K_ld);
+        D[q] = (i < K) ? logf(beta[q] + TMVB_EPS) - logf(beta_old[q] + TMVB_EPS) : 0.0f;
+    }
+}
+
+template <int RM>
+__global__ void lda_elbo_fast_kernel(const LdaDev p, const float *__restrict__ beta_old, const float *__restrict__ D, double lg_alpha_term,
+                                     double *out)
+{
+    const int lane = threadIdx.x & 31;
+    const int wpb = blockDim.x >> 5;
+    double acc = 0.0;
+    for (long long d = (long long)blockIdx.x * wpb + (threadIdx.x >> 5); d < p.M; d += (long long)gridDim.x * wpb) {
+        const long long o = p.doc_off[d];
+        const int Nd = (int)(p.doc_off[d + 1] - o);
+        const float *En = p.Elogtheta + d * p.K_ld, *Eo = p.Elogtheta_old + d * p.K_ld, *gm = p.gamma + d * p.K_ld;
+        double dacc = 0.0, g0 = 0.0;
+        float e_r[RM], dE_r[RM];
+#pragma unroll
+        for (int r = 0; r < RM; r++) {
+            const int i = lane + 32 * r;
+            e_r[r] = dE_r[r] = 0.0f;
+            if (i < p.K) {
+                const double g = gm[i], E = En[i];
+                g0 += g;
+                e_r[r] = expf(Eo[i]);
+                dE_r[r] = En[i] - Eo[i];
+                const PsiLg pl = psi_lgamma<true>((float)g);
+                dacc += ((double)p.alpha[i] - 1.0) * E + (double)pl.lg - (g - 1.0) * (double)pl.psi;
+            }
+        }
+        g0 = warp_sum_d(g0);
+        float tacc = 0.0f;
+        constexpr int UN = 4;
+        for (int n0 = 0; n0 < Nd; n0 += UN) {
+            float s[UN], a[UN], c[UN];
+#pragma unroll
+            for (int q = 0; q < UN; q++) {
+                const int n = min(n0 + q, Nd - 1);
+                const int term = p.terms[o + n];
+                c[q] = (n0 + q < Nd) ? p.counts[o + n] : 0.0f;
+                const float *bo = beta_old + (size_t)term * p.K_ld, *dr = D + (size_t)term * p.K_ld;
+                s[q] = a[q] = 0.0f;
+#pragma unroll
+                for (int r = 0; r < RM; r++) {
+                    const int i = lane + 32 * r;
+                    if (i < p.K) {
+                        const float u = fmaf(bo[i], e_r[r], TMVB_EPS);
+                        s[q] += u;
+                        a[q] = fmaf(u, dE_r[r] + dr[i], a[q]);
+                    }
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < UN; q++) {
+                s[q] = warp_sum(s[q]);
+                a[q] = warp_sum(a[q]);
+            }
+#pragma unroll
+            for (int q = 0; q < UN; q++) tacc += c[q] * (__fdividef(a[q], s[q]) + __logf(s[q]));
+        }
+        if (lane == 0) dacc += (double)tacc;
+        dacc = warp_sum_d(dacc);
+        if (lane == 0) {
+            double ent = 0.0;
+            if (p.K > 1) ent = -lgamma(g0) + (g0 - (double)p.K) * d_digamma(g0);
+            acc += dacc + ent + lg_alpha_term;
+        }
+    }
+    if (lane == 0 && acc != 0.0) atomicAdd(out, acc);
+}
+
 // Block-wide fp64 reductions for lda_alpha_kernel (blockDim.x = 32 * nw, nw <= 9): warp shuffles, then one shared-memory
 // round; every thread receives the result.  `red` is double[3][16], two barriers per call.
 __device__ __forceinline__ void block_sum3(double &a, double &b, double &c, double (*red)[16])
@@ -1443,9 +1524,19 @@ int tmvb_lda_elbo(tmvb_lda_t h, int mode, int64_t M_total, double *elbo_docs, do
         if (mode == 2) {
             if (K <= 32) TMVB_ELBO_LAUNCH(double, 1); else if (K <= 64) TMVB_ELBO_LAUNCH(double, 2);
             else if (K <= 128) TMVB_ELBO_LAUNCH(double, 4); else TMVB_ELBO_LAUNCH(double, 8);
-        } else {
+        } else if (env_int("TMVB_ELBO_LITERAL", 0)) {
             if (K <= 32) TMVB_ELBO_LAUNCH(float, 1); else if (K <= 64) TMVB_ELBO_LAUNCH(float, 2);
             else if (K <= 128) TMVB_ELBO_LAUNCH(float, 4); else TMVB_ELBO_LAUNCH(float, 8);
+        } else {
+            const long long n = (long long)s.V * K_ld;
+            TMVB_TRY(shard_scratch(&s, (size_t)std::max<long long>(n, 1) * 4));
+            float *D = (float *)s.d_scratch;
+            lda_logratio_kernel<<<grid_for(n, 256, s.n_sm), 256, 0, s.stream>>>(p.beta, bo, D, n, K, K_ld);
+            s.st.kernel_launches++;
+#define TMVB_ELBO_FAST(R) lda_elbo_fast_kernel<R><<<grid, 128, 0, s.stream>>>(p, bo, D, lga, out)
+            if (K <= 32) TMVB_ELBO_FAST(1); else if (K <= 64) TMVB_ELBO_FAST(2);
+            else if (K <= 128) TMVB_ELBO_FAST(4); else TMVB_ELBO_FAST(8);
+#undef TMVB_ELBO_FAST
         }
 #undef TMVB_ELBO_LAUNCH
         TMVB_CUDA(cudaGetLastError());
