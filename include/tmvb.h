@@ -65,6 +65,9 @@ int tmvb_lda_destroy(tmvb_lda_t h); /* idempotent on NULL */
  * (0-based), counts[sumN].  The inverted index (J_cumsum / terms_sortperm) is not needed.
  * Pointers may be pinned or pageable host memory. */
 int tmvb_lda_set_corpus(tmvb_lda_t h, const int64_t *N_cumsum, const int64_t *terms, const int64_t *counts);
+/* The same with Int32 token arrays: for hosts that keep a packed copy of the flattened corpus between train! calls (the
+ * reference rebuilds `terms`/`counts` with vcat on every update_buffer!, modelutils.jl:371-373); halves the corpus upload. */
+int tmvb_lda_set_corpus32(tmvb_lda_t h, const int64_t *N_cumsum, const int32_t *terms, const int32_t *counts);
 
 /* update_buffer!(model::gpuLDA), parameter half (modelutils.jl:390-392) and `@buffer model.alpha`
  * (macros.jl:64).  Any pointer may be NULL (left unchanged).  gamma is optional (the reference

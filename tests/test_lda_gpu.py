@@ -81,6 +81,23 @@ def test_fused_elbo_equals_standalone(tm, orc):
         assert abs(e1 - e2) <= 1e-6 * abs(e2), (it, e1, e2)
 
 
+def test_int64_and_int32_corpus_entry_points_agree(tm, monkeypatch):
+    """tmvb_lda_set_corpus (Int64 vectors, what update_buffer! builds) and tmvb_lda_set_corpus32 (the host mirror's packed
+    cache) lay out the same device corpus: the same trajectories."""
+    c = tm.synth.gencorp_lda(M=120, V=500, K=5, seed=21)
+    out = []
+    for force64 in ("1", "0"):
+        monkeypatch.setenv("TMVB_CORPUS64", force64)
+        model = tm.gpuLDA(tm.Corpus.from_csr(c), 7, seed=4)
+        tr = []
+        tm.train(model, iter=3, tol=0.0, printelbo=False, trace=tr)
+        out.append((tr, model.gamma.copy(), model.beta.copy()))
+    # equal up to the order of the fp32 atomic reductions into the statistics
+    np.testing.assert_allclose(out[0][0], out[1][0], rtol=1e-6)
+    np.testing.assert_allclose(out[0][1], out[1][1], rtol=1e-3, atol=1e-6)
+    np.testing.assert_allclose(out[0][2], out[1][2], rtol=1e-3, atol=1e-8)
+
+
 def test_ragged_and_edge_documents(tm, orc):
     """empty documents, single-token documents, a document longer than any shared-memory tile
     (overflow path), duplicate-free long counts."""

@@ -76,6 +76,7 @@ SIGNATURES = {
     "tmvb_lda_create": (C.c_int, [C.POINTER(_vp), C.c_int64, C.c_int64, C.c_int64, C.c_int, _vp]),
     "tmvb_lda_destroy": (C.c_int, [_vp]),
     "tmvb_lda_set_corpus": (C.c_int, [_vp, _vp, _vp, _vp]),
+    "tmvb_lda_set_corpus32": (C.c_int, [_vp, _vp, _vp, _vp]),
     "tmvb_lda_upload": (C.c_int, [_vp, _vp, _vp, _vp, _vp]),
     "tmvb_lda_set_alpha": (C.c_int, [_vp, _vp]),
     "tmvb_lda_estep": (C.c_int, [_vp, C.c_int, C.c_float, C.c_int]),

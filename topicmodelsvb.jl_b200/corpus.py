@@ -113,6 +113,22 @@ class Corpus:
         return self._flat
 
 
+def _flat32(self):
+    """(terms, counts) of flat() narrowed to page-locked Int32, built on first use; (None, None) when a count or term id
+    does not fit (the Int64 path is used then)."""
+    if getattr(self, "_flat32_cache", None) is None:
+        f = self.flat()
+        if f.nnz and (int(f.terms.max()) >= 2**31 or int(f.counts.max()) >= 2**31):
+            self._flat32_cache = (None, None)
+        else:
+            from . import _lib
+            self._flat32_cache = (_lib.pinned_copy(f.terms.astype(np.int32)), _lib.pinned_copy(f.counts.astype(np.int32)))
+    return self._flat32_cache
+
+
+Corpus.flat32 = _flat32
+
+
 def check_corp(corp: Corpus) -> None:
     """Corpus.jl:111-122 (the parts that concern the flattened arrays)."""
     if corp.docs is None:

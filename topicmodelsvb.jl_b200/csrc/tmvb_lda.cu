@@ -1222,12 +1222,24 @@ int tmvb_lda_kld(tmvb_lda_t h, int64_t *K_ld)
     return 0;
 }
 
+static int lda_set_corpus(tmvb_lda_t h, const int64_t *N_cumsum, const void *terms, const void *counts, int elem_bytes);
+
 int tmvb_lda_set_corpus(tmvb_lda_t h, const int64_t *N_cumsum, const int64_t *terms, const int64_t *counts)
+{
+    return lda_set_corpus(h, N_cumsum, terms, counts, 8);
+}
+
+int tmvb_lda_set_corpus32(tmvb_lda_t h, const int64_t *N_cumsum, const int32_t *terms, const int32_t *counts)
+{
+    return lda_set_corpus(h, N_cumsum, terms, counts, 4);
+}
+
+static int lda_set_corpus(tmvb_lda_t h, const int64_t *N_cumsum, const void *terms, const void *counts, int elem_bytes)
 {
     TMVB_CHECK_ARG(h != nullptr, "handle is NULL");
     Shard &s = h->s;
     // buckets are planned with the two-warp working set; launches for short documents use one warp per document
-    TMVB_TRY(shard_set_corpus(&s, N_cumsum, terms, counts, lda_fixed_smem(s.RS, s.lpt, 2)));
+    TMVB_TRY(shard_set_corpus(&s, N_cumsum, terms, counts, lda_fixed_smem(s.RS, s.lpt, 2), elem_bytes));
     const int force_w = env_int("TMVB_LDA_WARPS", 0);
     const size_t per_tok = (size_t)s.RS * 4 + 8;
     for (Bucket &b : s.buckets) {

@@ -93,7 +93,8 @@ __global__ void validate_kernel(const float *__restrict__ x, long long n, int wh
     if (e) atomicOr(err, e << (2 * what));
 }
 // CSR re-layout: internal document p takes the tokens of caller document perm[p]; Int64 -> int32 / float
-__global__ void pack_corpus_kernel(const long long *__restrict__ terms64, const long long *__restrict__ counts64,
+template <typename IntT>
+__global__ void pack_corpus_kernel(const IntT *__restrict__ terms64, const IntT *__restrict__ counts64,
                                    const long long *__restrict__ src_off, const long long *__restrict__ dst_off, long long M,
                                    int V, int *__restrict__ terms, float *__restrict__ counts, int *__restrict__ err)
 {
@@ -296,8 +297,9 @@ static int plan_buckets(Shard *s, size_t fixed_bytes)
     return 0;
 }
 
-int shard_set_corpus(Shard *s, const int64_t *N_cumsum, const int64_t *terms, const int64_t *counts, size_t fixed_bytes)
+int shard_set_corpus(Shard *s, const int64_t *N_cumsum, const void *terms, const void *counts, size_t fixed_bytes, int elem_bytes)
 {
+    TMVB_CHECK_ARG(elem_bytes == 8 || elem_bytes == 4, "token arrays must be Int64 or Int32");
     TMVB_CHECK_ARG(N_cumsum != nullptr, "N_cumsum is NULL");
     TMVB_CUDA(cudaSetDevice(s->device));
     const int64_t M = s->M;
@@ -310,10 +312,10 @@ int shard_set_corpus(Shard *s, const int64_t *N_cumsum, const int64_t *terms, co
     // overlap the host-side sort below (the caller's arrays stay alive until the synchronize at the end of this call)
     if (nnz > 0) {
         TMVB_TRY(shard_scratch(s, (size_t)nnz * 16));
-        long long *t64 = (long long *)s->d_scratch, *c64 = t64 + nnz;
-        TMVB_CUDA(cudaMemcpyAsync(t64, terms, nnz * 8, cudaMemcpyHostToDevice, s->stream));
-        TMVB_CUDA(cudaMemcpyAsync(c64, counts, nnz * 8, cudaMemcpyHostToDevice, s->stream));
-        s->st.h2d_bytes += nnz * 16;
+        unsigned char *t_in = (unsigned char *)s->d_scratch, *c_in = t_in + (size_t)nnz * elem_bytes;
+        TMVB_CUDA(cudaMemcpyAsync(t_in, terms, (size_t)nnz * elem_bytes, cudaMemcpyHostToDevice, s->stream));
+        TMVB_CUDA(cudaMemcpyAsync(c_in, counts, (size_t)nnz * elem_bytes, cudaMemcpyHostToDevice, s->stream));
+        s->st.h2d_bytes += nnz * 2 * elem_bytes;
     }
 
     // host: O(M) counting sort of the documents by length (descending, stable)
@@ -370,10 +372,15 @@ int shard_set_corpus(Shard *s, const int64_t *N_cumsum, const int64_t *terms, co
     }
     s->st.h2d_bytes += (M + 1) * 8 + M * 12;
     if (nnz > 0) {
-        long long *t64 = (long long *)s->d_scratch, *c64 = t64 + nnz;
+        unsigned char *t_in = (unsigned char *)s->d_scratch, *c_in = t_in + (size_t)nnz * elem_bytes;
         TMVB_CUDA(cudaMemsetAsync(s->d_counters + 63, 0, 4, s->stream));
-        pack_corpus_kernel<<<grid_for(M * 32, 256, s->n_sm), 256, 0, s->stream>>>(t64, c64, s->d_src_off, s->d_doc_off, M, (int)s->V,
-                                                                                 s->d_terms, s->d_counts, s->d_counters + 63);
+        const int grid = grid_for(M * 32, 256, s->n_sm);
+        if (elem_bytes == 8)
+            pack_corpus_kernel<long long><<<grid, 256, 0, s->stream>>>((const long long *)t_in, (const long long *)c_in, s->d_src_off, s->d_doc_off, M,
+                                                                       (int)s->V, s->d_terms, s->d_counts, s->d_counters + 63);
+        else
+            pack_corpus_kernel<int><<<grid, 256, 0, s->stream>>>((const int *)t_in, (const int *)c_in, s->d_src_off, s->d_doc_off, M, (int)s->V,
+                                                                 s->d_terms, s->d_counts, s->d_counters + 63);
         s->st.kernel_launches++;
         TMVB_CUDA(cudaGetLastError());
         int err = 0;
@@ -591,7 +598,7 @@ int shard_pack_aux(Shard *s, const int64_t *cumsum, const int64_t *ids, const in
         TMVB_CUDA(cudaMemcpyAsync(c64, vals, nnz * 8, cudaMemcpyHostToDevice, s->stream));
         s->st.h2d_bytes += nnz * 16;
         TMVB_CUDA(cudaMemsetAsync(s->d_counters + 63, 0, 4, s->stream));
-        pack_corpus_kernel<<<grid_for(M * 32, 256, s->n_sm), 256, 0, s->stream>>>(t64, c64, d_src, *d_off, M, (int)id_limit, *d_ids, *d_vals,
+        pack_corpus_kernel<long long><<<grid_for(M * 32, 256, s->n_sm), 256, 0, s->stream>>>(t64, c64, d_src, *d_off, M, (int)id_limit, *d_ids, *d_vals,
                                                                                  s->d_counters + 63);
         s->st.kernel_launches++;
         TMVB_CUDA(cudaGetLastError());

@@ -71,7 +71,8 @@ int shard_create(Shard *s, int64_t K, int64_t M, int64_t V, int device, void *st
 void shard_free(Shard *s);
 int shard_scratch(Shard *s, size_t bytes);
 // CSR upload + device re-layout (modelutils.jl:371-388); buckets are planned with smem(cap) = cap*(RS*4+8) + fixed_bytes
-int shard_set_corpus(Shard *s, const int64_t *N_cumsum, const int64_t *terms, const int64_t *counts, size_t fixed_bytes);
+// terms / counts: Int64 (elem_bytes = 8, what update_buffer! builds) or Int32 (elem_bytes = 4, a host-side packed cache)
+int shard_set_corpus(Shard *s, const int64_t *N_cumsum, const void *terms, const void *counts, size_t fixed_bytes, int elem_bytes = 8);
 // host [rows][K] (caller order) -> device [rows][K_ld] (internal order when perm); validate: -1 none, 0 x>=0, 1 x<=0, 2 x>0
 int shard_upload_rows(Shard *s, const float *host, float *d_dst, int64_t rows, const int *d_perm, int validate);
 int shard_download_rows(Shard *s, const float *d_src, float *host, int64_t rows, const int *d_perm);

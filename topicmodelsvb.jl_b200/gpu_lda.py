@@ -108,7 +108,13 @@ class gpuLDA:
         """update_buffer!(model::gpuLDA) (modelutils.jl:370-397): flatten, upload corpus and parameters."""
         lib, h = _lib.load(), self._handle()
         f = self.corp.flat()
-        _lib.check(lib.tmvb_lda_set_corpus(h, _lib.ptr(f.N_cumsum), _lib.ptr(f.terms), _lib.ptr(f.counts)))
+        # the flattened corpus is cached on the host as page-locked Int32 (built once per Corpus): half the upload of the
+        # Int64 vectors update_buffer! rebuilds on every call (modelutils.jl:371-373)
+        t32, c32 = (None, None) if os.environ.get("TMVB_CORPUS64") == "1" else self.corp.flat32()
+        if t32 is not None:
+            _lib.check(lib.tmvb_lda_set_corpus32(h, _lib.ptr(f.N_cumsum), _lib.ptr(t32), _lib.ptr(c32)))
+        else:
+            _lib.check(lib.tmvb_lda_set_corpus(h, _lib.ptr(f.N_cumsum), _lib.ptr(f.terms), _lib.ptr(f.counts)))
         self.alpha = np.ascontiguousarray(self.alpha, dtype=np.float32)
         self.beta = _fmat(self.beta, self.K, self.V, "beta")
         self.Elogtheta = _fmat(self.Elogtheta, self.K, self.M, "Elogtheta")
