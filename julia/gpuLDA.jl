@@ -44,6 +44,8 @@ mutable struct gpuLDA <: TopicModel
 	phi::MatrixList{Float32}
 	elbo::Float32
 	handle::Ptr{Cvoid}          # replaces the 20 OpenCL fields device/context/queue/*_kernel/*_buffer (gpuLDA.jl:21-44)
+	peers::Bool                 # true once connect_peers! has mapped the other ranks' buffers (multi-GPU)
+	M_total::Int                # corpus-wide document count (== M unless this model holds one shard)
 
 	function gpuLDA(corp::Corpus, K::Integer)
 		check_corp(corp)
@@ -63,7 +65,7 @@ mutable struct gpuLDA <: TopicModel
 		phi = [fill(Float32(1/K), K, N[d]) for d in 1:min(M, 1)]   # phi is materialised on demand (materialize_phi!)
 		elbo = 0f0
 
-		model = new(K, M, V, N, C, copy(corp), topics, alpha, beta, Elogtheta, Elogtheta_sum, Elogtheta_dist, gamma, phi, elbo, C_NULL)
+		model = new(K, M, V, N, C, copy(corp), topics, alpha, beta, Elogtheta, Elogtheta_sum, Elogtheta_dist, gamma, phi, elbo, C_NULL, false, M)
 		finalizer(m -> (m.handle != C_NULL && ccall((:tmvb_lda_destroy, LIBTMVB), Cint, (Ptr{Cvoid},), m.handle); m.handle = C_NULL), model)
 		return model
 	end
@@ -122,7 +124,7 @@ end
 function update_elbo!(model::gpuLDA; mode::Integer=0)
 	docs, glob = Ref{Cdouble}(0), Ref{Cdouble}(0)
 	tmvb_check(ccall((:tmvb_lda_elbo, LIBTMVB), Cint, (Ptr{Cvoid}, Cint, Int64, Ref{Cdouble}, Ref{Cdouble}),
-		model.handle, mode, model.M, docs, glob))
+		model.handle, mode, model.M_total, docs, glob))
 	model.elbo = docs[] + glob[]
 	return model.elbo
 end
@@ -130,11 +132,24 @@ end
 ## update_alpha! (gpuLDA.jl:132-154): interior-point Newton in fp64 inside the library.
 function update_alpha!(model::gpuLDA, niter::Integer, ntol::Real)
 	tmvb_check(ccall((:tmvb_lda_update_alpha, LIBTMVB), Cint, (Ptr{Cvoid}, Int64, Cint, Cdouble, Ptr{Float32}),
-		model.handle, model.M, niter, ntol, model.alpha))
+		model.handle, model.M_total, niter, ntol, model.alpha))
 end
 
 ## update_beta! (gpuLDA.jl:201-204)
-update_beta!(model::gpuLDA) = tmvb_check(ccall((:tmvb_lda_mstep, LIBTMVB), Cint, (Ptr{Cvoid},), model.handle))
+update_beta!(model::gpuLDA) = tmvb_check(ccall((model.peers ? :tmvb_lda_exchange_mstep : :tmvb_lda_mstep, LIBTMVB), Cint, (Ptr{Cvoid},), model.handle))
+
+## Multi-GPU (one Julia process per device; `model.corp` holds the shard d % world == rank, `model.M_total` the corpus-wide
+## document count).  Called once after update_buffer!: exchanges the 512-byte CUDA-IPC blobs over `allgather` (any transport:
+## MPI.Allgather, Distributed, sockets) and maps the peers; from then on update_beta! is the fused peer-memory kernel
+## (reduce-scatter of the statistics over NVLink + normalise + all-gather).  `model.peers::Bool` is a new struct field.
+function connect_peers!(model::gpuLDA, rank::Integer, world::Integer, allgather::Function)
+	blob = zeros(UInt8, 512)
+	tmvb_check(ccall((:tmvb_lda_comm_export, LIBTMVB), Cint, (Ptr{Cvoid}, Ptr{UInt8}, Int64), model.handle, blob, 512))
+	blobs = allgather(blob)::Vector{UInt8}                      # world * 512 bytes, rank order
+	tmvb_check(ccall((:tmvb_lda_comm_connect, LIBTMVB), Cint, (Ptr{Cvoid}, Cint, Cint, Ptr{UInt8}, Int64), model.handle, rank, world, blobs, 512))
+	model.peers = true
+	nothing
+end
 
 ## The folded inner loop: update_phi!/update_gamma!/update_Elogtheta! for v in 1:viter (gpuLDA.jl:356-364).
 estep!(model::gpuLDA, viter::Integer, vtol::Real, want_elbo::Bool) =

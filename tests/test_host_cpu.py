@@ -141,3 +141,48 @@ def test_two_rank_gloo_exchange_matches_single_process(tm, orc, tmp_path):
     np.testing.assert_allclose(got["elbo"], tr[1:], rtol=1e-11)
     np.testing.assert_allclose(got["beta"], st.beta, rtol=1e-9, atol=1e-300)
     np.testing.assert_allclose(got["alpha"], st.alpha, rtol=1e-9)
+
+
+def _handshake_main(rank, world, port, fail_rank, out_dir):
+    import json
+
+    import torch.distributed as dist
+
+    import topicmodelsvb_b200 as tm
+
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    red = tm.dist.Reducer()
+    seen = {}
+
+    def export(buf, n):                      # stands in for tmvb_lda_comm_export: a recognisable per-rank blob
+        assert n == 512
+        buf.raw = bytes([rank + 1]) * n
+
+    def connect(r, w, blobs, n):             # stands in for tmvb_lda_comm_connect
+        if rank == fail_rank:
+            raise RuntimeError("this rank cannot map its peers")
+        seen.update(rank=r, world=w, blobs=[blobs[i * n] for i in range(w)], size=len(blobs))
+
+    ok = red.connect_peers(export, connect, 512)
+    with open(os.path.join(out_dir, "r%d.json" % rank), "w") as f:
+        json.dump({"ok": ok, "seen": seen}, f)
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("fail_rank", [-1, 1])
+def test_peer_handshake_protocol_two_ranks(tm, tmp_path, fail_rank):
+    """The host side of the peer-memory exchange (dist.Reducer.connect_peers): every rank receives all blobs in rank
+    order, and if ANY rank cannot map its peers every rank falls back (to the NCCL all-reduce path) together."""
+    import json
+
+    import torch.multiprocessing as mp
+
+    world = 2
+    mp.spawn(_handshake_main, args=(world, _free_port(), fail_rank, str(tmp_path)), nprocs=world, join=True)
+    res = [json.load(open(tmp_path / ("r%d.json" % r))) for r in range(world)]
+    assert all(r["ok"] == (fail_rank < 0) for r in res)
+    for r, x in enumerate(res):
+        if r != fail_rank:
+            assert x["seen"]["rank"] == r and x["seen"]["world"] == world and x["seen"]["size"] == world * 512
+            assert x["seen"]["blobs"] == [1, 2]
