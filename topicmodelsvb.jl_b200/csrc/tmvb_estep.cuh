@@ -304,7 +304,7 @@ __device__ __forceinline__ void reg_sweep(const RegDoc<LPT, CPL, NR> &rd, int K,
 #pragma unroll
     for (int j = 0; j < NR; j++) {
         const float s = tok_dot<LPT, CPL>(rd.b[j], e01, e23) + Keps;
-        t[j] = (rd.c[j] > 0.0f) ? __fdividef(rd.c[j], s) : 0.0f;
+        t[j] = (rd.c[j] > 0.0f) ? (EPS ? fast_div_pos(rd.c[j], s) : __fdividef(rd.c[j], s)) : 0.0f;
     }
 #pragma unroll
     for (int j = 0; j < NR; j++) {
@@ -331,7 +331,7 @@ __device__ __forceinline__ void reg_final(const RegDoc<LPT, CPL, NR> &rd, float 
     for (int j = 0; j < NR; j++) {
         const float s = tok_dot<LPT, CPL>(rd.b[j], e01, e23) + Keps;
         if (rd.c[j] > 0.0f) {
-            const float t = __fdividef(rd.c[j], s);
+            const float t = EPS ? fast_div_pos(rd.c[j], s) : __fdividef(rd.c[j], s);
             const f32x2 t2 = pk2(t, t);
             float *srow = stats + (size_t)rd.term[j] * K_ld + 4 * kl;
 #pragma unroll

@@ -41,9 +41,9 @@ struct LdaDev {
     int dbg;         // developer probes: bit0 skip the scatter, bit1 skip the final pass
 };
 
-// shared memory of one E-step CTA beyond the tile: header (mbarrier, next-document slot, per-warp partial sums) |
+// shared memory of one E-step CTA beyond the tile: 256-byte header (mbarrier, next-document slot, per-warp partial sums) |
 // gs [W][S][RS] | e_s [RS]
-static size_t lda_fixed_smem(int RS, int lpt, int W) { return 128 + (size_t)W * (32 / lpt) * RS * 4 + (size_t)RS * 4; }
+static size_t lda_fixed_smem(int RS, int lpt, int W) { return 256 + (size_t)W * (32 / lpt) * RS * 4 + (size_t)RS * 4; }
 
 // documents drawn from a bucket's work counter per atomic
 constexpr int kDocChunk = 8;
@@ -78,10 +78,10 @@ __global__ void __launch_bounds__(32 * W, W == 2 ? 8 : 1) lda_estep_kernel(const
 
     unsigned long long *mbar = reinterpret_cast<unsigned long long *>(smem_raw);
     int *next_s = reinterpret_cast<int *>(smem_raw + 16);
-    float *csum_s = reinterpret_cast<float *>(smem_raw + 32);        // [W]
-    float *tsum_s = reinterpret_cast<float *>(smem_raw + 48);        // [W]
-    unsigned *dsum_s = reinterpret_cast<unsigned *>(smem_raw + 64);  // [2][W]
-    float *gs = reinterpret_cast<float *>(smem_raw + 128);           // [W][S][RS]
+    float *csum_s = reinterpret_cast<float *>(smem_raw + 32);        // [W <= 8]
+    float *tsum_s = reinterpret_cast<float *>(smem_raw + 64);        // [W <= 8]
+    unsigned *dsum_s = reinterpret_cast<unsigned *>(smem_raw + 96);  // [2][W <= 8]
+    float *gs = reinterpret_cast<float *>(smem_raw + 256);           // [W][S][RS]
     float *e_s = gs + (size_t)W * S * RS;                            // [RS]
     float *tile = e_s + RS;                                          // [cap][RS]
     float *cnt_s = tile + (size_t)cap * RS;                          // [cap]
@@ -1056,22 +1056,25 @@ static const LdaRegLayout *lda_reg_layout(int lpt, int cpl)
     return nullptr;
 }
 struct LdaPick {
-    const void *tile[2];
+    const void *tile[3];
     const LdaRegLayout *reg;
     bool elbo;
 };
 static const void *lda_pick(const Bucket &b, const void *ctx)
 {
     const LdaPick *pk = static_cast<const LdaPick *>(ctx);
-    if (b.nr == 0) return pk->tile[b.warps - 1];
+    if (b.nr == 0) return pk->tile[b.warps >= 4 ? 2 : b.warps - 1];
     for (int v = 0; v < kNumRegVariants; v++)
         if (kRegVariant[v][0] == b.warps && kRegVariant[v][1] == b.nr) return (const void *)pk->reg->fn[pk->elbo ? 1 : 0][v];
     return nullptr;
 }
 #define TMVB_LDA_FN1(L, C) {(LdaEstepFn)lda_estep_kernel<L, C, 1, false>, (LdaEstepFn)lda_estep_kernel<L, C, 1, true>},
 #define TMVB_LDA_FN2(L, C) {(LdaEstepFn)lda_estep_kernel<L, C, 2, false>, (LdaEstepFn)lda_estep_kernel<L, C, 2, true>},
+#define TMVB_LDA_FN4(L, C) {(LdaEstepFn)lda_estep_kernel<L, C, 4, false>, (LdaEstepFn)lda_estep_kernel<L, C, 4, true>},
 // [warps per document - 1][lane layout][want_elbo]
-static const LdaEstepFn kLdaEstep[2][kNumLaneLayouts][2] = {{TMVB_FOR_EACH_LAYOUT(TMVB_LDA_FN1)}, {TMVB_FOR_EACH_LAYOUT(TMVB_LDA_FN2)}};
+// [warps per document: 1, 2, 4][lane layout][want_elbo]  (eight warps per document measured slower than four at K=200: 25 vs 17 ms)
+static const LdaEstepFn kLdaEstep[3][kNumLaneLayouts][2] = {{TMVB_FOR_EACH_LAYOUT(TMVB_LDA_FN1)}, {TMVB_FOR_EACH_LAYOUT(TMVB_LDA_FN2)},
+                                                            {TMVB_FOR_EACH_LAYOUT(TMVB_LDA_FN4)}};
 
 }  // namespace tmvb
 
@@ -1183,7 +1186,7 @@ int tmvb_lda_create(tmvb_lda_t *out, int64_t K, int64_t M, int64_t V, int device
         A((void **)&h->d_small, (s.K_ld + 2) * 8);
         A((void **)&h->d_local, (3 * s.K_ld + 2) * 8);
         // opt in to the large dynamic shared memory for both instantiations of this K
-        for (int w = 0; w < 2; w++)
+        for (int w = 0; w < 3; w++)
             for (int eb = 0; eb < 2 && e == cudaSuccess; eb++)
                 e = cudaFuncSetAttribute((const void *)kLdaEstep[w][s.layout][eb], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s.smem_optin);
         if (e != cudaSuccess) rc = fail((int)e, "device allocation failed: %s", cudaGetErrorString(e));
@@ -1238,14 +1241,16 @@ static int lda_set_corpus(tmvb_lda_t h, const int64_t *N_cumsum, const void *ter
 {
     TMVB_CHECK_ARG(h != nullptr, "handle is NULL");
     Shard &s = h->s;
-    // buckets are planned with the two-warp working set; launches for short documents use one warp per document
-    TMVB_TRY(shard_set_corpus(&s, N_cumsum, terms, counts, lda_fixed_smem(s.RS, s.lpt, 2), elem_bytes));
+    // Warps per document in the tile kernel.  Small tiles (K_ld <= 64): one -- two measured the same E-step time (2.93 vs
+    // 2.89 ms at NSF K=50), the shorter per-document latency is paid for by fewer documents in flight.  Large tiles (K=200:
+    // 65 KB for an 80-token document, three documents per SM): the tile bounds the residency, so more warps per
+    // document are free parallelism (K=200, 200k documents: 34.8 / 26.2 / 17.7 ms with one / two / four warps; 25 ms with eight).
     const int force_w = env_int("TMVB_LDA_WARPS", 0);
+    const int tile_w = force_w ? (force_w >= 4 ? 4 : std::max(1, force_w)) : (s.K_ld > 64 ? 4 : 1);
+    TMVB_TRY(shard_set_corpus(&s, N_cumsum, terms, counts, lda_fixed_smem(s.RS, s.lpt, std::max(2, tile_w)), elem_bytes));
     const size_t per_tok = (size_t)s.RS * 4 + 8;
     for (Bucket &b : s.buckets) {
-        // one warp per document by default: two cooperating warps (TMVB_LDA_WARPS=2) measured the same E-step time
-        // (2.93 vs 2.89 ms at NSF K=50) -- the shorter per-document latency is paid for by fewer documents in flight
-        b.warps = force_w ? std::min(2, std::max(1, force_w)) : 1;
+        b.warps = tile_w;
         b.smem = lda_fixed_smem(s.RS, s.lpt, b.warps) + (size_t)b.cap * per_tok;
         b.grid = 0;
     }
@@ -1355,6 +1360,7 @@ int tmvb_lda_estep(tmvb_lda_t h, int viter, float vtol, int want_elbo)
     LdaPick pk;
     pk.tile[0] = (const void *)kLdaEstep[0][s.layout][want_elbo != 0];
     pk.tile[1] = (const void *)kLdaEstep[1][s.layout][want_elbo != 0];
+    pk.tile[2] = (const void *)kLdaEstep[2][s.layout][want_elbo != 0];
     pk.reg = lda_reg_layout(s.lpt, s.cpl);
     pk.elbo = want_elbo != 0;
     TMVB_TRY(shard_launch(&s, lda_pick, &pk, &p, sizeof(p)));
