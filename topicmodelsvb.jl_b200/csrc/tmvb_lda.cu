@@ -362,7 +362,10 @@ __global__ void __launch_bounds__(32 * W, W == 2 ? 8 : 1) lda_estep_kernel(const
 static size_t lda_reg_smem(int RS, int lpt, int W) { return 128 + (size_t)W * (32 / lpt) * RS * 4 + (size_t)W * RS * 4 + (size_t)RS * 4; }
 
 // resident CTAs per SM the register allocation is held to (the tile alone is 4 CPL NR registers per thread)
-constexpr int lda_reg_min_ctas(int W, int NR) { return W == 1 ? (NR <= 2 ? 12 : 10) : W == 2 ? (NR <= 3 ? 6 : 5) : W == 4 ? (NR <= 3 ? 3 : 2) : 1; }
+// (measured per launch, NSF K=50, first iteration: holding the 3-round variants to 168 registers pays -- (2,3) 955 -> 860 us,
+// (4,3) 518 -> 473 us -- while the 4-round variants spill under a cap and are faster left at ~250 registers:
+// (2,4) 538 vs 617 us, (1,4) 412 vs 498 us)
+constexpr int lda_reg_min_ctas(int W, int NR) { return W == 1 ? (NR <= 2 ? 12 : 8) : W == 2 ? (NR <= 3 ? 6 : 4) : W == 4 ? (NR <= 3 ? 3 : 2) : 1; }
 
 template <int LPT, int CPL, int W, int NR, bool ELBO>
 __global__ void __launch_bounds__(32 * W, lda_reg_min_ctas(W, NR)) lda_estep_reg_kernel(const LdaDev p, int doc_begin, int doc_end, int cap, int cap2, int *counter)
