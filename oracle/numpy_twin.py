@@ -111,6 +111,27 @@ class LDATwin:
         self.elbo = elbo
         return elbo
 
+    def update_elbo_device_form(self):
+        """The same ELBO through the decomposition the CUDA path evaluates: valid right after an E-step +
+        M-step + alpha update, when Elogtheta = psi(gamma) - psi(sum gamma) and gamma = alpha_estep + phi*c + eps hold.
+          per document   sum_i lnG(gamma_i) - lnG(sum gamma) + sum_n c_n ln s_n - sum_i (gamma_i - alpha_estep_i) Elogtheta_old_i
+          K-vectors      M (lnG(sum alpha) - sum lnG(alpha)) + sum_i (alpha_i - alpha_estep_i - eps) sum_d Elogtheta_di
+          K x V          sum_ij S_ij [ln(beta_ij + eps) - ln(beta_old_ij + eps)],  S = the statistics of the last E-step
+        No logarithm per (token, topic); agreement with update_elbo() pins the identity on the CPU."""
+        a, ae = self.alpha, self.alpha_estep
+        S = np.zeros((self.V, self.K))
+        docs = 0.0
+        for d in range(self.M):
+            terms, counts = self._doc(d)
+            u = EPSILON + self.beta_old[terms] * np.exp(self.Elogtheta_old[d])[None, :]
+            s = u.sum(axis=1)
+            S[terms] += (u / s[:, None]) * counts[:, None]
+            g = self.gamma[d]
+            docs += gammaln(g).sum() - gammaln(g.sum()) + np.dot(counts, np.log(s)) - np.dot(g - ae, self.Elogtheta_old[d])
+        lin = np.dot(a - ae - EPSILON, self.Elogtheta.sum(axis=0))
+        elbo_w = np.sum(S * (np.log(self.beta + EPSILON) - np.log(self.beta_old + EPSILON)))
+        return docs + self.M * (gammaln(a.sum()) - gammaln(a).sum()) + lin + elbo_w
+
     # LDA.jl:161-191 (+ check_elbo!, modelutils.jl:574-585)
     def train(self, iter=150, tol=1.0, niter=1000, ntol=None, viter=10, vtol=None, checkelbo=1):
         ntol = 1.0 / self.K**2 if ntol is None else ntol
@@ -128,6 +149,7 @@ class LDATwin:
                         break
                 self.update_beta_doc(d)
             self.update_beta()
+            self.alpha_estep = self.alpha.copy()   # not part of LDA.jl: kept for update_elbo_device_form
             self.update_alpha(niter, ntol)
             if k % checkelbo == 0:
                 old = self.elbo

@@ -44,6 +44,21 @@ def test_c_oracle_matches_numpy_twin(orc, K, M, V, seed):
     np.testing.assert_allclose(st.Elogtheta, tw.Elogtheta, rtol=1e-10, atol=1e-12)
 
 
+@pytest.mark.parametrize("K,M,V,seed", [(5, 100, 500, 0), (1, 20, 60, 5), (12, 30, 200, 6)])
+def test_device_elbo_decomposition_equals_literal_elbo(K, M, V, seed):
+    """The decomposition the CUDA path evaluates (no logarithm per token and topic) equals
+    update_elbo! (LDA.jl:50-93) after every outer iteration, in fp64 on the CPU."""
+    import topicmodelsvb_b200.synth as synth
+    from oracle.numpy_twin import LDATwin
+
+    c = synth.gencorp_lda(M=M, V=V, K=max(K, 2), seed=seed)
+    tw = LDATwin(c.N_cumsum, c.terms, c.counts, K, c.V, synth.init_beta(K, c.V, seed=7))
+    for it in range(4):
+        tr = tw.train(iter=1, tol=-np.inf)
+        lit, dev = tr[1], tw.update_elbo_device_form()
+        assert abs(dev - lit) <= 1e-11 * abs(lit), (it, lit, dev)
+
+
 def test_golden_lda_cfg0(orc):
     g = np.load(os.path.join(GOLD, "lda_cfg0.npz"))
     K, V = int(g["K"]), int(g["V"])
