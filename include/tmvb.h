@@ -138,6 +138,25 @@ int tmvb_lda_get_stats(tmvb_lda_t h, tmvb_stats *out);
 int tmvb_lda_kld(tmvb_lda_t h, int64_t *K_ld);
 
 
+/* ------------------------------------------------------------------ corpus ingest (host only) ---- */
+
+/* readcorp(docfile=..., delim, counts, readers, ratings) (Corpus.jl:277-296) fused with the flattening of update_buffer!
+ * (modelutils.jl:371-380,443-472): text -> packed CSR with 0-based Int32 keys, ready for tmvb_*_set_corpus32.  Multi-threaded
+ * (nthreads <= 0: all host threads).  Arrays are malloc'ed by the library and released by tmvb_free_csr.  A document that does
+ * not parse or fails check_doc (Corpus.jl:41-49) returns rc = -6 with the reference's message
+ * "document d beginning on line l failed to load." (Corpus.jl:293). */
+typedef struct {
+    int64_t M, nnz, nr;          /* documents, sum of N_d, sum of R_d */
+    int64_t max_term, max_reader; /* largest 1-based key seen (0 if none) */
+    int64_t *N_cumsum;           /* [M+1] */
+    int32_t *terms, *counts;     /* [nnz] terms 0-based; counts default 1 */
+    int64_t *R_cumsum;           /* [M+1] */
+    int32_t *readers, *ratings;  /* [nr] readers 0-based; ratings default 1 */
+} tmvb_csr;
+int tmvb_read_docfile(const char *path, char delim, int counts, int readers, int ratings, int nthreads, tmvb_csr *out);
+int tmvb_free_csr(tmvb_csr *c);
+
+
 /* ------------------------------------------------------------------ CTM ------------------ */
 
 /* gpuCTM(corp, K) device side (gpuCTM.jl:74-92: context + 9 cl.Program builds).  K <= 64 in this build.

@@ -26,6 +26,13 @@ class TopicModelError(RuntimeError):
     """Mirror of the reference's TopicModelError (modelutils.jl:1-5)."""
 
 
+class TmvbCsr(C.Structure):
+    """tmvb_csr (include/tmvb.h)"""
+    _fields_ = [("M", C.c_int64), ("nnz", C.c_int64), ("nr", C.c_int64), ("max_term", C.c_int64), ("max_reader", C.c_int64),
+                ("N_cumsum", C.POINTER(C.c_int64)), ("terms", C.POINTER(C.c_int32)), ("counts", C.POINTER(C.c_int32)),
+                ("R_cumsum", C.POINTER(C.c_int64)), ("readers", C.POINTER(C.c_int32)), ("ratings", C.POINTER(C.c_int32))]
+
+
 class TmvbStats(C.Structure):
     _fields_ = [("estep_ms", C.c_double), ("mstep_ms", C.c_double), ("sweeps", C.c_int64),
                 ("kernel_launches", C.c_int64), ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64)]
@@ -73,6 +80,8 @@ SIGNATURES = {
     "tmvb_device_count": (C.c_int, [C.POINTER(C.c_int)]),
     "tmvb_alloc_pinned": (C.c_int, [C.POINTER(_vp), C.c_int64]),
     "tmvb_free_pinned": (C.c_int, [_vp]),
+    "tmvb_read_docfile": (C.c_int, [C.c_char_p, C.c_char, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(TmvbCsr)]),
+    "tmvb_free_csr": (C.c_int, [C.POINTER(TmvbCsr)]),
     "tmvb_lda_create": (C.c_int, [C.POINTER(_vp), C.c_int64, C.c_int64, C.c_int64, C.c_int, _vp]),
     "tmvb_lda_destroy": (C.c_int, [_vp]),
     "tmvb_lda_set_corpus": (C.c_int, [_vp, _vp, _vp, _vp]),

@@ -122,11 +122,52 @@ def _flat32(self):
             self._flat32_cache = (None, None)
         else:
             from . import _lib
-            self._flat32_cache = (_lib.pinned_copy(f.terms.astype(np.int32)), _lib.pinned_copy(f.counts.astype(np.int32)))
+            t32, c32 = getattr(self, "_packed32", None) or (f.terms.astype(np.int32), f.counts.astype(np.int32))
+            self._flat32_cache = (_lib.pinned_copy(t32), _lib.pinned_copy(c32))
     return self._flat32_cache
 
 
 Corpus.flat32 = _flat32
+
+
+def readcorp(docfile: str, vocabfile: Optional[str] = None, userfile: Optional[str] = None, delim: str = ",", counts: bool = False,
+             readers: bool = False, ratings: bool = False, nthreads: int = 0) -> Corpus:
+    """readcorp(docfile=..., vocabfile=..., userfile=..., delim, counts, readers, ratings) (Corpus.jl:277-325) through the
+    native parser (tmvb_read_docfile): the text is parsed straight into the packed CSR that update_buffer! would build, on all
+    host threads.  vocabfile / userfile only size the vocabulary / user set here (one `key<TAB>name` line each, as the
+    reference's files); without them V and U are the largest keys seen.  Raises CorpusError with the reference's message when a
+    document fails to load."""
+    import ctypes as C
+
+    from . import _lib
+
+    lib = _lib.load()
+    c = _lib.TmvbCsr()
+    rc = lib.tmvb_read_docfile(docfile.encode(), delim.encode()[:1], int(counts), int(readers), int(ratings), int(nthreads), C.byref(c))
+    if rc == -6:
+        raise CorpusError(lib.tmvb_last_error().decode())
+    _lib.check(rc)
+    try:
+        def arr(ptr, n, dtype):
+            return np.ctypeslib.as_array(ptr, shape=(max(int(n), 1),))[: int(n)].astype(dtype) if n else np.zeros(0, dtype)
+
+        M = int(c.M)
+        off = np.ctypeslib.as_array(c.N_cumsum, shape=(M + 1,)).copy()
+        roff = np.ctypeslib.as_array(c.R_cumsum, shape=(M + 1,)).copy()
+        t32, c32 = arr(c.terms, c.nnz, np.int32), arr(c.counts, c.nnz, np.int32)
+        r32, g32 = arr(c.readers, c.nr, np.int32), arr(c.ratings, c.nr, np.int32)
+        nlines = lambda p: sum(1 for _ in open(p, "rb"))
+        V = nlines(vocabfile) if vocabfile else int(c.max_term)
+        U = nlines(userfile) if userfile else int(c.max_reader)
+        if int(c.max_term) > V:
+            raise CorpusError("documents contain term keys not found in corpus vocabulary (see fixcorp! function).")
+        if int(c.max_reader) > U:
+            raise CorpusError("documents contain user keys not found in corpus users (see fixcorp! function).")
+    finally:
+        lib.tmvb_free_csr(C.byref(c))
+    corp = Corpus.from_csr(CSR(M, V, off, t32.astype(np.int64), c32.astype(np.int64), U, roff, r32.astype(np.int64), g32.astype(np.int64)))
+    corp._packed32 = (t32, c32)   # what flat32() pins on first use: no second narrowing pass
+    return corp
 
 
 def check_corp(corp: Corpus) -> None:
