@@ -249,6 +249,36 @@ class CTMTwin:
         self.elbo = elbo
         return elbo
 
+    def update_elbo_device_form(self):
+        """CTM.jl:56-98 without a logarithm per (token, topic) -- the decomposition a device kernel can evaluate from what the
+        E-step already holds (cf. LDATwin.update_elbo_device_form).  With u_ni = beta_old_i,w exp(lambda_old_i - mx_d),
+        s_n = sum_i u_ni, phi = u / s:
+          -Elogqz  = sum_n c_n ln s_n - sum_i (phi c)_i (lambda_old_i - mx_d) - sum_ij S_ij ln beta_old_ij
+          Elogpw   = sum_ij S_ij ln(beta_ij + eps)                       (both K x V sums over the statistics S)
+          Elogpz   = (phi c) . lambda - C_d (sum_i exp(lambda_i + v_i / 2 - ln zeta) + ln zeta - 1)
+        Elogpeta and the Gaussian entropy are K-vector algebra per document."""
+        K = self.K
+        _, logdet = np.linalg.slogdet(self.invsigma)
+        S = np.zeros((self.V, K))
+        docs = 0.0
+        for d in range(self.M):
+            terms, counts = self._doc(d)
+            mx = self.lam_old[d].max()
+            u = self.beta_old[terms] * np.exp(self.lam_old[d] - mx)[None, :]
+            s = u.sum(axis=1)
+            phic = counts @ (u / s[:, None])
+            S[terms] += (u / s[:, None]) * counts[:, None]
+            lam, v = self.lam[d], self.vsq[d]
+            df = lam - self.mu
+            docs += 0.5 * (logdet - K * np.log(2 * np.pi) - np.dot(np.diag(self.invsigma), v) - df @ self.invsigma @ df)
+            docs += np.dot(phic, lam) - self.C[d] * (np.exp(lam + 0.5 * v - self.logzeta[d]).sum() + self.logzeta[d] - 1)
+            docs += 0.5 * (K * (np.log(2 * np.pi) + 1) + np.log(v).sum())
+            docs += np.dot(counts, np.log(s)) - np.dot(phic, self.lam_old[d] - mx)
+        pos = S > 0
+        with np.errstate(divide="ignore"):
+            glob = np.sum(S[pos] * (np.log(self.beta[pos] + EPSILON) - np.log(self.beta_old[pos])))
+        return docs + glob
+
     def train(self, iter=150, tol=1.0, niter=1000, ntol=None, viter=10, vtol=None, checkelbo=1):  # CTM.jl:185-217
         K = self.K
         ntol = 1.0 / K**2 if ntol is None else ntol

@@ -59,6 +59,20 @@ def test_device_elbo_decomposition_equals_literal_elbo(K, M, V, seed):
         assert abs(dev - lit) <= 1e-11 * abs(lit), (it, lit, dev)
 
 
+@pytest.mark.parametrize("K,M,V,seed", [(4, 40, 150, 2), (1, 15, 50, 3), (7, 25, 120, 8)])
+def test_ctm_elbo_decomposition_equals_literal_elbo(K, M, V, seed):
+    """The logarithm-free form of the CTM ELBO (CTMTwin.update_elbo_device_form) equals update_elbo! (CTM.jl:56-98)."""
+    import topicmodelsvb_b200.synth as synth
+    from oracle.numpy_twin import CTMTwin
+
+    c = synth.gencorp_lda(M=M, V=V, K=max(K, 2), seed=seed)
+    tw = CTMTwin(c.N_cumsum, c.terms, c.counts, K, c.V, synth.init_beta(K, c.V, seed=7))
+    for it in range(3):
+        tr = tw.train(iter=1, tol=-np.inf)
+        lit, dev = tr[1], tw.update_elbo_device_form()
+        assert abs(dev - lit) <= 1e-11 * abs(lit), (it, lit, dev)
+
+
 def test_golden_lda_cfg0(orc):
     g = np.load(os.path.join(GOLD, "lda_cfg0.npz"))
     K, V = int(g["K"]), int(g["V"])
