@@ -384,6 +384,37 @@ class CTPFTwin:
         self.elbo = x
         return x
 
+    def update_elbo_device_form(self):
+        """update_elbo() with the two entropy sums written without a logarithm per (token, topic) / (reader, topic) -- valid
+        after an E-step + M-step, when alef - a and he - e ARE the statistics of the last phi / xi.  With
+        q = psi(gimel_old) - ln dalet_old - ln bet_old and lse_n = ln sum_i exp(q_i + psi(alef_old[w_n, i])):
+          sum_n c_n H(phi_n) = sum_n c_n lse_n - (phi c) . q - sum_wi (alef - a)_wi psi(alef_old)_wi
+        and for the 2K-way xi with qa, qb (CTPF.jl:334-337) and the K x U table psi(he_old):
+          sum_r r H(xi_r) = sum_r r lse_r - (xi_a r) . qa - (xi_b r) . qb - sum_ui (he - e)_ui psi(he_old)_ui ."""
+        K = self.K
+        full = self.update_elbo()
+        ent_lit, ent_dev = 0.0, 0.0
+        for d in range(self.M):
+            t, cn = self.terms[self.off[d]:self.off[d + 1]], self.counts[self.off[d]:self.off[d + 1]]
+            r, ra = self.readers[self.roff[d]:self.roff[d + 1]], self.ratings[self.roff[d]:self.roff[d + 1]]
+            phi = self._phi(d, self.alef_old, self.gimel_old, self.dalet_old, self.bet_old)
+            xi = self._xi(d, self.he_old, self.gimel_old, self.zayin_old, self.dalet_old, self.het_old, self.vav_old)
+            with np.errstate(divide="ignore", invalid="ignore"):
+                ent_lit += np.sum(ra * -np.where(xi > 0, xi * np.log(xi), 0.0).sum(axis=1)) + np.sum(cn * -np.where(phi > 0, phi * np.log(phi), 0.0).sum(axis=1))
+            q = digamma(self.gimel_old[d]) - np.log(self.dalet_old) - np.log(self.bet_old)
+            x = q[None, :] + digamma(self.alef_old[t])
+            lse = x.max(axis=1) + np.log(np.exp(x - x.max(axis=1, keepdims=True)).sum(axis=1))
+            ent_dev += np.dot(cn, lse) - np.dot(cn @ phi, q)
+            if len(r):
+                qa = digamma(self.gimel_old[d]) - np.log(self.dalet_old) - np.log(self.vav_old)
+                qb = digamma(self.zayin_old[d]) - np.log(self.het_old) - np.log(self.vav_old)
+                ph = digamma(self.he_old[r])
+                y = np.concatenate([qa[None, :] + ph, qb[None, :] + ph], axis=1)
+                lse_r = y.max(axis=1) + np.log(np.exp(y - y.max(axis=1, keepdims=True)).sum(axis=1))
+                ent_dev += np.dot(ra, lse_r) - np.dot(ra @ xi[:, :K], qa) - np.dot(ra @ xi[:, K:], qb)
+        ent_dev -= np.sum((self.alef - self.a) * digamma(self.alef_old)) + np.sum((self.he - self.e) * digamma(self.he_old))
+        return full - ent_lit + ent_dev
+
     def train(self, iter=150, tol=1.0, viter=10, vtol=None, checkelbo=1):  # CTPF.jl:344-371
         K = self.K
         vtol = 1.0 / K**2 if vtol is None else vtol

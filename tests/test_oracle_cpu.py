@@ -73,6 +73,20 @@ def test_ctm_elbo_decomposition_equals_literal_elbo(K, M, V, seed):
         assert abs(dev - lit) <= 1e-11 * abs(lit), (it, lit, dev)
 
 
+@pytest.mark.parametrize("K,seed", [(4, 0), (1, 1), (6, 2)])
+def test_ctpf_entropy_decomposition_equals_literal_elbo(K, seed):
+    """The logarithm-free form of the two CTPF entropy sums (CTPFTwin.update_elbo_device_form) equals update_elbo!."""
+    import topicmodelsvb_b200.synth as synth
+    from oracle.numpy_twin import CTPFTwin
+
+    c = synth.gencorp_ctpf(M=40, V=150, U=25, K=3, seed=seed)
+    tw = CTPFTwin(c.N_cumsum, c.terms, c.counts, c.R_cumsum, c.readers, c.ratings, K, c.V, c.U, synth.init_alef(K, c.V, seed=7))
+    for it in range(3):
+        tr = tw.train(iter=1, tol=-np.inf)
+        lit, dev = tr[1], tw.update_elbo_device_form()
+        assert abs(dev - lit) <= 1e-11 * abs(lit), (it, lit, dev)
+
+
 def test_golden_lda_cfg0(orc):
     g = np.load(os.path.join(GOLD, "lda_cfg0.npz"))
     K, V = int(g["K"]), int(g["V"])
