@@ -186,3 +186,33 @@ def test_peer_handshake_protocol_two_ranks(tm, tmp_path, fail_rank):
         if r != fail_rank:
             assert x["seen"]["rank"] == r and x["seen"]["world"] == world and x["seen"]["size"] == world * 512
             assert x["seen"]["blobs"] == [1, 2]
+
+
+def test_ctpf_recommendations_follow_the_reference_loops(tm):
+    """libs / drecs / urecs (gpuCTPF.jl:88-91, 709-731) of the host mirror == the reference's loops over the dense score matrix
+    (findall(mask)[reverse(sortperm(scores[mask]))], ties included); no device needed."""
+    c = tm.synth.gencorp_ctpf(M=30, V=80, U=17, K=3, seed=5)
+    K = 4
+    m = tm.gpuCTPF(tm.Corpus.from_csr(c), K, seed=1)
+    rng = np.random.default_rng(0)
+    for n, cols in (("he", c.U), ("gimel", c.M), ("zayin", c.M)):
+        setattr(m, n, np.asfortranarray(rng.integers(1, 4, size=(K, cols)).astype(np.float32)))   # small integers: many tied scores
+    for n in ("vav", "dalet", "het"):
+        setattr(m, n, rng.integers(1, 3, size=K).astype(np.float32))
+    scores = m.scores()
+    assert scores.shape == (c.M, c.U)
+    libs = [[d + 1 for d in range(c.M) if u in c.readers[c.R_cumsum[d]:c.R_cumsum[d + 1]]] for u in range(c.U)]
+    for u in range(c.U):
+        np.testing.assert_array_equal(m.libs[u], libs[u])
+        ur = np.ones(c.M, bool)
+        ur[np.array(libs[u], dtype=int) - 1] = False
+        idx = np.flatnonzero(ur)
+        want = idx[np.argsort(scores[idx, u], kind="stable")[::-1]] + 1
+        np.testing.assert_array_equal(m.urecs[u], want)
+    for d in range(c.M):
+        nr = np.ones(c.U, bool)
+        nr[c.readers[c.R_cumsum[d]:c.R_cumsum[d + 1]]] = False
+        idx = np.flatnonzero(nr)
+        want = idx[np.argsort(scores[d, idx], kind="stable")[::-1]] + 1
+        np.testing.assert_array_equal(m.drecs[d], want)
+    assert len(m.drecs) == c.M and len(m.urecs) == c.U

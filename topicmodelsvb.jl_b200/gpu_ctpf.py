@@ -149,6 +149,62 @@ class gpuCTPF:
         Eth = self.gimel / self.dalet[:, None] + self.zayin / self.het[:, None]
         return (Eth.T.astype(np.float32) @ Eeta.astype(np.float32))
 
+    # ---- recommendations (gpuCTPF.jl:88-105, 709-731): the reference materialises scores (M x U) and the two complete
+    # rankings (M*U - sum R entries each, ~0.75 GB of Int at CiteULike) at the end of every train!; here one row / column of
+    # the score matrix is formed and ranked when it is asked for (showdrecs / showurecs look at a handful of them).
+    @property
+    def libs(self):
+        """libs[u] = 1-based documents user u+1 has in their library (gpuCTPF.jl:88-91)."""
+        if getattr(self, "_libs", None) is None:
+            f = self.corp.flat()
+            if f.readers is None or not len(f.readers):
+                self._libs = [np.zeros(0, np.int64) for _ in range(self.U)]
+            else:
+                doc_of = np.repeat(np.arange(1, self.M + 1), np.diff(f.R_cumsum))
+                order = np.argsort(f.readers, kind="stable")
+                cut = np.searchsorted(f.readers[order], np.arange(self.U + 1))
+                self._libs = [doc_of[order[cut[u]:cut[u + 1]]] for u in range(self.U)]
+        return self._libs
+
+    def _Etheta_eps(self):
+        return self.gimel / self.dalet[:, None] + self.zayin / self.het[:, None]      # (K, M): Etheta + Eepsilon
+
+    def _rank(self, vals, excluded_1based, n):
+        keep = np.ones(n, dtype=bool)
+        keep[np.asarray(excluded_1based, dtype=np.int64) - 1] = False
+        idx = np.flatnonzero(keep)
+        return idx[np.argsort(vals[idx], kind="stable")[::-1]] + 1                    # findall(.)[reverse(sortperm(.))], 1-based
+
+    @property
+    def drecs(self):
+        """drecs[d] = users who have not read document d+1, by descending score (gpuCTPF.jl:724-729); ranked on access."""
+        model = self
+
+        class _D:
+            def __len__(self):
+                return model.M
+
+            def __getitem__(self, d):
+                f = model.corp.flat()
+                row = (model._Etheta_eps()[:, d].astype(np.float32) @ (model.he / model.vav[:, None]).astype(np.float32))
+                readers = f.readers[f.R_cumsum[d]:f.R_cumsum[d + 1]] + 1 if f.readers is not None else []
+                return model._rank(row, readers, model.U)
+        return _D()
+
+    @property
+    def urecs(self):
+        """urecs[u] = documents not in user u+1's library, by descending score (gpuCTPF.jl:716-722); ranked on access."""
+        model = self
+
+        class _U:
+            def __len__(self):
+                return model.U
+
+            def __getitem__(self, u):
+                col = model._Etheta_eps().T.astype(np.float32) @ (model.he[:, u] / model.vav).astype(np.float32)
+                return model._rank(col, model.libs[u], model.M)
+        return _U()
+
     def stats(self) -> _lib.TmvbStats:
         st = _lib.TmvbStats()
         _lib.check(_lib.load().tmvb_ctpf_get_stats(self._handle(), C.byref(st)))
@@ -211,7 +267,8 @@ def check_model_ctpf(model: gpuCTPF) -> None:
 def train_ctpf(model: gpuCTPF, iter: int = 150, tol: float = 1.0, viter: int = 10, vtol: Optional[float] = None, checkelbo=1,
                printelbo: bool = True, trace: Optional[list] = None):
     """train!(model::gpuCTPF; iter, tol, viter, vtol, checkelbo, printelbo) (gpuCTPF.jl:677-733) up to the topic ranking;
-    the dense score matrix / drecs / urecs (gpuCTPF.jl:709-731) are computed on demand by ``model.scores()``."""
+    the dense score matrix / drecs / urecs (gpuCTPF.jl:709-731) are computed on demand (``model.scores()``, ``model.drecs[d]``,
+    ``model.urecs[u]``)."""
     from .gpu_lda import check_elbo
 
     K = model.K
