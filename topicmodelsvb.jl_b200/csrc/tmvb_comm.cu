@@ -33,6 +33,8 @@ int comm_connect(Comm *c, int rank, int world, const void *blobs, size_t blob_by
     TMVB_CHECK_ARG(rank >= 0 && rank < world, "rank out of range");
     TMVB_CHECK_ARG(c->d_ctl != nullptr, "comm_export must precede comm_connect");
     TMVB_CHECK_ARG(blobs != nullptr && blob_bytes >= kCommBufs * sizeof(cudaIpcMemHandle_t), "blobs missing");
+    c->rank = rank;   // set first: comm_free closes whatever has been mapped even if a later handle fails to open
+    c->world = world;
     for (int r = 0; r < world; r++) {
         for (int b = 0; b < kCommBufs; b++) {
             if (r == rank) {
@@ -46,18 +48,15 @@ int comm_connect(Comm *c, int rank, int world, const void *blobs, size_t blob_by
             c->peer[b][r] = p;
         }
     }
-    c->rank = rank;
-    c->world = world;
     c->connected = true;
     return 0;
 }
 
 void comm_free(Comm *c)
 {
-    if (c->connected)
-        for (int r = 0; r < c->world; r++)
-            for (int b = 0; b < kCommBufs; b++)
-                if (r != c->rank && c->peer[b][r]) cudaIpcCloseMemHandle(c->peer[b][r]);
+    for (int r = 0; r < c->world && r < kMaxPeers; r++)
+        for (int b = 0; b < kCommBufs; b++)
+            if (r != c->rank && c->peer[b][r]) cudaIpcCloseMemHandle(c->peer[b][r]);
     cudaFree(c->d_ctl);
     cudaFree(c->d_small_red);
     *c = Comm();
