@@ -124,6 +124,99 @@ def citeu_shaped(M=16980, V=8000, U=5551, seed=2) -> CSR:
     return CSR(M, V, off, t, c, U, roff, rd, np.ones_like(rd))
 
 
+# ---- BASELINE.json configs[4]: the HBM-bound scaling sweep -------------------------------------------------------------
+CFG4_M, CFG4_V, CFG4_K, CFG4_BLOCK = 1_000_000, 50_000, 200, 12_500
+
+
+def _draw_without_replacement(rng, Nt, cdf, V):
+    """For every document d, Nt[d] distinct term ids drawn successively from the popularity law `cdf` (a repeated id is
+    rejected and redrawn -- successive sampling without replacement), vectorised over the block.  Returns CSR offsets + ids
+    (sorted by id inside a document)."""
+    m = Nt.size
+    have = [np.zeros(0, np.int64)]           # accepted keys d * V + term
+    need = Nt.copy()
+    got = np.zeros(m, np.int64)
+    while True:
+        todo = np.nonzero(need > 0)[0]
+        if todo.size == 0:
+            break
+        draws = (need[todo] * 3) // 2 + 8
+        d = np.repeat(todo, draws)
+        w = np.minimum(np.searchsorted(cdf, rng.random(d.size)), V - 1)
+        key = d * V + w
+        # first occurrence of every new key, in draw order; drop keys accepted in earlier rounds
+        uk, first = np.unique(key, return_index=True)
+        if len(have) > 1:
+            old = np.concatenate(have)
+            keep = ~np.isin(uk, old, assume_unique=True)
+            uk, first = uk[keep], first[keep]
+        order = np.argsort(first, kind="stable")
+        uk, first = uk[order], first[order]
+        dd = uk // V
+        # rank of each new key among its document's new keys (draw order); keep the first need[d]
+        o2 = np.argsort(dd, kind="stable")
+        dd_s = dd[o2]
+        start = np.searchsorted(dd_s, dd_s, side="left")
+        rank = np.arange(dd_s.size) - start
+        ok = rank < need[dd_s]
+        acc = uk[o2][ok]
+        have.append(acc)
+        cnt = np.bincount(acc // V, minlength=m)
+        need = need - cnt
+        got += cnt
+    keys = np.sort(np.concatenate(have))
+    N = np.bincount(keys // V, minlength=m)
+    return np.concatenate([[0], np.cumsum(N)]).astype(np.int64), (keys % V).astype(np.int64)
+
+
+def cfg4_block(b: int, docs: int = CFG4_BLOCK, V: int = CFG4_V) -> CSR:
+    """Block `b` (documents [b*12500, (b+1)*12500)) of the synthetic corpus of SURVEY.md 8(d) cfg4: N_d = clip(round(LogNormal(4.30,
+    0.45)), 1, 400) distinct terms per document, ids drawn from a Zipf(1.07) law over V without replacement, counts
+    1 + Geometric(0.72); one generator per block (`default_rng([1, b])`) so every rank of a multi-GPU run can build its own
+    documents on the box."""
+    rng = np.random.default_rng([1, int(b)])
+    Nt = np.clip(np.rint(rng.lognormal(4.30, 0.45, size=docs)), 1, 400).astype(np.int64)
+    cdf = _popularity(V, 0.0, 1.07)
+    off, t = _draw_without_replacement(rng, Nt, cdf, V)
+    t = rng.permutation(V)[t]                 # popular terms are not the low ids
+    c = rng.geometric(0.72, size=t.size).astype(np.int64)   # support {1, 2, ...} = 1 + Geometric on {0, 1, ...}
+    return CSR(docs, V, off, t, c)
+
+
+def _concat_csr(parts, V) -> CSR:
+    base = np.cumsum([0] + [int(p.N_cumsum[-1]) for p in parts])
+    off = np.concatenate([np.zeros(1, np.int64)] + [p.N_cumsum[1:] + base[i] for i, p in enumerate(parts)]).astype(np.int64)
+    return CSR(sum(p.M for p in parts), V, off, np.concatenate([p.terms for p in parts]), np.concatenate([p.counts for p in parts]))
+
+
+def _cfg4_block_job(args):
+    return cfg4_block(*args)
+
+
+def cfg4_shard(rank: int = 0, world: int = 1, M: int = CFG4_M, V: int = CFG4_V, procs: int = 0) -> CSR:
+    """The documents of rank `rank` of `world` of the cfg4 corpus: blocks b = rank (mod world) of CFG4_BLOCK documents each
+    (block-cyclic document -> GPU hash, so a rank generates only what it owns), generated by `procs` worker processes
+    (0: one per host core, at most 16)."""
+    nb = (M + CFG4_BLOCK - 1) // CFG4_BLOCK
+    jobs = [(b, min(CFG4_BLOCK, M - b * CFG4_BLOCK), V) for b in range(rank, nb, world)]
+    if procs == 0:
+        import os
+
+        try:
+            procs = len(os.sched_getaffinity(0))
+        except AttributeError:  # pragma: no cover
+            procs = os.cpu_count() or 1
+        procs = max(1, min(16, procs // max(1, min(world, 8)), len(jobs)))
+    if procs > 1 and len(jobs) > 1:
+        import multiprocessing as mp
+
+        with mp.get_context("fork").Pool(procs) as pool:
+            parts = pool.map(_cfg4_block_job, jobs)
+    else:
+        parts = [cfg4_block(*j) for j in jobs]
+    return _concat_csr(parts, V)
+
+
 def load_packed(name: str) -> Optional[CSR]:
     """data/_packed/<name>.npz written by tools/pack_corpus.py from the reference's datasets."""
     import os
