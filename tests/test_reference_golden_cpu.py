@@ -1,0 +1,54 @@
+"""Pins the CPU oracle to the REFERENCE ITSELF when somebody with Julia has run tools/reference_golden.jl (the real
+TopicModelsVB.jl `train!` on the committed inputs of tests/golden/reference/inputs/) and committed its three JSON dumps.
+Until then the oracle is "parity unpinned"  and these tests skip, saying so.
+
+What runs without the dumps: the exported inputs must describe exactly the corpora / initial tables of the oracle goldens,
+so that a dump produced later is comparable."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REF = os.path.join(HERE, "golden", "reference")
+CASES = [("lda_cfg0", "beta0"), ("ctm_cfg", "beta0"), ("ctpf_cfg", "alef0")]
+
+
+@pytest.mark.parametrize("case,key", CASES)
+def test_exported_inputs_match_the_golden_cases(case, key):
+    z = np.load(os.path.join(HERE, "golden", case + ".npz"))
+    meta = json.load(open(os.path.join(REF, "inputs", case + "_meta.json")))
+    K, V = int(z["K"]), int(z["V"])
+    assert (meta["K"], meta["V"], meta["M"]) == (K, V, len(z["N_cumsum"]) - 1)
+    init = np.fromfile(os.path.join(REF, "inputs", case + "_init.f64"), dtype="<f8").reshape(V, K)
+    np.testing.assert_array_equal(init, np.asarray(z[key], dtype=np.float64))
+    lines = open(os.path.join(REF, "inputs", case + "_docs.txt")).read().split("\n")[:-1]
+    assert len(lines) == 2 * meta["M"]
+    off = z["N_cumsum"]
+    for d in (0, meta["M"] // 2, meta["M"] - 1):
+        terms = np.array([int(t) for t in lines[2 * d].split(",")]) - 1
+        counts = np.array([int(t) for t in lines[2 * d + 1].split(",")])
+        np.testing.assert_array_equal(terms, z["terms"][off[d]:off[d + 1]])
+        np.testing.assert_array_equal(counts, z["counts"][off[d]:off[d + 1]])
+    if "R_cumsum" in z:
+        np.testing.assert_array_equal(np.array(meta["readers"]) - 1, z["readers"])
+
+
+@pytest.mark.parametrize("case,key", CASES)
+def test_oracle_matches_the_reference_dump(case, key):
+    path = os.path.join(REF, case + ".json")
+    if not os.path.exists(path):
+        pytest.skip("PARITY UNPINNED: no dump of the reference's own train! for %s (run `julia tools/reference_golden.jl`)" % case)
+    ref = json.load(open(path))
+    z = np.load(os.path.join(HERE, "golden", case + ".npz"))
+    elbo = np.array(ref["elbo"], dtype=np.float64)
+    ours = np.asarray(z["elbo"], dtype=np.float64)
+    n = min(len(elbo), len(ours))
+    np.testing.assert_allclose(ours[:n], elbo[:n], rtol=1e-9)
+    K, V = int(z["K"]), int(z["V"])
+    table = "alef" if case == "ctpf_cfg" else "beta"
+    np.testing.assert_allclose(np.asarray(z[table]).reshape(V, K), np.array(ref[table]).reshape(V, K), rtol=1e-7, atol=1e-300)
+    for name in ("alpha", "mu", "bet", "vav", "dalet", "het"):
+        if name in ref and name in z:
+            np.testing.assert_allclose(np.asarray(z[name]), np.array(ref[name]), rtol=1e-7)

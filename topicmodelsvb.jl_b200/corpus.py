@@ -92,6 +92,18 @@ class Corpus:
         self.V, self.U = c.V, c.U
         return self
 
+    def copy(self) -> "Corpus":
+        """copy(corp) as the model constructors take it (gpuLDA.jl:84): documents and their vectors are duplicated, so editing
+        the caller's corpus after construction does not change what the model trains on.  A corpus wrapped from a flattened
+        CSR (`from_csr`, `readcorp`) is immutable by construction (NamedTuple of arrays nobody writes): shared, not duplicated."""
+        if self.docs is None:
+            return self
+        new = Corpus.__new__(Corpus)
+        new.docs = [Document(d.terms.copy(), d.counts.copy(), d.readers.copy(), d.ratings.copy(), d.title) for d in self.docs]
+        new._flat = None
+        new.V, new.U = self.V, self.U
+        return new
+
     def __len__(self):
         return self._flat.M if self.docs is None else len(self.docs)
 
@@ -156,18 +168,55 @@ def readcorp(docfile: str, vocabfile: Optional[str] = None, userfile: Optional[s
         roff = np.ctypeslib.as_array(c.R_cumsum, shape=(M + 1,)).copy()
         t32, c32 = arr(c.terms, c.nnz, np.int32), arr(c.counts, c.nnz, np.int32)
         r32, g32 = arr(c.readers, c.nr, np.int32), arr(c.ratings, c.nr, np.int32)
-        nlines = lambda p: sum(1 for _ in open(p, "rb"))
-        V = nlines(vocabfile) if vocabfile else int(c.max_term)
-        U = nlines(userfile) if userfile else int(c.max_reader)
-        if int(c.max_term) > V:
-            raise CorpusError("documents contain term keys not found in corpus vocabulary (see fixcorp! function).")
-        if int(c.max_reader) > U:
-            raise CorpusError("documents contain user keys not found in corpus users (see fixcorp! function).")
+        vkeys = _read_keys(vocabfile, "vocab") if vocabfile else None
+        ukeys = _read_keys(userfile, "user") if userfile else None
+        V = _key_count(vkeys, t32, int(c.max_term), "vocab", "term keys not found in corpus vocabulary")
+        U = _key_count(ukeys, r32, int(c.max_reader), "user", "user keys not found in corpus users")
     finally:
         lib.tmvb_free_csr(C.byref(c))
     corp = Corpus.from_csr(CSR(M, V, off, t32.astype(np.int64), c32.astype(np.int64), U, roff, r32.astype(np.int64), g32.astype(np.int64)))
     corp._packed32 = (t32, c32)   # what flat32() pins on first use: no second narrowing pass
     return corp
+
+
+def _read_keys(path: str, what: str) -> np.ndarray:
+    """First column of a `key<TAB>name` file as the reference reads it (readdlm + Dict(zip(keys, names)), Corpus.jl:301-315):
+    blank lines are skipped, a repeated key keeps one entry, keys must be positive integers (decimal, or with Julia's
+    0x / 0o / 0b prefixes as parse(Int, .) accepts them)."""
+    keys = []
+    with open(path, "r", encoding="utf-8", errors="replace") as f:
+        for line in f:
+            line = line.rstrip("\r\n")
+            if not line.strip():
+                continue
+            tok = line.split("\t", 1)[0].strip()
+            try:
+                keys.append(int(tok, 0) if tok[:2].lower() in ("0x", "0o", "0b") else int(tok))
+            except ValueError:
+                try:
+                    v = float(tok)          # readdlm yields Float64 for a numeric-looking column; Dict{Int,...} converts integral values
+                    if v != int(v):
+                        raise ValueError
+                    keys.append(int(v))
+                except ValueError:
+                    raise CorpusError("all %s keys must be positive integers." % what)
+    k = np.unique(np.asarray(keys, dtype=np.int64))
+    if k.size and k[0] <= 0:
+        raise CorpusError("all %s keys must be positive integers." % what)
+    return k
+
+
+def _key_count(keys, used0, max_used1, what, missing_msg) -> int:
+    """Size of the vocabulary / user set: the number of distinct keys (length of the reference's Dict), after the check_corp
+    invariants (Corpus.jl:111-122): used keys are a subset of the key set; the keys form the unit range 1:length."""
+    if keys is None:
+        return max_used1
+    n = int(keys.size)
+    if used0.size and not np.all(np.isin(np.unique(used0) + 1, keys, assume_unique=True)):
+        raise CorpusError("documents contain %s (see fixcorp! function)." % missing_msg)
+    if n != (int(keys[-1]) if n else 0):
+        raise CorpusError("corpus %s keys must form unit range starting at 1 (see fixcorp! function)." % what)
+    return n
 
 
 def check_corp(corp: Corpus) -> None:

@@ -46,6 +46,7 @@ class gpuLDA:
         if not (isinstance(K, (int, np.integer)) and K > 0):
             raise ValueError("number of topics must be a positive integer.")  # gpuLDA.jl:47
         M, V, _ = corp.size()
+        corp = corp.copy()      # the reference stores copy(corp): later edits of the caller's corpus do not reach the model
         flat = corp.flat()
         self.K, self.M, self.V = int(K), int(M), int(V)
         self.N = np.diff(flat.N_cumsum).astype(np.int64)
@@ -307,6 +308,10 @@ def train(model: gpuLDA, iter: int = 150, tol: float = 1.0, niter: int = 1000, n
         raise ValueError("iteration parameters must be nonnegative.")
     if not ((isinstance(checkelbo, (int, np.integer)) and checkelbo > 0) or checkelbo == math.inf):
         raise ValueError("checkelbo parameter must be a positive integer or Inf.")
+    if iter > 0 and viter < 1:
+        # the reference accepts viter = 0 and then scatters whatever phi the previous call left behind (CPU: a scratch matrix of
+        # another document's shape); the fused E-step has no stored phi, so the degenerate case is refused up front
+        raise ValueError("viter must be at least 1 (the fused E-step does not keep a stale phi to scatter).")
     if model.corp.flat().nnz == 0 and (model.reducer is None):
         iter = 0                                               # gpuLDA.jl:352
     else:
