@@ -348,6 +348,201 @@ __device__ __forceinline__ void reg_final(const RegDoc<LPT, CPL, NR> &rd, float 
     }
 }
 
+// ---------------------------------------------------------------- bare MUFU forms for the per-sweep hot path ----------
+// __fdividef / __logf / __expf carry range guards (denormal scaling: 4-6 extra instructions each); the arguments of the
+// K phase are normal numbers by construction (gamma >= alpha + eps, products of (x + k), exp of a non-positive number whose
+// flush to zero below 2^-126 is harmless), so the bare approximations are used: one MUFU and at most one multiply each.
+__device__ __forceinline__ float rcp_ftz(float x)
+{
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ float lg2_ftz(float x)
+{
+    float r;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ float ex2_ftz(float x)
+{
+    float r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+
+// psi(x) for two arguments in packed fp32, branch-free: the shift-by-6 rational recurrence of psi_lgamma (one reciprocal
+// instead of six) and the 3-term asymptotic series, selected per argument.  Same arithmetic as psi_pair up to the guards.
+__device__ __forceinline__ void psi_pair_fast(float x0, float x1, float &p0, float &p1)
+{
+    const f32x2 x = pk2(x0, x1);
+    f32x2 P = x, D = pk2(1.0f, 1.0f);
+#pragma unroll
+    for (int k = 1; k < 6; k++) {
+        const f32x2 f = add2(x, pk2((float)k, (float)k));
+        D = fma2(D, f, P);
+        P = mul2(P, f);
+    }
+    float P0, P1, D0, D1;
+    unpk2(P, P0, P1);
+    unpk2(D, D0, D1);
+    const bool lo0 = x0 < 6.0f, lo1 = x1 < 6.0f;
+    const float y0 = lo0 ? x0 + 6.0f : x0, y1 = lo1 ? x1 + 6.0f : x1;
+    const float c0 = lo0 ? D0 * rcp_ftz(P0) : 0.0f, c1 = lo1 ? D1 * rcp_ftz(P1) : 0.0f;
+    const f32x2 t = pk2(rcp_ftz(y0), rcp_ftz(y1)), nt2 = mul2(mul2(t, t), pk2(-1.0f, -1.0f));
+    // psi = ln y - t/2 - t2 (1/12 - t2 (1/120 - t2/252)) - corr
+    const f32x2 in1 = fma2(nt2, pk2(3.9682539683e-3f, 3.9682539683e-3f), pk2(8.3333333333e-3f, 8.3333333333e-3f));
+    const f32x2 in2 = fma2(nt2, in1, pk2(8.3333333333e-2f, 8.3333333333e-2f));
+    f32x2 r = fma2(t, pk2(-0.5f, -0.5f), pk2(fmaf(lg2_ftz(y0), 0.69314718056f, -c0), fmaf(lg2_ftz(y1), 0.69314718056f, -c1)));
+    r = fma2(nt2, in2, r);
+    unpk2(r, p0, p1);
+}
+
+// s = init + sum_i T_i e_i over this lane's chunks in two FFMA2 chains (FFMA2 issues every other cycle, so two chains of a
+// round plus the other rounds in flight cover its latency), then across the LPT lanes of the token.  `init` carries K eps in
+// one lane of the token's group (the "@positive" epsilon of LDA.jl:150-154 summed over topics).
+template <int LPT, int CPL>
+__device__ __forceinline__ float tok_dot2(const ulonglong2 (&b)[CPL], const f32x2 (&e01)[CPL], const f32x2 (&e23)[CPL], f32x2 init)
+{
+    f32x2 sa = init, sb = 0ull;
+#pragma unroll
+    for (int m = 0; m < CPL; m++) {
+        sa = fma2(b[m].x, e01[m], sa);
+        sb = fma2(b[m].y, e23[m], sb);
+    }
+    return group_sum<LPT>(hsum2(add2(sa, sb)));
+}
+
+// ---------------------------------------------------------------- hybrid documents: registers + shared-memory tile ----------
+// The register-resident rounds of a document (RegDoc) are complemented by a shared-memory tile for the tokens beyond
+// W * NR * S: tile round q (tokens q S + ts of the tile) belongs to warp q % W.  Registers hold what the register file has
+// room for at the target occupancy; the tile holds the rest, so one kernel serves every document length without
+// falling off a cliff (a pure tile kernel is bound by the shared-memory pipe, a pure register kernel by occupancy).
+//
+// Sweep over the register rounds that also returns s_n (kept for the scatter pass: the last sweep's s_n is the
+// normaliser of the phi that update_beta! scatters, LDA.jl:129-132, so the final pass needs no second dot product).
+template <int LPT, int CPL, int NR, bool EPS>
+__device__ __forceinline__ void reg_sweep_keep(const RegDoc<LPT, CPL, NR> &rd, f32x2 keps_init, const f32x2 (&e01)[CPL], const f32x2 (&e23)[CPL],
+                                               f32x2 (&g01)[CPL], f32x2 (&g23)[CPL], float &tsum, float (&s_keep)[NR])
+{
+    static_assert(EPS, "without the epsilon a padded token (all-zero row) would divide by zero");
+    float t[NR];
+#pragma unroll
+    for (int j = 0; j < NR; j++) {
+        const float s = tok_dot2<LPT, CPL>(rd.b[j], e01, e23, keps_init);
+        s_keep[j] = s;
+        t[j] = rd.c[j] * rcp_ftz(s);   // padded tokens: c = 0, s = K eps > 0
+    }
+#pragma unroll
+    for (int j = 0; j < NR; j++) {
+        const f32x2 t2 = pk2(t[j], t[j]);
+#pragma unroll
+        for (int m = 0; m < CPL; m++) {
+            g01[m] = fma2(rd.b[j][m].x, t2, g01[m]);
+            g23[m] = fma2(rd.b[j][m].y, t2, g23[m]);
+        }
+        tsum += t[j];
+    }
+}
+
+// scatter pass over the register rounds from the kept normalisers (cf. reg_final)
+template <int LPT, int CPL, int NR, bool EPS, bool ELBO>
+__device__ __forceinline__ void reg_final_keep(const RegDoc<LPT, CPL, NR> &rd, float *__restrict__ stats, int K, int K_ld, int kl,
+                                               const f32x2 (&e01)[CPL], const f32x2 (&e23)[CPL], const float (&s_keep)[NR], float &ent, int dbg)
+{
+    const float eps = EPS ? TMVB_EPS : 0.0f;
+    const f32x2 eps2 = pk2(eps, eps);
+#pragma unroll
+    for (int j = 0; j < NR; j++) {
+        if (rd.c[j] > 0.0f) {
+            const float s = s_keep[j];
+            const float t = EPS ? fast_div_pos(rd.c[j], s) : __fdividef(rd.c[j], s);
+            const f32x2 t2 = pk2(t, t);
+            float *srow = stats + (size_t)rd.term[j] * K_ld + 4 * kl;
+#pragma unroll
+            for (int m = 0; m < CPL; m++) {
+                if (4 * (kl + LPT * m) < K) {
+                    float px, py, pz, pw;
+                    unpk2(mul2(t2, fma2(rd.b[j][m].x, e01[m], eps2)), px, py);
+                    unpk2(mul2(t2, fma2(rd.b[j][m].y, e23[m], eps2)), pz, pw);
+                    if (!(dbg & 1)) red_add_v4(srow + 4 * LPT * m, px, py, pz, pw);
+                }
+            }
+            if (ELBO && kl == 0) ent += rd.c[j] * __logf(s);
+        }
+    }
+}
+
+// the tile part of a sweep: rounds q = q0, q0 + qstep, ... of the shared-memory tile (n_tile tokens), packed accumulators
+template <int LPT, int CPL, bool EPS>
+__device__ __forceinline__ void tile_sweep_pk(const float *tile, const float *cnt_s, int n_tile, int RS, f32x2 keps_init, int CH, int ts, int kl, int q0,
+                                              int qstep, const f32x2 (&e01)[CPL], const f32x2 (&e23)[CPL], f32x2 (&g01)[CPL], f32x2 (&g23)[CPL],
+                                              float &tsum)
+{
+    static_assert(EPS, "without the epsilon a padded token would divide by zero");
+    constexpr int S = 32 / LPT;
+    const ulonglong2 zero = make_ulonglong2(0ull, 0ull);
+    const int rounds = (n_tile + S - 1) / S;
+#pragma unroll 1
+    for (int q = q0; q < rounds; q += qstep) {
+        const int n = q * S + ts;
+        const bool ok = n < n_tile;
+        const ulonglong2 *row = reinterpret_cast<const ulonglong2 *>(tile + (ok ? n : 0) * RS) + kl;
+        ulonglong2 b[CPL];
+#pragma unroll
+        for (int m = 0; m < CPL; m++) b[m] = (m < CPL - 1 || kl + LPT * m < CH) ? row[LPT * m] : zero;
+        const float c = ok ? cnt_s[n] : 0.0f;
+        const float s = tok_dot2<LPT, CPL>(b, e01, e23, keps_init);
+        const float t = c * rcp_ftz(s);
+        const f32x2 t2 = pk2(t, t);
+#pragma unroll
+        for (int m = 0; m < CPL; m++) {
+            g01[m] = fma2(b[m].x, t2, g01[m]);
+            g23[m] = fma2(b[m].y, t2, g23[m]);
+        }
+        tsum += t;
+    }
+}
+
+// the tile part of the scatter pass (the "ELBO = 2" form of tok_final: only sum_n c_n ln s_n is accumulated)
+template <int LPT, int CPL, bool EPS, bool ELBO>
+__device__ __forceinline__ void tile_final_pk(const float *tile, const float *cnt_s, const int *term_s, float *__restrict__ stats, int n_tile,
+                                              int RS, int K, int K_ld, int CH, int ts, int kl, int q0, int qstep, const f32x2 (&e01)[CPL],
+                                              const f32x2 (&e23)[CPL], float &ent, int dbg)
+{
+    constexpr int S = 32 / LPT;
+    const float Keps = EPS ? (float)K * TMVB_EPS : 0.0f;
+    const float eps = EPS ? TMVB_EPS : 0.0f;
+    const f32x2 eps2 = pk2(eps, eps);
+    const ulonglong2 zero = make_ulonglong2(0ull, 0ull);
+    const int rounds = (n_tile + S - 1) / S;
+    for (int q = q0; q < rounds; q += qstep) {
+        const int n = q * S + ts;
+        const bool ok = n < n_tile;
+        const ulonglong2 *row = reinterpret_cast<const ulonglong2 *>(tile + (ok ? n : 0) * RS) + kl;
+        ulonglong2 b[CPL];
+#pragma unroll
+        for (int m = 0; m < CPL; m++) b[m] = (m < CPL - 1 || kl + LPT * m < CH) ? row[LPT * m] : zero;
+        const float s = tok_dot<LPT, CPL>(b, e01, e23) + Keps;
+        if (ok) {
+            const float c = cnt_s[n];
+            const float t = EPS ? fast_div_pos(c, s) : __fdividef(c, s);
+            const f32x2 t2 = pk2(t, t);
+            float *srow = stats + (size_t)term_s[n] * K_ld + 4 * kl;
+#pragma unroll
+            for (int m = 0; m < CPL; m++) {
+                if (4 * (kl + LPT * m) < K) {
+                    float px, py, pz, pw;
+                    unpk2(mul2(t2, fma2(b[m].x, e01[m], eps2)), px, py);
+                    unpk2(mul2(t2, fma2(b[m].y, e23[m], eps2)), pz, pw);
+                    if (!(dbg & 1)) red_add_v4(srow + 4 * LPT * m, px, py, pz, pw);
+                }
+            }
+            if (ELBO && kl == 0) ent += c * __logf(s);
+        }
+    }
+}
+
 // psi(x) for two arguments at once in packed fp32 (FFMA2 / FMUL2 / FADD2; the MUFU ops stay scalar): the same
 // shift-by-6 rational recurrence and 3-term asymptotic series as psi_lgamma<false, true>.
 __device__ __forceinline__ void psi_pair(float x0, float x1, float &p0, float &p1)

@@ -19,555 +19,10 @@
 #include <stdlib.h>
 #include <string.h>
 
-#include "tmvb_comm.cuh"
-#include "tmvb_shard.cuh"
+#include "tmvb_lda_estep.cuh"
+#include "tmvb_lda_hyb.cuh"
 
 namespace tmvb {
-
-struct LdaDev {
-    int K, K_ld, V, RS;
-    long long M;
-    const float *beta;
-    const float *alpha;
-    float *stats;
-    const long long *doc_off;
-    const int *terms;
-    const float *counts;
-    float *Elogtheta, *Elogtheta_old, *gamma;
-    double *small;
-    int viter;
-    float vtol;
-    int stage_bulk;  // 1: TMA bulk row copies (UBLKCP), 0: 16-byte cp.async (LDGSTS)
-    int dbg;         // developer probes: bit0 skip the scatter, bit1 skip the final pass
-};
-
-// shared memory of one E-step CTA beyond the tile: 256-byte header (mbarrier, next-document slot, per-warp partial sums) |
-// gs [W][S][RS] | e_s [RS]
-static size_t lda_fixed_smem(int RS, int lpt, int W) { return 256 + (size_t)W * (32 / lpt) * RS * 4 + (size_t)RS * 4; }
-
-// documents drawn from a bucket's work counter per atomic
-constexpr int kDocChunk = 8;
-
-template <int W>
-__device__ __forceinline__ void cta_sync()
-{
-    if (W == 1)
-        __syncwarp();
-    else
-        __syncthreads();
-}
-
-// W warps cooperate on one document (W = 1 for short documents, 2 for the rest): they share the staged tile, split the
-// token rounds (warp w takes rounds w, w+W, ...) and split the topics of the K phase (thread t owns topics t + 32W r).
-// Two CTA barriers per sweep: after the per-stream partial K-vectors are in shared memory, and after exp(Elogtheta) and
-// the partial convergence sums are.
-template <int LPT, int CPL, int W, bool ELBO>
-__global__ void __launch_bounds__(32 * W, W == 2 ? 8 : 1) lda_estep_kernel(const LdaDev p, int doc_begin, int doc_end, int cap, int cap2, int *counter)
-{
-    constexpr int S = 32 / LPT;                             // token streams per warp
-    constexpr int T = 32 * W;                               // threads per document
-    constexpr int R = (4 * LPT * CPL + T - 1) / T;          // K-phase topics per thread
-    constexpr int RV = (R % 2 == 0) ? 2 : 1;                // ... owned as RV consecutive topics (LDS.64 / FADD2 owner sums)
-#define TOPIC(r) (RV * (tid + T * ((r) / RV)) + ((r) % RV))
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int kl = lane % LPT, ts = lane / LPT;
-    const int K = p.K, K_ld = p.K_ld, CH = K_ld >> 2, RS = p.RS;
-    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
-    (void)cap2;
-
-    unsigned long long *mbar = reinterpret_cast<unsigned long long *>(smem_raw);
-    int *next_s = reinterpret_cast<int *>(smem_raw + 16);
-    float *csum_s = reinterpret_cast<float *>(smem_raw + 32);        // [W <= 8]
-    float *tsum_s = reinterpret_cast<float *>(smem_raw + 64);        // [W <= 8]
-    unsigned *dsum_s = reinterpret_cast<unsigned *>(smem_raw + 96);  // [2][W <= 8]
-    float *gs = reinterpret_cast<float *>(smem_raw + 256);           // [W][S][RS]
-    float *e_s = gs + (size_t)W * S * RS;                            // [RS]
-    float *tile = e_s + RS;                                          // [cap][RS]
-    float *cnt_s = tile + (size_t)cap * RS;                          // [cap]
-    int *term_s = reinterpret_cast<int *>(cnt_s + cap);              // [cap]
-
-    // K-phase state: topics i = TOPIC(r)
-    float alpha_k[R], Eold_k[R], Enew_k[R], e_k[R], gam_k[R];
-    double esum_k[R];
-    float asum = 0.0f;
-    for (int i = lane; i < K; i += 32) asum += p.alpha[i];
-    asum = warp_sum(asum);
-#pragma unroll
-    for (int r = 0; r < R; r++) {
-        const int i = TOPIC(r);
-        alpha_k[r] = (i < K) ? p.alpha[i] : 0.0f;
-        esum_k[r] = 0.0;
-        Enew_k[r] = gam_k[r] = Eold_k[r] = e_k[r] = 0.0f;
-    }
-    // convergence test in fixed point: sum_i (dE_i)^2 * (2^20 / vtol^2) < 2^20, summed with one REDUX per warp
-    const float dscale = (p.vtol > 0.0f) ? 1048576.0f / (p.vtol * p.vtol) : 0.0f;
-    double elbo_thr = 0.0;
-    unsigned long long sweeps_thr = 0;
-    unsigned phase = 0;
-    if (p.stage_bulk && tid == 0) mbar_init(mbar, 1);
-    cta_sync<W>();
-
-    // documents per draw: kDocChunk, fewer when the launch has less than ~4 draws per CTA (multi-GPU shards: balance over atomics)
-    const int chunk = max(1, min(kDocChunk, (doc_end - doc_begin) / (4 * (int)gridDim.x)));
-    int d_next = 0, d_lim = 0;
-    for (;;) {
-        // documents are drawn from the bucket's work counter kDocChunk at a time: one same-address atomic per document
-        // serialises in L2 (128 804 of them cost ~0.4 ms of a 2.4 ms E-step)
-        if (d_next >= d_lim) {
-            if (W == 1) {
-                if (lane == 0) d_next = doc_begin + atomicAdd(counter, chunk);
-                d_next = __shfl_sync(0xffffffffu, d_next, 0);
-            } else {
-                if (tid == 0) *next_s = doc_begin + atomicAdd(counter, chunk);
-                __syncthreads();
-                d_next = *next_s;
-            }
-            d_lim = min(d_next + chunk, doc_end);
-        }
-        if (d_next >= doc_end) break;
-        const int d = d_next++;
-        const long long o = p.doc_off[d];
-        const int Nd = (int)(p.doc_off[d + 1] - o);
-        const int ns = min(Nd, cap);
-        const bool ovf = Nd > cap;
-
-        // stage the document: term ids + counts, then its K x N_d slab of beta -- one TMA bulk copy per term row
-        // (a row is K_ld*4 contiguous bytes in HBM/L2), completion tracked by an mbarrier
-        float csum = 0.0f;
-        for (int n = tid; n < Nd; n += T) {
-            const float c = p.counts[o + n];
-            csum += c;
-            if (n < ns) {
-                term_s[n] = p.terms[o + n];
-                cnt_s[n] = c;
-            }
-        }
-        csum = warp_sum(csum);
-        if (W > 1 && lane == 0) csum_s[warp] = csum;
-        if (p.stage_bulk) {
-            fence_proxy_async_smem();
-            cta_sync<W>();
-            if (tid == 0) mbar_arrive_expect_tx(mbar, (unsigned)(ns * K_ld * 4));
-            cta_sync<W>();
-            for (int n = tid; n < ns; n += T) bulk_g2s(tile + n * RS, p.beta + (size_t)term_s[n] * K_ld, (unsigned)(K_ld * 4), mbar);
-        } else {
-            cta_sync<W>();
-            for (int c = tid; c < ns * CH; c += T) {
-                const int n = c / CH, q = c - n * CH;
-                cp_async16(tile + n * RS + 4 * q, p.beta + (size_t)term_s[n] * K_ld + 4 * q);
-            }
-            cp_async_commit();
-        }
-#pragma unroll
-        for (int r = 0; r < R; r++) {
-            const int i = TOPIC(r);
-            Eold_k[r] = (i < K) ? p.Elogtheta[(size_t)d * K_ld + i] : 0.0f;
-            e_k[r] = (i < K) ? expf(Eold_k[r]) : 0.0f;
-            if (i < K_ld) e_s[i] = e_k[r];
-        }
-        if (W > 1) {
-            csum = 0.0f;
-#pragma unroll
-            for (int w = 0; w < W; w++) csum += csum_s[w];
-        }
-        // sum(gamma_d) = sum(alpha) + sum_n c_n + K*EPS whatever phi is (each phi column sums to one), so
-        // digamma(sum gamma) (LDA.jl:138) is a per-document constant
-        const float gsum = (asum + csum) + (float)K * TMVB_EPS;
-        const float psi_sum = psi_lgamma<false>(gsum).psi;
-        if (p.stage_bulk) {
-            mbar_wait(mbar, phase);
-            phase ^= 1u;
-        } else {
-            cp_async_wait_all();
-        }
-        cta_sync<W>();
-
-        TokArgs ta;
-        ta.tile = tile;
-        ta.cnt_s = cnt_s;
-        ta.term_s = term_s;
-        ta.gtable = p.beta;
-        ta.gterms = p.terms + o;
-        ta.gcounts = p.counts + o;
-        ta.stats = p.stats;
-        ta.Nd = Nd;
-        ta.cap = cap;
-        ta.rounds = (Nd + S - 1) / S;
-        ta.K = K;
-        ta.K_ld = K_ld;
-        ta.RS = RS;
-        ta.dbg = p.dbg;
-        ta.r0 = warp;
-        ta.rstep = W;
-
-        float4 e[CPL];
-        int v = 0;
-        for (;;) {
-            // ---- token phase: update_phi! + the phi*counts product of update_gamma! (LDA.jl:143-154)
-#pragma unroll
-            for (int m = 0; m < CPL; m++)
-                e[m] = (m < CPL - 1 || kl + LPT * m < CH) ? reinterpret_cast<const float4 *>(e_s)[kl + LPT * m] : zero4;
-            float4 g[CPL];
-            float tsum = 0.0f;
-#pragma unroll
-            for (int m = 0; m < CPL; m++) g[m] = zero4;
-            if (!ovf)
-                tok_sweep<LPT, CPL, false, true, (W == 2 ? 1 : kSweepUnroll)>(ta, ts, kl, e, g, tsum);
-            else
-                tok_sweep<LPT, CPL, true, true, (W == 2 ? 1 : kSweepUnroll)>(ta, ts, kl, e, g, tsum);
-#pragma unroll
-            for (int m = 0; m < CPL; m++)
-                if (m < CPL - 1 || kl + LPT * m < CH) reinterpret_cast<float4 *>(gs + (warp * S + ts) * RS)[kl + LPT * m] = g[m];
-            float tt = across_streams_sum<LPT>(tsum);
-            if (W > 1 && lane == 0) tsum_s[warp] = tt;
-            cta_sync<W>();  // also orders this sweep's reads of e_s before the K phase overwrites it
-            if (W > 1) {
-                tt = 0.0f;
-#pragma unroll
-                for (int w = 0; w < W; w++) tt += tsum_s[w];
-            }
-
-            // ---- K phase: update_gamma! (LDA.jl:143-146), update_Elogtheta! (LDA.jl:136-139)
-            float dpart = 0.0f;
-            float e_new[R];
-            float g_own[R];
-            if (RV == 2) {
-#pragma unroll
-                for (int r = 0; r < R; r += 2) {
-                    const float2 gg = (TOPIC(r) < K_ld) ? owner_sum2<W * S>(gs, RS, TOPIC(r)) : make_float2(0.f, 0.f);
-                    g_own[r] = gg.x;
-                    g_own[r + (R > 1 ? 1 : 0)] = gg.y;
-                }
-            } else {
-#pragma unroll
-                for (int r = 0; r < R; r++) g_own[r] = (TOPIC(r) < K) ? owner_sum<W * S>(gs, RS, TOPIC(r)) : 0.0f;
-            }
-#pragma unroll
-            for (int r = 0; r < R; r++) {
-                const int i = TOPIC(r);
-                const float gi = (i < K) ? g_own[r] : 0.0f;
-                // gamma = EPS + (alpha + phi*counts),   phi*counts = e .* g + eps * sum_n t_n
-                gam_k[r] = (i < K) ? (alpha_k[r] + fmaf(e_k[r], gi, TMVB_EPS * tt)) + TMVB_EPS : 1.0f;
-                Enew_k[r] = psi_lgamma<false, true>(gam_k[r]).psi - psi_sum;
-                e_new[r] = 0.0f;
-                if (i < K) {
-                    const float df = Enew_k[r] - Eold_k[r];
-                    dpart = fmaf(df, df, dpart);
-                    e_new[r] = fast_exp(Enew_k[r]);
-                }
-            }
-            v++;
-            // LDA.jl:175: stop when ||Elogtheta - Elogtheta_old||_2 < vtol (or after viter sweeps)
-            if (v >= p.viter) break;
-            // per-lane clamp 2^25 keeps the integer sum over up to 64 threads below 2^31
-            unsigned dtot = (dscale > 0.0f) ? __reduce_add_sync(0xffffffffu, (unsigned)fminf(dpart * dscale, 33554432.0f)) : 0xffffffffu;
-            if (W > 1) {
-                // tentatively publish exp(Elogtheta_new): the token phase keeps e in registers, so overwriting e_s is
-                // harmless even if the document turns out to have converged
-#pragma unroll
-                for (int r = 0; r < R; r++)
-                    if (TOPIC(r) < K_ld) e_s[TOPIC(r)] = e_new[r];
-                if (lane == 0) dsum_s[(v & 1) * W + warp] = dtot;
-                __syncthreads();
-                dtot = 0;
-#pragma unroll
-                for (int w = 0; w < W; w++) {
-                    const unsigned x = dsum_s[(v & 1) * W + w];
-                    dtot = (x > 0x7fffffffu - dtot) ? 0x7fffffffu : dtot + x;
-                }
-                if (dscale > 0.0f && dtot < 1048576u) break;
-#pragma unroll
-                for (int r = 0; r < R; r++) {
-                    Eold_k[r] = Enew_k[r];
-                    e_k[r] = e_new[r];
-                }
-            } else {
-                if (dscale > 0.0f && dtot < 1048576u) break;
-#pragma unroll
-                for (int r = 0; r < R; r++) {
-                    Eold_k[r] = Enew_k[r];
-                    e_k[r] = e_new[r];
-                    if (TOPIC(r) < K_ld) e_s[TOPIC(r)] = e_new[r];
-                }
-                __syncwarp();
-            }
-        }
-
-        // update_beta!(model, d) (LDA.jl:129-132): scatter the last phi, weighted by counts
-        if (!(p.dbg & 2)) {
-            float ent = 0.0f;
-            if (!ovf)
-                tok_final<LPT, CPL, false, true, (ELBO ? 2 : 0)>(ta, ts, kl, e, ent);
-            else
-                tok_final<LPT, CPL, true, true, (ELBO ? 2 : 0)>(ta, ts, kl, e, ent);
-            if (ELBO) elbo_thr += (double)ent;
-        }
-
-        float a = 0.0f;
-#pragma unroll
-        for (int r = 0; r < R; r++) {
-            const int i = TOPIC(r);
-            if (i < K_ld) {
-                const bool ok = i < K;
-                p.gamma[(size_t)d * K_ld + i] = ok ? gam_k[r] : 0.0f;
-                p.Elogtheta[(size_t)d * K_ld + i] = ok ? Enew_k[r] : 0.0f;
-                p.Elogtheta_old[(size_t)d * K_ld + i] = ok ? Eold_k[r] : 0.0f;
-                if (ok) {
-                    esum_k[r] += (double)Enew_k[r];
-                    // lnG(gamma_i), and the Elogtheta_old part of the entropy of the last phi:
-                    // sum_n c_n phi_ni ln e_i = (gamma_i - alpha_i) Elogtheta_old_i
-                    if (ELBO) a += psi_lgamma<true>(gam_k[r]).lg - (gam_k[r] - alpha_k[r]) * Eold_k[r];
-                }
-            }
-        }
-        // Dirichlet entropy (utils.jl:163-180) + Elogpz (LDA.jl:57-60): with gamma = alpha + phi*c and
-        // psi(gamma_i) = Elogtheta_i + psi(sum gamma) they collapse to
-        //   sum_i lnG(gamma_i) - lnG(sum gamma) + sum_i (1 - alpha_i) Elogtheta_i ;
-        // the last sum is linear in sum_d Elogtheta_d and is added by lda_alpha_kernel in fp64.
-        // -Elogqz (LDA.jl:76-79) = sum_n c_n H(phi_n) with phi_ni = u_ni / s_n, ln u_ni = ln beta_old_i,w + Elogtheta_old_i:
-        //   sum_n c_n ln s_n  [tok_final]  - sum_i (gamma_i - alpha_i) Elogtheta_old_i  [above]
-        //   - sum_ij S_ij ln beta_old_ij  [normalize_kernel, over the reduced statistics]
-        if (ELBO) {
-            if (tid == 0) a -= psi_lgamma<true>(gsum).lg;
-            elbo_thr += (double)a;
-        }
-        if (tid == 0) sweeps_thr += (unsigned long long)v;
-        cta_sync<W>();  // the tile, e_s and gs are free for the next document
-    }
-
-    // flush the accumulators
-    if (ELBO) {
-        const double tot = warp_sum_d(elbo_thr);
-        if (lane == 0 && tot != 0.0) atomicAdd(p.small + K_ld, tot);
-    }
-#pragma unroll
-    for (int r = 0; r < R; r++) {
-        const int i = TOPIC(r);
-        if (i < K && esum_k[r] != 0.0) atomicAdd(p.small + i, esum_k[r]);
-    }
-    if (tid == 0 && sweeps_thr) atomicAdd(p.small + K_ld + 1, (double)sweeps_thr);
-}
-#undef TOPIC
-
-// ------------------------------------------------------------------ register-resident E-step ----------
-// Same per-document algorithm as lda_estep_kernel for documents of at most W * NR * S tokens (NSF: 99.9 % of the
-// documents), with the document's K x N_d slab of beta held in REGISTERS for all sweeps (RegDoc, tmvb_estep.cuh) instead of
-// a shared-memory tile: no LDS in the token phase (the shared-memory data pipe was the busiest unit of the tile kernel,
-// 58 % of peak), no staging loop, and the NR rounds of a sweep fully unrolled.  Shared memory only carries the per-sweep
-// exchange between the token layout and the K-phase layout:
-//   gs [W][S][RS] per-stream partial K-vectors | xs [W][RS] per-warp sums | e_s [RS] exp(Elogtheta)
-// The K phase runs on warp 0 alone, lane l owning topics 2l and 2l+1 (K_ld <= 64) so that digamma is evaluated for
-// both in packed fp32 (psi_pair).  Barriers per sweep: two (W > 1) -- after the per-warp sums, after e_s / the stop flag.
-static size_t lda_reg_smem(int RS, int lpt, int W) { return 128 + (size_t)W * (32 / lpt) * RS * 4 + (size_t)W * RS * 4 + (size_t)RS * 4; }
-
-// resident CTAs per SM the register allocation is held to (the tile alone is 4 CPL NR registers per thread)
-// (measured per launch, NSF K=50, first iteration: holding the 3-round variants to 168 registers pays -- (2,3) 955 -> 860 us,
-// (4,3) 518 -> 473 us -- while the 4-round variants spill under a cap and are faster left at ~250 registers:
-// (2,4) 538 vs 617 us, (1,4) 412 vs 498 us)
-constexpr int lda_reg_min_ctas(int W, int NR) { return W == 1 ? (NR <= 2 ? 12 : 8) : W == 2 ? (NR <= 3 ? 6 : 4) : W == 4 ? (NR <= 3 ? 3 : 2) : 1; }
-
-template <int LPT, int CPL, int W, int NR, bool ELBO>
-__global__ void __launch_bounds__(32 * W, lda_reg_min_ctas(W, NR)) lda_estep_reg_kernel(const LdaDev p, int doc_begin, int doc_end, int cap, int cap2, int *counter)
-{
-    constexpr int S = 32 / LPT;
-    static_assert(4 * LPT * CPL <= 64, "the K phase keeps two topics per lane of warp 0");
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int kl = lane % LPT, ts = lane / LPT;
-    const int K = p.K, K_ld = p.K_ld, CH = K_ld >> 2, RS = p.RS;
-    (void)cap;
-    (void)cap2;
-    int *next_s = reinterpret_cast<int *>(smem_raw + 16);
-    int *flag_s = reinterpret_cast<int *>(smem_raw + 20);
-    float *csum_s = reinterpret_cast<float *>(smem_raw + 32);  // [W <= 8]
-    float *tsum_s = reinterpret_cast<float *>(smem_raw + 64);  // [W <= 8]
-    float *gs = reinterpret_cast<float *>(smem_raw + 128);     // [W][S][RS]
-    float *xs = gs + (size_t)W * S * RS;                       // [W][RS]
-    float *e_s = xs + (size_t)W * RS;                          // [RS]
-    float *gs_w = gs + (size_t)warp * S * RS;
-
-    // K-phase ownership (used by warp 0): topics i0, i0 + 1
-    const int i0 = 2 * lane;
-    const bool in_ld = i0 < K_ld, ok0 = i0 < K, ok1 = i0 + 1 < K;
-    const float a0 = ok0 ? p.alpha[i0] : 0.0f, a1 = ok1 ? p.alpha[i0 + 1] : 0.0f;
-    const float asum = warp_sum(a0 + a1);
-    const float dscale = (p.vtol > 0.0f) ? 1048576.0f / (p.vtol * p.vtol) : 0.0f;
-    const ulonglong2 zero = make_ulonglong2(0ull, 0ull);
-    double esum0 = 0.0, esum1 = 0.0, elbo_thr = 0.0;
-    unsigned long long sweeps_thr = 0;
-
-    // documents per draw: kDocChunk, fewer when the launch has less than ~4 draws per CTA (multi-GPU shards: balance over atomics)
-    const int chunk = max(1, min(kDocChunk, (doc_end - doc_begin) / (4 * (int)gridDim.x)));
-    int d_next = 0, d_lim = 0;
-    long long o_cur = 0, o_end = 0;
-    for (;;) {
-        if (d_next >= d_lim) {  // kDocChunk documents per draw from the work counter (see lda_estep_kernel)
-            if (W == 1) {
-                if (lane == 0) d_next = doc_begin + atomicAdd(counter, chunk);
-                d_next = __shfl_sync(0xffffffffu, d_next, 0);
-            } else {
-                if (tid == 0) *next_s = doc_begin + atomicAdd(counter, chunk);
-                __syncthreads();
-                d_next = *next_s;
-            }
-            d_lim = min(d_next + chunk, doc_end);
-            if (d_next < doc_end) {
-                o_cur = p.doc_off[d_next];
-                o_end = p.doc_off[d_next + 1];
-            }
-        }
-        if (d_next >= doc_end) break;
-        const int d = d_next++;
-        const long long o = o_cur;
-        const int Nd = (int)(o_end - o);
-        // the next document of the chunk starts where this one ends; its end offset is fetched now, used after the sweeps
-        o_cur = o_end;
-        if (d_next < d_lim) o_end = p.doc_off[d_next + 1];
-
-        RegDoc<LPT, CPL, NR> rd;
-        reg_load<LPT, CPL, W, NR>(rd, p.beta, p.terms + o, p.counts + o, Nd, K_ld, warp, ts, kl, p.dbg);
-
-        float Eo0 = 0.0f, Eo1 = 0.0f, En0 = 0.0f, En1 = 0.0f, ek0 = 0.0f, ek1 = 0.0f, gam0 = 1.0f, gam1 = 1.0f;
-        if (warp == 0 && in_ld) {
-            const float2 E = *reinterpret_cast<const float2 *>(p.Elogtheta + (size_t)d * K_ld + i0);
-            Eo0 = ok0 ? E.x : 0.0f;
-            Eo1 = ok1 ? E.y : 0.0f;
-            ek0 = ok0 ? expf(Eo0) : 0.0f;
-            ek1 = ok1 ? expf(Eo1) : 0.0f;
-            *reinterpret_cast<float2 *>(e_s + i0) = make_float2(ek0, ek1);
-        }
-        float csum = 0.0f;
-#pragma unroll
-        for (int j = 0; j < NR; j++) csum += rd.c[j];
-        csum = warp_sum(kl == 0 ? csum : 0.0f);
-        if (W > 1 && lane == 0) csum_s[warp] = csum;
-        cta_sync<W>();
-        if (W > 1) {
-            csum = 0.0f;
-#pragma unroll
-            for (int w = 0; w < W; w++) csum += csum_s[w];
-        }
-        // sum(gamma_d) = sum(alpha) + sum_n c_n + K*EPS whatever phi is: digamma(sum gamma) (LDA.jl:138) is a per-document constant
-        const float gsum = (asum + csum) + (float)K * TMVB_EPS;
-        const float psi_sum = psi_lgamma<false>(gsum).psi;
-
-        f32x2 e01[CPL], e23[CPL];
-        int v = 0;
-        for (;;) {
-            // ---- token phase: update_phi! + the phi*counts product of update_gamma! (LDA.jl:143-154)
-#pragma unroll
-            for (int m = 0; m < CPL; m++) {
-                const ulonglong2 ev = (m < CPL - 1 || kl + LPT * m < CH) ? reinterpret_cast<const ulonglong2 *>(e_s)[kl + LPT * m] : zero;
-                e01[m] = ev.x;
-                e23[m] = ev.y;
-            }
-            f32x2 g01[CPL], g23[CPL];
-            float tsum = 0.0f;
-#pragma unroll
-            for (int m = 0; m < CPL; m++) g01[m] = g23[m] = 0ull;
-            reg_sweep<LPT, CPL, NR, true>(rd, K, e01, e23, g01, g23, tsum);
-#pragma unroll
-            for (int m = 0; m < CPL; m++)
-                if (m < CPL - 1 || kl + LPT * m < CH) reinterpret_cast<ulonglong2 *>(gs_w + ts * RS)[kl + LPT * m] = make_ulonglong2(g01[m], g23[m]);
-            float tt = across_streams_sum<LPT>(tsum);
-            __syncwarp();
-            // per-warp sums over its S token streams, in the K-phase layout
-            float2 gg = in_ld ? owner_sum2<S>(gs_w, RS, i0) : make_float2(0.f, 0.f);
-            if (W > 1) {
-                if (warp > 0) {
-                    if (in_ld) *reinterpret_cast<float2 *>(xs + warp * RS + i0) = gg;
-                    if (lane == 0) tsum_s[warp] = tt;
-                }
-                __syncthreads();
-            }
-            // ---- K phase (warp 0): update_gamma! (LDA.jl:143-146), update_Elogtheta! (LDA.jl:136-139)
-            v++;
-            bool done = v >= p.viter;
-            if (warp == 0) {
-                if (W > 1) {
-#pragma unroll
-                    for (int w = 1; w < W; w++) {
-                        if (in_ld) {
-                            const float2 x = *reinterpret_cast<const float2 *>(xs + w * RS + i0);
-                            gg.x += x.x;
-                            gg.y += x.y;
-                        }
-                        tt += tsum_s[w];
-                    }
-                }
-                // gamma = EPS + (alpha + phi*counts),   phi*counts = e .* g + eps * sum_n t_n
-                gam0 = ok0 ? (a0 + fmaf(ek0, gg.x, TMVB_EPS * tt)) + TMVB_EPS : 1.0f;
-                gam1 = ok1 ? (a1 + fmaf(ek1, gg.y, TMVB_EPS * tt)) + TMVB_EPS : 1.0f;
-                psi_pair(gam0, gam1, En0, En1);
-                En0 -= psi_sum;
-                En1 -= psi_sum;
-                if (!done) {
-                    // LDA.jl:175: stop when ||Elogtheta - Elogtheta_old||_2 < vtol; fixed point, one REDUX
-                    const float d0 = ok0 ? En0 - Eo0 : 0.0f, d1 = ok1 ? En1 - Eo1 : 0.0f;
-                    const float dpart = fmaf(d0, d0, d1 * d1);
-                    const unsigned dtot = (dscale > 0.0f) ? __reduce_add_sync(0xffffffffu, (unsigned)fminf(dpart * dscale, 33554432.0f)) : 0xffffffffu;
-                    done = dscale > 0.0f && dtot < 1048576u;
-                    if (!done) {
-                        Eo0 = En0;
-                        Eo1 = En1;
-                        ek0 = ok0 ? fast_exp(En0) : 0.0f;
-                        ek1 = ok1 ? fast_exp(En1) : 0.0f;
-                        if (in_ld) *reinterpret_cast<float2 *>(e_s + i0) = make_float2(ek0, ek1);
-                    }
-                }
-                if (W > 1 && lane == 0) *flag_s = done ? 1 : 0;
-            }
-            if (W > 1) {
-                __syncthreads();
-                done = *flag_s != 0;
-            } else {
-                __syncwarp();
-            }
-            if (done) break;
-        }
-
-        // update_beta!(model, d) (LDA.jl:129-132): scatter the last phi, weighted by counts
-        if (!(p.dbg & 2)) {
-            float ent = 0.0f;
-            reg_final<LPT, CPL, NR, true, ELBO>(rd, p.stats, K, K_ld, kl, e01, e23, ent, p.dbg);
-            if (ELBO) elbo_thr += (double)ent;
-        }
-        if (warp == 0) {
-            if (in_ld) {
-                *reinterpret_cast<float2 *>(p.gamma + (size_t)d * K_ld + i0) = make_float2(ok0 ? gam0 : 0.0f, ok1 ? gam1 : 0.0f);
-                *reinterpret_cast<float2 *>(p.Elogtheta + (size_t)d * K_ld + i0) = make_float2(ok0 ? En0 : 0.0f, ok1 ? En1 : 0.0f);
-                *reinterpret_cast<float2 *>(p.Elogtheta_old + (size_t)d * K_ld + i0) = make_float2(ok0 ? Eo0 : 0.0f, ok1 ? Eo1 : 0.0f);
-            }
-            float a = 0.0f;
-            if (ok0) {
-                esum0 += (double)En0;
-                if (ELBO) a += psi_lgamma<true>(gam0).lg - (gam0 - a0) * Eo0;
-            }
-            if (ok1) {
-                esum1 += (double)En1;
-                if (ELBO) a += psi_lgamma<true>(gam1).lg - (gam1 - a1) * Eo1;
-            }
-            // the per-document ELBO terms: see lda_estep_kernel
-            if (ELBO) {
-                if (lane == 0) a -= psi_lgamma<true>(gsum).lg;
-                elbo_thr += (double)a;
-            }
-            if (lane == 0) sweeps_thr += (unsigned long long)v;
-        }
-        cta_sync<W>();  // gs, xs, e_s and the header slots are free for the next document
-    }
-
-    if (ELBO) {
-        const double tot = warp_sum_d(elbo_thr);
-        if (lane == 0 && tot != 0.0) atomicAdd(p.small + K_ld, tot);
-    }
-    if (warp == 0) {
-        if (ok0 && esum0 != 0.0) atomicAdd(p.small + i0, esum0);
-        if (ok1 && esum1 != 0.0) atomicAdd(p.small + i0 + 1, esum1);
-        if (lane == 0 && sweeps_thr) atomicAdd(p.small + K_ld + 1, (double)sweeps_thr);
-    }
-}
 
 // ------------------------------------------------------------------ standalone ELBO ---------
 __device__ inline double d_digamma(double x)
@@ -1032,44 +487,30 @@ __global__ void __launch_bounds__(256) lda_exchange_mstep_kernel(const LdaXchg x
     for (int i = tid; i < kCtlPartLen; i += blockDim.x) other[i] = 0.0;
 }
 
-typedef void (*LdaEstepFn)(const LdaDev, int, int, int, int, int *);
-// register-resident variants: (warps per document, rounds per warp), by descending capacity W * NR * S tokens
-// (the 8-warp variant exists for latency, not throughput: one warp would spend ~0.4 ms on a 400-token document, which
-// is the whole E-step of an 8-GPU run)
-constexpr int kNumRegVariants = 7;
-static const int kRegVariant[kNumRegVariants][2] = {{8, 4}, {4, 4}, {4, 3}, {2, 4}, {2, 3}, {1, 4}, {1, 2}};
-#define TMVB_LDA_REG_ROW(L, C, E)                                                                                              \
-    {(LdaEstepFn)lda_estep_reg_kernel<L, C, 8, 4, E>,                                                                          \
-     (LdaEstepFn)lda_estep_reg_kernel<L, C, 4, 4, E>, (LdaEstepFn)lda_estep_reg_kernel<L, C, 4, 3, E>,                         \
-     (LdaEstepFn)lda_estep_reg_kernel<L, C, 2, 4, E>, (LdaEstepFn)lda_estep_reg_kernel<L, C, 2, 3, E>,                         \
-     (LdaEstepFn)lda_estep_reg_kernel<L, C, 1, 4, E>, (LdaEstepFn)lda_estep_reg_kernel<L, C, 1, 2, E>}
-// lane layouts with a register-resident instantiation: K_ld = 56 (K = 49..56, e.g. the K = 50 NSF configuration) and K_ld = 32
-struct LdaRegLayout {
-    int lpt, cpl;
-    LdaEstepFn fn[2][kNumRegVariants];  // [want_elbo][variant]
-};
-static const LdaRegLayout kLdaReg[] = {
-    {2, 7, {TMVB_LDA_REG_ROW(2, 7, false), TMVB_LDA_REG_ROW(2, 7, true)}},
-    {1, 8, {TMVB_LDA_REG_ROW(1, 8, false), TMVB_LDA_REG_ROW(1, 8, true)}},
-};
-static const LdaRegLayout *lda_reg_layout(int lpt, int cpl)
+// The hybrid kernel is instantiated per K_ld (compile-time strides), one translation unit per value: tmvb_lda_hyb_<K_ld>.cu
+// built from tmvb_lda_hyb_inst.cuh; tmvb_lda_hyb.cuh declares the tables.  Other K use the tile kernel.
+static const LdaHybLayout *const kLdaHyb[] = {TMVB_LDA_HYB_TABLES};
+static const LdaHybLayout *lda_hyb_layout(int lpt, int cpl, int K_ld)
 {
-    for (const LdaRegLayout &l : kLdaReg)
-        if (l.lpt == lpt && l.cpl == cpl) return &l;
+    for (const LdaHybLayout *l : kLdaHyb)
+        if (l->lpt == lpt && l->cpl == cpl && l->K_ld == K_ld) return l;
     return nullptr;
 }
 struct LdaPick {
     const void *tile[3];
-    const LdaRegLayout *reg;
+    const LdaHybLayout *hyb;
     bool elbo;
 };
 static const void *lda_pick(const Bucket &b, const void *ctx)
 {
     const LdaPick *pk = static_cast<const LdaPick *>(ctx);
-    if (b.nr == 0) return pk->tile[b.warps >= 4 ? 2 : b.warps - 1];
-    for (int v = 0; v < kNumRegVariants; v++)
-        if (kRegVariant[v][0] == b.warps && kRegVariant[v][1] == b.nr) return (const void *)pk->reg->fn[pk->elbo ? 1 : 0][v];
-    return nullptr;
+    if (b.hyb) {
+        for (int v = 0; v < kNumHybVariants; v++)
+            if (kHybVariant[v][0] == b.warps && kHybVariant[v][1] == b.nr && kHybVariant[v][2] == (b.cap > 0 ? 1 : 0))
+                return (const void *)pk->hyb->fn[pk->elbo ? 1 : 0][v];
+        return nullptr;
+    }
+    return pk->tile[b.warps >= 4 ? 2 : b.warps - 1];
 }
 #define TMVB_LDA_FN1(L, C) {(LdaEstepFn)lda_estep_kernel<L, C, 1, false>, (LdaEstepFn)lda_estep_kernel<L, C, 1, true>},
 #define TMVB_LDA_FN2(L, C) {(LdaEstepFn)lda_estep_kernel<L, C, 2, false>, (LdaEstepFn)lda_estep_kernel<L, C, 2, true>},
@@ -1254,13 +695,42 @@ static int lda_set_corpus(tmvb_lda_t h, const int64_t *N_cumsum, const void *ter
     const size_t per_tok = (size_t)s.RS * 4 + 8;
     for (Bucket &b : s.buckets) {
         b.warps = tile_w;
+        b.hyb = 0;
         b.smem = lda_fixed_smem(s.RS, s.lpt, b.warps) + (size_t)b.cap * per_tok;
         b.grid = 0;
     }
-    // documents that fit the register-resident kernel (at most 16 rounds of S tokens) leave the tile launches
-    if (lda_reg_layout(s.lpt, s.cpl) && env_int("TMVB_LDA_REG", 1)) {
+    // Hybrid kernel (default): classes (W, NR, tile capacity) by ascending document length.  The tile capacity of a class is
+    // what leaves room for the number of resident CTAs its register allocation allows (12 / W: 168 registers per thread),
+    // then for fewer; documents longer than the last class stay with the tile kernel (which reads overflow rows from L2).
+    const LdaHybLayout *hl = lda_hyb_layout(s.lpt, s.cpl, s.K_ld);
+    if (hl && env_int("TMVB_LDA_HYB", 1)) {
         const int S = 32 / s.lpt, M = (int)s.len_sorted.size();
-        const int limit = S * kRegVariant[0][0] * kRegVariant[0][1];
+        struct Cls {
+            int W, NR, cap, maxlen;
+        };
+        std::vector<Cls> cls;
+        auto cap_for = [&](int W, int occ) {
+            // 228 KB of shared memory per SM, 1 KB of which every resident CTA reserves for the system
+            const long long budget = (long long)(228 * 1024 - 1024 * occ) / occ;
+            const long long room = std::min<long long>(budget, (long long)s.smem_optin) - (long long)lda_hyb_fixed_smem(s.RS, s.lpt, W);
+            return room <= 0 ? 0 : (int)(room / (long long)per_tok) / 4 * 4;   // cnt_s / term_s stay 16-byte aligned
+        };
+        // class list "W:NR:occ,..." (occ = resident CTAs per SM the tile capacity leaves room for; 0 = no tile), by ascending length
+        const char *spec = getenv("TMVB_HYB_CLASSES");
+        if (!spec || !*spec) spec = s.K_ld <= 64 ? "1:2:0,1:4:0,2:3:0,2:4:0,4:3:0,4:4:0,4:4:1" : "4:3:3,4:3:2,4:3:1";
+        for (const char *q = spec; *q;) {
+            int W = 0, NR = 0, occ = 0;
+            if (sscanf(q, "%d:%d:%d", &W, &NR, &occ) != 3) return fail(-1, "invalid argument: TMVB_HYB_CLASSES must be W:NR:occ[,W:NR:occ...]");
+            bool known = false;
+            for (int v = 0; v < kNumHybVariants; v++)
+                known = known || (kHybVariant[v][0] == W && kHybVariant[v][1] == NR && kHybVariant[v][2] == (occ > 0 ? 1 : 0) && hl->fn[0][v]);
+            if (!known) return fail(-1, "invalid argument: TMVB_HYB_CLASSES names a variant that is not built for this K (W=%d NR=%d)", W, NR);
+            cls.push_back({W, NR, occ > 0 ? cap_for(W, occ) : 0, 0});
+            while (*q && *q != ',') q++;
+            if (*q == ',') q++;
+        }
+        for (Cls &c : cls) c.maxlen = c.W * c.NR * S + c.cap;
+        const int limit = cls.back().maxlen;
         int first = 0;  // documents are sorted by length, longest first
         while (first < M && s.len_sorted[first] > limit) first++;
         std::vector<Bucket> nb;
@@ -1270,26 +740,32 @@ static int lda_set_corpus(tmvb_lda_t h, const int64_t *N_cumsum, const void *ter
             nb.push_back(b);
         }
         int begin = first;
-        for (int v = 0; v < kNumRegVariants && begin < M; v++) {
-            const int W = kRegVariant[v][0], NR = kRegVariant[v][1];
-            const int lo = (v + 1 < kNumRegVariants) ? S * kRegVariant[v + 1][0] * kRegVariant[v + 1][1] : -1;
+        for (int ci = (int)cls.size() - 1; ci >= 0 && begin < M; ci--) {
+            const int lo = ci > 0 ? cls[ci - 1].maxlen : -1;
             int end = begin;
             while (end < M && s.len_sorted[end] > lo) end++;
             if (end == begin) continue;
             Bucket b;
             b.doc_begin = begin;
             b.doc_end = end;
-            b.cap = S * W * NR;
+            // the tile only needs to hold the longest document of the launch
+            b.cap = cls[ci].cap > 0 ? std::max(4, std::min(cls[ci].cap / 4 * 4, (s.len_sorted[begin] - cls[ci].W * cls[ci].NR * S + 3) / 4 * 4)) : 0;
             b.cap2 = 0;
-            b.warps = W;
-            b.nr = NR;
-            b.smem = lda_reg_smem(s.RS, s.lpt, W);
+            b.warps = cls[ci].W;
+            b.nr = cls[ci].NR;
+            b.hyb = 1;
+            b.smem = lda_hyb_fixed_smem(s.RS, s.lpt, b.warps) + (size_t)b.cap * per_tok;
             b.grid = 0;
             nb.push_back(b);
             begin = end;
         }
         if ((int)nb.size() > kMaxBuckets) return fail(-1, "internal: too many launch buckets");
         s.buckets.swap(nb);
+        for (int eb = 0; eb < 2; eb++)
+            for (int v = 0; v < kNumHybVariants; v++)
+                if (hl->fn[eb][v])
+                    TMVB_CUDA(cudaFuncSetAttribute((const void *)hl->fn[eb][v], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s.smem_optin));
+        return 0;
     }
     return 0;
 }
@@ -1364,7 +840,7 @@ int tmvb_lda_estep(tmvb_lda_t h, int viter, float vtol, int want_elbo)
     pk.tile[0] = (const void *)kLdaEstep[0][s.layout][want_elbo != 0];
     pk.tile[1] = (const void *)kLdaEstep[1][s.layout][want_elbo != 0];
     pk.tile[2] = (const void *)kLdaEstep[2][s.layout][want_elbo != 0];
-    pk.reg = lda_reg_layout(s.lpt, s.cpl);
+    pk.hyb = lda_hyb_layout(s.lpt, s.cpl, s.K_ld);
     pk.elbo = want_elbo != 0;
     TMVB_TRY(shard_launch(&s, lda_pick, &pk, &p, sizeof(p)));
     TMVB_CUDA(cudaEventRecord(s.ev[1], s.stream));

@@ -288,6 +288,7 @@ static int plan_buckets(Shard *s, size_t fixed_bytes)
         b.cap2 = 0;
         b.warps = 1;
         b.nr = 0;
+        b.hyb = 0;
         b.smem = fixed_bytes + (size_t)b.cap * per_tok;
         b.grid = 0;
         s->buckets.push_back(b);
@@ -488,7 +489,7 @@ int shard_launch(Shard *s, BucketKernelFn pick, const void *ctx, void *dev_struc
             b.grid = std::min(b.doc_end - b.doc_begin, occ * s->n_sm);
         }
         // the launch geometry is part of the key, so a re-planned corpus never replays a stale graph
-        const long long geo[8] = {(long long)(size_t)fn, b.doc_begin, b.doc_end, b.cap, b.cap2, b.grid, (long long)b.smem, b.warps};
+        const long long geo[8] = {(long long)(size_t)fn, b.doc_begin, b.doc_end, b.cap, b.cap2, b.grid, (long long)b.smem, b.warps + 64 * b.nr + 4096 * b.hyb};
         key.append((const char *)geo, sizeof(geo));
     }
     s->st.kernel_launches += (int64_t)s->buckets.size();

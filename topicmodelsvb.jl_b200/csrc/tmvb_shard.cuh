@@ -13,7 +13,8 @@ struct Bucket {
     int doc_begin, doc_end, cap, grid;
     int cap2;  // second tile capacity (CTPF reader lists); 0 otherwise
     int warps; // warps cooperating on one document in this launch (CTA = 32 * warps threads)
-    int nr;    // > 0: register-resident kernel, rounds per warp (capacity warps * nr * S tokens); 0: shared-memory tile kernel
+    int nr;    // > 0: register rounds per warp (register capacity warps * nr * S tokens); 0: shared-memory tile kernel
+    int hyb;   // 1: hybrid kernel (nr register rounds per warp + a tile of `cap` tokens); 0: pure register (nr > 0) / pure tile kernel
     size_t smem;
 };
 
