@@ -555,6 +555,7 @@ LdaDev dev_view(tmvb_lda_t h)
     p.doc_off = s.d_doc_off;
     p.terms = s.d_terms;
     p.counts = s.d_counts;
+    p.doc_c = s.d_doc_c;
     p.Elogtheta = h->d_Elogtheta;
     p.Elogtheta_old = h->d_Elogtheta_old;
     p.gamma = h->d_gamma;
@@ -712,12 +713,15 @@ static int lda_set_corpus(tmvb_lda_t h, const int64_t *N_cumsum, const void *ter
         auto cap_for = [&](int W, int occ) {
             // 228 KB of shared memory per SM, 1 KB of which every resident CTA reserves for the system
             const long long budget = (long long)(228 * 1024 - 1024 * occ) / occ;
-            const long long room = std::min<long long>(budget, (long long)s.smem_optin) - (long long)lda_hyb_fixed_smem(s.RS, s.lpt, W);
+            const long long room = std::min<long long>(budget, (long long)s.smem_optin) - (long long)lda_hyb_fixed_smem(s.K_ld, s.lpt, W);
             return room <= 0 ? 0 : (int)(room / (long long)per_tok) / 4 * 4;   // cnt_s / term_s stay 16-byte aligned
         };
         // class list "W:NR:occ,..." (occ = resident CTAs per SM the tile capacity leaves room for; 0 = no tile), by ascending length
         const char *spec = getenv("TMVB_HYB_CLASSES");
-        if (!spec || !*spec) spec = s.K_ld <= 64 ? "1:2:0,1:4:0,2:3:0,2:4:0,4:3:0,4:4:0,4:4:1" : "4:3:3,4:3:2,4:3:1";
+        // (measured on B200, NSF K=50 and cfg4 K=200: the more of a document one warp holds in registers the better -- instructions per
+        // document count for more than resident warps -- so one warp takes documents up to 6 rounds, two warps up to 12, four up to 24)
+        if (!spec || !*spec)
+            spec = s.K_ld <= 64 ? "1:2:0,1:3:0,1:4:0,1:5:0,1:6:0,2:4:0,2:5:0,2:6:0,4:5:0,4:6:0,4:6:1" : "4:3:0,4:4:0,4:5:0,4:6:0,4:6:2,4:6:1";
         for (const char *q = spec; *q;) {
             int W = 0, NR = 0, occ = 0;
             if (sscanf(q, "%d:%d:%d", &W, &NR, &occ) != 3) return fail(-1, "invalid argument: TMVB_HYB_CLASSES must be W:NR:occ[,W:NR:occ...]");
@@ -754,7 +758,7 @@ static int lda_set_corpus(tmvb_lda_t h, const int64_t *N_cumsum, const void *ter
             b.warps = cls[ci].W;
             b.nr = cls[ci].NR;
             b.hyb = 1;
-            b.smem = lda_hyb_fixed_smem(s.RS, s.lpt, b.warps) + (size_t)b.cap * per_tok;
+            b.smem = lda_hyb_fixed_smem(s.K_ld, s.lpt, b.warps) + (size_t)b.cap * per_tok;
             b.grid = 0;
             nb.push_back(b);
             begin = end;

@@ -16,6 +16,7 @@ struct LdaDev {
     const long long *doc_off;
     const int *terms;
     const float *counts;
+    const float *doc_c;   // [M] sum of a document's counts
     float *Elogtheta, *Elogtheta_old, *gamma;
     double *small;
     int viter;
@@ -334,36 +335,38 @@ __global__ void __launch_bounds__(32 * W, W == 2 ? 8 : 1) lda_estep_kernel(const
 #undef TOPIC
 
 // ------------------------------------------------------------------ hybrid E-step (registers + tile) ----------
-// lda_estep_hyb_kernel<LPT, CPL, W, NR, ELBO>: W warps share a document.  Warp w keeps its NR register rounds (tokens
-// ((j W + w) S + ts), j < NR -- RegDoc) for all sweeps; tokens beyond W * NR * S live in a shared-memory tile (tile round q
-// belongs to warp q % W), staged once per document with one TMA bulk copy per term row.  What it changes with respect
-// to lda_estep_reg_kernel, from the per-instruction profile of that kernel (profiles/r2_lda_reg_sass_hot_loop.txt):
-//   * one launch covers a wide range of lengths (registers for the first W NR S tokens, the tile for the rest), so a document
-//     no longer pays for empty register rounds of a coarse length bucket;
-//   * exp(Elogtheta) is dead during the K phase (the scatter pass reloads it from a double-buffered shared copy), which gives
-//     the owner sums the registers to pipeline their 16 LDS (they were serialised on one register pair: 10 % of all samples);
-//   * K_ld <= 64, W <= 2: EVERY warp runs the K phase for all topics (redundantly), so a sweep has ONE CTA barrier (the exchange
-//     of the per-warp sums) instead of two and no warp sits idle while another evaluates digamma (16 % of all samples);
+// lda_estep_hyb_kernel<LPT, CPL, KLD, W, NR, TILE, ELBO>: W warps share a document.  Warp w keeps its NR register rounds
+// (tokens ((j W + w) S + ts), j < NR -- RegDoc) for all sweeps; with TILE, tokens beyond W * NR * S live in a shared-memory
+// tile (tile round q belongs to warp q % W), staged once per document with one TMA bulk copy per term row.  Design points,
+// each from the per-instruction profile of its predecessor (profiles/r2_lda_*):
+//   * K_ld is a template parameter: every shared-memory exchange addresses with immediate offsets;
+//   * exp(Elogtheta) is dead during the K phase (the scatter pass reloads it from a double-buffered shared copy), so the
+//     owner sums have the registers to issue their 16 LDS before the first FADD2 (they were serialised on one register pair);
+//   * K_ld <= 64, W <= 2 ("RK"): EVERY warp runs the K phase for all topics, redundantly, so a sweep has ONE CTA barrier (the
+//     exchange of the per-warp sums) and no warp idles while another evaluates digamma; a document starts and ends without
+//     a barrier (sum_n c_n comes precomputed, the exchange buffers rotate with the document parity);
 //   * otherwise (W = 4, or K_ld > 64) the K phase is spread over all threads of the CTA (thread t owns topics 2t, 2t+1): this
 //     is what lets K = 200 leave the pure tile kernel -- W = 4, LPT = 8, 48 tokens in registers, a tile less than half the size;
-//   * the scatter pass reuses the normalisers s_n of the last sweep for the register rounds.
-// Shared memory: header (128 B) | gs [W][S][RS] | xs [2][W][RS] | e_s [EW][2][RS] | tile [cap][RS] | cnt_s [cap] | term_s [cap]
-// (EW = W when every warp runs the K phase, else 1).
-static size_t lda_hyb_fixed_smem(int RS, int lpt, int W) { return 128 + (size_t)W * (32 / lpt) * RS * 4 + (size_t)2 * W * RS * 4 + (size_t)2 * W * RS * 4; }
-
-// registers per thread the hybrid variants are held to: 65536 / (32 * resident warps per SM) in units of 8 -- 12 / 10 / 9 / 8
-// warps per SM
-constexpr int lda_hyb_maxreg(int NR) { return NR <= 3 ? 168 : NR == 4 ? 200 : 255; }
-constexpr int lda_hyb_warps_per_sm(int NR) { return 65536 / (32 * lda_hyb_maxreg(NR)); }
-
-// row_stride() of tmvb_shard.cu as a constant expression
-__host__ __device__ constexpr int hyb_row_stride(int CH, int lpt)
+//   * sum_n t_n (the epsilon term of gamma) rides through the exchange as one more column instead of a shuffle reduction;
+//   * the K phase uses bare MUFU forms; the scatter pass reuses the normalisers s_n of the last sweep for the register rounds.
+// Shared memory: header (128 B) | gs [W][S][RSG] | xs [RK ? 4 : 2][W][RSG] | e_s [RK ? W : 1][2][RS] | tile [cap][RS] | cnt_s [cap] |
+// term_s [cap]   (RSG = row stride with room for one more column: the per-warp sum_n t_n travels in it).
+__host__ __device__ constexpr int hyb_row_stride(int CH, int lpt)   // row_stride() of tmvb_shard.cu as a constant expression
 {
     int r = CH;
     if (lpt < 8)
         while (r % (2 * lpt) != lpt) r++;
     return 4 * r;
 }
+static size_t lda_hyb_fixed_smem(int K_ld, int lpt, int W)
+{
+    const size_t RS = hyb_row_stride(K_ld / 4, lpt), RSG = hyb_row_stride(K_ld / 4 + 1, lpt);
+    const bool rk = W <= 2 && K_ld <= 62;   // RK of the kernel: exchange buffers x 4 (document parity), one e copy per warp
+    return 128 + (size_t)W * (32 / lpt) * RSG * 4 + (size_t)(rk ? 4 : 2) * W * RSG * 4 + (size_t)2 * (rk ? W : 1) * RS * 4;
+}
+
+// registers per thread the hybrid variants are held to: 65536 / (32 * resident warps per SM) in units of 8 -- 12 / 10 / 8
+constexpr int lda_hyb_maxreg(int NR) { return NR <= 3 ? 168 : NR == 4 ? 200 : 255; }
 
 // owner-lane sums of topics i, i+1 over the S per-stream partials: all loads first, then a tree of FADD2
 template <int S>
@@ -380,53 +383,78 @@ __device__ __forceinline__ float2 owner_sum2_tree(const float *gs, int RS, int i
     unpk2(v[0], r.x, r.y);
     return r;
 }
+// developer switches for A/B builds of the hybrid kernel (tools/build_variants.sh); the defaults are the shipped configuration
+#ifndef TMVB_V_TSUMCOL
+#define TMVB_V_TSUMCOL 0   // 1: sum_n t_n rides through the exchange as an extra column; 0: shuffle reduction in the token phase
+#endif
+#ifndef TMVB_V_STS64
+#define TMVB_V_STS64 0     // 1: per-stream partials stored as 8-byte pairs; 0: as 16-byte chunks
+#endif
+#ifndef TMVB_V_OPAQUE
+#define TMVB_V_OPAQUE 0    // 1: thread index and shared-window base are read once and kept (no S2R / S2UR rematerialisation in the sweep loop)
+#endif
+#ifndef TMVB_V_NODOCSYNC
+#define TMVB_V_NODOCSYNC 1 // 1: RK variants without a tile start and end a document without a CTA barrier
+#endif
+__device__ __forceinline__ void sts64(unsigned addr, f32x2 v) { asm volatile("st.shared.b64 [%0], %1;" ::"r"(addr), "l"(v) : "memory"); }
 
 template <int LPT, int CPL, int KLD, int W, int NR, bool TILE, bool ELBO>
 __global__ void __maxnreg__(lda_hyb_maxreg(NR)) lda_estep_hyb_kernel(const LdaDev p, int doc_begin, int doc_end, int cap, int cap2, int *counter)
 {
     constexpr int S = 32 / LPT;
     constexpr int T = 32 * W;
-    // K_ld, and with it the row stride of every shared-memory array, is a compile-time constant: the per-sweep exchange
-    // (gs / xs / e_s) then addresses shared memory with immediate offsets instead of ~70 integer instructions per warp and sweep
-    constexpr int K_ld = KLD, CH = KLD / 4, RS = hyb_row_stride(KLD / 4, LPT);
-    constexpr int PM = (KLD + 63) / 64;           // topic pairs per lane when a warp folds its own S streams
+    constexpr int K_ld = KLD, CH = KLD / 4, RS = hyb_row_stride(KLD / 4, LPT), RSG = hyb_row_stride(KLD / 4 + 1, LPT);
+    constexpr int PM = (KLD + 2 + 63) / 64;       // topic pairs (+ the sum_n t_n column) per lane when a warp folds its own S streams
     constexpr int REGTOK = W * NR * S;            // tokens of a document that live in registers
-    constexpr bool RK = (W <= 2 && KLD <= 64);    // every warp runs the whole K phase (one barrier per sweep)
-    constexpr int EW = RK ? W : 1;
+    constexpr bool RK = (W <= 2 && KLD <= 62);    // every warp runs the whole K phase (one barrier per sweep, none per document)
+    constexpr bool DOCSYNC = TILE || !RK || !TMVB_V_NODOCSYNC;   // a document starts and ends with a CTA barrier
     static_assert(KLD % 8 == 0 && KLD <= 4 * LPT * CPL && KLD > 4 * LPT * (CPL - 1), "K_ld must fill the lane layout's last chunk column");
-    static_assert(64 * W >= KLD, "the K phase keeps one topic pair per thread");
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    static_assert(64 * W >= KLD + 2, "the K phase keeps one topic pair (or the sum_n t_n column) per thread");
+    extern __shared__ __align__(16) unsigned char smem_dyn[];
+    int tid_ = threadIdx.x;
+    unsigned char *smem_raw = smem_dyn;
+#if TMVB_V_OPAQUE
+    // opaque copies: the compiler otherwise re-reads SR_TID and rebuilds the shared-window base (S2UR SR_CgaCtaId, ~30 cycles of
+    // exposed latency each) several times per sweep instead of keeping them in registers
+    asm volatile("mov.u32 %0, %0;" : "+r"(tid_));
+    {
+        unsigned long long g = reinterpret_cast<unsigned long long>(smem_dyn);
+        asm volatile("mov.u64 %0, %0;" : "+l"(g));
+        smem_raw = reinterpret_cast<unsigned char *>(g);
+    }
+#endif
+    const int tid = tid_, lane = tid & 31, warp = tid >> 5;
     const int kl = lane % LPT, ts = lane / LPT;
     const int K = p.K;
     (void)cap2;
     unsigned long long *mbar = reinterpret_cast<unsigned long long *>(smem_raw);
     int *next_s = reinterpret_cast<int *>(smem_raw + 16);
-    float *csum_s = reinterpret_cast<float *>(smem_raw + 32);        // [W <= 4]
-    float *tsum_s = reinterpret_cast<float *>(smem_raw + 48);        // [2][W <= 4]
-    unsigned *dsum_s = reinterpret_cast<unsigned *>(smem_raw + 80);  // [2][W <= 4]
-    float *gs = reinterpret_cast<float *>(smem_raw + 128);           // [W][S][RS]
-    float *xs = gs + (size_t)W * S * RS;                             // [2][W][RS]
-    float *e_s = xs + (size_t)2 * W * RS;                            // [EW][2][RS] (room for [W][2][RS])
-    float *tile = e_s + (size_t)2 * W * RS;                          // [cap][RS]
+    float *asum_s = reinterpret_cast<float *>(smem_raw + 32);        // [W <= 4]
+    unsigned *dsum_s = reinterpret_cast<unsigned *>(smem_raw + 64);  // [2][W <= 4]
+    float *gs = reinterpret_cast<float *>(smem_raw + 128);           // [W][S][RSG]
+    float *xs = gs + (size_t)W * S * RSG;                            // [RK ? 4 : 2][W][RSG]
+    float *e_s = xs + (size_t)(RK ? 4 : 2) * W * RSG;                // [RK ? W : 1][2][RS]
+    float *tile = e_s + (size_t)2 * (RK ? W : 1) * RS;               // [cap][RS]
     float *cnt_s = tile + (size_t)cap * RS;                          // [cap]
     int *term_s = reinterpret_cast<int *>(cnt_s + cap);              // [cap]
-    float *gs_w = gs + (size_t)warp * S * RS;
-    float *e_w = e_s + (size_t)(EW > 1 ? warp : 0) * 2 * RS;         // this warp's (or the CTA's) double-buffered exp(Elogtheta)
+    float *gs_w = gs + (size_t)warp * S * RSG;
+    float *e_w = e_s + (size_t)(RK ? warp : 0) * 2 * RS;
+    // shared-window address of this lane's slice of its stream's partial vector (8-byte stores: an STS.128 would cost four MOVs
+    // per chunk to line the two accumulator pairs up in one aligned register quad)
+    const unsigned gs_st = (unsigned)__cvta_generic_to_shared(gs_w + ts * RSG + 4 * kl);
 
-    // K-phase ownership: topics i0, i0 + 1 -- pair `lane` in every warp (RK), else pair `tid`
+    // K-phase ownership: topics i0, i0 + 1 -- pair `lane` in every warp (RK), else pair `tid`; pair K_ld / 2 is the sum_n t_n column
     const int i0 = 2 * (RK ? lane : tid);
-    const bool in_ld = i0 < K_ld, ok0 = i0 < K, ok1 = i0 + 1 < K;
+    const bool in_ld = i0 < K_ld, in_x = i0 < K_ld + 2, ok0 = i0 < K, ok1 = i0 + 1 < K;
     const bool writer = RK ? (warp == 0) : true;                     // who stores the document's K-vectors and accumulates its sums
     const float a0 = ok0 ? p.alpha[i0] : 0.0f, a1 = ok1 ? p.alpha[i0 + 1] : 0.0f;
     float asum = warp_sum(a0 + a1);
     if (!RK) {
-        if (lane == 0) csum_s[warp] = asum;
+        if (lane == 0) asum_s[warp] = asum;
         __syncthreads();
         asum = 0.0f;
 #pragma unroll
-        for (int w = 0; w < W; w++) asum += csum_s[w];
-        __syncthreads();
+        for (int w = 0; w < W; w++) asum += asum_s[w];
     }
     // convergence test in fixed point: sum_i dE_i^2 * (2^20 / vtol^2) < 2^20 with one REDUX per warp.  vtol = 0: the scale is
     // +inf, every term saturates at the clamp (0 * inf = NaN is dropped by fminf) and the test never passes, as ||.|| < 0 never does
@@ -441,7 +469,7 @@ __global__ void __maxnreg__(lda_hyb_maxreg(NR)) lda_estep_hyb_kernel(const LdaDe
     cta_sync<W>();
 
     const int chunk = max(1, min(kDocChunk, (doc_end - doc_begin) / (4 * (int)gridDim.x)));
-    int d_next = 0, d_lim = 0;
+    int d_next = 0, d_lim = 0, dpar = 0;
     long long o_cur = 0, o_end = 0;
     for (;;) {
         if (d_next >= d_lim) {  // kDocChunk documents per draw from the work counter (see lda_estep_kernel)
@@ -466,6 +494,7 @@ __global__ void __maxnreg__(lda_hyb_maxreg(NR)) lda_estep_hyb_kernel(const LdaDe
         o_cur = o_end;
         if (d_next < d_lim) o_end = p.doc_off[d_next + 1];
         const int n_tile = TILE ? max(Nd - REGTOK, 0) : 0;   // <= cap: the launch buckets are planned that way
+        const float csum = __ldg(p.doc_c + d);
 
         RegDoc<LPT, CPL, NR> rd;
         reg_load<LPT, CPL, W, NR>(rd, p.beta, p.terms + o, p.counts + o, Nd, K_ld, warp, ts, kl, p.dbg);
@@ -478,13 +507,10 @@ __global__ void __maxnreg__(lda_hyb_maxreg(NR)) lda_estep_hyb_kernel(const LdaDe
             if (lane < 8 || 128 * (lane - 8) < K_ld * 4) asm volatile("prefetch.global.L2 [%0];" ::"l"(a));
         }
         // tile: ids and counts of the tokens beyond the register rounds, then one TMA bulk copy per term row
-        float csum_t = 0.0f;
         if (n_tile > 0) {
             for (int n = tid; n < n_tile; n += T) {
-                const float c = __ldg(p.counts + o + REGTOK + n);
-                csum_t += c;
                 term_s[n] = __ldg(p.terms + o + REGTOK + n);
-                cnt_s[n] = c;
+                cnt_s[n] = __ldg(p.counts + o + REGTOK + n);
             }
             fence_proxy_async_smem();
             cta_sync<W>();
@@ -502,30 +528,27 @@ __global__ void __maxnreg__(lda_hyb_maxreg(NR)) lda_estep_hyb_kernel(const LdaDe
             ek1 = ok1 ? expf(Eo1) : 0.0f;
             *reinterpret_cast<float2 *>(e_w + i0) = make_float2(ek0, ek1);
         }
-        float csum = 0.0f;
-#pragma unroll
-        for (int j = 0; j < NR; j++) csum += rd.c[j];
-        csum = warp_sum((kl == 0 ? csum : 0.0f) + csum_t);
-        if (W > 1 && lane == 0) csum_s[warp] = csum;
         if (n_tile > 0) {
             mbar_wait(mbar, phase);
             phase ^= 1u;
         }
-        cta_sync<W>();
-        if (W > 1) {
-            csum = 0.0f;
-#pragma unroll
-            for (int w = 0; w < W; w++) csum += csum_s[w];
-        }
+        if (DOCSYNC)
+            cta_sync<W>();
+        else
+            __syncwarp();
         // sum(gamma_d) = sum(alpha) + sum_n c_n + K*EPS whatever phi is: digamma(sum gamma) (LDA.jl:138) is a per-document constant
         const float gsum = (asum + csum) + (float)K * TMVB_EPS;
         const float psi_sum = psi_lgamma<false>(gsum).psi;
+        // this document's pair of exchange buffers: they alternate with the documents THIS CTA processes, so a warp that runs
+        // ahead into the next document never writes a buffer the other warp may still be reading
+        dpar ^= 1;
+        float *xd = xs + (size_t)(RK ? dpar : 0) * 2 * W * RSG;
 
         float s_keep[NR];
         int v = 0;
         for (;;) {
             const int eb = v & 1;
-            float tt;
+            float tt_w = 0.0f;   // this warp's sum_n t_n
             {
                 // ---- token phase: update_phi! + the phi*counts product of update_gamma! (LDA.jl:143-154)
                 f32x2 e01[CPL], e23[CPL];
@@ -543,34 +566,70 @@ __global__ void __maxnreg__(lda_hyb_maxreg(NR)) lda_estep_hyb_kernel(const LdaDe
                 reg_sweep_keep<LPT, CPL, NR, true>(rd, keps_init, e01, e23, g01, g23, tsum, s_keep);
 #pragma unroll
                 for (int m = 0; m < CPL; m++)
-                    if (m < CPL - 1 || kl + LPT * m < CH) reinterpret_cast<ulonglong2 *>(gs_w + ts * RS)[kl + LPT * m] = make_ulonglong2(g01[m], g23[m]);
-                tt = across_streams_sum<LPT>(tsum);
+                    if (m < CPL - 1 || kl + LPT * m < CH) {
+#if TMVB_V_STS64
+                        sts64(gs_st + 16 * LPT * m, g01[m]);
+                        sts64(gs_st + 16 * LPT * m + 8, g23[m]);
+#else
+                        reinterpret_cast<ulonglong2 *>(gs_w + ts * RSG)[kl + LPT * m] = make_ulonglong2(g01[m], g23[m]);
+#endif
+                    }
+#if TMVB_V_TSUMCOL
+                if (kl == 0) gs_w[ts * RSG + K_ld] = tsum;   // the extra column: this stream's sum_n t_n
+#else
+                tt_w = across_streams_sum<LPT>(tsum);
+#endif
             }
             __syncwarp();
             // ---- fold the S per-stream partials of this warp, then the W warps, into the K-phase layout
             float2 gg = make_float2(0.f, 0.f);
             if (W == 1) {
-                if (in_ld) gg = owner_sum2_tree<S>(gs_w, RS, i0);
+                if (TMVB_V_TSUMCOL ? in_x : in_ld) gg = owner_sum2_tree<S>(gs_w, RSG, i0);
             } else {
-                float *xb = xs + (size_t)eb * W * RS;
+                float *xb = xd + (size_t)eb * W * RSG;
 #pragma unroll
                 for (int m = 0; m < PM; m++) {
                     const int i = 2 * (lane + 32 * m);
-                    if (i < K_ld) *reinterpret_cast<float2 *>(xb + warp * RS + i) = owner_sum2_tree<S>(gs_w, RS, i);
+#if TMVB_V_TSUMCOL
+                    if (i < K_ld + 2) *reinterpret_cast<float2 *>(xb + warp * RSG + i) = owner_sum2_tree<S>(gs_w, RSG, i);
+#else
+                    if (i < K_ld) *reinterpret_cast<float2 *>(xb + warp * RSG + i) = owner_sum2_tree<S>(gs_w, RSG, i);
+#endif
                 }
-                if (lane == 0) tsum_s[eb * W + warp] = tt;
+#if !TMVB_V_TSUMCOL
+                if (lane == 0) xb[warp * RSG + K_ld] = tt_w;
+#endif
                 __syncthreads();
-                tt = 0.0f;
+                if (TMVB_V_TSUMCOL ? in_x : in_ld) {
 #pragma unroll
-                for (int w = 0; w < W; w++) {
-                    if (in_ld) {
-                        const float2 x = *reinterpret_cast<const float2 *>(xb + w * RS + i0);
+                    for (int w = 0; w < W; w++) {
+                        const float2 x = *reinterpret_cast<const float2 *>(xb + w * RSG + i0);
                         gg.x += x.x;
                         gg.y += x.y;
                     }
-                    tt += tsum_s[eb * W + w];
                 }
             }
+            float tt;
+#if TMVB_V_TSUMCOL
+            // sum_n t_n lives in the first slot of pair K_ld / 2
+            if (RK || W == 1) {
+                tt = __shfl_sync(0xffffffffu, gg.x, K_ld / 2);
+            } else {
+                tt = 0.0f;
+                const float *xb = xd + (size_t)eb * W * RSG;
+#pragma unroll
+                for (int w = 0; w < W; w++) tt += xb[w * RSG + K_ld];
+            }
+#else
+            if (W == 1) {
+                tt = tt_w;
+            } else {
+                tt = 0.0f;
+                const float *xb = xd + (size_t)eb * W * RSG;
+#pragma unroll
+                for (int w = 0; w < W; w++) tt += xb[w * RSG + K_ld];   // written below, before the barrier
+            }
+#endif
             // ---- K phase: update_gamma! (LDA.jl:143-146), update_Elogtheta! (LDA.jl:136-139)
             v++;
             // gamma = EPS + (alpha + phi*counts),   phi*counts = e .* g + eps * sum_n t_n   (pad topics: gamma = 1, harmless)
@@ -581,14 +640,14 @@ __global__ void __maxnreg__(lda_hyb_maxreg(NR)) lda_estep_hyb_kernel(const LdaDe
             En0 -= psi_sum;
             En1 -= psi_sum;
             if (v >= p.viter) break;
+            // exp(Elogtheta_new); pad topics need no mask: their table entries are zero, so they reach neither s_n nor g
+            const float en0 = ex2_ftz(En0 * 1.4426950408889634f), en1 = ex2_ftz(En1 * 1.4426950408889634f);
             // LDA.jl:175: stop when ||Elogtheta - Elogtheta_old||_2 < vtol; fixed point, one REDUX per warp
             const float d0 = (En0 - Eo0) * m0, d1 = (En1 - Eo1) * m1;
             const float dpart = fmaf(d0, d0, d1 * d1);
             // per-thread clamp 2^23 keeps the integer sum over up to 128 threads below 2^31
             unsigned dtot = __reduce_add_sync(0xffffffffu, (unsigned)fminf(dpart * dscale, 8388608.0f));
-            // exp(Elogtheta_new); pad topics need no mask: their table entries are zero, so they reach neither s_n nor g
-            const float en0 = ex2_ftz(En0 * 1.4426950408889634f), en1 = ex2_ftz(En1 * 1.4426950408889634f);
-            if (RK) {
+            if (RK || W == 1) {
                 // every warp holds all topic pairs: the decision is warp-local and identical in all warps
                 if (dtot < 1048576u) break;
                 if (in_ld) *reinterpret_cast<float2 *>(e_w + (eb ^ 1) * RS + i0) = make_float2(en0, en1);
@@ -649,7 +708,12 @@ __global__ void __maxnreg__(lda_hyb_maxreg(NR)) lda_estep_hyb_kernel(const LdaDe
             }
             if (tid == 0) sweeps_thr += (unsigned long long)v;
         }
-        cta_sync<W>();  // gs, xs, e_s, the tile and the header slots are free for the next document
+        // the tile, the shared e_s and the header slots are free for the next document; with RK and no tile every buffer a warp
+        // writes before the next exchange barrier is its own (gs_w, e_w) or belongs to the other document parity (xd)
+        if (DOCSYNC)
+            cta_sync<W>();
+        else
+            __syncwarp();
     }
 
     if (ELBO) {

@@ -11,9 +11,10 @@ typedef void (*LdaEstepFn)(const LdaDev, int, int, int, int, int *);
 
 // variants: (warps per document, register rounds per warp, with / without a shared-memory tile).  K_ld <= 64: all;
 // K_ld > 64: four warps only (the K phase keeps one topic pair per thread: 64 W >= K_ld).
-constexpr int kNumHybVariants = 13;
+constexpr int kNumHybVariants = 20;
 static const int kHybVariant[kNumHybVariants][3] = {{1, 2, 0}, {1, 3, 0}, {1, 4, 0}, {2, 2, 0}, {2, 3, 0}, {2, 4, 0}, {4, 3, 0}, {4, 4, 0},
-                                                    {1, 2, 1}, {2, 2, 1}, {2, 3, 1}, {4, 3, 1}, {4, 4, 1}};
+                                                    {1, 2, 1}, {2, 2, 1}, {2, 3, 1}, {4, 3, 1}, {4, 4, 1}, {1, 5, 0}, {1, 6, 0}, {2, 5, 0}, {2, 6, 0},
+                                                    {4, 5, 0}, {4, 6, 0}, {4, 6, 1}};
 struct LdaHybLayout {
     int lpt, cpl, K_ld;
     LdaEstepFn fn[2][kNumHybVariants];  // [want_elbo][variant]

@@ -96,19 +96,26 @@ __global__ void validate_kernel(const float *__restrict__ x, long long n, int wh
 template <typename IntT>
 __global__ void pack_corpus_kernel(const IntT *__restrict__ terms64, const IntT *__restrict__ counts64,
                                    const long long *__restrict__ src_off, const long long *__restrict__ dst_off, long long M,
-                                   int V, int *__restrict__ terms, float *__restrict__ counts, int *__restrict__ err)
+                                   int V, int *__restrict__ terms, float *__restrict__ counts, int *__restrict__ err,
+                                   float *__restrict__ doc_c)
 {
     const int lane = threadIdx.x & 31;
     const int wpb = blockDim.x >> 5;
     for (long long d = (long long)blockIdx.x * wpb + (threadIdx.x >> 5); d < M; d += (long long)gridDim.x * wpb) {
         const long long so = src_off[d], o = dst_off[d];
         const int Nd = (int)(dst_off[d + 1] - o);
+        float csum = 0.0f;
         for (int n = lane; n < Nd; n += 32) {
             const long long t = terms64[so + n], c = counts64[so + n];
             if (t < 0 || t >= V) atomicOr(err, 1);
             if (c <= 0) atomicOr(err, 2);
             terms[o + n] = (int)t;
             counts[o + n] = (float)c;
+            csum += (float)c;
+        }
+        if (doc_c) {   // C_d: integer-valued, so the fp32 sum is exact below 2^24 whatever the order
+            csum = warp_sum(csum);
+            if (lane == 0) doc_c[d] = csum;
         }
     }
 }
@@ -230,6 +237,7 @@ void shard_free(Shard *s)
     cudaFree(s->d_terms);
     cudaFree(s->d_perm);
     cudaFree(s->d_counts);
+    cudaFree(s->d_doc_c);
     cudaFree(s->d_beta[0]);
     cudaFree(s->d_beta[1]);
     cudaFree(s->d_stats);
@@ -355,6 +363,7 @@ int shard_set_corpus(Shard *s, const int64_t *N_cumsum, const void *terms, const
         TMVB_CUDA(cudaMalloc((void **)&s->d_doc_off, (M + 1) * 8));
         TMVB_CUDA(cudaMalloc((void **)&s->d_src_off, std::max<int64_t>(M, 1) * 8));
         TMVB_CUDA(cudaMalloc((void **)&s->d_perm, std::max<int64_t>(M, 1) * 4));
+        TMVB_CUDA(cudaMalloc((void **)&s->d_doc_c, std::max<int64_t>(M, 1) * 4));
     }
     if (nz > s->nnz_cap) {  // token arrays are reused across calls while they fit
         cudaFree(s->d_terms);
@@ -378,10 +387,10 @@ int shard_set_corpus(Shard *s, const int64_t *N_cumsum, const void *terms, const
         const int grid = grid_for(M * 32, 256, s->n_sm);
         if (elem_bytes == 8)
             pack_corpus_kernel<long long><<<grid, 256, 0, s->stream>>>((const long long *)t_in, (const long long *)c_in, s->d_src_off, s->d_doc_off, M,
-                                                                       (int)s->V, s->d_terms, s->d_counts, s->d_counters + 63);
+                                                                       (int)s->V, s->d_terms, s->d_counts, s->d_counters + 63, s->d_doc_c);
         else
             pack_corpus_kernel<int><<<grid, 256, 0, s->stream>>>((const int *)t_in, (const int *)c_in, s->d_src_off, s->d_doc_off, M, (int)s->V,
-                                                                 s->d_terms, s->d_counts, s->d_counters + 63);
+                                                                 s->d_terms, s->d_counts, s->d_counters + 63, s->d_doc_c);
         s->st.kernel_launches++;
         TMVB_CUDA(cudaGetLastError());
         int err = 0;
@@ -600,7 +609,7 @@ int shard_pack_aux(Shard *s, const int64_t *cumsum, const int64_t *ids, const in
         s->st.h2d_bytes += nnz * 16;
         TMVB_CUDA(cudaMemsetAsync(s->d_counters + 63, 0, 4, s->stream));
         pack_corpus_kernel<long long><<<grid_for(M * 32, 256, s->n_sm), 256, 0, s->stream>>>(t64, c64, d_src, *d_off, M, (int)id_limit, *d_ids, *d_vals,
-                                                                                 s->d_counters + 63);
+                                                                                 s->d_counters + 63, nullptr);
         s->st.kernel_launches++;
         TMVB_CUDA(cudaGetLastError());
         TMVB_CUDA(cudaMemcpyAsync(&err, s->d_counters + 63, 4, cudaMemcpyDeviceToHost, s->stream));

@@ -37,6 +37,7 @@ struct Shard {
     long long *d_doc_off = nullptr, *d_src_off = nullptr;
     int *d_terms = nullptr, *d_perm = nullptr;
     float *d_counts = nullptr;
+    float *d_doc_c = nullptr;   // [M] sum of a document's counts (C_d of the reference's structs, gpuLDA.jl:52), internal order
     std::vector<int> h_perm, len_sorted;
     std::vector<Bucket> buckets;
     // captured launch sequences of one E-step (see shard_launch), keyed by kernel set + by-value parameter block
