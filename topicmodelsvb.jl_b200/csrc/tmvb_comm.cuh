@@ -17,7 +17,7 @@ constexpr int kCommBufs = 5;          // stats | table[0] | table[1] | small | c
 constexpr int kCtlBytes = 16384;      // per-rank control block (flags, grid barrier, partial sums)
 constexpr int kCtlPartOff = 1024;     // double part[2][kCtlPartLen]: column-sum partials | elbo_w partial
 constexpr int kCtlPartLen = 264;      // >= max K_ld (256) + 1
-constexpr long long kSpinTimeoutNs = 4000000000ll;  // a peer that does not arrive within 4 s: give up (status flag), never hang
+constexpr int kSpinTimeoutMsDefault = 4000;  // a peer that does not arrive in time: give up (status flag), never hang; TMVB_COMM_TIMEOUT_MS
 
 struct Comm {
     int rank = 0, world = 1;
@@ -28,6 +28,7 @@ struct Comm {
     void *local[kCommBufs] = {};
     unsigned long long epoch = 0;            // three barrier epochs are consumed per exchange
     unsigned long long calls = 0;
+    int timeout_ms = kSpinTimeoutMsDefault;  // bounded spin of the device barriers (env TMVB_COMM_TIMEOUT_MS at connect time)
 };
 
 // blob = kCommBufs cudaIpcMemHandle_t (64 B each) for the local buffers
@@ -79,7 +80,7 @@ __device__ __forceinline__ CtlView ctl_view(void *ctl)
 }
 
 // All CTAs of a co-resident (cooperative) grid; `target` = gridDim.x * (number of barriers passed so far + 1).
-__device__ __forceinline__ void grid_barrier(unsigned *count, unsigned target, unsigned *status)
+__device__ __forceinline__ void grid_barrier(unsigned *count, unsigned target, unsigned *status, long long timeout_ns)
 {
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -87,7 +88,7 @@ __device__ __forceinline__ void grid_barrier(unsigned *count, unsigned target, u
         atomicAdd(count, 1u);
         const long long t0 = global_ns();
         while (ld_acquire_gpu(count) < target) {
-            if (global_ns() - t0 > kSpinTimeoutNs) {
+            if (global_ns() - t0 > timeout_ns) {
                 atomicExch(status, 2u);
                 break;
             }
@@ -98,7 +99,7 @@ __device__ __forceinline__ void grid_barrier(unsigned *count, unsigned target, u
 }
 
 // Cross-GPU barrier, executed by CTA 0 between two grid barriers: thread r < world signals rank r and waits for it.
-__device__ __forceinline__ void peer_barrier(void *const *peer_ctl, void *my_ctl, int rank, int world, unsigned long long epoch)
+__device__ __forceinline__ void peer_barrier(void *const *peer_ctl, void *my_ctl, int rank, int world, unsigned long long epoch, long long timeout_ns)
 {
     const int r = threadIdx.x;
     if (r < world && r != rank) {
@@ -107,7 +108,7 @@ __device__ __forceinline__ void peer_barrier(void *const *peer_ctl, void *my_ctl
         const CtlView me = ctl_view(my_ctl);
         const long long t0 = global_ns();
         while (ld_acquire_sys(me.flag + r) < epoch) {
-            if (global_ns() - t0 > kSpinTimeoutNs) {
+            if (global_ns() - t0 > timeout_ns) {
                 atomicExch(me.status, 1u);
                 break;
             }

@@ -326,8 +326,20 @@ __global__ void lda_alpha_kernel(double *__restrict__ alpha64, float *__restrict
     }
     if (want_elbo) {
         block_sum3(a0, sl, lin, red);
-        if (tid == 0) result[0] = small[K_ld] + Md * (lgamma(a0) - sl) + lin + local[K_ld];
+        // want_elbo = 2: only the part that depends on alpha -- the kernel then runs beside the M-step kernels on another
+        // stream and lda_elbo_assemble_kernel adds the M-step's term once both have finished
+        if (tid == 0) {
+            if (want_elbo == 2)
+                result[1] = Md * (lgamma(a0) - sl) + lin;
+            else
+                result[0] = small[K_ld] + Md * (lgamma(a0) - sl) + lin + local[K_ld];
+        }
     }
+}
+
+__global__ void lda_elbo_assemble_kernel(const double *__restrict__ small, const double *__restrict__ local, int K_ld, double *__restrict__ result)
+{
+    result[0] = small[K_ld] + result[1] + local[K_ld];
 }
 
 // phi[K x sumN] in the caller's token order, rebuilt from beta_old / Elogtheta_old (LDA.jl:87-88)
@@ -534,6 +546,7 @@ struct tmvb_lda_s {
     bool alpha_on_device = false, elbo_dev_valid = false;
     double *d_small = nullptr;          // [K_ld+2], summed over ranks
     double *d_local = nullptr;          // [K_ld] rowsum | [K_ld] elbo_w | [K_ld+1] scratch for the standalone ELBO
+    bool solo = true;                   // no other rank: nothing sums `small` between the E-step and update_alpha!
     Comm comm;                          // peer-memory exchange (multi-GPU), see tmvb_comm.cuh
 };
 
@@ -593,6 +606,15 @@ int sync_alpha(tmvb_lda_t h)
     s.st.d2h_bytes += s.K * 8;
     h->alpha_on_device = false;
     return 0;
+}
+
+// a non-zero time-out status of the peer exchange: report it, and clear the flag so that the next exchange starts clean
+int comm_raise(tmvb_lda_t h, unsigned st)
+{
+    if (!st) return 0;
+    cudaMemsetAsync(h->comm.d_ctl + 132, 0, 4, h->s.stream);
+    return fail(900 + (int)st, "peer exchange timed out (%s): a rank did not reach tmvb_lda_exchange_mstep within %d ms; the statistics of this iteration are incomplete",
+                st == 1 ? "peer barrier" : "grid barrier", h->comm.timeout_ms);
 }
 
 double lg_alpha_term(const std::vector<double> &a)
@@ -856,6 +878,7 @@ int tmvb_lda_estep(tmvb_lda_t h, int viter, float vtol, int want_elbo)
 int tmvb_lda_reduce_buffers(tmvb_lda_t h, void **stats, int64_t *n_stats, void **small, int64_t *n_small)
 {
     TMVB_CHECK_ARG(h != nullptr, "handle is NULL");
+    h->solo = false;   // the caller sums these buffers over ranks between estep and mstep
     if (stats) *stats = h->s.d_stats;
     if (n_stats) *n_stats = (int64_t)h->s.V * h->s.K_ld;
     if (small) *small = h->d_small;
@@ -889,6 +912,7 @@ int tmvb_lda_comm_connect(tmvb_lda_t h, int rank, int world, const void *blobs, 
 {
     TMVB_CHECK_ARG(h != nullptr, "handle is NULL");
     TMVB_CUDA(cudaSetDevice(h->s.device));
+    h->solo = false;
     return comm_connect(&h->comm, rank, world, blobs, (size_t)blob_bytes);
 }
 
@@ -954,8 +978,7 @@ int tmvb_lda_comm_status(tmvb_lda_t h, int *status)
     TMVB_CUDA(cudaMemcpyAsync(&st, h->comm.d_ctl + 132, 4, cudaMemcpyDeviceToHost, s.stream));
     TMVB_CUDA(cudaStreamSynchronize(s.stream));
     *status = (int)st;
-    if (st) return fail(900 + (int)st, "peer exchange timed out (%s): a rank did not reach tmvb_lda_exchange_mstep", st == 1 ? "peer barrier" : "grid barrier");
-    return 0;
+    return comm_raise(h, st);
 }
 
 int tmvb_lda_get_elogtheta_sum(tmvb_lda_t h, double *out)
@@ -977,10 +1000,27 @@ int tmvb_lda_update_alpha(tmvb_lda_t h, int64_t M_total, int niter, double ntol,
     Shard &s = h->s;
     TMVB_CUDA(cudaSetDevice(s.device));
     // LDA.jl:97-118 on the device in fp64 (one warp), fused with the ELBO assembly; asynchronous unless alpha_out is given
-    double *result = h->d_local + 2 * s.K_ld + 1;
-    lda_alpha_kernel<<<1, 32 * (((int)s.K + 1 + 31) / 32), 0, s.stream>>>(h->d_alpha64, h->d_alpha, h->d_small, h->d_local, (int)s.K, s.K_ld, (double)M_total, niter, ntol,
-                                            h->elbo_valid ? 1 : 0, result);
-    TMVB_CUDA(cudaGetLastError());
+    double *result = h->d_local + 2 * s.K_ld + 1;   // [0] the ELBO, [1] its alpha-dependent part
+    const int threads = 32 * (((int)s.K + 1 + 31) / 32);
+    if (h->solo && s.estep_timed && s.n_streams > 1) {
+        // one GPU: the Newton iteration needs only sum_d Elogtheta_d (ready when the E-step is), so it runs on an auxiliary
+        // stream beside colsum / normalize; the ELBO is assembled on the main stream when both are done
+        TMVB_CUDA(cudaStreamWaitEvent(s.aux[0], s.ev[1], 0));
+        lda_alpha_kernel<<<1, threads, 0, s.aux[0]>>>(h->d_alpha64, h->d_alpha, h->d_small, h->d_local, (int)s.K, s.K_ld, (double)M_total, niter, ntol,
+                                                      h->elbo_valid ? 2 : 0, result);
+        TMVB_CUDA(cudaGetLastError());
+        TMVB_CUDA(cudaEventRecord(s.ev_join[0], s.aux[0]));
+        TMVB_CUDA(cudaStreamWaitEvent(s.stream, s.ev_join[0], 0));
+        if (h->elbo_valid) {
+            lda_elbo_assemble_kernel<<<1, 1, 0, s.stream>>>(h->d_small, h->d_local, s.K_ld, result);
+            TMVB_CUDA(cudaGetLastError());
+            s.st.kernel_launches++;
+        }
+    } else {
+        lda_alpha_kernel<<<1, threads, 0, s.stream>>>(h->d_alpha64, h->d_alpha, h->d_small, h->d_local, (int)s.K, s.K_ld, (double)M_total, niter, ntol,
+                                                      h->elbo_valid ? 1 : 0, result);
+        TMVB_CUDA(cudaGetLastError());
+    }
     s.st.kernel_launches++;
     h->alpha_on_device = true;
     h->elbo_dev_valid = h->elbo_valid;
@@ -1005,8 +1045,13 @@ int tmvb_lda_elbo(tmvb_lda_t h, int mode, int64_t M_total, double *elbo_docs, do
         //                                                     from the per-document entropy/Elogpz terms, see lda_estep_kernel]
         //   + sum_ij S_ij ln(beta_ij + eps)                                                              [Elogpw over the statistics]
         TMVB_CUDA(cudaMemcpyAsync(s.h_pinned, h->d_local + 2 * K_ld + 1, 8, cudaMemcpyDeviceToHost, s.stream));
+        // the read-back is the one host synchronisation of an iteration: the time-out flag of the peer exchange rides along, so
+        // an exchange that gave up on a missing rank (and reduced half-written statistics) raises here instead of going unnoticed
+        const bool peers = h->comm.connected && h->comm.d_ctl;
+        if (peers) TMVB_CUDA(cudaMemcpyAsync(s.h_pinned + 1, h->comm.d_ctl + 128, 8, cudaMemcpyDeviceToHost, s.stream));
         TMVB_CUDA(cudaStreamSynchronize(s.stream));
-        s.st.d2h_bytes += 8;
+        s.st.d2h_bytes += peers ? 16 : 8;
+        if (peers) TMVB_TRY(comm_raise(h, reinterpret_cast<const unsigned *>(s.h_pinned + 1)[1]));
         *elbo_docs = s.h_pinned[0];
         *elbo_global = 0.0;
         (void)K;
@@ -1056,6 +1101,10 @@ int tmvb_lda_download(tmvb_lda_t h, float *alpha, float *beta, float *Elogtheta,
     TMVB_CHECK_ARG(h != nullptr, "handle is NULL");
     Shard &s = h->s;
     TMVB_CUDA(cudaSetDevice(s.device));
+    if (h->comm.connected && h->comm.d_ctl) {   // update_host! of a run that never read an ELBO (checkelbo = Inf)
+        int st = 0;
+        TMVB_TRY(tmvb_lda_comm_status(h, &st));
+    }
     if (alpha) {
         TMVB_TRY(sync_alpha(h));
         for (int64_t i = 0; i < s.K; i++) alpha[i] = std::max((float)h->h_alpha[i], 1.1754944e-38f);

@@ -142,24 +142,46 @@ __global__ void colsum_kernel(const float *__restrict__ stats, int V, int K_ld, 
 // sum_d sum_n c_n H(phi_n) (LDA.jl:76-79) that is linear in the statistics (ln u_ni = ln beta_old_i,w + Elogtheta_old_i),
 // which spares the E-step kernel one logarithm per (token, topic).
 __global__ void normalize_kernel(float *__restrict__ stats, float *__restrict__ beta_new, const float *__restrict__ beta_old,
-                                 const double *__restrict__ rowsum, long long n, int K, int K_ld, double *__restrict__ elbo_w, int want_elbo)
+                                 const double *__restrict__ rowsum, int V, int K, int K_ld, double *__restrict__ elbo_w, int want_elbo)
 {
+    // thread (rl, c): rows rl + RPP * n, the 16-byte chunk c of each -- the four column reciprocals are per-thread constants
+    // (one fp64 division per thread instead of one per element: the element-wise version ran at 0.5 TB/s on L2-resident data)
+    const int CH = K_ld >> 2, RPP = blockDim.x / CH;
+    const int rl = threadIdx.x / CH, c = threadIdx.x - rl * CH;
     double acc = 0.0;
-    for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < n; q += (long long)gridDim.x * blockDim.x) {
-        const int i = (int)(q % K_ld);
-        float s = stats[q];
-        float b = 0.0f;
-        if (i < K) {
-            const double rs = rowsum[i];
-            b = rs > 0.0 ? (float)((double)s / rs) : 0.0f;
-            if (want_elbo) {
-                float l = logf(b + TMVB_EPS);
-                if (beta_old) l -= logf(beta_old[q] + TMVB_EPS);
-                acc += (double)(s * l);
-            }
+    if (rl < RPP) {
+        double inv[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const double rs = (4 * c + j < K) ? rowsum[4 * c + j] : 0.0;
+            inv[j] = rs > 0.0 ? 1.0 / rs : 0.0;
         }
-        beta_new[q] = b;
-        stats[q] = 0.0f;
+        const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int r = blockIdx.x * RPP + rl; r < V; r += gridDim.x * RPP) {
+            const size_t q = (size_t)r * K_ld + 4 * c;
+            const float4 S = *reinterpret_cast<const float4 *>(stats + q);
+            float4 b;
+            b.x = (float)((double)S.x * inv[0]);
+            b.y = (float)((double)S.y * inv[1]);
+            b.z = (float)((double)S.z * inv[2]);
+            b.w = (float)((double)S.w * inv[3]);
+            if (want_elbo) {
+                float4 l = make_float4(logf(b.x + TMVB_EPS), logf(b.y + TMVB_EPS), logf(b.z + TMVB_EPS), logf(b.w + TMVB_EPS));
+                if (beta_old) {
+                    const float4 bo = *reinterpret_cast<const float4 *>(beta_old + q);
+                    l.x -= logf(bo.x + TMVB_EPS);
+                    l.y -= logf(bo.y + TMVB_EPS);
+                    l.z -= logf(bo.z + TMVB_EPS);
+                    l.w -= logf(bo.w + TMVB_EPS);
+                }
+                if (4 * c + 0 < K) acc += (double)(S.x * l.x);
+                if (4 * c + 1 < K) acc += (double)(S.y * l.y);
+                if (4 * c + 2 < K) acc += (double)(S.z * l.z);
+                if (4 * c + 3 < K) acc += (double)(S.w * l.w);
+            }
+            *reinterpret_cast<float4 *>(beta_new + q) = b;
+            *reinterpret_cast<float4 *>(stats + q) = z4;
+        }
     }
     if (want_elbo) {
         acc = warp_sum_d(acc);
@@ -543,10 +565,12 @@ int shard_normalize(Shard *s, double *d_acc, bool want_elbo, bool entropy_term)
     const int grid = (int)std::min<int64_t>((s->V + R - 1) / R, (int64_t)s->n_sm * 8);
     colsum_kernel<<<grid, threads, threads * 8, s->stream>>>(s->d_stats, (int)s->V, s->K_ld, d_acc);
     TMVB_CUDA(cudaGetLastError());
-    const long long n = (long long)s->V * s->K_ld;
-    normalize_kernel<<<grid_for(n, 256, s->n_sm), 256, 0, s->stream>>>(s->d_stats, s->d_beta[s->cur ^ 1],
-                                                                      (want_elbo && entropy_term) ? s->d_beta[s->cur] : nullptr, d_acc, n, (int)s->K,
-                                                                      s->K_ld, d_acc + s->K_ld, want_elbo ? 1 : 0);
+    {
+        const int CH = s->K_ld / 4, RPP = std::max(1, 256 / CH);
+        const int ngrid = (int)std::min<int64_t>((s->V + RPP - 1) / RPP, (int64_t)s->n_sm * 8);
+        normalize_kernel<<<ngrid, std::max(256, CH), 0, s->stream>>>(s->d_stats, s->d_beta[s->cur ^ 1], (want_elbo && entropy_term) ? s->d_beta[s->cur] : nullptr,
+                                                                   d_acc, (int)s->V, (int)s->K, s->K_ld, d_acc + s->K_ld, want_elbo ? 1 : 0);
+    }
     TMVB_CUDA(cudaGetLastError());
     s->st.kernel_launches += 2;
     s->cur ^= 1;  // beta_old <- beta ; beta <- new  (LDA.jl:122-123)

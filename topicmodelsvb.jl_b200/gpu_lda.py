@@ -74,6 +74,7 @@ class gpuLDA:
         self._h = None
         self._resident = False
         self._pinned = None
+        self._corpus_on_device = None   # the Corpus object whose flattening the handle holds
 
     # ------------------------------------------------------------------ device plumbing ------
     def _handle(self):
@@ -98,6 +99,7 @@ class gpuLDA:
             _lib.load().tmvb_lda_destroy(self._h)
             self._h = None
             self._resident = False
+            self._corpus_on_device = None
 
     def __del__(self):
         try:
@@ -109,13 +111,18 @@ class gpuLDA:
         """update_buffer!(model::gpuLDA) (modelutils.jl:370-397): flatten, upload corpus and parameters."""
         lib, h = _lib.load(), self._handle()
         f = self.corp.flat()
-        # the flattened corpus is cached on the host as page-locked Int32 (built once per Corpus): half the upload of the
-        # Int64 vectors update_buffer! rebuilds on every call (modelutils.jl:371-373)
-        t32, c32 = (None, None) if os.environ.get("TMVB_CORPUS64") == "1" else self.corp.flat32()
-        if t32 is not None:
-            _lib.check(lib.tmvb_lda_set_corpus32(h, _lib.ptr(f.N_cumsum), _lib.ptr(t32), _lib.ptr(c32)))
-        else:
-            _lib.check(lib.tmvb_lda_set_corpus(h, _lib.ptr(f.N_cumsum), _lib.ptr(f.terms), _lib.ptr(f.counts)))
+        # A corpus wrapped from a flattened CSR (Corpus.from_csr / readcorp) is immutable, so its device copy stays valid for the
+        # life of the handle: the reference re-flattens and re-uploads the corpus on every update_buffer! (modelutils.jl:371-388)
+        # because its documents are mutable -- a Corpus built from Document objects still takes that path here.
+        if not (self.corp.docs is None and self._corpus_on_device is self.corp):
+            # the flattened corpus is cached on the host as page-locked Int32 (built once per Corpus): half the upload of the
+            # Int64 vectors update_buffer! rebuilds on every call (modelutils.jl:371-373)
+            t32, c32 = (None, None) if os.environ.get("TMVB_CORPUS64") == "1" else self.corp.flat32()
+            if t32 is not None:
+                _lib.check(lib.tmvb_lda_set_corpus32(h, _lib.ptr(f.N_cumsum), _lib.ptr(t32), _lib.ptr(c32)))
+            else:
+                _lib.check(lib.tmvb_lda_set_corpus(h, _lib.ptr(f.N_cumsum), _lib.ptr(f.terms), _lib.ptr(f.counts)))
+            self._corpus_on_device = self.corp
         self.alpha = np.ascontiguousarray(self.alpha, dtype=np.float32)
         self.beta = _fmat(self.beta, self.K, self.V, "beta")
         self.Elogtheta = _fmat(self.Elogtheta, self.K, self.M, "Elogtheta")
