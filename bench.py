@@ -202,6 +202,9 @@ class Arm:
     def step(self):
         m, kind = self.model, self.cfg["model"]
         if kind == "lda":
+            if m.can_iterate():              # the whole iteration as one CUDA graph launch (what train() does)
+                m.elbo = m.iterate(VITER, self.vtol, 1000, self.ntol, want_elbo=True)
+                return m.elbo
             m.estep(VITER, self.vtol, want_elbo=True)
             m.update_beta()                  # all-reduce (N > 1) + normalise
             m.update_alpha(1000, self.ntol)

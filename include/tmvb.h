@@ -97,8 +97,9 @@ int tmvb_lda_mstep(tmvb_lda_t h);
  * from then on tmvb_lda_exchange_mstep() replaces { sum reduce_buffers over ranks; tmvb_lda_mstep }: ONE kernel that
  * reduce-scatters the statistics with loads from the peers' memory, normalises its slice of beta and all-gathers it with
  * stores into the peers' memory (gpuLDA.jl:179-204 semantics on the summed statistics).  Every rank must call it once per
- * outer iteration; a rank that does not arrive within 4 s makes the others give up (tmvb_lda_comm_status != 0) instead
- * of hanging.  world <= 8. */
+ * outer iteration; a rank that does not arrive within TMVB_COMM_TIMEOUT_MS (environment, default 4000) makes the others give
+ * up instead of hanging: the condition is raised (return code 901/902) by the next tmvb_lda_elbo(mode 0) / tmvb_lda_iterate
+ * read-back, by tmvb_lda_download and by tmvb_lda_comm_status, and cleared by the report.  world <= 8. */
 #define TMVB_COMM_BLOB_BYTES 512
 int tmvb_lda_comm_export(tmvb_lda_t h, void *blob, int64_t blob_bytes);
 int tmvb_lda_comm_connect(tmvb_lda_t h, int rank, int world, const void *blobs /* [world][blob_bytes] */, int64_t blob_bytes);
@@ -112,6 +113,15 @@ int tmvb_lda_get_elogtheta_sum(tmvb_lda_t h, double *out);
  * on the reduced Elogtheta_sum, fused with the assembly of the ELBO from the partials of the last estep/mstep.  M_total as
  * above.  Asynchronous when alpha_out is NULL; otherwise alpha_out[K] receives the new alpha (synchronises). */
 int tmvb_lda_update_alpha(tmvb_lda_t h, int64_t M_total, int niter, double ntol, float *alpha_out);
+
+/* One outer iteration of train! -- the body of `for k in 1:iter` (gpuLDA.jl:355-371): the folded inner loop + scatter
+ * (tmvb_lda_estep), update_beta! (tmvb_lda_mstep, or the fused peer exchange when tmvb_lda_comm_connect has been called),
+ * update_alpha! (tmvb_lda_update_alpha) and, with want_elbo, the ELBO that check_elbo! reads (tmvb_lda_elbo mode 0, written to
+ * *elbo) -- enqueued as ONE CUDA graph launch.  With several GPUs the exchange kernel also runs update_alpha! beside the
+ * reduce-scatter, so the iteration is E-step launches + one kernel.  The host synchronises only when want_elbo is set
+ * (checkelbo = Inf iterations are fully asynchronous).  Same result as the four separate calls.  Needs one GPU or connected
+ * peers (a driver that sums tmvb_lda_reduce_buffers itself keeps the separate calls). */
+int tmvb_lda_iterate(tmvb_lda_t h, int viter, float vtol, int want_elbo, int64_t M_total, int niter, double ntol, double *elbo);
 
 /* update_elbo! (gpuLDA.jl:121-128 via check_elbo!, modelutils.jl:574-585) without the K x sumN phi
  * transfer.  mode 0: the value assembled on the device by estep(want_elbo=1) -> mstep -> update_alpha (one 8-byte

@@ -81,6 +81,33 @@ def test_fused_elbo_equals_standalone(tm, orc):
         assert abs(e1 - e2) <= 1e-6 * abs(e2), (it, e1, e2)
 
 
+def test_fused_iteration_equals_separate_steps(tm, monkeypatch):
+    """tmvb_lda_iterate (one CUDA graph launch per outer iteration: what train() uses) == estep + mstep + update_alpha + elbo."""
+    c = tm.synth.gencorp_lda(M=300, V=700, K=6, seed=21)
+    K = 12
+
+    def run(unfused):
+        monkeypatch.setenv("TMVB_UNFUSED", "1" if unfused else "0")
+        model = tm.gpuLDA(tm.Corpus.from_csr(c), K, seed=5)
+        tr = []
+        tm.train(model, iter=5, tol=0.0, printelbo=False, trace=tr, checkelbo=1)
+        assert model.can_iterate() == (not unfused)
+        return np.array(tr), model.alpha.copy(), model.beta.copy(), model.gamma.copy()
+
+    e0, a0, b0, g0 = run(True)
+    e1, a1, b1, g1 = run(False)
+    np.testing.assert_allclose(e1, e0, rtol=1e-7)          # same kernels, same order: only the atomics' order differs
+    np.testing.assert_allclose(a1, a0, rtol=1e-5)
+    np.testing.assert_allclose(b1, b0, rtol=1e-4, atol=1e-9)
+    np.testing.assert_allclose(g1, g0, rtol=1e-4, atol=1e-6)
+    # checkelbo = 2: iterations without an ELBO do not synchronise, the traced ones agree
+    monkeypatch.setenv("TMVB_UNFUSED", "0")
+    model = tm.gpuLDA(tm.Corpus.from_csr(c), K, seed=5)
+    tr = []
+    tm.train(model, iter=4, tol=0.0, printelbo=False, trace=tr, checkelbo=2)
+    np.testing.assert_allclose(tr[1:], e0[[2, 4]], rtol=1e-7)
+
+
 def test_int64_and_int32_corpus_entry_points_agree(tm, monkeypatch):
     """tmvb_lda_set_corpus (Int64 vectors, what update_buffer! builds) and tmvb_lda_set_corpus32 (the host mirror's packed
     cache) lay out the same device corpus: the same trajectories."""

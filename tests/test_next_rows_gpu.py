@@ -79,7 +79,7 @@ dist.destroy_process_group()
 '''
 
 
-@pytest.mark.parametrize("p2p", ["1", "0"])
+@pytest.mark.parametrize("p2p", ["1", "unfused", "0"])
 def test_two_gpu_exchange_matches_single_gpu(tm, orc, tmp_path, p2p):
     """Doc-sharded d %% 2 over two GPUs == the single-process trajectory, with the statistics exchanged by the fused
     peer-memory kernel (tmvb_lda_exchange_mstep, TMVB_P2P=1) and by NCCL all-reduce + tmvb_lda_mstep (TMVB_P2P=0)."""
@@ -89,15 +89,17 @@ def test_two_gpu_exchange_matches_single_gpu(tm, orc, tmp_path, p2p):
         pytest.skip("needs 2 GPUs (run with gpurun --gpus 2)")
     script = tmp_path / "worker.py"
     script.write_text(_WORKER % ROOT)
-    env = dict(os.environ, TMVB_P2P=p2p)
+    # "1": fused iteration (exchange kernel with the update_alpha! CTA); "unfused": the exchange kernel between separate calls;
+    # "0": NCCL all-reduce + tmvb_lda_mstep
+    env = dict(os.environ, TMVB_P2P="0" if p2p == "0" else "1", TMVB_UNFUSED="1" if p2p == "unfused" else "0")
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
-                        "--master-port", "29533" if p2p == "1" else "29534", str(script)], capture_output=True, text=True, timeout=600, env=env)
+                        "--master-port", {"1": "29533", "unfused": "29535", "0": "29534"}[p2p], str(script)], capture_output=True, text=True, timeout=600, env=env)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     import json
     line = [l for l in r.stdout.splitlines() if l.startswith("RESULT ")][-1]
     got = json.loads(line[7:])
     assert got["status"] == 0
-    assert got["p2p"] == (p2p == "1"), "the peer-memory exchange was not used"
+    assert got["p2p"] == (p2p != "0"), "the peer-memory exchange was not used"
     assert got["beta_probe"][0] == got["beta_probe"][1], "ranks disagree on beta"
     c = tm.synth.gencorp_lda(M=400, V=600, K=6, seed=11)
     K = 8

@@ -97,6 +97,7 @@ SIGNATURES = {
     "tmvb_lda_comm_status": (C.c_int, [_vp, C.POINTER(C.c_int)]),
     "tmvb_lda_get_elogtheta_sum": (C.c_int, [_vp, _vp]),
     "tmvb_lda_update_alpha": (C.c_int, [_vp, C.c_int64, C.c_int, C.c_double, _vp]),
+    "tmvb_lda_iterate": (C.c_int, [_vp, C.c_int, C.c_float, C.c_int, C.c_int64, C.c_int, C.c_double, C.POINTER(C.c_double)]),
     "tmvb_lda_elbo": (C.c_int, [_vp, C.c_int, C.c_int64, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "tmvb_lda_download": (C.c_int, [_vp, _vp, _vp, _vp, _vp]),
     "tmvb_lda_download_old": (C.c_int, [_vp, _vp, _vp]),

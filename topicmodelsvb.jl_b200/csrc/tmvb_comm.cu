@@ -1,4 +1,5 @@
 // tmvb_comm.cu -- host side of the peer-memory exchange: CUDA IPC export / import of the per-rank buffers.
+#include <stdlib.h>
 #include <string.h>
 
 #include "tmvb_comm.cuh"
@@ -6,6 +7,12 @@
 namespace tmvb {
 
 static_assert(sizeof(cudaIpcMemHandle_t) == 64, "blob layout assumes 64-byte IPC handles");
+
+static int env_int_or(const char *name, int dflt)
+{
+    const char *v = getenv(name);
+    return (v && *v) ? atoi(v) : dflt;
+}
 
 int comm_export(Comm *c, void *const local_bufs[kCommBufs], void *blob, size_t blob_bytes)
 {
@@ -35,6 +42,8 @@ int comm_connect(Comm *c, int rank, int world, const void *blobs, size_t blob_by
     TMVB_CHECK_ARG(blobs != nullptr && blob_bytes >= kCommBufs * sizeof(cudaIpcMemHandle_t), "blobs missing");
     c->rank = rank;   // set first: comm_free closes whatever has been mapped even if a later handle fails to open
     c->world = world;
+    c->timeout_ms = env_int_or("TMVB_COMM_TIMEOUT_MS", kSpinTimeoutMsDefault);
+    if (c->timeout_ms < 1) c->timeout_ms = kSpinTimeoutMsDefault;
     for (int r = 0; r < world; r++) {
         for (int b = 0; b < kCommBufs; b++) {
             if (r == rank) {

@@ -5,7 +5,7 @@
 // its peers' buffers (CUDA IPC handles, exchanged once by the host driver) and ONE kernel per iteration does
 // reduce-scatter -> column sums -> normalise -> all-gather with plain loads/stores on the mapped peer pointers over NVLink
 // (lda_exchange_mstep_kernel, tmvb_lda.cu).  This header holds the model-independent part: the handle blob, the mapped
-// pointer table, and the device-side barriers (CTA-grid barrier; cross-GPU flag barrier with a bounded spin).
+// pointer table, the control block (flag words with bounded spins, arrival counters, epoch) and the memory-order helpers.
 #pragma once
 
 #include "tmvb_common.cuh"
@@ -26,8 +26,6 @@ struct Comm {
     double *d_small_red = nullptr;           // [kCtlPartLen + 2] local: `small` summed over ranks
     void *peer[kCommBufs][kMaxPeers] = {};   // mapped pointers; [.][rank] = local
     void *local[kCommBufs] = {};
-    unsigned long long epoch = 0;            // three barrier epochs are consumed per exchange
-    unsigned long long calls = 0;
     int timeout_ms = kSpinTimeoutMsDefault;  // bounded spin of the device barriers (env TMVB_COMM_TIMEOUT_MS at connect time)
 };
 
@@ -63,58 +61,27 @@ __device__ __forceinline__ long long global_ns()
 
 // control block layout
 struct CtlView {
-    unsigned long long *flag;   // [kMaxPeers] flag[r] = last epoch rank r has signalled to this rank
-    unsigned *grid_count;       // monotonically increasing arrival counter of the local grid barrier
-    unsigned *status;           // != 0: a spin timed out
-    double *part;               // [2][kCtlPartLen]
+    unsigned long long *flag;        // [kMaxPeers] flag[r] = last epoch rank r has signalled to this rank
+    unsigned *cnt_b, *cnt_c;         // arrival counters of the local CTAs (phases B and C), reset by CTA 0 at the end of a call
+    unsigned *status;                // != 0: a spin timed out
+    unsigned long long *epoch;       // three flag epochs are consumed per exchange
+    unsigned long long *calls;       // exchanges so far (parity selects the partial-sum buffer)
+    unsigned long long *alpha_done;  // progress of the update_alpha! CTA within the current exchange
+    double *part;                    // [2][kCtlPartLen]
 };
 __device__ __forceinline__ CtlView ctl_view(void *ctl)
 {
     unsigned char *b = static_cast<unsigned char *>(ctl);
     CtlView v;
     v.flag = reinterpret_cast<unsigned long long *>(b);
-    v.grid_count = reinterpret_cast<unsigned *>(b + 128);
+    v.cnt_b = reinterpret_cast<unsigned *>(b + 128);
     v.status = reinterpret_cast<unsigned *>(b + 132);
+    v.epoch = reinterpret_cast<unsigned long long *>(b + 136);
+    v.calls = reinterpret_cast<unsigned long long *>(b + 144);
+    v.alpha_done = reinterpret_cast<unsigned long long *>(b + 152);
+    v.cnt_c = reinterpret_cast<unsigned *>(b + 160);
     v.part = reinterpret_cast<double *>(b + kCtlPartOff);
     return v;
-}
-
-// All CTAs of a co-resident (cooperative) grid; `target` = gridDim.x * (number of barriers passed so far + 1).
-__device__ __forceinline__ void grid_barrier(unsigned *count, unsigned target, unsigned *status, long long timeout_ns)
-{
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        __threadfence_system();   // this CTA's writes (local and peer) before the arrival
-        atomicAdd(count, 1u);
-        const long long t0 = global_ns();
-        while (ld_acquire_gpu(count) < target) {
-            if (global_ns() - t0 > timeout_ns) {
-                atomicExch(status, 2u);
-                break;
-            }
-        }
-        __threadfence_system();
-    }
-    __syncthreads();
-}
-
-// Cross-GPU barrier, executed by CTA 0 between two grid barriers: thread r < world signals rank r and waits for it.
-__device__ __forceinline__ void peer_barrier(void *const *peer_ctl, void *my_ctl, int rank, int world, unsigned long long epoch, long long timeout_ns)
-{
-    const int r = threadIdx.x;
-    if (r < world && r != rank) {
-        __threadfence_system();
-        st_release_sys(ctl_view(peer_ctl[r]).flag + rank, epoch);
-        const CtlView me = ctl_view(my_ctl);
-        const long long t0 = global_ns();
-        while (ld_acquire_sys(me.flag + r) < epoch) {
-            if (global_ns() - t0 > timeout_ns) {
-                atomicExch(me.status, 1u);
-                break;
-            }
-        }
-    }
-    __syncthreads();
 }
 
 #endif  // __CUDACC__

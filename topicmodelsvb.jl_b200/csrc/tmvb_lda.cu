@@ -271,20 +271,16 @@ __device__ __forceinline__ double block_min(double v, double (*red)[16])
 
 // update_alpha! (LDA.jl:97-118): interior-point Newton with log barrier in fp64.  One CTA: thread i < K owns alpha_i, thread K
 // owns sum(alpha), so that every Newton step costs ONE digamma/trigamma evaluation per thread (the one-warp version
-// spent 57 us per outer iteration on three serial evaluations per lane).  Then, when the last E-step accumulated ELBO
-// partials, the whole ELBO is assembled here (see tmvb_lda_elbo) so that an outer iteration needs a single 8-byte
-// read-back instead of three host round trips.
-//   small = [sum_d Elogtheta_d (K_ld) | per-document ELBO terms | sweeps], local = [rowsum (K_ld) | elbo_w]
-__global__ void lda_alpha_kernel(double *__restrict__ alpha64, float *__restrict__ alpha32, const double *__restrict__ small,
-                                 const double *__restrict__ local, int K, int K_ld, double Md, int niter, double ntol, int want_elbo,
-                                 double *__restrict__ result)
+// spent 57 us per outer iteration on three serial evaluations per lane).  Returns (to every thread) the part of the ELBO
+// that depends on alpha:  M (lnG(sum alpha) - sum lnG(alpha)) + sum_i (alpha_i - alpha_estep_i - eps) Esum_i   (see tmvb_lda_elbo).
+//   Es = this thread's sum_d Elogtheta_di (i = threadIdx.x < K)
+__device__ __forceinline__ double lda_alpha_newton(double *__restrict__ alpha64, float *__restrict__ alpha32, double Es, int K, double Md, int niter,
+                                                   double ntol, double (*red)[16], double *bc)
 {
-    __shared__ double red[3][16];
-    __shared__ double bc[2];
     const int tid = threadIdx.x;
     const bool is_topic = tid < K, is_sum = tid == K;
     double a = is_topic ? alpha64[tid] : 1.0;
-    const double a_estep = a, Es = is_topic ? small[tid] : 0.0;
+    const double a_estep = a;
     double nu = (double)K;
     for (int it = 0; it < niter; it++) {
         double a0 = is_topic ? a : 0.0, u1 = 0.0, u2 = 0.0;
@@ -324,16 +320,27 @@ __global__ void lda_alpha_kernel(double *__restrict__ alpha64, float *__restrict
         sl = lgamma(a);
         lin = (a - a_estep - TMVB_EPS_D) * Es;
     }
-    if (want_elbo) {
-        block_sum3(a0, sl, lin, red);
-        // want_elbo = 2: only the part that depends on alpha -- the kernel then runs beside the M-step kernels on another
-        // stream and lda_elbo_assemble_kernel adds the M-step's term once both have finished
-        if (tid == 0) {
-            if (want_elbo == 2)
-                result[1] = Md * (lgamma(a0) - sl) + lin;
-            else
-                result[0] = small[K_ld] + Md * (lgamma(a0) - sl) + lin + local[K_ld];
-        }
+    block_sum3(a0, sl, lin, red);
+    return Md * (lgamma(a0) - sl) + lin;
+}
+
+// The stand-alone launch: small = [sum_d Elogtheta_d (K_ld) | per-document ELBO terms | sweeps], local = [rowsum (K_ld) | elbo_w].
+// want_elbo = 1: the whole ELBO is assembled here, so that an outer iteration needs a single 8-byte read-back; want_elbo = 2:
+// only the alpha-dependent part is written (result[1]) -- the kernel then runs beside the M-step kernels on another stream and
+// lda_elbo_assemble_kernel adds the M-step's term once both have finished.
+__global__ void lda_alpha_kernel(double *__restrict__ alpha64, float *__restrict__ alpha32, const double *__restrict__ small,
+                                 const double *__restrict__ local, int K, int K_ld, double Md, int niter, double ntol, int want_elbo,
+                                 double *__restrict__ result)
+{
+    __shared__ double red[3][16];
+    __shared__ double bc[2];
+    const double Es = threadIdx.x < K ? small[threadIdx.x] : 0.0;
+    const double part = lda_alpha_newton(alpha64, alpha32, Es, K, Md, niter, ntol, red, bc);
+    if (want_elbo && threadIdx.x == 0) {
+        if (want_elbo == 2)
+            result[1] = part;
+        else
+            result[0] = small[K_ld] + part + local[K_ld];
     }
 }
 
@@ -361,47 +368,120 @@ __global__ void lda_phi_kernel(const LdaDev p, const float *__restrict__ beta_ol
     }
 }
 
-// ------------------------------------------------------------------ fused exchange + M-step ----------
-// One kernel per outer iteration replaces { all-reduce(stats), all-reduce(small), colsum, normalise } when the ranks of a
-// box have mapped each other's buffers (tmvb_comm.cuh).  V is cut into `world` row slices; rank r
-//   1. waits until every rank's E-step has finished                                              [peer barrier 1]
-//   2. reduce-scatter: sums its slice of the K x V statistics over all ranks with loads from the mapped peer buffers
-//      (fixed rank order: every rank would compute bit-identical sums), accumulates the slice's column sums in fp64,
-//      and sums the small fp64 vector (sum_d Elogtheta_d, ELBO partials, sweeps) of all ranks
-//   3. publishes its column-sum partials                                                          [peer barrier 2]
-//   4. normalises its slice (LDA.jl:121-125), all-gathers it by storing into EVERY rank's next beta buffer, accumulates
-//      sum S (ln beta_new - ln beta_old) (Elogpw + the linear part of -Elogqz), and zeroes its local statistics
-//   5. [peer barrier 3], then sums the ELBO partials of all ranks.
+// ------------------------------------------------------------------ fused exchange + M-step (+ update_alpha!) ----------
+// One kernel per outer iteration replaces { all-reduce(stats), all-reduce(small), colsum, normalise, update_alpha!, ELBO assembly }
+// when the ranks of a box have mapped each other's buffers (tmvb_comm.cuh).  V is cut into `world` row slices; on rank r
+//   A. CTA 0 tells every peer that this rank's E-step has finished (flag epoch+1 in the peer's control block); every CTA waits
+//      for all peers' flags -- the statistics of all ranks are complete;
+//   B. reduce-scatter: each CTA sums its rows of the slice over all ranks with loads from the mapped peer buffers (fixed rank
+//      order), accumulates the slice's column sums in fp64 and publishes them (atomics into this rank's partial vector); when
+//      the last CTA has arrived CTA 0 raises flag epoch+2 on every rank (itself included);
+//   C. every CTA waits for all flags epoch+2, sums the column-sum partials of all ranks (fixed order: bit-identical on every
+//      rank), normalises its rows (LDA.jl:121-125), all-gathers them by storing into EVERY rank's next beta buffer, accumulates
+//      sum S (ln beta_new - ln beta_old) (Elogpw + the linear part of -Elogqz) and zeroes its local statistics; when the last CTA
+//      has arrived CTA 0 raises flag epoch+3 on the peers and waits for theirs -- every slice has landed everywhere;
+//   D. CTA 0 sums the ELBO partials of all ranks and assembles the ELBO.
+// With do_alpha the grid has one more CTA that does not take part in B and C: after A it sums the small fp64 vectors
+// (sum_d Elogtheta_d, per-document ELBO terms, sweeps) of all ranks and runs update_alpha! (LDA.jl:97-118) BESIDE the exchange;
+// CTA 0 waits for it before it lets the peers go (their next E-step clears the vector this CTA reads) and before it assembles
+// the ELBO.  No grid-wide barrier: two arrival counters and the flag words; no cooperative launch (the grid is at most one CTA
+// per SM plus one, resident at once on an otherwise idle device), so the kernel is an ordinary node of the iteration's CUDA graph.
+// The epoch and the buffer parity live in the control block: the kernel's parameters do not change from call to call.
 // Traffic per rank: (world-1)/world of the table in, the same out, over NVLink; no NCCL call, no host round trip.
 struct LdaXchg {
-    int V, K, K_ld, rank, world, want_elbo, n_small, parity;
-    unsigned long long epoch;
+    int V, K, K_ld, rank, world, want_elbo, n_small, do_alpha;
+    long long timeout_ns;
     const float *stats[kMaxPeers];
     float *beta_new[kMaxPeers];
     const double *small[kMaxPeers];
     void *ctl[kMaxPeers];
     float *my_stats;
     const float *beta_old;
-    double *small_red, *local;
+    double *small_red, *local, *result;
+    double *alpha64;
+    float *alpha32;
+    double Md, ntol;
+    int niter;
 };
+
+// thread r < world waits until rank r has signalled `target` (self included when with_self); every thread of the CTA returns after it
+__device__ __forceinline__ void wait_flags(const CtlView &me, int rank, int world, unsigned long long target, bool with_self, long long timeout_ns)
+{
+    const int r = threadIdx.x;
+    if (r < world && (with_self || r != rank)) {
+        const long long t0 = global_ns();
+        while (ld_acquire_sys(me.flag + r) < target) {
+            if (global_ns() - t0 > timeout_ns) {
+                atomicExch(me.status, 1u);
+                break;
+            }
+        }
+    }
+    __syncthreads();
+}
+__device__ __forceinline__ void wait_count(unsigned *count, unsigned target, unsigned *status, long long timeout_ns)
+{
+    const long long t0 = global_ns();
+    while (ld_acquire_gpu(count) < target) {
+        if (global_ns() - t0 > timeout_ns) {
+            atomicExch(status, 2u);
+            break;
+        }
+    }
+}
 
 __global__ void __launch_bounds__(256) lda_exchange_mstep_kernel(const LdaXchg x)
 {
     extern __shared__ double sh[];  // [RPP][K_ld] column-sum staging | rs[K_ld]
-    const int tid = threadIdx.x, G = gridDim.x;
+    __shared__ unsigned long long s_epoch[2];
+    __shared__ double red[3][16];
+    __shared__ double bc[2];
+    const int tid = threadIdx.x, G = gridDim.x - x.do_alpha;
     const int K_ld = x.K_ld, CH = K_ld >> 2, RPP = blockDim.x / CH;
     const int rl = tid / CH, c = tid - rl * CH;
     const bool active = rl < RPP;
     double *rs = sh + (size_t)RPP * K_ld;
     void *my_ctl = x.ctl[x.rank];
     const CtlView me = ctl_view(my_ctl);
-    double *my_part = me.part + x.parity * kCtlPartLen;
+    if (tid == 0) {
+        s_epoch[0] = *me.epoch;
+        s_epoch[1] = *me.calls;
+    }
+    __syncthreads();
+    const unsigned long long epoch = s_epoch[0];
+    const int parity = (int)(s_epoch[1] & 1);
+    double *my_part = me.part + parity * kCtlPartLen;
     const int r0 = (int)((long long)x.V * x.rank / x.world), r1 = (int)((long long)x.V * (x.rank + 1) / x.world);
 
-    if (blockIdx.x == 0 && x.world > 1) peer_barrier(x.ctl, my_ctl, x.rank, x.world, x.epoch + 1);
-    grid_barrier(me.grid_count, 1u * G, me.status);
+    if (x.do_alpha && (int)blockIdx.x == G) {
+        // ---- the update_alpha! CTA: observer of phase A, then the reduction of `small` and the Newton iteration
+        wait_flags(me, x.rank, x.world, epoch + 1, false, x.timeout_ns);
+        for (int i = tid; i < x.n_small; i += blockDim.x) {
+            double a = 0.0;
+            for (int pr = 0; pr < x.world; pr++) a += __ldcg(x.small[pr] + i);
+            x.small_red[i] = a;
+        }
+        __syncthreads();
+        const double Es = tid < x.K ? x.small_red[tid] : 0.0;
+        __threadfence();
+        if (tid == 0) st_release_sys(me.alpha_done, epoch + 1);   // the peers' small vectors have been read
+        const double part = lda_alpha_newton(x.alpha64, x.alpha32, Es, x.K, x.Md, x.niter, x.ntol, red, bc);
+        if (tid == 0) {
+            x.result[1] = part;
+            __threadfence();
+            st_release_sys(me.alpha_done, epoch + 3);
+        }
+        return;
+    }
 
-    // ---- reduce-scatter + column sums of the slice
+    // ---- A: every rank's E-step has finished
+    if (blockIdx.x == 0 && tid < x.world && tid != x.rank) {
+        __threadfence_system();
+        st_release_sys(ctl_view(x.ctl[tid]).flag + x.rank, epoch + 1);
+    }
+    wait_flags(me, x.rank, x.world, epoch + 1, false, x.timeout_ns);
+
+    // ---- B: reduce-scatter + column sums of the slice
     double cs0 = 0.0, cs1 = 0.0, cs2 = 0.0, cs3 = 0.0;
     if (active) {
         for (int r = r0 + blockIdx.x * RPP + rl; r < r1; r += G * RPP) {
@@ -432,20 +512,31 @@ __global__ void __launch_bounds__(256) lda_exchange_mstep_kernel(const LdaXchg x
         for (int q = 0; q < RPP; q++) a += sh[(size_t)q * K_ld + tid];
         if (a != 0.0) atomicAdd(my_part + tid, a);
     }
-    if (blockIdx.x == 0)
+    if (blockIdx.x == 0 && !x.do_alpha)
         for (int i = tid; i < x.n_small; i += blockDim.x) {
             double a = 0.0;
             for (int pr = 0; pr < x.world; pr++) a += __ldcg(x.small[pr] + i);
             x.small_red[i] = a;
         }
-    grid_barrier(me.grid_count, 2u * G, me.status);
-    if (blockIdx.x == 0 && x.world > 1) peer_barrier(x.ctl, my_ctl, x.rank, x.world, x.epoch + 2);
-    grid_barrier(me.grid_count, 3u * G, me.status);
+    __syncthreads();
+    if (tid == 0) {
+        __threadfence();
+        atomicAdd(me.cnt_b, 1u);
+    }
+    if (blockIdx.x == 0) {
+        if (tid == 0) wait_count(me.cnt_b, (unsigned)G, me.status, x.timeout_ns);
+        __syncthreads();
+        if (tid < x.world) {
+            __threadfence_system();
+            st_release_sys(ctl_view(x.ctl[tid]).flag + x.rank, epoch + 2);
+        }
+    }
+    wait_flags(me, x.rank, x.world, epoch + 2, true, x.timeout_ns);
 
-    // ---- total column sums (every CTA, fixed rank order), normalise + all-gather the slice, zero the local statistics
+    // ---- C: total column sums (fixed rank order), normalise + all-gather the rows, zero the local statistics
     if (tid < K_ld) {
         double a = 0.0;
-        for (int pr = 0; pr < x.world; pr++) a += __ldcg(ctl_view(x.ctl[pr]).part + x.parity * kCtlPartLen + tid);
+        for (int pr = 0; pr < x.world; pr++) a += __ldcg(ctl_view(x.ctl[pr]).part + parity * kCtlPartLen + tid);
         rs[tid] = a;
     }
     __syncthreads();
@@ -473,7 +564,7 @@ __global__ void __launch_bounds__(256) lda_exchange_mstep_kernel(const LdaXchg x
             *reinterpret_cast<float4 *>(x.my_stats + q) = make_float4(0.f, 0.f, 0.f, 0.f);
         }
     }
-    {   // the rows outside the slice (the peers have finished reading them: peer barrier 2)
+    {   // the rows outside the slice (the peers have finished reading them: flag epoch+2)
         const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
         float4 *st4 = reinterpret_cast<float4 *>(x.my_stats);
         const size_t n4 = (size_t)x.V * CH, s0 = (size_t)r0 * CH, s1 = (size_t)r1 * CH;
@@ -484,21 +575,57 @@ __global__ void __launch_bounds__(256) lda_exchange_mstep_kernel(const LdaXchg x
         eacc = warp_sum_d(eacc);
         if ((tid & 31) == 0 && eacc != 0.0) atomicAdd(my_part + K_ld, eacc);
     }
-    grid_barrier(me.grid_count, 4u * G, me.status);
+    __syncthreads();
+    if (tid == 0) {
+        __threadfence_system();   // this CTA's stores into the peers' tables before the arrival
+        atomicAdd(me.cnt_c, 1u);
+    }
     if (blockIdx.x != 0) return;
-    if (x.world > 1) peer_barrier(x.ctl, my_ctl, x.rank, x.world, x.epoch + 3);
 
-    // ---- the reduced ELBO term; rowsum for inspection; recycle the other parity of the partial sums
+    // ---- D (CTA 0): every local CTA has stored its rows; the update_alpha! CTA has read the peers' vectors; then the peers
+    if (tid == 0) {
+        wait_count(me.cnt_c, (unsigned)G, me.status, x.timeout_ns);
+        if (x.do_alpha) {
+            const long long t0 = global_ns();
+            while (ld_acquire_sys(me.alpha_done) < epoch + 1)
+                if (global_ns() - t0 > x.timeout_ns) {
+                    atomicExch(me.status, 2u);
+                    break;
+                }
+        }
+    }
+    __syncthreads();
+    if (tid < x.world && tid != x.rank) {
+        __threadfence_system();
+        st_release_sys(ctl_view(x.ctl[tid]).flag + x.rank, epoch + 3);
+    }
+    wait_flags(me, x.rank, x.world, epoch + 3, false, x.timeout_ns);
+
+    // the reduced ELBO term; rowsum for inspection; recycle the other parity of the partial sums; next call's epoch
     if (tid < K_ld) x.local[tid] = rs[tid];
     if (tid == 0) {
         double a = 0.0;
-        for (int pr = 0; pr < x.world; pr++) a += __ldcg(ctl_view(x.ctl[pr]).part + x.parity * kCtlPartLen + K_ld);
+        for (int pr = 0; pr < x.world; pr++) a += __ldcg(ctl_view(x.ctl[pr]).part + parity * kCtlPartLen + K_ld);
         x.local[K_ld] = a;
+        if (x.do_alpha) {
+            const long long t0 = global_ns();
+            while (ld_acquire_sys(me.alpha_done) < epoch + 3)
+                if (global_ns() - t0 > x.timeout_ns) {
+                    atomicExch(me.status, 2u);
+                    break;
+                }
+            if (x.want_elbo) x.result[0] = x.small_red[K_ld] + x.result[1] + a;
+        }
+        *me.cnt_b = 0u;
+        *me.cnt_c = 0u;
+        *me.epoch = epoch + 3;
+        *me.calls = s_epoch[1] + 1;
     }
-    double *other = me.part + (x.parity ^ 1) * kCtlPartLen;
+    double *other = me.part + (parity ^ 1) * kCtlPartLen;
     for (int i = tid; i < kCtlPartLen; i += blockDim.x) other[i] = 0.0;
 }
 
+typedef void (*LdaEstepFn)(const LdaDev, int, int, int, int, int *);
 // The hybrid kernel is instantiated per K_ld (compile-time strides), one translation unit per value: tmvb_lda_hyb_<K_ld>.cu
 // built from tmvb_lda_hyb_inst.cuh; tmvb_lda_hyb.cuh declares the tables.  Other K use the tile kernel.
 static const LdaHybLayout *const kLdaHyb[] = {TMVB_LDA_HYB_TABLES};
@@ -547,6 +674,7 @@ struct tmvb_lda_s {
     double *d_small = nullptr;          // [K_ld+2], summed over ranks
     double *d_local = nullptr;          // [K_ld] rowsum | [K_ld] elbo_w | [K_ld+1] scratch for the standalone ELBO
     bool solo = true;                   // no other rank: nothing sums `small` between the E-step and update_alpha!
+    std::vector<Shard::LaunchGraph> iter_graphs;   // captured outer iterations (tmvb_lda_iterate), keyed like the E-step graphs
     Comm comm;                          // peer-memory exchange (multi-GPU), see tmvb_comm.cuh
 };
 
@@ -584,6 +712,9 @@ void lda_free(tmvb_lda_t h)
 {
     cudaSetDevice(h->s.device);
     if (h->s.stream) cudaStreamSynchronize(h->s.stream);
+    for (auto &g : h->iter_graphs)
+        if (g.exec) cudaGraphExecDestroy(g.exec);
+    h->iter_graphs.clear();
     cudaFree(h->d_alpha);
     cudaFree(h->d_alpha64);
     cudaFree(h->d_Elogtheta);
@@ -916,6 +1047,56 @@ int tmvb_lda_comm_connect(tmvb_lda_t h, int rank, int world, const void *blobs, 
     return comm_connect(&h->comm, rank, world, blobs, (size_t)blob_bytes);
 }
 
+// enqueue the fused exchange kernel on s.stream; do_alpha: the kernel also runs update_alpha! and assembles the ELBO
+static int lda_enqueue_exchange(tmvb_lda_t h, bool do_alpha, int64_t M_total, int niter, double ntol)
+{
+    Shard &s = h->s;
+    Comm &c = h->comm;
+    LdaXchg x;
+    memset(&x, 0, sizeof(x));
+    x.V = (int)s.V;
+    x.K = (int)s.K;
+    x.K_ld = s.K_ld;
+    x.rank = c.rank;
+    x.world = c.world;
+    x.want_elbo = h->elbo_valid ? 1 : 0;
+    x.n_small = s.K_ld + 2;
+    x.do_alpha = do_alpha ? 1 : 0;
+    x.timeout_ns = (long long)c.timeout_ms * 1000000ll;
+    const int nb = s.cur ^ 1;  // the buffer that becomes `beta`
+    for (int r = 0; r < kMaxPeers; r++) {
+        const bool ok = r < c.world;
+        x.stats[r] = ok ? (const float *)c.peer[0][r] : nullptr;
+        x.beta_new[r] = ok ? (float *)c.peer[1 + nb][r] : nullptr;
+        x.small[r] = ok ? (const double *)c.peer[3][r] : nullptr;
+        x.ctl[r] = ok ? c.peer[4][r] : nullptr;
+    }
+    x.my_stats = s.d_stats;
+    x.beta_old = s.d_beta[s.cur];
+    x.small_red = c.d_small_red;
+    x.local = h->d_local;
+    x.result = h->d_local + 2 * s.K_ld + 1;
+    x.alpha64 = h->d_alpha64;
+    x.alpha32 = h->d_alpha;
+    x.Md = (double)M_total;
+    x.niter = niter;
+    x.ntol = ntol;
+    const int CH = s.K_ld / 4, RPP = 256 / CH;
+    const size_t smem = ((size_t)RPP * s.K_ld + s.K_ld) * 8;
+    const int rows = (int)((s.V + c.world - 1) / c.world);
+    const int G = std::min(s.n_sm, std::max(1, (rows + RPP - 1) / RPP));
+    // every CTA of the grid spins on its siblings: they must all be resident at once
+    int occ = 0;
+    TMVB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void *)lda_exchange_mstep_kernel, 256, smem));
+    if ((long long)occ * s.n_sm < G + x.do_alpha) return fail(-4, "internal: the exchange kernel's grid cannot be co-resident");
+    lda_exchange_mstep_kernel<<<G + x.do_alpha, 256, smem, s.stream>>>(x);
+    TMVB_CUDA(cudaGetLastError());
+    // the reduced small vector replaces the local one: no peer reads the local one any more once this kernel has finished
+    // (a peer lets this rank go only after its update_alpha! CTA / its CTA 0 has read it)
+    TMVB_CUDA(cudaMemcpyAsync(h->d_small, c.d_small_red, (s.K_ld + 2) * 8, cudaMemcpyDeviceToDevice, s.stream));
+    return 0;
+}
+
 int tmvb_lda_exchange_mstep(tmvb_lda_t h)
 {
     TMVB_CHECK_ARG(h != nullptr, "handle is NULL");
@@ -926,44 +1107,149 @@ int tmvb_lda_exchange_mstep(tmvb_lda_t h)
     TMVB_CUDA(cudaSetDevice(s.device));
     TMVB_CUDA(cudaEventRecord(s.ev[2], s.stream));
     if (s.V > 0) {
-        LdaXchg x;
-        x.V = (int)s.V;
-        x.K = (int)s.K;
-        x.K_ld = s.K_ld;
-        x.rank = c.rank;
-        x.world = c.world;
-        x.want_elbo = h->elbo_valid ? 1 : 0;
-        x.n_small = s.K_ld + 2;
-        x.parity = (int)(c.calls & 1);
-        x.epoch = c.epoch;
-        const int nb = s.cur ^ 1;  // the buffer that becomes `beta`
-        for (int r = 0; r < kMaxPeers; r++) {
-            const bool ok = r < c.world;
-            x.stats[r] = ok ? (const float *)c.peer[0][r] : nullptr;
-            x.beta_new[r] = ok ? (float *)c.peer[1 + nb][r] : nullptr;
-            x.small[r] = ok ? (const double *)c.peer[3][r] : nullptr;
-            x.ctl[r] = ok ? c.peer[4][r] : nullptr;
-        }
-        x.my_stats = s.d_stats;
-        x.beta_old = s.d_beta[s.cur];
-        x.small_red = c.d_small_red;
-        x.local = h->d_local;
-        TMVB_CUDA(cudaMemsetAsync(c.d_ctl + 128, 0, 4, s.stream));  // grid barrier arrival counter
-        const int CH = s.K_ld / 4, RPP = 256 / CH;
-        const size_t smem = ((size_t)RPP * s.K_ld + s.K_ld) * 8;
-        const int rows = (int)((s.V + c.world - 1) / c.world);
-        int grid = std::min(s.n_sm, std::max(1, (rows + RPP - 1) / RPP));
-        void *args[] = {&x};
-        TMVB_CUDA(cudaLaunchCooperativeKernel((const void *)lda_exchange_mstep_kernel, dim3(grid), dim3(256), args, smem, s.stream));
+        TMVB_TRY(lda_enqueue_exchange(h, false, 0, 0, 0.0));
         s.st.kernel_launches++;
-        // the reduced small vector replaces the local one (peers read the local one only before their second barrier)
-        TMVB_CUDA(cudaMemcpyAsync(h->d_small, c.d_small_red, (s.K_ld + 2) * 8, cudaMemcpyDeviceToDevice, s.stream));
-        c.epoch += 3;
-        c.calls++;
         s.cur ^= 1;  // beta_old <- beta ; beta <- new  (LDA.jl:122-123)
     }
     TMVB_CUDA(cudaEventRecord(s.ev[3], s.stream));
     s.mstep_timed = true;
+    return 0;
+}
+
+// One outer iteration of train! (gpuLDA.jl:355-371: the folded inner loop, update_beta!, update_alpha!, and the ELBO that
+// check_elbo! reads) as ONE CUDA graph launch: E-step bucket launches on four streams -> [one GPU: colsum + normalise with
+// update_alpha! beside them | several GPUs: the fused exchange kernel, which also runs update_alpha!] -> ELBO read-back into
+// page-locked memory.  The graph is captured once per (beta buffer parity, keyword set); an iteration then costs the host one
+// cudaGraphLaunch and -- only when the ELBO is wanted -- one stream synchronisation.
+int tmvb_lda_iterate(tmvb_lda_t h, int viter, float vtol, int want_elbo, int64_t M_total, int niter, double ntol, double *elbo)
+{
+    TMVB_CHECK_ARG(h != nullptr, "handle is NULL");
+    TMVB_CHECK_ARG(viter >= 1, "viter must be at least 1");
+    TMVB_CHECK_ARG(vtol >= 0.f && ntol >= 0.0 && niter >= 0, "iteration/tolerance parameters must be nonnegative");  // gpuLDA.jl:349-350
+    TMVB_CHECK_ARG(!want_elbo || elbo != nullptr, "elbo pointer is NULL");
+    Shard &s = h->s;
+    Comm &c = h->comm;
+    TMVB_CHECK_ARG(s.corpus_set, "set_corpus has not been called");
+    TMVB_CHECK_ARG(h->solo || c.connected, "tmvb_lda_iterate needs one GPU or connected peers (the NCCL path sums the buffers between estep and mstep)");
+    TMVB_CHECK_ARG(!c.connected || s.K_ld + 1 <= kCtlPartLen, "K too large for the exchange control block");
+    TMVB_CUDA(cudaSetDevice(s.device));
+    const bool fuse_alpha = c.connected && s.K + 1 <= 256 && s.V > 0;
+    LdaDev p = dev_view(h);
+    p.viter = viter;
+    p.vtol = vtol;
+    LdaPick pk;
+    pk.tile[0] = (const void *)kLdaEstep[0][s.layout][want_elbo != 0];
+    pk.tile[1] = (const void *)kLdaEstep[1][s.layout][want_elbo != 0];
+    pk.tile[2] = (const void *)kLdaEstep[2][s.layout][want_elbo != 0];
+    pk.hyb = lda_hyb_layout(s.lpt, s.cpl, s.K_ld);
+    pk.elbo = want_elbo != 0;
+    std::string key;
+    TMVB_TRY(shard_launch_key(&s, lda_pick, &pk, &p, sizeof(p), &key));
+    {
+        const long long extra[6] = {want_elbo != 0, (long long)M_total, niter, c.connected ? c.world : 0, c.rank, 0};
+        key.append((const char *)extra, sizeof(extra));
+        key.append((const char *)&ntol, sizeof(ntol));
+        key.append("iter", 4);
+    }
+    h->elbo_valid = want_elbo != 0;   // read by the enqueue helpers below
+    double *result = h->d_local + 2 * s.K_ld + 1;
+    const int threads = 32 * (((int)s.K + 1 + 31) / 32);
+
+    // timing events inside a capture must be recorded as external event nodes to be readable afterwards
+    auto rec = [&](cudaEvent_t ev) -> cudaError_t {
+        cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+        cudaStreamIsCapturing(s.stream, &cs);
+        return cs == cudaStreamCaptureStatusActive ? cudaEventRecordWithFlags(ev, s.stream, cudaEventRecordExternal) : cudaEventRecord(ev, s.stream);
+    };
+    const int64_t launches0 = s.st.kernel_launches;
+    auto enqueue = [&]() -> int {
+        TMVB_CUDA(rec(s.ev[0]));
+        TMVB_CUDA(cudaMemsetAsync(h->d_small, 0, (s.K_ld + 2) * 8, s.stream));
+        if (!s.buckets.empty()) TMVB_TRY(shard_enqueue_buckets(&s, lda_pick, &pk, &p));
+        TMVB_CUDA(rec(s.ev[1]));
+        TMVB_CUDA(rec(s.ev[2]));
+        if (c.connected && s.V > 0) {
+            TMVB_TRY(lda_enqueue_exchange(h, fuse_alpha, M_total, niter, ntol));
+            if (!fuse_alpha) {
+                lda_alpha_kernel<<<1, threads, 0, s.stream>>>(h->d_alpha64, h->d_alpha, h->d_small, h->d_local, (int)s.K, s.K_ld, (double)M_total, niter, ntol,
+                                                              want_elbo ? 1 : 0, result);
+                TMVB_CUDA(cudaGetLastError());
+            }
+        } else {
+            // update_alpha! on an auxiliary stream beside colsum / normalise (it needs only sum_d Elogtheta_d)
+            const bool beside = s.n_streams > 1;
+            cudaStream_t as = beside ? s.aux[0] : s.stream;
+            if (beside) {
+                TMVB_CUDA(cudaEventRecord(s.ev_fork, s.stream));
+                TMVB_CUDA(cudaStreamWaitEvent(as, s.ev_fork, 0));
+            }
+            lda_alpha_kernel<<<1, threads, 0, as>>>(h->d_alpha64, h->d_alpha, h->d_small, h->d_local, (int)s.K, s.K_ld, (double)M_total, niter, ntol,
+                                                    want_elbo ? 2 : 0, result);
+            TMVB_CUDA(cudaGetLastError());
+            if (s.V > 0) {
+                TMVB_TRY(shard_normalize(&s, h->d_local, want_elbo != 0, true));
+                s.cur ^= 1;   // shard_normalize flipped the buffers: the flip is redone once per LAUNCH below, not per capture
+            }
+            if (beside) {
+                TMVB_CUDA(cudaEventRecord(s.ev_join[0], as));
+                TMVB_CUDA(cudaStreamWaitEvent(s.stream, s.ev_join[0], 0));
+            }
+            if (want_elbo) {
+                lda_elbo_assemble_kernel<<<1, 1, 0, s.stream>>>(h->d_small, h->d_local, s.K_ld, result);
+                TMVB_CUDA(cudaGetLastError());
+            }
+        }
+        TMVB_CUDA(rec(s.ev[3]));
+        if (want_elbo) {
+            TMVB_CUDA(cudaMemcpyAsync(s.h_pinned, result, 8, cudaMemcpyDeviceToHost, s.stream));
+            if (c.connected) TMVB_CUDA(cudaMemcpyAsync(s.h_pinned + 1, c.d_ctl + 128, 8, cudaMemcpyDeviceToHost, s.stream));
+        }
+        return 0;
+    };
+
+    cudaGraphExec_t exec = nullptr;
+    for (auto &g : h->iter_graphs)
+        if (g.key == key) exec = g.exec;
+    if (!exec && s.use_graphs) {
+        if (h->iter_graphs.size() >= 8) {
+            for (auto &g : h->iter_graphs) cudaGraphExecDestroy(g.exec);
+            h->iter_graphs.clear();
+        }
+        cudaGraph_t graph = nullptr;
+        TMVB_CUDA(cudaStreamBeginCapture(s.stream, cudaStreamCaptureModeThreadLocal));
+        const int rc = enqueue();
+        const cudaError_t e = cudaStreamEndCapture(s.stream, &graph);
+        if (rc == 0 && e == cudaSuccess && graph) {
+            Shard::LaunchGraph lg;
+            lg.key = key;
+            if (cudaGraphInstantiate(&lg.exec, graph, 0) == cudaSuccess) {
+                h->iter_graphs.push_back(lg);
+                exec = lg.exec;
+            }
+        }
+        if (graph) cudaGraphDestroy(graph);
+        if (!exec) {
+            cudaGetLastError();
+            s.use_graphs = false;   // capture is not possible here (the caller's stream is capturing, ...): launch directly
+            if (rc != 0) return rc;
+        }
+    }
+    if (exec)
+        TMVB_CUDA(cudaGraphLaunch(exec, s.stream));
+    else
+        TMVB_TRY(enqueue());
+    // host-side bookkeeping of what the graph did
+    s.st.kernel_launches = launches0 + (int64_t)s.buckets.size() + (c.connected ? (fuse_alpha ? 1 : 2) : (s.V > 0 ? 3 : 1) + (want_elbo ? 1 : 0));
+    if (s.V > 0) s.cur ^= 1;  // beta_old <- beta ; beta <- new  (LDA.jl:122-123)
+    s.estep_timed = s.mstep_timed = true;
+    h->alpha_on_device = true;
+    h->elbo_dev_valid = h->elbo_valid;
+    if (want_elbo) {
+        TMVB_CUDA(cudaStreamSynchronize(s.stream));
+        s.st.d2h_bytes += c.connected ? 16 : 8;
+        if (c.connected) TMVB_TRY(comm_raise(h, reinterpret_cast<const unsigned *>(s.h_pinned + 1)[1]));
+        *elbo = s.h_pinned[0];
+    }
     return 0;
 }
 

@@ -471,7 +471,7 @@ int shard_download_rows(Shard *s, const float *d_src, float *host, int64_t rows,
 const void *pick_by_warps(const Bucket &b, const void *ctx) { return static_cast<const void *const *>(ctx)[b.warps - 1]; }
 
 // the launches of one E-step, enqueued on s->stream and its auxiliary streams (fork / join through events)
-static int launch_buckets(Shard *s, BucketKernelFn pick, const void *ctx, void *dev_struct)
+int shard_enqueue_buckets(Shard *s, BucketKernelFn pick, const void *ctx, void *dev_struct)
 {
     TMVB_CUDA(cudaMemsetAsync(s->d_counters, 0, kMaxBuckets * 4, s->stream));
     const int ns = (s->buckets.size() > 1) ? s->n_streams : 1;
@@ -506,9 +506,8 @@ void shard_drop_graphs(Shard *s)
 // therefore captured once per distinct (kernel set, by-value parameter block) into a CUDA graph and replayed with a
 // single cudaGraphLaunch; the by-value struct changes only with beta's double-buffer parity, want_elbo and the
 // train! keywords, so a handful of graphs serves a whole training run.  TMVB_GRAPH=0 disables the capture.
-int shard_launch(Shard *s, BucketKernelFn pick, const void *ctx, void *dev_struct, size_t dev_struct_bytes)
+int shard_launch_key(Shard *s, BucketKernelFn pick, const void *ctx, const void *dev_struct, size_t dev_struct_bytes, std::string *key_out)
 {
-    if (s->buckets.empty()) return 0;
     std::string key((const char *)dev_struct, dev_struct_bytes);
     for (Bucket &b : s->buckets) {
         const void *fn = pick(b, ctx);
@@ -523,8 +522,17 @@ int shard_launch(Shard *s, BucketKernelFn pick, const void *ctx, void *dev_struc
         const long long geo[8] = {(long long)(size_t)fn, b.doc_begin, b.doc_end, b.cap, b.cap2, b.grid, (long long)b.smem, b.warps + 64 * b.nr + 4096 * b.hyb};
         key.append((const char *)geo, sizeof(geo));
     }
+    *key_out = key;
+    return 0;
+}
+
+int shard_launch(Shard *s, BucketKernelFn pick, const void *ctx, void *dev_struct, size_t dev_struct_bytes)
+{
+    if (s->buckets.empty()) return 0;
+    std::string key;
+    TMVB_TRY(shard_launch_key(s, pick, ctx, dev_struct, dev_struct_bytes, &key));
     s->st.kernel_launches += (int64_t)s->buckets.size();
-    if (!s->use_graphs) return launch_buckets(s, pick, ctx, dev_struct);
+    if (!s->use_graphs) return shard_enqueue_buckets(s, pick, ctx, dev_struct);
 
     for (auto &g : s->graphs)
         if (g.key == key) {
@@ -534,13 +542,13 @@ int shard_launch(Shard *s, BucketKernelFn pick, const void *ctx, void *dev_struc
     if (s->graphs.size() >= 16) shard_drop_graphs(s);
     cudaGraph_t graph = nullptr;
     TMVB_CUDA(cudaStreamBeginCapture(s->stream, cudaStreamCaptureModeThreadLocal));
-    const int rc = launch_buckets(s, pick, ctx, dev_struct);
+    const int rc = shard_enqueue_buckets(s, pick, ctx, dev_struct);
     const cudaError_t e = cudaStreamEndCapture(s->stream, &graph);
     if (rc != 0 || e != cudaSuccess || !graph) {
         if (graph) cudaGraphDestroy(graph);
         cudaGetLastError();
         s->use_graphs = false;  // capture is not possible here (e.g. the caller's stream is already capturing): launch directly
-        return launch_buckets(s, pick, ctx, dev_struct);
+        return shard_enqueue_buckets(s, pick, ctx, dev_struct);
     }
     Shard::LaunchGraph lg;
     lg.key = key;
@@ -549,7 +557,7 @@ int shard_launch(Shard *s, BucketKernelFn pick, const void *ctx, void *dev_struc
     if (ei != cudaSuccess) {
         cudaGetLastError();
         s->use_graphs = false;
-        return launch_buckets(s, pick, ctx, dev_struct);
+        return shard_enqueue_buckets(s, pick, ctx, dev_struct);
     }
     s->graphs.push_back(lg);
     TMVB_CUDA(cudaGraphLaunch(lg.exec, s->stream));

@@ -84,6 +84,10 @@ int shard_validation(Shard *s, int *mask);
 // instantiation for the bucket's (warps, nr)
 typedef const void *(*BucketKernelFn)(const Bucket &b, const void *ctx);
 int shard_launch(Shard *s, BucketKernelFn pick, const void *ctx, void *dev_struct, size_t dev_struct_bytes);
+// the pieces of shard_launch for callers that capture a longer sequence themselves (tmvb_lda_iterate): grids + cache key of the
+// launch set, and the bare enqueue of the bucket launches on s->stream and its auxiliary streams (fork / join through events)
+int shard_launch_key(Shard *s, BucketKernelFn pick, const void *ctx, const void *dev_struct, size_t dev_struct_bytes, std::string *key_out);
+int shard_enqueue_buckets(Shard *s, BucketKernelFn pick, const void *ctx, void *dev_struct);
 void shard_drop_graphs(Shard *s);
 // pick for kernels that only come in "warps per document" flavours: ctx = const void *const fn_by_warps[]
 const void *pick_by_warps(const Bucket &b, const void *ctx);

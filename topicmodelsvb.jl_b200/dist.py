@@ -86,6 +86,10 @@ class Reducer:
                 ok = False
         return self.all_agree(ok)
 
+    def barrier(self) -> None:
+        """All ranks have reached this point (host side)."""
+        self.all_agree(True)
+
     def allreduce_host(self, x: float) -> float:
         t = self.torch.tensor([x], dtype=self.torch.float64)
         if self.dist.get_backend(self.group) == "nccl":

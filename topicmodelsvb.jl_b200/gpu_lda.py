@@ -240,6 +240,20 @@ class gpuLDA:
         # asynchronous: the Newton iteration runs in an fp64 device kernel; model.alpha is refreshed by update_host!
         _lib.check(_lib.load().tmvb_lda_update_alpha(self._handle(), self.M_total, int(niter), float(ntol), None))
 
+    def can_iterate(self) -> bool:
+        """The fused outer iteration (tmvb_lda_iterate) applies on one GPU and with mapped peers; a run that sums the statistics
+        through torch.distributed (NCCL / gloo fallback) keeps the separate steps."""
+        self._handle()
+        return os.environ.get("TMVB_UNFUSED") != "1" and (self.reducer is None or self.reducer.world == 1 or getattr(self, "_p2p", False))
+
+    def iterate(self, viter: int, vtol: float, niter: int, ntol: float, want_elbo: bool = True):
+        """One pass of the `for k in 1:iter` body of train! (gpuLDA.jl:355-371) as one CUDA graph launch: E-step, update_beta!,
+        update_alpha! and -- with want_elbo -- the ELBO check_elbo! reads (returned; model.elbo is NOT touched here)."""
+        e = C.c_double()
+        _lib.check(_lib.load().tmvb_lda_iterate(self._handle(), int(viter), float(vtol), int(bool(want_elbo)), self.M_total, int(niter),
+                                                float(ntol), C.byref(e)))
+        return e.value if want_elbo else None
+
     def update_elbo(self, mode: int = 0) -> float:
         """update_elbo!(model) (gpuLDA.jl:121-128) from device-side partials; no phi transfer."""
         docs, glob = C.c_double(), C.c_double()
@@ -329,12 +343,25 @@ def train(model: gpuLDA, iter: int = 150, tol: float = 1.0, niter: int = 1000, n
         if trace is not None:
             trace.append(model.elbo)
 
+    fused = iter > 0 and model.can_iterate()
+    if model.reducer is not None and model.reducer.world > 1 and iter > 0:
+        model.reducer.barrier()    # every rank has uploaded before the first exchange (the device barriers only wait so long)
     for k in range(1, iter + 1):
         want = check and (k % checkelbo == 0)
-        model.estep(viter, vtol, want_elbo=want)               # gpuLDA.jl:356-364, per-document stopping (LDA.jl:171-178)
-        model.update_beta()                                    # gpuLDA.jl:365
-        model.update_alpha(niter, ntol)                        # gpuLDA.jl:366
-        stop = check_elbo(model, checkelbo, printelbo, k, tol)  # gpuLDA.jl:368
+        if fused:
+            # gpuLDA.jl:356-368 as one graph launch; check_elbo! (modelutils.jl:574-585) on the value it returns
+            new_elbo = model.iterate(viter, vtol, niter, ntol, want_elbo=want)
+            stop = False
+            if want:
+                delta, model.elbo = new_elbo - model.elbo, new_elbo
+                if printelbo:
+                    print("%d ∆elbo: %.3f" % (k, delta))
+                stop = delta < tol
+        else:
+            model.estep(viter, vtol, want_elbo=want)               # gpuLDA.jl:356-364, per-document stopping (LDA.jl:171-178)
+            model.update_beta()                                    # gpuLDA.jl:365
+            model.update_alpha(niter, ntol)                        # gpuLDA.jl:366
+            stop = check_elbo(model, checkelbo, printelbo, k, tol)  # gpuLDA.jl:368
         if want and trace is not None:
             trace.append(model.elbo)
         if stop:
