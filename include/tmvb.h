@@ -82,6 +82,10 @@ int tmvb_lda_set_alpha(tmvb_lda_t h, const float *alpha);
  * want_elbo != 0 also accumulates the per-document ELBO terms.  Asynchronous. */
 int tmvb_lda_estep(tmvb_lda_t h, int viter, float vtol, int want_elbo);
 
+/* The inner loop of predict(corp, train_model::gpuLDA) (modelutils.jl:846-855): update_phi!/update_gamma!/update_Elogtheta! per
+ * document with the uploaded alpha / beta frozen; unlike tmvb_lda_estep no statistics are scattered and no ELBO partials are kept. */
+int tmvb_lda_predict(tmvb_lda_t h, int viter, float vtol);
+
 /* Device buffers that a multi-GPU driver must sum over ranks between estep and mstep:
  * stats = float[n_stats] (K_ld x V padded statistics), small = double[n_small]
  * (sum_d Elogtheta_d, ELBO partials, sweep counter). */
@@ -187,6 +191,10 @@ int tmvb_ctm_upload(tmvb_ctm_t h, const float *mu, const float *sigma, const flo
  * CPU model's order and per-document stopping rule (CTM.jl:194-203), the scatter half of update_beta! (gpuCTM.jl:208-229)
  * and the second moments update_sigma!/update_mu! need (gpuCTM.jl:144-196).  Asynchronous. */
 int tmvb_ctm_estep(tmvb_ctm_t h, int niter, float ntol, int viter, float vtol, int want_elbo);
+
+/* The inner loop of predict(corp, train_model::gpuCTM) (modelutils.jl:903-913): phi / logzeta / vsq / lambda per document with
+ * mu, sigma, beta frozen; no statistics are scattered. */
+int tmvb_ctm_predict(tmvb_ctm_t h, int niter, float ntol, int viter, float vtol);
 
 /* buffers a multi-GPU driver sums over ranks between estep and mstep (stats float, small double) */
 int tmvb_ctm_reduce_buffers(tmvb_ctm_t h, void **stats, int64_t *n_stats, void **small, int64_t *n_small);

@@ -20,10 +20,12 @@ def _run_pair(tm, orc, c, K, iters, seed=7, nthreads=1):
     return model, np.array(trace), st, ref, sweeps
 
 
-@pytest.mark.parametrize("K", [6, 1, 3, 8, 17, 30, 33, 64])
+@pytest.mark.parametrize("K", [6, 1, 3, 8, 17, 30, 33, 64, 65, 100, 128])
 def test_ctm_elbo_trajectory_small(tm, orc, K):
+    """K <= 64: invsigma and the Cholesky factor in shared memory, two rows of the factor per lane; 65 <= K <= 128: invsigma read
+    from global memory, up to four rows per lane (gpuCTM.jl:258-337 has no bound on K; ours is the factor's shared-memory footprint)."""
     c = tm.synth.gencorp_lda(M=80, V=400, K=5, seed=1)
-    model, trace, st, ref, _ = _run_pair(tm, orc, c, K, iters=5)
+    model, trace, st, ref, _ = _run_pair(tm, orc, c, K, iters=5 if K <= 64 else 3)
     assert len(trace) == len(ref) >= 2
     np.testing.assert_allclose(trace, ref, rtol=ELBO_RTOL)
     np.testing.assert_allclose(model.mu, st.mu, rtol=2e-3, atol=2e-4)
@@ -85,8 +87,8 @@ def test_ctm_argument_errors(tm):
     m.vsq[0, 0] = -1.0
     with pytest.raises(tm.TopicModelError, match="vsq must be positive"):
         tm.train(m, iter=1, printelbo=False)
-    with pytest.raises(ValueError):
-        tm.train(tm.gpuCTM(tm.Corpus.from_csr(c), 65), iter=1, printelbo=False)   # K <= 64 in this build
+    with pytest.raises(ValueError, match="K <= 128"):
+        tm.train(tm.gpuCTM(tm.Corpus.from_csr(c), 129), iter=1, printelbo=False)
 
 
 def test_ctm_citeulike_size_parity(tm, orc):

@@ -28,7 +28,12 @@ def test_predict_lda_matches_oracle_estep(tm, orc):
         tm.predict(tm.Corpus.from_csr(tm.synth.gencorp_lda(M=5, V=77, K=3, seed=0)), m)
 
 
-def test_predict_ctm_runs_and_is_finite(tm):
+def test_predict_ctm_matches_oracle_estep(tm):
+    """predict(corp, train_model::gpuCTM) (modelutils.jl:886-913) == the per-document loop of the CPU model (update_phi!,
+    update_logzeta!, update_vsq!, update_lambda!; CTM.jl:129-178) run by the NumPy twin of the oracle with the trained mu, sigma,
+    beta frozen."""
+    from oracle.numpy_twin import CTMTwin
+
     train = tm.synth.gencorp_lda(M=100, V=300, K=4, seed=1)
     new = tm.synth.gencorp_lda(M=30, V=300, K=4, seed=5)
     # CTM has no epsilon in phi (CTM.jl:177): a term unseen in training has beta = 0 for every topic and yields NaN in the
@@ -39,12 +44,40 @@ def test_predict_ctm_runs_and_is_finite(tm):
     doc = np.repeat(np.arange(new.M), np.diff(new.N_cumsum))[keep]
     off = np.concatenate([[0], np.cumsum(np.bincount(doc, minlength=new.M))]).astype(np.int64)
     new = tm.synth.CSR(new.M, new.V, off, new.terms[keep], new.counts[keep])
-    m = tm.gpuCTM(tm.Corpus.from_csr(train), 5, seed=3)
+    K = 5
+    m = tm.gpuCTM(tm.Corpus.from_csr(train), K, seed=3)
     tm.train(m, iter=3, tol=0.0, printelbo=False)
     p = tm.predict(tm.Corpus.from_csr(new), m)
-    assert p.lam.shape == (5, new.M) and np.all(np.isfinite(p.lam)) and np.all(p.vsq > 0)
+    assert p.lam.shape == (K, new.M) and np.all(np.isfinite(p.lam)) and np.all(p.vsq > 0)
     td = tm.topicdist(p, 3)
     assert abs(td.sum() - 1) < 1e-6
+    # the oracle's loop on the new documents with the device's globals
+    tw = CTMTwin(new.N_cumsum, new.terms, new.counts, K, new.V, np.asarray(m.beta, dtype=np.float64).T)
+    tw.mu = np.asarray(m.mu, dtype=np.float64)
+    tw.sigma = np.asarray(m.sigma, dtype=np.float64)
+    tw.invsigma = np.linalg.inv(tw.sigma)
+    tol = ntol = 1.0 / K**2
+    for d in range(new.M):
+        if new.N_cumsum[d + 1] == new.N_cumsum[d]:
+            continue
+        for _ in range(10):
+            tw.update_phi(d)
+            tw.update_logzeta(d)
+            tw.update_vsq(d, 1000, ntol)
+            tw.update_lambda(d, 1000, ntol)
+            if np.linalg.norm(tw.lam[d] - tw.lam_old[d]) < tol:
+                break
+    nz = np.diff(new.N_cumsum) > 0
+    np.testing.assert_allclose(p.lam.T[nz], tw.lam[nz], rtol=5e-3, atol=5e-3)
+    np.testing.assert_allclose(p.vsq.T[nz], tw.vsq[nz], rtol=5e-3, atol=1e-5)
+    np.testing.assert_allclose(p.logzeta[nz], tw.logzeta[nz], rtol=2e-3, atol=2e-3)
+    # predict scatters nothing: the statistics buffer of the predict handle is still zero
+    import ctypes as C
+    sp, sn = C.c_void_p(), C.c_int64()
+    tm._lib.check(tm._lib.load().tmvb_ctm_reduce_buffers(p._handle(), C.byref(sp), C.byref(sn), None, None))
+    import torch
+    stats = torch.as_tensor(tm.dist._DevBuf(sp.value, sn.value, "<f4"), device="cuda")
+    assert float(stats.abs().sum()) == 0.0
 
 
 _WORKER = r'''

@@ -89,6 +89,8 @@ SIGNATURES = {
     "tmvb_lda_upload": (C.c_int, [_vp, _vp, _vp, _vp, _vp]),
     "tmvb_lda_set_alpha": (C.c_int, [_vp, _vp]),
     "tmvb_lda_estep": (C.c_int, [_vp, C.c_int, C.c_float, C.c_int]),
+    "tmvb_lda_predict": (C.c_int, [_vp, C.c_int, C.c_float]),
+    "tmvb_ctm_predict": (C.c_int, [_vp, C.c_int, C.c_float, C.c_int, C.c_float]),
     "tmvb_lda_reduce_buffers": (C.c_int, [_vp, C.POINTER(_vp), C.POINTER(C.c_int64), C.POINTER(_vp), C.POINTER(C.c_int64)]),
     "tmvb_lda_mstep": (C.c_int, [_vp]),
     "tmvb_lda_comm_export": (C.c_int, [_vp, _vp, C.c_int64]),

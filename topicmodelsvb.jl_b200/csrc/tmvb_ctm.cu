@@ -49,13 +49,27 @@ static int ctm_kp(int K)
     return kp;
 }
 // shared memory beyond the tile: mbarrier | gs [S][RS] | e_s [RS] | invsigma [K][KP] | L [K][KP] | vec [K_ld] | dinv [K_ld]
-static size_t ctm_fixed_smem(int RS, int lpt, int K, int K_ld) { return 16 + (size_t)(32 / lpt) * RS * 4 + (size_t)RS * 4 + (size_t)2 * K * ctm_kp(K) * 4 + (size_t)2 * K_ld * 4; }
+// (K > 64: invsigma stays in global memory -- read-only, shared by every CTA, L1/L2 resident -- so that the factor alone, 66 KB at K = 128, fits)
+static size_t ctm_fixed_smem(int RS, int lpt, int K, int K_ld) { return 16 + (size_t)(32 / lpt) * RS * 4 + (size_t)RS * 4 + (size_t)(K <= 64 ? 2 : 1) * K * ctm_kp(K) * 4 + (size_t)2 * K_ld * 4; }
 
 __device__ __forceinline__ float warp_max(float v)
 {
 #pragma unroll
     for (int m = 16; m > 0; m >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, m));
     return v;
+}
+
+// entry j of a vector distributed over the warp as v[r] on lane l for j = l + 32 r
+template <int R>
+__device__ __forceinline__ float warp_entry(const float (&v)[R], int j)
+{
+    float out = 0.0f;
+#pragma unroll
+    for (int r = 0; r < R; r++) {
+        const float x = __shfl_sync(0xffffffffu, v[r], j & 31);
+        if ((j >> 5) == r) out = x;
+    }
+    return out;
 }
 
 // Cholesky A = L L' of the SPD matrix A = inv_s + diag(w) (lane l owns rows l + 32 r), left-looking by columns,
@@ -87,8 +101,7 @@ __device__ __forceinline__ void warp_cholesky(const float *inv_s, float *L_s, fl
                 acc[r] = a0 + a1;
             }
         }
-        float djj = __shfl_sync(0xffffffffu, acc[0], j & 31);
-        if (R > 1 && j >= 32) djj = __shfl_sync(0xffffffffu, acc[R > 1 ? 1 : 0], j & 31);
+        const float djj = warp_entry<R>(acc, j);
         const float di = rsqrtf(fmaxf(djj, 1e-30f));
         __syncwarp();  // every lane has finished reading row j before column j is written into it
 #pragma unroll
@@ -106,8 +119,7 @@ template <int R>
 __device__ __forceinline__ void warp_chol_solve(const float *L_s, const float *dinv_s, float (&b)[R], int K, int KP, int lane)
 {
     for (int j = 0; j < K; j++) {
-        float bj = __shfl_sync(0xffffffffu, b[0], j & 31);
-        if (R > 1 && j >= 32) bj = __shfl_sync(0xffffffffu, b[R > 1 ? 1 : 0], j & 31);
+        const float bj = warp_entry<R>(b, j);
         const float yj = bj * dinv_s[j];
 #pragma unroll
         for (int r = 0; r < R; r++) {
@@ -117,8 +129,7 @@ __device__ __forceinline__ void warp_chol_solve(const float *L_s, const float *d
         }
     }
     for (int j = K - 1; j >= 0; j--) {
-        float bj = __shfl_sync(0xffffffffu, b[0], j & 31);
-        if (R > 1 && j >= 32) bj = __shfl_sync(0xffffffffu, b[R > 1 ? 1 : 0], j & 31);
+        const float bj = warp_entry<R>(b, j);
         const float xj = bj * dinv_s[j];
 #pragma unroll
         for (int r = 0; r < R; r++) {
@@ -134,7 +145,7 @@ __global__ void __launch_bounds__(32) ctm_estep_kernel(const CtmDev p, int doc_b
 {
     constexpr int S = 32 / LPT;
     constexpr int R = (LPT * CPL + 7) / 8;
-    static_assert(R <= 2, "CTM supports K <= 64");
+    static_assert(R <= 4, "CTM supports K <= 128 (the Cholesky factor lives in shared memory)");
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x;
     const int kl = lane % LPT, ts = lane / LPT;
@@ -145,15 +156,18 @@ __global__ void __launch_bounds__(32) ctm_estep_kernel(const CtmDev p, int doc_b
     unsigned long long *mbar = reinterpret_cast<unsigned long long *>(smem_raw);
     float *gs = reinterpret_cast<float *>(smem_raw + 16);  // [S][RS]
     float *e_s = gs + (size_t)S * RS;                      // [RS]
-    float *inv_s = e_s + RS;                               // [K][KP]
-    float *L_s = inv_s + K * KP;                           // [K][KP]
+    const bool inv_in_smem = K <= 64;
+    float *inv_own = e_s + RS;                             // [K][KP] copy of invsigma (K <= 64)
+    float *L_s = inv_own + (inv_in_smem ? K * KP : 0);     // [K][KP]
+    const float *inv_s = inv_in_smem ? inv_own : p.invsigma;
     float *vec_s = L_s + K * KP;                           // [K_ld]
     float *dinv_s = vec_s + K_ld;                          // [K_ld]
     float *tile = dinv_s + K_ld;                           // [cap][RS]
     float *cnt_s = tile + (size_t)cap * RS;
     int *term_s = reinterpret_cast<int *>(cnt_s + cap);
 
-    for (int q = lane; q < K * KP; q += 32) inv_s[q] = p.invsigma[q];
+    if (inv_in_smem)
+        for (int q = lane; q < K * KP; q += 32) inv_own[q] = p.invsigma[q];
     float mu_k[R], isd_k[R];
 #pragma unroll
     for (int r = 0; r < R; r++) {
@@ -380,21 +394,25 @@ __global__ void __launch_bounds__(32) ctm_estep_kernel(const CtmDev p, int doc_b
 }
 
 // Second moments for update_sigma!/update_mu! (CTM.jl:102-111): mom = [sum lambda (K_ld) | sum vsq (K_ld) | sum lambda lambda' (K x K)]
+template <int NQ>   // pairs per thread: K*K <= 256 NQ
 __global__ void ctm_moments_kernel(const float *__restrict__ lambda, const float *__restrict__ vsq, long long M, int K, int K_ld, double *__restrict__ mom)
 {
     extern __shared__ float lam_s[];  // [chunk][K_ld]
     const int CHUNK = 32;
     const int npairs = K * K;
-    double acc[16];  // K*K <= 4096 pairs over 256 threads
+    double acc[NQ];
 #pragma unroll
-    for (int q = 0; q < 16; q++) acc[q] = 0.0;
+    for (int q = 0; q < NQ; q++) acc[q] = 0.0;
     double sl = 0.0, sv = 0.0;
     for (long long d0 = (long long)blockIdx.x * CHUNK; d0 < M; d0 += (long long)gridDim.x * CHUNK) {
         const int nd = (int)min((long long)CHUNK, M - d0);
         __syncthreads();
         for (int q = threadIdx.x; q < nd * K_ld; q += blockDim.x) lam_s[q] = lambda[d0 * K_ld + q];
         __syncthreads();
-        for (int q = 0, pr = threadIdx.x; q < 16 && pr < npairs; q++, pr += blockDim.x) {
+#pragma unroll
+        for (int q = 0; q < NQ; q++) {
+            const int pr = threadIdx.x + q * 256;
+            if (pr >= npairs) break;
             const int i = pr / K, j = pr - i * K;
             double a = 0.0;
             for (int dd = 0; dd < nd; dd++) a += (double)(lam_s[dd * K_ld + i] * lam_s[dd * K_ld + j]);
@@ -406,8 +424,11 @@ __global__ void ctm_moments_kernel(const float *__restrict__ lambda, const float
                 sv += (double)vsq[(d0 + dd) * K_ld + threadIdx.x];
             }
     }
-    for (int q = 0, pr = threadIdx.x; q < 16 && pr < npairs; q++, pr += blockDim.x)
-        if (acc[q] != 0.0) atomicAdd(mom + 2 * K_ld + pr, acc[q]);
+#pragma unroll
+    for (int q = 0; q < NQ; q++) {
+        const int pr = threadIdx.x + q * 256;
+        if (pr < npairs && acc[q] != 0.0) atomicAdd(mom + 2 * K_ld + pr, acc[q]);
+    }
     if (threadIdx.x < K) {
         atomicAdd(mom + threadIdx.x, sl);
         atomicAdd(mom + K_ld + threadIdx.x, sv);
@@ -485,8 +506,8 @@ __global__ void ctm_phi_kernel(const CtmDev p, const float *__restrict__ beta_ol
 }
 
 typedef void (*CtmEstepFn)(const CtmDev, int, int, int, int, int *);
-// layouts with R = ceil(LPT*CPL/8) <= 2, i.e. K <= 64; the others are not instantiated
-template <int L, int C, bool E, bool OK = ((L * C + 7) / 8 <= 2)>
+// layouts with R = ceil(LPT*CPL/8) <= 4, i.e. K <= 128; the others are not instantiated
+template <int L, int C, bool E, bool OK = ((L * C + 7) / 8 <= 4)>
 struct CtmPick {
     static CtmEstepFn get() { return (CtmEstepFn)ctm_estep_kernel<L, C, E>; }
 };
@@ -545,6 +566,7 @@ using namespace tmvb;
 struct tmvb_ctm_s {
     Shard s;
     int KP = 0;
+    bool no_scatter = false;   // predict: the E-step leaves the statistics alone
     bool elbo_valid = false;
     float *d_lambda = nullptr, *d_lambda_old = nullptr, *d_vsq = nullptr, *d_logzeta = nullptr;
     float *d_mu = nullptr, *d_invsigma = nullptr;
@@ -586,7 +608,7 @@ CtmDev ctm_view(tmvb_ctm_t h)
     p.viter = 0;
     p.vtol = 0.f;
     p.stage_bulk = env_int("TMVB_STAGE_BULK", 1);
-    p.dbg = env_int("TMVB_DBG", 0);
+    p.dbg = env_int("TMVB_DBG", 0) | (h->no_scatter ? 1 : 0);   // bit 0: the scatter pass computes but does not store (predict)
     return p;
 }
 
@@ -631,7 +653,7 @@ int tmvb_ctm_create(tmvb_ctm_t *out, int64_t K, int64_t M, int64_t V, int device
     TMVB_CHECK_ARG(out != nullptr, "handle pointer is NULL");
     *out = nullptr;
     TMVB_CHECK_ARG(K > 0, "number of topics must be a positive integer");  // gpuCTM.jl:55
-    if (K > 64) return fail(-2, "gpuCTM supports K <= 64 in this build (K=%lld)", (long long)K);
+    if (K > 128) return fail(-2, "gpuCTM supports K <= 128 (K=%lld): the K x K Cholesky factor of update_lambda! lives in shared memory", (long long)K);
     tmvb_ctm_t h = new tmvb_ctm_s();
     const int64_t K_ld = (K + 7) / 8 * 8;
     h->n_small = 2 + 2 * K_ld + K * K;
@@ -763,7 +785,10 @@ int tmvb_ctm_estep(tmvb_ctm_t h, int niter, float ntol, int viter, float vtol, i
     TMVB_TRY(shard_launch(&s, pick_by_warps, fns, &p, sizeof(p)));
     if (s.M > 0) {
         const int grid = (int)std::min<int64_t>((s.M + 31) / 32, (int64_t)s.n_sm * 4);
-        ctm_moments_kernel<<<grid, 256, 32 * s.K_ld * 4, s.stream>>>(h->d_lambda, h->d_vsq, s.M, (int)s.K, s.K_ld, h->d_small + 2);
+        if (s.K <= 64)
+            ctm_moments_kernel<16><<<grid, 256, 32 * s.K_ld * 4, s.stream>>>(h->d_lambda, h->d_vsq, s.M, (int)s.K, s.K_ld, h->d_small + 2);
+        else
+            ctm_moments_kernel<64><<<grid, 256, 32 * s.K_ld * 4, s.stream>>>(h->d_lambda, h->d_vsq, s.M, (int)s.K, s.K_ld, h->d_small + 2);
         TMVB_CUDA(cudaGetLastError());
         s.st.kernel_launches++;
     }
@@ -771,6 +796,16 @@ int tmvb_ctm_estep(tmvb_ctm_t h, int niter, float ntol, int viter, float vtol, i
     s.estep_timed = true;
     h->elbo_valid = (want_elbo != 0);
     return 0;
+}
+
+// the inner loop of predict (modelutils.jl:903-913): the E-step without update_beta!(model, d) -- no statistics are scattered
+int tmvb_ctm_predict(tmvb_ctm_t h, int niter, float ntol, int viter, float vtol)
+{
+    TMVB_CHECK_ARG(h != nullptr, "handle is NULL");
+    h->no_scatter = true;
+    const int rc = tmvb_ctm_estep(h, niter, ntol, viter, vtol, 0);
+    h->no_scatter = false;
+    return rc;
 }
 
 int tmvb_ctm_reduce_buffers(tmvb_ctm_t h, void **stats, int64_t *n_stats, void **small, int64_t *n_small)

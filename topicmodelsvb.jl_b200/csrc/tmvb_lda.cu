@@ -673,6 +673,7 @@ struct tmvb_lda_s {
     bool alpha_on_device = false, elbo_dev_valid = false;
     double *d_small = nullptr;          // [K_ld+2], summed over ranks
     double *d_local = nullptr;          // [K_ld] rowsum | [K_ld] elbo_w | [K_ld+1] scratch for the standalone ELBO
+    bool no_scatter = false;            // predict: the E-step leaves the statistics alone
     bool solo = true;                   // no other rank: nothing sums `small` between the E-step and update_alpha!
     std::vector<Shard::LaunchGraph> iter_graphs;   // captured outer iterations (tmvb_lda_iterate), keyed like the E-step graphs
     Comm comm;                          // peer-memory exchange (multi-GPU), see tmvb_comm.cuh
@@ -704,7 +705,7 @@ LdaDev dev_view(tmvb_lda_t h)
     p.viter = 0;
     p.vtol = 0.f;
     p.stage_bulk = env_int("TMVB_STAGE_BULK", 1);
-    p.dbg = env_int("TMVB_DBG", 0);
+    p.dbg = env_int("TMVB_DBG", 0) | (h->no_scatter ? 1 : 0);   // bit 0: the scatter pass computes but does not store (predict)
     return p;
 }
 
@@ -1004,6 +1005,16 @@ int tmvb_lda_estep(tmvb_lda_t h, int viter, float vtol, int want_elbo)
     s.estep_timed = true;
     h->elbo_valid = (want_elbo != 0);
     return 0;
+}
+
+// the inner loop of predict (modelutils.jl:846-855): the E-step without update_beta!(model, d) -- no statistics are scattered
+int tmvb_lda_predict(tmvb_lda_t h, int viter, float vtol)
+{
+    TMVB_CHECK_ARG(h != nullptr, "handle is NULL");
+    h->no_scatter = true;
+    const int rc = tmvb_lda_estep(h, viter, vtol, 0);
+    h->no_scatter = false;
+    return rc;
 }
 
 int tmvb_lda_reduce_buffers(tmvb_lda_t h, void **stats, int64_t *n_stats, void **small, int64_t *n_small)

@@ -6,6 +6,7 @@ from typing import Optional
 
 import numpy as np
 
+from . import _lib
 from .corpus import Corpus, CorpusError, check_corp
 from .gpu_ctm import check_model_ctm, gpuCTM
 from .gpu_lda import check_model as check_model_lda
@@ -33,7 +34,8 @@ def predict(corp: Corpus, train_model, iter: int = 10, tol: Optional[float] = No
         model.topics = train_model.topics
         if iter > 0 and corp.flat().nnz > 0:
             model.update_buffer()
-            model.estep(iter, tol, want_elbo=False)        # update_phi!/update_gamma!/update_Elogtheta! per document
+            # update_phi!/update_gamma!/update_Elogtheta! per document; nothing is scattered (there is no M-step to feed)
+            _lib.check(_lib.load().tmvb_lda_predict(model._handle(), int(iter), float(tol)))
             model.update_host()
         return model
     if isinstance(train_model, gpuCTM):
@@ -46,8 +48,7 @@ def predict(corp: Corpus, train_model, iter: int = 10, tol: Optional[float] = No
         model.topics = train_model.topics
         if iter > 0 and corp.flat().nnz > 0:
             model.update_buffer()
-            model.estep(niter, ntol, iter, tol, want_elbo=False)
-            mu, sigma, invsigma = model.mu, model.sigma, model.invsigma
+            _lib.check(_lib.load().tmvb_ctm_predict(model._handle(), int(niter), float(ntol), int(iter), float(tol)))
             model.update_host()
         return model
     raise TypeError("predict: unsupported model type %r" % type(train_model).__name__)
