@@ -49,8 +49,9 @@ static int ctm_kp(int K)
     return kp;
 }
 // shared memory beyond the tile: mbarrier | gs [S][RS] | e_s [RS] | invsigma [K][KP] | L [K][KP] | vec [K_ld] | dinv [K_ld]
-// (K > 64: invsigma stays in global memory -- read-only, shared by every CTA, L1/L2 resident -- so that the factor alone, 66 KB at K = 128, fits)
-static size_t ctm_fixed_smem(int RS, int lpt, int K, int K_ld) { return 16 + (size_t)(32 / lpt) * RS * 4 + (size_t)RS * 4 + (size_t)(K <= 64 ? 2 : 1) * K * ctm_kp(K) * 4 + (size_t)2 * K_ld * 4; }
+// (invsigma stays in global memory -- read-only, shared by every CTA, L1/L2 resident: the kernel is bound by the latency of the
+// in-warp Cholesky chains, so what counts is how many documents an SM holds, i.e. shared memory per warp)
+static size_t ctm_fixed_smem(int RS, int lpt, int K, int K_ld) { return 16 + (size_t)(32 / lpt) * RS * 4 + (size_t)RS * 4 + (size_t)K * ctm_kp(K) * 4 + (size_t)2 * K_ld * 4; }
 
 __device__ __forceinline__ float warp_max(float v)
 {
@@ -140,8 +141,11 @@ __device__ __forceinline__ void warp_chol_solve(const float *L_s, const float *d
     }
 }
 
+#ifndef TMVB_CTM_MIN_CTAS
+#define TMVB_CTM_MIN_CTAS 16   // 128 registers per thread
+#endif
 template <int LPT, int CPL, bool ELBO>
-__global__ void __launch_bounds__(32) ctm_estep_kernel(const CtmDev p, int doc_begin, int doc_end, int cap, int cap2, int *counter)
+__global__ void __launch_bounds__(32, TMVB_CTM_MIN_CTAS) ctm_estep_kernel(const CtmDev p, int doc_begin, int doc_end, int cap, int cap2, int *counter)
 {
     constexpr int S = 32 / LPT;
     constexpr int R = (LPT * CPL + 7) / 8;
@@ -156,18 +160,14 @@ __global__ void __launch_bounds__(32) ctm_estep_kernel(const CtmDev p, int doc_b
     unsigned long long *mbar = reinterpret_cast<unsigned long long *>(smem_raw);
     float *gs = reinterpret_cast<float *>(smem_raw + 16);  // [S][RS]
     float *e_s = gs + (size_t)S * RS;                      // [RS]
-    const bool inv_in_smem = K <= 64;
-    float *inv_own = e_s + RS;                             // [K][KP] copy of invsigma (K <= 64)
-    float *L_s = inv_own + (inv_in_smem ? K * KP : 0);     // [K][KP]
-    const float *inv_s = inv_in_smem ? inv_own : p.invsigma;
+    float *L_s = e_s + RS;                                 // [K][KP]
+    const float *inv_s = p.invsigma;                       // global: L1-resident, shared by all CTAs
     float *vec_s = L_s + K * KP;                           // [K_ld]
     float *dinv_s = vec_s + K_ld;                          // [K_ld]
     float *tile = dinv_s + K_ld;                           // [cap][RS]
     float *cnt_s = tile + (size_t)cap * RS;
     int *term_s = reinterpret_cast<int *>(cnt_s + cap);
 
-    if (inv_in_smem)
-        for (int q = lane; q < K * KP; q += 32) inv_own[q] = p.invsigma[q];
     float mu_k[R], isd_k[R];
 #pragma unroll
     for (int r = 0; r < R; r++) {
@@ -712,6 +712,9 @@ int tmvb_ctm_destroy(tmvb_ctm_t h)
 int tmvb_ctm_set_corpus(tmvb_ctm_t h, const int64_t *N_cumsum, const int64_t *terms, const int64_t *counts)
 {
     TMVB_CHECK_ARG(h != nullptr, "handle is NULL");
+    // a small tile: the E-step is bound by the latency of the per-document Newton / Cholesky chains, not by the token passes, so
+    // resident documents per SM beat shared-memory reads of the rows (CiteULike K=30: 6.5 ms with full tiles, 4.0 ms with 16 tokens)
+    h->s.tile_cap_max = 16;
     return shard_set_corpus(&h->s, N_cumsum, terms, counts, ctm_fixed_smem(h->s.RS, h->s.lpt, (int)h->s.K, h->s.K_ld));
 }
 

@@ -692,6 +692,9 @@ int tmvb_ctpf_set_corpus(tmvb_ctpf_t h, const int64_t *N_cumsum, const int64_t *
     Shard &s = h->s;
     const size_t per_tok = (size_t)s.RS * 4 + 8;
     const int cap2_max = 64;
+    // at most 64 term rows staged per document: more resident documents per SM beat shared-memory reads of the remaining
+    // rows (CiteULike K=30: 0.70 ms with full tiles, 0.52 ms with 64-token tiles; 16-token tiles 0.68 ms)
+    s.tile_cap_max = 64;
     TMVB_TRY(shard_set_corpus(&s, N_cumsum, terms, counts, ctpf_fixed_smem(s.RS, s.lpt) + cap2_max * per_tok));
     TMVB_TRY(shard_pack_aux(&s, R_cumsum, readers, ratings, h->U, &h->d_r_off, &h->d_readers, &h->d_ratings, &h->nnz_r, &h->r_len));
     // size the reader tile of each launch for (about) the 90th percentile of its documents' reader counts;

@@ -301,6 +301,9 @@ static int plan_buckets(Shard *s, size_t fixed_bytes)
     if (fixed_bytes + 16 * per_tok > s->smem_optin) return fail(-4, "internal: E-step working set does not fit in shared memory");
     int cap_max = 16;
     while (fixed_bytes + (size_t)(cap_max + 16) * per_tok <= s->smem_optin) cap_max += 16;
+    // developer knob: a smaller tile trades shared-memory reads for L2 reads of the overflow rows and raises the occupancy
+    if (s->tile_cap_max > 0) cap_max = std::min(cap_max, s->tile_cap_max);
+    cap_max = std::max(16, std::min(cap_max, env_int("TMVB_TILE_CAP_MAX", cap_max)));
     std::vector<int> caps;
     for (int c = 16; c < cap_max; c = (c < 128) ? c + 16 : (c < 256 ? c + 32 : c + c / 4 / 16 * 16)) caps.push_back(c);
     caps.push_back(cap_max);

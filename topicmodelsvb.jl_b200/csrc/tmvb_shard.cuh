@@ -40,6 +40,7 @@ struct Shard {
     float *d_doc_c = nullptr;   // [M] sum of a document's counts (C_d of the reference's structs, gpuLDA.jl:52), internal order
     std::vector<int> h_perm, len_sorted;
     std::vector<Bucket> buckets;
+    int tile_cap_max = 0;   // > 0: largest shared-memory tile (tokens) a launch bucket may stage; longer documents read the rest from L2
     // captured launch sequences of one E-step (see shard_launch), keyed by kernel set + by-value parameter block
     struct LaunchGraph {
         std::string key;
