@@ -264,6 +264,8 @@ def measure(tm, torch, args, name, rank, local, world, reducer, work_stream, pea
     for s in range(total):
         if s % cycle == 0:
             arm.reinit_device()
+            if world > 1:
+                barrier()   # the re-initialisation is outside the timed region on EVERY rank: nobody's next step waits for a peer's upload
         if s == warmup:
             barrier()
             launches0 = model.stats().kernel_launches

@@ -10,9 +10,10 @@ world = int(os.environ.get("WORLD", 8))
 c = (tm.synth.load_packed("nsf") or tm.synth.nsf_shaped()).shard(0, world)
 model = tm.gpuLDA(tm.Corpus.from_csr(c), K, seed=7)
 model.update_buffer()
-for it in range(int(os.environ.get("ITERS", 4))):
-    model.estep(10, 1.0 / K**2, want_elbo=True)
-    model.update_beta()
-    model.update_alpha(1000, 1.0 / K**2)
+out = []
+for it in range(int(os.environ.get("ITERS", 6))):
+    model.iterate(10, 1.0 / K**2, 1000, 1.0 / K**2, want_elbo=True)
     st = model.stats()
-    print(it, "docs", c.M, "estep_ms %.3f mstep_ms %.3f sweeps/doc %.2f" % (st.estep_ms, st.mstep_ms, st.sweeps / c.M), flush=True)
+    out.append(st.estep_ms)
+print("WORLD", world, "streams", os.environ.get("TMVB_STREAMS", "4"), "classes", os.environ.get("TMVB_HYB_CLASSES", "default"), "docs", c.M,
+      "estep_ms", " ".join("%.3f" % x for x in out), flush=True)

@@ -457,8 +457,12 @@ __global__ void __launch_bounds__(256) lda_exchange_mstep_kernel(const LdaXchg x
         // ---- the update_alpha! CTA: observer of phase A, then the reduction of `small` and the Newton iteration
         wait_flags(me, x.rank, x.world, epoch + 1, false, x.timeout_ns);
         for (int i = tid; i < x.n_small; i += blockDim.x) {
+            double v[kMaxPeers];
+#pragma unroll
+            for (int pr = 0; pr < kMaxPeers; pr++) v[pr] = pr < x.world ? __ldcg(x.small[pr] + i) : 0.0;
             double a = 0.0;
-            for (int pr = 0; pr < x.world; pr++) a += __ldcg(x.small[pr] + i);
+#pragma unroll
+            for (int pr = 0; pr < kMaxPeers; pr++) a += v[pr];
             x.small_red[i] = a;
         }
         __syncthreads();
@@ -486,13 +490,19 @@ __global__ void __launch_bounds__(256) lda_exchange_mstep_kernel(const LdaXchg x
     if (active) {
         for (int r = r0 + blockIdx.x * RPP + rl; r < r1; r += G * RPP) {
             const size_t q = (size_t)r * K_ld + 4 * c;
+            // all peer loads in flight at once (a remote load costs ~2 us: eight dependent ones would be most of the kernel), then
+            // the sum in fixed rank order
+            float4 v[kMaxPeers];
+#pragma unroll
+            for (int pr = 0; pr < kMaxPeers; pr++)
+                v[pr] = pr < x.world ? __ldcg(reinterpret_cast<const float4 *>(x.stats[pr] + q)) : make_float4(0.f, 0.f, 0.f, 0.f);
             float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-            for (int pr = 0; pr < x.world; pr++) {
-                const float4 v = __ldcg(reinterpret_cast<const float4 *>(x.stats[pr] + q));
-                acc.x += v.x;
-                acc.y += v.y;
-                acc.z += v.z;
-                acc.w += v.w;
+#pragma unroll
+            for (int pr = 0; pr < kMaxPeers; pr++) {
+                acc.x += v[pr].x;
+                acc.y += v[pr].y;
+                acc.z += v[pr].z;
+                acc.w += v[pr].w;
             }
             *reinterpret_cast<float4 *>(x.my_stats + q) = acc;
             cs0 += (double)acc.x;
@@ -535,8 +545,12 @@ __global__ void __launch_bounds__(256) lda_exchange_mstep_kernel(const LdaXchg x
 
     // ---- C: total column sums (fixed rank order), normalise + all-gather the rows, zero the local statistics
     if (tid < K_ld) {
+        double v[kMaxPeers];
+#pragma unroll
+        for (int pr = 0; pr < kMaxPeers; pr++) v[pr] = pr < x.world ? __ldcg(ctl_view(x.ctl[pr]).part + parity * kCtlPartLen + tid) : 0.0;
         double a = 0.0;
-        for (int pr = 0; pr < x.world; pr++) a += __ldcg(ctl_view(x.ctl[pr]).part + parity * kCtlPartLen + tid);
+#pragma unroll
+        for (int pr = 0; pr < kMaxPeers; pr++) a += v[pr];
         rs[tid] = a;
     }
     __syncthreads();

@@ -23,9 +23,9 @@ struct Shard {
     size_t smem_optin = 0;
     cudaStream_t stream = nullptr;
     bool own_stream = false;
-    static constexpr int kAux = 3;  // bucket launches are spread over stream + aux streams so their tails overlap
-    cudaStream_t aux[kAux] = {nullptr, nullptr, nullptr};
-    cudaEvent_t ev_fork = nullptr, ev_join[kAux] = {nullptr, nullptr, nullptr};
+    static constexpr int kAux = 11;  // bucket launches are spread over stream + aux streams so their tails overlap
+    cudaStream_t aux[kAux] = {};
+    cudaEvent_t ev_fork = nullptr, ev_join[kAux] = {};
     int n_streams = 1;
 
     int64_t K = 0, M = 0, V = 0, nnz = 0;
