@@ -251,6 +251,17 @@ int tmvb_ctpf_download(tmvb_ctpf_t h, float *alef, float *he, float *bet, float 
 int tmvb_ctpf_download_old(tmvb_ctpf_t h, float *alef_old, float *he_old, float *bet_old, float *vav_old, float *gimel_old, float *zayin_old,
                            float *dalet_old, float *het_old);
 int tmvb_ctpf_topics(tmvb_ctpf_t h, int32_t *topics); /* gpuCTPF.jl:706-707 */
+
+/* The recommendation step that ends train!(::gpuCTPF) (gpuCTPF.jl:709-731; CTPF.jl:378-400), from the device-resident state:
+ *   scores [M x U] Float32, column-major as Julia's model.scores: scores[d, u] = sum_i Eeta[i, u] (Etheta[i, d] + Eepsilon[i, d])
+ *   urecs  concatenated: urecs[uoff[u] .. uoff[u+1]) = 1-based documents NOT in user u's library, by descending score
+ *          (findall(.)[reverse(sortperm(.))] of gpuCTPF.jl:716-722, ties ordered like the reference's stable sort reversed)
+ *   drecs  concatenated: drecs[doff[d] .. doff[d+1]) = 1-based users who have NOT read document d (gpuCTPF.jl:724-729)
+ *   uoff [U + 1], doff [M + 1]; both rankings hold M * U - sum(R) entries in total.
+ * Every output may be NULL (a ranking and its offsets together).  The contraction runs on the tensor cores (tcgen05 kind::tf32
+ * with a hi/lo split of both operands: fp32-level accuracy); mode bit 0 selects the plain fp32 CUDA-core contraction instead
+ * (the checker the tests compare the tensor-core kernel with).  Single-GPU handles only (M = all documents). */
+int tmvb_ctpf_recs(tmvb_ctpf_t h, float *scores, int32_t *urecs, int64_t *uoff, int32_t *drecs, int64_t *doff, int mode);
 int tmvb_ctpf_get_stats(tmvb_ctpf_t h, tmvb_stats *out);
 
 #ifdef __cplusplus

@@ -256,3 +256,32 @@ def ctpf_train(st: CTPFState, c, iter=150, tol=1.0, viter=10, vtol=None, checkel
     if fin.size:
         st.elbo = float(fin[-1])
     return trace, sweeps[:iter], done.value
+
+
+def ctpf_recs(st: CTPFState, c, dtype=np.float64):
+    """The recommendation step that ends train!(model::CTPF) (CTPF.jl:381-400; gpuCTPF.jl:709-731 is the same with Float32
+    state): scores[d, :] = sum(Eeta .* (Etheta + Eepsilon), dims=1), urecs[u] = findall(ur)[reverse(sortperm(scores[ur, u]))],
+    drecs[d] = findall(nr)[reverse(sortperm(scores[d, nr]))].  Plain NumPy; returns (scores (M, U), urecs, drecs) with 1-based
+    rankings.  ``dtype`` is the arithmetic type of the scores (float64 = CTPF.jl, float32 = gpuCTPF.jl)."""
+    Eeta = (np.asarray(st.he, dtype) / np.asarray(st.vav, dtype)[None, :])                        # (U, K)   CTPF.jl:381
+    X = np.asarray(st.gimel, dtype) / np.asarray(st.dalet, dtype)[None, :] + np.asarray(st.zayin, dtype) / np.asarray(st.het, dtype)[None, :]
+    scores = np.zeros((st.M, st.U), dtype)
+    for d in range(st.M):                                                                         # CTPF.jl:382-386
+        scores[d, :] = (Eeta * X[d][None, :]).sum(axis=1)
+    Rc, readers = np.asarray(c.R_cumsum), np.asarray(c.readers)
+    libs = [[] for _ in range(st.U)]
+    for d in range(st.M):
+        for u in readers[Rc[d]:Rc[d + 1]]:
+            libs[u].append(d)
+    urecs, drecs = [], []
+    for u in range(st.U):                                                                         # CTPF.jl:388-393
+        ur = np.ones(st.M, bool)
+        ur[libs[u]] = False
+        idx = np.flatnonzero(ur)
+        urecs.append(idx[np.argsort(scores[idx, u], kind="stable")[::-1]] + 1)
+    for d in range(st.M):                                                                         # CTPF.jl:395-400
+        nr = np.ones(st.U, bool)
+        nr[readers[Rc[d]:Rc[d + 1]]] = False
+        idx = np.flatnonzero(nr)
+        drecs.append(idx[np.argsort(scores[d, idx], kind="stable")[::-1]] + 1)
+    return scores, urecs, drecs

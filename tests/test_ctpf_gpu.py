@@ -123,3 +123,110 @@ def test_ctpf_against_committed_golden(tm):
     tm.train(model, iter=len(g["elbo"]) - 1, tol=0.0, printelbo=False, trace=tr)
     np.testing.assert_allclose(tr, g["elbo"][: len(tr)], rtol=ELBO_RTOL)
     np.testing.assert_allclose(model.vav, g["vav"], rtol=2e-3)
+
+
+# ---- the recommendation step of train!(::gpuCTPF) (gpuCTPF.jl:709-731) on the device: tmvb_ctpf_recs ----------------------
+def _rank_from(scores_col, excluded0, n):
+    keep = np.ones(n, bool)
+    keep[excluded0] = False
+    idx = np.flatnonzero(keep)
+    return idx[np.argsort(scores_col[idx], kind="stable")[::-1]] + 1
+
+
+def _check_rankings_against(sc, ur, dr, c):
+    """bit-exact: the rankings are findall(.)[reverse(sortperm(.))] of the score matrix the device itself returned"""
+    Rc, readers = np.asarray(c.R_cumsum), np.asarray(c.readers)
+    libs = [[] for _ in range(c.U)]
+    for d in range(c.M):
+        for u in readers[Rc[d]:Rc[d + 1]]:
+            libs[u].append(d)
+    for u in range(c.U):
+        np.testing.assert_array_equal(ur[u], _rank_from(sc[:, u], libs[u], c.M))
+    for d in range(c.M):
+        np.testing.assert_array_equal(dr[d], _rank_from(sc[d, :], readers[Rc[d]:Rc[d + 1]], c.U))
+
+
+@pytest.mark.parametrize("M,U,K", [(60, 40, 4), (300, 130, 30), (129, 257, 33), (5, 3, 2), (700, 515, 100)])
+def test_ctpf_recs_small(tm, orc, M, U, K):
+    """scores: tensor-core contraction (tf32 hi/lo split) == CUDA-core fp32 contraction == fp64 oracle to fp32 rounding;
+    urecs / drecs: exactly the reference's ranking of the returned scores (ties included), and the oracle's ranking wherever
+    the oracle's scores are not tied to within fp32 rounding."""
+    c = tm.synth.gencorp_ctpf(M=M, V=200, U=U, K=3, seed=M + U)
+    model, trace, st, ref, _ = _run_pair(tm, orc, c, K, iters=2)
+    sc, ur, dr = model.update_recs()
+    sc1, ur1, dr1 = model.update_recs(mode=1)
+    assert sc.shape == (c.M, c.U) and sc.flags.f_contiguous
+    np.testing.assert_allclose(sc, sc1, rtol=1e-5, atol=0)     # K <= 100 positive terms: fp32 summation order only
+    st32 = orc.CTPFState(K, c.M, c.V, c.U, st.alef)
+    for n in ("he", "vav", "gimel", "zayin", "dalet", "het"):
+        setattr(st32, n, np.asarray(getattr(model, n), dtype=np.float64).T if getattr(model, n).ndim == 2 else np.asarray(getattr(model, n), np.float64))
+    so, uo, do = orc.ctpf_recs(st32, c)                     # fp64 loops over the device's own (downloaded) state
+    np.testing.assert_allclose(sc, so, rtol=1e-5)
+    np.testing.assert_allclose(sc1, so, rtol=1e-5)
+    print("scores vs fp64: tensor cores %.2e, CUDA cores %.2e (max rel)" % (np.max(np.abs(sc - so) / so), np.max(np.abs(sc1 - so) / so)))
+    _check_rankings_against(sc, ur, dr, c)
+    _check_rankings_against(sc1, ur1, dr1, c)
+    nz = c.M * c.U - len(c.readers)
+    assert sum(len(x) for x in ur) == nz == sum(len(x) for x in dr)
+    for u in range(c.U):                                    # against the oracle's rankings: swaps only between near-ties
+        bad = np.flatnonzero(ur[u] != uo[u])
+        if len(bad):
+            a, b = so[ur[u][bad] - 1, u], so[uo[u][bad] - 1, u]
+            np.testing.assert_allclose(a, b, rtol=1e-5)
+    # the model after the oracle's own training gives the same scores to the ELBO-level tolerance
+    s_ref, _, _ = orc.ctpf_recs(st, c)
+    np.testing.assert_allclose(sc, s_ref, rtol=2e-2, atol=1e-6)
+
+
+def test_ctpf_recs_ties_and_partial_outputs(tm):
+    """small-integer state: many exactly tied scores (exact in tf32 hi/lo and fp32), so the rankings must equal the
+    reference's reversed stable sort element for element; every output is optional."""
+    c = tm.synth.gencorp_ctpf(M=90, V=80, U=70, K=3, seed=5)
+    K = 6
+    m = tm.gpuCTPF(tm.Corpus.from_csr(c), K, seed=1)
+    rng = np.random.default_rng(0)
+    for n, cols in (("he", c.U), ("gimel", c.M), ("zayin", c.M)):
+        setattr(m, n, np.asfortranarray(rng.integers(1, 4, size=(K, cols)).astype(np.float32)))
+    for n in ("vav", "dalet", "het"):
+        setattr(m, n, rng.integers(1, 3, size=K).astype(np.float32))
+    want = m.scores()
+    sc, ur, dr = m.update_recs()
+    np.testing.assert_array_equal(sc, want)
+    _check_rankings_against(sc, ur, dr, c)
+    for u in range(c.U):
+        np.testing.assert_array_equal(ur[u], m.urecs[u])
+    for d in range(c.M):
+        np.testing.assert_array_equal(dr[d], m.drecs[d])
+    s2, u2, d2 = m.update_recs(scores=False, urecs=True, drecs=False)
+    assert s2 is None and d2 is None
+    for u in range(c.U):
+        np.testing.assert_array_equal(u2[u], ur[u])
+    s3, u3, d3 = m.update_recs(scores=False, urecs=False, drecs=True)
+    for d in range(c.M):
+        np.testing.assert_array_equal(d3[d], dr[d])
+
+
+def test_ctpf_recs_citeulike_size(tm):
+    """BASELINE config 3 shape (16 980 x 5 551, K = 30): tensor-core scores == CUDA-core scores, rankings of sampled
+    users / documents == the reference's loops over the returned scores; the end of train!(recs=True)."""
+    import time
+    c = tm.synth.load_packed("citeu") or tm.synth.citeu_shaped()
+    model = tm.gpuCTPF(tm.Corpus.from_csr(c), 30, seed=3)
+    tm.train(model, iter=2, tol=0.0, printelbo=False, recs=True)
+    t0 = time.perf_counter()
+    sc, ur, dr = model.update_recs()
+    t1 = time.perf_counter()
+    sc1, _, _ = model.update_recs(urecs=False, drecs=False, mode=1)
+    print("update_recs (scores + urecs + drecs, M=%d U=%d): %.1f ms" % (c.M, c.U, (t1 - t0) * 1e3))
+    np.testing.assert_allclose(sc, sc1, rtol=1e-5)
+    np.testing.assert_array_equal(sc, model.scores_)
+    Eeta = (model.he / model.vav[:, None]).astype(np.float64)
+    X = (model.gimel / model.dalet[:, None] + model.zayin / model.het[:, None]).astype(np.float64)
+    rng = np.random.default_rng(0)
+    Rc, readers = np.asarray(c.R_cumsum), np.asarray(c.readers)
+    for d in rng.choice(c.M, 40, replace=False):
+        np.testing.assert_allclose(sc[d, :], X[:, d] @ Eeta, rtol=1e-5)
+        np.testing.assert_array_equal(dr[d], _rank_from(sc[d, :], readers[Rc[d]:Rc[d + 1]], c.U))
+    for u in rng.choice(c.U, 40, replace=False):
+        np.testing.assert_array_equal(ur[u], _rank_from(sc[:, u], np.asarray(model.libs[u], dtype=np.int64) - 1, c.M))
+    assert sum(len(x) for x in ur) == c.M * c.U - len(readers) == sum(len(x) for x in dr)

@@ -132,6 +132,7 @@ SIGNATURES = {
     "tmvb_ctpf_download": (C.c_int, [_vp] * 9),
     "tmvb_ctpf_download_old": (C.c_int, [_vp] * 9),
     "tmvb_ctpf_topics": (C.c_int, [_vp, _vp]),
+    "tmvb_ctpf_recs": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, C.c_int]),
     "tmvb_ctpf_get_stats": (C.c_int, [_vp, C.POINTER(TmvbStats)]),
 }
 

@@ -19,6 +19,8 @@
 #include <stdlib.h>
 #include <string.h>
 
+#define TMVB_RECS_KERNELS
+#include "tmvb_recs.cuh"
 #include "tmvb_shard.cuh"
 
 namespace tmvb {
@@ -938,6 +940,150 @@ int tmvb_ctpf_topics(tmvb_ctpf_t h, int32_t *topics)
     TMVB_CHECK_ARG(h && topics, "NULL argument");
     TMVB_CUDA(cudaSetDevice(h->s.device));
     return shard_topics(&h->s, h->d_alef, nullptr, topics);
+}
+
+// exclusive prefix sums of (len - nmask[seg]) -- one thread: nseg is the number of users or documents
+__global__ void recs_offsets_kernel(const int *__restrict__ nmask, int nseg, int len, long long *__restrict__ off)
+{
+    long long a = 0;
+    for (int s = 0; s < nseg; s++) {
+        off[s] = a;
+        a += len - nmask[s];
+    }
+    off[nseg] = a;
+}
+__global__ void recs_nmask_d_kernel(const long long *__restrict__ r_off, const int *__restrict__ perm, long long M, int *__restrict__ nmask_d)
+{
+    for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < M; p += (long long)gridDim.x * blockDim.x)
+        nmask_d[perm[p]] = (int)(r_off[p + 1] - r_off[p]);
+}
+
+/* scores / urecs / drecs of train!(::gpuCTPF) (gpuCTPF.jl:709-731) on the device -- see tmvb_recs.cuh.  Every output is optional:
+ *   scores  [M x U] column-major Float32 (Julia's model.scores)
+ *   urecs   concatenated rankings, urecs[uoff[u] .. uoff[u+1]) = documents (1-based) not in user u's library, by descending score
+ *   drecs   concatenated rankings, drecs[doff[d] .. doff[d+1]) = users (1-based) who have not read document d, by descending score
+ *   uoff [U + 1], doff [M + 1]  (both rankings have M * U - sum(R) entries)
+ * mode bit 0: contraction on the CUDA cores in fp32 instead of the tensor cores (the checker of the tcgen05 kernel). */
+int tmvb_ctpf_recs(tmvb_ctpf_t h, float *scores, int32_t *urecs, int64_t *uoff, int32_t *drecs, int64_t *doff, int mode)
+{
+    TMVB_CHECK_ARG(h != nullptr, "handle is NULL");
+    Shard &s = h->s;
+    TMVB_CHECK_ARG(s.corpus_set && h->readers_set, "set_corpus has not been called");
+    TMVB_CHECK_ARG((urecs == nullptr) == (uoff == nullptr) && (drecs == nullptr) == (doff == nullptr), "a ranking needs its offsets array");
+    TMVB_CUDA(cudaSetDevice(s.device));
+    const int64_t M = s.M, U = h->U;
+    const int K = (int)s.K, KP = (K + kRecBK - 1) / kRecBK * kRecBK;
+    if (M == 0 || U == 0) {
+        if (uoff) memset(uoff, 0, (U + 1) * 8);
+        if (doff) memset(doff, 0, (M + 1) * 8);
+        return 0;
+    }
+    const int ld_d = (int)((U + 3) / 4 * 4), ld_u = (int)((M + 3) / 4 * 4);
+    const bool want_u = urecs != nullptr || scores != nullptr, want_d = drecs != nullptr;
+    float *X = nullptr, *Y = nullptr, *kv = nullptr, *keys_d = nullptr, *keys_u = nullptr;
+    int *nmask = nullptr, *out = nullptr;
+    long long *off = nullptr;
+    void *ws = nullptr;
+    size_t ws_bytes = 0;
+    int rc = 0;
+    auto cleanup = [&]() {
+        cudaStreamSynchronize(s.stream);
+        cudaFree(X);
+        cudaFree(Y);
+        cudaFree(kv);
+        cudaFree(keys_d);
+        cudaFree(keys_u);
+        cudaFree(nmask);
+        cudaFree(out);
+        cudaFree(off);
+        cudaFree(ws);
+    };
+#define RECS_CUDA(expr)                                                                                              \
+    do {                                                                                                             \
+        cudaError_t _e = (expr);                                                                                     \
+        if (_e != cudaSuccess) {                                                                                     \
+            cleanup();                                                                                               \
+            return fail((int)_e, "%s failed at %s:%d: %s", #expr, __FILE__, __LINE__, cudaGetErrorString(_e));      \
+        }                                                                                                            \
+    } while (0)
+    RECS_CUDA(cudaMalloc((void **)&X, (size_t)M * KP * 4));
+    RECS_CUDA(cudaMalloc((void **)&Y, (size_t)U * KP * 4));
+    RECS_CUDA(cudaMalloc((void **)&kv, (size_t)3 * K * 4));
+    RECS_CUDA(cudaMalloc((void **)&nmask, (size_t)(M + U) * 4));
+    RECS_CUDA(cudaMalloc((void **)&off, (size_t)(M + U + 2) * 8));
+    RECS_CUDA(cudaMalloc((void **)&out, (size_t)std::max<int64_t>(M * U - h->nnz_r, 1) * 4));
+    if (want_d) RECS_CUDA(cudaMalloc((void **)&keys_d, (size_t)M * ld_d * 4));
+    if (want_u) RECS_CUDA(cudaMalloc((void **)&keys_u, (size_t)U * ld_u * 4));
+    {   // Eeta = he ./ vav, Etheta = gimel ./ dalet, Eepsilon = zayin ./ het (gpuCTPF.jl:709-713) from the fp64 masters of the rates
+        std::vector<float> hv(3 * K);
+        for (int i = 0; i < K; i++) {
+            hv[i] = (float)(1.0 / h->dalet[i]);
+            hv[K + i] = (float)(1.0 / h->het[i]);
+            hv[2 * K + i] = (float)(1.0 / h->vav[i]);
+        }
+        RECS_CUDA(cudaMemcpyAsync(kv, hv.data(), hv.size() * 4, cudaMemcpyHostToDevice, s.stream));
+        RECS_CUDA(cudaStreamSynchronize(s.stream));
+        s.st.h2d_bytes += hv.size() * 4;
+    }
+    recs_theta_kernel<<<grid_for(M * KP, 256, s.n_sm), 256, 0, s.stream>>>(h->d_gimel, h->d_zayin, kv, kv + K, s.d_perm, M, K, s.K_ld, KP, X);
+    recs_eta_kernel<<<grid_for(U * KP, 256, s.n_sm), 256, 0, s.stream>>>(h->d_he, kv + 2 * K, U, K, s.K_ld, KP, Y);
+    RECS_CUDA(cudaGetLastError());
+    const size_t smem = (size_t)(2 * kRecBM + 2 * kRecBN) * 128;
+    RECS_CUDA(cudaFuncSetAttribute((const void *)recs_scores_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    auto contract = [&](const float *A, const float *B, float *Cm, int P, int Q, int ldc) {
+        if (mode & 1) {
+            recs_scores_ref_kernel<<<grid_for((long long)P * Q, 256, s.n_sm), 256, 0, s.stream>>>(A, B, Cm, P, Q, KP, ldc);
+        } else {
+            const int gx = (P + kRecBM - 1) / kRecBM, ntile = (Q + kRecBN - 1) / kRecBN;
+            const int gy = std::max(1, std::min(ntile, (2 * s.n_sm + gx - 1) / gx));
+            recs_scores_umma_kernel<<<dim3(gx, gy), 128, smem, s.stream>>>(A, B, Cm, P, Q, KP, ldc);
+        }
+        s.st.kernel_launches++;
+    };
+    if (want_d) contract(X, Y, keys_d, (int)M, (int)U, ld_d);
+    if (want_u) contract(Y, X, keys_u, (int)U, (int)M, ld_u);
+    RECS_CUDA(cudaGetLastError());
+    if (scores) {
+        RECS_CUDA(cudaMemcpy2DAsync(scores, (size_t)M * 4, keys_u, (size_t)ld_u * 4, (size_t)M * 4, (size_t)U, cudaMemcpyDeviceToHost, s.stream));
+        s.st.d2h_bytes += M * U * 4;
+    }
+    if (urecs || drecs) {
+        int *nmask_d = nmask, *nmask_u = nmask + M;
+        RECS_CUDA(cudaMemsetAsync(nmask, 0, (size_t)(M + U) * 4, s.stream));
+        recs_nmask_d_kernel<<<grid_for(M, 256, s.n_sm), 256, 0, s.stream>>>(h->d_r_off, s.d_perm, M, nmask_d);
+        recs_mask_kernel<<<grid_for(M * 32, 256, s.n_sm), 256, 0, s.stream>>>(h->d_r_off, h->d_readers, s.d_perm, M, drecs ? keys_d : nullptr, ld_d,
+                                                                          keys_u, ld_u, nmask_u);
+        RECS_CUDA(cudaGetLastError());
+        long long *off_d = off, *off_u = off + M + 1;
+        const int64_t total = M * U - h->nnz_r;
+        if (drecs) {
+            recs_offsets_kernel<<<1, 1, 0, s.stream>>>(nmask_d, (int)M, (int)U, off_d);
+            rc = segmented_rank(keys_d, (int)M, (int)U, ld_d, nmask_d, off_d, out, &ws, &ws_bytes, s.stream, s.n_sm);
+            if (rc) {
+                cleanup();
+                return rc;
+            }
+            RECS_CUDA(cudaMemcpyAsync(drecs, out, (size_t)total * 4, cudaMemcpyDeviceToHost, s.stream));
+            RECS_CUDA(cudaMemcpyAsync(doff, off_d, (size_t)(M + 1) * 8, cudaMemcpyDeviceToHost, s.stream));
+            RECS_CUDA(cudaStreamSynchronize(s.stream));
+            s.st.d2h_bytes += total * 4 + (M + 1) * 8;
+        }
+        if (urecs) {
+            recs_offsets_kernel<<<1, 1, 0, s.stream>>>(nmask_u, (int)U, (int)M, off_u);
+            rc = segmented_rank(keys_u, (int)U, (int)M, ld_u, nmask_u, off_u, out, &ws, &ws_bytes, s.stream, s.n_sm);
+            if (rc) {
+                cleanup();
+                return rc;
+            }
+            RECS_CUDA(cudaMemcpyAsync(urecs, out, (size_t)total * 4, cudaMemcpyDeviceToHost, s.stream));
+            RECS_CUDA(cudaMemcpyAsync(uoff, off_u, (size_t)(U + 1) * 8, cudaMemcpyDeviceToHost, s.stream));
+            s.st.d2h_bytes += total * 4 + (U + 1) * 8;
+        }
+        s.st.kernel_launches += 8;
+    }
+    cleanup();
+#undef RECS_CUDA
+    return 0;
 }
 
 int tmvb_ctpf_get_stats(tmvb_ctpf_t h, tmvb_stats *out)

@@ -4,6 +4,7 @@
 #include <cub/cub.cuh>
 
 #include "tmvb_common.cuh"
+#include "tmvb_recs.cuh"
 
 namespace tmvb {
 
@@ -61,6 +62,66 @@ int topics_argsort(const float *d_mat, const float *d_scale, int K, int ld, int 
     topics_reverse_kernel<<<grid, 256, 0, stream>>>(vout, K, V, d_out);
     TMVB_CUDA(cudaGetLastError());
     TMVB_CUDA(cudaStreamSynchronize(stream));  // h_offs staging
+    return 0;
+}
+
+// ---- complete rankings of the CTPF recommendation step (gpuCTPF.jl:716-729) -------------------------------------------
+__global__ void rank_iota_kernel(int *__restrict__ vals, int *__restrict__ seg_begin, int *__restrict__ seg_end, int nseg, int len, int ld)
+{
+    const long long n = (long long)nseg * ld;
+    for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < n; q += (long long)gridDim.x * blockDim.x) {
+        const int seg = (int)(q / ld), j = (int)(q - (long long)seg * ld);
+        vals[q] = j;
+        if (j == 0) {
+            seg_begin[seg] = seg * ld;
+            seg_end[seg] = seg * ld + len;
+        }
+    }
+}
+// out[off[seg] + r] = 1 + vals_sorted[seg][len - 1 - r], r < len - nmask[seg]: the reverse of the ascending stable order is
+// findall(.)[reverse(sortperm(.))] of the reference (1-based); the masked entries (key -inf) sorted first, i.e. come last here
+__global__ void rank_compact_kernel(const int *__restrict__ vals, const int *__restrict__ nmask, const long long *__restrict__ off, int nseg, int len,
+                                    int ld, int *__restrict__ out)
+{
+    for (int seg = blockIdx.x; seg < nseg; seg += gridDim.x) {
+        const int keep = len - nmask[seg];
+        const long long o = off[seg];
+        for (int r = threadIdx.x; r < keep; r += blockDim.x) out[o + r] = 1 + vals[(size_t)seg * ld + (len - 1 - r)];
+    }
+}
+
+// d_keys: [nseg][ld] scores (masked entries -inf), overwritten.  d_out: concatenated rankings at d_out_off[seg] (device).
+int segmented_rank(float *d_keys, int nseg, int len, int ld, const int *d_nmask, const long long *d_out_off, int *d_out, void **ws, size_t *ws_bytes,
+                   cudaStream_t stream, int n_sm)
+{
+    if (nseg == 0 || len == 0) return 0;
+    const size_t n = (size_t)nseg * ld;
+    if (n >= (1ull << 31)) return fail(-2, "recommendation matrix too large for the device ranking (M * U >= 2^31)");
+    size_t cub_bytes = 0;
+    float *kout = nullptr;
+    int *vin = nullptr, *vout = nullptr, *sb = nullptr, *se = nullptr;
+    TMVB_CUDA(cub::DeviceSegmentedSort::StableSortPairs(nullptr, cub_bytes, d_keys, kout, vin, vout, (int)n, nseg, sb, se, stream));
+    const size_t need = 3 * n * 4 + 2 * (size_t)nseg * 4 + 512 + cub_bytes;
+    if (need > *ws_bytes) {
+        if (*ws) TMVB_CUDA(cudaFree(*ws));
+        *ws = nullptr;
+        *ws_bytes = 0;
+        TMVB_CUDA(cudaMalloc(ws, need));
+        *ws_bytes = need;
+    }
+    char *base = (char *)*ws;
+    kout = (float *)base;
+    vin = (int *)(kout + n);
+    vout = vin + n;
+    sb = vout + n;
+    se = sb + nseg;
+    void *cub_ws = (void *)(((uintptr_t)(se + nseg) + 255) & ~(uintptr_t)255);
+    const int grid = (int)std::min<long long>((long long)(n + 255) / 256, (long long)n_sm * 16);
+    rank_iota_kernel<<<grid, 256, 0, stream>>>(vin, sb, se, nseg, len, ld);
+    TMVB_CUDA(cudaGetLastError());
+    TMVB_CUDA(cub::DeviceSegmentedSort::StableSortPairs(cub_ws, cub_bytes, d_keys, kout, vin, vout, (int)n, nseg, sb, se, stream));
+    rank_compact_kernel<<<std::min(nseg, n_sm * 16), 256, 0, stream>>>(vout, d_nmask, d_out_off, nseg, len, ld, d_out);
+    TMVB_CUDA(cudaGetLastError());
     return 0;
 }
 

@@ -206,6 +206,29 @@ class gpuCTPF:
                 return model._rank(col, model.libs[u], model.M)
         return _U()
 
+    def update_recs(self, scores: bool = True, urecs: bool = True, drecs: bool = True, mode: int = 0):
+        """The recommendation step that ends train!(::gpuCTPF) (gpuCTPF.jl:709-731) on the device (tmvb_ctpf_recs): the dense
+        M x U score matrix on the tensor cores and both complete rankings by segmented sorts.  Returns (scores, urecs, drecs):
+        scores an (M, U) float32 view (Fortran order: Julia's model.scores), urecs / drecs lists of 1-based int32 arrays
+        (views into one concatenated buffer each).  Outputs not asked for are None.  One GPU only: a sharded model has no
+        process that holds every document."""
+        if self.reducer is not None:
+            raise _lib.TopicModelError("update_recs needs the whole corpus on one GPU")
+        if not self._resident:
+            self.update_buffer()
+        M, U = self.M, self.U
+        total = M * U - (int(self.corp.flat().R_cumsum[-1]) if M else 0)
+        sc = np.empty((M, U), dtype=np.float32, order="F") if scores else None
+        ur = np.empty(max(total, 1), np.int32) if urecs else None
+        uo = np.zeros(U + 1, np.int64) if urecs else None
+        dr = np.empty(max(total, 1), np.int32) if drecs else None
+        do = np.zeros(M + 1, np.int64) if drecs else None
+        ptr = lambda a: None if a is None else a.ctypes.data  # noqa: E731
+        _lib.check(_lib.load().tmvb_ctpf_recs(self._handle(), ptr(sc), ptr(ur), ptr(uo), ptr(dr), ptr(do), int(mode)))
+        ul = [ur[uo[u]:uo[u + 1]] for u in range(U)] if urecs else None
+        dl = [dr[do[d]:do[d + 1]] for d in range(M)] if drecs else None
+        return sc, ul, dl
+
     def stats(self) -> _lib.TmvbStats:
         st = _lib.TmvbStats()
         _lib.check(_lib.load().tmvb_ctpf_get_stats(self._handle(), C.byref(st)))
@@ -266,10 +289,11 @@ def check_model_ctpf(model: gpuCTPF) -> None:
 
 
 def train_ctpf(model: gpuCTPF, iter: int = 150, tol: float = 1.0, viter: int = 10, vtol: Optional[float] = None, checkelbo=1,
-               printelbo: bool = True, trace: Optional[list] = None):
-    """train!(model::gpuCTPF; iter, tol, viter, vtol, checkelbo, printelbo) (gpuCTPF.jl:677-733) up to the topic ranking;
-    the dense score matrix / drecs / urecs (gpuCTPF.jl:709-731) are computed on demand (``model.scores()``, ``model.drecs[d]``,
-    ``model.urecs[u]``)."""
+               printelbo: bool = True, trace: Optional[list] = None, recs: bool = False):
+    """train!(model::gpuCTPF; iter, tol, viter, vtol, checkelbo, printelbo) (gpuCTPF.jl:677-733).  With ``recs=True`` the call
+    ends like the reference's: the dense score matrix and the complete drecs / urecs rankings (gpuCTPF.jl:709-731) are formed
+    on the device (``model.update_recs()``) and left in ``model.scores_``, ``model.urecs_``, ``model.drecs_``; by default
+    they are computed on demand, one row at a time (``model.scores()``, ``model.drecs[d]``, ``model.urecs[u]``)."""
     from .gpu_lda import check_elbo
 
     K = model.K
@@ -306,4 +330,6 @@ def train_ctpf(model: gpuCTPF, iter: int = 150, tol: float = 1.0, viter: int = 1
     if iter > 0:
         model.update_host()
     model.update_topics()
+    if recs:
+        model.scores_, model.urecs_, model.drecs_ = model.update_recs()
     return None
