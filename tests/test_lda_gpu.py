@@ -81,6 +81,29 @@ def test_fused_elbo_equals_standalone(tm, orc):
         assert abs(e1 - e2) <= 1e-6 * abs(e2), (it, e1, e2)
 
 
+@pytest.mark.parametrize("K", [3, 10, 50, 100, 200])
+def test_fresh_state_elbo_equals_literal(tm, monkeypatch, K):
+    """mode 1 right after update_buffer! (beta_old == beta, Elogtheta_old == Elogtheta on the device: the `update_elbo!` that opens
+    every train! call, gpuLDA.jl:353) takes the one-dot-product-per-token kernel; it must equal the table-assisted pass
+    (TMVB_ELBO_NOFRESH=1) and the literal fp64 restatement (mode 2) on the same re-uploaded state."""
+    c = tm.synth.gencorp_lda(M=250, V=600, K=6, seed=K)
+    model = tm.gpuLDA(tm.Corpus.from_csr(c), K, seed=3)
+    tm.train(model, iter=2, tol=0.0, printelbo=False)        # a non-trivial state on the host (Elogtheta, gamma, beta, alpha)
+    model.update_buffer()                                     # re-upload: the lagged copies now equal the current ones
+    e_fresh = model.update_elbo(1)
+    monkeypatch.setenv("TMVB_ELBO_NOFRESH", "1")
+    e_table = model.update_elbo(1)
+    monkeypatch.delenv("TMVB_ELBO_NOFRESH")
+    e_lit = model.update_elbo(2)
+    assert abs(e_fresh - e_lit) <= 1e-6 * abs(e_lit), (e_fresh, e_lit)
+    assert abs(e_table - e_lit) <= 1e-6 * abs(e_lit), (e_table, e_lit)
+    # after a step the copies differ again and mode 1 falls back to the table pass
+    model.estep(10, 1.0 / K**2, want_elbo=True)
+    model.update_beta()
+    model.update_alpha(1000, 1.0 / K**2)
+    assert abs(model.update_elbo(1) - model.update_elbo(2)) <= 1e-6 * abs(model.update_elbo(2))
+
+
 def test_fused_iteration_equals_separate_steps(tm, monkeypatch):
     """tmvb_lda_iterate (one CUDA graph launch per outer iteration: what train() uses) == estep + mstep + update_alpha + elbo."""
     c = tm.synth.gencorp_lda(M=300, V=700, K=6, seed=21)

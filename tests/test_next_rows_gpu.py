@@ -141,3 +141,78 @@ def test_two_gpu_exchange_matches_single_gpu(tm, orc, tmp_path, p2p):
     ref, _, _ = orc.lda_train(st, c.N_cumsum, c.terms, c.counts, iter=4, tol=0.0)
     np.testing.assert_allclose(got["elbo"], ref, rtol=2e-6)
     np.testing.assert_allclose(got["alpha"], st.alpha, rtol=5e-4)
+
+
+_WORKER_CTX = r'''
+import os, sys, json
+import numpy as np
+sys.path.insert(0, %r)
+import torch, torch.distributed as dist
+import topicmodelsvb_b200 as tm
+which = %r
+rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+torch.cuda.set_device(int(os.environ["LOCAL_RANK"]))
+dist.init_process_group("nccl", device_id=torch.device("cuda", int(os.environ["LOCAL_RANK"])))
+work = torch.cuda.Stream(); torch.cuda.set_stream(work)
+red = tm.dist.Reducer()
+K = 7
+if which == "ctm":
+    c = tm.synth.gencorp_lda(M=300, V=500, K=5, seed=13)
+    m = tm.gpuCTM(tm.Corpus.from_csr(c.shard(rank, world)), K, reducer=red, M_total=c.M, stream=work.cuda_stream)
+    m.beta = np.array(tm.synth.init_beta(K, c.V, seed=7).astype(np.float32).T, order="F", copy=True)
+else:
+    c = tm.synth.gencorp_ctpf(M=300, V=500, U=90, K=5, seed=13)
+    m = tm.gpuCTPF(tm.Corpus.from_csr(c.shard(rank, world)), K, reducer=red, M_total=c.M, stream=work.cuda_stream)
+    m.alef = np.array(tm.synth.init_alef(K, c.V, seed=7).astype(np.float32).T, order="F", copy=True)
+tr = []
+tm.train(m, iter=4, tol=0.0, printelbo=False, trace=tr)
+glob = m.beta if which == "ctm" else m.alef
+probe = torch.tensor([float(np.abs(glob).sum()), float(glob[1, 5])], dtype=torch.float64, device="cuda")
+both = [torch.empty_like(probe) for _ in range(world)]
+dist.all_gather(both, probe)
+if rank == 0:
+    out = {"elbo": tr, "probe": [b.tolist() for b in both]}
+    if which == "ctm":
+        out.update(mu=np.asarray(m.mu, dtype=float).tolist(), sigma=np.asarray(m.sigma, dtype=float).tolist())
+    else:
+        out.update(vav=np.asarray(m.vav, dtype=float).tolist(), bet=np.asarray(m.bet, dtype=float).tolist(), he_sum=float(np.asarray(m.he, dtype=np.float64).sum()))
+    print("RESULT " + json.dumps(out))
+dist.destroy_process_group()
+'''
+
+
+@pytest.mark.parametrize("which", ["ctm", "ctpf"])
+def test_two_gpu_ctm_ctpf_match_oracle(tm, orc, tmp_path, which):
+    """gpuCTM / gpuCTPF doc-sharded d %% 2 over two GPUs (per-iteration all-reduce of the sufficient statistics,
+    tmvb_*_reduce_buffers) == the oracle's single-process trajectory (CTM.jl:185-217 / CTPF.jl:344-371)."""
+    import json
+
+    import torch
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (run with gpurun --gpus 2)")
+    script = tmp_path / "worker_ctx.py"
+    script.write_text(_WORKER_CTX % (ROOT, which))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                        "--master-port", {"ctm": "29541", "ctpf": "29542"}[which], str(script)], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    got = json.loads([l for l in r.stdout.splitlines() if l.startswith("RESULT ")][-1][7:])
+    assert got["probe"][0] == got["probe"][1], "ranks disagree on the global parameters"
+    K = 7
+    if which == "ctm":
+        c = tm.synth.gencorp_lda(M=300, V=500, K=5, seed=13)
+        st = orc.CTMState(K, c.M, c.V, tm.synth.init_beta(K, c.V, seed=7).astype(np.float32))
+        ref = orc.ctm_train(st, c.N_cumsum, c.terms, c.counts, iter=4, tol=0.0)[0]
+        ref = np.asarray(ref)[np.isfinite(ref)]
+        np.testing.assert_allclose(got["elbo"], ref, rtol=2e-5)
+        np.testing.assert_allclose(got["mu"], st.mu, rtol=5e-3, atol=5e-4)
+        np.testing.assert_allclose(got["sigma"], st.sigma, rtol=5e-3, atol=5e-4)
+    else:
+        c = tm.synth.gencorp_ctpf(M=300, V=500, U=90, K=5, seed=13)
+        st = orc.CTPFState(K, c.M, c.V, c.U, tm.synth.init_alef(K, c.V, seed=7).astype(np.float32))
+        ref = orc.ctpf_train(st, c, iter=4, tol=0.0)[0]
+        ref = ref[np.isfinite(ref)]
+        np.testing.assert_allclose(got["elbo"], ref, rtol=2e-5)
+        np.testing.assert_allclose(got["vav"], st.vav, rtol=1e-3)
+        np.testing.assert_allclose(got["bet"], st.bet, rtol=1e-3)
+        np.testing.assert_allclose(got["he_sum"], st.he.sum(), rtol=1e-4)

@@ -1030,18 +1030,18 @@ int tmvb_ctpf_recs(tmvb_ctpf_t h, float *scores, int32_t *urecs, int64_t *uoff, 
     RECS_CUDA(cudaGetLastError());
     const size_t smem = (size_t)(2 * kRecBM + 2 * kRecBN) * 128;
     RECS_CUDA(cudaFuncSetAttribute((const void *)recs_scores_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    auto contract = [&](const float *A, const float *B, float *Cm, int P, int Q, int ldc) {
+    auto contract = [&](const float *A, const float *B, float *Cm, int P, int Q, int ldc, int swap) {
         if (mode & 1) {
             recs_scores_ref_kernel<<<grid_for((long long)P * Q, 256, s.n_sm), 256, 0, s.stream>>>(A, B, Cm, P, Q, KP, ldc);
         } else {
             const int gx = (P + kRecBM - 1) / kRecBM, ntile = (Q + kRecBN - 1) / kRecBN;
             const int gy = std::max(1, std::min(ntile, (2 * s.n_sm + gx - 1) / gx));
-            recs_scores_umma_kernel<<<dim3(gx, gy), 128, smem, s.stream>>>(A, B, Cm, P, Q, KP, ldc);
+            recs_scores_umma_kernel<<<dim3(gx, gy), 128, smem, s.stream>>>(A, B, Cm, P, Q, KP, ldc, swap);
         }
         s.st.kernel_launches++;
     };
-    if (want_d) contract(X, Y, keys_d, (int)M, (int)U, ld_d);
-    if (want_u) contract(Y, X, keys_u, (int)U, (int)M, ld_u);
+    if (want_d) contract(X, Y, keys_d, (int)M, (int)U, ld_d, 0);
+    if (want_u) contract(Y, X, keys_u, (int)U, (int)M, ld_u, 1);
     RECS_CUDA(cudaGetLastError());
     if (scores) {
         RECS_CUDA(cudaMemcpy2DAsync(scores, (size_t)M * 4, keys_u, (size_t)ld_u * 4, (size_t)M * 4, (size_t)U, cudaMemcpyDeviceToHost, s.stream));

@@ -233,6 +233,80 @@ __global__ void lda_elbo_fast_kernel(const LdaDev p, const float *__restrict__ b
     if (lane == 0 && acc != 0.0) atomicAdd(out, acc);
 }
 
+// update_elbo! for a state whose lagged copies EQUAL the current ones (right after tmvb_lda_upload: beta_old = copy(beta),
+// Elogtheta_old = deepcopy(Elogtheta), LDA.jl:36,39) -- the `update_elbo!` at the top of train! (gpuLDA.jl:353) in every
+// train call.  With beta_old = beta and Elogtheta_old = Elogtheta the table D and dE of lda_elbo_fast_kernel vanish and the
+// token terms collapse to  sum_n c_n ln s_n,  s_n = K eps + sum_i beta_i,w exp(Elogtheta_i)  (same eps-weighted remainder as
+// there): one dot product per token in the E-step's lane layout (LPT lanes x CPL 16-byte chunks per row, rows straight from
+// L2), UN rounds in flight.  The per-document Dirichlet terms are those of lda_elbo_fast_kernel.
+template <int LPT, int CPL>
+__global__ void __launch_bounds__(128) lda_elbo_fresh_kernel(const LdaDev p, double lg_alpha_term, double *out)
+{
+    constexpr int S = 32 / LPT, UN = 4;
+    const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+    const int kl = lane % LPT, ts = lane / LPT;
+    const int K = p.K, K_ld = p.K_ld, CH = K_ld >> 2;
+    const float Keps = (float)K * TMVB_EPS;
+    const ulonglong2 zero = make_ulonglong2(0ull, 0ull);
+    double acc = 0.0;
+    for (long long d = (long long)blockIdx.x * wpb + (threadIdx.x >> 5); d < p.M; d += (long long)gridDim.x * wpb) {
+        const long long o = p.doc_off[d];
+        const int Nd = (int)(p.doc_off[d + 1] - o);
+        const float *En = p.Elogtheta + d * K_ld, *gm = p.gamma + d * K_ld;
+        double dacc = 0.0, g0 = 0.0;
+        for (int i = lane; i < K; i += 32) {
+            const double g = gm[i], E = En[i];
+            g0 += g;
+            const PsiLg pl = psi_lgamma<true>((float)g);
+            dacc += ((double)p.alpha[i] - 1.0) * E + (double)pl.lg - (g - 1.0) * (double)pl.psi;
+        }
+        g0 = warp_sum_d(g0);
+        f32x2 e01[CPL], e23[CPL];
+#pragma unroll
+        for (int m = 0; m < CPL; m++) {
+            const int q = kl + LPT * m;
+            float4 E = make_float4(0.f, 0.f, 0.f, 0.f);
+            const bool in = (m < CPL - 1 || q < CH);
+            if (in) E = *reinterpret_cast<const float4 *>(En + 4 * q);
+            // pad topics (i >= K) have beta = 0: their e does not matter
+            e01[m] = in ? pk2(__expf(E.x), __expf(E.y)) : 0ull;
+            e23[m] = in ? pk2(__expf(E.z), __expf(E.w)) : 0ull;
+        }
+        float tacc = 0.0f;
+        const int rounds = (Nd + S - 1) / S;
+        for (int r0 = 0; r0 < rounds; r0 += UN) {
+            ulonglong2 b[UN][CPL];
+            float c[UN];
+#pragma unroll
+            for (int u = 0; u < UN; u++) {
+                const int n = (r0 + u) * S + ts;
+                const bool ok = n < Nd;
+                const int term = ok ? __ldg(p.terms + o + n) : 0;
+                c[u] = ok ? __ldg(p.counts + o + n) : 0.0f;
+                const ulonglong2 *row = reinterpret_cast<const ulonglong2 *>(p.beta + (size_t)term * K_ld) + kl;
+#pragma unroll
+                for (int m = 0; m < CPL; m++) b[u][m] = (ok && (m < CPL - 1 || kl + LPT * m < CH)) ? __ldg(row + LPT * m) : zero;
+            }
+#pragma unroll
+            for (int u = 0; u < UN; u++) {
+                const float sn = tok_dot<LPT, CPL>(b[u], e01, e23) + Keps;
+                if (kl == 0 && c[u] > 0.0f) tacc = fmaf(c[u], __logf(sn), tacc);
+            }
+        }
+        dacc += (double)tacc;
+        dacc = warp_sum_d(dacc);
+        if (lane == 0) {
+            double ent = 0.0;
+            if (K > 1) ent = -lgamma(g0) + (g0 - (double)K) * d_digamma(g0);
+            acc += dacc + ent + lg_alpha_term;
+        }
+    }
+    if (lane == 0 && acc != 0.0) atomicAdd(out, acc);
+}
+typedef void (*LdaElboFreshFn)(const LdaDev, double, double *);
+#define TMVB_LDA_FRESH_FN(L, C) (LdaElboFreshFn)lda_elbo_fresh_kernel<L, C>,
+static const LdaElboFreshFn kLdaElboFresh[kNumLaneLayouts] = {TMVB_FOR_EACH_LAYOUT(TMVB_LDA_FRESH_FN)};
+
 // Block-wide fp64 reductions for lda_alpha_kernel (blockDim.x = 32 * nw, nw <= 9): warp shuffles, then one shared-memory
 // round; every thread receives the result.  `red` is double[3][16], two barriers per call.
 __device__ __forceinline__ void block_sum3(double &a, double &b, double &c, double (*red)[16])
@@ -680,6 +754,7 @@ using namespace tmvb;
 struct tmvb_lda_s {
     Shard s;
     bool params_set = false, elbo_valid = false;
+    bool beta_fresh = false, E_fresh = false;   // beta_old == beta / Elogtheta_old == Elogtheta on the device (set by upload, cleared by any step)
     float *d_alpha = nullptr;
     float *d_Elogtheta = nullptr, *d_Elogtheta_old = nullptr, *d_gamma = nullptr;
     std::vector<double> h_alpha;        // fp64 master copy of alpha (update_alpha! runs in fp64 on the host)
@@ -972,6 +1047,7 @@ int tmvb_lda_upload(tmvb_lda_t h, const float *alpha, const float *beta, const f
         TMVB_TRY(shard_upload_rows(&s, beta, s.d_beta[s.cur], s.V, nullptr, 0));
         // beta_old = copy(beta)  (LDA.jl:36)
         TMVB_CUDA(cudaMemcpyAsync(s.d_beta[s.cur ^ 1], s.d_beta[s.cur], (size_t)s.V * s.K_ld * 4, cudaMemcpyDeviceToDevice, s.stream));
+        h->beta_fresh = true;
     }
     if ((Elogtheta || gamma) && s.M > 0) {
         TMVB_CHECK_ARG(s.corpus_set, "set_corpus must precede the upload of per-document parameters");
@@ -979,6 +1055,7 @@ int tmvb_lda_upload(tmvb_lda_t h, const float *alpha, const float *beta, const f
         // Elogtheta_old = deepcopy(Elogtheta)  (LDA.jl:39)
         if (Elogtheta)
             TMVB_CUDA(cudaMemcpyAsync(h->d_Elogtheta_old, h->d_Elogtheta, (size_t)s.M * s.K_ld * 4, cudaMemcpyDeviceToDevice, s.stream));
+        if (Elogtheta) h->E_fresh = true;
         TMVB_TRY(shard_upload_rows(&s, gamma, h->d_gamma, s.M, s.d_perm, 2));
     }
     int verr = 0;
@@ -1018,6 +1095,7 @@ int tmvb_lda_estep(tmvb_lda_t h, int viter, float vtol, int want_elbo)
     TMVB_CUDA(cudaEventRecord(s.ev[1], s.stream));
     s.estep_timed = true;
     h->elbo_valid = (want_elbo != 0);
+    h->E_fresh = false;
     return 0;
 }
 
@@ -1051,6 +1129,7 @@ int tmvb_lda_mstep(tmvb_lda_t h)
     TMVB_TRY(shard_normalize(&s, h->d_local, h->elbo_valid, true));
     TMVB_CUDA(cudaEventRecord(s.ev[3], s.stream));
     s.mstep_timed = true;
+    h->beta_fresh = false;
     return 0;
 }
 
@@ -1131,6 +1210,7 @@ int tmvb_lda_exchange_mstep(tmvb_lda_t h)
     TMVB_CHECK_ARG(s.K_ld + 1 <= kCtlPartLen, "K too large for the exchange control block");
     TMVB_CUDA(cudaSetDevice(s.device));
     TMVB_CUDA(cudaEventRecord(s.ev[2], s.stream));
+    h->beta_fresh = false;
     if (s.V > 0) {
         TMVB_TRY(lda_enqueue_exchange(h, false, 0, 0, 0.0));
         s.st.kernel_launches++;
@@ -1177,6 +1257,7 @@ int tmvb_lda_iterate(tmvb_lda_t h, int viter, float vtol, int want_elbo, int64_t
         key.append("iter", 4);
     }
     h->elbo_valid = want_elbo != 0;   // read by the enqueue helpers below
+    h->beta_fresh = h->E_fresh = false;
     double *result = h->d_local + 2 * s.K_ld + 1;
     const int threads = 32 * (((int)s.K + 1 + 31) / 32);
 
@@ -1384,6 +1465,9 @@ int tmvb_lda_elbo(tmvb_lda_t h, int mode, int64_t M_total, double *elbo_docs, do
         } else if (env_int("TMVB_ELBO_LITERAL", 0)) {
             if (K <= 32) TMVB_ELBO_LAUNCH(float, 1); else if (K <= 64) TMVB_ELBO_LAUNCH(float, 2);
             else if (K <= 128) TMVB_ELBO_LAUNCH(float, 4); else TMVB_ELBO_LAUNCH(float, 8);
+        } else if (h->beta_fresh && h->E_fresh && !env_int("TMVB_ELBO_NOFRESH", 0)) {
+            // the lagged copies equal the current state (nothing ran since the upload): the one-dot-product-per-token form
+            kLdaElboFresh[s.layout]<<<grid, 128, 0, s.stream>>>(p, lga, out);
         } else {
             const long long n = (long long)s.V * K_ld;
             TMVB_TRY(shard_scratch(&s, (size_t)std::max<long long>(n, 1) * 4));

@@ -149,8 +149,10 @@ __device__ __forceinline__ void stage_operand(const float *__restrict__ g, long 
 
 // C[p][q] = sum_k X[p][k] Y[q][k]   (X: [P][KP], Y: [Q][KP], KP a multiple of 32, zero padded; C row-major, leading dimension ldc)
 // grid (ceil(P / 128), NY): CTA (bx, by) owns rows 128 bx .. of X and the column tiles by, by + NY, ...
+// swap: the two small products are issued in the other order, so that the transposed launch (X and Y exchanged) accumulates
+// the same three terms in the same order and C'[q][p] == C[p][q] bit for bit (both rankings then see the same scores)
 __global__ void __launch_bounds__(128) recs_scores_umma_kernel(const float *__restrict__ X, const float *__restrict__ Y, float *__restrict__ C, int P, int Q,
-                                                               int KP, long long ldc)
+                                                               int KP, long long ldc, int swap)
 {
     extern __shared__ __align__(128) unsigned char smem[];
     unsigned char *xhi = smem, *xlo = xhi + kRecBM * 128, *yhi = xlo + kRecBM * 128, *ylo = yhi + kRecBN * 128;
@@ -178,8 +180,9 @@ __global__ void __launch_bounds__(128) recs_scores_umma_kernel(const float *__re
                 tc_fence_after();
                 const unsigned axh = smem_u32(xhi), axl = smem_u32(xlo), ayh = smem_u32(yhi), ayl = smem_u32(ylo);
 #pragma unroll
-                for (int prod = 0; prod < 3; prod++) {   // small terms first: Xlo Yhi', Xhi Ylo', Xhi Yhi'
-                    const unsigned ax = prod == 0 ? axl : axh, ay = prod == 1 ? ayl : ayh;
+                for (int prod = 0; prod < 3; prod++) {   // small terms first: Xlo Yhi', Xhi Ylo', Xhi Yhi' (swap: the first two exchanged)
+                    const int lo_x = swap ? 1 : 0, lo_y = swap ? 0 : 1;
+                    const unsigned ax = prod == lo_x ? axl : axh, ay = prod == lo_y ? ayl : ayh;
 #pragma unroll
                     for (int k = 0; k < kRecBK / 8; k++)   // an MMA spans K = 8 tf32 values = two 16-byte chunks = 256 bytes of the layout
                         umma_tf32(tmem, umma_smem_desc(ax + k * 256, 128, 1024), umma_smem_desc(ay + k * 256, 128, 1024), kRecIdesc,
