@@ -264,6 +264,35 @@ int tmvb_ctpf_topics(tmvb_ctpf_t h, int32_t *topics); /* gpuCTPF.jl:706-707 */
 int tmvb_ctpf_recs(tmvb_ctpf_t h, float *scores, int32_t *urecs, int64_t *uoff, int32_t *drecs, int64_t *doff, int mode);
 int tmvb_ctpf_get_stats(tmvb_ctpf_t h, tmvb_stats *out);
 
+/* ------------------------------------------------------------------ fLDA ----------------- */
+
+/* Filtered LDA (src/fLDA.jl) on the device.  The reference has no gpufLDA: `@gpu` leaves fLDA / fCTM untouched (macros.jl:274-278)
+ * and its todo list asks for them; these entry points are what a `gpufLDA` mirror of gpuLDA would bind.
+ * Layouts as for LDA; tau / tau_old are flat over the CSR tokens in the caller's order (tau[d][n] at N_cumsum[d] + n). */
+typedef struct tmvb_flda_s *tmvb_flda_t;
+int tmvb_flda_create(tmvb_flda_t *h, int64_t K, int64_t M, int64_t V, int device, void *stream);
+int tmvb_flda_destroy(tmvb_flda_t h);
+int tmvb_flda_set_corpus(tmvb_flda_t h, const int64_t *N_cumsum, const int64_t *terms, const int64_t *counts);
+/* the struct fields of fLDA.jl:14-26: eta, alpha[K], kappa[V], beta[K*V], Elogtheta[K*M], gamma[K*M], tau[sum N]; the *_old copies are
+ * set to the uploaded values (fLDA.jl:42,45,48,51).  Any pointer may be NULL. */
+int tmvb_flda_upload(tmvb_flda_t h, const double *eta, const float *alpha, const float *kappa, const float *beta, const float *Elogtheta,
+                     const float *gamma, const float *tau);
+/* the per-document inner loop of train!(::fLDA) (fLDA.jl:223-233: update_phi!/update_tau!/update_gamma!/update_Elogtheta! with the
+ * per-document stopping rule), then update_beta!(model, d) and update_kappa!(model, d) (fLDA.jl:156-171) */
+int tmvb_flda_estep(tmvb_flda_t h, int viter, float vtol);
+/* the same without the scatter: predict(corp, train_model::fLDA) (modelutils.jl:857-884) */
+int tmvb_flda_predict(tmvb_flda_t h, int viter, float vtol);
+int tmvb_flda_reduce_buffers(tmvb_flda_t h, void **stats, int64_t *n_stats, void **kstats, int64_t *n_kstats, void **small, int64_t *n_small);
+/* update_beta!(model), update_kappa!(model), update_alpha!(model, niter, ntol), update_eta!(model) (fLDA.jl:236-239);
+ * M_total / C_total = number of documents / sum of all counts over every rank */
+int tmvb_flda_mstep(tmvb_flda_t h, int64_t M_total, double C_total, int niter, double ntol);
+/* update_elbo! (fLDA.jl:105-117) summed over the shard's documents */
+int tmvb_flda_elbo(tmvb_flda_t h, double *elbo_docs);
+int tmvb_flda_download(tmvb_flda_t h, double *eta, float *alpha, float *kappa, float *beta, float *Elogtheta, float *gamma, float *tau);
+int tmvb_flda_download_old(tmvb_flda_t h, float *kappa_old, float *beta_old, float *Elogtheta_old, float *tau_old);
+int tmvb_flda_topics(tmvb_flda_t h, int32_t *topics); /* fLDA.jl:246 */
+int tmvb_flda_get_stats(tmvb_flda_t h, tmvb_stats *out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -449,3 +449,116 @@ class CTPFTwin:
                 if delta < tol:
                     break
         return np.array(trace)
+
+
+class FLDATwin(LDATwin):
+    """src/fLDA.jl, line for line (filtered LDA: per-token Bernoulli tau, corpus distribution kappa, mixing weight eta)."""
+
+    def __init__(self, N_cumsum, terms, counts, K, V, beta, kappa, alpha=None, eta=0.5):
+        super().__init__(N_cumsum, terms, counts, K, V, beta, alpha)
+        self.eta = float(eta)                                              # fLDA.jl:39
+        self.kappa = np.array(kappa, dtype=np.float64)
+        self.kappa_old = self.kappa.copy()
+        self.kappa_temp = np.zeros(V)
+        self.tau = np.full(len(self.terms), self.eta)                      # fLDA.jl:50
+        self.tau_old = self.tau.copy()
+        self.C = np.array([self.counts[self.off[d]:self.off[d + 1]].sum() for d in range(self.M)])
+
+    def _sl(self, d):
+        return slice(self.off[d], self.off[d + 1])
+
+    @staticmethod
+    def _additive_logistic(x):                                             # utils.jl:114-121, dims = the topic axis
+        x = np.exp(x - x.max(axis=1, keepdims=True))
+        return x / x.sum(axis=1, keepdims=True)
+
+    # fLDA.jl:198-201
+    def update_phi(self, d):
+        terms, _ = self._doc(d)
+        self.phi = self._additive_logistic(self.tau[self._sl(d)][:, None] * np.log(self.beta[terms] + EPSILON) + self.Elogtheta[d][None, :])
+
+    # fLDA.jl:189-194
+    def update_tau(self, d):
+        terms, _ = self._doc(d)
+        s = self._sl(d)
+        self.tau_old[s] = self.tau[s]
+        with np.errstate(divide="ignore", over="ignore"):
+            pr = np.prod(self.beta[terms] ** (-self.phi), axis=1)
+            self.tau[s] = self.eta / ((self.eta + (1 - self.eta) * (self.kappa[terms] * pr)) + EPSILON)
+
+    # fLDA.jl:182-185
+    def update_gamma(self, d):
+        _, counts = self._doc(d)
+        self.gamma[d] = EPSILON + (self.alpha + counts @ self.phi)
+
+    # fLDA.jl:168-171, 156-159
+    def update_beta_doc(self, d):
+        terms, counts = self._doc(d)
+        t = self.tau[self._sl(d)]
+        self.beta_temp[terms] += self.phi * (t * counts)[:, None]
+        self.kappa_temp[terms] += (1 - t) * counts
+
+    # fLDA.jl:149-153
+    def update_kappa(self):
+        self.kappa_old = self.kappa
+        self.kappa = self.kappa_temp / self.kappa_temp.sum()
+        self.kappa_temp = np.zeros(self.V)
+
+    # fLDA.jl:119-121
+    def update_eta(self):
+        self.eta = sum(np.dot(self.tau[self._sl(d)], self.counts[self._sl(d)]) for d in range(self.M)) / self.C.sum()
+
+    # fLDA.jl:62-117
+    def update_elbo(self):
+        elbo = 0.0
+        a = self.alpha
+        for d in range(self.M):
+            terms, counts = self._doc(d)
+            s = self._sl(d)
+            phi = self._additive_logistic(self.tau_old[s][:, None] * np.log(self.beta_old[terms] + EPSILON) + self.Elogtheta_old[d][None, :])
+            Et, g, tau = self.Elogtheta[d], self.gamma[d], self.tau[s]
+            Elogptheta = _finite(gammaln(a.sum())) - _finite(gammaln(a).sum()) + np.dot(a - 1, Et)
+            tc = np.dot(tau, counts)
+            Elogpc = np.log(self.eta**tc * (1 - self.eta) ** (self.C[d] - tc) + EPSILON)
+            Elogpz = np.dot(counts @ phi, Et)
+            Elogpw = np.sum((phi * np.log(self.beta[terms] + EPSILON)) * (counts * tau)[:, None]) + np.dot(counts * (1 - tau), np.log(self.kappa[terms] + EPSILON))
+            if self.K == 1:
+                ent_dir = 0.0
+            else:  # utils.jl:163-180
+                ent_dir = gammaln(g).sum() - gammaln(g.sum()) + (g.sum() - self.K) * digamma(g.sum()) - np.dot(g - 1, digamma(g))
+            p0 = 1 - tau
+            with np.errstate(divide="ignore", invalid="ignore"):
+                hb = np.where((p0 == 0) | (p0 == 1), 0.0, -(p0 * np.log(p0) + tau * np.log(tau)))
+                hz = -np.sum(np.where(phi > 0, phi * np.log(phi), 0.0), axis=1)
+            elbo += Elogptheta + Elogpc + Elogpz + Elogpw + ent_dir + np.dot(counts, hb) + np.dot(counts, hz)
+        self.elbo = elbo
+        return elbo
+
+    # fLDA.jl:214-247
+    def train(self, iter=150, tol=1.0, niter=1000, ntol=None, viter=10, vtol=None, checkelbo=1):
+        ntol = 1.0 / self.K**2 if ntol is None else ntol
+        vtol = 1.0 / self.K**2 if vtol is None else vtol
+        trace = [np.nan] * (iter + 1)
+        if checkelbo <= iter:
+            trace[0] = self.update_elbo()
+        for k in range(1, iter + 1):
+            for d in range(self.M):
+                for _ in range(viter):
+                    self.update_phi(d)
+                    self.update_tau(d)
+                    self.update_gamma(d)
+                    self.update_Elogtheta(d)
+                    if np.linalg.norm(self.Elogtheta[d] - self.Elogtheta_old[d]) < vtol:
+                        break
+                self.update_beta_doc(d)
+            self.update_beta()
+            self.update_kappa()
+            self.update_alpha(niter, ntol)
+            self.update_eta()
+            if k % checkelbo == 0:
+                old = self.elbo
+                delta = self.update_elbo() - old
+                trace[k] = self.elbo
+                if delta < tol:
+                    break
+        return np.array(trace)

@@ -81,7 +81,7 @@ def test_fused_elbo_equals_standalone(tm, orc):
         assert abs(e1 - e2) <= 1e-6 * abs(e2), (it, e1, e2)
 
 
-@pytest.mark.parametrize("K", [3, 10, 50, 100, 200])
+@pytest.mark.parametrize("K", [1, 3, 10, 50, 100, 200])
 def test_fresh_state_elbo_equals_literal(tm, monkeypatch, K):
     """mode 1 right after update_buffer! (beta_old == beta, Elogtheta_old == Elogtheta on the device: the `update_elbo!` that opens
     every train! call, gpuLDA.jl:353) takes the one-dot-product-per-token kernel; it must equal the table-assisted pass
@@ -119,7 +119,7 @@ def test_fused_iteration_equals_separate_steps(tm, monkeypatch):
 
     e0, a0, b0, g0 = run(True)
     e1, a1, b1, g1 = run(False)
-    np.testing.assert_allclose(e1, e0, rtol=1e-7)          # same kernels, same order: only the atomics' order differs
+    np.testing.assert_allclose(e1, e0, rtol=1e-6)          # same kernels, same order: only the atomics' order differs (2e-7 seen after 5 iterations)
     np.testing.assert_allclose(a1, a0, rtol=1e-5)
     np.testing.assert_allclose(b1, b0, rtol=1e-4, atol=1e-9)
     np.testing.assert_allclose(g1, g0, rtol=1e-4, atol=1e-6)
@@ -128,7 +128,7 @@ def test_fused_iteration_equals_separate_steps(tm, monkeypatch):
     model = tm.gpuLDA(tm.Corpus.from_csr(c), K, seed=5)
     tr = []
     tm.train(model, iter=4, tol=0.0, printelbo=False, trace=tr, checkelbo=2)
-    np.testing.assert_allclose(tr[1:], e0[[2, 4]], rtol=1e-7)
+    np.testing.assert_allclose(tr[1:], e0[[2, 4]], rtol=1e-6)
 
 
 def test_int64_and_int32_corpus_entry_points_agree(tm, monkeypatch):

@@ -215,3 +215,35 @@ def test_golden_ctm_and_ctpf(orc):
     tr, _, _ = orc.ctpf_train(st, c, iter=len(g["elbo"]) - 1, tol=0.0)
     np.testing.assert_allclose(tr, g["elbo"], rtol=1e-10)
     np.testing.assert_allclose(st.vav, g["vav"], rtol=1e-10)
+
+
+def test_flda_c_oracle_equals_numpy_twin(orc):
+    """oracle/flda_oracle.c == the literal NumPy transcription of src/fLDA.jl (FLDATwin) to <= 1e-12 relative: ELBO trajectory,
+    eta, tau, beta, kappa, alpha; the OpenMP document split only re-associates fp64 sums."""
+    import topicmodelsvb_b200 as tm
+    from oracle.numpy_twin import FLDATwin
+
+    c = tm.synth.gencorp_lda(M=40, V=120, K=4, seed=3)
+    for K in (1, 5):
+        beta0 = tm.synth.init_beta(K, c.V, seed=7)
+        kappa = np.random.default_rng(1).dirichlet(np.ones(c.V))
+        tw = FLDATwin(c.N_cumsum, c.terms, c.counts, K, c.V, beta0, kappa)
+        t1 = tw.train(iter=4, tol=0.0)
+        st = orc.FLDAState(K, c.M, c.V, len(c.terms), beta0, kappa)
+        t2, sweeps, done = orc.flda_train(st, c.N_cumsum, c.terms, c.counts, iter=4, tol=0.0)
+        assert done == 4 and np.all(sweeps > 0)
+        np.testing.assert_allclose(t2, t1, rtol=1e-12)
+        assert abs(st.eta[0] - tw.eta) < 1e-13
+        np.testing.assert_allclose(st.tau, tw.tau, rtol=1e-11, atol=1e-15)
+        np.testing.assert_allclose(st.tau_old, tw.tau_old, rtol=1e-11, atol=1e-15)
+        np.testing.assert_allclose(st.beta, tw.beta, rtol=1e-11, atol=1e-300)
+        np.testing.assert_allclose(st.kappa, tw.kappa, rtol=1e-11)
+        np.testing.assert_allclose(st.alpha, tw.alpha, rtol=1e-11)
+        np.testing.assert_allclose(st.gamma, tw.gamma, rtol=1e-11)
+        st4 = orc.FLDAState(K, c.M, c.V, len(c.terms), beta0, kappa)
+        t4, _, _ = orc.flda_train(st4, c.N_cumsum, c.terms, c.counts, iter=4, tol=0.0, nthreads=4)
+        np.testing.assert_allclose(t4, t2, rtol=1e-12)
+    # checkelbo = 2 evaluates every other iteration; a large tol stops at the first check
+    st = orc.FLDAState(5, c.M, c.V, len(c.terms), tm.synth.init_beta(5, c.V, seed=7), kappa)
+    t, _, done = orc.flda_train(st, c.N_cumsum, c.terms, c.counts, iter=6, tol=1e12, checkelbo=2)
+    assert done == 2 and np.isfinite(t[[0, 2]]).all() and np.isnan(t[1])

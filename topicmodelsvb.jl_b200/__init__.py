@@ -7,6 +7,7 @@ from ._lib import TopicModelError, build  # noqa: F401
 from .corpus import Corpus, CorpusError, Document, DocumentError, readcorp  # noqa: F401
 from .gpu_ctm import check_model_ctm, gpuCTM, train_ctm  # noqa: F401
 from .gpu_ctpf import check_model_ctpf, gpuCTPF, train_ctpf  # noqa: F401
+from .gpu_flda import check_model_flda, gpufLDA, train_flda  # noqa: F401
 from .gpu_lda import check_elbo, gpuLDA  # noqa: F401
 from .gpu_lda import check_model as check_model_lda  # noqa: F401
 from .gpu_lda import train as train_lda  # noqa: F401
@@ -22,6 +23,8 @@ def train(model, **kwargs):
         return train_ctm(model, **kwargs)
     if isinstance(model, gpuCTPF):
         return train_ctpf(model, **kwargs)
+    if isinstance(model, gpufLDA):
+        return train_flda(model, **kwargs)
     raise TypeError("train!: unsupported model type %r" % type(model).__name__)
 
 
@@ -33,4 +36,6 @@ def check_model(model):
         return check_model_ctm(model)
     if isinstance(model, gpuCTPF):
         return check_model_ctpf(model)
+    if isinstance(model, gpufLDA):
+        return check_model_flda(model)
     raise TypeError("check_model: unsupported model type %r" % type(model).__name__)

@@ -134,6 +134,19 @@ SIGNATURES = {
     "tmvb_ctpf_topics": (C.c_int, [_vp, _vp]),
     "tmvb_ctpf_recs": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, C.c_int]),
     "tmvb_ctpf_get_stats": (C.c_int, [_vp, C.POINTER(TmvbStats)]),
+    "tmvb_flda_create": (C.c_int, [C.POINTER(_vp), C.c_int64, C.c_int64, C.c_int64, C.c_int, _vp]),
+    "tmvb_flda_destroy": (C.c_int, [_vp]),
+    "tmvb_flda_set_corpus": (C.c_int, [_vp] * 4),
+    "tmvb_flda_upload": (C.c_int, [_vp, C.POINTER(C.c_double)] + [_vp] * 6),
+    "tmvb_flda_estep": (C.c_int, [_vp, C.c_int, C.c_float]),
+    "tmvb_flda_predict": (C.c_int, [_vp, C.c_int, C.c_float]),
+    "tmvb_flda_reduce_buffers": (C.c_int, [_vp, C.POINTER(_vp), C.POINTER(C.c_int64), C.POINTER(_vp), C.POINTER(C.c_int64), C.POINTER(_vp), C.POINTER(C.c_int64)]),
+    "tmvb_flda_mstep": (C.c_int, [_vp, C.c_int64, C.c_double, C.c_int, C.c_double]),
+    "tmvb_flda_elbo": (C.c_int, [_vp, C.POINTER(C.c_double)]),
+    "tmvb_flda_download": (C.c_int, [_vp, C.POINTER(C.c_double)] + [_vp] * 6),
+    "tmvb_flda_download_old": (C.c_int, [_vp] * 5),
+    "tmvb_flda_topics": (C.c_int, [_vp, _vp]),
+    "tmvb_flda_get_stats": (C.c_int, [_vp, C.POINTER(TmvbStats)]),
 }
 
 

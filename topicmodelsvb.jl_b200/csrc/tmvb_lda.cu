@@ -69,7 +69,7 @@ __global__ void lda_elbo_kernel(const LdaDev p, const float *__restrict__ beta_o
                     dacc += ((double)p.alpha[i] - 1.0) * E + lgamma(g) - (g - 1.0) * d_digamma(g);
                 } else {
                     const PsiLg pl = psi_lgamma<true>((float)g);
-                    dacc += ((double)p.alpha[i] - 1.0) * E + (double)pl.lg - (g - 1.0) * (double)pl.psi;
+                    dacc += ((double)p.alpha[i] - 1.0) * E + (p.K > 1 ? (double)pl.lg - (g - 1.0) * (double)pl.psi : 0.0);   // K = 1: entropy(Dirichlet) = 0, utils.jl:168
                 }
             }
         }
@@ -189,7 +189,7 @@ __global__ void lda_elbo_fast_kernel(const LdaDev p, const float *__restrict__ b
                 e_r[r] = expf(Eo[i]);
                 dE_r[r] = En[i] - Eo[i];
                 const PsiLg pl = psi_lgamma<true>((float)g);
-                dacc += ((double)p.alpha[i] - 1.0) * E + (double)pl.lg - (g - 1.0) * (double)pl.psi;
+                dacc += ((double)p.alpha[i] - 1.0) * E + (p.K > 1 ? (double)pl.lg - (g - 1.0) * (double)pl.psi : 0.0);   // K = 1: entropy(Dirichlet) = 0, utils.jl:168
             }
         }
         g0 = warp_sum_d(g0);
@@ -258,7 +258,7 @@ __global__ void __launch_bounds__(128) lda_elbo_fresh_kernel(const LdaDev p, dou
             const double g = gm[i], E = En[i];
             g0 += g;
             const PsiLg pl = psi_lgamma<true>((float)g);
-            dacc += ((double)p.alpha[i] - 1.0) * E + (double)pl.lg - (g - 1.0) * (double)pl.psi;
+            dacc += ((double)p.alpha[i] - 1.0) * E + (p.K > 1 ? (double)pl.lg - (g - 1.0) * (double)pl.psi : 0.0);   // K = 1: entropy(Dirichlet) = 0, utils.jl:168
         }
         g0 = warp_sum_d(g0);
         f32x2 e01[CPL], e23[CPL];
@@ -416,6 +416,16 @@ __global__ void lda_alpha_kernel(double *__restrict__ alpha64, float *__restrict
         else
             result[0] = small[K_ld] + part + local[K_ld];
     }
+}
+
+// host-callable launch for the other model families that share update_alpha! (fLDA.jl:122-146 is LDA.jl:97-118 verbatim)
+int lda_launch_alpha(double *alpha64, float *alpha32, const double *small, int K, int K_ld, double Md, int niter, double ntol, cudaStream_t stream)
+{
+    const int threads = 32 * ((K + 1 + 31) / 32);
+    if (threads > 288) return fail(-2, "update_alpha! on the device supports K <= 287");
+    lda_alpha_kernel<<<1, threads, 0, stream>>>(alpha64, alpha32, small, nullptr, K, K_ld, Md, niter, ntol, 0, nullptr);
+    TMVB_CUDA(cudaGetLastError());
+    return 0;
 }
 
 __global__ void lda_elbo_assemble_kernel(const double *__restrict__ small, const double *__restrict__ local, int K_ld, double *__restrict__ result)

@@ -88,7 +88,9 @@ __global__ void validate_kernel(const float *__restrict__ x, long long n, int wh
     for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < n; q += (long long)gridDim.x * blockDim.x) {
         const float v = x[q];
         if (!isfinite(v)) e |= 1;
-        if ((what == 0 && v < 0.f) || (what == 1 && v > 0.f) || (what == 2 && !(v > 0.f))) e |= 2;
+        // what == 1 (Elogtheta <= 0): psi(gamma_i) - psi(sum gamma) evaluated in fp32 can come out a few ulp above zero when one topic
+        // holds all the mass (K = 1: the two arguments are equal), and such a state must survive a second train! call
+        if ((what == 0 && v < 0.f) || (what == 1 && v > 1e-6f) || (what == 2 && !(v > 0.f))) e |= 2;
     }
     if (e) atomicOr(err, e << (2 * what));
 }
@@ -297,7 +299,7 @@ static int plan_buckets(Shard *s, size_t fixed_bytes)
     const std::vector<int> &len_sorted = s->len_sorted;
     const int M = (int)len_sorted.size();
     if (M == 0) return 0;
-    const size_t per_tok = (size_t)s->RS * 4 + 8;
+    const size_t per_tok = (size_t)s->RS * 4 + 8 + s->per_tok_extra;
     if (fixed_bytes + 16 * per_tok > s->smem_optin) return fail(-4, "internal: E-step working set does not fit in shared memory");
     int cap_max = 16;
     while (fixed_bytes + (size_t)(cap_max + 16) * per_tok <= s->smem_optin) cap_max += 16;

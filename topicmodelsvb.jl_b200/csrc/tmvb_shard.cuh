@@ -40,6 +40,7 @@ struct Shard {
     float *d_doc_c = nullptr;   // [M] sum of a document's counts (C_d of the reference's structs, gpuLDA.jl:52), internal order
     std::vector<int> h_perm, len_sorted;
     std::vector<Bucket> buckets;
+    size_t per_tok_extra = 0;   // shared-memory bytes per staged token beyond the row, its count and its id (fLDA: tau, tau_old, kappa weight)
     int tile_cap_max = 0;   // > 0: largest shared-memory tile (tokens) a launch bucket may stage; longer documents read the rest from L2
     // captured launch sequences of one E-step (see shard_launch), keyed by kernel set + by-value parameter block
     struct LaunchGraph {
@@ -90,6 +91,8 @@ int shard_launch(Shard *s, BucketKernelFn pick, const void *ctx, void *dev_struc
 int shard_launch_key(Shard *s, BucketKernelFn pick, const void *ctx, const void *dev_struct, size_t dev_struct_bytes, std::string *key_out);
 int shard_enqueue_buckets(Shard *s, BucketKernelFn pick, const void *ctx, void *dev_struct);
 void shard_drop_graphs(Shard *s);
+// update_alpha! (LDA.jl:97-118 == fLDA.jl:122-146) on the device: small[0..K) = sum_d Elogtheta_d; alpha64 / alpha32 are updated in place (tmvb_lda.cu)
+int lda_launch_alpha(double *alpha64, float *alpha32, const double *small, int K, int K_ld, double Md, int niter, double ntol, cudaStream_t stream);
 // pick for kernels that only come in "warps per document" flavours: ctx = const void *const fn_by_warps[]
 const void *pick_by_warps(const Bucket &b, const void *ctx);
 // beta_new = stats ./ rowsum ; stats <- 0 ; [elbo_w = sum stats ln(beta_new + eps)].  d_acc: double[2*K_ld] (rowsum | elbo_w)
