@@ -293,6 +293,18 @@ int tmvb_flda_download_old(tmvb_flda_t h, float *kappa_old, float *beta_old, flo
 int tmvb_flda_topics(tmvb_flda_t h, int32_t *topics); /* fLDA.jl:246 */
 int tmvb_flda_get_stats(tmvb_flda_t h, tmvb_stats *out);
 
+/* ------------------------------------------------------------------ fCTM ----------------- */
+
+/* Filtered CTM (src/fCTM.jl) on the device: a gpuCTM handle that additionally holds eta, kappa and the per-token tau of fCTM.jl:10-28.
+ * After tmvb_fctm_create every tmvb_ctm_* entry point applies to it: tmvb_ctm_estep runs the inner loop of train!(::fCTM)
+ * (fCTM.jl:258-268: update_phi!, update_tau!, update_logzeta!, update_lambda!, update_vsq!) and the scatters of fCTM.jl:162-178,
+ * tmvb_ctm_mstep adds update_kappa!(model) (fCTM.jl:154-158), tmvb_ctm_elbo evaluates update_elbo! of fCTM.jl:67-130 (either mode).
+ * Like fLDA the reference has no GPU version of it (macros.jl:277-278). */
+int tmvb_fctm_create(tmvb_ctm_t *h, int64_t K, int64_t M, int64_t V, int device, void *stream);
+int tmvb_fctm_upload(tmvb_ctm_t h, const double *eta, const float *kappa, const float *tau);
+int tmvb_fctm_download(tmvb_ctm_t h, float *kappa, float *kappa_old, float *tau, float *tau_old);
+int tmvb_fctm_reduce_buffers(tmvb_ctm_t h, void **kstats, int64_t *n_kstats);
+
 #ifdef __cplusplus
 }
 #endif

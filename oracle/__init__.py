@@ -89,6 +89,10 @@ def load():
                                       _c.POINTER(_c.c_int), _c.c_int])
     lib.orc_flda_elbo.restype = _c.c_double
     lib.orc_flda_elbo.argtypes = [_c.c_int64] * 3 + [_i64p] * 3 + [_c.c_double] + [_f64p] * 10 + [_c.c_int]
+    lib.orc_fctm_train.restype = _c.c_int
+    lib.orc_fctm_train.argtypes = ([_c.c_int64] * 3 + [_i64p] * 3 + [_c.c_double] + [_f64p] * 13
+                                   + [_c.c_int, _c.c_double, _c.c_int, _c.c_double, _c.c_int, _c.c_double, _c.c_int, _f64p, _i64p,
+                                      _c.POINTER(_c.c_int), _c.c_int])
     _lib = lib
     return lib
 
@@ -320,6 +324,39 @@ def flda_train(st: FLDAState, N_cumsum, terms, counts, iter=150, tol=1.0, niter=
     lib.orc_flda_train(K, st.M, st.V, i64(N_cumsum), i64(terms), i64(counts), st.eta, st.alpha, st.kappa, st.kappa_old, st.beta, st.beta_old,
                        st.Elogtheta, st.Elogtheta_old, st.gamma, st.tau, st.tau_old, int(iter), float(tol), int(niter), float(ntol), int(viter),
                        float(vtol), ce, trace, sweeps, _c.byref(done), int(nthreads))
+    fin = trace[np.isfinite(trace)]
+    if fin.size:
+        st.elbo = float(fin[-1])
+    return trace, sweeps[:iter], done.value
+
+
+class FCTMState(CTMState):
+    """The mutable fields of the reference's ``fCTM`` struct (fCTM.jl:6-32, init :46-60): CTMState + eta, kappa, tau."""
+
+    def __init__(self, K, M, V, nnz, beta, kappa, eta=0.5):
+        super().__init__(K, M, V, beta)
+        self.eta = float(eta)
+        self.kappa = np.ascontiguousarray(kappa, dtype=np.float64).copy()
+        self.kappa_old = self.kappa.copy()
+        self.tau = np.full(int(nnz), float(eta))
+        self.tau_old = self.tau.copy()
+
+
+def fctm_train(st: FCTMState, N_cumsum, terms, counts, iter=150, tol=1.0, niter=1000, ntol=None, viter=10, vtol=None, checkelbo=1,
+               nthreads=1):
+    """train!(model::fCTM; ...) (fCTM.jl:249-290) on the C oracle.  Returns (elbo_trace, sweeps, iters_done)."""
+    lib = load()
+    K = st.K
+    ntol = 1.0 / K**2 if ntol is None else ntol
+    vtol = 1.0 / K**2 if vtol is None else vtol
+    trace = np.full(iter + 1, np.nan)
+    sweeps = np.zeros(max(iter, 1), dtype=np.int64)
+    done = _c.c_int(0)
+    ce = 0 if (checkelbo is None or checkelbo == float("inf")) else int(checkelbo)
+    i64 = lambda a: np.ascontiguousarray(a, dtype=np.int64)  # noqa: E731
+    lib.orc_fctm_train(K, st.M, st.V, i64(N_cumsum), i64(terms), i64(counts), float(st.eta), st.mu, st.sigma, st.invsigma, st.kappa,
+                       st.kappa_old, st.beta, st.beta_old, st.lam, st.lam_old, st.vsq, st.logzeta, st.tau, st.tau_old, int(iter), float(tol),
+                       int(niter), float(ntol), int(viter), float(vtol), ce, trace, sweeps, _c.byref(done), int(nthreads))
     fin = trace[np.isfinite(trace)]
     if fin.size:
         st.elbo = float(fin[-1])

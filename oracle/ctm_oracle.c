@@ -54,6 +54,9 @@ static void chol_solve(int64_t K, const double *L, double *b)
 }
 
 /* inv(A) and logdet(A) of an SPD matrix (CTM.jl:57,110) */
+#ifdef ORC_CTM_HELPERS_ONLY
+int orc_spd_inv_logdet(int64_t K, const double *A, double *Ainv, double *logdet);
+#else
 int orc_spd_inv_logdet(int64_t K, const double *A, double *Ainv, double *logdet)
 {
     double *L = (double *)malloc(sizeof(double) * K * K);
@@ -73,6 +76,8 @@ int orc_spd_inv_logdet(int64_t K, const double *A, double *Ainv, double *logdet)
     free(e);
     return 0;
 }
+
+#endif /* ORC_CTM_HELPERS_ONLY */
 
 /* CTM.jl:175-178  update_phi!: phi = additive_logistic(log.(beta[:,terms]) .+ lambda[d], dims=1) (utils.jl:114-123) */
 static void ctm_update_phi(int64_t K, int64_t Nd, const int64_t *terms, const double *beta, const double *lambda_d, double *phi)
@@ -144,6 +149,7 @@ static void ctm_update_lambda(int64_t K, int64_t Nd, const int64_t *counts, doub
     }
 }
 
+#ifndef ORC_CTM_HELPERS_ONLY
 typedef struct {
     double *phi, *phic, *grad, *H;
 } ctm_ws;
@@ -344,3 +350,4 @@ int orc_ctm_train(int64_t K, int64_t M, int64_t V, const int64_t *N_cumsum, cons
     if (iters_done) *iters_done = k_done;
     return 0;
 }
+#endif /* ORC_CTM_HELPERS_ONLY */

@@ -562,3 +562,95 @@ class FLDATwin(LDATwin):
                 if delta < tol:
                     break
         return np.array(trace)
+
+
+class FCTMTwin(CTMTwin):
+    """src/fCTM.jl, line for line (filtered CTM: CTM + per-token tau, corpus distribution kappa; eta stays at its initial value,
+    update_eta! being commented out of the training loop, fCTM.jl:279)."""
+
+    def __init__(self, N_cumsum, terms, counts, K, V, beta, kappa, eta=0.5):
+        super().__init__(N_cumsum, terms, counts, K, V, beta)
+        self.eta = float(eta)
+        self.kappa = np.array(kappa, dtype=np.float64)
+        self.kappa_old = self.kappa.copy()
+        self.kappa_temp = np.zeros(V)
+        self.tau = np.full(len(self.terms), self.eta)
+        self.tau_old = self.tau.copy()
+
+    def _sl(self, d):
+        return slice(self.off[d], self.off[d + 1])
+
+    def update_phi(self, d):  # fCTM.jl:239-242
+        terms, _ = self._doc(d)
+        self.phi = self._softmax_rows(self.tau[self._sl(d)][:, None] * np.log(self.beta[terms] + EPSILON) + self.lam[d][None, :])
+
+    def update_tau(self, d):  # fCTM.jl:230-235
+        terms, _ = self._doc(d)
+        s = self._sl(d)
+        self.tau_old[s] = self.tau[s]
+        with np.errstate(divide="ignore", over="ignore"):
+            pr = np.prod(self.beta[terms] ** (-self.phi), axis=1)
+            self.tau[s] = self.eta / ((self.eta + (1 - self.eta) * (self.kappa[terms] * pr)) + EPSILON)
+
+    def update_elbo(self):  # fCTM.jl:67-130
+        elbo = 0.0
+        K = self.K
+        _, logdet = np.linalg.slogdet(self.invsigma)
+        for d in range(self.M):
+            terms, counts = self._doc(d)
+            s = self._sl(d)
+            phi = self._softmax_rows(self.tau_old[s][:, None] * np.log(self.beta_old[terms] + EPSILON) + self.lam_old[d][None, :])
+            lam, v, tau = self.lam[d], self.vsq[d], self.tau[s]
+            df = lam - self.mu
+            Elogpeta = 0.5 * (logdet - K * np.log(2 * np.pi) - np.dot(np.diag(self.invsigma), v) - df @ self.invsigma @ df)
+            tc = np.dot(tau, counts)
+            Elogpc = np.log(self.eta**tc * (1 - self.eta) ** (self.C[d] - tc) + EPSILON)
+            Elogpz = np.dot(phi @ lam, counts) - self.C[d] * (np.exp(lam + 0.5 * v - self.logzeta[d]).sum() + self.logzeta[d] - 1)
+            Elogpw = np.sum((phi * np.log(self.beta[terms] + EPSILON)) * (counts * tau)[:, None]) + np.dot(counts * (1 - tau), np.log(self.kappa[terms] + EPSILON))
+            ent_eta = 0.5 * (K * (np.log(2 * np.pi) + 1) + np.log(v).sum())
+            p0 = 1 - tau
+            with np.errstate(divide="ignore", invalid="ignore"):
+                hb = np.where((p0 == 0) | (p0 == 1), 0.0, -(p0 * np.log(p0) + tau * np.log(tau)))
+                plogp = np.where(phi > 0, phi * np.log(phi), 0.0)
+            elbo += Elogpeta + Elogpc + Elogpz + Elogpw + ent_eta + np.dot(counts, hb) - (plogp.sum(axis=1) * counts).sum()
+        self.elbo = elbo
+        return elbo
+
+    def train(self, iter=150, tol=1.0, niter=1000, ntol=None, viter=10, vtol=None, checkelbo=1):  # fCTM.jl:249-290
+        K = self.K
+        ntol = 1.0 / K**2 if ntol is None else ntol
+        vtol = 1.0 / K**2 if vtol is None else vtol
+        trace = [np.nan] * (iter + 1)
+        if checkelbo <= iter:
+            trace[0] = self.update_elbo()
+        for k in range(1, iter + 1):
+            for d in range(self.M):
+                terms, counts = self._doc(d)
+                for _ in range(viter):
+                    self.update_phi(d)
+                    self.update_tau(d)
+                    self.update_logzeta(d)
+                    self.update_lambda(d, niter, ntol)
+                    self.update_vsq(d, niter, ntol)
+                    if np.linalg.norm(self.lam[d] - self.lam_old[d]) < vtol:
+                        break
+                t = self.tau[self._sl(d)]
+                self.beta_temp[terms] += self.phi * (t * counts)[:, None]      # fCTM.jl:175-178
+                self.kappa_temp[terms] += (1 - t) * counts                     # fCTM.jl:162-165
+            self.beta_old = self.beta
+            self.beta = self.beta_temp / self.beta_temp.sum(axis=0, keepdims=True)
+            self.beta_temp = np.zeros((self.V, K))
+            self.kappa_old = self.kappa
+            self.kappa = self.kappa_temp / self.kappa_temp.sum()
+            self.kappa_temp = np.zeros(self.V)
+            dl = self.lam - self.mu[None, :]                                   # update_sigma! with the old mu
+            self.sigma = (np.diag(self.vsq.sum(axis=0)) + dl.T @ dl) / self.M
+            self.invsigma = np.linalg.inv(self.sigma)
+            self.mu = self.lam.sum(axis=0) / self.M
+            if k % checkelbo == 0:
+                old = self.elbo
+                delta = self.update_elbo() - old
+                trace[k] = self.elbo
+                if delta < tol:
+                    break
+        return np.array(trace)

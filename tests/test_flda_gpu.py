@@ -142,3 +142,68 @@ def test_flda_nsf_size_parity(tm, orc):
     assert np.all(rel < ELBO_RTOL)
     assert abs(model.eta - st.eta[0]) < 1e-4
     tm.check_model(model)
+
+
+# ---- filtered CTM (gpufCTM, fCTM.jl) -------------------------------------------------------------------------------------------
+def _run_pair_fctm(tm, orc, c, K, iters, nthreads=1):
+    beta0, kappa0 = _init(tm, c, K)
+    model = tm.gpufCTM(tm.Corpus.from_csr(c), K)
+    model.beta = np.array(beta0.T, order="F", copy=True)
+    model.kappa = kappa0.copy()
+    trace = []
+    tm.train(model, iter=iters, tol=0.0, checkelbo=1, printelbo=False, trace=trace)
+    st = orc.FCTMState(K, c.M, c.V, len(c.terms), beta0, kappa0)
+    ref, sweeps, done = orc.fctm_train(st, c.N_cumsum, c.terms, c.counts, iter=iters, tol=0.0, nthreads=nthreads)
+    return model, np.array(trace), st, ref[np.isfinite(ref)], sweeps
+
+
+@pytest.mark.parametrize("K", [5, 1, 3, 8, 30, 64, 100])
+def test_fctm_elbo_trajectory_small(tm, orc, K):
+    c = tm.synth.gencorp_lda(M=60, V=250, K=4, seed=K + 1)
+    model, trace, st, ref, sweeps = _run_pair_fctm(tm, orc, c, K, iters=4)
+    n = min(len(trace), len(ref))
+    assert n >= 3 and (K == 1 or n == 5)
+    np.testing.assert_allclose(trace[:n], ref[:n], rtol=ELBO_RTOL)
+    if n < 5:
+        return
+    assert model.eta == 0.5                                   # update_eta! is commented out of the loop (fCTM.jl:279)
+    np.testing.assert_allclose(model.kappa, st.kappa, rtol=5e-3, atol=1e-7)
+    np.testing.assert_allclose(model.beta.T, st.beta, rtol=2e-2, atol=1e-5)
+    np.testing.assert_allclose(model.mu, st.mu, rtol=5e-3, atol=5e-4)
+    np.testing.assert_allclose(model.sigma, st.sigma, rtol=5e-3, atol=5e-4)
+    np.testing.assert_allclose(model.lam.T, st.lam, rtol=5e-3, atol=5e-3)
+    np.testing.assert_allclose(model.lam_old.T, st.lam_old, rtol=5e-3, atol=5e-3)
+    np.testing.assert_allclose(model.vsq.T, st.vsq, rtol=5e-3, atol=1e-5)
+    np.testing.assert_allclose(model.logzeta, st.logzeta, rtol=2e-3, atol=2e-3)
+    np.testing.assert_allclose(model.tau, st.tau, rtol=5e-3, atol=1e-5)
+    np.testing.assert_allclose(model.tau_old, st.tau_old, rtol=5e-3, atol=1e-5)
+    tm.check_model(model)
+    assert abs(model.stats().sweeps - int(sweeps[-1])) <= max(3, 0.02 * sweeps[-1])
+
+
+def test_fctm_citeulike_size_parity(tm, orc):
+    """CiteULike-size filtered CTM, K = 30: ELBO within 1e-4 relative of the CPU oracle (all host threads) at every iteration."""
+    c = tm.synth.load_packed("citeu") or tm.synth.citeu_shaped()
+    c = tm.synth.CSR(c.M, c.V, c.N_cumsum, c.terms, c.counts)      # the reader lists play no part
+    model, trace, st, ref, sweeps = _run_pair_fctm(tm, orc, c, 30, iters=2, nthreads=orc.host_threads())
+    rel = np.abs(trace - ref) / np.abs(ref)
+    stt = model.stats()
+    print("CiteULike-size fCTM ELBO gpu   ", trace.tolist())
+    print("CiteULike-size fCTM ELBO oracle", ref.tolist())
+    print("rel diff", rel.tolist(), "estep_ms %.3f sweeps/doc %.2f" % (stt.estep_ms, stt.sweeps / c.M))
+    assert np.all(rel < ELBO_RTOL)
+    tm.check_model(model)
+
+
+def test_fctm_argument_errors(tm):
+    c = tm.synth.gencorp_lda(M=10, V=50, K=3, seed=0)
+    m = tm.gpufCTM(tm.Corpus.from_csr(c), 3)
+    m.eta = -0.1
+    with pytest.raises(tm.TopicModelError, match="eta must belong"):
+        tm.train(m, iter=1, printelbo=False)
+    m = tm.gpufCTM(tm.Corpus.from_csr(c), 3)
+    m.tau = np.full(len(c.terms), 2.0, np.float32)
+    with pytest.raises(tm.TopicModelError, match="tau must contain probabilities"):
+        tm.train(m, iter=1, printelbo=False)
+    with pytest.raises(ValueError, match="K <= 128"):
+        tm.train(tm.gpufCTM(tm.Corpus.from_csr(c), 129), iter=1, printelbo=False)

@@ -247,3 +247,28 @@ def test_flda_c_oracle_equals_numpy_twin(orc):
     st = orc.FLDAState(5, c.M, c.V, len(c.terms), tm.synth.init_beta(5, c.V, seed=7), kappa)
     t, _, done = orc.flda_train(st, c.N_cumsum, c.terms, c.counts, iter=6, tol=1e12, checkelbo=2)
     assert done == 2 and np.isfinite(t[[0, 2]]).all() and np.isnan(t[1])
+
+
+def test_fctm_c_oracle_equals_numpy_twin(orc):
+    """oracle/fctm_oracle.c == the literal NumPy transcription of src/fCTM.jl (FCTMTwin)."""
+    import topicmodelsvb_b200 as tm
+    from oracle.numpy_twin import FCTMTwin
+
+    c = tm.synth.gencorp_lda(M=30, V=100, K=4, seed=3)
+    kappa = np.random.default_rng(1).dirichlet(np.ones(c.V))
+    for K in (1, 4):
+        beta0 = tm.synth.init_beta(K, c.V, seed=7)
+        tw = FCTMTwin(c.N_cumsum, c.terms, c.counts, K, c.V, beta0, kappa)
+        t1 = tw.train(iter=3, tol=0.0)
+        st = orc.FCTMState(K, c.M, c.V, len(c.terms), beta0, kappa)
+        t2, sweeps, done = orc.fctm_train(st, c.N_cumsum, c.terms, c.counts, iter=3, tol=0.0)
+        assert done == 3
+        np.testing.assert_allclose(t2, t1, rtol=1e-11)
+        np.testing.assert_allclose(st.tau, tw.tau, rtol=1e-9, atol=1e-14)
+        np.testing.assert_allclose(st.lam, tw.lam, rtol=1e-8, atol=1e-10)
+        np.testing.assert_allclose(st.vsq, tw.vsq, rtol=1e-8)
+        np.testing.assert_allclose(st.kappa, tw.kappa, rtol=1e-9)
+        np.testing.assert_allclose(st.sigma, tw.sigma, rtol=1e-8, atol=1e-12)
+        st4 = orc.FCTMState(K, c.M, c.V, len(c.terms), beta0, kappa)
+        t4, _, _ = orc.fctm_train(st4, c.N_cumsum, c.terms, c.counts, iter=3, tol=0.0, nthreads=4)
+        np.testing.assert_allclose(t4, t2, rtol=1e-11)

@@ -5,7 +5,7 @@ include/tmvb.h); this package is the host-side mirror of the reference's Julia A
 from . import _lib, synth  # noqa: F401
 from ._lib import TopicModelError, build  # noqa: F401
 from .corpus import Corpus, CorpusError, Document, DocumentError, readcorp  # noqa: F401
-from .gpu_ctm import check_model_ctm, gpuCTM, train_ctm  # noqa: F401
+from .gpu_ctm import check_model_ctm, gpuCTM, gpufCTM, train_ctm  # noqa: F401
 from .gpu_ctpf import check_model_ctpf, gpuCTPF, train_ctpf  # noqa: F401
 from .gpu_flda import check_model_flda, gpufLDA, train_flda  # noqa: F401
 from .gpu_lda import check_elbo, gpuLDA  # noqa: F401

@@ -19,6 +19,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include "tmvb_filt.cuh"
 #include "tmvb_shard.cuh"
 
 namespace tmvb {
@@ -35,6 +36,9 @@ struct CtmDev {
     const float *mu;        // [K_ld]
     const float *invsigma;  // [K][KP] row-major, KP = 4 (mod 8)
     double *small;          // [0] per-document ELBO terms, [1] sweep counter
+    // filtered CTM (fCTM.jl) only: log2 table of beta, (1 - eta) kappa | eta, update_kappa! statistics, per-token tau / tau_old
+    const float *L, *kq;
+    float *kstats, *tau, *tau_old;
     int niter;
     float ntol;
     int viter;
@@ -53,12 +57,6 @@ static int ctm_kp(int K)
 // in-warp Cholesky chains, so what counts is how many documents an SM holds, i.e. shared memory per warp)
 static size_t ctm_fixed_smem(int RS, int lpt, int K, int K_ld) { return 16 + (size_t)(32 / lpt) * RS * 4 + (size_t)RS * 4 + (size_t)K * ctm_kp(K) * 4 + (size_t)2 * K_ld * 4; }
 
-__device__ __forceinline__ float warp_max(float v)
-{
-#pragma unroll
-    for (int m = 16; m > 0; m >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, m));
-    return v;
-}
 
 // entry j of a vector distributed over the warp as v[r] on lane l for j = l + 32 r
 template <int R>
@@ -393,6 +391,351 @@ __global__ void __launch_bounds__(32, TMVB_CTM_MIN_CTAS) ctm_estep_kernel(const 
     if (lane == 0 && sweeps_thr) atomicAdd(p.small + 1, (double)sweeps_thr);
 }
 
+// ------------------------------------------------------------------ filtered CTM (src/fCTM.jl) ----------
+// The inner loop of train!(::fCTM) (fCTM.jl:258-268): update_phi!, update_tau!, update_logzeta!, update_lambda!, update_vsq! -- in
+// THAT order (lambda before vsq, unlike CTM.jl:196-199) -- with the filtered token pass of tmvb_filt.cuh: phi = softmax_i(tau_n
+// log2(beta + eps) + (lambda_i - max lambda) log2 e) from the log2 table p.L, update_tau! fused, tau / tau_old in global memory
+// (L2-resident between sweeps; the tile holds 16 rows only, as in ctm_estep_kernel).  The Newton iterations and the Cholesky
+// solve are those of ctm_estep_kernel.  Scatter: phi tau c into the statistics (fCTM.jl:175-178), (1 - tau) c into kstats
+// (fCTM.jl:162-165).  The ELBO comes from fctm_elbo_kernel (no fused partials).
+template <int LPT, int CPL>
+__global__ void __launch_bounds__(32, 8) fctm_estep_kernel(const CtmDev p, int doc_begin, int doc_end, int cap, int cap2, int *counter)
+{
+    constexpr int S = 32 / LPT;
+    constexpr int R = (LPT * CPL + 7) / 8;
+    static_assert(R <= 4, "fCTM supports K <= 128");
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x;
+    const int kl = lane % LPT, ts = lane / LPT;
+    const int K = p.K, K_ld = p.K_ld, CH = K_ld >> 2, RS = p.RS, KP = p.KP;
+    (void)cap2;
+    unsigned long long *mbar = reinterpret_cast<unsigned long long *>(smem_raw);
+    float *gs = reinterpret_cast<float *>(smem_raw + 16);  // [S][RS]
+    float *e_s = gs + (size_t)S * RS;                      // [RS]
+    float *L_s = e_s + RS;                                 // [K][KP]
+    const float *inv_s = p.invsigma;
+    float *vec_s = L_s + K * KP;                           // [K_ld]
+    float *dinv_s = vec_s + K_ld;                          // [K_ld]
+    float *tile = dinv_s + K_ld;                           // [cap][RS]
+    float *cnt_s = tile + (size_t)cap * RS;
+    int *term_s = reinterpret_cast<int *>(cnt_s + cap);
+
+    float mu_k[R], isd_k[R];
+#pragma unroll
+    for (int r = 0; r < R; r++) {
+        const int i = lane + 32 * r;
+        mu_k[r] = (i < K) ? p.mu[i] : 0.0f;
+        isd_k[r] = (i < K) ? p.invsigma[i * KP + i] : 1.0f;
+    }
+    const float eta = __ldg(p.kq + p.V);
+    unsigned long long sweeps_thr = 0;
+    unsigned phase = 0;
+    if (lane == 0) mbar_init(mbar, 1);
+    __syncwarp();
+
+    for (;;) {
+        int d = 0;
+        if (lane == 0) d = doc_begin + atomicAdd(counter, 1);
+        d = __shfl_sync(0xffffffffu, d, 0);
+        if (d >= doc_end) break;
+        const long long o = p.doc_off[d];
+        const int Nd = (int)(p.doc_off[d + 1] - o);
+        const int ns = min(Nd, cap);
+        const int rounds = (Nd + S - 1) / S;
+
+        __syncwarp();
+        float csum = 0.0f;
+        for (int n = lane; n < Nd; n += 32) {
+            const float c = p.counts[o + n];
+            csum += c;
+            if (n < ns) {
+                term_s[n] = p.terms[o + n];
+                cnt_s[n] = c;
+            }
+        }
+        stage_rows(tile, term_s, p.L, ns, K_ld, RS, lane, mbar, 1);
+        float lam_k[R], lold_k[R], vsq_k[R], phic_k[R];
+#pragma unroll
+        for (int r = 0; r < R; r++) {
+            const int i = lane + 32 * r;
+            lam_k[r] = (i < K) ? p.lambda[(size_t)d * K_ld + i] : 0.0f;
+            vsq_k[r] = (i < K) ? p.vsq[(size_t)d * K_ld + i] : 1.0f;
+            lold_k[r] = lam_k[r];
+            phic_k[r] = 0.0f;
+        }
+        const float Cd = warp_sum(csum);
+        stage_wait(mbar, phase, 1);
+
+        float logzeta = 0.0f;
+        int v = 0;
+        for (;;) {
+            // ---- update_phi! (fCTM.jl:239-242) + update_tau! (fCTM.jl:230-235)
+            float lmax = -INFINITY;
+#pragma unroll
+            for (int r = 0; r < R; r++)
+                if (lane + 32 * r < K) lmax = fmaxf(lmax, lam_k[r]);
+            lmax = warp_max(lmax);
+            __syncwarp();
+#pragma unroll
+            for (int r = 0; r < R; r++) {
+                const int i = lane + 32 * r;
+                if (i < K_ld) e_s[i] = (i < K) ? (lam_k[r] - lmax) * kLog2e : kPadE;
+            }
+            __syncwarp();
+            f32x2 E01[CPL], E23[CPL], g01[CPL], g23[CPL];
+#pragma unroll
+            for (int m = 0; m < CPL; m++) {
+                const bool in = kl + LPT * m < CH;
+                const float4 E = in ? reinterpret_cast<const float4 *>(e_s)[kl + LPT * m] : make_float4(kPadE, kPadE, kPadE, kPadE);
+                E01[m] = pk2(E.x, E.y);
+                E23[m] = pk2(E.z, E.w);
+                g01[m] = g23[m] = 0ull;
+            }
+            for (int r = 0; r < rounds; r++) {
+                const int n = r * S + ts;
+                const bool ok = n < Nd;
+                const int nn = ok ? n : 0;
+                const bool in_tile = nn < cap;
+                const int term = in_tile ? term_s[nn] : __ldg(p.terms + o + nn);
+                ulonglong2 b[CPL];
+                flda_load_row<LPT, CPL>(tile, p.L, RS, K_ld, CH, nn, cap, term, kl, b);
+                const float c = ok ? (in_tile ? cnt_s[nn] : __ldg(p.counts + o + nn)) : 0.0f;
+                const float tau = __ldcg(p.tau + o + nn);
+                f32x2 p01[CPL], p23[CPL];
+                float sn, q;
+                flda_row<CPL>(b, E01, E23, tau, p01, p23, sn, q);
+                sn = group_sum<LPT>(sn);
+                q = group_sum<LPT>(q);
+                const float rs = rcp_ftz(sn);
+                const float t = c * rs;
+                const f32x2 t2 = pk2(t, t);
+#pragma unroll
+                for (int m = 0; m < CPL; m++) {
+                    g01[m] = fma2(p01[m], t2, g01[m]);
+                    g23[m] = fma2(p23[m], t2, g23[m]);
+                }
+                if (ok && kl == 0) {
+                    const float den = (eta + __ldg(p.kq + term) * ex2_ftz(-q * rs)) + TMVB_EPS;
+                    __stcg(p.tau_old + o + nn, tau);
+                    __stcg(p.tau + o + nn, fast_div_pos(eta, den));
+                }
+            }
+#pragma unroll
+            for (int m = 0; m < CPL; m++)
+                if (kl + LPT * m < CH) {
+                    float4 gv;
+                    unpk2(g01[m], gv.x, gv.y);
+                    unpk2(g23[m], gv.z, gv.w);
+                    reinterpret_cast<float4 *>(gs + (size_t)ts * RS)[kl + LPT * m] = gv;
+                }
+            __syncwarp();
+#pragma unroll
+            for (int r = 0; r < R; r++) {
+                const int i = lane + 32 * r;
+                phic_k[r] = (i < K) ? owner_sum<S>(gs, RS, i) : 0.0f;
+            }
+
+            // ---- update_logzeta! (fCTM.jl:224-226)
+            float zmax = -INFINITY;
+#pragma unroll
+            for (int r = 0; r < R; r++)
+                if (lane + 32 * r < K) zmax = fmaxf(zmax, fmaf(0.5f, vsq_k[r], lam_k[r]));
+            zmax = warp_max(zmax);
+            float zs = 0.0f;
+#pragma unroll
+            for (int r = 0; r < R; r++)
+                if (lane + 32 * r < K) zs += __expf(fmaf(0.5f, vsq_k[r], lam_k[r]) - zmax);
+            logzeta = zmax + logf(warp_sum(zs));
+
+            // ---- update_lambda! (fCTM.jl:181-196)
+#pragma unroll
+            for (int r = 0; r < R; r++) lold_k[r] = lam_k[r];
+            for (int it = 0; it < p.niter; it++) {
+                float w_k[R], grad_k[R];
+                __syncwarp();
+#pragma unroll
+                for (int r = 0; r < R; r++) {
+                    const int i = lane + 32 * r;
+                    w_k[r] = (i < K) ? Cd * __expf(fmaf(0.5f, vsq_k[r], lam_k[r]) - logzeta) : 0.0f;
+                    if (i < K_ld) vec_s[i] = (i < K) ? mu_k[r] - lam_k[r] : 0.0f;
+                }
+                __syncwarp();
+                float gn = 0.0f;
+#pragma unroll
+                for (int r = 0; r < R; r++) {
+                    const int i = lane + 32 * r;
+                    grad_k[r] = 0.0f;
+                    if (i < K) {
+                        float a0 = 0.0f, a1 = 0.0f;
+                        const float4 *row = reinterpret_cast<const float4 *>(inv_s + i * KP);
+                        const float4 *vv = reinterpret_cast<const float4 *>(vec_s);
+                        for (int c = 0; c < (K + 3) >> 2; c++) {
+                            const float4 a = row[c], b = vv[c];
+                            a0 = fmaf(a.x, b.x, a0);
+                            a1 = fmaf(a.y, b.y, a1);
+                            a0 = fmaf(a.z, b.z, a0);
+                            a1 = fmaf(a.w, b.w, a1);
+                        }
+                        grad_k[r] = (a0 + a1) + phic_k[r] - w_k[r];
+                        gn = fmaf(grad_k[r], grad_k[r], gn);
+                    }
+                }
+                gn = warp_sum(gn);
+                warp_cholesky<R>(inv_s, L_s, dinv_s, w_k, K, KP, lane);
+                warp_chol_solve<R>(L_s, dinv_s, grad_k, K, KP, lane);
+#pragma unroll
+                for (int r = 0; r < R; r++)
+                    if (lane + 32 * r < K) lam_k[r] += grad_k[r];
+                if (sqrtf(gn) < p.ntol) break;
+            }
+
+            // ---- update_vsq! (fCTM.jl:200-219)
+#pragma unroll
+            for (int r = 0; r < R; r++) {
+                bool active = lane + 32 * r < K;
+                for (int it = 0; it < p.niter; it++) {
+                    if (active) {
+                        float rho = 1.0f;
+                        const float ex = Cd * __expf(fmaf(0.5f, vsq_k[r], lam_k[r]) - logzeta);
+                        const float grad = -0.5f * (isd_k[r] + ex - 1.0f / vsq_k[r]);
+                        const float invhess = -1.0f / (0.25f * ex + 0.5f / (vsq_k[r] * vsq_k[r]));
+                        const float pp = invhess * grad;
+                        while (vsq_k[r] - rho * pp <= 0.0f) rho *= 0.5f;
+                        vsq_k[r] -= rho * pp;
+                        if (rho * fabsf(grad) < p.ntol) active = false;
+                    }
+                    if (!__any_sync(0xffffffffu, active)) break;
+                }
+                vsq_k[r] += TMVB_EPS;
+            }
+            float dl = 0.0f;
+#pragma unroll
+            for (int r = 0; r < R; r++)
+                if (lane + 32 * r < K) dl = fmaf(lam_k[r] - lold_k[r], lam_k[r] - lold_k[r], dl);
+            dl = warp_sum(dl);
+            v++;
+            if (sqrtf(dl) < p.vtol || v >= p.viter) break;  // fCTM.jl:264
+        }
+
+        // update_beta!(model, d), update_kappa!(model, d): the last phi from (tau_old, e_s = the lambda it was computed from)
+        if (!(p.dbg & 1)) {
+            f32x2 E01[CPL], E23[CPL];
+#pragma unroll
+            for (int m = 0; m < CPL; m++) {
+                const bool in = kl + LPT * m < CH;
+                const float4 E = in ? reinterpret_cast<const float4 *>(e_s)[kl + LPT * m] : make_float4(kPadE, kPadE, kPadE, kPadE);
+                E01[m] = pk2(E.x, E.y);
+                E23[m] = pk2(E.z, E.w);
+            }
+            for (int r = 0; r < rounds; r++) {
+                const int n = r * S + ts;
+                const bool ok = n < Nd;
+                const int nn = ok ? n : 0;
+                const bool in_tile = nn < cap;
+                const int term = in_tile ? term_s[nn] : __ldg(p.terms + o + nn);
+                ulonglong2 b[CPL];
+                flda_load_row<LPT, CPL>(tile, p.L, RS, K_ld, CH, nn, cap, term, kl, b);
+                const float c = in_tile ? cnt_s[nn] : __ldg(p.counts + o + nn);
+                const float tauo = __ldcg(p.tau_old + o + nn), tauf = __ldcg(p.tau + o + nn);
+                f32x2 p01[CPL], p23[CPL];
+                float sn, q;
+                flda_row<CPL>(b, E01, E23, tauo, p01, p23, sn, q);
+                sn = group_sum<LPT>(sn);
+                if (ok) {
+                    const float w = tauf * c * rcp_ftz(sn);
+                    const f32x2 w2 = pk2(w, w);
+                    float *srow = p.stats + (size_t)term * K_ld + 4 * kl;
+#pragma unroll
+                    for (int m = 0; m < CPL; m++)
+                        if (4 * (kl + LPT * m) < K) {
+                            float px, py, pz, pw;
+                            unpk2(mul2(p01[m], w2), px, py);
+                            unpk2(mul2(p23[m], w2), pz, pw);
+                            red_add_v4(srow + 4 * LPT * m, px, py, pz, pw);
+                        }
+                    if (kl == 0) red_add(p.kstats + term, (1.0f - tauf) * c);
+                }
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < R; r++) {
+            const int i = lane + 32 * r;
+            if (i < K_ld) {
+                const bool ok = i < K;
+                p.lambda[(size_t)d * K_ld + i] = ok ? lam_k[r] : 0.0f;
+                p.lambda_old[(size_t)d * K_ld + i] = ok ? lold_k[r] : 0.0f;
+                p.vsq[(size_t)d * K_ld + i] = ok ? vsq_k[r] : 0.0f;
+            }
+        }
+        if (lane == 0) {
+            p.logzeta[d] = logzeta;
+            sweeps_thr += (unsigned long long)v;
+        }
+    }
+    if (lane == 0 && sweeps_thr) atomicAdd(p.small + 1, (double)sweeps_thr);
+}
+
+// update_elbo! (fCTM.jl:67-130), literally, one warp per document, lane = topic: the lagged phi from (tau_old, beta_old, lambda_old)
+// (fCTM.jl:125), everything else current.  L_old / p.L are the log2 tables of beta_old / beta.
+__global__ void fctm_elbo_kernel(const CtmDev p, const float *__restrict__ L_old, const float *__restrict__ kappa, double ln_eta, double ln_1m_eta,
+                                 double *out)
+{
+    const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+    const int K = p.K, KP = p.KP;
+    double acc = 0.0;
+    for (long long d = (long long)blockIdx.x * wpb + (threadIdx.x >> 5); d < p.M; d += (long long)gridDim.x * wpb) {
+        const long long o = p.doc_off[d];
+        const int Nd = (int)(p.doc_off[d + 1] - o);
+        const float *lam = p.lambda + d * p.K_ld, *lo = p.lambda_old + d * p.K_ld, *vs = p.vsq + d * p.K_ld;
+        const float lz = p.logzeta[d];
+        float lmax = -INFINITY;
+        for (int i = lane; i < K; i += 32) lmax = fmaxf(lmax, lo[i]);
+        lmax = warp_max(lmax);
+        double dacc = 0.0;
+        float Cd = 0.0f, tc = 0.0f;
+        for (int n = 0; n < Nd; n++) {
+            const int term = p.terms[o + n];
+            const float c = p.counts[o + n], tau = p.tau[o + n], tauo = p.tau_old[o + n];
+            Cd += c;
+            tc = fmaf(tau, c, tc);
+            const float *bo = L_old + (size_t)term * p.K_ld, *bn = p.L + (size_t)term * p.K_ld;
+            float s = 0.0f;
+            for (int i = lane; i < K; i += 32) s += ex2_ftz(fmaf(tauo, bo[i], (lo[i] - lmax) * kLog2e));
+            s = warp_sum(s);
+            const float l2s = lg2_ftz(s);
+            float a = 0.0f;
+            for (int i = lane; i < K; i += 32) {
+                const float x = fmaf(tauo, bo[i], (lo[i] - lmax) * kLog2e);
+                const float ph = ex2_ftz(x) / s;
+                // phi (lambda_i + tau ln(beta_i + eps) - ln phi),  ln phi = ln 2 (x - log2 s)
+                if (ph > 0.0f) a += ph * (lam[i] + kLn2 * (tau * bn[i] - (x - l2s)));
+            }
+            a = warp_sum(a);
+            a = fmaf(1.0f - tau, logf(kappa[term] + TMVB_EPS), a);          // corpus part of Elogpw, fCTM.jl:90
+            const float t0 = 1.0f - tau;
+            if (t0 != 0.0f && t0 != 1.0f) a -= t0 * logf(t0) + tau * logf(tau);   // -Elogqc, fCTM.jl:101-105
+            if (lane == 0) dacc += (double)(c * a);
+        }
+        float q = 0.0f, se = 0.0f, lv = 0.0f, dv = 0.0f;
+        for (int i = lane; i < K; i += 32) {
+            float t = 0.0f;
+            for (int j = 0; j < K; j++) t += p.invsigma[i * KP + j] * (lam[j] - p.mu[j]);
+            q += (lam[i] - p.mu[i]) * t;
+            dv += p.invsigma[i * KP + i] * vs[i];
+            se += expf(lam[i] + 0.5f * vs[i] - lz);
+            lv += logf(vs[i]);
+        }
+        dacc += (double)(-0.5f * (dv + q) + 0.5f * lv);
+        dacc = warp_sum_d(dacc);
+        se = warp_sum(se);
+        if (lane == 0) {
+            const double elogpc = log(exp((double)tc * ln_eta + ((double)Cd - (double)tc) * ln_1m_eta) + TMVB_EPS_D);   // fCTM.jl:73-77
+            acc += dacc - (double)Cd * ((double)se + (double)lz - 1.0) + elogpc;
+        }
+    }
+    if (lane == 0 && acc != 0.0) atomicAdd(out, acc);
+}
+
 // Second moments for update_sigma!/update_mu! (CTM.jl:102-111): mom = [sum lambda (K_ld) | sum vsq (K_ld) | sum lambda lambda' (K x K)]
 template <int NQ>   // pairs per thread: K*K <= 256 NQ
 __global__ void ctm_moments_kernel(const float *__restrict__ lambda, const float *__restrict__ vsq, long long M, int K, int K_ld, double *__restrict__ mom)
@@ -522,6 +865,21 @@ static CtmEstepFn ctm_fn(int layout, int elbo)
     return tab[layout][elbo];
 }
 
+template <int L, int C, bool OK = ((L * C + 7) / 8 <= 4)>
+struct FctmPick {
+    static CtmEstepFn get() { return (CtmEstepFn)fctm_estep_kernel<L, C>; }
+};
+template <int L, int C>
+struct FctmPick<L, C, false> {
+    static CtmEstepFn get() { return nullptr; }
+};
+#define TMVB_FCTM_FN(L, C) FctmPick<L, C>::get(),
+static CtmEstepFn fctm_fn(int layout)
+{
+    static const CtmEstepFn tab[kNumLaneLayouts] = {TMVB_FOR_EACH_LAYOUT(TMVB_FCTM_FN)};
+    return tab[layout];
+}
+
 // in-place inverse and log-determinant of an SPD matrix (fp64, host): inv(sigma), logdet (CTM.jl:57,110)
 static int spd_inv_logdet(int K, std::vector<double> &A, double *logdet)
 {
@@ -576,6 +934,12 @@ struct tmvb_ctm_s {
     double *d_local = nullptr;  // [K_ld] rowsum | [K_ld] elbo_w | [1] standalone ELBO
     std::vector<double> h_mom;  // host copy of the (reduced) moments of the last E-step
     int64_t n_small = 0;
+    // filtered CTM (tmvb_fctm_*): fCTM.jl's eta / kappa / tau on top of the CTM state
+    bool filtered = false, filt_set = false;
+    double eta = 0.5;
+    float *d_L[2] = {nullptr, nullptr}, *d_kappa = nullptr, *d_kappa_old = nullptr, *d_kstats = nullptr, *d_kq = nullptr;
+    float *d_tau = nullptr, *d_tau_old = nullptr;
+    size_t tau_cap = 0;
 };
 
 namespace {
@@ -603,6 +967,11 @@ CtmDev ctm_view(tmvb_ctm_t h)
     p.mu = h->d_mu;
     p.invsigma = h->d_invsigma;
     p.small = h->d_small;
+    p.L = h->d_L[s.cur];
+    p.kq = h->d_kq;
+    p.kstats = h->d_kstats;
+    p.tau = h->d_tau;
+    p.tau_old = h->d_tau_old;
     p.niter = 0;
     p.ntol = 0.f;
     p.viter = 0;
@@ -624,6 +993,14 @@ void ctm_free(tmvb_ctm_t h)
     cudaFree(h->d_invsigma);
     cudaFree(h->d_small);
     cudaFree(h->d_local);
+    cudaFree(h->d_L[0]);
+    cudaFree(h->d_L[1]);
+    cudaFree(h->d_kappa);
+    cudaFree(h->d_kappa_old);
+    cudaFree(h->d_kstats);
+    cudaFree(h->d_kq);
+    cudaFree(h->d_tau);
+    cudaFree(h->d_tau_old);
     shard_free(&h->s);
 }
 
@@ -741,6 +1118,10 @@ int tmvb_ctm_upload(tmvb_ctm_t h, const float *mu, const float *sigma, const flo
     if (beta && s.V > 0) {
         TMVB_TRY(shard_upload_rows(&s, beta, s.d_beta[s.cur], s.V, nullptr, 0));
         TMVB_CUDA(cudaMemcpyAsync(s.d_beta[s.cur ^ 1], s.d_beta[s.cur], (size_t)s.V * s.K_ld * 4, cudaMemcpyDeviceToDevice, s.stream));  // CTM.jl:42
+        if (h->filtered) {
+            TMVB_TRY(filt_log_table(&s, s.d_beta[0], h->d_L[0]));
+            TMVB_TRY(filt_log_table(&s, s.d_beta[1], h->d_L[1]));
+        }
     }
     if ((lambda || vsq || logzeta) && s.M > 0) {
         TMVB_CHECK_ARG(s.corpus_set, "set_corpus must precede the upload of per-document parameters");
@@ -784,7 +1165,12 @@ int tmvb_ctm_estep(tmvb_ctm_t h, int niter, float ntol, int viter, float vtol, i
     p.vtol = vtol;
     TMVB_CUDA(cudaEventRecord(s.ev[0], s.stream));
     TMVB_CUDA(cudaMemsetAsync(h->d_small, 0, h->n_small * 8, s.stream));
-    const void *fns[2] = {(const void *)ctm_fn(s.layout, want_elbo != 0), (const void *)ctm_fn(s.layout, want_elbo != 0)};
+    if (h->filtered) {
+        TMVB_CHECK_ARG(h->filt_set, "tmvb_fctm_upload has not been called");
+        want_elbo = 0;   // the filtered ELBO is evaluated by fctm_elbo_kernel (tmvb_ctm_elbo), not from fused partials
+    }
+    const void *fn = h->filtered ? (const void *)fctm_fn(s.layout) : (const void *)ctm_fn(s.layout, want_elbo != 0);
+    const void *fns[2] = {fn, fn};
     TMVB_TRY(shard_launch(&s, pick_by_warps, fns, &p, sizeof(p)));
     if (s.M > 0) {
         const int grid = (int)std::min<int64_t>((s.M + 31) / 32, (int64_t)s.n_sm * 4);
@@ -828,6 +1214,11 @@ int tmvb_ctm_mstep(tmvb_ctm_t h, int64_t M_total)
     TMVB_CUDA(cudaSetDevice(s.device));
     TMVB_CUDA(cudaEventRecord(s.ev[2], s.stream));
     TMVB_TRY(shard_normalize(&s, h->d_local, h->elbo_valid, false));  // update_beta! CTM.jl:114-118
+    if (h->filtered) {   // the log2 table of the new beta; update_kappa!(model) (fCTM.jl:154-158)
+        TMVB_TRY(filt_log_table(&s, s.d_beta[s.cur], h->d_L[s.cur]));
+        TMVB_TRY(filt_kappa_update(&s, h->d_kstats, h->d_kappa, h->d_kappa_old));
+        TMVB_TRY(filt_push_kq(&s, h->d_kappa, h->d_kq, h->eta));   // eta is not updated: update_eta! is commented out, fCTM.jl:279
+    }
     TMVB_CUDA(cudaMemcpyAsync(s.h_pinned, h->d_small, h->n_small * 8, cudaMemcpyDeviceToHost, s.stream));
     TMVB_CUDA(cudaStreamSynchronize(s.stream));
     s.st.d2h_bytes += h->n_small * 8;
@@ -864,6 +1255,7 @@ int tmvb_ctm_elbo(tmvb_ctm_t h, int mode, int64_t M_total, double *elbo_docs, do
     const int K = (int)s.K, K_ld = s.K_ld;
     const double Md = (double)M_total;
     const double LOG2PI = 1.8378770664093453;
+    if (h->filtered) mode = 1;
     if (mode == 0) {
         TMVB_CHECK_ARG(h->elbo_valid, "mode 0 needs estep(want_elbo=1) followed by mstep");
         TMVB_CUDA(cudaMemcpyAsync(s.h_pinned, h->d_local + K_ld, 8, cudaMemcpyDeviceToHost, s.stream));
@@ -891,7 +1283,10 @@ int tmvb_ctm_elbo(tmvb_ctm_t h, int mode, int64_t M_total, double *elbo_docs, do
     double *out = h->d_local + 2 * K_ld;
     TMVB_CUDA(cudaMemsetAsync(out, 0, 8, s.stream));
     if (s.M > 0) {
-        ctm_elbo_kernel<<<grid_for(s.M * 32, 128, s.n_sm), 128, 0, s.stream>>>(p, s.d_beta[s.cur ^ 1], out);
+        if (h->filtered)
+            fctm_elbo_kernel<<<grid_for(s.M * 32, 128, s.n_sm), 128, 0, s.stream>>>(p, h->d_L[s.cur ^ 1], h->d_kappa, log(h->eta), log1p(-h->eta), out);
+        else
+            ctm_elbo_kernel<<<grid_for(s.M * 32, 128, s.n_sm), 128, 0, s.stream>>>(p, s.d_beta[s.cur ^ 1], out);
         TMVB_CUDA(cudaGetLastError());
         s.st.kernel_launches++;
     }
@@ -964,6 +1359,107 @@ int tmvb_ctm_topics(tmvb_ctm_t h, int32_t *topics)
     TMVB_CHECK_ARG(h && topics, "NULL argument");
     TMVB_CUDA(cudaSetDevice(h->s.device));
     return shard_topics(&h->s, h->s.d_beta[h->s.cur], nullptr, topics);
+}
+
+/* ---- filtered CTM (src/fCTM.jl): a CTM handle with eta / kappa / tau on top; every tmvb_ctm_* call applies to it ---- */
+int tmvb_fctm_create(tmvb_ctm_t *out, int64_t K, int64_t M, int64_t V, int device, void *stream)
+{
+    TMVB_TRY(tmvb_ctm_create(out, K, M, V, device, stream));
+    tmvb_ctm_t h = *out;
+    Shard &s = h->s;
+    h->filtered = true;
+    const size_t kv = (size_t)std::max<int64_t>(V, 1) * s.K_ld, v1 = (size_t)std::max<int64_t>(V, 1);
+    cudaError_t e = cudaSuccess;
+    auto A = [&](void **p, size_t bytes) {
+        if (e == cudaSuccess) e = cudaMalloc(p, bytes);
+        if (e == cudaSuccess) e = cudaMemsetAsync(*p, 0, bytes, s.stream);
+    };
+    A((void **)&h->d_L[0], kv * 4);
+    A((void **)&h->d_L[1], kv * 4);
+    A((void **)&h->d_kappa, v1 * 4);
+    A((void **)&h->d_kappa_old, v1 * 4);
+    A((void **)&h->d_kstats, v1 * 4);
+    A((void **)&h->d_kq, (v1 + 1) * 4);
+    if (e == cudaSuccess && !fctm_fn(s.layout)) {
+        tmvb_ctm_destroy(h);
+        *out = nullptr;
+        return fail(-2, "internal: no fCTM kernel for this K");
+    }
+    if (e == cudaSuccess) e = cudaFuncSetAttribute((const void *)fctm_fn(s.layout), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s.smem_optin);
+    if (e != cudaSuccess) {
+        tmvb_ctm_destroy(h);
+        *out = nullptr;
+        return fail((int)e, "device allocation failed: %s", cudaGetErrorString(e));
+    }
+    return 0;
+}
+
+/* eta, kappa[V], tau[sum N] (the caller's CSR order) of fCTM.jl:10-28; *_old are set to the uploaded values (fCTM.jl:50,59).
+ * Call after tmvb_ctm_set_corpus; any pointer may be NULL. */
+int tmvb_fctm_upload(tmvb_ctm_t h, const double *eta, const float *kappa, const float *tau)
+{
+    TMVB_CHECK_ARG(h != nullptr && h->filtered, "not a filtered-CTM handle");
+    Shard &s = h->s;
+    TMVB_CUDA(cudaSetDevice(s.device));
+    if (eta) {
+        if (!(*eta >= 0.0 && *eta <= 1.0)) return fail(-5, "eta must belong to the interval [0,1].");   // modelutils.jl:104
+        h->eta = *eta;
+    }
+    if (kappa && s.V > 0) {
+        double ks = 0.0;
+        for (int64_t j = 0; j < s.V; j++) {
+            if (!(kappa[j] >= 0.f) || !isfinite(kappa[j])) return fail(-5, "kappa must be a probability vector.");
+            ks += kappa[j];
+        }
+        if (fabs(ks - 1.0) > 1e-3) return fail(-5, "kappa must be a probability vector.");
+        TMVB_CUDA(cudaMemcpyAsync(h->d_kappa, kappa, s.V * 4, cudaMemcpyHostToDevice, s.stream));
+        TMVB_CUDA(cudaMemcpyAsync(h->d_kappa_old, h->d_kappa, s.V * 4, cudaMemcpyDeviceToDevice, s.stream));
+        TMVB_CUDA(cudaStreamSynchronize(s.stream));
+        s.st.h2d_bytes += s.V * 4;
+    }
+    TMVB_TRY(filt_push_kq(&s, h->d_kappa, h->d_kq, h->eta));
+    if (tau) {
+        TMVB_CHECK_ARG(s.corpus_set, "set_corpus must precede the upload of tau");
+        const size_t need = (size_t)std::max<int64_t>(s.nnz, 1);
+        if (need > h->tau_cap) {
+            cudaFree(h->d_tau);
+            cudaFree(h->d_tau_old);
+            h->d_tau = h->d_tau_old = nullptr;
+            h->tau_cap = 0;
+            TMVB_CUDA(cudaMalloc((void **)&h->d_tau, need * 4));
+            TMVB_CUDA(cudaMalloc((void **)&h->d_tau_old, need * 4));
+            h->tau_cap = need;
+        }
+        int terr = 0;
+        TMVB_TRY(filt_tau_upload(&s, tau, h->d_tau, &terr));
+        if (s.nnz > 0) TMVB_CUDA(cudaMemcpyAsync(h->d_tau_old, h->d_tau, (size_t)s.nnz * 4, cudaMemcpyDeviceToDevice, s.stream));
+        if (terr) return fail(-5, "tau must contain probabilities.");
+        h->filt_set = true;
+    }
+    return 0;
+}
+
+int tmvb_fctm_download(tmvb_ctm_t h, float *kappa, float *kappa_old, float *tau, float *tau_old)
+{
+    TMVB_CHECK_ARG(h != nullptr && h->filtered, "not a filtered-CTM handle");
+    Shard &s = h->s;
+    TMVB_CUDA(cudaSetDevice(s.device));
+    if (kappa && s.V > 0) TMVB_CUDA(cudaMemcpyAsync(kappa, h->d_kappa, s.V * 4, cudaMemcpyDeviceToHost, s.stream));
+    if (kappa_old && s.V > 0) TMVB_CUDA(cudaMemcpyAsync(kappa_old, h->d_kappa_old, s.V * 4, cudaMemcpyDeviceToHost, s.stream));
+    s.st.d2h_bytes += ((kappa ? 1 : 0) + (kappa_old ? 1 : 0)) * s.V * 4;
+    if (tau && h->d_tau) TMVB_TRY(filt_tau_download(&s, h->d_tau, tau));
+    if (tau_old && h->d_tau_old) TMVB_TRY(filt_tau_download(&s, h->d_tau_old, tau_old));
+    TMVB_CUDA(cudaStreamSynchronize(s.stream));
+    return 0;
+}
+
+/* the update_kappa! statistics: summed over ranks next to the buffers of tmvb_ctm_reduce_buffers */
+int tmvb_fctm_reduce_buffers(tmvb_ctm_t h, void **kstats, int64_t *n_kstats)
+{
+    TMVB_CHECK_ARG(h != nullptr && h->filtered, "not a filtered-CTM handle");
+    if (kstats) *kstats = h->d_kstats;
+    if (n_kstats) *n_kstats = h->s.V;
+    return 0;
 }
 
 int tmvb_ctm_get_stats(tmvb_ctm_t h, tmvb_stats *out)

@@ -20,6 +20,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include "tmvb_filt.cuh"
 #include "tmvb_shard.cuh"
 
 namespace tmvb {
@@ -45,57 +46,8 @@ struct FldaDev {
     int dbg;   // bit 0: no scatter (predict), bit 1: skip the final pass (developer probe)
 };
 
-constexpr float kLog2e = 1.4426950408889634f, kLn2 = 0.6931471805599453f;
-constexpr float kPadE = -1000.0f;   // E2 of a pad topic: 2^-1000 flushes to zero
-
 static size_t flda_fixed_smem(int RS, int lpt) { return 64 + (size_t)(32 / lpt) * RS * 4 + (size_t)RS * 4; }
 constexpr size_t kFldaPerTokExtra = 12;   // tau_s, tauo_s, kq_s
-
-__device__ __forceinline__ float warp_max(float v)
-{
-#pragma unroll
-    for (int m = 16; m > 0; m >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, m));
-    return v;
-}
-
-// p = 2^(tau L + E2) for this lane's chunks of one row; returns the lane's partial s and q (packed pairs summed by the caller)
-template <int CPL>
-__device__ __forceinline__ void flda_row(const ulonglong2 (&b)[CPL], const f32x2 (&E01)[CPL], const f32x2 (&E23)[CPL], float tau, f32x2 (&p01)[CPL],
-                                         f32x2 (&p23)[CPL], float &s, float &q)
-{
-    const f32x2 t2 = pk2(tau, tau);
-    f32x2 sa = 0ull, sb = 0ull, qa = 0ull, qb = 0ull;
-#pragma unroll
-    for (int m = 0; m < CPL; m++) {
-        float x0, x1, x2, x3;
-        unpk2(fma2(t2, b[m].x, E01[m]), x0, x1);
-        unpk2(fma2(t2, b[m].y, E23[m]), x2, x3);
-        p01[m] = pk2(ex2_ftz(x0), ex2_ftz(x1));
-        p23[m] = pk2(ex2_ftz(x2), ex2_ftz(x3));
-        sa = add2(sa, p01[m]);
-        sb = add2(sb, p23[m]);
-        qa = fma2(p01[m], b[m].x, qa);
-        qb = fma2(p23[m], b[m].y, qb);
-    }
-    s = hsum2(add2(sa, sb));
-    q = hsum2(add2(qa, qb));
-}
-
-template <int LPT, int CPL>
-__device__ __forceinline__ void flda_load_row(const float *tile, const float *gL, int RS, int K_ld, int CH, int n, int cap, int term, int kl,
-                                              ulonglong2 (&b)[CPL])
-{
-    const ulonglong2 zero = make_ulonglong2(0ull, 0ull);
-    if (n < cap) {
-        const ulonglong2 *row = reinterpret_cast<const ulonglong2 *>(tile + (size_t)n * RS) + kl;
-#pragma unroll
-        for (int m = 0; m < CPL; m++) b[m] = (kl + LPT * m < CH) ? row[LPT * m] : zero;
-    } else {
-        const ulonglong2 *row = reinterpret_cast<const ulonglong2 *>(gL + (size_t)term * K_ld) + kl;
-#pragma unroll
-        for (int m = 0; m < CPL; m++) b[m] = (kl + LPT * m < CH) ? __ldg(row + LPT * m) : zero;
-    }
-}
 
 // One warp per document.  Token phase: lane (ts = lane / LPT, kl = lane % LPT) owns token stream ts and the 16-byte chunks
 // kl + LPT m of every row; K phase: lane l owns topics l + 32 r (tmvb_estep.cuh).
@@ -513,6 +465,60 @@ __global__ void flda_tok_permute_kernel(const float *__restrict__ src, float *__
     if (e && err) atomicOr(err, 1);
 }
 
+// ---- host-side launches shared with the filtered CTM (tmvb_filt.cuh) --------------------------------------------------
+int filt_log_table(Shard *s, const float *beta, float *L)
+{
+    const long long n = (long long)s->V * s->K_ld;
+    if (n == 0) return 0;
+    flda_logtable_kernel<<<grid_for(n, 256, s->n_sm), 256, 0, s->stream>>>(beta, L, n, (int)s->K, s->K_ld);
+    TMVB_CUDA(cudaGetLastError());
+    s->st.kernel_launches++;
+    return 0;
+}
+int filt_kappa_update(Shard *s, float *kstats, float *kappa, float *kappa_old)
+{
+    if (s->V == 0) return 0;
+    flda_kappa_kernel<<<1, 1024, 0, s->stream>>>(kstats, kappa, kappa_old, (int)s->V);
+    TMVB_CUDA(cudaGetLastError());
+    s->st.kernel_launches++;
+    return 0;
+}
+int filt_push_kq(Shard *s, const float *kappa, float *kq, double eta)
+{
+    flda_kq_kernel<<<grid_for(std::max<int64_t>(s->V, 1), 256, s->n_sm), 256, 0, s->stream>>>(kappa, kq, (int)s->V, (float)eta);
+    TMVB_CUDA(cudaGetLastError());
+    s->st.kernel_launches++;
+    return 0;
+}
+int filt_tau_upload(Shard *s, const float *host_tau, float *d_tau, int *bad)
+{
+    *bad = 0;
+    if (s->nnz == 0) return 0;
+    TMVB_TRY(shard_scratch(s, (size_t)s->nnz * 4));
+    TMVB_CUDA(cudaMemcpyAsync(s->d_scratch, host_tau, (size_t)s->nnz * 4, cudaMemcpyHostToDevice, s->stream));
+    TMVB_CUDA(cudaMemsetAsync(s->d_counters + 61, 0, 4, s->stream));
+    flda_tok_permute_kernel<<<grid_for(s->M * 32, 256, s->n_sm), 256, 0, s->stream>>>((const float *)s->d_scratch, d_tau, s->d_src_off, s->d_doc_off, s->M, 1,
+                                                                                 s->d_counters + 61);
+    TMVB_CUDA(cudaGetLastError());
+    TMVB_CUDA(cudaMemcpyAsync(bad, s->d_counters + 61, 4, cudaMemcpyDeviceToHost, s->stream));
+    TMVB_CUDA(cudaStreamSynchronize(s->stream));
+    s->st.h2d_bytes += s->nnz * 4;
+    s->st.kernel_launches++;
+    return 0;
+}
+int filt_tau_download(Shard *s, const float *d_tau, float *host_tau)
+{
+    if (s->nnz == 0) return 0;
+    TMVB_TRY(shard_scratch(s, (size_t)s->nnz * 4));
+    flda_tok_permute_kernel<<<grid_for(s->M * 32, 256, s->n_sm), 256, 0, s->stream>>>(d_tau, (float *)s->d_scratch, s->d_src_off, s->d_doc_off, s->M, 0, nullptr);
+    TMVB_CUDA(cudaGetLastError());
+    TMVB_CUDA(cudaMemcpyAsync(host_tau, s->d_scratch, (size_t)s->nnz * 4, cudaMemcpyDeviceToHost, s->stream));
+    TMVB_CUDA(cudaStreamSynchronize(s->stream));
+    s->st.d2h_bytes += s->nnz * 4;
+    s->st.kernel_launches++;
+    return 0;
+}
+
 typedef void (*FldaEstepFn)(const FldaDev, int, int, int, int, int *);
 typedef void (*FldaElboFn)(const FldaDev, const float *, const float *, double, double, double, double *);
 #define TMVB_FLDA_FN(L, C) (FldaEstepFn)flda_estep_kernel<L, C>,
@@ -595,25 +601,9 @@ void flda_free(tmvb_flda_t h)
     shard_free(&h->s);
 }
 
-int flda_log_table(tmvb_flda_t h, int which)
-{
-    Shard &s = h->s;
-    const long long n = (long long)s.V * s.K_ld;
-    if (n == 0) return 0;
-    flda_logtable_kernel<<<grid_for(n, 256, s.n_sm), 256, 0, s.stream>>>(s.d_beta[which], h->d_L[which], n, (int)s.K, s.K_ld);
-    TMVB_CUDA(cudaGetLastError());
-    s.st.kernel_launches++;
-    return 0;
-}
+int flda_log_table(tmvb_flda_t h, int which) { return filt_log_table(&h->s, h->s.d_beta[which], h->d_L[which]); }
 
-int flda_push_kq(tmvb_flda_t h)
-{
-    Shard &s = h->s;
-    flda_kq_kernel<<<grid_for(std::max<int64_t>(s.V, 1), 256, s.n_sm), 256, 0, s.stream>>>(h->d_kappa, h->d_kq, (int)s.V, (float)h->eta);
-    TMVB_CUDA(cudaGetLastError());
-    s.st.kernel_launches++;
-    return 0;
-}
+int flda_push_kq(tmvb_flda_t h) { return filt_push_kq(&h->s, h->d_kappa, h->d_kq, h->eta); }
 
 }  // namespace
 
@@ -742,18 +732,9 @@ int tmvb_flda_upload(tmvb_flda_t h, const double *eta, const float *alpha, const
             TMVB_CUDA(cudaMemcpyAsync(h->d_Elogtheta_old, h->d_Elogtheta, (size_t)s.M * s.K_ld * 4, cudaMemcpyDeviceToDevice, s.stream));
         TMVB_TRY(shard_upload_rows(&s, gamma, h->d_gamma, s.M, s.d_perm, 2));
         if (tau && s.nnz > 0) {
-            TMVB_TRY(shard_scratch(&s, (size_t)s.nnz * 4));
-            TMVB_CUDA(cudaMemcpyAsync(s.d_scratch, tau, (size_t)s.nnz * 4, cudaMemcpyHostToDevice, s.stream));
-            TMVB_CUDA(cudaMemsetAsync(s.d_counters + 61, 0, 4, s.stream));
-            flda_tok_permute_kernel<<<grid_for(s.M * 32, 256, s.n_sm), 256, 0, s.stream>>>((const float *)s.d_scratch, h->d_tau, s.d_src_off, s.d_doc_off, s.M, 1,
-                                                                                        s.d_counters + 61);
-            TMVB_CUDA(cudaGetLastError());
-            TMVB_CUDA(cudaMemcpyAsync(h->d_tau_old, h->d_tau, (size_t)s.nnz * 4, cudaMemcpyDeviceToDevice, s.stream));   // tau_old = deepcopy(tau), fLDA.jl:51
             int terr = 0;
-            TMVB_CUDA(cudaMemcpyAsync(&terr, s.d_counters + 61, 4, cudaMemcpyDeviceToHost, s.stream));
-            TMVB_CUDA(cudaStreamSynchronize(s.stream));
-            s.st.h2d_bytes += s.nnz * 4;
-            s.st.kernel_launches++;
+            TMVB_TRY(filt_tau_upload(&s, tau, h->d_tau, &terr));
+            TMVB_CUDA(cudaMemcpyAsync(h->d_tau_old, h->d_tau, (size_t)s.nnz * 4, cudaMemcpyDeviceToDevice, s.stream));   // tau_old = deepcopy(tau), fLDA.jl:51
             if (terr) return fail(-5, "tau must contain probabilities.");
         }
     }
@@ -824,11 +805,7 @@ int tmvb_flda_mstep(tmvb_flda_t h, int64_t M_total, double C_total, int niter, d
     TMVB_CUDA(cudaEventRecord(s.ev[2], s.stream));
     TMVB_TRY(shard_normalize(&s, h->d_local, false, false));   // beta_old <- beta; beta = beta_temp ./ rowsum; beta_temp <- 0
     TMVB_TRY(flda_log_table(h, s.cur));
-    if (s.V > 0) {
-        flda_kappa_kernel<<<1, 1024, 0, s.stream>>>(h->d_kstats, h->d_kappa, h->d_kappa_old, (int)s.V);
-        TMVB_CUDA(cudaGetLastError());
-        s.st.kernel_launches++;
-    }
+    TMVB_TRY(filt_kappa_update(&s, h->d_kstats, h->d_kappa, h->d_kappa_old));
     TMVB_TRY(lda_launch_alpha(h->d_alpha64, h->d_alpha, h->d_small, (int)s.K, s.K_ld, (double)M_total, niter, ntol, s.stream));
     s.st.kernel_launches++;
     TMVB_CUDA(cudaMemcpyAsync(s.h_pinned, h->d_small + s.K_ld + 1, 8, cudaMemcpyDeviceToHost, s.stream));
@@ -890,14 +867,7 @@ int tmvb_flda_download(tmvb_flda_t h, double *eta, float *alpha, float *kappa, f
     if (beta) TMVB_TRY(shard_download_rows(&s, s.d_beta[s.cur], beta, s.V, nullptr));
     if (Elogtheta) TMVB_TRY(shard_download_rows(&s, h->d_Elogtheta, Elogtheta, s.M, s.d_perm));
     if (gamma) TMVB_TRY(shard_download_rows(&s, h->d_gamma, gamma, s.M, s.d_perm));
-    if (tau && s.nnz > 0) {
-        TMVB_TRY(shard_scratch(&s, (size_t)s.nnz * 4));
-        flda_tok_permute_kernel<<<grid_for(s.M * 32, 256, s.n_sm), 256, 0, s.stream>>>(h->d_tau, (float *)s.d_scratch, s.d_src_off, s.d_doc_off, s.M, 0, nullptr);
-        TMVB_CUDA(cudaGetLastError());
-        TMVB_CUDA(cudaMemcpyAsync(tau, s.d_scratch, (size_t)s.nnz * 4, cudaMemcpyDeviceToHost, s.stream));
-        s.st.d2h_bytes += s.nnz * 4;
-        s.st.kernel_launches++;
-    }
+    if (tau) TMVB_TRY(filt_tau_download(&s, h->d_tau, tau));
     TMVB_CUDA(cudaStreamSynchronize(s.stream));
     return 0;
 }
@@ -913,15 +883,7 @@ int tmvb_flda_download_old(tmvb_flda_t h, float *kappa_old, float *beta_old, flo
     }
     if (beta_old) TMVB_TRY(shard_download_rows(&s, s.d_beta[s.cur ^ 1], beta_old, s.V, nullptr));
     if (Elogtheta_old) TMVB_TRY(shard_download_rows(&s, h->d_Elogtheta_old, Elogtheta_old, s.M, s.d_perm));
-    if (tau_old && s.nnz > 0) {
-        TMVB_TRY(shard_scratch(&s, (size_t)s.nnz * 4));
-        flda_tok_permute_kernel<<<grid_for(s.M * 32, 256, s.n_sm), 256, 0, s.stream>>>(h->d_tau_old, (float *)s.d_scratch, s.d_src_off, s.d_doc_off, s.M, 0,
-                                                                                    nullptr);
-        TMVB_CUDA(cudaGetLastError());
-        TMVB_CUDA(cudaMemcpyAsync(tau_old, s.d_scratch, (size_t)s.nnz * 4, cudaMemcpyDeviceToHost, s.stream));
-        s.st.d2h_bytes += s.nnz * 4;
-        s.st.kernel_launches++;
-    }
+    if (tau_old) TMVB_TRY(filt_tau_download(&s, h->d_tau_old, tau_old));
     TMVB_CUDA(cudaStreamSynchronize(s.stream));
     return 0;
 }

@@ -66,7 +66,7 @@ __global__ void lda_elbo_kernel(const LdaDev p, const float *__restrict__ beta_o
                 e_r[r] = F64 ? (real)exp((double)Eo[i]) : (real)expf(Eo[i]);
                 En_r[r] = (real)E;
                 if (F64) {
-                    dacc += ((double)p.alpha[i] - 1.0) * E + lgamma(g) - (g - 1.0) * d_digamma(g);
+                    dacc += ((double)p.alpha[i] - 1.0) * E + (p.K > 1 ? lgamma(g) - (g - 1.0) * d_digamma(g) : 0.0);
                 } else {
                     const PsiLg pl = psi_lgamma<true>((float)g);
                     dacc += ((double)p.alpha[i] - 1.0) * E + (p.K > 1 ? (double)pl.lg - (g - 1.0) * (double)pl.psi : 0.0);   // K = 1: entropy(Dirichlet) = 0, utils.jl:168

@@ -241,3 +241,74 @@ def train_ctm(model: gpuCTM, iter: int = 150, tol: float = 1.0, niter: int = 100
         model.update_host()
     model.update_topics()                                           # gpuCTM.jl:517
     return None
+
+
+class gpufCTM(gpuCTM):
+    """GPU accelerated filtered correlated topic model: the fields of fCTM.jl:6-32 (init :34-64) on top of gpuCTM -- ``eta``,
+    ``kappa`` (V), ``tau`` / ``tau_old`` (flat float32 over the CSR tokens; ``tau_of(d)`` = the reference's ``tau[d]``).  The reference
+    has no GPU version (macros.jl:277-278 skips fCTM); ``train(model, ...)`` follows train!(::fCTM) (fCTM.jl:249-290)."""
+
+    def __init__(self, corp: Corpus, K: int, seed: Optional[int] = None, **kw):
+        super().__init__(corp, K, seed=seed, **kw)
+        rng = np.random.default_rng(None if seed is None else seed + 1)
+        V = self.V
+        self.eta = 0.5                                                            # fCTM.jl:46
+        gk = rng.standard_exponential(size=V) if V else np.zeros(0)
+        self.kappa = (gk / gk.sum()).astype(np.float32) if V else np.zeros(0, np.float32)   # fCTM.jl:50
+        self.kappa_old = self.kappa.copy()
+        self.tau = np.full(self.corp.flat().nnz, self.eta, dtype=np.float32)      # fCTM.jl:58
+        self.tau_old = self.tau.copy()
+
+    def tau_of(self, d: int) -> np.ndarray:
+        f = self.corp.flat()
+        return self.tau[f.N_cumsum[d]:f.N_cumsum[d + 1]]
+
+    def _handle(self):
+        if self._h is None:
+            h = C.c_void_p()
+            stream = self._stream if self._stream is not None else (self.reducer.stream_ptr() if self.reducer is not None else None)
+            _lib.check(_lib.load().tmvb_fctm_create(C.byref(h), self.K, self.M, self.V, self._device, stream))
+            self._h = h
+        return self._h
+
+    def update_buffer(self):
+        E = _lib.TopicModelError
+        if not (0 <= self.eta <= 1):
+            raise E("eta must belong to the interval [0,1].")                      # modelutils.jl:104
+        self.kappa = np.ascontiguousarray(self.kappa, dtype=np.float32)
+        if self.kappa.shape != (self.V,):
+            raise E("kappa must be of length V")
+        nnz = self.corp.flat().nnz
+        self.tau = np.ascontiguousarray(self.tau, dtype=np.float32)
+        if self.tau.shape != (nnz,):
+            raise E("tau must contain one probability per document term.")
+        super().update_buffer()
+        eta = C.c_double(float(self.eta))
+        _lib.check(_lib.load().tmvb_fctm_upload(self._handle(), C.byref(eta), _lib.ptr(self.kappa) if self.V else None, _lib.ptr(self.tau)))
+
+    def update_host(self):
+        if not self._resident:
+            return
+        super().update_host()
+        nnz = self.corp.flat().nnz
+        self.kappa, self.kappa_old = np.empty(self.V, np.float32), np.empty(self.V, np.float32)
+        self.tau, self.tau_old = np.empty(nnz, np.float32), np.empty(nnz, np.float32)
+        hp = lambda a: a.ctypes.data if a.size else None  # noqa: E731
+        _lib.check(_lib.load().tmvb_fctm_download(self._handle(), hp(self.kappa), hp(self.kappa_old), hp(self.tau), hp(self.tau_old)))
+
+    @property
+    def phi(self):
+        raise NotImplementedError("phi of the filtered model is not materialised; rebuild it from tau_old / beta_old / lam_old (fCTM.jl:125)")
+
+    def mstep(self):
+        """update_beta!(), update_kappa!(), update_sigma!(), update_mu!() (fCTM.jl:274-277)."""
+        if self.reducer is not None:
+            lib, h = _lib.load(), self._handle()
+            kp, kn = C.c_void_p(), C.c_int64()
+            _lib.check(lib.tmvb_fctm_reduce_buffers(h, C.byref(kp), C.byref(kn)))
+            self.reducer.allreduce_device([(kp.value, kn.value, "<f4")], self.reducer.torch.cuda.current_device())
+        super().mstep()
+
+    def update_elbo(self, mode: int = 1) -> float:
+        """update_elbo! (fCTM.jl:120-130): always the stand-alone evaluation of the device state."""
+        return super().update_elbo(1)
