@@ -62,6 +62,15 @@ CONFIGS = {
                            workload="gpuLDA K=200 on synthetic 1M docs x 50k vocab (synth.cfg4_shard), block-cyclic doc shards",
                            metric="LDA K=200 synthetic 1M x 50k: documents/sec over full VI iterations (E-step + M-step + alpha + ELBO)",
                            cpu_docs=4096, cpu_iters=1, ref_docs=8192),
+    # the filtered models (fLDA.jl / fCTM.jl; no GPU version in the reference): measured like the others
+    "nsf_flda_k50": dict(model="flda", K=50, corpus="nsf", cycle=5,
+                         workload="gpufLDA K=50 on NSF (128804 docs x 25319 vocab), filtered LDA (per-token tau, kappa, eta), doc-sharded d % N",
+                         metric="fLDA K=50 NSF: documents/sec over full VI iterations (E-step + M-step + alpha/eta + ELBO)",
+                         cpu_docs=8192, cpu_iters=1, ref_docs=None),
+    "citeu_fctm_k30": dict(model="fctm", K=30, corpus="citeu", cycle=5,
+                           workload="gpufCTM K=30 on CiteULike (16980 docs x 8000 vocab), filtered CTM, doc-sharded d % N",
+                           metric="fCTM K=30 CiteULike: documents/sec over full VI iterations (E-step + M-step + sigma/mu/kappa + ELBO)",
+                           cpu_docs=2048, cpu_iters=1, ref_docs=None),
 }
 DEFAULT_CONFIG = "nsf_lda_k50"
 
@@ -92,9 +101,15 @@ def algorithmic_bytes(cfg, nnz, M, V, U, nr):
     if cfg["model"] == "lda":
         e = nnz * (8 * K + 8) + 12 * K * M
         return e, e + 12 * K * V
+    if cfg["model"] == "flda":   # + tau read, tau / tau_old written, kappa weight read per token; the log2 table and kappa in the M-step
+        e = nnz * (8 * K + 8 + 16) + 12 * K * M
+        return e, e + 16 * K * V + 12 * V
     if cfg["model"] == "ctm":
         e = nnz * (8 * K + 8) + M * 4 * (3 * K + 2)
         return e, e + 12 * K * V + 4 * K * K
+    if cfg["model"] == "fctm":
+        e = nnz * (8 * K + 8 + 16) + M * 4 * (3 * K + 2)
+        return e, e + 16 * K * V + 4 * K * K + 12 * V
     e = nnz * (8 * K + 8) + nr * (8 * K + 8) + 16 * K * M
     return e, e + 12 * K * (V + U)
 
@@ -140,6 +155,11 @@ class ClockSampler(threading.Thread):
 
 
 # ------------------------------------------------------------------------------------------------ model arms ------
+def filtered_kappa0(V):
+    """The injected initial kappa of the filtered configurations (oracle and device read the same float32 vector)."""
+    return np.random.default_rng(8).dirichlet(np.ones(V)).astype(np.float32)
+
+
 class Arm:
     """What the measurement loop needs from one model family: construction with the injected initial state, the
     constructor state again (`reinit`), one resident outer iteration (`step`), the public train call."""
@@ -159,6 +179,16 @@ class Arm:
             self.init0 = np.asfortranarray(tm.synth.init_beta(K, V, seed=7).T.astype(np.float32))
             self.model = m = tm.gpuCTM(corp, K, reducer=reducer, M_total=M_total, stream=stream)
             m.beta, m.lam, m.vsq = pin(self.init0), pin(m.lam), pin(m.vsq)
+        elif kind in ("flda", "fctm"):
+            self.init0 = np.asfortranarray(tm.synth.init_beta(K, V, seed=7).T.astype(np.float32))
+            self.kappa0 = filtered_kappa0(V)
+            cls = tm.gpufLDA if kind == "flda" else tm.gpufCTM
+            kw = {}
+            if kind == "flda":   # update_eta! divides by sum(model.C) over ALL ranks
+                c_local = float(np.asarray(shard.counts, dtype=np.float64).sum())
+                kw = dict(C_total=reducer.allreduce_host(c_local) if reducer is not None else c_local)
+            self.model = m = cls(corp, K, reducer=reducer, M_total=M_total, stream=stream, **kw)
+            m.beta, m.kappa = self.init0.copy(order="F"), self.kappa0.copy()
         else:
             self.init0 = np.asfortranarray(tm.synth.init_alef(K, V, seed=7).T.astype(np.float32))
             self.model = m = tm.gpuCTPF(corp, K, reducer=reducer, M_total=M_total, stream=stream)
@@ -182,6 +212,23 @@ class Arm:
             m.lam[...] = 0.0
             m.vsq[...] = 1.0
             m.logzeta = np.full(m.M, 0.5, np.float32)
+        elif kind in ("flda", "fctm"):
+            nnz = m.corp.flat().nnz
+            m.eta = 0.5
+            m.kappa = self.kappa0.copy()
+            m.beta = self.init0.copy(order="F")
+            m.tau = np.full(nnz, 0.5, np.float32)
+            if kind == "flda":
+                m.alpha = np.ones(K, dtype=np.float32)
+                m.Elogtheta = np.full((K, m.M), np.float32(-(np.euler_gamma + digamma(K))), dtype=np.float32, order="F")
+                m.gamma = np.ones((K, m.M), dtype=np.float32, order="F")
+            else:
+                m.mu = np.zeros(K, np.float32)
+                m.sigma = np.eye(K, dtype=np.float32)
+                m.invsigma = np.eye(K, dtype=np.float32)
+                m.lam = np.zeros((K, m.M), dtype=np.float32, order="F")
+                m.vsq = np.ones((K, m.M), dtype=np.float32, order="F")
+                m.logzeta = np.full(m.M, 0.5, np.float32)
         else:
             m.alef[...] = self.init0
             m.he[...] = 1.0
@@ -211,6 +258,14 @@ class Arm:
         elif kind == "ctm":
             m.estep(1000, self.ntol, VITER, self.vtol, want_elbo=True)
             m.mstep()
+        elif kind == "flda":
+            m.estep(VITER, self.vtol)
+            m.mstep(1000, self.ntol)
+            return m.update_elbo()
+        elif kind == "fctm":
+            m.estep(1000, self.ntol, VITER, self.vtol, want_elbo=False)
+            m.mstep()
+            return m.update_elbo()
         else:
             m.estep(VITER, self.vtol, want_elbo=True)
             m.mstep()
@@ -332,7 +387,8 @@ def measure(tm, torch, args, name, rank, local, world, reducer, work_stream, pea
         tj = json.load(open(tpath)).get(name)
         if tj:
             traffic, tsrc = tj.get("dram_bytes_per_estep"), tj.get("source")
-    kernel_names = {"lda": "lda_estep_reg_kernel / lda_estep_kernel", "ctm": "ctm_estep_kernel", "ctpf": "ctpf_estep_kernel"}
+    kernel_names = {"lda": "lda_estep_hyb_kernel / lda_estep_kernel", "ctm": "ctm_estep_kernel", "ctpf": "ctpf_estep_kernel",
+                    "flda": "flda_estep_kernel", "fctm": "fctm_estep_kernel"}
     roofline = {"bound": "hbm", "kernel": kernel_names[cfg["model"]] + " (all length-bucket launches of one E-step)", "achieved": achieved,
                 "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_source": tsrc, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": est_bytes_total // world, "kernel_ms": est_ms,
@@ -414,6 +470,10 @@ def oracle_runner(synth, cfg, sub, init0, nthreads):
             state["st"] = oracle.LDAState(K, sub.M, sub.V, beta=table)
         elif kind == "ctm":
             state["st"] = oracle.CTMState(K, sub.M, sub.V, table)
+        elif kind == "flda":
+            state["st"] = oracle.FLDAState(K, sub.M, sub.V, len(sub.terms), table, filtered_kappa0(sub.V))
+        elif kind == "fctm":
+            state["st"] = oracle.FCTMState(K, sub.M, sub.V, len(sub.terms), table, filtered_kappa0(sub.V))
         else:
             state["st"] = oracle.CTPFState(K, sub.M, sub.V, sub.U, table)
 
@@ -425,6 +485,10 @@ def oracle_runner(synth, cfg, sub, init0, nthreads):
         elif kind == "ctm":
             # checkelbo=1 evaluates the ELBO before and after the iteration: count one of the two
             oracle.ctm_train(st, sub.N_cumsum, sub.terms, sub.counts, iter=1, tol=0.0, viter=VITER, checkelbo=1, nthreads=nthreads)
+        elif kind == "flda":
+            oracle.flda_train(st, sub.N_cumsum, sub.terms, sub.counts, iter=1, tol=0.0, viter=VITER, checkelbo=1, nthreads=nthreads)
+        elif kind == "fctm":
+            oracle.fctm_train(st, sub.N_cumsum, sub.terms, sub.counts, iter=1, tol=0.0, viter=VITER, checkelbo=1, nthreads=nthreads)
         else:
             oracle.ctpf_train(st, sub, iter=1, tol=0.0, viter=VITER, checkelbo=1, nthreads=nthreads)
 
@@ -441,6 +505,7 @@ def cpu_baseline(synth, cfg, full, init0, nthreads, docs, iters):
         step()
     dt = time.perf_counter() - t0
     src = {"lda": "oracle/lda_oracle.c (fp64 restatement of LDA.jl train!)", "ctm": "oracle/ctm_oracle.c (fp64 restatement of CTM.jl train!)",
+           "flda": "oracle/flda_oracle.c (fp64 restatement of fLDA.jl train!)", "fctm": "oracle/fctm_oracle.c (fp64 restatement of fCTM.jl train!)",
            "ctpf": "oracle/ctpf_oracle.c (fp64 restatement of CTPF.jl train!, long-form ELBO)"}[cfg["model"]]
     return {"value": sub.M * iters / dt, "unit": "docs/s", "cores": nthreads, "kind": "port",
             "sample": "first %d documents, %d outer iterations of %s" % (sub.M, iters, src), "seconds": dt}
@@ -534,7 +599,12 @@ def run_ours(args):
     for n in names:
         # a failure must fail on every rank alike (the ranks meet in collectives): no per-rank recovery
         t0 = time.perf_counter()
-        line = measure(tm, torch, args, n, rank, local, world, reducer, work_stream, peak, peak_src)
+        try:
+            line = measure(tm, torch, args, n, rank, local, world, reducer, work_stream, peak, peak_src)
+        except Exception as e:   # a secondary configuration must not take the headline line with it (one process: nobody waits in a collective)
+            if world > 1:
+                raise
+            line = {"error": repr(e)}
         line["bench_seconds"] = time.perf_counter() - t0
         out["configs"][n] = line
     if rank == 0:

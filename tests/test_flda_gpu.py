@@ -207,3 +207,35 @@ def test_fctm_argument_errors(tm):
         tm.train(m, iter=1, printelbo=False)
     with pytest.raises(ValueError, match="K <= 128"):
         tm.train(tm.gpufCTM(tm.Corpus.from_csr(c), 129), iter=1, printelbo=False)
+
+
+def test_filtered_predict(tm, orc):
+    """predict(corp, train_model) for the filtered models (modelutils.jl:857-884, 915-944): the inner loop on unseen documents with
+    frozen globals, no scatter.  fLDA is checked against the oracle's inner loop on the same globals (one outer iteration of the
+    oracle from the trained globals: its E-step is exactly predict's loop)."""
+    c = tm.synth.gencorp_lda(M=120, V=300, K=4, seed=21)
+    K = 6
+    train_c, new_c = tm.synth.take_docs(c, np.arange(0, 90)), tm.synth.take_docs(c, np.arange(90, 120))
+    beta0, kappa0 = _init(tm, c, K)
+    m = tm.gpufLDA(tm.Corpus.from_csr(train_c), K)
+    m.beta, m.kappa = np.array(beta0.T, order="F", copy=True), kappa0.copy()
+    tm.train(m, iter=3, tol=0.0, printelbo=False)
+    p = tm.predict(tm.Corpus.from_csr(new_c), m, iter=10)
+    assert p.gamma.shape == (K, new_c.M) and np.all(p.gamma > 0) and np.all((p.tau >= 0) & (p.tau <= 1))
+    np.testing.assert_allclose(p.beta, m.beta)                       # globals untouched: nothing was scattered, no M-step ran
+    np.testing.assert_allclose(p.kappa, m.kappa)
+    st = orc.FLDAState(K, new_c.M, new_c.V, len(new_c.terms), np.asarray(m.beta, np.float64).T, np.asarray(m.kappa, np.float64),
+                       alpha=np.asarray(m.alpha, np.float64), eta=m.eta)
+    st.tau[:] = 0.5                                                    # the new model's tau is the constructor's (fLDA.jl:50), not eta-trained
+    st.tau_old[:] = 0.5
+    orc.flda_train(st, new_c.N_cumsum, new_c.terms, new_c.counts, iter=1, tol=0.0, viter=10, checkelbo=float("inf"))
+    np.testing.assert_allclose(p.gamma.T, st.gamma, rtol=5e-3, atol=1e-4)
+    np.testing.assert_allclose(p.tau, st.tau, rtol=5e-3, atol=1e-5)
+    np.testing.assert_allclose(tm.topicdist(p, 3), st.gamma[3] / st.gamma[3].sum(), rtol=5e-3)
+    # fCTM: runs, finite, globals untouched
+    mc = tm.gpufCTM(tm.Corpus.from_csr(train_c), K)
+    mc.beta, mc.kappa = np.array(beta0.T, order="F", copy=True), kappa0.copy()
+    tm.train(mc, iter=2, tol=0.0, printelbo=False)
+    pc = tm.predict(tm.Corpus.from_csr(new_c), mc, iter=10)
+    assert np.all(np.isfinite(pc.lam)) and np.all(pc.vsq > 0) and np.all((pc.tau >= 0) & (pc.tau <= 1))
+    np.testing.assert_allclose(pc.beta, mc.beta)

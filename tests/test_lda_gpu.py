@@ -217,6 +217,19 @@ def test_argument_errors(tm):
     m3.Elogtheta[0, 0] = np.nan
     with pytest.raises(tm.TopicModelError, match="Elogtheta must be finite"):
         tm.train(m3, iter=1, printelbo=False)
+    # isstochastic(beta, dims=2) (modelutils.jl:268): row sums on the device copy
+    m3 = tm.gpuLDA(tm.Corpus.from_csr(c), 3, seed=0)
+    m3.beta[1, :] *= 1.01
+    with pytest.raises(tm.TopicModelError, match="right stochastic"):
+        tm.train(m3, iter=1, printelbo=False)
+    m3 = tm.gpuLDA(tm.Corpus.from_csr(c), 3, seed=0)
+    m3.beta[2, 4] = -0.25
+    with pytest.raises(tm.TopicModelError, match="right stochastic"):
+        tm.train(m3, iter=1, printelbo=False)
+    m4 = tm.gpuCTM(tm.Corpus.from_csr(c), 3, seed=0)
+    m4.beta[0, :] *= 0.9
+    with pytest.raises(tm.TopicModelError, match="right stochastic"):
+        tm.train(m4, iter=1, printelbo=False)
     # out-of-range term id is rejected by the library
     bad = tm.synth.CSR(1, 5, np.array([0, 2], np.int64), np.array([1, 7], np.int64), np.array([1, 1], np.int64))
     m2 = tm.gpuLDA(tm.Corpus.from_csr(bad), 2)

@@ -72,6 +72,32 @@ def synth_lda_k200():
                 alpha_head=st.alpha[:8].tolist(), seconds=time.time() - t0, threads=NT)
 
 
+def _kappa0(V):
+    return np.random.default_rng(8).dirichlet(np.ones(V)).astype(np.float32)      # bench.filtered_kappa0
+
+
+def nsf_flda_k50():
+    c = synth.load_packed("nsf")
+    K = 50
+    beta0 = synth.init_beta(K, c.V, seed=7).astype(np.float32)
+    st = oracle.FLDAState(K, c.M, c.V, len(c.terms), beta0, _kappa0(c.V))
+    t0 = time.time()
+    trace, sweeps, _ = oracle.flda_train(st, c.N_cumsum, c.terms, c.counts, iter=5, tol=0.0, viter=10, checkelbo=1, nthreads=NT)
+    return dict(corpus="data/_packed/nsf.npz", M=c.M, V=c.V, K=K, nnz=c.nnz, init="synth.init_beta(K, V, seed=7), default_rng(8).dirichlet(ones(V)) as float32",
+                iter=5, viter=10, elbo=trace.tolist(), sweeps=sweeps.tolist(), eta=float(st.eta[0]), seconds=time.time() - t0, threads=NT)
+
+
+def citeu_fctm_k30():
+    c = synth.load_packed("citeu")
+    K = 30
+    beta0 = synth.init_beta(K, c.V, seed=7).astype(np.float32)
+    st = oracle.FCTMState(K, c.M, c.V, len(c.terms), beta0, _kappa0(c.V))
+    t0 = time.time()
+    trace, sweeps, _ = oracle.fctm_train(st, c.N_cumsum, c.terms, c.counts, iter=5, tol=0.0, viter=10, checkelbo=1, nthreads=NT)
+    return dict(corpus="data/_packed/citeu.npz", M=c.M, V=c.V, K=K, nnz=c.nnz, init="synth.init_beta(K, V, seed=7), default_rng(8).dirichlet(ones(V)) as float32",
+                iter=5, viter=10, elbo=trace.tolist(), sweeps=sweeps.tolist(), mu=st.mu.tolist(), seconds=time.time() - t0, threads=NT)
+
+
 if __name__ == "__main__":
     which = sys.argv[1:] or ["nsf_lda_k50", "citeu_ctm_k30", "citeu_ctpf_k30", "synth_lda_k200"]
     out = json.load(open(OUT)) if os.path.exists(OUT) else {}

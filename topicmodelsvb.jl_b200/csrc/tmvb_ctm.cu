@@ -1117,6 +1117,7 @@ int tmvb_ctm_upload(tmvb_ctm_t h, const float *mu, const float *sigma, const flo
     TMVB_TRY(ctm_push_globals(h));
     if (beta && s.V > 0) {
         TMVB_TRY(shard_upload_rows(&s, beta, s.d_beta[s.cur], s.V, nullptr, 0));
+        TMVB_TRY(shard_check_stochastic(&s, s.d_beta[s.cur]));   // the row sums of check_model, on the device copy
         TMVB_CUDA(cudaMemcpyAsync(s.d_beta[s.cur ^ 1], s.d_beta[s.cur], (size_t)s.V * s.K_ld * 4, cudaMemcpyDeviceToDevice, s.stream));  // CTM.jl:42
         if (h->filtered) {
             TMVB_TRY(filt_log_table(&s, s.d_beta[0], h->d_L[0]));
@@ -1142,7 +1143,7 @@ int tmvb_ctm_upload(tmvb_ctm_t h, const float *mu, const float *sigma, const flo
     }
     int verr = 0;
     TMVB_TRY(shard_validation(&s, &verr));
-    if (verr & 0x3) return fail(-5, "beta must be a right stochastic matrix.");  // modelutils.jl:293
+    if (verr & 0x4003) return fail(-5, "beta must be a right stochastic matrix.");  // modelutils.jl:293
     if (verr & 0x40) return fail(-5, "lambda must be finite.");                 // modelutils.jl:296
     if (verr & 0x10) return fail(-5, "vsq must be finite.");                    // modelutils.jl:299
     if (verr & 0x20) return fail(-5, "vsq must be positive.");                  // modelutils.jl:300

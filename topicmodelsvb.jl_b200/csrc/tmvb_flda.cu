@@ -721,6 +721,7 @@ int tmvb_flda_upload(tmvb_flda_t h, const double *eta, const float *alpha, const
     TMVB_TRY(flda_push_kq(h));
     if (beta && s.V > 0) {
         TMVB_TRY(shard_upload_rows(&s, beta, s.d_beta[s.cur], s.V, nullptr, 0));
+        TMVB_TRY(shard_check_stochastic(&s, s.d_beta[s.cur]));   // the row sums of check_model, on the device copy
         TMVB_CUDA(cudaMemcpyAsync(s.d_beta[s.cur ^ 1], s.d_beta[s.cur], (size_t)s.V * s.K_ld * 4, cudaMemcpyDeviceToDevice, s.stream));   // fLDA.jl:45
         TMVB_TRY(flda_log_table(h, 0));
         TMVB_TRY(flda_log_table(h, 1));
@@ -740,7 +741,7 @@ int tmvb_flda_upload(tmvb_flda_t h, const double *eta, const float *alpha, const
     }
     int verr = 0;
     TMVB_TRY(shard_validation(&s, &verr));
-    if (verr & 0x3) return fail(-5, "beta must be a right stochastic matrix.");   // the messages of check_model(::fLDA), modelutils.jl:69-98
+    if (verr & 0x4003) return fail(-5, "beta must be a right stochastic matrix.");   // the messages of check_model(::fLDA), modelutils.jl:69-98
     if (verr & 0x4) return fail(-5, "Elogtheta must be finite.");
     if (verr & 0x8) return fail(-5, "Elogtheta must be nonpositive.");
     if (verr & 0x10) return fail(-5, "gamma must be finite.");

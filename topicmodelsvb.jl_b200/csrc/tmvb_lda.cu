@@ -1055,6 +1055,7 @@ int tmvb_lda_upload(tmvb_lda_t h, const float *alpha, const float *beta, const f
     if (alpha) TMVB_TRY(tmvb_lda_set_alpha(h, alpha));
     if (beta && s.V > 0) {
         TMVB_TRY(shard_upload_rows(&s, beta, s.d_beta[s.cur], s.V, nullptr, 0));
+        TMVB_TRY(shard_check_stochastic(&s, s.d_beta[s.cur]));   // the row sums of check_model, on the device copy
         // beta_old = copy(beta)  (LDA.jl:36)
         TMVB_CUDA(cudaMemcpyAsync(s.d_beta[s.cur ^ 1], s.d_beta[s.cur], (size_t)s.V * s.K_ld * 4, cudaMemcpyDeviceToDevice, s.stream));
         h->beta_fresh = true;
@@ -1071,7 +1072,7 @@ int tmvb_lda_upload(tmvb_lda_t h, const float *alpha, const float *beta, const f
     int verr = 0;
     TMVB_TRY(shard_validation(&s, &verr));
     // the messages of check_model(::gpuLDA), modelutils.jl:264-273
-    if (verr & 0x3) return fail(-5, "beta must be a right stochastic matrix.");
+    if (verr & 0x4003) return fail(-5, "beta must be a right stochastic matrix.");
     if (verr & 0x4) return fail(-5, "Elogtheta must be finite.");
     if (verr & 0x8) return fail(-5, "Elogtheta must be nonpositive.");
     if (verr & 0x10) return fail(-5, "gamma must be finite.");

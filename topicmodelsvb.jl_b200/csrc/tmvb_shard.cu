@@ -236,6 +236,7 @@ int shard_create(Shard *s, int64_t K, int64_t M, int64_t V, int device, void *st
     }
     TMVB_CUDA(cudaMalloc((void **)&s->d_stats, kv * 4));
     TMVB_CUDA(cudaMemsetAsync(s->d_stats, 0, kv * 4, s->stream));
+    TMVB_CUDA(cudaMalloc((void **)&s->d_rowchk, 256 * 8));
     TMVB_CUDA(cudaMalloc((void **)&s->d_counters, 64 * 4));
     TMVB_CUDA(cudaMemsetAsync(s->d_counters, 0, 64 * 4, s->stream));
     s->pinned_doubles = pinned_doubles;
@@ -265,6 +266,7 @@ void shard_free(Shard *s)
     cudaFree(s->d_beta[0]);
     cudaFree(s->d_beta[1]);
     cudaFree(s->d_stats);
+    cudaFree(s->d_rowchk);
     cudaFree(s->d_counters);
     cudaFree(s->d_scratch);
     cudaFree(s->d_sort_ws);
@@ -447,6 +449,27 @@ int shard_upload_rows(Shard *s, const float *host, float *d_dst, int64_t rows, c
     TMVB_CUDA(cudaGetLastError());
     s->st.kernel_launches++;
     s->st.h2d_bytes += n * 4;
+    return 0;
+}
+
+__global__ void rowsum_check_kernel(const double *__restrict__ rowsum, int K, int *__restrict__ err)
+{
+    const int i = threadIdx.x;
+    // isapprox(sum, 1) with Julia's default rtol = sqrt(eps(Float32)) (utils.jl:150-160 isstochastic on a Float32 matrix)
+    if (i < K && !(fabs(rowsum[i] - 1.0) <= 3.4526698e-4)) atomicOr(err, 1 << 14);
+}
+
+int shard_check_stochastic(Shard *s, const float *d_table)
+{
+    if (s->V == 0) return 0;
+    TMVB_CUDA(cudaMemsetAsync(s->d_rowchk, 0, 256 * 8, s->stream));
+    const int R = std::max(1, 256 / s->K_ld);
+    const int threads = std::max(R * s->K_ld, s->K_ld);
+    const int grid = (int)std::min<int64_t>((s->V + R - 1) / R, (int64_t)s->n_sm * 8);
+    colsum_kernel<<<grid, threads, threads * 8, s->stream>>>(d_table, (int)s->V, s->K_ld, s->d_rowchk);
+    rowsum_check_kernel<<<1, 256, 0, s->stream>>>(s->d_rowchk, (int)s->K, s->d_counters + 62);
+    TMVB_CUDA(cudaGetLastError());
+    s->st.kernel_launches += 2;
     return 0;
 }
 

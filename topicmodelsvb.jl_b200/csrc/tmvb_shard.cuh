@@ -54,7 +54,8 @@ struct Shard {
     float *d_beta[2] = {nullptr, nullptr}, *d_stats = nullptr;
     int cur = 0;
 
-    int *d_counters = nullptr;  // [0..47] bucket work counters, [62] validation flags, [63] corpus error flags
+    int *d_counters = nullptr;  // [0..47] bucket work counters, [61] tau range flag, [62] validation flags, [63] corpus error flags
+    double *d_rowchk = nullptr; // [K_ld] row sums of an uploaded topic-word table (shard_check_stochastic)
     void *d_scratch = nullptr;
     size_t scratch_bytes = 0;
     void *d_sort_ws = nullptr;
@@ -80,6 +81,9 @@ int shard_set_corpus(Shard *s, const int64_t *N_cumsum, const void *terms, const
 // host [rows][K] (caller order) -> device [rows][K_ld] (internal order when perm); validate: -1 none, 0 x>=0, 1 x<=0, 2 x>0
 int shard_upload_rows(Shard *s, const float *host, float *d_dst, int64_t rows, const int *d_perm, int validate);
 int shard_download_rows(Shard *s, const float *d_src, float *host, int64_t rows, const int *d_perm);
+// isstochastic(table, dims=2) of check_model (modelutils.jl:268,293,...) on the device copy: every row sum within sqrt(eps(Float32)) of one;
+// asynchronous, a violation sets bit 14 of the validation mask
+int shard_check_stochastic(Shard *s, const float *d_table);
 // returns and clears the validation bit mask accumulated by shard_upload_rows (2 bits per `validate` code)
 int shard_validation(Shard *s, int *mask);
 // launch an E-step kernel `fn(Dev, doc_begin, doc_end, cap, cap2, counter)` over every bucket; pick(bucket, ctx) returns the

@@ -186,10 +186,7 @@ def check_model_ctm(model: gpuCTM) -> None:
         raise E("sigma must be positive-definite.")
     if np.shape(model.beta) != (K, V):
         raise E("beta must be of size (K, V).")
-    if V:
-        rs = np.asarray(model.beta).sum(axis=1, dtype=np.float64)
-        if not np.allclose(rs, 1.0, rtol=math.sqrt(np.finfo(np.float32).eps)):
-            raise E("beta must be a right stochastic matrix.")
+    # isstochastic(beta, dims=2) (modelutils.jl:293): on the device copy during update_buffer! (shard_check_stochastic)
     if np.shape(model.lam) != (K, M):
         raise E("lambda must contain M vectors of length K.")
     if np.shape(model.vsq) != (K, M):

@@ -8,7 +8,8 @@ import numpy as np
 
 from . import _lib
 from .corpus import Corpus, CorpusError, check_corp
-from .gpu_ctm import check_model_ctm, gpuCTM
+from .gpu_ctm import check_model_ctm, gpuCTM, gpufCTM
+from .gpu_flda import check_model_flda, gpufLDA
 from .gpu_lda import check_model as check_model_lda
 from .gpu_lda import gpuLDA
 
@@ -38,9 +39,28 @@ def predict(corp: Corpus, train_model, iter: int = 10, tol: Optional[float] = No
             _lib.check(_lib.load().tmvb_lda_predict(model._handle(), int(iter), float(tol)))
             model.update_host()
         return model
+    if isinstance(train_model, gpufLDA):
+        # predict(corp, train_model::fLDA) (modelutils.jl:857-884).  The reference copies alpha, beta and topics only -- the new model
+        # keeps a freshly drawn kappa and eta = 0.5 -- and its loop reads an undefined `vtol` (:877); here the trained kappa and eta
+        # travel with beta (the filter they describe belongs to the trained topics) and `tol` is the stopping tolerance.
+        check_model_flda(train_model)
+        model = gpufLDA(corp, K)
+        model.alpha = np.array(train_model.alpha, dtype=np.float32)
+        model.beta = np.array(train_model.beta, dtype=np.float32, order="F")
+        model.kappa = np.array(train_model.kappa, dtype=np.float32)
+        model.eta = float(train_model.eta)
+        model.topics = train_model.topics
+        if iter > 0 and corp.flat().nnz > 0:
+            model.update_buffer()
+            _lib.check(_lib.load().tmvb_flda_predict(model._handle(), int(iter), float(tol)))
+            model.update_host()
+        return model
     if isinstance(train_model, gpuCTM):
         check_model_ctm(train_model)
-        model = gpuCTM(corp, K)
+        model = gpufCTM(corp, K) if isinstance(train_model, gpufCTM) else gpuCTM(corp, K)
+        if isinstance(train_model, gpufCTM):   # predict(corp, train_model::fCTM) (modelutils.jl:915-944), kappa / eta as for fLDA above
+            model.kappa = np.array(train_model.kappa, dtype=np.float32)
+            model.eta = float(train_model.eta)
         model.mu = np.array(train_model.mu, dtype=np.float32)
         model.sigma = np.array(train_model.sigma, dtype=np.float32)
         model.invsigma = np.array(train_model.invsigma, dtype=np.float32)
@@ -57,7 +77,7 @@ def predict(corp: Corpus, train_model, iter: int = 10, tol: Optional[float] = No
 def topicdist(model, d: int) -> np.ndarray:
     """topicdist(model, d) (modelutils.jl:946-983): gamma-normalised topic proportions for LDA, additive-logistic of
     lambda for CTM, Etheta-normalised for CTPF.  ``d`` is 0-based here."""
-    if isinstance(model, gpuLDA):
+    if isinstance(model, (gpuLDA, gpufLDA)):
         g = np.asarray(model.gamma[:, d], dtype=np.float64)
         return g / g.sum()
     if isinstance(model, gpuCTM):
