@@ -188,7 +188,12 @@ class Arm:
                 c_local = float(np.asarray(shard.counts, dtype=np.float64).sum())
                 kw = dict(C_total=reducer.allreduce_host(c_local) if reducer is not None else c_local)
             self.model = m = cls(corp, K, reducer=reducer, M_total=M_total, stream=stream, **kw)
-            m.beta, m.kappa = self.init0.copy(order="F"), self.kappa0.copy()
+            m.beta, m.kappa = pin(self.init0), self.kappa0.copy()
+            m.tau = pin(m.tau)
+            if kind == "flda":
+                m.Elogtheta, m.gamma = pin(m.Elogtheta), pin(m.gamma)
+            else:
+                m.lam, m.vsq = pin(m.lam), pin(m.vsq)
         else:
             self.init0 = np.asfortranarray(tm.synth.init_alef(K, V, seed=7).T.astype(np.float32))
             self.model = m = tm.gpuCTPF(corp, K, reducer=reducer, M_total=M_total, stream=stream)
@@ -213,21 +218,20 @@ class Arm:
             m.vsq[...] = 1.0
             m.logzeta = np.full(m.M, 0.5, np.float32)
         elif kind in ("flda", "fctm"):
-            nnz = m.corp.flat().nnz
             m.eta = 0.5
             m.kappa = self.kappa0.copy()
-            m.beta = self.init0.copy(order="F")
-            m.tau = np.full(nnz, 0.5, np.float32)
+            m.beta[...] = self.init0          # in place: the fields stay views of page-locked memory
+            m.tau[...] = 0.5
             if kind == "flda":
                 m.alpha = np.ones(K, dtype=np.float32)
-                m.Elogtheta = np.full((K, m.M), np.float32(-(np.euler_gamma + digamma(K))), dtype=np.float32, order="F")
-                m.gamma = np.ones((K, m.M), dtype=np.float32, order="F")
+                m.Elogtheta[...] = np.float32(-(np.euler_gamma + digamma(K)))
+                m.gamma[...] = 1.0
             else:
                 m.mu = np.zeros(K, np.float32)
                 m.sigma = np.eye(K, dtype=np.float32)
                 m.invsigma = np.eye(K, dtype=np.float32)
-                m.lam = np.zeros((K, m.M), dtype=np.float32, order="F")
-                m.vsq = np.ones((K, m.M), dtype=np.float32, order="F")
+                m.lam[...] = 0.0
+                m.vsq[...] = 1.0
                 m.logzeta = np.full(m.M, 0.5, np.float32)
         else:
             m.alef[...] = self.init0

@@ -229,9 +229,16 @@ def test_filtered_predict(tm, orc):
     st.tau[:] = 0.5                                                    # the new model's tau is the constructor's (fLDA.jl:50), not eta-trained
     st.tau_old[:] = 0.5
     orc.flda_train(st, new_c.N_cumsum, new_c.terms, new_c.counts, iter=1, tol=0.0, viter=10, checkelbo=float("inf"))
-    np.testing.assert_allclose(p.gamma.T, st.gamma, rtol=5e-3, atol=1e-4)
-    np.testing.assert_allclose(p.tau, st.tau, rtol=5e-3, atol=1e-5)
-    np.testing.assert_allclose(tm.topicdist(p, 3), st.gamma[3] / st.gamma[3].sum(), rtol=5e-3)
+    # a term the training documents never contained has beta = 0 in every topic AND kappa = 0: the reference's update_tau!
+    # (fLDA.jl:193) then evaluates 0 * 0^(-phi) = 0 * Inf = NaN and the document's gamma is lost (the oracle reproduces that);
+    # the device works from log2(beta + eps) and stays finite.  Compare the documents the reference can handle.
+    ok = np.isfinite(st.gamma).all(axis=1)
+    assert ok.sum() >= new_c.M // 2 and np.all(np.isfinite(p.gamma)) and np.all(np.isfinite(p.tau))
+    np.testing.assert_allclose(p.gamma.T[ok], st.gamma[ok], rtol=5e-3, atol=1e-4)
+    tok_ok = np.repeat(ok, np.diff(new_c.N_cumsum))
+    np.testing.assert_allclose(p.tau[tok_ok], st.tau[tok_ok], rtol=5e-3, atol=1e-5)
+    d0 = int(np.flatnonzero(ok)[0])
+    np.testing.assert_allclose(tm.topicdist(p, d0), st.gamma[d0] / st.gamma[d0].sum(), rtol=5e-3)
     # fCTM: runs, finite, globals untouched
     mc = tm.gpufCTM(tm.Corpus.from_csr(train_c), K)
     mc.beta, mc.kappa = np.array(beta0.T, order="F", copy=True), kappa0.copy()

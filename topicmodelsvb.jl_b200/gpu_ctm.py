@@ -289,7 +289,10 @@ class gpufCTM(gpuCTM):
         super().update_host()
         nnz = self.corp.flat().nnz
         self.kappa, self.kappa_old = np.empty(self.V, np.float32), np.empty(self.V, np.float32)
-        self.tau, self.tau_old = np.empty(nnz, np.float32), np.empty(nnz, np.float32)
+        if "tau" not in self._pinned:
+            self._pinned["tau"] = _lib.pinned_empty(max(nnz, 1), np.float32)[:nnz]
+            self._pinned["tau_old"] = _lib.pinned_empty(max(nnz, 1), np.float32)[:nnz]
+        self.tau, self.tau_old = self._pinned["tau"], self._pinned["tau_old"]
         hp = lambda a: a.ctypes.data if a.size else None  # noqa: E731
         _lib.check(_lib.load().tmvb_fctm_download(self._handle(), hp(self.kappa), hp(self.kappa_old), hp(self.tau), hp(self.tau_old)))
 

@@ -58,6 +58,8 @@ class gpufLDA:
         self._device, self._stream = device, stream
         self._h = None
         self._resident = False
+        self._pinned = None
+        self._corpus_on_device = None
 
     def tau_of(self, d: int) -> np.ndarray:
         """model.tau[d] of the reference (0-based d)."""
@@ -77,6 +79,7 @@ class gpufLDA:
             _lib.load().tmvb_flda_destroy(self._h)
             self._h = None
             self._resident = False
+            self._corpus_on_device = None
 
     def __del__(self):
         try:
@@ -89,7 +92,10 @@ class gpufLDA:
         lib, h = _lib.load(), self._handle()
         f = self.corp.flat()
         z = np.zeros(1, np.int64)
-        _lib.check(lib.tmvb_flda_set_corpus(h, _lib.ptr(f.N_cumsum), _lib.ptr(f.terms if f.nnz else z), _lib.ptr(f.counts if f.nnz else z)))
+        # an immutable corpus (wrapped from a flattened CSR) is uploaded once per handle, as for gpuLDA
+        if not (self.corp.docs is None and self._corpus_on_device is self.corp):
+            _lib.check(lib.tmvb_flda_set_corpus(h, _lib.ptr(f.N_cumsum), _lib.ptr(f.terms if f.nnz else z), _lib.ptr(f.counts if f.nnz else z)))
+            self._corpus_on_device = self.corp
         self.alpha = np.ascontiguousarray(self.alpha, dtype=np.float32)
         self.kappa = np.ascontiguousarray(self.kappa, dtype=np.float32)
         if self.alpha.shape != (self.K,):
@@ -118,10 +124,17 @@ class gpufLDA:
         eta = C.c_double()
         self.alpha = np.empty(K, np.float32)
         self.kappa, self.kappa_old = np.empty(V, np.float32), np.empty(V, np.float32)
-        self.beta, self.beta_old = np.empty((K, V), np.float32, order="F"), np.empty((K, V), np.float32, order="F")
-        self.Elogtheta, self.Elogtheta_old = np.empty((K, M), np.float32, order="F"), np.empty((K, M), np.float32, order="F")
-        self.gamma = np.empty((K, M), np.float32, order="F")
-        self.tau, self.tau_old = np.empty(nnz, np.float32), np.empty(nnz, np.float32)
+        # page-locked staging arrays, allocated once per model (D2H at PCIe speed): the fields are live views of these buffers and
+        # are overwritten by the next update_host! -- copy to keep a snapshot (as for gpuLDA)
+        if self._pinned is None:
+            pe = _lib.pinned_empty
+            self._pinned = dict(beta=pe((K, V), np.float32, order="F"), beta_old=pe((K, V), np.float32, order="F"),
+                                Elogtheta=pe((K, M), np.float32, order="F"), Elogtheta_old=pe((K, M), np.float32, order="F"),
+                                gamma=pe((K, M), np.float32, order="F"), tau=pe(max(nnz, 1), np.float32)[:nnz],
+                                tau_old=pe(max(nnz, 1), np.float32)[:nnz])
+        pb = self._pinned
+        self.beta, self.beta_old, self.Elogtheta, self.Elogtheta_old = pb["beta"], pb["beta_old"], pb["Elogtheta"], pb["Elogtheta_old"]
+        self.gamma, self.tau, self.tau_old = pb["gamma"], pb["tau"], pb["tau_old"]
         hp = lambda a: a.ctypes.data if a.size else None  # noqa: E731
         _lib.check(lib.tmvb_flda_download(h, C.byref(eta), _lib.ptr(self.alpha), hp(self.kappa), hp(self.beta), hp(self.Elogtheta), hp(self.gamma),
                                           hp(self.tau)))
