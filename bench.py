@@ -325,10 +325,11 @@ def measure(tm, torch, args, name, rank, local, world, reducer, work_stream, pea
             arm.reinit_device()
             if world > 1:
                 barrier()   # the re-initialisation is outside the timed region on EVERY rank: nobody's next step waits for a peer's upload
+        if s == warmup - 1:
+            sampler.start()                  # the NVML thread is up (and has taken its first sample) before the timed region opens
         if s == warmup:
             barrier()
             launches0 = model.stats().kernel_launches
-            sampler.start()
         flush.zero_()                        # evict the previous step's lines from L2
         if s >= warmup:
             ev[s - warmup][0].record()
@@ -401,6 +402,7 @@ def measure(tm, torch, args, name, rank, local, world, reducer, work_stream, pea
     out = {
         "metric": cfg["metric"], "value": value, "unit": "docs/s", "n_gpus": world, "steps": steps, "warmup": warmup,
         "ms_per_step": ms_per_step, "ms_per_step_min_med_max": [min(per_step), statistics.median(per_step), max(per_step)],
+        "ms_per_step_rank0": [round(x, 4) for x in per_step],
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": data_desc,
         "config": {"workload": cfg["workload"], "name": name, "M": int(M_total), "V": int(V), "K": K, "nnz": int(nnz_total), "viter": VITER,
                    "vtol": arm.vtol, "step": "one outer VI iteration; steps cycle through iterations 1..%d from the initial state" % cycle,
