@@ -334,13 +334,15 @@ def train(model: gpuLDA, iter: int = 150, tol: float = 1.0, niter: int = 1000, n
     else:
         model.update_buffer()
     check = checkelbo != math.inf
+    synced = False
     if check and checkelbo <= iter:
         model.update_elbo(1)                                   # gpuLDA.jl:353
+        synced = model.reducer is not None                     # the all-reduce of the initial ELBO: every rank has uploaded
         if trace is not None:
             trace.append(model.elbo)
 
     fused = iter > 0 and model.can_iterate()
-    if model.reducer is not None and model.reducer.world > 1 and iter > 0:
+    if model.reducer is not None and model.reducer.world > 1 and iter > 0 and not synced:
         model.reducer.barrier()    # every rank has uploaded before the first exchange (the device barriers only wait so long)
     for k in range(1, iter + 1):
         want = check and (k % checkelbo == 0)
