@@ -388,7 +388,7 @@ def measure(tm, torch, args, name, rank, local, world, reducer, work_stream, pea
     achieved = (est_bytes_total / world) / (est_ms * 1e-3) / 1e9          # per GPU
     traffic, tsrc = None, None
     tpath = os.path.join(ROOT, "profiles", "r2_traffic.json")
-    if os.path.exists(tpath):
+    if os.path.exists(tpath) and world == 1:   # the capture is of the whole corpus on one GPU
         tj = json.load(open(tpath)).get(name)
         if tj:
             traffic, tsrc = tj.get("dram_bytes_per_estep"), tj.get("source")
