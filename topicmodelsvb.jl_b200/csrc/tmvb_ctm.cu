@@ -780,6 +780,9 @@ __global__ void ctm_moments_kernel(const float *__restrict__ lambda, const float
 
 // update_elbo! restated (CTM.jl:56-98) on the device state: phi from beta_old / lambda_old, everything else current.
 // One warp per document, lanes over topics; fp32 per element, fp64 accumulation.  logdet(invsigma) enters on the host.
+// RM = topics per lane (i = lane + 32 r): exp(lambda_old - max) and lambda are per-document and stay in registers; per (token,
+// topic) one product for s, then phi (lambda_i + ln(beta_i + eps) - ln phi_i) with two logarithms.
+template <int RM>
 __global__ void ctm_elbo_kernel(const CtmDev p, const float *__restrict__ beta_old, double *out)
 {
     const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
@@ -790,9 +793,18 @@ __global__ void ctm_elbo_kernel(const CtmDev p, const float *__restrict__ beta_o
         const int Nd = (int)(p.doc_off[d + 1] - o);
         const float *lam = p.lambda + d * p.K_ld, *lo = p.lambda_old + d * p.K_ld, *vs = p.vsq + d * p.K_ld;
         const float lz = p.logzeta[d];
+        float e_r[RM], lam_r[RM];
         float lmax = -INFINITY;
-        for (int i = lane; i < K; i += 32) lmax = fmaxf(lmax, lo[i]);
+#pragma unroll
+        for (int r = 0; r < RM; r++) {
+            const int i = lane + 32 * r;
+            e_r[r] = (i < K) ? lo[i] : -INFINITY;
+            lam_r[r] = (i < K) ? lam[i] : 0.0f;
+            lmax = fmaxf(lmax, e_r[r]);
+        }
         lmax = warp_max(lmax);
+#pragma unroll
+        for (int r = 0; r < RM; r++) e_r[r] = expf(e_r[r] - lmax);
         double dacc = 0.0;
         float Cd = 0.0f;
         for (int n = 0; n < Nd; n++) {
@@ -800,13 +812,21 @@ __global__ void ctm_elbo_kernel(const CtmDev p, const float *__restrict__ beta_o
             const float c = p.counts[o + n];
             Cd += c;
             const float *bo = beta_old + (size_t)term * p.K_ld, *bn = p.beta + (size_t)term * p.K_ld;
-            float s = 0.0f;
-            for (int i = lane; i < K; i += 32) s += bo[i] * expf(lo[i] - lmax);
+            float u[RM], s = 0.0f;
+#pragma unroll
+            for (int r = 0; r < RM; r++) {
+                const int i = lane + 32 * r;
+                u[r] = (i < K) ? bo[i] * e_r[r] : 0.0f;
+                s += u[r];
+            }
             s = warp_sum(s);
+            const float rs = 1.0f / s;
             float a = 0.0f;
-            for (int i = lane; i < K; i += 32) {
-                const float ph = bo[i] * expf(lo[i] - lmax) / s;
-                if (ph > 0.0f) a += ph * (lam[i] + logf(bn[i] + TMVB_EPS) - logf(ph));
+#pragma unroll
+            for (int r = 0; r < RM; r++) {
+                const int i = lane + 32 * r;
+                const float ph = u[r] * rs;
+                if (i < K && ph > 0.0f) a += ph * (lam_r[r] + logf(bn[i] + TMVB_EPS) - logf(ph));
             }
             dacc += (double)(c * a);
         }
@@ -1287,7 +1307,12 @@ int tmvb_ctm_elbo(tmvb_ctm_t h, int mode, int64_t M_total, double *elbo_docs, do
         if (h->filtered)
             fctm_elbo_kernel<<<grid_for(s.M * 32, 128, s.n_sm), 128, 0, s.stream>>>(p, h->d_L[s.cur ^ 1], h->d_kappa, log(h->eta), log1p(-h->eta), out);
         else
-            ctm_elbo_kernel<<<grid_for(s.M * 32, 128, s.n_sm), 128, 0, s.stream>>>(p, s.d_beta[s.cur ^ 1], out);
+        {
+            const int grid = grid_for(s.M * 32, 128, s.n_sm);
+            if (K <= 32) ctm_elbo_kernel<1><<<grid, 128, 0, s.stream>>>(p, s.d_beta[s.cur ^ 1], out);
+            else if (K <= 64) ctm_elbo_kernel<2><<<grid, 128, 0, s.stream>>>(p, s.d_beta[s.cur ^ 1], out);
+            else ctm_elbo_kernel<4><<<grid, 128, 0, s.stream>>>(p, s.d_beta[s.cur ^ 1], out);
+        }
         TMVB_CUDA(cudaGetLastError());
         s.st.kernel_launches++;
     }

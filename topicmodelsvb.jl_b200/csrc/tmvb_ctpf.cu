@@ -406,6 +406,12 @@ __global__ void ctpf_table_kernel(float *__restrict__ stats, float prior, float 
 // update_elbo! restated (CTPF.jl:232-247) per document: phi / xi from the *_old state (A_old, H_old, gimel_old, zayin_old,
 // old rates), every expectation with the current alef / he / rates / gimel / zayin.  One warp per document, lanes over
 // topics; fp32 per element, fp64 accumulation.  The corpus-level Gamma terms of alef / he are added on the host.
+// Everything that depends on the document only -- exp(psi(gimel_old) + ln rates_old - max) of the three softmaxes and the
+// psi(gimel) / psi(zayin) - ln rates constants of the expectations -- is evaluated once per document and kept in RM registers per
+// lane (topics i = lane + 32 r); per (token, topic) and (reader, topic) there remain one table load, psi(alef) resp. psi(he) and
+// one logarithm (the first version re-evaluated four digammas and two exponentials per element: 2.1 ms at CiteULike, three
+// E-steps' worth, inside every train! call).
+template <int RM>
 __global__ void ctpf_elbo_kernel(const CtpfDev p, const float *__restrict__ A_old, const float *__restrict__ H_old,
                                  const float *__restrict__ alef, const float *__restrict__ he, float hd, float hh, double *out)
 {
@@ -417,59 +423,90 @@ __global__ void ctpf_elbo_kernel(const CtpfDev p, const float *__restrict__ A_ol
         const long long o = p.doc_off[d], ro = p.r_off[d];
         const int Nd = (int)(p.doc_off[d + 1] - o), Rd = (int)(p.r_off[d + 1] - ro);
         const float *gm = p.gimel + d * K_ld, *zy = p.zayin + d * K_ld, *go = p.gimel_old + d * K_ld, *zo = p.zayin_old + d * K_ld;
-        float mphi = -INFINITY, mx = -INFINITY;
-        for (int i = lane; i < K; i += 32) {
-            const float pg = psi_lgamma<false>(go[i]).psi, pz = psi_lgamma<false>(zo[i]).psi;
-            mphi = fmaxf(mphi, pg + kv[KV_LNDB_OLD * K_ld + i]);
-            mx = fmaxf(mx, fmaxf(pg + kv[KV_LNDV_OLD * K_ld + i], pz + kv[KV_LNHV_OLD * K_ld + i]));
+        float xphi[RM], xa[RM], xb[RM], cphi[RM], ca[RM], cb[RM];
+        float mphi = -INFINITY, mx = -INFINITY, b = 0.0f;
+#pragma unroll
+        for (int r = 0; r < RM; r++) {
+            const int i = lane + 32 * r;
+            xphi[r] = xa[r] = xb[r] = -INFINITY;
+            cphi[r] = ca[r] = cb[r] = 0.0f;
+            if (i < K) {
+                const float pgo = psi_lgamma<false>(go[i]).psi, pzo = psi_lgamma<false>(zo[i]).psi;
+                xphi[r] = pgo + kv[KV_LNDB_OLD * K_ld + i];
+                xa[r] = pgo + kv[KV_LNDV_OLD * K_ld + i];
+                xb[r] = pzo + kv[KV_LNHV_OLD * K_ld + i];
+                mphi = fmaxf(mphi, xphi[r]);
+                mx = fmaxf(mx, fmaxf(xa[r], xb[r]));
+                const PsiLg pg = psi_lgamma<true>(gm[i]), pz = psi_lgamma<true>(zy[i]);
+                cphi[r] = pg.psi - kv[KV_LN_DALET * K_ld + i] - kv[KV_LN_BET * K_ld + i];
+                ca[r] = pg.psi - kv[KV_LN_DALET * K_ld + i] - kv[KV_LN_VAV * K_ld + i];
+                cb[r] = pz.psi - kv[KV_LN_HET * K_ld + i] - kv[KV_LN_VAV * K_ld + i];
+                b -= gm[i] * (kv[KV_HE_DV * K_ld + i] + kv[KV_AL_DB * K_ld + i]) + zy[i] * kv[KV_HE_HV * K_ld + i];   // CTPF.jl:112,123,134
+                b += (p.hc - 1.0f) * (pg.psi - kv[KV_LN_DALET * K_ld + i]) - hd * gm[i] * kv[KV_INV_DALET * K_ld + i];  // Elogptheta
+                b += (p.hg - 1.0f) * (pz.psi - kv[KV_LN_HET * K_ld + i]) - hh * zy[i] * kv[KV_INV_HET * K_ld + i];      // Elogpepsilon
+                b += gm[i] - kv[KV_LN_DALET * K_ld + i] + pg.lg + (1.0f - gm[i]) * pg.psi;                              // entropy(Gamma)
+                b += zy[i] - kv[KV_LN_HET * K_ld + i] + pz.lg + (1.0f - zy[i]) * pz.psi;
+            }
         }
         mphi = warp_max_f(mphi);
         mx = warp_max_f(mx);
+#pragma unroll
+        for (int r = 0; r < RM; r++) {   // exp(-inf) = 0 for the slots beyond K
+            xphi[r] = expf(xphi[r] - mphi);
+            xa[r] = expf(xa[r] - mx);
+            xb[r] = expf(xb[r] - mx);
+        }
         double dacc = 0.0;
         for (int n = 0; n < Nd; n++) {
             const int term = p.terms[o + n];
             const float c = p.counts[o + n];
-            float s = 0.0f;
-            for (int i = lane; i < K; i += 32) s += A_old[(size_t)term * K_ld + i] * expf(psi_lgamma<false>(go[i]).psi + kv[KV_LNDB_OLD * K_ld + i] - mphi);
+            const float *Ao = A_old + (size_t)term * K_ld, *al = alef + (size_t)term * K_ld;
+            float u[RM], s = 0.0f;
+#pragma unroll
+            for (int r = 0; r < RM; r++) {
+                const int i = lane + 32 * r;
+                u[r] = (i < K) ? Ao[i] * xphi[r] : 0.0f;
+                s += u[r];
+            }
             s = warp_sum(s);
+            const float rs = 1.0f / s;
             float a = 0.0f;
-            for (int i = lane; i < K; i += 32) {
-                const float ph = A_old[(size_t)term * K_ld + i] * expf(psi_lgamma<false>(go[i]).psi + kv[KV_LNDB_OLD * K_ld + i] - mphi) / s;
-                if (ph > 0.0f)
-                    a += ph * (psi_lgamma<false>(gm[i]).psi - kv[KV_LN_DALET * K_ld + i] - kv[KV_LN_BET * K_ld + i] +
-                               psi_lgamma<false>(alef[(size_t)term * K_ld + i]).psi - logf(ph));
+#pragma unroll
+            for (int r = 0; r < RM; r++) {
+                const int i = lane + 32 * r;
+                const float ph = u[r] * rs;
+                if (i < K && ph > 0.0f) a += ph * (cphi[r] + psi_lgamma<false>(al[i]).psi - logf(ph));
             }
             dacc += (double)(c * a);
             if (lane == 0) dacc -= (double)lgammaf(c + 1.0f);
         }
         for (int n = 0; n < Rd; n++) {
-            const int u = p.readers[ro + n];
+            const int uu = p.readers[ro + n];
             const float c = p.ratings[ro + n];
-            float s = 0.0f;
-            for (int i = lane; i < K; i += 32) {
-                const float hv = H_old[(size_t)u * K_ld + i];
-                s += hv * (expf(psi_lgamma<false>(go[i]).psi + kv[KV_LNDV_OLD * K_ld + i] - mx) + expf(psi_lgamma<false>(zo[i]).psi + kv[KV_LNHV_OLD * K_ld + i] - mx));
+            const float *Ho = H_old + (size_t)uu * K_ld, *hr = he + (size_t)uu * K_ld;
+            float va[RM], vb[RM], s = 0.0f;
+#pragma unroll
+            for (int r = 0; r < RM; r++) {
+                const int i = lane + 32 * r;
+                const float hv = (i < K) ? Ho[i] : 0.0f;
+                va[r] = hv * xa[r];
+                vb[r] = hv * xb[r];
+                s += va[r] + vb[r];
             }
             s = warp_sum(s);
+            const float rs = 1.0f / s;
             float a = 0.0f;
-            for (int i = lane; i < K; i += 32) {
-                const float hv = H_old[(size_t)u * K_ld + i], phe = psi_lgamma<false>(he[(size_t)u * K_ld + i]).psi;
-                const float xa = hv * expf(psi_lgamma<false>(go[i]).psi + kv[KV_LNDV_OLD * K_ld + i] - mx) / s;
-                const float xb = hv * expf(psi_lgamma<false>(zo[i]).psi + kv[KV_LNHV_OLD * K_ld + i] - mx) / s;
-                if (xa > 0.0f) a += xa * (psi_lgamma<false>(gm[i]).psi - kv[KV_LN_DALET * K_ld + i] - kv[KV_LN_VAV * K_ld + i] + phe - logf(xa));
-                if (xb > 0.0f) a += xb * (psi_lgamma<false>(zy[i]).psi - kv[KV_LN_HET * K_ld + i] - kv[KV_LN_VAV * K_ld + i] + phe - logf(xb));
+#pragma unroll
+            for (int r = 0; r < RM; r++) {
+                const int i = lane + 32 * r;
+                if (i < K) {
+                    const float phe = psi_lgamma<false>(hr[i]).psi, pa = va[r] * rs, pb = vb[r] * rs;
+                    if (pa > 0.0f) a += pa * (ca[r] + phe - logf(pa));
+                    if (pb > 0.0f) a += pb * (cb[r] + phe - logf(pb));
+                }
             }
             dacc += (double)(c * a);
             if (lane == 0) dacc -= (double)lgammaf(c + 1.0f);
-        }
-        float b = 0.0f;
-        for (int i = lane; i < K; i += 32) {
-            const PsiLg pg = psi_lgamma<true>(gm[i]), pz = psi_lgamma<true>(zy[i]);
-            b -= gm[i] * (kv[KV_HE_DV * K_ld + i] + kv[KV_AL_DB * K_ld + i]) + zy[i] * kv[KV_HE_HV * K_ld + i];   // CTPF.jl:112,123,134
-            b += (p.hc - 1.0f) * (pg.psi - kv[KV_LN_DALET * K_ld + i]) - hd * gm[i] * kv[KV_INV_DALET * K_ld + i];  // Elogptheta
-            b += (p.hg - 1.0f) * (pz.psi - kv[KV_LN_HET * K_ld + i]) - hh * zy[i] * kv[KV_INV_HET * K_ld + i];      // Elogpepsilon
-            b += gm[i] - kv[KV_LN_DALET * K_ld + i] + pg.lg + (1.0f - gm[i]) * pg.psi;                              // entropy(Gamma)
-            b += zy[i] - kv[KV_LN_HET * K_ld + i] + pz.lg + (1.0f - zy[i]) * pz.psi;
         }
         dacc += (double)b;
         dacc = warp_sum_d(dacc);
@@ -880,8 +917,10 @@ int tmvb_ctpf_elbo(tmvb_ctpf_t h, int mode, int64_t M_total, double *elbo_docs, 
     double *out = h->d_tsum + 2 * (3 * K_ld + 1);
     TMVB_CUDA(cudaMemsetAsync(out, 0, 8, s.stream));
     if (s.M > 0) {
-        ctpf_elbo_kernel<<<grid_for(s.M * 32, 128, s.n_sm), 128, 0, s.stream>>>(p, s.d_beta[s.cur ^ 1], h->d_H[h->hcur ^ 1], h->d_alef, h->d_he,
-                                                                               (float)dd, (float)hh, out);
+        const int grid = grid_for(s.M * 32, 128, s.n_sm);
+#define TMVB_CTPF_ELBO(R) ctpf_elbo_kernel<R><<<grid, 128, 0, s.stream>>>(p, s.d_beta[s.cur ^ 1], h->d_H[h->hcur ^ 1], h->d_alef, h->d_he, (float)dd, (float)hh, out)
+        if (s.K <= 32) TMVB_CTPF_ELBO(1); else if (s.K <= 64) TMVB_CTPF_ELBO(2); else if (s.K <= 128) TMVB_CTPF_ELBO(4); else TMVB_CTPF_ELBO(8);
+#undef TMVB_CTPF_ELBO
         TMVB_CUDA(cudaGetLastError());
         s.st.kernel_launches++;
     }

@@ -74,6 +74,7 @@ class gpuCTM:
             _lib.load().tmvb_ctm_destroy(self._h)
             self._h = None
             self._resident = False
+            self._corpus_on_device = None
 
     def __del__(self):
         try:
@@ -85,7 +86,10 @@ class gpuCTM:
         """update_buffer!(model::gpuCTM) (modelutils.jl:400-435)."""
         lib, h = _lib.load(), self._handle()
         f = self.corp.flat()
-        _lib.check(lib.tmvb_ctm_set_corpus(h, _lib.ptr(f.N_cumsum), _lib.ptr(f.terms), _lib.ptr(f.counts)))
+        # an immutable corpus (wrapped from a flattened CSR) is uploaded once per handle, as for gpuLDA
+        if not (self.corp.docs is None and getattr(self, "_corpus_on_device", None) is self.corp):
+            _lib.check(lib.tmvb_ctm_set_corpus(h, _lib.ptr(f.N_cumsum), _lib.ptr(f.terms), _lib.ptr(f.counts)))
+            self._corpus_on_device = self.corp
         self.mu = np.ascontiguousarray(self.mu, dtype=np.float32)
         self.sigma = np.ascontiguousarray(self.sigma, dtype=np.float32)
         if self.sigma.shape != (self.K, self.K):

@@ -71,6 +71,7 @@ class gpuCTPF:
             _lib.load().tmvb_ctpf_destroy(self._h)
             self._h = None
             self._resident = False
+            self._corpus_on_device = None
 
     def __del__(self):
         try:
@@ -89,8 +90,11 @@ class gpuCTPF:
         rc = f.R_cumsum if f.R_cumsum is not None else np.zeros(self.M + 1, np.int64)
         rd = f.readers if f.readers is not None and len(f.readers) else z
         rt = f.ratings if f.ratings is not None and len(f.ratings) else z
-        _lib.check(lib.tmvb_ctpf_set_corpus(h, _lib.ptr(f.N_cumsum), _lib.ptr(f.terms if f.nnz else z), _lib.ptr(f.counts if f.nnz else z),
-                                            _lib.ptr(np.ascontiguousarray(rc)), _lib.ptr(np.ascontiguousarray(rd)), _lib.ptr(np.ascontiguousarray(rt))))
+        # an immutable corpus (wrapped from a flattened CSR) is uploaded once per handle, as for gpuLDA
+        if not (self.corp.docs is None and getattr(self, "_corpus_on_device", None) is self.corp):
+            _lib.check(lib.tmvb_ctpf_set_corpus(h, _lib.ptr(f.N_cumsum), _lib.ptr(f.terms if f.nnz else z), _lib.ptr(f.counts if f.nnz else z),
+                                                _lib.ptr(np.ascontiguousarray(rc)), _lib.ptr(np.ascontiguousarray(rd)), _lib.ptr(np.ascontiguousarray(rt))))
+            self._corpus_on_device = self.corp
         self.alef = _fmat(self.alef, self.K, self.V, "alef")
         self.he = _fmat(self.he, self.K, self.U, "he")
         self.gimel = _fmat(self.gimel, self.K, self.M, "gimel")
