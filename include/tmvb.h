@@ -305,6 +305,23 @@ int tmvb_fctm_upload(tmvb_ctm_t h, const double *eta, const float *kappa, const 
 int tmvb_fctm_download(tmvb_ctm_t h, float *kappa, float *kappa_old, float *tau, float *tau_old);
 int tmvb_fctm_reduce_buffers(tmvb_ctm_t h, void **kstats, int64_t *n_kstats);
 
+/* ------------------------------------------------------------------ multi-GPU (CTM, CTPF, fLDA, fCTM) ----------------- */
+
+/* The statistics of these models only need summing over the ranks (their M-steps take the sums as they are): ONE kernel over
+ * CUDA-IPC peer memory per outer iteration (csrc/tmvb_peer.cu: rank r reduces slice r of every buffer with loads from the peers
+ * and stores the sum into every rank's copy) instead of one NCCL all-reduce per buffer.  Handshake as tmvb_lda_comm_export /
+ * _connect; then tmvb_*_peer_reduce(h) between estep and mstep on every rank (a filtered CTM handle includes its kappa
+ * statistics).  Fallback without peer access: sum the buffers of tmvb_*_reduce_buffers with any all-reduce. */
+int tmvb_ctm_comm_export(tmvb_ctm_t h, void *blob, int64_t blob_bytes);
+int tmvb_ctm_comm_connect(tmvb_ctm_t h, int rank, int world, const void *blobs, int64_t blob_bytes);
+int tmvb_ctm_peer_reduce(tmvb_ctm_t h);
+int tmvb_ctpf_comm_export(tmvb_ctpf_t h, void *blob, int64_t blob_bytes);
+int tmvb_ctpf_comm_connect(tmvb_ctpf_t h, int rank, int world, const void *blobs, int64_t blob_bytes);
+int tmvb_ctpf_peer_reduce(tmvb_ctpf_t h);
+int tmvb_flda_comm_export(tmvb_flda_t h, void *blob, int64_t blob_bytes);
+int tmvb_flda_comm_connect(tmvb_flda_t h, int rank, int world, const void *blobs, int64_t blob_bytes);
+int tmvb_flda_peer_reduce(tmvb_flda_t h);
+
 #ifdef __cplusplus
 }
 #endif

@@ -171,7 +171,7 @@ probe = torch.tensor([float(np.abs(glob).sum()), float(glob[1, 5])], dtype=torch
 both = [torch.empty_like(probe) for _ in range(world)]
 dist.all_gather(both, probe)
 if rank == 0:
-    out = {"elbo": tr, "probe": [b.tolist() for b in both]}
+    out = {"elbo": tr, "probe": [b.tolist() for b in both], "p2p": bool(getattr(m, "_p2p", False))}
     if which == "ctm":
         out.update(mu=np.asarray(m.mu, dtype=float).tolist(), sigma=np.asarray(m.sigma, dtype=float).tolist())
     else:
@@ -181,10 +181,12 @@ dist.destroy_process_group()
 '''
 
 
+@pytest.mark.parametrize("p2p", ["1", "0"])
 @pytest.mark.parametrize("which", ["ctm", "ctpf"])
-def test_two_gpu_ctm_ctpf_match_oracle(tm, orc, tmp_path, which):
-    """gpuCTM / gpuCTPF doc-sharded d %% 2 over two GPUs (per-iteration all-reduce of the sufficient statistics,
-    tmvb_*_reduce_buffers) == the oracle's single-process trajectory (CTM.jl:185-217 / CTPF.jl:344-371)."""
+def test_two_gpu_ctm_ctpf_match_oracle(tm, orc, tmp_path, which, p2p):
+    """gpuCTM / gpuCTPF doc-sharded d %% 2 over two GPUs == the oracle's single-process trajectory (CTM.jl:185-217 /
+    CTPF.jl:344-371), with the sufficient statistics summed by the one-kernel peer-memory all-reduce (tmvb_*_peer_reduce,
+    TMVB_P2P=1) and by NCCL all-reduces of tmvb_*_reduce_buffers (TMVB_P2P=0)."""
     import json
 
     import torch
@@ -193,10 +195,12 @@ def test_two_gpu_ctm_ctpf_match_oracle(tm, orc, tmp_path, which):
         pytest.skip("needs 2 GPUs (run with gpurun --gpus 2)")
     script = tmp_path / "worker_ctx.py"
     script.write_text(_WORKER_CTX % (ROOT, which))
+    port = {"ctm": 29541, "ctpf": 29543}[which] + int(p2p)
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
-                        "--master-port", {"ctm": "29541", "ctpf": "29542"}[which], str(script)], capture_output=True, text=True, timeout=600)
+                        "--master-port", str(port), str(script)], capture_output=True, text=True, timeout=600, env=dict(os.environ, TMVB_P2P=p2p))
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     got = json.loads([l for l in r.stdout.splitlines() if l.startswith("RESULT ")][-1][7:])
+    assert got["p2p"] == (p2p == "1"), "the peer-memory all-reduce was not used"
     assert got["probe"][0] == got["probe"][1], "ranks disagree on the global parameters"
     K = 7
     if which == "ctm":
@@ -216,3 +220,72 @@ def test_two_gpu_ctm_ctpf_match_oracle(tm, orc, tmp_path, which):
         np.testing.assert_allclose(got["vav"], st.vav, rtol=1e-3)
         np.testing.assert_allclose(got["bet"], st.bet, rtol=1e-3)
         np.testing.assert_allclose(got["he_sum"], st.he.sum(), rtol=1e-4)
+
+
+_WORKER_FILT = r'''
+import os, sys, json
+import numpy as np
+sys.path.insert(0, %r)
+import torch, torch.distributed as dist
+import topicmodelsvb_b200 as tm
+which = %r
+rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+torch.cuda.set_device(int(os.environ["LOCAL_RANK"]))
+dist.init_process_group("nccl", device_id=torch.device("cuda", int(os.environ["LOCAL_RANK"])))
+work = torch.cuda.Stream(); torch.cuda.set_stream(work)
+red = tm.dist.Reducer()
+K = 6
+c = tm.synth.gencorp_lda(M=300, V=503, K=5, seed=17)          # V not a multiple of four: the padded kappa statistics
+sh = c.shard(rank, world)
+beta0 = tm.synth.init_beta(K, c.V, seed=7).astype(np.float32)
+kappa0 = np.random.default_rng(8).dirichlet(np.ones(c.V)).astype(np.float32)
+if which == "flda":
+    m = tm.gpufLDA(tm.Corpus.from_csr(sh), K, reducer=red, M_total=c.M, C_total=float(np.asarray(c.counts).sum()), stream=work.cuda_stream)
+else:
+    m = tm.gpufCTM(tm.Corpus.from_csr(sh), K, reducer=red, M_total=c.M, stream=work.cuda_stream)
+m.beta, m.kappa = np.array(beta0.T, order="F", copy=True), kappa0.copy()
+tr = []
+tm.train(m, iter=3, tol=0.0, printelbo=False, trace=tr)
+probe = torch.tensor([float(np.abs(m.beta).sum()), float(m.kappa[7])], dtype=torch.float64, device="cuda")
+both = [torch.empty_like(probe) for _ in range(world)]
+dist.all_gather(both, probe)
+if rank == 0:
+    print("RESULT " + json.dumps({"elbo": tr, "probe": [b.tolist() for b in both], "p2p": bool(getattr(m, "_p2p", False)), "eta": float(m.eta),
+                                  "kappa_head": np.asarray(m.kappa[:8], dtype=float).tolist()}))
+dist.destroy_process_group()
+'''
+
+
+@pytest.mark.parametrize("p2p", ["1", "0"])
+@pytest.mark.parametrize("which", ["flda", "fctm"])
+def test_two_gpu_filtered_models_match_oracle(tm, orc, tmp_path, which, p2p):
+    """gpufLDA / gpufCTM doc-sharded over two GPUs == the oracle's single-process trajectory (fLDA.jl:214-247 / fCTM.jl:249-290):
+    K x V statistics, the V-vector of update_kappa!, and the small fp64 sums (incl. update_eta!'s numerator) cross the ranks."""
+    import json
+
+    import torch
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (run with gpurun --gpus 2)")
+    script = tmp_path / "worker_filt.py"
+    script.write_text(_WORKER_FILT % (ROOT, which))
+    port = {"flda": 29551, "fctm": 29553}[which] + int(p2p)
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                        "--master-port", str(port), str(script)], capture_output=True, text=True, timeout=600, env=dict(os.environ, TMVB_P2P=p2p))
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    got = json.loads([l for l in r.stdout.splitlines() if l.startswith("RESULT ")][-1][7:])
+    assert got["p2p"] == (p2p == "1")
+    assert got["probe"][0] == got["probe"][1], "ranks disagree on the global parameters"
+    K = 6
+    c = tm.synth.gencorp_lda(M=300, V=503, K=5, seed=17)
+    beta0 = tm.synth.init_beta(K, c.V, seed=7).astype(np.float32)
+    kappa0 = np.random.default_rng(8).dirichlet(np.ones(c.V)).astype(np.float32)
+    if which == "flda":
+        st = orc.FLDAState(K, c.M, c.V, len(c.terms), beta0, kappa0)
+        ref = orc.flda_train(st, c.N_cumsum, c.terms, c.counts, iter=3, tol=0.0)[0]
+        assert abs(got["eta"] - st.eta[0]) < 1e-4
+    else:
+        st = orc.FCTMState(K, c.M, c.V, len(c.terms), beta0, kappa0)
+        ref = orc.fctm_train(st, c.N_cumsum, c.terms, c.counts, iter=3, tol=0.0)[0]
+    np.testing.assert_allclose(got["elbo"], ref[np.isfinite(ref)], rtol=2e-5)
+    np.testing.assert_allclose(got["kappa_head"], st.kappa[:8], rtol=5e-3, atol=1e-7)

@@ -147,6 +147,15 @@ SIGNATURES = {
     "tmvb_flda_download_old": (C.c_int, [_vp] * 5),
     "tmvb_flda_topics": (C.c_int, [_vp, _vp]),
     "tmvb_flda_get_stats": (C.c_int, [_vp, C.POINTER(TmvbStats)]),
+    "tmvb_ctm_comm_export": (C.c_int, [_vp, _vp, C.c_int64]),
+    "tmvb_ctm_comm_connect": (C.c_int, [_vp, C.c_int, C.c_int, _vp, C.c_int64]),
+    "tmvb_ctm_peer_reduce": (C.c_int, [_vp]),
+    "tmvb_ctpf_comm_export": (C.c_int, [_vp, _vp, C.c_int64]),
+    "tmvb_ctpf_comm_connect": (C.c_int, [_vp, C.c_int, C.c_int, _vp, C.c_int64]),
+    "tmvb_ctpf_peer_reduce": (C.c_int, [_vp]),
+    "tmvb_flda_comm_export": (C.c_int, [_vp, _vp, C.c_int64]),
+    "tmvb_flda_comm_connect": (C.c_int, [_vp, C.c_int, C.c_int, _vp, C.c_int64]),
+    "tmvb_flda_peer_reduce": (C.c_int, [_vp]),
     "tmvb_fctm_create": (C.c_int, [C.POINTER(_vp), C.c_int64, C.c_int64, C.c_int64, C.c_int, _vp]),
     "tmvb_fctm_upload": (C.c_int, [_vp, C.POINTER(C.c_double), _vp, _vp]),
     "tmvb_fctm_download": (C.c_int, [_vp] * 5),

@@ -34,6 +34,20 @@ int comm_export(Comm *c, void *const local_bufs[kCommBufs], void *blob, size_t b
 int comm_connect(Comm *c, int rank, int world, const void *blobs, size_t blob_bytes);
 void comm_free(Comm *c);
 
+// generic in-place all-reduce over peer memory (tmvb_peer.cu): up to kPeerFloatBufs float buffers (element counts multiples of
+// four) and one fp64 vector, summed over the ranks; blob layout = float buffers | small | ctl
+constexpr int kPeerFloatBufs = kCommBufs - 2;
+struct PeerReduce {
+    float *f[kPeerFloatBufs] = {};
+    long long nf[kPeerFloatBufs] = {};
+    double *small = nullptr;
+    long long n_small = 0;
+};
+int peer_export(Comm *c, const PeerReduce &b, void *blob, size_t blob_bytes);
+int peer_allreduce(Comm *c, const PeerReduce &b, cudaStream_t stream, int n_sm);
+// reads and clears the sticky time-out flag of the device-side spins (synchronises the stream); non-zero -> fail()
+int peer_status(Comm *c, cudaStream_t stream, int *status);
+
 #ifdef __CUDACC__
 
 __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p)

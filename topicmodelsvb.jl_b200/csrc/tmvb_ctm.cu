@@ -19,6 +19,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include "tmvb_comm.cuh"
 #include "tmvb_filt.cuh"
 #include "tmvb_shard.cuh"
 
@@ -960,6 +961,7 @@ struct tmvb_ctm_s {
     float *d_L[2] = {nullptr, nullptr}, *d_kappa = nullptr, *d_kappa_old = nullptr, *d_kstats = nullptr, *d_kq = nullptr;
     float *d_tau = nullptr, *d_tau_old = nullptr;
     size_t tau_cap = 0;
+    Comm comm;   // peer-memory all-reduce of the statistics (multi-GPU)
 };
 
 namespace {
@@ -1021,10 +1023,25 @@ void ctm_free(tmvb_ctm_t h)
     cudaFree(h->d_kq);
     cudaFree(h->d_tau);
     cudaFree(h->d_tau_old);
+    comm_free(&h->comm);
     shard_free(&h->s);
 }
 
 // push the fp64 masters mu / invsigma to the device (`@buffer model.invsigma`, macros.jl:67)
+PeerReduce ctm_peer_bufs(tmvb_ctm_t h)
+{
+    PeerReduce b;
+    b.f[0] = h->s.d_stats;
+    b.nf[0] = (long long)h->s.V * h->s.K_ld;
+    if (h->filtered) {
+        b.f[1] = h->d_kstats;
+        b.nf[1] = ((long long)std::max<int64_t>(h->s.V, 1) + 3) / 4 * 4;
+    }
+    b.small = h->d_small;
+    b.n_small = h->n_small;
+    return b;
+}
+
 int ctm_push_globals(tmvb_ctm_t h)
 {
     Shard &s = h->s;
@@ -1244,6 +1261,10 @@ int tmvb_ctm_mstep(tmvb_ctm_t h, int64_t M_total)
     TMVB_CUDA(cudaStreamSynchronize(s.stream));
     s.st.d2h_bytes += h->n_small * 8;
     memcpy(h->h_mom.data(), s.h_pinned, h->n_small * 8);
+    if (h->comm.connected) {   // a peer that never arrived: raise instead of normalising half-summed statistics
+        int pst = 0;
+        TMVB_TRY(peer_status(&h->comm, s.stream, &pst));
+    }
     const int K = (int)s.K, K_ld = s.K_ld;
     const double *sl = h->h_mom.data() + 2, *sv = sl + K_ld, *G = sv + K_ld;
     const double Md = (double)M_total;
@@ -1404,7 +1425,7 @@ int tmvb_fctm_create(tmvb_ctm_t *out, int64_t K, int64_t M, int64_t V, int devic
     A((void **)&h->d_L[1], kv * 4);
     A((void **)&h->d_kappa, v1 * 4);
     A((void **)&h->d_kappa_old, v1 * 4);
-    A((void **)&h->d_kstats, v1 * 4);
+    A((void **)&h->d_kstats, (v1 + 3) / 4 * 16);   // a multiple of four floats: the peer all-reduce moves 16-byte elements
     A((void **)&h->d_kq, (v1 + 1) * 4);
     if (e == cudaSuccess && !fctm_fn(s.layout)) {
         tmvb_ctm_destroy(h);
@@ -1485,6 +1506,34 @@ int tmvb_fctm_reduce_buffers(tmvb_ctm_t h, void **kstats, int64_t *n_kstats)
     TMVB_CHECK_ARG(h != nullptr && h->filtered, "not a filtered-CTM handle");
     if (kstats) *kstats = h->d_kstats;
     if (n_kstats) *n_kstats = h->s.V;
+    return 0;
+}
+
+/* ---- multi-GPU: the statistics summed over the ranks by ONE kernel over CUDA-IPC peer memory (tmvb_peer.cu) instead of one NCCL
+ * all-reduce per buffer.  Handshake as for gpuLDA: export -> all-gather the blobs over any transport -> connect; then
+ * tmvb_ctm_peer_reduce(h) between estep and mstep on every rank. ---- */
+int tmvb_ctm_comm_export(tmvb_ctm_t h, void *blob, int64_t blob_bytes)
+{
+    TMVB_CHECK_ARG(h != nullptr, "handle is NULL");
+    TMVB_CHECK_ARG(blob_bytes >= TMVB_COMM_BLOB_BYTES, "blob must hold TMVB_COMM_BLOB_BYTES");
+    TMVB_CUDA(cudaSetDevice(h->s.device));
+    return peer_export(&h->comm, ctm_peer_bufs(h), blob, (size_t)blob_bytes);
+}
+
+int tmvb_ctm_comm_connect(tmvb_ctm_t h, int rank, int world, const void *blobs, int64_t blob_bytes)
+{
+    TMVB_CHECK_ARG(h != nullptr, "handle is NULL");
+    TMVB_CUDA(cudaSetDevice(h->s.device));
+    TMVB_CUDA(cudaStreamSynchronize(h->s.stream));
+    return comm_connect(&h->comm, rank, world, blobs, (size_t)blob_bytes);
+}
+
+int tmvb_ctm_peer_reduce(tmvb_ctm_t h)
+{
+    TMVB_CHECK_ARG(h != nullptr, "handle is NULL");
+    TMVB_CUDA(cudaSetDevice(h->s.device));
+    TMVB_TRY(peer_allreduce(&h->comm, ctm_peer_bufs(h), h->s.stream, h->s.n_sm));
+    h->s.st.kernel_launches++;
     return 0;
 }
 

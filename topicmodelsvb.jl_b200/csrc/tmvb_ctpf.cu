@@ -20,6 +20,7 @@
 #include <string.h>
 
 #define TMVB_RECS_KERNELS
+#include "tmvb_comm.cuh"
 #include "tmvb_recs.cuh"
 #include "tmvb_shard.cuh"
 
@@ -542,6 +543,7 @@ struct tmvb_ctpf_s {
     double *d_tsum = nullptr;   // [2][3 K_ld + 1] table sums (alef | he) + [1] standalone ELBO
     std::vector<double> h_small, h_tsum;
     std::vector<int> r_len;
+    Comm comm;   // peer-memory all-reduce of the statistics (multi-GPU)
 };
 
 namespace {
@@ -586,6 +588,7 @@ void ctpf_free(tmvb_ctpf_t h)
 {
     cudaSetDevice(h->s.device);
     if (h->s.stream) cudaStreamSynchronize(h->s.stream);
+    comm_free(&h->comm);
     cudaFree(h->d_alef);
     cudaFree(h->d_alef_old);
     cudaFree(h->d_he);
@@ -841,6 +844,48 @@ int tmvb_ctpf_reduce_buffers(tmvb_ctpf_t h, void **stats_alef, int64_t *n_alef, 
     return 0;
 }
 
+static PeerReduce ctpf_peer_bufs(tmvb_ctpf_t h)
+{
+    PeerReduce b;
+    b.f[0] = h->s.d_stats;
+    b.nf[0] = (long long)h->s.V * h->s.K_ld;
+    if (h->U > 0) {
+        b.f[1] = h->d_hstats;
+        b.nf[1] = (long long)h->U * h->s.K_ld;
+    }
+    b.small = h->d_small;
+    b.n_small = 2 * h->s.K_ld + 2;
+    return b;
+}
+
+/* ---- multi-GPU: the statistics summed over the ranks by ONE kernel over CUDA-IPC peer memory (tmvb_peer.cu) instead of one NCCL
+ * all-reduce per buffer.  Handshake as for gpuLDA: export -> all-gather the blobs over any transport -> connect; then
+ * tmvb_ctpf_peer_reduce(h) between estep and mstep on every rank. ---- */
+int tmvb_ctpf_comm_export(tmvb_ctpf_t h, void *blob, int64_t blob_bytes)
+{
+    TMVB_CHECK_ARG(h != nullptr, "handle is NULL");
+    TMVB_CHECK_ARG(blob_bytes >= TMVB_COMM_BLOB_BYTES, "blob must hold TMVB_COMM_BLOB_BYTES");
+    TMVB_CUDA(cudaSetDevice(h->s.device));
+    return peer_export(&h->comm, ctpf_peer_bufs(h), blob, (size_t)blob_bytes);
+}
+
+int tmvb_ctpf_comm_connect(tmvb_ctpf_t h, int rank, int world, const void *blobs, int64_t blob_bytes)
+{
+    TMVB_CHECK_ARG(h != nullptr, "handle is NULL");
+    TMVB_CUDA(cudaSetDevice(h->s.device));
+    TMVB_CUDA(cudaStreamSynchronize(h->s.stream));
+    return comm_connect(&h->comm, rank, world, blobs, (size_t)blob_bytes);
+}
+
+int tmvb_ctpf_peer_reduce(tmvb_ctpf_t h)
+{
+    TMVB_CHECK_ARG(h != nullptr, "handle is NULL");
+    TMVB_CUDA(cudaSetDevice(h->s.device));
+    TMVB_TRY(peer_allreduce(&h->comm, ctpf_peer_bufs(h), h->s.stream, h->s.n_sm));
+    h->s.st.kernel_launches++;
+    return 0;
+}
+
 int tmvb_ctpf_mstep(tmvb_ctpf_t h, int64_t M_total)
 {
     TMVB_CHECK_ARG(h != nullptr && M_total > 0, "bad arguments");
@@ -859,6 +904,10 @@ int tmvb_ctpf_mstep(tmvb_ctpf_t h, int64_t M_total)
     TMVB_CUDA(cudaMemcpyAsync(s.h_pinned + 2 * (3 * K_ld + 1), h->d_small, (2 * K_ld + 2) * 8, cudaMemcpyDeviceToHost, s.stream));
     TMVB_TRY(ctpf_fetch_tsum(h));
     memcpy(h->h_small.data(), s.h_pinned + 2 * (3 * K_ld + 1), (2 * K_ld + 2) * 8);
+    if (h->comm.connected) {
+        int pst = 0;
+        TMVB_TRY(peer_status(&h->comm, s.stream, &pst));
+    }
     s.st.d2h_bytes += (2 * K_ld + 2) * 8;
     const double *AL = h->h_tsum.data() + K_ld, *HE = h->h_tsum.data() + (3 * K_ld + 1) + K_ld;
     const double *Gs = h->h_small.data(), *Zs = Gs + K_ld;

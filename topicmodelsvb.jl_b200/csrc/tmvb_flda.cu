@@ -20,6 +20,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include "tmvb_comm.cuh"
 #include "tmvb_filt.cuh"
 #include "tmvb_shard.cuh"
 
@@ -544,6 +545,7 @@ struct tmvb_flda_s {
     double *d_small = nullptr;   // [K_ld] sum_d Elogtheta | sweeps | sum tau c | ELBO
     double *d_local = nullptr;   // [2 K_ld] rowsum | elbo_w (shard_normalize)
     int64_t n_small = 0;
+    Comm comm;   // peer-memory all-reduce of the statistics (multi-GPU)
 };
 
 namespace {
@@ -598,7 +600,20 @@ void flda_free(tmvb_flda_t h)
     cudaFree(h->d_doc_tc);
     cudaFree(h->d_small);
     cudaFree(h->d_local);
+    comm_free(&h->comm);
     shard_free(&h->s);
+}
+
+PeerReduce flda_peer_bufs(tmvb_flda_t h)
+{
+    PeerReduce b;
+    b.f[0] = h->s.d_stats;
+    b.nf[0] = (long long)h->s.V * h->s.K_ld;
+    b.f[1] = h->d_kstats;
+    b.nf[1] = ((long long)std::max<int64_t>(h->s.V, 1) + 3) / 4 * 4;
+    b.small = h->d_small;
+    b.n_small = h->n_small;
+    return b;
 }
 
 int flda_log_table(tmvb_flda_t h, int which) { return filt_log_table(&h->s, h->s.d_beta[which], h->d_L[which]); }
@@ -633,7 +648,7 @@ int tmvb_flda_create(tmvb_flda_t *out, int64_t K, int64_t M, int64_t V, int devi
         A((void **)&h->d_L[1], kv * 4);
         A((void **)&h->d_kappa, v1 * 4);
         A((void **)&h->d_kappa_old, v1 * 4);
-        A((void **)&h->d_kstats, v1 * 4);
+        A((void **)&h->d_kstats, (v1 + 3) / 4 * 16);   // a multiple of four floats: the peer all-reduce moves 16-byte elements
         A((void **)&h->d_kq, (v1 + 1) * 4);
         A((void **)&h->d_Elogtheta, km * 4);
         A((void **)&h->d_Elogtheta_old, km * 4);
@@ -795,6 +810,34 @@ int tmvb_flda_reduce_buffers(tmvb_flda_t h, void **stats, int64_t *n_stats, void
     return 0;
 }
 
+/* ---- multi-GPU: the statistics summed over the ranks by ONE kernel over CUDA-IPC peer memory (tmvb_peer.cu) instead of one NCCL
+ * all-reduce per buffer.  Handshake as for gpuLDA: export -> all-gather the blobs over any transport -> connect; then
+ * tmvb_flda_peer_reduce(h) between estep and mstep on every rank. ---- */
+int tmvb_flda_comm_export(tmvb_flda_t h, void *blob, int64_t blob_bytes)
+{
+    TMVB_CHECK_ARG(h != nullptr, "handle is NULL");
+    TMVB_CHECK_ARG(blob_bytes >= TMVB_COMM_BLOB_BYTES, "blob must hold TMVB_COMM_BLOB_BYTES");
+    TMVB_CUDA(cudaSetDevice(h->s.device));
+    return peer_export(&h->comm, flda_peer_bufs(h), blob, (size_t)blob_bytes);
+}
+
+int tmvb_flda_comm_connect(tmvb_flda_t h, int rank, int world, const void *blobs, int64_t blob_bytes)
+{
+    TMVB_CHECK_ARG(h != nullptr, "handle is NULL");
+    TMVB_CUDA(cudaSetDevice(h->s.device));
+    TMVB_CUDA(cudaStreamSynchronize(h->s.stream));
+    return comm_connect(&h->comm, rank, world, blobs, (size_t)blob_bytes);
+}
+
+int tmvb_flda_peer_reduce(tmvb_flda_t h)
+{
+    TMVB_CHECK_ARG(h != nullptr, "handle is NULL");
+    TMVB_CUDA(cudaSetDevice(h->s.device));
+    TMVB_TRY(peer_allreduce(&h->comm, flda_peer_bufs(h), h->s.stream, h->s.n_sm));
+    h->s.st.kernel_launches++;
+    return 0;
+}
+
 /* update_beta!(model), update_kappa!(model), update_alpha!(model, niter, ntol), update_eta!(model) (fLDA.jl:236-239);
  * C_total = sum(model.C) over ALL ranks */
 int tmvb_flda_mstep(tmvb_flda_t h, int64_t M_total, double C_total, int niter, double ntol)
@@ -813,6 +856,10 @@ int tmvb_flda_mstep(tmvb_flda_t h, int64_t M_total, double C_total, int niter, d
     TMVB_CUDA(cudaStreamSynchronize(s.stream));
     s.st.d2h_bytes += 8;
     h->eta = s.h_pinned[0] / C_total;   // update_eta!, fLDA.jl:119-121
+    if (h->comm.connected) {
+        int pst = 0;
+        TMVB_TRY(peer_status(&h->comm, s.stream, &pst));
+    }
     TMVB_TRY(flda_push_kq(h));
     TMVB_CUDA(cudaEventRecord(s.ev[3], s.stream));
     s.mstep_timed = true;

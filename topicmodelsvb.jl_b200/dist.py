@@ -107,3 +107,20 @@ def default_reducer() -> Optional[Reducer]:
     if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
         return Reducer()
     return None
+
+
+def connect_model_peers(model, prefix: str) -> bool:
+    """Peer-memory handshake of a sharded model's handle (tmvb_<prefix>_comm_export / _connect): True when the statistics will be
+    summed by the one-kernel peer all-reduce (tmvb_<prefix>_peer_reduce), False when the run keeps torch.distributed all-reduces
+    (one GPU, TMVB_P2P=0, or a rank that cannot map its peers)."""
+    import os
+
+    from . import _lib
+
+    red = model.reducer
+    if red is None or red.world <= 1 or os.environ.get("TMVB_P2P", "1") == "0":
+        return False
+    lib, h = _lib.load(), model._h
+    exp, con = getattr(lib, "tmvb_%s_comm_export" % prefix), getattr(lib, "tmvb_%s_comm_connect" % prefix)
+    return red.connect_peers(lambda buf, n: _lib.check(exp(h, buf, n)), lambda rank, world, blobs, n: _lib.check(con(h, rank, world, blobs, n)),
+                             _lib.COMM_BLOB_BYTES)

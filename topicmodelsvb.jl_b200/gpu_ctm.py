@@ -67,6 +67,8 @@ class gpuCTM:
             stream = self._stream if self._stream is not None else (self.reducer.stream_ptr() if self.reducer is not None else None)
             _lib.check(lib.tmvb_ctm_create(C.byref(h), self.K, self.M, self.V, self._device, stream))
             self._h = h
+            from .dist import connect_model_peers
+            self._p2p = connect_model_peers(self, "ctm")
         return self._h
 
     def close(self):
@@ -155,7 +157,9 @@ class gpuCTM:
 
     def mstep(self):
         """update_beta!(), update_sigma!(), update_mu!() (gpuCTM.jl:509-511)."""
-        if self.reducer is not None:
+        if getattr(self, "_p2p", False):
+            _lib.check(_lib.load().tmvb_ctm_peer_reduce(self._handle()))      # one kernel over peer memory (tmvb_peer.cu)
+        elif self.reducer is not None:
             lib, h = _lib.load(), self._handle()
             sp, sn, mp, mn = C.c_void_p(), C.c_int64(), C.c_void_p(), C.c_int64()
             _lib.check(lib.tmvb_ctm_reduce_buffers(h, C.byref(sp), C.byref(sn), C.byref(mp), C.byref(mn)))
@@ -270,6 +274,8 @@ class gpufCTM(gpuCTM):
             stream = self._stream if self._stream is not None else (self.reducer.stream_ptr() if self.reducer is not None else None)
             _lib.check(_lib.load().tmvb_fctm_create(C.byref(h), self.K, self.M, self.V, self._device, stream))
             self._h = h
+            from .dist import connect_model_peers
+            self._p2p = connect_model_peers(self, "ctm")       # a filtered handle exports its kappa statistics too
         return self._h
 
     def update_buffer(self):
@@ -306,7 +312,8 @@ class gpufCTM(gpuCTM):
 
     def mstep(self):
         """update_beta!(), update_kappa!(), update_sigma!(), update_mu!() (fCTM.jl:274-277)."""
-        if self.reducer is not None:
+        self._handle()
+        if self.reducer is not None and not getattr(self, "_p2p", False):
             lib, h = _lib.load(), self._handle()
             kp, kn = C.c_void_p(), C.c_int64()
             _lib.check(lib.tmvb_fctm_reduce_buffers(h, C.byref(kp), C.byref(kn)))

@@ -64,6 +64,8 @@ class gpuCTPF:
             stream = self._stream if self._stream is not None else (self.reducer.stream_ptr() if self.reducer is not None else None)
             _lib.check(lib.tmvb_ctpf_create(C.byref(h), self.K, self.M, self.V, self.U, self._device, stream))
             self._h = h
+            from .dist import connect_model_peers
+            self._p2p = connect_model_peers(self, "ctpf")
         return self._h
 
     def close(self):
@@ -243,7 +245,10 @@ class gpuCTPF:
 
     def mstep(self):
         """update_he!(), update_alef!(), update_dalet!(), update_het!(), update_bet!(), update_vav!() (gpuCTPF.jl:699-704)."""
-        if self.reducer is not None:
+        self._handle()
+        if getattr(self, "_p2p", False):
+            _lib.check(_lib.load().tmvb_ctpf_peer_reduce(self._handle()))     # one kernel over peer memory (tmvb_peer.cu)
+        elif self.reducer is not None:
             lib, h = _lib.load(), self._handle()
             p = [C.c_void_p() for _ in range(3)]
             n = [C.c_int64() for _ in range(3)]

@@ -72,6 +72,8 @@ class gpufLDA:
             stream = self._stream if self._stream is not None else (self.reducer.stream_ptr() if self.reducer is not None else None)
             _lib.check(_lib.load().tmvb_flda_create(C.byref(h), self.K, self.M, self.V, self._device, stream))
             self._h = h
+            from .dist import connect_model_peers
+            self._p2p = connect_model_peers(self, "flda")
         return self._h
 
     def close(self):
@@ -163,7 +165,9 @@ class gpufLDA:
     def mstep(self, niter, ntol):
         """update_beta!(model), update_kappa!(model), update_alpha!(model, niter, ntol), update_eta!(model) (fLDA.jl:236-239)."""
         lib, h = _lib.load(), self._handle()
-        if self.reducer is not None:
+        if getattr(self, "_p2p", False):
+            _lib.check(lib.tmvb_flda_peer_reduce(h))                            # one kernel over peer memory (tmvb_peer.cu)
+        elif self.reducer is not None:
             p = [C.c_void_p() for _ in range(3)]
             n = [C.c_int64() for _ in range(3)]
             _lib.check(lib.tmvb_flda_reduce_buffers(h, C.byref(p[0]), C.byref(n[0]), C.byref(p[1]), C.byref(n[1]), C.byref(p[2]), C.byref(n[2])))
