@@ -515,6 +515,7 @@ __global__ void __launch_bounds__(32, 8) fctm_estep_kernel(const CtmDev p, int d
                     g01[m] = fma2(p01[m], t2, g01[m]);
                     g23[m] = fma2(p23[m], t2, g23[m]);
                 }
+                __syncwarp();   // every lane of the token has read tau before lane kl = 0 replaces it
                 if (ok && kl == 0) {
                     const float den = (eta + __ldg(p.kq + term) * ex2_ftz(-q * rs)) + TMVB_EPS;
                     __stcg(p.tau_old + o + nn, tau);

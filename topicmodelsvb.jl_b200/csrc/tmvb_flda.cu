@@ -169,6 +169,7 @@ __global__ void __launch_bounds__(32) flda_estep_kernel(const FldaDev p, int doc
                     g01[m] = fma2(p01[m], t2, g01[m]);
                     g23[m] = fma2(p23[m], t2, g23[m]);
                 }
+                __syncwarp();   // every lane of the token has read tau before lane kl = 0 replaces it
                 if (ok && kl == 0) {
                     // prod_i beta_i^(-phi_i) = 2^(-q / s); eps + eta + (1 - eta) kappa prod  (fLDA.jl:193, @boink on the whole denominator)
                     const float kq = in_tile ? kq_s[nn] : __ldg(p.kq + term);
