@@ -401,9 +401,26 @@ __device__ __forceinline__ void psi_pair_fast(float x0, float x1, float &p0, flo
 // s = init + sum_i T_i e_i over this lane's chunks in two FFMA2 chains (FFMA2 issues every other cycle, so two chains of a
 // round plus the other rounds in flight cover its latency), then across the LPT lanes of the token.  `init` carries K eps in
 // one lane of the token's group (the "@positive" epsilon of LDA.jl:150-154 summed over topics).
+#ifndef TMVB_V_DOT4
+#define TMVB_V_DOT4 0   // 1: four FFMA2 chains per dot product instead of two (A/B switch, tools/build_variants.sh)
+#endif
 template <int LPT, int CPL>
 __device__ __forceinline__ float tok_dot2(const ulonglong2 (&b)[CPL], const f32x2 (&e01)[CPL], const f32x2 (&e23)[CPL], f32x2 init)
 {
+#if TMVB_V_DOT4
+    f32x2 sa = init, sb = 0ull, sc = 0ull, sd = 0ull;
+#pragma unroll
+    for (int m = 0; m < CPL; m++) {
+        if (m & 1) {
+            sc = fma2(b[m].x, e01[m], sc);
+            sd = fma2(b[m].y, e23[m], sd);
+        } else {
+            sa = fma2(b[m].x, e01[m], sa);
+            sb = fma2(b[m].y, e23[m], sb);
+        }
+    }
+    return group_sum<LPT>(hsum2(add2(add2(sa, sc), add2(sb, sd))));
+#else
     f32x2 sa = init, sb = 0ull;
 #pragma unroll
     for (int m = 0; m < CPL; m++) {
@@ -411,6 +428,7 @@ __device__ __forceinline__ float tok_dot2(const ulonglong2 (&b)[CPL], const f32x
         sb = fma2(b[m].y, e23[m], sb);
     }
     return group_sum<LPT>(hsum2(add2(sa, sb)));
+#endif
 }
 
 // ---------------------------------------------------------------- hybrid documents: registers + shared-memory tile ----------
