@@ -56,7 +56,13 @@ static int ctm_kp(int K)
 // shared memory beyond the tile: mbarrier | gs [S][RS] | e_s [RS] | invsigma [K][KP] | L [K][KP] | vec [K_ld] | dinv [K_ld]
 // (invsigma stays in global memory -- read-only, shared by every CTA, L1/L2 resident: the kernel is bound by the latency of the
 // in-warp Cholesky chains, so what counts is how many documents an SM holds, i.e. shared memory per warp)
-static size_t ctm_fixed_smem(int RS, int lpt, int K, int K_ld) { return 16 + (size_t)(32 / lpt) * RS * 4 + (size_t)RS * 4 + (size_t)K * ctm_kp(K) * 4 + (size_t)2 * K_ld * 4; }
+// the register factorisation (K_ld <= 32) borrows L for its 32 x 33 row store and vec | dinv for its two 32-float column buffers
+__host__ __device__ constexpr int ctm_l_floats(int K, int KP, int K_ld) { return (K_ld <= 32 && K * KP < 32 * 33) ? 32 * 33 : K * KP; }
+__host__ __device__ constexpr int ctm_vd_floats(int K_ld) { return 2 * K_ld < 64 ? 64 : 2 * K_ld; }
+static size_t ctm_fixed_smem(int RS, int lpt, int K, int K_ld)
+{
+    return 16 + (size_t)(32 / lpt) * RS * 4 + (size_t)RS * 4 + (size_t)ctm_l_floats(K, ctm_kp(K), K_ld) * 4 + (size_t)ctm_vd_floats(K_ld) * 4;
+}
 
 
 // entry j of a vector distributed over the warp as v[r] on lane l for j = l + 32 r
@@ -140,6 +146,94 @@ __device__ __forceinline__ void warp_chol_solve(const float *L_s, const float *d
     }
 }
 
+// ---- K_ld <= 32: the whole factorisation in registers ------------------------------------------------------------------
+// Lane i keeps row i of the lower triangle (a[0..i]); right-looking Cholesky with the loops fully unrolled (KP = K_ld is a
+// compile-time constant of the lane layout), the column broadcast by shuffles: KP (KP - 1) / 2 x (SHFL + FFMA), no shared
+// memory, no loop or branch instructions.  The shared-memory version above spends ~2 900 warp-instructions per factorisation at
+// K = 30 (450 of them FFMA: chunk loops, address arithmetic, two warp barriers per column) and was 65 % of the E-step; this one
+// ~1 100.  Rows / columns beyond K are the identity.  dinv = 1 / l_ii of this lane's row.
+#ifndef TMVB_CTM_REGCHOL
+#define TMVB_CTM_REGCHOL 1   // 0: the shared-memory factorisation for every K (A/B switch)
+#endif
+template <int KP>
+__device__ __forceinline__ void reg_chol_load(const float *__restrict__ inv_s, int ldp, float w, int K, int lane, float (&a)[KP])
+{
+    if (lane < K) {
+        const float4 *row = reinterpret_cast<const float4 *>(inv_s + (size_t)lane * ldp);
+#pragma unroll
+        for (int c = 0; c < KP / 4; c++) {
+            const float4 v = (4 * c < K) ? __ldg(row + c) : make_float4(0.f, 0.f, 0.f, 0.f);   // pad columns of inv_s (j >= K) are zero
+            a[4 * c] = v.x;
+            a[4 * c + 1] = v.y;
+            a[4 * c + 2] = v.z;
+            a[4 * c + 3] = v.w;
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < KP; k++) a[k] = 0.0f;
+    }
+#pragma unroll
+    for (int k = 0; k < KP; k++)
+        if (k == lane) a[k] = (lane < K) ? a[k] + w : 1.0f;
+}
+// col_s: [2][32] floats of warp-private shared memory (column j of L is published there, double-buffered by the parity of j, and read
+// back as broadcast LDS.128: 32 shuffles + ~124 LDS.128 per factorisation instead of 496 shuffles -- the shuffle pipe was the limit)
+template <int KP>
+__device__ __forceinline__ float reg_cholesky(float (&a)[KP], int lane, float *col_s)
+{
+    float dinv = 1.0f;
+#pragma unroll
+    for (int j = 0; j < KP; j++) {
+        const float djj = __shfl_sync(0xffffffffu, a[j], j);
+        const float di = rsqrtf(fmaxf(djj, 1e-30f));
+        a[j] *= di;                       // l_ij for the lanes i >= j (lane j: sqrt(d_jj)); unused garbage above the diagonal
+        if (lane == j) dinv = di;
+        if (j + 1 < KP) {
+            float *cs = col_s + 32 * (j & 1);
+            cs[lane] = a[j];
+            __syncwarp();
+#pragma unroll
+            for (int c = (j + 1) / 4; c < KP / 4; c++) {
+                const float4 v = reinterpret_cast<const float4 *>(cs)[c];
+                if (4 * c + 0 > j) a[4 * c + 0] = fmaf(-a[j], v.x, a[4 * c + 0]);   // a_ik -= l_ij l_kj  (meaningful for i >= k)
+                if (4 * c + 1 > j) a[4 * c + 1] = fmaf(-a[j], v.y, a[4 * c + 1]);
+                if (4 * c + 2 > j) a[4 * c + 2] = fmaf(-a[j], v.z, a[4 * c + 2]);
+                if (4 * c + 3 > j) a[4 * c + 3] = fmaf(-a[j], v.w, a[4 * c + 3]);
+            }
+        }
+    }
+    __syncwarp();
+    return dinv;
+}
+// x = (L L')^-1 b, b distributed one entry per lane; L row-wise in registers as left by reg_cholesky.  Lt_s: [KP][33] floats of
+// warp-private shared memory: the rows of L are stored there once so that the back substitution reads column j of L' (= row
+// entries l_ij of the lanes i > j) as one conflict-free LDS per step instead of a five-step warp reduction.
+template <int KP>
+__device__ __forceinline__ float reg_chol_solve(const float (&a)[KP], float dinv, float b, int lane, float *Lt_s)
+{
+    if (lane < KP) {
+#pragma unroll
+        for (int k = 0; k < KP; k++) Lt_s[k * 33 + lane] = a[k];   // Lt_s[k][i] = l_ik: lanes write consecutive words
+    }
+#pragma unroll
+    for (int j = 0; j < KP; j++) {        // L y = b: lane j finishes y_j and broadcasts it
+        const float yj = __shfl_sync(0xffffffffu, b * dinv, j);
+        if (lane > j) b = fmaf(-a[j], yj, b);
+        if (lane == j) b = yj;
+    }
+    __syncwarp();
+#pragma unroll
+    for (int i = KP - 1; i >= 0; i--) {   // L' x = y: lane i finishes x_i and broadcasts it; lane j < i subtracts l_ij x_i
+        const float xi = __shfl_sync(0xffffffffu, b * dinv, i);
+        // l_ij of row i lives in lane i; lane j reads it from the row store: Lt_s[j][i] would be the transposed view of lane j's
+        // own registers, so read the copy lane i wrote: element (k = j, lane = i)
+        if (lane < i) b = fmaf(-Lt_s[lane * 33 + i], xi, b);
+        if (lane == i) b = xi;
+    }
+    __syncwarp();
+    return b;
+}
+
 #ifndef TMVB_CTM_MIN_CTAS
 #define TMVB_CTM_MIN_CTAS 16   // 128 registers per thread
 #endif
@@ -161,9 +255,9 @@ __global__ void __launch_bounds__(32, TMVB_CTM_MIN_CTAS) ctm_estep_kernel(const 
     float *e_s = gs + (size_t)S * RS;                      // [RS]
     float *L_s = e_s + RS;                                 // [K][KP]
     const float *inv_s = p.invsigma;                       // global: L1-resident, shared by all CTAs
-    float *vec_s = L_s + K * KP;                           // [K_ld]
-    float *dinv_s = vec_s + K_ld;                          // [K_ld]
-    float *tile = dinv_s + K_ld;                           // [cap][RS]
+    float *vec_s = L_s + ctm_l_floats(K, KP, K_ld);        // [K_ld]
+    float *dinv_s = vec_s + K_ld;                          // [K_ld]  (vec | dinv: at least 64 floats)
+    float *tile = vec_s + ctm_vd_floats(K_ld);             // [cap][RS]
     float *cnt_s = tile + (size_t)cap * RS;
     int *term_s = reinterpret_cast<int *>(cnt_s + cap);
 
@@ -338,8 +432,16 @@ __global__ void __launch_bounds__(32, TMVB_CTM_MIN_CTAS) ctm_estep_kernel(const 
                     }
                 }
                 gn = warp_sum(gn);
-                warp_cholesky<R>(inv_s, L_s, dinv_s, w_k, K, KP, lane);
-                warp_chol_solve<R>(L_s, dinv_s, grad_k, K, KP, lane);
+                if (TMVB_CTM_REGCHOL && 4 * LPT * CPL <= 32 && K_ld == 4 * LPT * CPL) {
+                    constexpr int KC = (4 * LPT * CPL <= 32) ? 4 * LPT * CPL : 4;   // (the second arm keeps the dead instantiation small)
+                    float a_row[KC];
+                    reg_chol_load<KC>(inv_s, KP, w_k[0], K, lane, a_row);
+                    const float di = reg_cholesky<KC>(a_row, lane, vec_s);           // vec | dinv: >= 64 floats (the gradient's vec_s is dead by now)
+                    grad_k[0] = reg_chol_solve<KC>(a_row, di, grad_k[0], lane, L_s);   // L_s: >= 32 * 33 floats (ctm_l_floats)
+                } else {
+                    warp_cholesky<R>(inv_s, L_s, dinv_s, w_k, K, KP, lane);
+                    warp_chol_solve<R>(L_s, dinv_s, grad_k, K, KP, lane);
+                }
 #pragma unroll
                 for (int r = 0; r < R; r++)
                     if (lane + 32 * r < K) lam_k[r] += grad_k[r];
@@ -415,9 +517,9 @@ __global__ void __launch_bounds__(32, 8) fctm_estep_kernel(const CtmDev p, int d
     float *e_s = gs + (size_t)S * RS;                      // [RS]
     float *L_s = e_s + RS;                                 // [K][KP]
     const float *inv_s = p.invsigma;
-    float *vec_s = L_s + K * KP;                           // [K_ld]
-    float *dinv_s = vec_s + K_ld;                          // [K_ld]
-    float *tile = dinv_s + K_ld;                           // [cap][RS]
+    float *vec_s = L_s + ctm_l_floats(K, KP, K_ld);        // [K_ld]
+    float *dinv_s = vec_s + K_ld;                          // [K_ld]  (vec | dinv: at least 64 floats)
+    float *tile = vec_s + ctm_vd_floats(K_ld);             // [cap][RS]
     float *cnt_s = tile + (size_t)cap * RS;
     int *term_s = reinterpret_cast<int *>(cnt_s + cap);
 
@@ -583,8 +685,16 @@ __global__ void __launch_bounds__(32, 8) fctm_estep_kernel(const CtmDev p, int d
                     }
                 }
                 gn = warp_sum(gn);
-                warp_cholesky<R>(inv_s, L_s, dinv_s, w_k, K, KP, lane);
-                warp_chol_solve<R>(L_s, dinv_s, grad_k, K, KP, lane);
+                if (TMVB_CTM_REGCHOL && 4 * LPT * CPL <= 32 && K_ld == 4 * LPT * CPL) {
+                    constexpr int KC = (4 * LPT * CPL <= 32) ? 4 * LPT * CPL : 4;   // (the second arm keeps the dead instantiation small)
+                    float a_row[KC];
+                    reg_chol_load<KC>(inv_s, KP, w_k[0], K, lane, a_row);
+                    const float di = reg_cholesky<KC>(a_row, lane, vec_s);           // vec | dinv: >= 64 floats (the gradient's vec_s is dead by now)
+                    grad_k[0] = reg_chol_solve<KC>(a_row, di, grad_k[0], lane, L_s);   // L_s: >= 32 * 33 floats (ctm_l_floats)
+                } else {
+                    warp_cholesky<R>(inv_s, L_s, dinv_s, w_k, K, KP, lane);
+                    warp_chol_solve<R>(L_s, dinv_s, grad_k, K, KP, lane);
+                }
 #pragma unroll
                 for (int r = 0; r < R; r++)
                     if (lane + 32 * r < K) lam_k[r] += grad_k[r];
