@@ -74,6 +74,15 @@ CONFIGS = {
 }
 DEFAULT_CONFIG = "nsf_lda_k50"
 
+# What the reference publishes for these workloads (wall-clock bar charts, Apple M1, values in plots.R:4) -- other
+# hardware, train! wall time of 10 iterations incl. everything; context only: `vs_baseline` stays null (no number for B200 / this metric)
+PUBLISHED = {
+    "nsf_lda_k50": {"source": "plots.R:4 (README chart images/gpubar.png), Apple M1, 10 outer iterations of train! on NSF K=50",
+                    "reference_cpu_LDA_seconds_per_10_iterations": 444.0, "reference_gpuLDA_opencl_seconds_per_10_iterations": 26.0,
+                    "reference_gpuLDA_opencl_docs_per_sec_upper_bound": 49540.0,
+                    "compare_with": "e2e_iter10 of this line (one train(iter=10) call incl. update_buffer! / update_host!)"},
+}
+
 
 # ------------------------------------------------------------------------------------------------ corpora --------
 def load_corpus(synth, cfg, rank, world, data):
@@ -410,6 +419,7 @@ def measure(tm, torch, args, name, rank, local, world, reducer, work_stream, pea
                    "exchange": ("none (one GPU)" if world == 1 else
                                 "fused peer-memory kernel (reduce-scatter + normalise + all-gather over NVLink)"
                                 if getattr(model, "_p2p", False) else "NCCL all-reduce + normalisation kernels")},
+        "published_context": PUBLISHED.get(name),
         "vi_iterations_per_sec": 1e3 / ms_per_step,
         "estep_docs_per_sec": M_total / (est_ms * 1e-3),
         "sweeps_per_doc": float(np.mean(sweeps)) / (M_total if world > 1 else shard.M),
