@@ -352,11 +352,16 @@ __global__ void __launch_bounds__(32) ctpf_estep_kernel(const CtpfDev p, int doc
 // x = prior + stats (one warp per table row): raw <- x, table <- exp(psi(x) - rowmax), stats <- 0, and per-topic sums
 // acc = [sum psi(x) (K_ld) | sum x (K_ld) | sum lnG(x) + (1-x) psi(x) (K_ld) | sum stats psi(x) (1)]
 // (update_alef!/update_he! CTPF.jl:251-270 + the table of exp(psi) the sweeps read + the global ELBO sums CTPF.jl:143-168,197-221)
+// RMAX = topics per lane (ceil(K / 32) rounded up to 1 / 2 / 4 / 8).  The per-topic sums are reduced in shared memory per CTA before
+// they reach the global accumulators (one warp per row with its own 3 K global fp64 atomics made the 8 000-row alef table cost 65 us).
+template <int RMAX>
 __global__ void ctpf_table_kernel(float *__restrict__ stats, float prior, float *__restrict__ raw, float *__restrict__ table, int rows,
                                   int K, int K_ld, double *__restrict__ acc, int zero_stats)
 {
+    extern __shared__ double tsh[];   // [3 K_ld + 1]
     const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
-    constexpr int RMAX = 8;
+    for (int q = threadIdx.x; q < 3 * K_ld + 1; q += blockDim.x) tsh[q] = 0.0;
+    __syncthreads();
     double t1[RMAX], t2[RMAX], t3[RMAX], t4 = 0.0;
 #pragma unroll
     for (int r = 0; r < RMAX; r++) t1[r] = t2[r] = t3[r] = 0.0;
@@ -395,13 +400,16 @@ __global__ void ctpf_table_kernel(float *__restrict__ stats, float prior, float 
     for (int r = 0; r < RMAX; r++) {
         const int i = lane + 32 * r;
         if (i < K) {
-            atomicAdd(acc + i, t1[r]);
-            atomicAdd(acc + K_ld + i, t2[r]);
-            atomicAdd(acc + 2 * K_ld + i, t3[r]);
+            atomicAdd(tsh + i, t1[r]);
+            atomicAdd(tsh + K_ld + i, t2[r]);
+            atomicAdd(tsh + 2 * K_ld + i, t3[r]);
         }
     }
     t4 = warp_sum_d(t4);
-    if (lane == 0 && t4 != 0.0) atomicAdd(acc + 3 * K_ld, t4);
+    if (lane == 0 && t4 != 0.0) atomicAdd(tsh + 3 * K_ld, t4);
+    __syncthreads();
+    for (int q = threadIdx.x; q < 3 * K_ld + 1; q += blockDim.x)
+        if (tsh[q] != 0.0) atomicAdd(acc + q, tsh[q]);
 }
 
 // update_elbo! restated (CTPF.jl:232-247) per document: phi / xi from the *_old state (A_old, H_old, gimel_old, zayin_old,
@@ -650,7 +658,11 @@ int ctpf_build_table(tmvb_ctpf_t h, int which, float prior, int zero_stats)
     float *stats = which == 0 ? s.d_stats : h->d_hstats;
     float *raw = which == 0 ? h->d_alef : h->d_he;
     float *table = which == 0 ? s.d_beta[s.cur] : h->d_H[h->hcur];
-    ctpf_table_kernel<<<std::min((rows + 7) / 8, s.n_sm * 8), 256, 0, s.stream>>>(stats, prior, raw, table, rows, (int)s.K, s.K_ld, acc, zero_stats);
+    const int grid = std::max(1, std::min((rows + 31) / 32, s.n_sm * 4));   // >= 4 rows per warp
+    const size_t tsm = (size_t)(3 * s.K_ld + 1) * 8;
+#define TMVB_CTPF_TABLE(R) ctpf_table_kernel<R><<<grid, 256, tsm, s.stream>>>(stats, prior, raw, table, rows, (int)s.K, s.K_ld, acc, zero_stats)
+    if (s.K <= 32) TMVB_CTPF_TABLE(1); else if (s.K <= 64) TMVB_CTPF_TABLE(2); else if (s.K <= 128) TMVB_CTPF_TABLE(4); else TMVB_CTPF_TABLE(8);
+#undef TMVB_CTPF_TABLE
     TMVB_CUDA(cudaGetLastError());
     s.st.kernel_launches++;
     return 0;
