@@ -216,3 +216,52 @@ def test_ctpf_recommendations_follow_the_reference_loops(tm):
         want = idx[np.argsort(scores[d, idx], kind="stable")[::-1]] + 1
         np.testing.assert_array_equal(m.drecs[d], want)
     assert len(m.drecs) == c.M and len(m.urecs) == c.U
+
+
+def test_filtered_model_constructors_and_check_model(tm):
+    """gpufLDA / gpufCTM host mirrors (fields of fLDA.jl:6-58 / fCTM.jl:6-64) and check_model(::fLDA) (modelutils.jl:69-98) without a
+    device: initial state, shapes, the keyword validation of train!, and that train! on an all-empty corpus returns without
+    touching the library (fLDA.jl:219)."""
+    import pytest
+
+    c = tm.synth.gencorp_lda(M=12, V=40, K=3, seed=2)
+    m = tm.gpufLDA(tm.Corpus.from_csr(c), 4, seed=0)
+    assert m.eta == 0.5 and m.alpha.shape == (4,) and m.kappa.shape == (c.V,) and abs(float(m.kappa.sum()) - 1) < 1e-5
+    assert m.beta.shape == (4, c.V) and m.Elogtheta.shape == (4, c.M) and m.gamma.shape == (4, c.M)
+    assert m.tau.shape == (len(c.terms),) and np.all(m.tau == 0.5) and np.all(m.tau_old == 0.5)
+    np.testing.assert_array_equal(m.tau_of(3), m.tau[c.N_cumsum[3]:c.N_cumsum[4]])
+    np.testing.assert_allclose(m.beta.sum(axis=1), 1.0, rtol=1e-5)
+    tm.check_model(m)
+    m.eta = 1.2
+    with pytest.raises(tm.TopicModelError, match="eta must belong"):
+        tm.check_model(m)
+    m.eta = 0.5
+    m.alpha = np.array([1, 1, -1, 1], np.float32)
+    with pytest.raises(tm.TopicModelError, match="alpha must be positive"):
+        tm.check_model(m)
+    m.alpha = np.ones(4, np.float32)
+    m.kappa = np.full(c.V, 1.0, np.float32)
+    with pytest.raises(tm.TopicModelError, match="kappa must be a probability vector"):
+        tm.check_model(m)
+    m = tm.gpufLDA(tm.Corpus.from_csr(c), 4, seed=0)
+    for kw in (dict(tol=-1.0), dict(iter=-1), dict(checkelbo=0), dict(viter=0)):
+        with pytest.raises(ValueError):
+            tm.train(m, printelbo=False, **kw)
+    with pytest.raises(ValueError, match="positive integer"):
+        tm.gpufLDA(tm.Corpus.from_csr(c), 0)
+    fc = tm.gpufCTM(tm.Corpus.from_csr(c), 4, seed=0)
+    assert isinstance(fc, tm.gpuCTM) and fc.eta == 0.5 and fc.kappa.shape == (c.V,) and fc.tau.shape == (len(c.terms),)
+    assert fc.lam.shape == (4, c.M) and np.all(fc.vsq == 1) and np.all(fc.logzeta == 0.5)
+    tm.check_model(fc)
+    # an all-empty corpus: iter = 0, nothing is uploaded (no device is needed)
+    empty = tm.synth.CSR(3, 10, np.zeros(4, np.int64), np.zeros(0, np.int64), np.zeros(0, np.int64))
+    me = tm.gpufLDA(tm.Corpus.from_csr(empty), 2)
+    tm.train(me, iter=5, printelbo=False)
+    assert me.elbo == 0.0 and [len(t) for t in me.topics] == [10, 10]
+
+
+def test_connect_model_peers_single_rank_is_a_no_op(tm):
+    """dist.connect_model_peers: no reducer / one rank / TMVB_P2P=0 keep the NCCL path without touching the library."""
+    class _M:
+        reducer, _h = None, None
+    assert tm.dist.connect_model_peers(_M(), "ctm") is False
