@@ -246,3 +246,30 @@ def test_filtered_predict(tm, orc):
     pc = tm.predict(tm.Corpus.from_csr(new_c), mc, iter=10)
     assert np.all(np.isfinite(pc.lam)) and np.all(pc.vsq > 0) and np.all((pc.tau >= 0) & (pc.tau <= 1))
     np.testing.assert_allclose(pc.beta, mc.beta)
+
+
+@pytest.mark.parametrize("case", ["flda_cfg", "fctm_cfg"])
+def test_filtered_against_committed_golden(tm, case):
+    """tests/golden/{flda_cfg,fctm_cfg}.npz: generated by tools/make_golden.py from both oracle restatements (C and numpy twin);
+    the same inputs are exported for the real reference under tests/golden/reference/inputs (tools/reference_golden.jl)."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", case + ".npz"))
+    K, V = int(g["K"]), int(g["V"])
+    c = tm.synth.CSR(len(g["N_cumsum"]) - 1, V, g["N_cumsum"], g["terms"].astype(np.int64), g["counts"].astype(np.int64))
+    model = (tm.gpufLDA if case == "flda_cfg" else tm.gpufCTM)(tm.Corpus.from_csr(c), K)
+    model.beta = np.array(g["beta0"].T, dtype=np.float32, order="F")
+    model.kappa = g["kappa0"].astype(np.float32)
+    tr = []
+    tm.train(model, iter=len(g["elbo"]) - 1, tol=0.0, printelbo=False, trace=tr)
+    np.testing.assert_allclose(tr, g["elbo"][: len(tr)], rtol=ELBO_RTOL)
+    assert len(tr) == len(g["elbo"])
+    np.testing.assert_allclose(model.kappa, g["kappa"], rtol=5e-3, atol=1e-7)
+    np.testing.assert_allclose(model.beta.T, g["beta"], rtol=1e-2, atol=1e-6)
+    np.testing.assert_allclose(model.tau, g["tau"], rtol=5e-3, atol=1e-5)
+    if case == "flda_cfg":
+        assert abs(model.eta - float(np.ravel(g["eta"])[0])) < 1e-4
+        np.testing.assert_allclose(model.alpha, g["alpha"], rtol=2e-3)
+        np.testing.assert_allclose(model.gamma.T, g["gamma"], rtol=5e-3, atol=1e-4)
+    else:
+        np.testing.assert_allclose(model.mu, g["mu"], rtol=5e-3, atol=1e-4)
+        np.testing.assert_allclose(model.sigma, g["sigma"], rtol=1e-2, atol=1e-3)

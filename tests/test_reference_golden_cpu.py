@@ -12,7 +12,7 @@ import pytest
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 REF = os.path.join(HERE, "golden", "reference")
-CASES = [("lda_cfg0", "beta0"), ("ctm_cfg", "beta0"), ("ctpf_cfg", "alef0")]
+CASES = [("lda_cfg0", "beta0"), ("ctm_cfg", "beta0"), ("ctpf_cfg", "alef0"), ("flda_cfg", "beta0"), ("fctm_cfg", "beta0")]
 
 
 @pytest.mark.parametrize("case,key", CASES)
@@ -33,6 +33,9 @@ def test_exported_inputs_match_the_golden_cases(case, key):
         np.testing.assert_array_equal(counts, z["counts"][off[d]:off[d + 1]])
     if "R_cumsum" in z:
         np.testing.assert_array_equal(np.array(meta["readers"]) - 1, z["readers"])
+    if "kappa0" in z:
+        kap = np.fromfile(os.path.join(REF, "inputs", case + "_kappa.f64"), dtype="<f8")
+        np.testing.assert_array_equal(kap, np.asarray(z["kappa0"], dtype=np.float64))
 
 
 @pytest.mark.parametrize("case,key", CASES)
@@ -49,6 +52,6 @@ def test_oracle_matches_the_reference_dump(case, key):
     K, V = int(z["K"]), int(z["V"])
     table = "alef" if case == "ctpf_cfg" else "beta"
     np.testing.assert_allclose(np.asarray(z[table]).reshape(V, K), np.array(ref[table]).reshape(V, K), rtol=1e-7, atol=1e-300)
-    for name in ("alpha", "mu", "bet", "vav", "dalet", "het"):
+    for name in ("alpha", "mu", "bet", "vav", "dalet", "het", "kappa", "eta", "tau"):
         if name in ref and name in z:
             np.testing.assert_allclose(np.asarray(z[name]), np.array(ref[name]), rtol=1e-7)

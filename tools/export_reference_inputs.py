@@ -30,7 +30,8 @@ def write_docs(path, z, readers):
 
 def main():
     os.makedirs(OUT, exist_ok=True)
-    for case, model, key, iters in (("lda_cfg0", "LDA", "beta0", 20), ("ctm_cfg", "CTM", "beta0", 8), ("ctpf_cfg", "CTPF", "alef0", 8)):
+    for case, model, key, iters in (("lda_cfg0", "LDA", "beta0", 20), ("ctm_cfg", "CTM", "beta0", 8), ("ctpf_cfg", "CTPF", "alef0", 8),
+                                    ("flda_cfg", "fLDA", "beta0", 8), ("fctm_cfg", "fCTM", "beta0", 6)):
         z = np.load(os.path.join(ROOT, "tests", "golden", case + ".npz"))
         readers = "R_cumsum" in z
         if readers and any(z["R_cumsum"][d + 1] == z["R_cumsum"][d] for d in range(len(z["R_cumsum"]) - 1)):
@@ -43,6 +44,8 @@ def main():
         assert table.shape == (V, K)
         table.astype("<f8").tofile(os.path.join(OUT, case + "_init.f64"))
         meta = dict(model=model, K=K, V=V, M=int(len(z["N_cumsum"]) - 1), iter=iters, viter=10, init_field="alef" if model == "CTPF" else "beta")
+        if "kappa0" in z:   # the filtered models: the injected initial kappa (fLDA.jl:41 / fCTM.jl:50 draw it from Julia's RNG)
+            np.asarray(z["kappa0"], dtype="<f8").tofile(os.path.join(OUT, case + "_kappa.f64"))
         if readers:
             meta["U"] = int(z["U"])
             meta["R_cumsum"] = [int(x) for x in z["R_cumsum"]]

@@ -14,7 +14,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import oracle  # noqa: E402
-from oracle.numpy_twin import CTMTwin, CTPFTwin, LDATwin  # noqa: E402
+from oracle.numpy_twin import CTMTwin, CTPFTwin, FCTMTwin, FLDATwin, LDATwin  # noqa: E402
 import topicmodelsvb_b200.synth as synth  # noqa: E402
 
 
@@ -60,11 +60,46 @@ def ctpf_cfg():
                 gimel=st.gimel, zayin=st.zayin)
 
 
+def flda_cfg():
+    """Filtered LDA (fLDA.jl): M=80, V=300, K=5, iter=8; kappa0 injected like beta0."""
+    K = 5
+    c = synth.gencorp_lda(M=80, V=300, K=4, seed=2)
+    beta0 = synth.init_beta(K, c.V, seed=7)
+    kappa0 = np.random.default_rng(8).dirichlet(np.ones(c.V))
+    st = oracle.FLDAState(K, c.M, c.V, len(c.terms), beta0, kappa0)
+    trace, sweeps, _ = oracle.flda_train(st, c.N_cumsum, c.terms, c.counts, iter=8, tol=0.0)
+    tw = FLDATwin(c.N_cumsum, c.terms, c.counts, K, c.V, beta0, kappa0)
+    assert np.max(np.abs(trace - tw.train(iter=8, tol=0.0)) / np.abs(trace)) < 1e-12
+    return dict(K=K, V=c.V, N_cumsum=c.N_cumsum, terms=c.terms.astype(np.int32), counts=c.counts.astype(np.int32), beta0=beta0, kappa0=kappa0,
+                elbo=trace, sweeps=sweeps, eta=st.eta, alpha=st.alpha, kappa=st.kappa, beta=st.beta, gamma=st.gamma, tau=st.tau)
+
+
+def fctm_cfg():
+    """Filtered CTM (fCTM.jl): M=60, V=300, K=6, iter=6."""
+    K = 6
+    c = synth.gencorp_lda(M=60, V=300, K=4, seed=3)
+    beta0 = synth.init_beta(K, c.V, seed=7)
+    kappa0 = np.random.default_rng(8).dirichlet(np.ones(c.V))
+    st = oracle.FCTMState(K, c.M, c.V, len(c.terms), beta0, kappa0)
+    trace, sweeps, _ = oracle.fctm_train(st, c.N_cumsum, c.terms, c.counts, iter=6, tol=0.0)
+    tw = FCTMTwin(c.N_cumsum, c.terms, c.counts, K, c.V, beta0, kappa0)
+    assert np.max(np.abs(trace - tw.train(iter=6, tol=0.0)) / np.abs(trace)) < 1e-10
+    return dict(K=K, V=c.V, N_cumsum=c.N_cumsum, terms=c.terms.astype(np.int32), counts=c.counts.astype(np.int32), beta0=beta0, kappa0=kappa0,
+                elbo=trace, sweeps=sweeps, mu=st.mu, sigma=st.sigma, kappa=st.kappa, beta=st.beta, lam=st.lam, vsq=st.vsq, tau=st.tau)
+
+
 if __name__ == "__main__":
     out = os.path.join(ROOT, "tests", "golden")
     os.makedirs(out, exist_ok=True)
+    only = set(sys.argv[1:])     # e.g. `python tools/make_golden.py flda_cfg fctm_cfg` leaves the other fixtures untouched
+    if only:
+        for name in only:
+            np.savez_compressed(os.path.join(out, name + ".npz"), **globals()[name]())
+        sys.exit(0)
     np.savez_compressed(os.path.join(out, "lda_cfg0.npz"), **lda_cfg0())
     np.savez_compressed(os.path.join(out, "ctm_cfg.npz"), **ctm_cfg())
     np.savez_compressed(os.path.join(out, "ctpf_cfg.npz"), **ctpf_cfg())
+    np.savez_compressed(os.path.join(out, "flda_cfg.npz"), **flda_cfg())
+    np.savez_compressed(os.path.join(out, "fctm_cfg.npz"), **fctm_cfg())
     for f in sorted(os.listdir(out)):
         print(f, os.path.getsize(os.path.join(out, f)), "bytes")

@@ -4,13 +4,13 @@
 # the oracle is "parity unpinned" until somebody runs this once and commits the three small JSON files it writes:
 #
 #     python tools/export_reference_inputs.py          # tests/golden/reference/inputs/*  (already committed)
-#     julia tools/reference_golden.jl                  # tests/golden/reference/{lda_cfg0,ctm_cfg,ctpf_cfg}.json
+#     julia tools/reference_golden.jl                  # tests/golden/reference/{lda_cfg0,ctm_cfg,ctpf_cfg,flda_cfg,fctm_cfg}.json
 #     python -m pytest tests/test_reference_golden_cpu.py
 #
 # For every case it loads the corpus with the reference's own `readcorp`, builds the reference's CPU model, INJECTS the initial
 # topic table (Julia's RNG stream cannot be reproduced elsewhere; everything else in the constructors is deterministic:
 # LDA.jl:34-44, CTM.jl:38-49, CTPF.jl:81-103), then runs the real `train!` one outer iteration at a time
-# (`train!(model, iter=1, tol=0, checkelbo=1)`: LDA.jl:161-191, CTM.jl:185-217, CTPF.jl:344-402) recording `model.elbo`
+# (`train!(model, iter=1, tol=0, checkelbo=1)`: LDA.jl:161-191, CTM.jl:185-217, CTPF.jl:344-402, fLDA.jl:214-247, fCTM.jl:249-290) recording `model.elbo`
 # after each, and finally dumps the trace and the trained parameters.
 using TopicModelsVB, JSON, LinearAlgebra
 
@@ -36,27 +36,34 @@ function load_case(case)
 	return meta, corp, init
 end
 
-function run_case(case)
-	meta, corp, init = load_case(case)
-	K = meta["K"]
-	model = meta["model"] == "LDA" ? LDA(corp, K) : meta["model"] == "CTM" ? CTM(corp, K) : CTPF(corp, K)
+function build(meta, corp, init, case)
+	K, V = meta["K"], meta["V"]
+	ctor = Dict("LDA" => LDA, "CTM" => CTM, "CTPF" => CTPF, "fLDA" => fLDA, "fCTM" => fCTM)[meta["model"]]
+	model = ctor(corp, K)
 	if meta["model"] == "CTPF"
 		model.alef = copy(init); model.alef_old = copy(init)
 	else
 		model.beta = copy(init); model.beta_old = copy(init)
 	end
+	if meta["model"] in ("fLDA", "fCTM")                  # the injected initial kappa (fLDA.jl:41-42, fCTM.jl:50-51)
+		kappa = Vector{Float64}(undef, V)
+		read!(joinpath(IN, case * "_kappa.f64"), kappa)
+		model.kappa = copy(kappa); model.kappa_old = copy(kappa)
+	end
+	return model
+end
+
+function run_case(case)
+	meta, corp, init = load_case(case)
+	K = meta["K"]
+	model = build(meta, corp, init, case)
 	trace = Float64[]
 	for k in 1:meta["iter"]
 		train!(model, iter=1, tol=0.0, viter=meta["viter"], checkelbo=1, printelbo=false)
 		push!(trace, model.elbo)
 	end
 	# the ELBO of the initial state: a fresh model, train!(iter=0) does not evaluate it, so call update_elbo! directly
-	m0 = meta["model"] == "LDA" ? LDA(corp, K) : meta["model"] == "CTM" ? CTM(corp, K) : CTPF(corp, K)
-	if meta["model"] == "CTPF"
-		m0.alef = copy(init); m0.alef_old = copy(init)
-	else
-		m0.beta = copy(init); m0.beta_old = copy(init)
-	end
+	m0 = build(meta, corp, init, case)
 	elbo0 = TopicModelsVB.update_elbo!(m0)
 	out = Dict{String,Any}("case" => case, "model" => meta["model"], "elbo" => [elbo0; trace],
 		"julia" => string(VERSION), "package" => "TopicModelsVB")
@@ -70,6 +77,20 @@ function run_case(case)
 		out["beta"] = vec(model.beta)
 		out["lambda"] = vcat(model.lambda...)
 		out["vsq"] = vcat(model.vsq...)
+	elseif meta["model"] == "fLDA"
+		out["eta"] = model.eta
+		out["alpha"] = model.alpha
+		out["kappa"] = model.kappa
+		out["beta"] = vec(model.beta)
+		out["gamma"] = vcat(model.gamma...)
+		out["tau"] = vcat(model.tau...)
+	elseif meta["model"] == "fCTM"
+		out["mu"] = model.mu
+		out["sigma"] = vec(Matrix(model.sigma))
+		out["kappa"] = model.kappa
+		out["beta"] = vec(model.beta)
+		out["lambda"] = vcat(model.lambda...)
+		out["tau"] = vcat(model.tau...)
 	else
 		out["alef"] = vec(model.alef)
 		out["he"] = vec(model.he)
@@ -83,6 +104,6 @@ function run_case(case)
 	println(case, ": ELBO ", out["elbo"][1], " -> ", out["elbo"][end])
 end
 
-for case in ("lda_cfg0", "ctm_cfg", "ctpf_cfg")
+for case in ("lda_cfg0", "ctm_cfg", "ctpf_cfg", "flda_cfg", "fctm_cfg")
 	run_case(case)
 end
