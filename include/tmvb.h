@@ -137,6 +137,12 @@ int tmvb_lda_elbo(tmvb_lda_t h, int mode, int64_t M_total, double *elbo_docs, do
 
 /* update_host!(model::gpuLDA) (modelutils.jl:501-514): any pointer may be NULL. */
 int tmvb_lda_download(tmvb_lda_t h, float *alpha, float *beta, float *Elogtheta, float *gamma);
+/* The Elogtheta / gamma half of update_host! (modelutils.jl:507-512) folded into the last E-step of a train! call: with the
+ * mirror armed, the NEXT tmvb_lda_estep / tmvb_lda_iterate also writes every document's final rows straight into these
+ * page-locked, device-mapped K x M arrays (tmvb_alloc_pinned, cudaHostAlloc or cudaHostRegister memory) while the other
+ * documents are still being swept, and a following tmvb_lda_download with the same two pointers only waits for the stream
+ * instead of copying them.  One-shot; (NULL, NULL) disarms; any later E-step or upload makes download copy again. */
+int tmvb_lda_arm_host_mirror(tmvb_lda_t h, float *Elogtheta, float *gamma);
 /* the lagged copies the CPU struct keeps (LDA.jl:17,20): beta_old, Elogtheta_old */
 int tmvb_lda_download_old(tmvb_lda_t h, float *beta_old, float *Elogtheta_old);
 /* phi of every document, K x sumN column-major, original token order (modelutils.jl:515-516) */

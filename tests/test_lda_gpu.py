@@ -313,3 +313,73 @@ def test_lda_k200_layout(tm, orc):
     model, trace, st, ref, _ = _run_pair(tm, orc, c, 200, iters=3)
     np.testing.assert_allclose(trace, ref, rtol=ELBO_RTOL)
     np.testing.assert_allclose(model.gamma.T, st.gamma, rtol=2e-3, atol=1e-6)
+
+
+@pytest.mark.parametrize("K,M,lens", [(50, 3000, (1, 300)), (51, 700, (1, 120)), (5, 600, (1, 200)), (200, 400, (1, 260)), (7, 300, (0, 40))])
+def test_host_mirror_equals_download(tm, monkeypatch, K, M, lens):
+    """update_host! folded into the last E-step (tmvb_lda_arm_host_mirror): gamma / Elogtheta written by the E-step kernels into the
+    page-locked arrays must be bit-identical to what tmvb_lda_download copies (same kernels, same values), for the hybrid kernel
+    (K=50, odd K=51, K=200), the generic one (K=5, 7), documents of every length class incl. empty ones, and across repeated
+    train! calls on one model (whose Elogtheta / gamma then ARE the mirrored arrays)."""
+    rng = np.random.default_rng(K)
+    V = 900
+    n = rng.integers(lens[0], lens[1] + 1, size=M)
+    n[:3] = lens[1]
+    off = np.concatenate([[0], np.cumsum(n)]).astype(np.int64)
+    terms = np.concatenate([rng.choice(V, size=k, replace=False) for k in n] + [np.zeros(0, np.int64)]).astype(np.int64)
+    counts = rng.integers(1, 5, size=len(terms)).astype(np.int64)
+    c = tm.synth.CSR(M, V, off, terms, counts)
+    beta0 = tm.synth.init_beta(K, V, seed=3).astype(np.float32)
+    lib = tm._lib.load()
+
+    def device_copy(model):
+        E, g = np.empty((K, M), np.float32, order="F"), np.empty((K, M), np.float32, order="F")
+        tm._lib.check(lib.tmvb_lda_download(model._handle(), None, None, E.ctypes.data, g.ctypes.data))   # other pointers: a plain copy
+        return E, g
+
+    out = {}
+    for mirror in ("1", "0"):
+        monkeypatch.setenv("TMVB_HOST_MIRROR", mirror)
+        model = tm.gpuLDA(tm.Corpus.from_csr(c), K)
+        model.beta = np.array(beta0.T, order="F", copy=True)
+        tr = []
+        d2h = []
+        for kw in (dict(iter=3, tol=0.0), dict(iter=2, tol=0.0),    # the second call uploads out of the mirrored arrays
+                   dict(iter=5, tol=1e30)):                          # stops at k = 1 < iter: the mirror is never armed
+            d0 = model.stats().d2h_bytes
+            tm.train(model, printelbo=False, trace=tr, **kw)
+            d2h.append(model.stats().d2h_bytes - d0)
+            E, g = device_copy(model)
+            # the rows the kernels wrote over the bus ARE the device rows (the statistics' atomics make two runs differ in the last
+            # bits, so the bit-exact comparison is within one run)
+            np.testing.assert_array_equal(model.Elogtheta, E)
+            np.testing.assert_array_equal(model.gamma, g)
+            tm.check_model(model)
+        out[mirror] = (np.array(model.gamma), np.array(model.Elogtheta), np.array(model.beta), np.array(tr), d2h)
+        model.close()
+    for a, b in zip(out["1"][:4], out["0"][:4]):
+        np.testing.assert_allclose(a, b, rtol=2e-4, atol=1e-6)
+    assert out["1"][4] == out["0"][4]            # the bytes the kernels wrote over the bus are counted like the copies they replace
+
+
+def test_host_mirror_argument_errors(tm):
+    import ctypes as C
+    c = tm.synth.gencorp_lda(M=50, V=200, K=4, seed=1)
+    model = tm.gpuLDA(tm.Corpus.from_csr(c), 6)
+    model.update_buffer()
+    lib, h = tm._lib.load(), model._handle()
+    pageable = np.zeros((6, 50), np.float32, order="F")
+    pinned = tm._lib.pinned_empty((6, 50), np.float32, order="F")
+    assert lib.tmvb_lda_arm_host_mirror(h, pageable.ctypes.data, pinned.ctypes.data) != 0
+    assert "page-locked" in lib.tmvb_last_error().decode()
+    assert lib.tmvb_lda_arm_host_mirror(h, pinned.ctypes.data, None) != 0
+    assert lib.tmvb_lda_arm_host_mirror(h, None, None) == 0
+    g = tm._lib.pinned_empty((6, 50), np.float32, order="F")
+    assert lib.tmvb_lda_arm_host_mirror(h, pinned.ctypes.data, g.ctypes.data) == 0
+    model.estep(10, 1e-3, want_elbo=False)
+    E2, g2 = np.empty((6, 50), np.float32, order="F"), np.empty((6, 50), np.float32, order="F")
+    tm._lib.check(lib.tmvb_lda_download(h, None, None, E2.ctypes.data, g2.ctypes.data))   # other pointers: a plain copy
+    tm._lib.check(lib.tmvb_lda_download(h, None, None, pinned.ctypes.data, g.ctypes.data))  # the mirrored ones: only a wait
+    np.testing.assert_array_equal(E2, pinned)
+    np.testing.assert_array_equal(g2, g)
+    assert np.all(g > 0) and np.all(pinned <= 0)

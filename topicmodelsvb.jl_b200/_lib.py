@@ -102,6 +102,7 @@ SIGNATURES = {
     "tmvb_lda_iterate": (C.c_int, [_vp, C.c_int, C.c_float, C.c_int, C.c_int64, C.c_int, C.c_double, C.POINTER(C.c_double)]),
     "tmvb_lda_elbo": (C.c_int, [_vp, C.c_int, C.c_int64, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "tmvb_lda_download": (C.c_int, [_vp, _vp, _vp, _vp, _vp]),
+    "tmvb_lda_arm_host_mirror": (C.c_int, [_vp, _vp, _vp]),
     "tmvb_lda_download_old": (C.c_int, [_vp, _vp, _vp]),
     "tmvb_lda_materialize_phi": (C.c_int, [_vp, _vp]),
     "tmvb_lda_topics": (C.c_int, [_vp, _vp]),

@@ -72,7 +72,7 @@ int tmvb_alloc_pinned(void **ptr, int64_t bytes)
 {
     TMVB_CHECK_ARG(ptr != nullptr && bytes >= 0, "bad pinned allocation request");
     *ptr = nullptr;
-    TMVB_CUDA(cudaHostAlloc(ptr, (size_t)(bytes > 0 ? bytes : 1), cudaHostAllocDefault));
+    TMVB_CUDA(cudaHostAlloc(ptr, (size_t)(bytes > 0 ? bytes : 1), cudaHostAllocPortable | cudaHostAllocMapped));
     return 0;
 }
 

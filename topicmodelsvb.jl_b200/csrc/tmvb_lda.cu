@@ -776,9 +776,27 @@ struct tmvb_lda_s {
     bool solo = true;                   // no other rank: nothing sums `small` between the E-step and update_alpha!
     std::vector<Shard::LaunchGraph> iter_graphs;   // captured outer iterations (tmvb_lda_iterate), keyed like the E-step graphs
     Comm comm;                          // peer-memory exchange (multi-GPU), see tmvb_comm.cuh
+    // host mirror (tmvb_lda_arm_host_mirror): the caller's page-locked Elogtheta / gamma arrays as the device sees them, armed for
+    // the next E-step; mirror_valid = those arrays hold the rows of the last E-step (tmvb_lda_download then skips their transfer)
+    float *mirror_E = nullptr, *mirror_gamma = nullptr, *mirror_E_host = nullptr, *mirror_gamma_host = nullptr;
+    bool mirror_armed = false, mirror_valid = false;
 };
 
 namespace {
+
+// the armed host mirror rides with the next E-step only (the rows every other E-step writes would be overwritten anyway)
+void take_mirror(tmvb_lda_t h, LdaDev *p)
+{
+    h->mirror_valid = false;
+    if (!h->mirror_armed) return;
+    h->mirror_armed = false;
+    if (h->no_scatter) return;
+    p->host_E = h->mirror_E;
+    p->host_gamma = h->mirror_gamma;
+    p->perm = h->s.d_perm;
+    h->mirror_valid = true;
+    h->s.st.d2h_bytes += 2 * h->s.M * h->s.K * 4;   // written over the bus by the E-step kernels
+}
 
 LdaDev dev_view(tmvb_lda_t h)
 {
@@ -1066,6 +1084,7 @@ int tmvb_lda_upload(tmvb_lda_t h, const float *alpha, const float *beta, const f
     }
     if ((Elogtheta || gamma) && s.M > 0) {
         TMVB_CHECK_ARG(s.corpus_set, "set_corpus must precede the upload of per-document parameters");
+        h->mirror_valid = false;
         TMVB_TRY(shard_upload_rows(&s, Elogtheta, h->d_Elogtheta, s.M, s.d_perm, 1));
         // Elogtheta_old = deepcopy(Elogtheta)  (LDA.jl:39)
         if (Elogtheta)
@@ -1097,6 +1116,7 @@ int tmvb_lda_estep(tmvb_lda_t h, int viter, float vtol, int want_elbo)
     LdaDev p = dev_view(h);
     p.viter = viter;
     p.vtol = vtol;
+    take_mirror(h, &p);
     TMVB_CUDA(cudaEventRecord(s.ev[0], s.stream));
     TMVB_CUDA(cudaMemsetAsync(h->d_small, 0, (s.K_ld + 2) * 8, s.stream));
     h->elbo_dev_valid = false;
@@ -1257,6 +1277,7 @@ int tmvb_lda_iterate(tmvb_lda_t h, int viter, float vtol, int want_elbo, int64_t
     LdaDev p = dev_view(h);
     p.viter = viter;
     p.vtol = vtol;
+    take_mirror(h, &p);
     LdaPick pk;
     pk.tile[0] = (const void *)kLdaEstep[0][s.layout][want_elbo != 0];
     pk.tile[1] = (const void *)kLdaEstep[1][s.layout][want_elbo != 0];
@@ -1506,6 +1527,37 @@ int tmvb_lda_elbo(tmvb_lda_t h, int mode, int64_t M_total, double *elbo_docs, do
     return 0;
 }
 
+int tmvb_lda_arm_host_mirror(tmvb_lda_t h, float *Elogtheta, float *gamma)
+{
+    TMVB_CHECK_ARG(h != nullptr, "handle is NULL");
+    Shard &s = h->s;
+    TMVB_CUDA(cudaSetDevice(s.device));
+    h->mirror_armed = false;
+    if (!Elogtheta && !gamma) return 0;   // disarm
+    TMVB_CHECK_ARG(Elogtheta && gamma, "the host mirror needs both arrays");
+    TMVB_CHECK_ARG(s.corpus_set, "set_corpus has not been called");
+    long long covered = 0;
+    for (const Bucket &b : s.buckets) covered += b.doc_end - b.doc_begin;
+    TMVB_CHECK_ARG(covered == (long long)s.M, "internal: the E-step launches do not cover every document");
+    float *dev[2] = {nullptr, nullptr};
+    float *host[2] = {Elogtheta, gamma};
+    for (int a = 0; a < 2; a++) {
+        cudaPointerAttributes at;
+        memset(&at, 0, sizeof(at));
+        if (cudaPointerGetAttributes(&at, host[a]) != cudaSuccess || at.type != cudaMemoryTypeHost || !at.devicePointer) {
+            cudaGetLastError();
+            return fail(-1, "invalid argument: the host mirror arrays must be page-locked (cudaHostAlloc / cudaHostRegister) and mapped");
+        }
+        dev[a] = (float *)at.devicePointer;
+    }
+    h->mirror_E = dev[0];
+    h->mirror_gamma = dev[1];
+    h->mirror_E_host = Elogtheta;
+    h->mirror_gamma_host = gamma;
+    h->mirror_armed = true;
+    return 0;
+}
+
 int tmvb_lda_download(tmvb_lda_t h, float *alpha, float *beta, float *Elogtheta, float *gamma)
 {
     TMVB_CHECK_ARG(h != nullptr, "handle is NULL");
@@ -1521,8 +1573,11 @@ int tmvb_lda_download(tmvb_lda_t h, float *alpha, float *beta, float *Elogtheta,
     }
     TMVB_TRY(shard_download_rows(&s, s.d_beta[s.cur], beta, s.V, nullptr));
     if (s.M > 0 && (Elogtheta || gamma)) TMVB_CHECK_ARG(s.corpus_set, "set_corpus has not been called");
-    TMVB_TRY(shard_download_rows(&s, h->d_Elogtheta, Elogtheta, s.M, s.d_perm));
-    TMVB_TRY(shard_download_rows(&s, h->d_gamma, gamma, s.M, s.d_perm));
+    // rows the last E-step already wrote into these very arrays (host mirror) are complete once the stream is idle
+    const bool have_E = h->mirror_valid && Elogtheta == h->mirror_E_host, have_g = h->mirror_valid && gamma == h->mirror_gamma_host;
+    if (have_E || have_g) TMVB_CUDA(cudaStreamSynchronize(s.stream));
+    if (!have_E) TMVB_TRY(shard_download_rows(&s, h->d_Elogtheta, Elogtheta, s.M, s.d_perm));
+    if (!have_g) TMVB_TRY(shard_download_rows(&s, h->d_gamma, gamma, s.M, s.d_perm));
     return 0;
 }
 

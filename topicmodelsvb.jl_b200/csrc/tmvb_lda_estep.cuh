@@ -23,6 +23,10 @@ struct LdaDev {
     float vtol;
     int stage_bulk;  // 1: TMA bulk row copies (UBLKCP), 0: 16-byte cp.async (LDGSTS)
     int dbg;         // developer probes: bit0 skip the scatter, bit1 skip the final pass
+    // host mirror (tmvb_lda_arm_host_mirror): when set, the E-step also writes each document's final gamma / Elogtheta row into
+    // the caller's page-locked K x M arrays (row perm[d], K floats) -- update_host! overlapped with the sweeps of the other documents
+    float *host_E, *host_gamma;
+    const int *perm;  // sorted position -> the caller's document index
 };
 
 // shared memory of one E-step CTA beyond the tile: 256-byte header (mbarrier, next-document slot, per-warp partial sums) |
@@ -289,6 +293,7 @@ __global__ void __launch_bounds__(32 * W, W == 2 ? 8 : 1) lda_estep_kernel(const
         }
 
         float a = 0.0f;
+        const size_t hrow = p.host_E ? (size_t)__ldg(p.perm + d) * (size_t)K : 0;
 #pragma unroll
         for (int r = 0; r < R; r++) {
             const int i = TOPIC(r);
@@ -297,6 +302,10 @@ __global__ void __launch_bounds__(32 * W, W == 2 ? 8 : 1) lda_estep_kernel(const
                 p.gamma[(size_t)d * K_ld + i] = ok ? gam_k[r] : 0.0f;
                 p.Elogtheta[(size_t)d * K_ld + i] = ok ? Enew_k[r] : 0.0f;
                 p.Elogtheta_old[(size_t)d * K_ld + i] = ok ? Eold_k[r] : 0.0f;
+                if (p.host_E && ok) {
+                    __stcs(p.host_gamma + hrow + i, gam_k[r]);
+                    __stcs(p.host_E + hrow + i, Enew_k[r]);
+                }
                 if (ok) {
                     esum_k[r] += (double)Enew_k[r];
                     // lnG(gamma_i), and the Elogtheta_old part of the entropy of the last phi:
@@ -691,6 +700,22 @@ __global__ void __maxnreg__(lda_hyb_maxreg(NR)) lda_estep_hyb_kernel(const LdaDe
                 *reinterpret_cast<float2 *>(p.gamma + (size_t)d * K_ld + i0) = make_float2(ok0 ? gam0 : 0.0f, ok1 ? gam1 : 0.0f);
                 *reinterpret_cast<float2 *>(p.Elogtheta + (size_t)d * K_ld + i0) = make_float2(ok0 ? En0 : 0.0f, ok1 ? En1 : 0.0f);
                 *reinterpret_cast<float2 *>(p.Elogtheta_old + (size_t)d * K_ld + i0) = make_float2(ok0 ? Eo0 : 0.0f, ok1 ? Eo1 : 0.0f);
+            }
+            if (p.host_E) {   // uniform: the row goes over the bus while the other documents are swept
+                const size_t hrow = (size_t)__ldg(p.perm + d) * (size_t)K + i0;
+                if (ok1 && !(K & 1)) {   // rows of an even K start 8-byte aligned
+                    __stcs(reinterpret_cast<float2 *>(p.host_gamma + hrow), make_float2(gam0, gam1));
+                    __stcs(reinterpret_cast<float2 *>(p.host_E + hrow), make_float2(En0, En1));
+                } else {
+                    if (ok0) {
+                        __stcs(p.host_gamma + hrow, gam0);
+                        __stcs(p.host_E + hrow, En0);
+                    }
+                    if (ok1) {
+                        __stcs(p.host_gamma + hrow + 1, gam1);
+                        __stcs(p.host_E + hrow + 1, En1);
+                    }
+                }
             }
             float a = 0.0f;
             if (ok0) {

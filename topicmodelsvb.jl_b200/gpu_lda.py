@@ -139,13 +139,7 @@ class gpuLDA:
         # fresh arrays, as the reference's update_host! rebinds the fields (never write through to caller arrays)
         # page-locked staging arrays (D2H at PCIe speed), allocated once per model: the fields are live
         # views of these buffers and are overwritten by the next update_host! -- copy to keep a snapshot
-        if self._pinned is None:
-            pe = _lib.pinned_empty
-            self._pinned = dict(beta=pe((self.K, self.V), np.float32, order="F"), beta_old=pe((self.K, self.V), np.float32, order="F"),
-                                Elogtheta=pe((self.K, self.M), np.float32, order="F"),
-                                Elogtheta_old=pe((self.K, self.M), np.float32, order="F"),
-                                gamma=pe((self.K, self.M), np.float32, order="F"), topics=pe((self.K, self.V), np.int32))
-        pb = self._pinned
+        pb = self._staging()
         self.alpha = np.empty(self.K, np.float32)
         self.beta, self.Elogtheta, self.gamma = pb["beta"], pb["Elogtheta"], pb["gamma"]
         _lib.check(lib.tmvb_lda_download(h, _lib.ptr(self.alpha), self.beta.ctypes.data, self.Elogtheta.ctypes.data,
@@ -154,6 +148,27 @@ class gpuLDA:
         es = np.zeros(self.K)
         _lib.check(lib.tmvb_lda_get_elogtheta_sum(h, _lib.ptr(es)))
         self.Elogtheta_sum = es
+
+    def _staging(self):
+        if self._pinned is None:
+            pe = _lib.pinned_empty
+            self._pinned = dict(beta=pe((self.K, self.V), np.float32, order="F"), beta_old=pe((self.K, self.V), np.float32, order="F"),
+                                Elogtheta=pe((self.K, self.M), np.float32, order="F"),
+                                Elogtheta_old=pe((self.K, self.M), np.float32, order="F"),
+                                gamma=pe((self.K, self.M), np.float32, order="F"), topics=pe((self.K, self.V), np.int32))
+        return self._pinned
+
+    def arm_host_mirror(self):
+        """The Elogtheta / gamma half of update_host! (modelutils.jl:507-512) rides with the next E-step: its kernels write each
+        document's final rows into the page-locked arrays update_host! hands out, while the other documents are still swept.
+        Called by train! before the iteration that is certainly its last (k == iter); a run that stops earlier on `tol`
+        downloads as before.  One GPU only (TMVB_HOST_MIRROR=0 switches it off)."""
+        if os.environ.get("TMVB_HOST_MIRROR", "1") == "0" or not self.M or (self.reducer is not None and self.reducer.world > 1):
+            return
+        # (after an earlier train! call model.Elogtheta / model.gamma ARE these arrays: update_buffer!'s copy out of them is
+        # ordered before the E-step on the handle's stream, and update_host! rebinds the fields to them anyway)
+        pb = self._staging()
+        _lib.check(_lib.load().tmvb_lda_arm_host_mirror(self._handle(), pb["Elogtheta"].ctypes.data, pb["gamma"].ctypes.data))
 
     def _fetch_old(self):
         """beta_old (LDA.jl:122) / Elogtheta_old (LDA.jl:137) live on the device between update_host! calls; the reference's
@@ -346,6 +361,8 @@ def train(model: gpuLDA, iter: int = 150, tol: float = 1.0, niter: int = 1000, n
         model.reducer.barrier()    # every rank has uploaded before the first exchange (the device barriers only wait so long)
     for k in range(1, iter + 1):
         want = check and (k % checkelbo == 0)
+        if k == iter:
+            model.arm_host_mirror()                                # update_host! of gamma / Elogtheta inside this E-step
         if fused:
             # gpuLDA.jl:356-368 as one graph launch; check_elbo! (modelutils.jl:574-585) on the value it returns
             new_elbo = model.iterate(viter, vtol, niter, ntol, want_elbo=want)
