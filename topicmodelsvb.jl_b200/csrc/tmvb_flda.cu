@@ -304,6 +304,413 @@ __global__ void __launch_bounds__(32) flda_estep_kernel(const FldaDev p, int doc
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------------
+// The same inner loop with the per-token scalars in registers ("register-state" variant, LPT = 2: S = 16 token streams).
+// flda_estep_kernel keeps tau / tau_old / counts / (1 - eta) kappa of the staged tokens in shared memory and lets lane kl = 0 of a
+// token rewrite tau at the end of every round (a warp barrier and a divergent branch per round), and it sizes the tile for the
+// longest document of the launch (43-100 KB: 2-5 resident warps per SM at NSF).  Here the tile holds at most TR * S = 64 tokens
+// (longer documents read the remaining rows from L2 as before), and for those TR rounds each lane keeps c, tau, tau_old and kq of
+// its token in registers -- both lanes of a token compute the new tau redundantly, so the round has no shared-memory write, no
+// barrier and no branch, and two rounds are issued as ONE basic block (flda_token2): two independent dependency chains
+// (LDS -> FFMA2 -> MUFU.EX2 -> sums -> SHFL -> MUFU.RCP -> FFMA2) per warp at 8-12 resident warps per SM.
+template <int LPT, int CPL>
+__device__ __forceinline__ void flda_tile_row(const float *tile, int RS, int CH, int n, int kl, ulonglong2 (&b)[CPL])
+{
+    const ulonglong2 zero = make_ulonglong2(0ull, 0ull);
+    const ulonglong2 *row = reinterpret_cast<const ulonglong2 *>(tile + (size_t)n * RS) + kl;
+#pragma unroll
+    for (int m = 0; m < CPL; m++) b[m] = (kl + LPT * m < CH) ? row[LPT * m] : zero;
+}
+
+// tau_n = eta / (eta + (1 - eta) kappa prod_i beta_i^(-phi_i) + eps),  prod = 2^(-q / s)   (fLDA.jl:190-195)
+__device__ __forceinline__ float flda_new_tau(float eta, float kq, float q, float rs) { return fast_div_pos(eta, (eta + kq * ex2_ftz(-q * rs)) + TMVB_EPS); }
+
+template <int LPT, int CPL>
+__device__ __forceinline__ float flda_token1(const float *tile, int RS, int CH, int n, int kl, const f32x2 (&E01)[CPL], const f32x2 (&E23)[CPL], float c,
+                                             float tau, float kq, float eta, f32x2 (&g01)[CPL], f32x2 (&g23)[CPL])
+{
+    ulonglong2 b[CPL];
+    flda_tile_row<LPT, CPL>(tile, RS, CH, n, kl, b);
+    f32x2 p01[CPL], p23[CPL];
+    float s, q;
+    flda_row<CPL>(b, E01, E23, tau, p01, p23, s, q);
+    s = group_sum<LPT>(s);
+    q = group_sum<LPT>(q);
+    const float rs = rcp_ftz(s), t = c * rs;
+    const f32x2 t2 = pk2(t, t);
+#pragma unroll
+    for (int m = 0; m < CPL; m++) {
+        g01[m] = fma2(p01[m], t2, g01[m]);
+        g23[m] = fma2(p23[m], t2, g23[m]);
+    }
+    return flda_new_tau(eta, kq, q, rs);
+}
+
+template <int LPT, int CPL>
+__device__ __forceinline__ void flda_token2(const float *tile, int RS, int CH, int na, int nb, int kl, const f32x2 (&E01)[CPL], const f32x2 (&E23)[CPL],
+                                            float ca, float cb, float &taua, float &taub, float kqa, float kqb, float eta, f32x2 (&g01)[CPL],
+                                            f32x2 (&g23)[CPL])
+{
+    ulonglong2 ba[CPL], bb[CPL];
+    flda_tile_row<LPT, CPL>(tile, RS, CH, na, kl, ba);
+    flda_tile_row<LPT, CPL>(tile, RS, CH, nb, kl, bb);
+    f32x2 pa01[CPL], pa23[CPL], pb01[CPL], pb23[CPL];
+    float sa, qa, sb, qb;
+    flda_row<CPL>(ba, E01, E23, taua, pa01, pa23, sa, qa);
+    flda_row<CPL>(bb, E01, E23, taub, pb01, pb23, sb, qb);
+    sa = group_sum<LPT>(sa);
+    sb = group_sum<LPT>(sb);
+    qa = group_sum<LPT>(qa);
+    qb = group_sum<LPT>(qb);
+    const float rsa = rcp_ftz(sa), rsb = rcp_ftz(sb);
+    const float ta = ca * rsa, tb = cb * rsb;
+    const f32x2 ta2 = pk2(ta, ta), tb2 = pk2(tb, tb);
+#pragma unroll
+    for (int m = 0; m < CPL; m++) {   // the order of the two additions is the order of the rounds
+        g01[m] = fma2(pb01[m], tb2, fma2(pa01[m], ta2, g01[m]));
+        g23[m] = fma2(pb23[m], tb2, fma2(pa23[m], ta2, g23[m]));
+    }
+    taua = flda_new_tau(eta, kqa, qa, rsa);
+    taub = flda_new_tau(eta, kqb, qb, rsb);
+}
+
+template <int W>
+__device__ __forceinline__ void flda_cta_sync()
+{
+    if (W == 1)
+        __syncwarp();
+    else
+        __syncthreads();
+}
+
+// 64-byte header (mbarrier | next-document slot | per-warp partials) | gs [W][S][RS] | En_s [2][RS]
+static size_t flda_reg_fixed_smem(int RS, int lpt, int W) { return 64 + (size_t)W * (32 / lpt) * RS * 4 + 2 * (size_t)RS * 4; }
+constexpr float kPadRaw = -3.0e4f;   // Elogtheta of a pad topic: (kPadRaw - max) log2(e) flushes 2^x to zero
+
+// W warps share one document and its tile (W = 2 for the launches whose tile exceeds 64 tokens: twice the tile at the same
+// shared memory per resident warp, so that NSF's documents fit -- 3 % of the tokens lie beyond 128, 29 % beyond 64): warp w takes the
+// rounds w, w + W, ... and the 32-topic slices w, w + W, ... of the K phase.  Two CTA barriers per sweep (after the per-stream
+// partial sums are in shared memory; after the new Elogtheta, the partial norms and maxima are), three per document.
+template <int LPT, int CPL, int TR, int W, int MAXREG>
+__global__ void __maxnreg__(MAXREG) flda_estep_reg_kernel(const FldaDev p, int doc_begin, int doc_end, int cap, int cap2, int *counter)
+{
+    constexpr int S = 32 / LPT;
+    constexpr int R = (4 * LPT * CPL + 31) / 32;   // 32-topic slices of a K vector
+    constexpr int RW = (R + W - 1) / W;            // slices per warp: slice warp + W j
+    static_assert(W <= 4 && TR % 2 == 0, "header slots / pairing");
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, kl = lane % LPT, ts = lane / LPT;
+    const int K = p.K, K_ld = p.K_ld, CH = K_ld >> 2, RS = p.RS;
+    (void)cap2;
+    unsigned long long *mbar = reinterpret_cast<unsigned long long *>(smem_raw);
+    int *next_s = reinterpret_cast<int *>(smem_raw + 8);
+    float *dpart_s = reinterpret_cast<float *>(smem_raw + 16);   // [W]
+    float *mx_s = reinterpret_cast<float *>(smem_raw + 32);      // [W]
+    float *tc_s = reinterpret_cast<float *>(smem_raw + 48);      // [W]
+    float *gs = reinterpret_cast<float *>(smem_raw + 64);        // [W][S][RS]
+    float *En_s = gs + (size_t)W * S * RS;                       // [2][RS]: the Elogtheta sweep v reads is buffer v & 1
+    float *tile = En_s + 2 * RS;                                 // [cap][RS],  cap <= W * TR * S, a multiple of S
+    int *term_s = reinterpret_cast<int *>(tile + (size_t)cap * RS + cap);   // [cap]  (plan_buckets: rows | 4 bytes | 4 bytes per token | ...)
+    float *gs_w = gs + (size_t)warp * S * RS;
+
+    float alpha_k[RW], Eold_k[RW], Enew_k[RW], gam_k[RW];
+    double esum_k[RW];
+    float asum = 0.0f;
+    for (int i = lane; i < K; i += 32) asum += p.alpha[i];
+    asum = warp_sum(asum);
+#pragma unroll
+    for (int j = 0; j < RW; j++) {
+        const int i = lane + 32 * (warp + W * j);
+        alpha_k[j] = (i < K) ? p.alpha[i] : 0.0f;
+        esum_k[j] = 0.0;
+        Eold_k[j] = Enew_k[j] = gam_k[j] = 0.0f;
+        if (i < K_ld) En_s[i] = En_s[RS + i] = kPadRaw;
+    }
+    const float eta = __ldg(p.kq + p.V);
+    double tc_thr = 0.0;
+    unsigned long long sweeps_thr = 0;
+    unsigned phase = 0;
+    if (tid == 0) mbar_init(mbar, 1);
+    flda_cta_sync<W>();
+
+    const int chunk = max(1, min(8, (doc_end - doc_begin) / (4 * (int)gridDim.x)));
+    int d_next = 0, d_lim = 0;
+    for (;;) {
+        if (d_next >= d_lim) {
+            if (W == 1) {
+                if (lane == 0) d_next = doc_begin + atomicAdd(counter, chunk);
+                d_next = __shfl_sync(0xffffffffu, d_next, 0);
+            } else {
+                if (tid == 0) *next_s = doc_begin + atomicAdd(counter, chunk);
+                __syncthreads();
+                d_next = *next_s;
+            }
+            d_lim = min(d_next + chunk, doc_end);
+        }
+        if (d_next >= doc_end) break;
+        const int d = d_next++;
+        const long long o = p.doc_off[d];
+        const int Nd = (int)(p.doc_off[d + 1] - o);
+        const int ns = min(Nd, cap);
+        const int trounds = (ns + S - 1) / S;     // rounds served by the tile and the register state (<= W * TR)
+        const int rounds = (Nd + S - 1) / S;
+
+        // this lane's tokens of its warp's tile rounds: slot j is token (warp + W j) S + ts (an empty slot has c = 0 and reads row 0)
+        float c_r[TR], tau_r[TR], tauo_r[TR], kq_r[TR];
+        int term_r[TR];
+#pragma unroll
+        for (int j = 0; j < TR; j++) {
+            const int n = (warp + W * j) * S + ts;
+            const bool ok = n < ns;
+            term_r[j] = ok ? __ldg(p.terms + o + n) : 0;
+            c_r[j] = ok ? __ldg(p.counts + o + n) : 0.0f;
+            tau_r[j] = ok ? __ldcg(p.tau + o + n) : 0.5f;
+            tauo_r[j] = ok ? __ldcg(p.tau_old + o + n) : 0.5f;
+        }
+#pragma unroll
+        for (int j = 0; j < TR; j++) {
+            const int n = (warp + W * j) * S + ts;
+            kq_r[j] = (n < ns) ? __ldg(p.kq + term_r[j]) : 0.0f;
+            if (n < ns && kl == 0) term_s[n] = term_r[j];
+        }
+        float mx = -3.0e38f;
+#pragma unroll
+        for (int j = 0; j < RW; j++) {
+            const int i = lane + 32 * (warp + W * j);
+            Eold_k[j] = (i < K) ? p.Elogtheta[(size_t)d * K_ld + i] : 0.0f;
+            Enew_k[j] = Eold_k[j];
+            if (i < K) {
+                mx = fmaxf(mx, Eold_k[j]);
+                En_s[i] = Eold_k[j];
+            }
+        }
+        mx = warp_max(mx);
+        if (W > 1 && lane == 0) mx_s[warp] = mx;
+        fence_proxy_async_smem();   // the tile was read through the generic proxy; the bulk copies write it through the async proxy
+        if (tid == 0) mbar_arrive_expect_tx(mbar, (unsigned)(ns * K_ld * 4));
+        flda_cta_sync<W>();
+        for (int n = tid; n < ns; n += 32 * W) bulk_g2s(tile + n * RS, p.L + (size_t)term_s[n] * K_ld, (unsigned)(K_ld * 4), mbar);
+        if (W > 1) {
+            mx = mx_s[0];
+#pragma unroll
+            for (int w = 1; w < W; w++) mx = fmaxf(mx, mx_s[w]);
+        }
+        // sum(gamma_d) = sum(alpha) + C_d + K eps whatever phi is: psi(sum gamma) (fLDA.jl:177) is a per-document constant
+        const float gsum = (asum + __ldg(p.doc_c + d)) + (float)K * TMVB_EPS;
+        const float psi_sum = psi_lgamma<false>(gsum).psi;
+        mbar_wait(mbar, phase);
+        phase ^= 1u;
+
+        int v = 0;
+        for (;;) {
+            const float *En = En_s + (v & 1) * RS;
+            f32x2 E01[CPL], E23[CPL], g01[CPL], g23[CPL];
+#pragma unroll
+            for (int m = 0; m < CPL; m++) {
+                const bool in = (kl + LPT * m < CH);
+                const float4 E = in ? reinterpret_cast<const float4 *>(En)[kl + LPT * m] : make_float4(kPadRaw, kPadRaw, kPadRaw, kPadRaw);
+                E01[m] = pk2((E.x - mx) * kLog2e, (E.y - mx) * kLog2e);
+                E23[m] = pk2((E.z - mx) * kLog2e, (E.w - mx) * kLog2e);
+                g01[m] = g23[m] = 0ull;
+            }
+            // ---- token phase: update_phi!, update_tau!, and the phi * counts product of update_gamma!
+#pragma unroll
+            for (int j = 0; j < TR; j += 2) {
+                const int ra = warp + W * j, rb = ra + W;
+                const int na = ra * S + ts, nb = rb * S + ts;
+                if (rb < trounds) {
+                    float ta = tau_r[j], tb = tau_r[j + 1];
+                    tauo_r[j] = ta;
+                    tauo_r[j + 1] = tb;
+                    flda_token2<LPT, CPL>(tile, RS, CH, na < ns ? na : 0, nb < ns ? nb : 0, kl, E01, E23, c_r[j], c_r[j + 1], ta, tb, kq_r[j], kq_r[j + 1], eta,
+                                          g01, g23);
+                    tau_r[j] = ta;
+                    tau_r[j + 1] = tb;
+                } else if (ra < trounds) {
+                    tauo_r[j] = tau_r[j];
+                    tau_r[j] = flda_token1<LPT, CPL>(tile, RS, CH, na < ns ? na : 0, kl, E01, E23, c_r[j], tau_r[j], kq_r[j], eta, g01, g23);
+                }
+            }
+            for (int r = trounds; r < rounds; r++) {   // beyond the tile: rows from L2, tau in global memory (flda_estep_kernel's round)
+                if (r % W != warp) continue;
+                const int n = r * S + ts;
+                const bool ok = n < Nd;
+                const int nn = ok ? n : Nd - 1;
+                const int term = __ldg(p.terms + o + nn);
+                const float kq = __ldg(p.kq + term);
+                ulonglong2 b[CPL];
+                flda_load_row<LPT, CPL>(tile, p.L, RS, K_ld, CH, nn, 0, term, kl, b);
+                const float c = ok ? __ldg(p.counts + o + nn) : 0.0f;
+                const float tau = __ldcg(p.tau + o + nn);
+                f32x2 p01[CPL], p23[CPL];
+                float s, q;
+                flda_row<CPL>(b, E01, E23, tau, p01, p23, s, q);
+                s = group_sum<LPT>(s);
+                q = group_sum<LPT>(q);
+                const float rs = rcp_ftz(s);
+                const float t = c * rs;
+                const f32x2 t2 = pk2(t, t);
+#pragma unroll
+                for (int m = 0; m < CPL; m++) {
+                    g01[m] = fma2(p01[m], t2, g01[m]);
+                    g23[m] = fma2(p23[m], t2, g23[m]);
+                }
+                __syncwarp();   // every lane of the token (and the empty slots that alias the last token) has read tau
+                if (ok && kl == 0) {
+                    __stcg(p.tau_old + o + nn, tau);
+                    __stcg(p.tau + o + nn, flda_new_tau(eta, kq, q, rs));
+                }
+            }
+#pragma unroll
+            for (int m = 0; m < CPL; m++)
+                if (kl + LPT * m < CH) {
+                    float4 gv;
+                    unpk2(g01[m], gv.x, gv.y);
+                    unpk2(g23[m], gv.z, gv.w);
+                    reinterpret_cast<float4 *>(gs_w + (size_t)ts * RS)[kl + LPT * m] = gv;
+                }
+            flda_cta_sync<W>();
+            // ---- K phase: update_gamma! (fLDA.jl:182-185), update_Elogtheta! (fLDA.jl:175-178) for this warp's topic slices
+            float dpart = 0.0f, mxn = -3.0e38f;
+            v++;
+            float *Enn = En_s + (v & 1) * RS;   // last read two token phases ago
+#pragma unroll
+            for (int j = 0; j < RW; j++) {
+                const int i = lane + 32 * (warp + W * j);
+                if (i < K) {
+                    float gi = owner_sum<S>(gs, RS, i);
+#pragma unroll
+                    for (int w = 1; w < W; w++) gi += owner_sum<S>(gs + (size_t)w * S * RS, RS, i);
+                    gam_k[j] = (alpha_k[j] + gi) + TMVB_EPS;
+                    Eold_k[j] = Enew_k[j];
+                    Enew_k[j] = psi_lgamma<false, true>(gam_k[j]).psi - psi_sum;
+                    const float df = Enew_k[j] - Eold_k[j];
+                    dpart = fmaf(df, df, dpart);
+                    mxn = fmaxf(mxn, Enew_k[j]);
+                    Enn[i] = Enew_k[j];
+                }
+            }
+            dpart = warp_sum(dpart);
+            mxn = warp_max(mxn);
+            if (W > 1) {
+                if (lane == 0) {
+                    dpart_s[warp] = dpart;
+                    mx_s[warp] = mxn;
+                }
+                __syncthreads();
+                dpart = dpart_s[0];
+                mxn = mx_s[0];
+#pragma unroll
+                for (int w = 1; w < W; w++) {
+                    dpart += dpart_s[w];
+                    mxn = fmaxf(mxn, mx_s[w]);
+                }
+            } else {
+                __syncwarp();   // the owner sums have been read before gs is overwritten; the new Elogtheta is visible
+            }
+            // fLDA.jl:229: stop when ||Elogtheta - Elogtheta_old||_2 < vtol (or after viter sweeps); buffer (v - 1) & 1 and mx then
+            // still are what the last phi was computed from
+            if (v >= p.viter || sqrtf(dpart) < p.vtol) break;
+            mx = mxn;
+        }
+
+        // ---- update_beta!(model, d) (fLDA.jl:168-171), update_kappa!(model, d) (fLDA.jl:156-159): the last phi, rebuilt from the
+        // tau it was computed from (tau_old) and the Elogtheta of the last sweep; weights tau_n c_n and (1 - tau_n) c_n with the FINAL tau
+        float tc = 0.0f;
+        if (!(p.dbg & 2)) {
+            const float *En = En_s + ((v - 1) & 1) * RS;
+            f32x2 E01[CPL], E23[CPL];
+#pragma unroll
+            for (int m = 0; m < CPL; m++) {
+                const bool in = (kl + LPT * m < CH);
+                const float4 E = in ? reinterpret_cast<const float4 *>(En)[kl + LPT * m] : make_float4(kPadRaw, kPadRaw, kPadRaw, kPadRaw);
+                E01[m] = pk2((E.x - mx) * kLog2e, (E.y - mx) * kLog2e);
+                E23[m] = pk2((E.z - mx) * kLog2e, (E.w - mx) * kLog2e);
+            }
+            auto scatter = [&](const ulonglong2(&b)[CPL], bool ok, int term, float c, float tauo, float tauf) {
+                f32x2 p01[CPL], p23[CPL];
+                float s, q;
+                flda_row<CPL>(b, E01, E23, tauo, p01, p23, s, q);
+                s = group_sum<LPT>(s);
+                if (ok) {
+                    const float w = tauf * c * rcp_ftz(s);
+                    const f32x2 w2 = pk2(w, w);
+                    float *srow = p.stats + (size_t)term * K_ld + 4 * kl;
+                    if (!(p.dbg & 1)) {
+#pragma unroll
+                        for (int m = 0; m < CPL; m++)
+                            if (4 * (kl + LPT * m) < K) {
+                                float px, py, pz, pw;
+                                unpk2(mul2(p01[m], w2), px, py);
+                                unpk2(mul2(p23[m], w2), pz, pw);
+                                red_add_v4(srow + 4 * LPT * m, px, py, pz, pw);
+                            }
+                        if (kl == 0) red_add(p.kstats + term, (1.0f - tauf) * c);
+                    }
+                    if (kl == 0) tc = fmaf(tauf, c, tc);
+                }
+            };
+#pragma unroll
+            for (int j = 0; j < TR; j++) {
+                if (warp + W * j < trounds) {
+                    const int n = (warp + W * j) * S + ts;
+                    const bool ok = n < ns;
+                    ulonglong2 b[CPL];
+                    flda_tile_row<LPT, CPL>(tile, RS, CH, ok ? n : 0, kl, b);
+                    scatter(b, ok, term_r[j], c_r[j], tauo_r[j], tau_r[j]);
+                    if (ok && kl == 0) {
+                        p.tau[o + n] = tau_r[j];
+                        p.tau_old[o + n] = tauo_r[j];
+                    }
+                }
+            }
+            for (int r = trounds; r < rounds; r++) {
+                if (r % W != warp) continue;
+                const int n = r * S + ts;
+                const bool ok = n < Nd;
+                const int nn = ok ? n : Nd - 1;
+                const int term = __ldg(p.terms + o + nn);
+                ulonglong2 b[CPL];
+                flda_load_row<LPT, CPL>(tile, p.L, RS, K_ld, CH, nn, 0, term, kl, b);
+                scatter(b, ok, term, __ldg(p.counts + o + nn), __ldcg(p.tau_old + o + nn), __ldcg(p.tau + o + nn));
+            }
+        }
+        tc = warp_sum(tc);
+#pragma unroll
+        for (int j = 0; j < RW; j++) {
+            const int i = lane + 32 * (warp + W * j);
+            if (i < K_ld) {
+                const bool ok = i < K;
+                p.gamma[(size_t)d * K_ld + i] = ok ? gam_k[j] : 0.0f;
+                p.Elogtheta[(size_t)d * K_ld + i] = ok ? Enew_k[j] : 0.0f;
+                p.Elogtheta_old[(size_t)d * K_ld + i] = ok ? Eold_k[j] : 0.0f;
+                if (ok) esum_k[j] += (double)Enew_k[j];
+            }
+        }
+        if (W > 1 && lane == 0) tc_s[warp] = tc;
+        flda_cta_sync<W>();   // the tile, term_s, gs and En_s are free for the next document
+        if (tid == 0) {
+            if (W > 1) {
+                tc = tc_s[0];
+#pragma unroll
+                for (int w = 1; w < W; w++) tc += tc_s[w];
+            }
+            p.doc_tc[d] = tc;
+            tc_thr += (double)tc;
+            sweeps_thr += (unsigned long long)v;
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < RW; j++) {
+        const int i = lane + 32 * (warp + W * j);
+        if (i < K && esum_k[j] != 0.0) atomicAdd(p.small + i, esum_k[j]);
+    }
+    if (tid == 0) {
+        if (sweeps_thr) atomicAdd(p.small + K_ld, (double)sweeps_thr);
+        if (tc_thr != 0.0) atomicAdd(p.small + K_ld + 1, tc_thr);
+    }
+}
+
 // update_elbo! (fLDA.jl:62-117), literally: phi rebuilt from (tau_old, beta_old, Elogtheta_old) (fLDA.jl:108), every other
 // quantity current.  L_old / L_new are the log2 tables of beta_old / beta; per (token, topic) one FFMA2 + MUFU.EX2 for phi and
 // two FFMA2 for  phi (Elogtheta_i + tau ln(beta_i + eps) - ln phi_i),  ln phi_i = ln 2 (x_i - log2 s).
@@ -526,6 +933,35 @@ typedef void (*FldaElboFn)(const FldaDev, const float *, const float *, double, 
 #define TMVB_FLDA_FN(L, C) (FldaEstepFn)flda_estep_kernel<L, C>,
 #define TMVB_FLDA_ELBO_FN(L, C) (FldaElboFn)flda_elbo_kernel<L, C>,
 static const FldaEstepFn kFldaEstep[kNumLaneLayouts] = {TMVB_FOR_EACH_LAYOUT(TMVB_FLDA_FN)};
+// the register-state variant exists for the two-lanes-per-token layouts (K_ld <= 64: 16 token streams, 4 tile rounds per warp);
+// [0]: one warp per document (tiles up to 64 tokens), [1]: two warps per document (tiles up to 128 tokens)
+constexpr int kFldaRegTile = 64;   // tokens one warp keeps register state for
+template <int L, int C, int W>
+constexpr FldaEstepFn flda_reg_fn()
+{
+    if constexpr (L == 2)
+        return (FldaEstepFn)flda_estep_reg_kernel<L, C, kFldaRegTile / (32 / L), W, 200>;
+    else
+        return nullptr;
+}
+#define TMVB_FLDA_REG_FN(L, C) {flda_reg_fn<L, C, 1>(), flda_reg_fn<L, C, 2>()},
+static const FldaEstepFn kFldaEstepReg[kNumLaneLayouts][2] = {TMVB_FOR_EACH_LAYOUT(TMVB_FLDA_REG_FN)};
+
+struct FldaPick {
+    const void *tile, *reg[2];
+};
+const void *flda_pick(const Bucket &b, const void *ctx)
+{
+    const FldaPick *pk = static_cast<const FldaPick *>(ctx);
+    return b.hyb ? pk->reg[b.warps - 1] : pk->tile;
+}
+// TMVB_FLDA_REG (default 2): 0 = flda_estep_kernel everywhere (64-token tiles), 1 = register-state variant with one warp per document
+// (64-token tiles), 2 = ... and two warps per document on the launches with 80- to 128-token tiles
+int flda_reg_mode(const Shard &s)
+{
+    const int v = env_int("TMVB_FLDA_REG", 2);
+    return (v >= 1 && v <= 2 && kFldaEstepReg[s.layout][0]) ? v : 0;
+}
 static const FldaElboFn kFldaElbo[kNumLaneLayouts] = {TMVB_FOR_EACH_LAYOUT(TMVB_FLDA_ELBO_FN)};
 
 }  // namespace tmvb
@@ -543,6 +979,7 @@ struct tmvb_flda_s {
     float *d_Elogtheta = nullptr, *d_Elogtheta_old = nullptr, *d_gamma = nullptr;
     float *d_tau = nullptr, *d_tau_old = nullptr, *d_doc_tc = nullptr;
     size_t tau_cap = 0;
+    int reg_mode = 0;            // TMVB_FLDA_REG at create: 0 tile kernel, 1 / 2 register-state kernel with up to 1 / 2 warps per document
     double *d_small = nullptr;   // [K_ld] sum_d Elogtheta | sweeps | sum tau c | ELBO
     double *d_local = nullptr;   // [2 K_ld] rowsum | elbo_w (shard_normalize)
     int64_t n_small = 0;
@@ -658,6 +1095,13 @@ int tmvb_flda_create(tmvb_flda_t *out, int64_t K, int64_t M, int64_t V, int devi
         A((void **)&h->d_small, (h->n_small + 1) * 8);
         A((void **)&h->d_local, (2 * s.K_ld + 2) * 8);
         if (e == cudaSuccess) e = cudaFuncSetAttribute((const void *)kFldaEstep[s.layout], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s.smem_optin);
+        for (int v = 0; v < 2; v++)
+            if (e == cudaSuccess && kFldaEstepReg[s.layout][v])
+                e = cudaFuncSetAttribute((const void *)kFldaEstepReg[s.layout][v], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s.smem_optin);
+        // a tile of at most 64 tokens per warp (longer documents read their remaining rows from L2): NSF K=50 E-step 5.23 ms with tiles
+        // sized for the longest document of a launch (2-5 resident warps per SM), 4.47 / 4.18 / 3.93 / 3.91 / 4.30 ms at 16 / 32 / 48 / 64 / 96
+        h->reg_mode = flda_reg_mode(s);
+        s.tile_cap_max = kFldaRegTile * (h->reg_mode == 2 ? 2 : 1);
         if (e != cudaSuccess) rc = fail((int)e, "device allocation failed: %s", cudaGetErrorString(e));
     }
     if (rc != 0) {
@@ -681,7 +1125,16 @@ int tmvb_flda_set_corpus(tmvb_flda_t h, const int64_t *N_cumsum, const int64_t *
 {
     TMVB_CHECK_ARG(h != nullptr, "handle is NULL");
     Shard &s = h->s;
-    TMVB_TRY(shard_set_corpus(&s, N_cumsum, terms, counts, flda_fixed_smem(s.RS, s.lpt)));
+    const size_t fixed = h->reg_mode ? flda_reg_fixed_smem(s.RS, s.lpt, h->reg_mode) : flda_fixed_smem(s.RS, s.lpt);
+    TMVB_TRY(shard_set_corpus(&s, N_cumsum, terms, counts, fixed));
+    const size_t per_tok = (size_t)s.RS * 4 + 8 + s.per_tok_extra;
+    for (Bucket &b : s.buckets) {
+        // register-state kernel where the tile is a whole number of 16-token rounds its warps can keep state for
+        b.hyb = (h->reg_mode && b.cap % 16 == 0 && b.cap <= kFldaRegTile * h->reg_mode) ? 1 : 0;
+        b.warps = (b.hyb && b.cap > kFldaRegTile) ? 2 : 1;
+        b.smem = (b.hyb ? flda_reg_fixed_smem(s.RS, s.lpt, b.warps) : flda_fixed_smem(s.RS, s.lpt)) + (size_t)b.cap * per_tok;
+        b.grid = 0;
+    }
     const size_t need = (size_t)std::max<int64_t>(s.nnz, 1);
     if (need > h->tau_cap) {
         TMVB_CUDA(cudaSetDevice(s.device));
@@ -781,8 +1234,8 @@ int tmvb_flda_estep(tmvb_flda_t h, int viter, float vtol)
     p.vtol = vtol;
     TMVB_CUDA(cudaEventRecord(s.ev[0], s.stream));
     TMVB_CUDA(cudaMemsetAsync(h->d_small, 0, h->n_small * 8, s.stream));
-    const void *fns[1] = {(const void *)kFldaEstep[s.layout]};
-    TMVB_TRY(shard_launch(&s, pick_by_warps, fns, &p, sizeof(p)));
+    const FldaPick pk = {(const void *)kFldaEstep[s.layout], {(const void *)kFldaEstepReg[s.layout][0], (const void *)kFldaEstepReg[s.layout][1]}};
+    TMVB_TRY(shard_launch(&s, flda_pick, &pk, &p, sizeof(p)));
     TMVB_CUDA(cudaEventRecord(s.ev[1], s.stream));
     s.estep_timed = true;
     return 0;
