@@ -402,13 +402,13 @@ def measure(tm, torch, args, name, rank, local, world, reducer, work_stream, pea
         if tj:
             traffic, tsrc = tj.get("dram_bytes_per_estep"), tj.get("source")
     kernel_names = {"lda": "lda_estep_hyb_kernel / lda_estep_kernel", "ctm": "ctm_estep_kernel", "ctpf": "ctpf_estep_kernel",
-                    "flda": "flda_estep_kernel", "fctm": "fctm_estep_kernel"}
+                    "flda": "flda_estep_reg_kernel / flda_estep_kernel", "fctm": "fctm_estep_kernel"}
     # what ncu names as the limiter of each kernel (profiles/r2_*_ncu_full_summary.txt): none of these working sets is HBM-resident at its
     # configuration, so `frac` (algorithmic bytes against the HBM peak, the contract's roofline) is a lower bound on distance, not the limiter
     limiter = {"lda": "warp issue / fixed-latency FFMA2 chains at register-limited occupancy (8-12 warps per SM); DRAM traffic is 4 % of the algorithmic bytes (table and slab L2- / register-resident)",
                "ctm": "instruction issue in the per-document Newton iterations (register-resident Cholesky + triangular solves: ~60 % of the instructions)",
                "ctpf": "instruction issue / latency at 12 % occupancy (two token passes over two tiles per sweep, digamma per topic)",
-               "flda": "MUFU.EX2 (one exponential per token and topic and sweep) and issue at 7 % occupancy (one warp per document, shared-memory tile)",
+               "flda": "warp issue (44-56 %) and the XU pipe (40-47 %: one MUFU.EX2 per token, topic and sweep; its floor is 1.7 ms) at 168 registers / 12 resident warps per SM",
                "fctm": "instruction issue in the Newton iterations, as ctm, plus one exponential per token and topic"}[cfg["model"]]
     roofline = {"bound": "hbm", "limiter": limiter, "kernel": kernel_names[cfg["model"]] + " (all length-bucket launches of one E-step)", "achieved": achieved,
                 "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_source": tsrc, "peak_source": peak_src,
