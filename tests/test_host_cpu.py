@@ -265,3 +265,27 @@ def test_connect_model_peers_single_rank_is_a_no_op(tm):
     class _M:
         reducer, _h = None, None
     assert tm.dist.connect_model_peers(_M(), "ctm") is False
+
+
+def test_document_lengths_are_checked_by_identity_or_value(tm):
+    """check_model's "N must contain document lengths." (modelutils.jl:258): model.N is the corpus' cached read-only length vector,
+    so the check is an identity test; a rebound N is compared by value, and writing into the shared vector is refused."""
+    from topicmodelsvb_b200 import gpu_lda
+    c = tm.synth.gencorp_lda(M=30, V=60, K=3, seed=2)
+    corp = tm.Corpus.from_csr(c)
+    model = tm.gpuLDA(corp, 4)
+    assert model.N is model.corp.lengths() and model.N.dtype == np.int64
+    np.testing.assert_array_equal(model.N, np.diff(c.N_cumsum))
+    gpu_lda.check_model(model)
+    with pytest.raises(ValueError):
+        model.N[0] += 1                              # the vector is shared with the corpus: read-only
+    model.N = np.array(model.N)                      # an equal copy passes by value
+    gpu_lda.check_model(model)
+    model.N = model.N + 1
+    with pytest.raises(tm._lib.TopicModelError, match="N must contain document lengths"):
+        gpu_lda.check_model(model)
+    # a corpus of Document objects: one vector per flattening
+    docs = [tm.Document(terms=np.array([1, 2, 3]), counts=np.array([1, 1, 2])), tm.Document(terms=np.array([2]), counts=np.array([4]))]
+    m2 = tm.gpuLDA(tm.Corpus(docs, vocab=5), 2)
+    np.testing.assert_array_equal(m2.N, [3, 1])
+    gpu_lda.check_model(m2)

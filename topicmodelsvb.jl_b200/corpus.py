@@ -107,6 +107,18 @@ class Corpus:
     def __len__(self):
         return self._flat.M if self.docs is None else len(self.docs)
 
+    def lengths(self) -> np.ndarray:
+        """[length(doc) for doc in corp] (the N field of every model, e.g. LDA.jl:30) as ONE read-only Int64 array per flattening:
+        the models bind it as ``model.N``, so check_model's "N must contain document lengths" is an identity test unless the
+        caller rebinds N (0.25 ms of host time per train! call at NSF size otherwise)."""
+        f = self.flat()
+        cached = getattr(self, "_lengths", None)
+        if cached is None or cached[0] is not f:
+            n = np.diff(f.N_cumsum).astype(np.int64)
+            n.setflags(write=False)
+            self._lengths = cached = (f, n)
+        return cached[1]
+
     def size(self):
         return len(self), self.V, self.U
 

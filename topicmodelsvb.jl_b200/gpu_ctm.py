@@ -30,7 +30,7 @@ class gpuCTM:
         corp = corp.copy()      # the reference stores copy(corp): later edits of the caller's corpus do not reach the model
         flat = corp.flat()
         self.K, self.M, self.V = int(K), int(M), int(V)
-        self.N = np.diff(flat.N_cumsum).astype(np.int64)
+        self.N = corp.lengths()             # read-only; rebind (not mutate) to change it
         cs = np.concatenate([[0], np.cumsum(flat.counts)]).astype(np.int64)
         self.C = cs[flat.N_cumsum[1:]] - cs[flat.N_cumsum[:-1]]
         self.corp = corp

@@ -31,7 +31,7 @@ class gpufLDA:
         corp = corp.copy()
         flat = corp.flat()
         self.K, self.M, self.V = int(K), int(M), int(V)
-        self.N = np.diff(flat.N_cumsum).astype(np.int64)
+        self.N = corp.lengths()             # read-only; rebind (not mutate) to change it
         cs = np.concatenate([[0], np.cumsum(flat.counts)]).astype(np.int64)
         self.C = cs[flat.N_cumsum[1:]] - cs[flat.N_cumsum[:-1]]
         self.corp = corp
@@ -193,7 +193,8 @@ def check_model_flda(model: gpufLDA) -> None:
     f = model.corp.flat()
     if M != len(model.corp):
         raise E("M must equal the number of documents in the corpus.")
-    if not np.array_equal(model.N, np.diff(f.N_cumsum)):
+    L = model.corp.lengths()
+    if model.N is not L and not np.array_equal(model.N, L):
         raise E("N must contain document lengths.")
     if not (0 <= model.eta <= 1):
         raise E("eta must belong to the interval [0,1].")

@@ -49,7 +49,7 @@ class gpuLDA:
         corp = corp.copy()      # the reference stores copy(corp): later edits of the caller's corpus do not reach the model
         flat = corp.flat()
         self.K, self.M, self.V = int(K), int(M), int(V)
-        self.N = np.diff(flat.N_cumsum).astype(np.int64)
+        self.N = corp.lengths()             # read-only; rebind (not mutate) to change it
         cs = np.concatenate([[0], np.cumsum(flat.counts)]).astype(np.int64)
         self.C = cs[flat.N_cumsum[1:]] - cs[flat.N_cumsum[:-1]]
         self.corp = corp
@@ -287,7 +287,8 @@ def check_model(model: gpuLDA) -> None:
     f = model.corp.flat()
     if M != len(model.corp):
         raise E("M must equal the number of documents in the corpus.")
-    if not np.array_equal(model.N, np.diff(f.N_cumsum)):
+    L = model.corp.lengths()
+    if model.N is not L and not np.array_equal(model.N, L):
         raise E("N must contain document lengths.")
     a = np.asarray(model.alpha)
     if a.shape != (K,):
