@@ -308,11 +308,13 @@ __global__ void __launch_bounds__(32) flda_estep_kernel(const FldaDev p, int doc
 // The same inner loop with the per-token scalars in registers ("register-state" variant, LPT = 2: S = 16 token streams).
 // flda_estep_kernel keeps tau / tau_old / counts / (1 - eta) kappa of the staged tokens in shared memory and lets lane kl = 0 of a
 // token rewrite tau at the end of every round (a warp barrier and a divergent branch per round), and it sizes the tile for the
-// longest document of the launch (43-100 KB: 2-5 resident warps per SM at NSF).  Here the tile holds at most TR * S = 64 tokens
-// (longer documents read the remaining rows from L2 as before), and for those TR rounds each lane keeps c, tau, tau_old and kq of
-// its token in registers -- both lanes of a token compute the new tau redundantly, so the round has no shared-memory write, no
-// barrier and no branch, and two rounds are issued as ONE basic block (flda_token2): two independent dependency chains
-// (LDS -> FFMA2 -> MUFU.EX2 -> sums -> SHFL -> MUFU.RCP -> FFMA2) per warp at 8-12 resident warps per SM.
+// longest document of the launch (43-100 KB: 2-5 resident warps per SM at NSF).  Here the tile holds at most TR * S = 64 tokens per
+// warp (W = 1 or 2 warps per document, see the kernel; longer documents read the remaining rows from L2 as before), and for its TR
+// tile rounds each lane keeps c, tau, tau_old and kq of its token in registers -- both lanes of a token compute the new tau
+// redundantly, so the round has no shared-memory write, no barrier and no branch, and two rounds are issued as ONE basic block
+// (flda_token2): two independent dependency chains (LDS -> FFMA2 -> MUFU.EX2 -> sums -> SHFL -> MUFU.RCP -> FFMA2) per warp at 12
+// resident warps per SM.  Measured on B200 (NSF K=50): E-step 5.23 ms (flda_estep_kernel, full tiles) -> 3.91 (64-token tiles) ->
+// 3.55 ms (this kernel); DESIGN.md 4.9.
 template <int LPT, int CPL>
 __device__ __forceinline__ void flda_tile_row(const float *tile, int RS, int CH, int n, int kl, ulonglong2 (&b)[CPL])
 {
