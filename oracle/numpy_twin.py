@@ -534,6 +534,48 @@ class FLDATwin(LDATwin):
         self.elbo = elbo
         return elbo
 
+    def update_elbo_device_form(self):
+        """fLDA.jl:62-117 without a logarithm per (token, topic): the decomposition a fused device ELBO can evaluate from what the
+        E-step's scatter pass already holds (cf. LDATwin.update_elbo_device_form).  Valid after an E-step + M-step +
+        alpha / eta updates.  In base 2 as on the device: L = log2(beta_old + eps), x_ni = tau_old_n L_ni + (Elogtheta_old_i - mx) log2 e,
+        p = 2^x, s_n = sum_i p_ni, q_n = sum_i p_ni L_ni, phi = p / s, g_i = sum_n c_n phi_ni:
+          sum_n c_n H(phi_n) = sum_n c_n (ln s_n - ln 2 tau_old_n q_n / s_n) - sum_i (Elogtheta_old_i - mx) g_i
+          Elogpz             = g . Elogtheta
+          H(Dirichlet)       = sum_i lnG(gamma_i) - lnG(sum gamma) - sum_i (gamma_i - 1) Elogtheta_i          (K > 1)
+          Elogpw             = sum_iw S_iw ln(beta_iw + eps) + sum_w KS_w ln(kappa_w + eps),   S, KS = the statistics of the E-step
+          Elogptheta         = M (lnG(sum alpha) - sum lnG(alpha)) + (alpha - 1) . sum_d Elogtheta_d
+        Elogpc (saturating at ln eps for long documents) and the Bernoulli entropy of tau stay per document / per token."""
+        a, K = self.alpha, self.K
+        S, KS = np.zeros((self.V, K)), np.zeros(self.V)
+        docs = 0.0
+        ln2 = np.log(2.0)
+        for d in range(self.M):
+            terms, counts = self._doc(d)
+            sl = self._sl(d)
+            tau, tauo = self.tau[sl], self.tau_old[sl]
+            Eo, Et, gam = self.Elogtheta_old[d], self.Elogtheta[d], self.gamma[d]
+            mx = Eo.max()
+            L = np.log2(self.beta_old[terms] + EPSILON)
+            p = np.exp2(tauo[:, None] * L + ((Eo - mx) / ln2)[None, :])
+            sn = p.sum(axis=1)
+            qn = (p * L).sum(axis=1)
+            phi = p / sn[:, None]
+            g = counts @ phi
+            S[terms] += phi * (counts * tau)[:, None]
+            KS[terms] += (1 - tau) * counts
+            docs += np.dot(counts, np.log(sn) - ln2 * tauo * qn / sn) - np.dot(Eo - mx, g)            # sum_n c_n H(phi_n)
+            docs += np.dot(g, Et)                                                                     # Elogpz
+            if K > 1:
+                docs += gammaln(gam).sum() - gammaln(gam.sum()) - np.dot(gam - 1, Et)                  # H(Dirichlet(gamma_d))
+            tc = np.dot(tau, counts)
+            docs += np.log(self.eta**tc * (1 - self.eta) ** (self.C[d] - tc) + EPSILON)               # Elogpc
+            p0 = 1 - tau
+            with np.errstate(divide="ignore", invalid="ignore"):
+                docs += np.dot(counts, np.where((p0 == 0) | (p0 == 1), 0.0, -(p0 * np.log(p0) + tau * np.log(tau))))
+        glob = self.M * (_finite(gammaln(a.sum())) - _finite(gammaln(a).sum())) + np.dot(a - 1, self.Elogtheta.sum(axis=0))
+        glob += np.sum(S * np.log(self.beta + EPSILON)) + np.dot(KS, np.log(self.kappa + EPSILON))
+        return docs + glob
+
     # fLDA.jl:214-247
     def train(self, iter=150, tol=1.0, niter=1000, ntol=None, viter=10, vtol=None, checkelbo=1):
         ntol = 1.0 / self.K**2 if ntol is None else ntol

@@ -272,3 +272,19 @@ def test_fctm_c_oracle_equals_numpy_twin(orc):
         st4 = orc.FCTMState(K, c.M, c.V, len(c.terms), beta0, kappa)
         t4, _, _ = orc.fctm_train(st4, c.N_cumsum, c.terms, c.counts, iter=3, tol=0.0, nthreads=4)
         np.testing.assert_allclose(t4, t2, rtol=1e-11)
+
+
+@pytest.mark.parametrize("K,M,V,seed", [(5, 40, 150, 2), (1, 15, 60, 3), (8, 30, 120, 5)])
+def test_flda_elbo_device_form_equals_literal_form(K, M, V, seed):
+    """The logarithm-free form of the fLDA ELBO (FLDATwin.update_elbo_device_form: what a fused device ELBO would evaluate)
+    equals update_elbo! (fLDA.jl:62-117) after every outer iteration, in fp64 on the CPU."""
+    import topicmodelsvb_b200.synth as synth
+    from oracle.numpy_twin import FLDATwin
+
+    c = synth.gencorp_lda(M=M, V=V, K=max(K, 2), seed=seed)
+    kappa0 = np.random.default_rng(seed).dirichlet(np.ones(c.V))
+    tw = FLDATwin(c.N_cumsum, c.terms, c.counts, K, c.V, synth.init_beta(K, c.V, seed=7), kappa0)
+    for it in range(4):
+        tr = tw.train(iter=1, tol=-np.inf)
+        lit, dev = tr[1], tw.update_elbo_device_form()
+        assert abs(dev - lit) <= 1e-11 * abs(lit), (it, lit, dev)
