@@ -658,6 +658,45 @@ class FCTMTwin(CTMTwin):
         self.elbo = elbo
         return elbo
 
+    def update_elbo_device_form(self):
+        """fCTM.jl:67-130 without a logarithm per (token, topic) (cf. FLDATwin / CTMTwin.update_elbo_device_form).  In base 2 over
+        L = log2(beta_old + eps): x_ni = tau_old_n L_ni + (lambda_old_i - mx) log2 e, p = 2^x, s = sum_i p, q = sum_i p L, phi = p / s,
+        g_i = sum_n c_n phi_ni:
+          sum_n c_n H(phi_n) = sum_n c_n (ln s_n - ln 2 tau_old_n q_n / s_n) - sum_i (lambda_old_i - mx) g_i
+          Elogpz             = g . lambda - C_d (sum_i exp(lambda_i + v_i / 2 - ln zeta) + ln zeta - 1)
+          Elogpw             = sum_iw S_iw ln(beta_iw + eps) + sum_w KS_w ln(kappa_w + eps)        (the statistics of the E-step)
+        Elogpeta, the Gaussian entropy, Elogpc and the Bernoulli entropy of tau are K-vector / per-token algebra."""
+        K = self.K
+        _, logdet = np.linalg.slogdet(self.invsigma)
+        S, KS = np.zeros((self.V, K)), np.zeros(self.V)
+        docs = 0.0
+        ln2 = np.log(2.0)
+        for d in range(self.M):
+            terms, counts = self._doc(d)
+            sl = self._sl(d)
+            tau, tauo = self.tau[sl], self.tau_old[sl]
+            lo, lam, v = self.lam_old[d], self.lam[d], self.vsq[d]
+            mx = lo.max()
+            L = np.log2(self.beta_old[terms] + EPSILON)
+            p = np.exp2(tauo[:, None] * L + ((lo - mx) / ln2)[None, :])
+            sn = p.sum(axis=1)
+            qn = (p * L).sum(axis=1)
+            phi = p / sn[:, None]
+            g = counts @ phi
+            S[terms] += phi * (counts * tau)[:, None]
+            KS[terms] += (1 - tau) * counts
+            df = lam - self.mu
+            docs += 0.5 * (logdet - K * np.log(2 * np.pi) - np.dot(np.diag(self.invsigma), v) - df @ self.invsigma @ df)
+            docs += np.dot(g, lam) - self.C[d] * (np.exp(lam + 0.5 * v - self.logzeta[d]).sum() + self.logzeta[d] - 1)
+            docs += 0.5 * (K * (np.log(2 * np.pi) + 1) + np.log(v).sum())
+            docs += np.dot(counts, np.log(sn) - ln2 * tauo * qn / sn) - np.dot(lo - mx, g)
+            tc = np.dot(tau, counts)
+            docs += np.log(self.eta**tc * (1 - self.eta) ** (self.C[d] - tc) + EPSILON)
+            p0 = 1 - tau
+            with np.errstate(divide="ignore", invalid="ignore"):
+                docs += np.dot(counts, np.where((p0 == 0) | (p0 == 1), 0.0, -(p0 * np.log(p0) + tau * np.log(tau))))
+        return docs + np.sum(S * np.log(self.beta + EPSILON)) + np.dot(KS, np.log(self.kappa + EPSILON))
+
     def train(self, iter=150, tol=1.0, niter=1000, ntol=None, viter=10, vtol=None, checkelbo=1):  # fCTM.jl:249-290
         K = self.K
         ntol = 1.0 / K**2 if ntol is None else ntol

@@ -288,3 +288,18 @@ def test_flda_elbo_device_form_equals_literal_form(K, M, V, seed):
         tr = tw.train(iter=1, tol=-np.inf)
         lit, dev = tr[1], tw.update_elbo_device_form()
         assert abs(dev - lit) <= 1e-11 * abs(lit), (it, lit, dev)
+
+
+@pytest.mark.parametrize("K,M,V,seed", [(4, 30, 120, 2), (1, 12, 50, 3), (6, 25, 100, 7)])
+def test_fctm_elbo_device_form_equals_literal_form(K, M, V, seed):
+    """The same for fCTM (FCTMTwin.update_elbo_device_form vs update_elbo!, fCTM.jl:67-130)."""
+    import topicmodelsvb_b200.synth as synth
+    from oracle.numpy_twin import FCTMTwin
+
+    c = synth.gencorp_lda(M=M, V=V, K=max(K, 2), seed=seed)
+    kappa0 = np.random.default_rng(seed).dirichlet(np.ones(c.V))
+    tw = FCTMTwin(c.N_cumsum, c.terms, c.counts, K, c.V, synth.init_beta(K, c.V, seed=7), kappa0)
+    for it in range(3):
+        tr = tw.train(iter=1, tol=-np.inf)
+        lit, dev = tr[1], tw.update_elbo_device_form()
+        assert abs(dev - lit) <= 1e-11 * abs(lit), (it, lit, dev)
