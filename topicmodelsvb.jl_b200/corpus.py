@@ -195,13 +195,16 @@ def _read_keys(path: str, what: str) -> np.ndarray:
     """First column of a `key<TAB>name` file as the reference reads it (readdlm + Dict(zip(keys, names)), Corpus.jl:301-315):
     blank lines are skipped, a repeated key keeps one entry, keys must be positive integers (decimal, or with Julia's
     0x / 0o / 0b prefixes as parse(Int, .) accepts them)."""
-    keys = []
     with open(path, "r", encoding="utf-8", errors="replace") as f:
-        for line in f:
-            line = line.rstrip("\r\n")
-            if not line.strip():
-                continue
-            tok = line.split("\t", 1)[0].strip()
+        toks = [ln.split("\t", 1)[0].strip() for ln in f.read().splitlines() if ln.strip()]
+    try:
+        # the usual file: plain decimal keys, converted in one pass
+        if not all(t.isascii() and t.isdigit() for t in toks):
+            raise ValueError
+        keys = np.array(toks, dtype=np.int64) if toks else np.zeros(0, np.int64)
+    except (ValueError, OverflowError):
+        keys = []
+        for tok in toks:
             try:
                 keys.append(int(tok, 0) if tok[:2].lower() in ("0x", "0o", "0b") else int(tok))
             except ValueError:
@@ -224,8 +227,15 @@ def _key_count(keys, used0, max_used1, what, missing_msg) -> int:
     if keys is None:
         return max_used1
     n = int(keys.size)
-    if used0.size and not np.all(np.isin(np.unique(used0) + 1, keys, assume_unique=True)):
-        raise CorpusError("documents contain %s (see fixcorp! function)." % missing_msg)
+    if used0.size:
+        if n and int(keys[-1]) == n:
+            subset = max_used1 <= n      # keys ARE 1:n (sorted, distinct, positive) and the parser only lets positive keys through
+        else:
+            present = np.zeros(max(max_used1, int(keys[-1]) if n else 0) + 1, dtype=bool)
+            present[keys] = True
+            subset = bool(present[1:][used0].all())
+        if not subset:
+            raise CorpusError("documents contain %s (see fixcorp! function)." % missing_msg)
     if n != (int(keys[-1]) if n else 0):
         raise CorpusError("corpus %s keys must form unit range starting at 1 (see fixcorp! function)." % what)
     return n

@@ -10,8 +10,13 @@
 // check_doc (Corpus.jl:41-49); the first one that does not, or does not parse, raises the reference's
 //     CorpusError("document d beginning on line l failed to load.")
 // No device code in this file; it lives in libtmvb.so so that the binding stays a single library.
+#include <fcntl.h>
+#include <stdint.h>
 #include <stdlib.h>
 #include <string.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
 
 #include <algorithm>
 #include <atomic>
@@ -21,6 +26,39 @@
 #include "tmvb_common.cuh"
 
 namespace {
+
+// read-only mapping of a whole file (an empty file maps to an empty range)
+struct Mapping {
+    const char *data = nullptr;
+    size_t size = 0;
+    bool open(const char *path)
+    {
+        const int fd = ::open(path, O_RDONLY);
+        if (fd < 0) return false;
+        struct stat st;
+        if (fstat(fd, &st) != 0 || !S_ISREG(st.st_mode)) {
+            ::close(fd);
+            return false;
+        }
+        size = (size_t)st.st_size;
+        if (size > 0) {
+            void *m = mmap(nullptr, size, PROT_READ, MAP_PRIVATE, fd, 0);
+            if (m == MAP_FAILED) {
+                ::close(fd);
+                size = 0;
+                return false;
+            }
+            madvise(m, size, MADV_WILLNEED);
+            data = (const char *)m;
+        }
+        ::close(fd);
+        return true;
+    }
+    ~Mapping()
+    {
+        if (data) munmap((void *)data, size);
+    }
+};
 
 struct Line {
     const char *b, *e;  // [b, e) without the line terminator
@@ -34,30 +72,47 @@ inline int64_t count_fields(const Line &l, char delim)
     return n;
 }
 
-// parse(Int, field) for every field of the line into out[0..n); false on anything Julia would throw on (or > Int32)
+// parse(Int, field) for every field of the line into out[0..n); false on anything Julia would throw on (or > Int32).
+// Fast path per field: a bare run of 1-10 digits followed by the delimiter (or the end of the line for the last field); anything
+// else -- surrounding blanks, a sign, garbage -- takes the general scan from the start of the field.
 inline bool parse_line(const Line &l, char delim, int32_t *out, int64_t n, int64_t sub, bool positive)
 {
     const char *p = l.b;
+    const char *const e = l.e;
     auto blank = [delim](char ch) { return (ch == ' ' || ch == '\t') && ch != delim; };
     for (int64_t k = 0; k < n; k++) {
-        while (p < l.e && blank(*p)) p++;
+        const bool last = (k + 1 == n);
+        {
+            const char *q = p;
+            uint64_t v = 0;
+            while (q < e && (unsigned)(*q - '0') <= 9u) v = v * 10 + (unsigned)(*q++ - '0');
+            const int64_t nd = q - p;
+            if (nd >= 1 && nd <= 10 && (last ? q == e : (q < e && *q == delim))) {
+                if (v > 2147483647ull) return false;
+                if (positive && v == 0) return false;  // check_doc: all terms / counts / readers / ratings must be positive
+                out[k] = (int32_t)((int64_t)v - sub);
+                p = last ? q : q + 1;
+                continue;
+            }
+        }
+        while (p < e && blank(*p)) p++;
         bool neg = false;
-        if (p < l.e && (*p == '+' || *p == '-')) neg = (*p++ == '-');
-        if (p >= l.e || *p < '0' || *p > '9') return false;
+        if (p < e && (*p == '+' || *p == '-')) neg = (*p++ == '-');
+        if (p >= e || *p < '0' || *p > '9') return false;
         int64_t v = 0;
-        while (p < l.e && *p >= '0' && *p <= '9') {
+        while (p < e && *p >= '0' && *p <= '9') {
             v = v * 10 + (*p++ - '0');
             if (v > 2147483647ll) return false;
         }
-        while (p < l.e && blank(*p)) p++;
-        if (k + 1 < n) {
-            if (p >= l.e || *p != delim) return false;
+        while (p < e && blank(*p)) p++;
+        if (!last) {
+            if (p >= e || *p != delim) return false;
             p++;
-        } else if (p != l.e) {
+        } else if (p != e) {
             return false;
         }
         if (neg) v = -v;
-        if (positive && v <= 0) return false;  // check_doc: all terms / counts / readers / ratings must be positive
+        if (positive && v <= 0) return false;
         out[k] = (int32_t)(v - sub);
     }
     return true;
@@ -87,32 +142,47 @@ int tmvb_read_docfile(const char *path, char delim, int counts, int readers, int
     memset(out, 0, sizeof(*out));
     if (ratings && !readers) ratings = 0;  // "ratings require readers, ratings switch set to false." (Corpus.jl:278)
 
-    FILE *f = fopen(path, "rb");
-    if (!f) return fail(-1, "invalid argument: cannot open docfile %s", path);
-    fseek(f, 0, SEEK_END);
-    const long fsz = ftell(f);
-    fseek(f, 0, SEEK_SET);
-    std::vector<char> buf((size_t)std::max<long>(fsz, 0) + 1);
-    const size_t got = fsz > 0 ? fread(buf.data(), 1, (size_t)fsz, f) : 0;
-    fclose(f);
-    if ((long)got != fsz) return fail(-1, "invalid argument: short read on docfile %s", path);
+    // the file is mapped, not copied (79 MB at NSF: a read() into a zero-initialised buffer cost more than the parse on 8 threads)
+    Mapping map;
+    if (!map.open(path)) return fail(-1, "invalid argument: cannot open docfile %s", path);
+    const char *base = map.data;
+    const size_t got = map.size;
+    if (nthreads <= 0) nthreads = (int)std::max(1u, std::thread::hardware_concurrency());
 
-    // readlines(): split at '\n', drop one trailing '\r'; no empty last line after a final newline
+    // readlines(): split at '\n', drop one trailing '\r'; no empty last line after a final newline.  The newline positions are
+    // collected by all threads (one slice of the file each), then turned into lines in order.
     std::vector<Line> lines;
     {
-        const char *p = buf.data(), *end = buf.data() + got;
-        while (p < end) {
-            const char *nl = (const char *)memchr(p, '\n', (size_t)(end - p));
-            const char *e = nl ? nl : end;
-            Line l{p, (e > p && e[-1] == '\r') ? e - 1 : e};
-            lines.push_back(l);
-            p = nl ? nl + 1 : end;
-        }
+        const int T = (int)std::max<size_t>(1, std::min<size_t>((size_t)nthreads, got / (1u << 20)));
+        std::vector<std::vector<const char *>> nls((size_t)T);
+        std::vector<std::thread> th;
+        for (int t = 0; t < T; t++)
+            th.emplace_back([&, t] {
+                const char *p = base + got * (size_t)t / (size_t)T, *end = base + got * (size_t)(t + 1) / (size_t)T;
+                std::vector<const char *> &v = nls[(size_t)t];
+                v.reserve((size_t)(end - p) / 128 + 16);
+                while (p < end) {
+                    const char *nl = (const char *)memchr(p, '\n', (size_t)(end - p));
+                    if (!nl) break;
+                    v.push_back(nl);
+                    p = nl + 1;
+                }
+            });
+        for (auto &x : th) x.join();
+        size_t total = 0;
+        for (auto &v : nls) total += v.size();
+        lines.reserve(total + 1);
+        const char *p = base, *end = base + got;
+        for (auto &v : nls)
+            for (const char *nl : v) {
+                lines.push_back(Line{p, (nl > p && nl[-1] == '\r') ? nl - 1 : nl});
+                p = nl + 1;
+            }
+        if (p < end) lines.push_back(Line{p, (end[-1] == '\r') ? end - 1 : end});
     }
     const int L = 1 + (counts != 0) + (readers != 0) + (ratings != 0);
     const int64_t nl = (int64_t)lines.size(), M = (nl + L - 1) / L;
     const int li_counts = counts ? 1 : -1, li_readers = readers ? 1 + (counts != 0) : -1, li_ratings = ratings ? li_readers + 1 : -1;
-    if (nthreads <= 0) nthreads = (int)std::max(1u, std::thread::hardware_concurrency());
     nthreads = (int)std::min<int64_t>(nthreads, std::max<int64_t>(1, M / 256));
 
     out->M = M;
@@ -164,12 +234,12 @@ int tmvb_read_docfile(const char *path, char delim, int counts, int readers, int
             const int64_t o = out->N_cumsum[d], n = out->N_cumsum[d + 1] - o, ro = out->R_cumsum[d], rn = out->R_cumsum[d + 1] - ro;
             bool ok = parse_line(*line_of(d, 0), delim, out->terms + o, n, 1, true);
             if (const Line *c = line_of(d, li_counts))
-                ok = ok && count_fields(*c, delim) == n && parse_line(*c, delim, out->counts + o, n, 0, true);
+                ok = ok && parse_line(*c, delim, out->counts + o, n, 0, true);   // exactly n fields, or it fails
             else
                 std::fill(out->counts + o, out->counts + o + n, 1);
             if (const Line *r = line_of(d, li_readers)) ok = ok && parse_line(*r, delim, out->readers + ro, rn, 1, true);
             if (const Line *g = line_of(d, li_ratings))
-                ok = ok && count_fields(*g, delim) == rn && parse_line(*g, delim, out->ratings + ro, rn, 0, true);
+                ok = ok && parse_line(*g, delim, out->ratings + ro, rn, 0, true);
             else
                 std::fill(out->ratings + ro, out->ratings + ro + rn, 1);
             if (!ok) {
