@@ -131,3 +131,73 @@ def test_real_nsf_and_citeulike_files(tm):
     u = tm.readcorp(docfile=root + "/citeu/citeudocs.txt", vocabfile=root + "/citeu/citeuvocab.txt", userfile=root + "/citeu/citeuusers.txt",
                     counts=True, readers=True)
     assert u.size() == (16980, 8000, 5551) and u.flat().nnz == 1130920 and int(u.flat().R_cumsum[-1]) == 204986
+
+
+def test_mapped_file_edges(tm, tmp_path):
+    """The parser reads the file through a mapping: a file whose size is an exact multiple of the page size and that does not end in a
+    newline must not be read past its end; an empty file is an empty corpus; a file of several MB is indexed by several threads and
+    must give the same corpus as one thread."""
+    import mmap
+    p = str(tmp_path / "d.txt")
+    page = mmap.PAGESIZE
+    line = "1,2,3,4,5,6,7\n"
+    body = line * (2 * page // len(line))
+    pad = 2 * page - len(body)                     # fill up to exactly two pages with one last line without a newline
+    if pad == 0:
+        body, pad = body[:-len(line)], len(line)
+    body += "1" * pad if pad <= 9 else "1," + "1" * (pad - 2)
+    assert len(body) == 2 * page and not body.endswith("\n")
+    open(p, "w").write(body)
+    f = tm.readcorp(docfile=p).flat()
+    assert f.M == body.count("\n") + 1 and f.nnz == body.count(",") + f.M
+    open(p, "w").write("")
+    assert tm.readcorp(docfile=p).flat().M == 0
+    rng = np.random.default_rng(0)
+    rows = ["%s\n%s\n" % (",".join(map(str, rng.integers(1, 50000, size=n))), ",".join(map(str, rng.integers(1, 9, size=n))))
+            for n in rng.integers(1, 120, size=12000)]
+    open(p, "w").write("".join(rows))
+    assert os.path.getsize(p) > 4 << 20
+    a, b = tm.readcorp(docfile=p, counts=True, nthreads=1).flat(), tm.readcorp(docfile=p, counts=True, nthreads=7).flat()
+    for x, y in zip((a.N_cumsum, a.terms, a.counts), (b.N_cumsum, b.terms, b.counts)):
+        np.testing.assert_array_equal(x, y)
+    assert a.M == 12000
+
+
+@pytest.mark.parametrize("body,kw,ok", [
+    ("1,2\n1,1,1\n", dict(counts=True), False),          # more counts than terms
+    ("1,2\n 1 ,\t+2\n", dict(counts=True), True),        # blanks and a sign: the general scan
+    ("1,2\n1,-2\n", dict(counts=True), False),           # check_doc: counts must be positive
+    ("2147483647\n", dict(), True),                      # the largest key the packed CSR holds
+    ("2147483648\n", dict(), False),
+    ("00000000001,2\n", dict(), True),                   # 11 digits: not the fast path, still 1
+    ("1,,2\n", dict(), False),
+    ("1,2,\n", dict(), False),
+])
+def test_field_parser_paths(tm, tmp_path, body, kw, ok):
+    p = str(tmp_path / "d.txt")
+    open(p, "w").write(body)
+    if ok:
+        f = tm.readcorp(docfile=p, **kw).flat()
+        assert f.M == 1 and f.terms[0] + 1 == int(body.split("\n")[0].split(",")[0])
+        if kw:
+            np.testing.assert_array_equal(f.counts, [1, 2])
+    else:
+        with pytest.raises(tm.CorpusError, match=r"document 1 beginning on line 1 failed to load\."):
+            tm.readcorp(docfile=p, **kw)
+
+
+def test_key_files_that_are_not_the_unit_range(tm, tmp_path):
+    """check_corp's order (Corpus.jl:111-122): a used key outside the key set is reported before the unit-range violation."""
+    p, v = str(tmp_path / "d.txt"), str(tmp_path / "v.txt")
+    open(p, "w").write("1,3\n")
+    open(v, "w").write("1\ta\n3\tc\n7\tg\n")                      # contains every used key, but is not 1:3
+    with pytest.raises(tm.CorpusError, match="must form unit range"):
+        tm.readcorp(docfile=p, vocabfile=v)
+    open(p, "w").write("1,2\n")
+    with pytest.raises(tm.CorpusError, match="term keys not found"):
+        tm.readcorp(docfile=p, vocabfile=v)
+    open(v, "w").write("0x1\ta\n2.0\tb\n\n3\tc\n3\tc again\n")    # prefixes, an integral float, a blank line, a repeated key
+    assert tm.readcorp(docfile=p, vocabfile=v).V == 3
+    open(v, "w").write("1\ta\nx\tb\n")
+    with pytest.raises(tm.CorpusError, match="vocab keys must be positive integers"):
+        tm.readcorp(docfile=p, vocabfile=v)
